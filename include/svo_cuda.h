@@ -1,0 +1,222 @@
+/* svo_cuda.h — C-ABI of the B200 (sm_100a) tracking hot path of stereo-svo-slam.
+ *
+ * The reference (eichenberger/stereo-svo-slam) has no FFI seam of its own: its seam is the C++ class
+ * StereoSlam (src/include/stereo_slam.hpp:27-79).  This header is the boundary a maintainer binds
+ * instead of the reference's CPU stages; every entry point cites the reference code it replaces.
+ * Two layers are exported from one shared library (libstereosvo_b200.so):
+ *
+ *   svo_*        device layer: context, device-resident image sets ("slots"), one entry point per
+ *                hot-path stage, and the fused per-frame tracking call.
+ *   svo_slam_*   host facade with the semantics of StereoSlam (new_image / get_frame / keyframes /
+ *                trajectory / update_pose); written in C++ on top of svo_* only.
+ *
+ * Conventions: plain pointers and sizes, caller-owned host buffers, no exceptions; every function
+ * returns an int status (SVO_OK == 0).  Images are 8-bit single channel with an explicit row stride
+ * (cv::Mat::step — inputs may be ROIs, src/app/video_input.cpp:35-36).  One context per sequence; calls on one
+ * context must be serialised by the caller (the reference is not re-entrant either);
+ * any number of contexts may live in one process.  There is NO CPU fallback: without a CUDA device
+ * every call fails with SVO_ERR_NO_DEVICE.
+ */
+#ifndef SVO_CUDA_H
+#define SVO_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVO_OK 0
+#define SVO_ERR_INVALID 1   /* bad argument */
+#define SVO_ERR_CUDA 2      /* CUDA runtime error, see svo_last_error */
+#define SVO_ERR_NO_DEVICE 3 /* no CUDA device / extension built without one */
+#define SVO_ERR_CAPACITY 4  /* more keypoints / keyframes than the context was created for */
+#define SVO_ERR_STATE 5     /* call order violated (e.g. tracking before the first frame) */
+
+/* Field-for-field the reference's CameraSettings (src/include/stereo_slam_types.hpp:16-36). */
+typedef struct svo_camera_settings {
+    float baseline, fx, fy, cx, cy, k1, k2, k3, p1, p2;
+    int grid_height, grid_width, search_x, search_y;
+    int window_size_pose_estimator, window_size_opt_flow, window_size_depth_calculator;
+    int max_pyramid_levels, min_pyramid_level_pose_estimation;
+} svo_camera_settings;
+
+typedef struct svo_ctx svo_ctx;
+
+/* keypoint flag bits == KeyPointInformation::{ignore_during_refinement, ignore_completely, ignore_temporary}
+ * (src/include/stereo_slam_types.hpp:94-98) */
+#define SVO_FLAG_IGNORE_REFINEMENT 1
+#define SVO_FLAG_IGNORE_COMPLETELY 2
+#define SVO_FLAG_IGNORE_TEMPORARY 4
+/* KeyPointType (stereo_slam_types.hpp:52-55) */
+#define SVO_KP_FAST 0
+#define SVO_KP_EDGELET 1
+
+/* ------------------------------------------------------------------ context ------------------- */
+/* Replaces StereoSlam::StereoSlam's per-instance state (stereo_slam.cpp:29-41) on the device side. */
+int svo_ctx_create(const svo_camera_settings *settings, int device, int width, int height, int max_keypoints,
+                   svo_ctx **out);
+int svo_ctx_destroy(svo_ctx *ctx);
+const char *svo_last_error(svo_ctx *ctx); /* ctx may be NULL: last error of a failed svo_ctx_create */
+int svo_device_count(void);
+
+/* ------------------------------------------------------------------ image sets ---------------- */
+/* Upload one stereo pair and build, on the device, everything new_image builds per frame
+ * (stereo_slam.cpp:135-139): the halfSample pyramid of `left` (max_pyramid_levels levels, :93-121),
+ * level 0 of `right`, and the 3-level LK pyramid of `left` (cv::buildOpticalFlowPyramid(left, win, 2):
+ * Gaussian pyrDown, REFLECT_101 border; Scharr derivatives are fused into svo_klt, not stored).
+ * Returns a slot id; slots are reference counted (a keyframe shares its frame's images,
+ * keyframe_manager.cpp:27-29). */
+int svo_upload_stereo(svo_ctx *ctx, const uint8_t *left, size_t left_stride, const uint8_t *right, size_t right_stride,
+                      int *slot_out);
+int svo_slot_retain(svo_ctx *ctx, int slot);
+int svo_slot_release(svo_ctx *ctx, int slot);
+/* kind: 0 = left halfSample pyramid level, 1 = right level 0, 2 = LK pyramid level (unpadded view) */
+int svo_slot_level_size(svo_ctx *ctx, int kind, int level, int *width, int *height);
+int svo_download_level(svo_ctx *ctx, int slot, int kind, int level, uint8_t *out, size_t out_stride);
+
+/* ------------------------------------------------------------------ stages -------------------- */
+/* CornerDetector::detect_keypoints (corner_detector.cpp:13-79) on left pyramid level `level` with the
+ * given grid: FAST-9/16 (threshold 6, NMS) best response per cell, else Sobel-x edgelet arg-max;
+ * exactly one keypoint per cell, row-major cell order.  xy: n*2 (level coordinates), score: n, type: n. */
+int svo_detect_keypoints(svo_ctx *ctx, int slot, int level, int grid_width, int grid_height, int max_out, float *xy,
+                         float *score, int *type, int *n_out);
+/* test/diagnostic: the raw FAST list (x, y, score) in raster order == cv::FastFeatureDetector(6) */
+int svo_fast_corners(svo_ctx *ctx, int slot, int level, int max_out, int *xys, int *n_out);
+
+/* Stereo SSD match: DepthCalculator::calculate_depth's template match (depth_calculator.cpp:200-239,
+ * mode 0) and DepthFilter::calculate_disparities (depth_filter.cpp:259-327, mode 1: clamps to >= 0.5 and
+ * returns -1 for windows outside the image).  Exact integer SSD (the specification behind
+ * cv::matchTemplate(TM_SQDIFF)), first minimum in raster order, tie rule of :226-237. */
+int svo_stereo_match(svo_ctx *ctx, int slot, const float *kps2d, int n, int mode, float *disparity);
+
+/* PoseEstimator::estimate_pose (pose_estimator.cpp:115-130): coarse-to-fine sparse image alignment of the
+ * previous frame's keypoints into the current frame, Gauss-Newton with step halving solved in-kernel.
+ * flags may be NULL (all keypoints used); keypoints with SVO_FLAG_IGNORE_TEMPORARY are skipped
+ * (pose_estimator.cpp:238-245).  evals16: per level l, [2l] = cost evaluations, [2l+1] = gradient calls. */
+int svo_align(svo_ctx *ctx, int prev_slot, int cur_slot, const float *kps2d, const float *kps3d, const uint8_t *flags,
+              int n, const float pose_in[6], float pose_out[6], float *cost, int *evals16);
+/* one cost evaluation + one gradient at `pose` on pyramid level `level` (PoseEstimatorCallback::do_calc /
+ * get_gradient, pose_estimator.cpp:275-300, :418-539) — parity probe */
+int svo_align_probe(svo_ctx *ctx, int prev_slot, int cur_slot, const float *kps2d, const float *kps3d, int n, int level,
+                    const float pose[6], float *cost, float grad[6]);
+
+/* OpticalFlow::calculate_optical_flow -> cv::calcOpticalFlowPyrLK (optical_flow.cpp:14-56): win x win,
+ * 3 levels, 30 iterations / eps 0.01, OPTFLOW_USE_INITIAL_FLOW, minEig 1e-4.  prev points live in the
+ * keyframe whose id is keyframe_ids[i] (registered with svo_keyframe_commit); status 0 => err = +inf. */
+int svo_klt(svo_ctx *ctx, const int *keyframe_ids, int cur_slot, const float *prev_pts, const float *init_pts, int n,
+            float *next_pts, uint8_t *status, float *err);
+/* same, between two explicit slots (parity tests) */
+int svo_klt_slots(svo_ctx *ctx, int prev_slot, int cur_slot, const float *prev_pts, const float *init_pts, int n,
+                  float *next_pts, uint8_t *status, float *err);
+
+/* PoseRefiner::update_pose (pose_refinement.cpp:236-290, :321-412): Gauss-Newton on the reprojection
+ * error. evals2 = {cost evaluations, gradient calls}. */
+int svo_reproj_refine(svo_ctx *ctx, const float *kps2d, const float *kps3d, const uint8_t *flags, int n,
+                      const float pose_in[6], float pose_out[6], float *cost, int *evals2);
+
+/* project_keypoints (transform_keypoints.cpp:11-47) */
+int svo_project(svo_ctx *ctx, const float pose[6], const float *kps3d, int n, float *kps2d);
+
+/* Register the image set `slot` as keyframe (KeyFrameManager::create_keyframe, keyframe_manager.cpp:15-32):
+ * the device keeps its LK pyramid and pose resident for svo_klt / the depth filter. */
+int svo_keyframe_commit(svo_ctx *ctx, int slot, const float pose[6], int *keyframe_id_out);
+
+/* ------------------------------------------------------------------ fused per-frame tracking --- */
+/* Everything StereoSlam::new_image does on a tracking frame between the pyramid build and the keyframe
+ * decision (stereo_slam.cpp:196-229), enqueued as one stream-ordered sequence with a single host
+ * synchronisation at the end:
+ *   sparse alignment (estimate_pose :58-90) -> projection -> KLT against the origin keyframes + gating
+ *   (pose_refinement.cpp:62-150) -> reprojection Gauss-Newton (:236-290) -> depth filter: stereo SSD
+ *   disparities, outlier vote, triangulation + per-point Kalman update (depth_filter.cpp:40-327) ->
+ *   flag post-processing (:205-226) -> re-projection of the updated points (:228-229).
+ * All arrays are host memory of length n (x2 / x3 where noted); in/out arrays are updated in place. */
+typedef struct svo_track_io {
+    int n;
+    const float *prev_kps2d;  /* n*2 in : previous frame's keypoints (alignment reference patches) */
+    float *kps3d;             /* n*3 in/out : world points; out = depth-filter-updated */
+    const float *ref_kps2d;   /* n*2 in : keypoint position in its origin keyframe */
+    const int *keyframe_id;   /* n   in : origin keyframe id */
+    uint8_t *flags;           /* n   in/out : SVO_FLAG_* */
+    int *inlier_count;        /* n   in/out */
+    int *outlier_count;       /* n   in/out */
+    float *kf_state;          /* n*2 in/out : (inverse depth, variance) of the per-point Kalman filter */
+    float pose_prior[6];      /* in  */
+    float *kps2d;             /* n*2 out : re-projected positions under pose_refined */
+    float pose_aligned[6];    /* out : after sparse alignment */
+    float pose_refined[6];    /* out : after reprojection refinement (== frame pose before the motion filter) */
+    float align_cost, refine_cost;
+    int align_evals[16];
+    int refine_evals[2];
+    /* optional traces (NULL to skip) */
+    float *klt_pts;           /* n*2 : tracked positions */
+    float *klt_err;           /* n */
+    uint8_t *klt_status;      /* n */
+    float *disparity;         /* n */
+    float *kps2d_refine_in;   /* n*2 : positions fed to the refinement / depth filter */
+} svo_track_io;
+
+int svo_track_frame(svo_ctx *ctx, int prev_slot, int cur_slot, svo_track_io *io);
+/* asynchronous pair (multi-sequence throughput): enqueue on the context's stream / wait + unpack */
+int svo_track_frame_begin(svo_ctx *ctx, int prev_slot, int cur_slot, svo_track_io *io);
+int svo_track_frame_end(svo_ctx *ctx, svo_track_io *io);
+
+/* GPU time (ms, CUDA events on the context's stream) of the last svo_track_frame, and the number of kernel
+ * launches it issued */
+int svo_last_track_timing(svo_ctx *ctx, float *gpu_ms, int *launches);
+int svo_sync(svo_ctx *ctx);
+
+/* ================================================================== host facade ================ */
+/* StereoSlam (src/include/stereo_slam.hpp:27-79) with plain-C types. */
+typedef struct svo_slam svo_slam;
+
+typedef struct svo_pose {  /* == struct Pose, src/include/pose_manager.hpp:21-28 */
+    float x, y, z, rx, ry, rz;
+} svo_pose;
+
+typedef struct svo_keypoint_info {  /* KeyPointInformation without the cv::KalmanFilter (stereo_slam_types.hpp:86-100) */
+    float score;
+    int level;
+    int type;
+    uint64_t keyframe_id;
+    uint64_t keypoint_index;
+    uint8_t color[3];
+    uint8_t ignore_during_refinement, ignore_completely, ignore_temporary;
+    int outlier_count, inlier_count;
+    float kf_inv_depth, kf_variance; /* statePost / errorCovPost of the 1x1 filter */
+} svo_keypoint_info;
+
+int svo_slam_create(const svo_camera_settings *settings, int device, int width, int height, svo_slam **out);
+int svo_slam_destroy(svo_slam *s);
+const char *svo_slam_last_error(svo_slam *s);
+/* StereoSlam::new_image (stereo_slam.cpp:123-271) */
+int svo_slam_new_image(svo_slam *s, const uint8_t *left, size_t left_stride, const uint8_t *right, size_t right_stride,
+                       float time_stamp);
+/* pipelined variant for many independent sequences: begin enqueues the frame, end finishes the host part */
+int svo_slam_new_image_begin(svo_slam *s, const uint8_t *left, size_t left_stride, const uint8_t *right,
+                             size_t right_stride, float time_stamp);
+int svo_slam_new_image_end(svo_slam *s);
+/* StereoSlam::get_frame (stereo_slam.cpp:278-284): returns SVO_ERR_STATE before the first image */
+int svo_slam_get_frame(svo_slam *s, uint64_t *id, svo_pose *pose, double *time_stamp, int *n_keypoints);
+int svo_slam_get_frame_keypoints(svo_slam *s, int max, float *kps2d, float *kps3d, svo_keypoint_info *info);
+int svo_slam_get_frame_image(svo_slam *s, int kind, int level, uint8_t *out, size_t out_stride);
+/* StereoSlam::get_keyframe(s) (stereo_slam.cpp:273-276, :286-289); index -1 = last keyframe */
+int svo_slam_keyframe_count(svo_slam *s);
+int svo_slam_get_keyframe(svo_slam *s, int index, uint64_t *id, svo_pose *pose, double *time_stamp, int *n_keypoints);
+int svo_slam_get_keyframe_keypoints(svo_slam *s, int index, int max, float *kps2d, float *kps3d, svo_keypoint_info *info);
+int svo_slam_get_keyframe_image(svo_slam *s, int index, int kind, int level, uint8_t *out, size_t out_stride);
+/* StereoSlam::get_trajectory (stereo_slam.cpp:291-294): returns the number of poses, copies up to max */
+int svo_slam_get_trajectory(svo_slam *s, int max, svo_pose *out);
+/* StereoSlam::update_pose (stereo_slam.cpp:296-359) */
+int svo_slam_update_pose(svo_slam *s, const svo_pose *pose, const float speed[6], const float pose_variance[6],
+                         const float speed_variance[6], double dt, svo_pose *filtered);
+/* diagnostics of the last new_image: device ms, kernel launches, whether a keyframe was created */
+int svo_slam_last_stats(svo_slam *s, float *gpu_ms, int *launches, int *keyframe_created);
+/* the device context behind the facade (for stage-level probes in tests) */
+svo_ctx *svo_slam_ctx(svo_slam *s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVO_CUDA_H */

@@ -272,6 +272,12 @@ class OracleSlam:
         lib().orc_slam_get_pose(self.h, _p(p))
         return p
 
+    def stage_ms(self):
+        """[pyramids, alignment, klt, refine-gn, ssd, filter, keyframe, total] of the last new_image (ms)."""
+        out = np.zeros(8, np.float64)
+        lib().orc_slam_stage_ms(self.h, _p(out))
+        return out
+
     def n_kps(self):
         return lib().orc_slam_n_kps(self.h)
 

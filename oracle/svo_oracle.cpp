@@ -20,6 +20,7 @@
 #include <cstdio>
 #include <array>
 #include <limits>
+#include <chrono>
 
 using namespace orc;
 
@@ -554,7 +555,8 @@ struct OracleSlam {
     uint64_t keyframe_count = 0;  // depth_calculator.cpp:135 static
     std::map<std::string, std::vector<float>> trace;
     bool tracing = true;
-    double stage_ms[8] = {0};
+    double stage_ms[8] = {0};  // 0 pyramids 1 alignment 2 klt 3 refine-gn 4 ssd 5 filter 6 keyframe 7 total
+    static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
     OracleSlam(const Settings &s, int w, int h) : cs(s), W(w), H(h)
     {
@@ -724,12 +726,14 @@ struct OracleSlam {
         tr("klt_prev", ref.data(), ref.size());
         tr("klt_init", act.data(), act.size());
         tri("klt_kf", kfid);
+        double t0 = now_ms();
         for (size_t i = 0; i < n; i++) {
             KeyFrame *k = keyframes[f.kps.info[i].keyframe_id].get();
-            lk_track_point(k->img->opt_flow, f.img->opt_flow, cs.window_size_opt_flow, 2, 30, 0.01 * 0.01, 1e-4f, &ref[2 * i], &act[2 * i],
+            lk_track_point(k->img->opt_flow, f.img->opt_flow, cs.window_size_opt_flow, 2, 30, 0.01 * 0.01, 1e-4, &ref[2 * i], &act[2 * i],
                            &status[i], &err[i]);
             if (status[i] == 0) err[i] = std::numeric_limits<float>::infinity();  // optical_flow.cpp:46-50
         }
+        stage_ms[2] = now_ms() - t0;
         tr("klt_next", act.data(), act.size());
         tr("klt_err", err.data(), err.size());
         if (tracing) { std::vector<float> s(status.begin(), status.end()); trace["klt_status"] = s; }
@@ -748,7 +752,9 @@ struct OracleSlam {
         PoseRefinerCb cb(f.kps.kps2d.data(), f.kps.kps3d.data(), f.kps.info, cs);
         PoseM refined;
         int ev = 0, gr = 0;
+        t0 = now_ms();
         float ret = gn_driver(cb, f.pose, refined, 0.0001f, &ev, &gr);
+        stage_ms[3] = now_ms() - t0;
         f.pose = refined;
         tr("ref_pose_out", f.pose.p, 6);
         if (tracing) { trace["ref_cost"] = {ret}; trace["ref_evals"] = {(float)ev, (float)gr}; }
@@ -777,7 +783,9 @@ struct OracleSlam {
         tr("align_pose_in", frame->pose.p, 6);
         PoseM est;
         AlignStats st;
+        double t0 = now_ms();
         float cost = estimate_pose(frame->img->left, prev->img->left, prev->kps, cs, frame->pose, est, &st);
+        stage_ms[1] = now_ms() - t0;
         tr("align_pose_out", est.p, 6);
         if (tracing) {
             trace["align_cost"] = {cost};
@@ -802,8 +810,11 @@ struct OracleSlam {
         size_t n = f.kps.size();
         // calculate_disparities :259-327
         std::vector<float> disp(n);
+        double t0 = now_ms();
         for (size_t i = 0; i < n; i++)
             disp[i] = stereo_disparity(f.img->left[0], f.img->right[0], f.kps.kps2d[2 * i], f.kps.kps2d[2 * i + 1], cs, 1);
+        stage_ms[4] = now_ms() - t0;
+        t0 = now_ms();
         tr("df_disp", disp.data(), n);
         // outlier_check :52-128
         std::vector<float> k3(n * 3);
@@ -868,6 +879,7 @@ struct OracleSlam {
             m33v(k->pose.R, cp, o);
             for (int q = 0; q < 3; q++) updated[3 * i + q] = c1[q] + o[q];
         }
+        stage_ms[5] = now_ms() - t0;
     }
 
     // ---- StereoSlam::update_pose (stereo_slam.cpp:296-359) ----
@@ -890,14 +902,19 @@ struct OracleSlam {
         frame = std::make_shared<Frame>();
         frame->time_stamp = time_stamp;
         frame->img = std::make_shared<StereoImage>();
+        for (double &m : stage_ms) m = 0;
+        double t_start = now_ms(), t0 = t_start;
         create_img_pyramid(left, W, H, stride, cs.max_pyramid_levels, frame->img->left);
         create_img_pyramid(right, W, H, stride, 1, frame->img->right);
         build_lk_pyramid(left, W, H, stride, 2, frame->img->opt_flow);
+        stage_ms[0] = now_ms() - t0;
         if (!previous) {
             frame->id = 0;
             float z[6] = {0, 0, 0, 0, 0, 0};
             frame->pose.set(z);
+            t0 = now_ms();
             keyframe = create_keyframe(*frame);
+            stage_ms[6] = now_ms() - t0;
             for (auto &i : frame->kps.info) i.ignore_temporary = false;
             // the keyframe copy was taken before the flags were cleared (keyframe_manager.cpp:27 precedes
             // stereo_slam.cpp:157-159); later write-backs (stereo_slam.cpp:218-223) refresh it.
@@ -942,7 +959,9 @@ struct OracleSlam {
             bool need = keyframe_needed(*frame);
             if (tracing) trace["kf_needed"] = {need ? 1.f : 0.f};
             if (need) {
+                t0 = now_ms();
                 keyframe = create_keyframe(*frame);
+                stage_ms[6] = now_ms() - t0;
                 size_t c = 0;
                 for (auto &i : frame->kps.info) if (!i.ignore_temporary) c++;
                 if (c < frame->kps.info.size() / 4)
@@ -962,6 +981,7 @@ struct OracleSlam {
         std::array<float, 6> p;
         for (int i = 0; i < 6; i++) p[i] = frame->pose.p[i];
         trajectory.push_back(p);
+        stage_ms[7] = now_ms() - t_start;
     }
 };
 
@@ -1022,7 +1042,7 @@ void orc_lk(const uint8_t *prev, const uint8_t *next, int w, int h, int win, con
     build_lk_pyramid(prev, w, h, w, 2, a);
     build_lk_pyramid(next, w, h, w, 2, b);
     for (int i = 0; i < n; i++)
-        lk_track_point(a, b, win, 2, 30, 0.01 * 0.01, 1e-4f, prev_pts + 2 * i, next_pts + 2 * i, status + i, err + i);
+        lk_track_point(a, b, win, 2, 30, 0.01 * 0.01, 1e-4, prev_pts + 2 * i, next_pts + 2 * i, status + i, err + i);
 }
 void orc_ssd_disparity(const uint8_t *left, const uint8_t *right, int w, int h, const OrcCameraSettings *cs, const float *kps2d, int n,
                        int mode, float *out)
@@ -1093,6 +1113,7 @@ void orc_slam_update_pose(void *h, const float *pose, const float *speed, const 
     ((OracleSlam *)h)->update_pose_kf(pose, speed, pv, sv, dt, out);
 }
 void orc_slam_get_pose(void *h, float *p6) { OracleSlam *s = (OracleSlam *)h; for (int i = 0; i < 6; i++) p6[i] = s->frame ? s->frame->pose.p[i] : 0; }
+void orc_slam_stage_ms(void *h, double *out8) { for (int i = 0; i < 8; i++) out8[i] = ((OracleSlam *)h)->stage_ms[i]; }
 int orc_slam_n_kps(void *h) { OracleSlam *s = (OracleSlam *)h; return s->frame ? (int)s->frame->kps.size() : 0; }
 int orc_slam_n_keyframes(void *h) { return (int)((OracleSlam *)h)->keyframes.size(); }
 int orc_slam_trajectory(void *h, float *out, int max)

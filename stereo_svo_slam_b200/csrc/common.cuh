@@ -1,0 +1,162 @@
+// Shared device/host helpers for the sm_100a tracking kernels.
+// All translation units are compiled with -fmad=false: the reference's float arithmetic is plain scalar
+// C++ without FMA contraction (src/Makefile:5-6), and per-keypoint values are reproduced operation by
+// operation so that only cross-keypoint reductions differ in rounding.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cuda_runtime.h>
+#include "../../include/svo_cuda.h"
+
+#define SVO_MAX_LEVELS 8
+#define SVO_LK_LEVELS 3
+#define SVO_LK_PAD 32  // border (px) materialised around every LK pyramid level (>= winSize + 1)
+
+// ---- flags (bit layout shared by host and device; mirrors KeyPointInformation's three booleans,
+//      src/include/stereo_slam_types.hpp:86-100)
+#define SVO_F_IGN_REFINE 1u
+#define SVO_F_IGN_COMPLETE 2u
+#define SVO_F_IGN_TEMP 4u
+
+struct DevCam {  // camera + algorithm settings, passed by value to kernels
+    float baseline, fx, fy, cx, cy, k1, k2, k3, p1, p2;
+    int grid_height, grid_width, search_x, search_y;
+    int win_pose, win_flow, win_depth, max_levels, min_level;
+};
+
+static inline DevCam make_devcam(const svo_camera_settings &s)
+{
+    DevCam c;
+    c.baseline = s.baseline; c.fx = s.fx; c.fy = s.fy; c.cx = s.cx; c.cy = s.cy;
+    c.k1 = s.k1; c.k2 = s.k2; c.k3 = s.k3; c.p1 = s.p1; c.p2 = s.p2;
+    c.grid_height = s.grid_height; c.grid_width = s.grid_width; c.search_x = s.search_x; c.search_y = s.search_y;
+    c.win_pose = s.window_size_pose_estimator; c.win_flow = s.window_size_opt_flow;
+    c.win_depth = s.window_size_depth_calculator; c.max_levels = s.max_pyramid_levels;
+    c.min_level = s.min_pyramid_level_pose_estimation;
+    return c;
+}
+
+#ifdef __CUDACC__
+// cv::Rodrigues (vector -> matrix) in double — same expression order as OpenCV (pose_manager.cpp:15-16).
+__device__ __forceinline__ void dev_rodrigues_d(float r0, float r1, float r2, double R[9])
+{
+    double rx = r0, ry = r1, rz = r2;
+    double theta = sqrt(rx * rx + ry * ry + rz * rz);
+    if (theta < 2.220446049250313e-16) {
+        R[0] = 1; R[1] = 0; R[2] = 0; R[3] = 0; R[4] = 1; R[5] = 0; R[6] = 0; R[7] = 0; R[8] = 1;
+        return;
+    }
+    double s, c;
+    sincos(theta, &s, &c);
+    double c1 = 1. - c;
+    double it = 1. / theta;
+    rx *= it; ry *= it; rz *= it;
+    R[0] = c * 1 + c1 * (rx * rx) + s * 0;     R[1] = c * 0 + c1 * (rx * ry) + s * (-rz); R[2] = c * 0 + c1 * (rx * rz) + s * ry;
+    R[3] = c * 0 + c1 * (rx * ry) + s * rz;    R[4] = c * 1 + c1 * (ry * ry) + s * 0;     R[5] = c * 0 + c1 * (ry * rz) + s * (-rx);
+    R[6] = c * 0 + c1 * (rx * rz) + s * (-ry); R[7] = c * 0 + c1 * (ry * rz) + s * rx;    R[8] = c * 1 + c1 * (rz * rz) + s * 0;
+}
+__device__ __forceinline__ void dev_rodrigues_f(float r0, float r1, float r2, float R[9])
+{
+    double Rd[9];
+    dev_rodrigues_d(r0, r1, r2, Rd);
+#pragma unroll
+    for (int k = 0; k < 9; k++) R[k] = (float)Rd[k];
+}
+
+// cv::Matx33f * cv::Vec3f : s = 0; s += a(i,k)*b(k)  (float, sequential)
+__device__ __forceinline__ void dev_m33v(const float *M, float v0, float v1, float v2, float &o0, float &o1, float &o2)
+{
+    float s;
+    s = 0.f; s += M[0] * v0; s += M[1] * v1; s += M[2] * v2; o0 = s;
+    s = 0.f; s += M[3] * v0; s += M[4] * v1; s += M[5] * v2; o1 = s;
+    s = 0.f; s += M[6] * v0; s += M[7] * v1; s += M[8] * v2; o2 = s;
+}
+
+// project_keypoints (transform_keypoints.cpp:11-47): float (P - t), then cv::projectPoints in double with
+// rotation Rd = Rodrigues(-r) (double, NOT rounded to float) and tvec = 0.
+__device__ __forceinline__ void dev_project(const double *Rd, float px, float py, float pz, float tx, float ty, float tz,
+                                            float fx, float fy, float cx, float cy, float k1, float k2, float p1, float p2,
+                                            float k3, float &u, float &v)
+{
+    double X = (double)(px - tx), Y = (double)(py - ty), Z = (double)(pz - tz);
+    double x = Rd[0] * X + Rd[1] * Y + Rd[2] * Z + 0.0;
+    double y = Rd[3] * X + Rd[4] * Y + Rd[5] * Z + 0.0;
+    double z = Rd[6] * X + Rd[7] * Y + Rd[8] * Z + 0.0;
+    z = z ? 1. / z : 1;
+    x *= z; y *= z;
+    double r2 = x * x + y * y, r4 = r2 * r2, r6 = r4 * r2;
+    double a1 = 2 * x * y, a2 = r2 + 2 * x * x, a3 = r2 + 2 * y * y;
+    double cdist = 1 + (double)k1 * r2 + (double)k2 * r4 + (double)k3 * r6;
+    double xd0 = x * cdist * 1.0 + (double)p1 * a1 + (double)p2 * a2;
+    double yd0 = y * cdist * 1.0 + (double)p1 * a3 + (double)p2 * a1;
+    u = (float)(xd0 * (double)fx + (double)cx);
+    v = (float)(yd0 * (double)fy + (double)cy);
+}
+
+// exponential_map.hpp:12-37 — norm fixed to 1, w unchanged; Matx * double -> float rounding as in OpenCV
+__device__ __forceinline__ void dev_expmap(const float tw[6], float out[6])
+{
+    const double C1 = 0.45969769413186023;  // 1 - cos(1)
+    const double C2 = 0.1585290151921035;   // 1 - sin(1)
+    float w0 = tw[3], w1 = tw[4], w2 = tw[5];
+    float K[9] = {0.f, -w2, w1, w2, 0.f, -w0, -w1, w0, 0.f};
+    float M[9];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            float s = 0.f;
+            s += K[i * 3 + 0] * K[0 * 3 + j];
+            s += K[i * 3 + 1] * K[1 * 3 + j];
+            s += K[i * 3 + 2] * K[2 * 3 + j];
+            float e = (i == j) ? 1.f : 0.f;
+            float a = (float)((double)K[i * 3 + j] * C1);
+            float b = (float)((double)s * C2);
+            M[i * 3 + j] = (e + a) + b;
+        }
+    dev_m33v(M, tw[0], tw[1], tw[2], out[0], out[1], out[2]);
+    out[3] = w0; out[4] = w1; out[5] = w2;
+}
+
+__device__ __forceinline__ int dev_reflect101(int p, int len)
+{
+    if (len == 1) return 0;
+    while (p < 0 || p >= len) p = (p < 0) ? -p : 2 * (len - 1) - p;
+    return p;
+}
+
+// block-wide sum of `NV` doubles per thread; result valid in ALL threads of warp 0 lane 0 -> written to out[]
+// (fixed reduction tree => deterministic). scratch must hold NV * 32 doubles.
+template <int NV>
+__device__ __forceinline__ void block_reduce_sum(double (&v)[NV], double *scratch, double *out)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
+        double x = v[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+        if (lane == 0) scratch[k * 32 + warp] = x;
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; k++) {
+            double x = (lane < nwarps) ? scratch[k * 32 + lane] : 0.0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+            if (lane == 0) out[k] = x;
+        }
+    }
+    __syncthreads();
+}
+#endif  // __CUDACC__
+
+#define SVO_CUDA_CHECK(ctx_err, expr)                                                                   \
+    do {                                                                                                \
+        cudaError_t _e = (expr);                                                                        \
+        if (_e != cudaSuccess) {                                                                        \
+            snprintf((ctx_err), 256, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return SVO_ERR_CUDA;                                                                        \
+        }                                                                                               \
+    } while (0)

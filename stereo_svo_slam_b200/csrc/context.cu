@@ -1,0 +1,743 @@
+// Device layer of the C-ABI (include/svo_cuda.h, svo_* functions): context, device-resident image sets,
+// per-stage entry points and the fused per-frame tracking sequence.  Host code only orchestrates: every
+// arithmetic step of the hot path runs in the kernels of pyramid.cu / align.cu / klt.cu / refine.cu /
+// stereo.cu / detect.cu.  There is no CPU fallback.
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "kernels.cuh"
+
+static char g_create_err[256] = "";
+
+struct Slot {
+    uint8_t *base = nullptr;
+    ImageSetDev dev;
+    int refcount = 0;
+};
+
+// layout of the keypoint I/O block (same offsets on device and in the pinned host mirror)
+struct IoLayout {
+    size_t n, pose_prior, prev_kps2d, ref_kps2d, kf_id;            // in
+    size_t kps3d, flags, inlier, outlier, kf_state;                // in/out
+    size_t pose_aligned, pose_refined, costs, evals, klt_pts, klt_err, klt_status, disparity, kps2d_ref_in, kps2d_out;  // out
+    size_t in_end, inout_begin, total;
+};
+
+struct svo_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    svo_camera_settings cs;
+    DevCam cam;
+    int W = 0, H = 0, max_kps = 0, n_levels = 0;
+    // slot layout
+    size_t slot_bytes = 0;
+    size_t off_left[SVO_MAX_LEVELS], off_right0, off_lk[SVO_LK_LEVELS];
+    int lw[SVO_MAX_LEVELS], lh[SVO_MAX_LEVELS], lkw[SVO_LK_LEVELS], lkh[SVO_LK_LEVELS], lkpitch[SVO_LK_LEVELS];
+    std::vector<Slot> slots;
+    uint8_t *h_stage[2] = {nullptr, nullptr};  // pinned upload staging (double buffered)
+    int stage_idx = 0;
+    // keyframe tables
+    LevelDesc *d_kf_lk = nullptr;
+    float *d_kf_pose = nullptr;
+    int kf_cap = 0, kf_count = 0;
+    std::vector<int> kf_slot;
+    // keypoint I/O
+    IoLayout lay;
+    uint8_t *d_io = nullptr, *h_io = nullptr;
+    float *d_align_scratch = nullptr;
+    uint8_t *d_detect_scratch = nullptr;  // 2*W*H bytes
+    float *d_cell_xy = nullptr, *d_cell_score = nullptr;
+    int *d_cell_type = nullptr;
+    int cell_cap = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float last_ms = 0;
+    int last_launches = 0;
+    bool track_pending = false;
+    char err[256];
+};
+
+template <class T> static T *io_ptr(uint8_t *base, size_t off) { return reinterpret_cast<T *>(base + off); }
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static void make_layout(IoLayout &L, int M)
+{
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 64); return r; };
+    L.n = take(16);
+    L.pose_prior = take(6 * 4);
+    L.prev_kps2d = take((size_t)M * 8);
+    L.ref_kps2d = take((size_t)M * 8);
+    L.kf_id = take((size_t)M * 4);
+    L.in_end = o;
+    L.inout_begin = o;
+    L.kps3d = take((size_t)M * 12);
+    L.flags = take((size_t)M);
+    L.inlier = take((size_t)M * 4);
+    L.outlier = take((size_t)M * 4);
+    L.kf_state = take((size_t)M * 8);
+    L.pose_aligned = take(6 * 4);
+    L.pose_refined = take(6 * 4);
+    L.costs = take(2 * 4);
+    L.evals = take(18 * 4);
+    L.klt_pts = take((size_t)M * 8);
+    L.klt_err = take((size_t)M * 4);
+    L.klt_status = take((size_t)M);
+    L.disparity = take((size_t)M * 4);
+    L.kps2d_ref_in = take((size_t)M * 8);
+    L.kps2d_out = take((size_t)M * 8);
+    L.total = o;
+}
+
+#define CK(expr) SVO_CUDA_CHECK(ctx->err, expr)
+
+extern "C" int svo_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+extern "C" const char *svo_last_error(svo_ctx *ctx) { return ctx ? ctx->err : g_create_err; }
+
+static int fail_create(svo_ctx *ctx, int code, const char *msg)
+{
+    snprintf(g_create_err, sizeof(g_create_err), "%s", msg);
+    delete ctx;
+    return code;
+}
+
+extern "C" int svo_ctx_create(const svo_camera_settings *s, int device, int width, int height, int max_keypoints, svo_ctx **out)
+{
+    if (!s || !out || width < 16 || height < 16) return fail_create(nullptr, SVO_ERR_INVALID, "bad arguments");
+    if (s->max_pyramid_levels < 1 || s->max_pyramid_levels > 7 || s->min_pyramid_level_pose_estimation < 0 ||
+        s->min_pyramid_level_pose_estimation > s->max_pyramid_levels)
+        return fail_create(nullptr, SVO_ERR_INVALID, "max_pyramid_levels must be in 1..7 and min level in 0..max");
+    if (s->window_size_opt_flow < 3 || s->window_size_opt_flow > 31) return fail_create(nullptr, SVO_ERR_INVALID, "window_size_opt_flow must be in 3..31");
+    if (s->window_size_depth_calculator < 1 || s->window_size_depth_calculator > 63 || s->search_x < 0 || s->search_y < 0)
+        return fail_create(nullptr, SVO_ERR_INVALID, "bad depth calculator window / search range");
+    if (s->window_size_pose_estimator < 1 || s->window_size_pose_estimator > 16) return fail_create(nullptr, SVO_ERR_INVALID, "window_size_pose_estimator must be in 1..16");
+    if (s->grid_width < 2 || s->grid_height < 2) return fail_create(nullptr, SVO_ERR_INVALID, "grid cell must be at least 2x2");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail_create(nullptr, SVO_ERR_NO_DEVICE, "no CUDA device (there is no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail_create(nullptr, SVO_ERR_INVALID, "device index out of range");
+    svo_ctx *ctx = new svo_ctx();
+    ctx->err[0] = 0;
+    ctx->device = device;
+    ctx->cs = *s;
+    ctx->cam = make_devcam(*s);
+    ctx->W = width; ctx->H = height;
+    ctx->n_levels = s->max_pyramid_levels;
+    if (max_keypoints <= 0) {
+        // one keypoint per grid cell per keyframe, surviving ones from older keyframes on top: 4x cells is ample
+        max_keypoints = 4 * (width / s->grid_width + 1) * (height / s->grid_height + 1);
+    }
+    ctx->max_kps = (int)align_up((size_t)max_keypoints, 32);
+#define CKC(expr)                                                                                      \
+    do {                                                                                               \
+        cudaError_t _e = (expr);                                                                       \
+        if (_e != cudaSuccess) {                                                                       \
+            char m[256];                                                                               \
+            snprintf(m, sizeof(m), "%s failed: %s", #expr, cudaGetErrorString(_e));                    \
+            return fail_create(ctx, SVO_ERR_CUDA, m);                                                  \
+        }                                                                                              \
+    } while (0)
+    CKC(cudaSetDevice(device));
+    CKC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CKC(cudaEventCreate(&ctx->ev0));
+    CKC(cudaEventCreate(&ctx->ev1));
+    CKC(align_init_device());
+    // ---- slot layout
+    size_t o = 0;
+    int w = width, h = height;
+    for (int l = 0; l < ctx->n_levels; l++) {
+        ctx->lw[l] = w; ctx->lh[l] = h;
+        ctx->off_left[l] = o;
+        o = align_up(o + (size_t)w * h + 16, 256);
+        w /= 2; h /= 2;
+        if (w < 1 || h < 1) return fail_create(ctx, SVO_ERR_INVALID, "image too small for max_pyramid_levels");
+    }
+    ctx->off_right0 = o;
+    o = align_up(o + (size_t)width * height + 16, 256);
+    w = width; h = height;
+    for (int l = 0; l < SVO_LK_LEVELS; l++) {
+        ctx->lkw[l] = w; ctx->lkh[l] = h;
+        ctx->lkpitch[l] = (int)align_up((size_t)w + 2 * SVO_LK_PAD, 16);
+        ctx->off_lk[l] = o;
+        o = align_up(o + (size_t)ctx->lkpitch[l] * (h + 2 * SVO_LK_PAD) + 16, 256);
+        w = (w + 1) / 2; h = (h + 1) / 2;
+    }
+    ctx->slot_bytes = o;
+    for (int k = 0; k < 2; k++) CKC(cudaMallocHost(&ctx->h_stage[k], (size_t)2 * width * height));
+    make_layout(ctx->lay, ctx->max_kps);
+    CKC(cudaMalloc(&ctx->d_io, ctx->lay.total));
+    CKC(cudaMemset(ctx->d_io, 0, ctx->lay.total));
+    CKC(cudaMallocHost(&ctx->h_io, ctx->lay.total));
+    memset(ctx->h_io, 0, ctx->lay.total);
+    CKC(cudaMalloc(&ctx->d_align_scratch, (size_t)49 * ctx->max_kps * sizeof(float)));
+    CKC(cudaMalloc(&ctx->d_detect_scratch, (size_t)2 * width * height + 64));
+    ctx->cell_cap = (width / 2 + 1) * (height / 2 + 1) / 1 + 16;
+    ctx->cell_cap = (width / s->grid_width + 2) * (height / s->grid_height + 2) * 4 + 64;
+    CKC(cudaMalloc(&ctx->d_cell_xy, (size_t)ctx->cell_cap * 8));
+    CKC(cudaMalloc(&ctx->d_cell_score, (size_t)ctx->cell_cap * 4));
+    CKC(cudaMalloc(&ctx->d_cell_type, (size_t)ctx->cell_cap * 4));
+    ctx->kf_cap = 64;
+    CKC(cudaMalloc(&ctx->d_kf_lk, (size_t)ctx->kf_cap * SVO_LK_LEVELS * sizeof(LevelDesc)));
+    CKC(cudaMalloc(&ctx->d_kf_pose, (size_t)ctx->kf_cap * 24 * sizeof(float)));
+#undef CKC
+    *out = ctx;
+    return SVO_OK;
+}
+
+extern "C" int svo_ctx_destroy(svo_ctx *ctx)
+{
+    if (!ctx) return SVO_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (auto &s : ctx->slots) if (s.base) cudaFree(s.base);
+    for (int k = 0; k < 2; k++) if (ctx->h_stage[k]) cudaFreeHost(ctx->h_stage[k]);
+    if (ctx->d_io) cudaFree(ctx->d_io);
+    if (ctx->h_io) cudaFreeHost(ctx->h_io);
+    if (ctx->d_align_scratch) cudaFree(ctx->d_align_scratch);
+    if (ctx->d_detect_scratch) cudaFree(ctx->d_detect_scratch);
+    if (ctx->d_cell_xy) cudaFree(ctx->d_cell_xy);
+    if (ctx->d_cell_score) cudaFree(ctx->d_cell_score);
+    if (ctx->d_cell_type) cudaFree(ctx->d_cell_type);
+    if (ctx->d_kf_lk) cudaFree(ctx->d_kf_lk);
+    if (ctx->d_kf_pose) cudaFree(ctx->d_kf_pose);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return SVO_OK;
+}
+
+extern "C" int svo_sync(svo_ctx *ctx)
+{
+    if (!ctx) return SVO_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SVO_OK;
+}
+
+static int slot_ok(svo_ctx *ctx, int slot) { return slot >= 0 && slot < (int)ctx->slots.size() && ctx->slots[slot].refcount > 0; }
+
+static int alloc_slot(svo_ctx *ctx, int *slot_out)
+{
+    int id = -1;
+    for (size_t i = 0; i < ctx->slots.size(); i++)
+        if (ctx->slots[i].refcount == 0) { id = (int)i; break; }
+    if (id < 0) {
+        Slot s;
+        CK(cudaMalloc(&s.base, ctx->slot_bytes));
+        CK(cudaMemsetAsync(s.base, 0, ctx->slot_bytes, ctx->stream));
+        ImageSetDev &d = s.dev;
+        d.n_levels = ctx->n_levels;
+        for (int l = 0; l < SVO_MAX_LEVELS; l++) d.left[l] = LevelDesc{nullptr, 0, 0, 0};
+        for (int l = 0; l < ctx->n_levels; l++) d.left[l] = LevelDesc{s.base + ctx->off_left[l], ctx->lw[l], ctx->lh[l], ctx->lw[l]};
+        d.right0 = LevelDesc{s.base + ctx->off_right0, ctx->W, ctx->H, ctx->W};
+        for (int l = 0; l < SVO_LK_LEVELS; l++)
+            d.lk[l] = LevelDesc{s.base + ctx->off_lk[l] + (size_t)SVO_LK_PAD * ctx->lkpitch[l] + SVO_LK_PAD, ctx->lkw[l], ctx->lkh[l], ctx->lkpitch[l]};
+        ctx->slots.push_back(s);
+        id = (int)ctx->slots.size() - 1;
+    }
+    ctx->slots[id].refcount = 1;
+    *slot_out = id;
+    return SVO_OK;
+}
+
+extern "C" int svo_upload_stereo(svo_ctx *ctx, const uint8_t *left, size_t ls, const uint8_t *right, size_t rs, int *slot_out)
+{
+    if (!ctx || !left || !right || !slot_out || ls < (size_t)ctx->W || rs < (size_t)ctx->W) return SVO_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    int id;
+    int rc = alloc_slot(ctx, &id);
+    if (rc) return rc;
+    Slot &s = ctx->slots[id];
+    const size_t img = (size_t)ctx->W * ctx->H;
+    // the staging half used two uploads ago must have been consumed: uploads on one stream are ordered, and the
+    // caller synchronises once per frame (svo_track_frame / svo_sync), so double buffering is sufficient.
+    uint8_t *stage = ctx->h_stage[ctx->stage_idx];
+    ctx->stage_idx ^= 1;
+    for (int y = 0; y < ctx->H; y++) {
+        memcpy(stage + (size_t)y * ctx->W, left + (size_t)y * ls, ctx->W);
+        memcpy(stage + img + (size_t)y * ctx->W, right + (size_t)y * rs, ctx->W);
+    }
+    CK(cudaMemcpyAsync(s.dev.left[0].ptr, stage, img, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(s.dev.right0.ptr, stage + img, img, cudaMemcpyHostToDevice, ctx->stream));
+    launch_pyr_halfsample(s.dev, ctx->stream);
+    launch_lk_pyramid(s.dev, ctx->stream);
+    CK(cudaGetLastError());
+    *slot_out = id;
+    return SVO_OK;
+}
+
+extern "C" int svo_slot_retain(svo_ctx *ctx, int slot)
+{
+    if (!ctx || !slot_ok(ctx, slot)) return SVO_ERR_INVALID;
+    ctx->slots[slot].refcount++;
+    return SVO_OK;
+}
+
+extern "C" int svo_slot_release(svo_ctx *ctx, int slot)
+{
+    if (!ctx || !slot_ok(ctx, slot)) return SVO_ERR_INVALID;
+    ctx->slots[slot].refcount--;
+    return SVO_OK;
+}
+
+static bool level_desc(svo_ctx *ctx, int slot, int kind, int level, LevelDesc &d)
+{
+    const ImageSetDev &s = ctx->slots[slot].dev;
+    if (kind == 0 && level >= 0 && level < ctx->n_levels) { d = s.left[level]; return true; }
+    if (kind == 1 && level == 0) { d = s.right0; return true; }
+    if (kind == 2 && level >= 0 && level < SVO_LK_LEVELS) { d = s.lk[level]; return true; }
+    return false;
+}
+
+extern "C" int svo_slot_level_size(svo_ctx *ctx, int kind, int level, int *width, int *height)
+{
+    if (!ctx || !width || !height) return SVO_ERR_INVALID;
+    if (kind == 0 && level >= 0 && level < ctx->n_levels) { *width = ctx->lw[level]; *height = ctx->lh[level]; return SVO_OK; }
+    if (kind == 1 && level == 0) { *width = ctx->W; *height = ctx->H; return SVO_OK; }
+    if (kind == 2 && level >= 0 && level < SVO_LK_LEVELS) { *width = ctx->lkw[level]; *height = ctx->lkh[level]; return SVO_OK; }
+    return SVO_ERR_INVALID;
+}
+
+extern "C" int svo_download_level(svo_ctx *ctx, int slot, int kind, int level, uint8_t *out, size_t out_stride)
+{
+    if (!ctx || !out || !slot_ok(ctx, slot)) return SVO_ERR_INVALID;
+    LevelDesc d;
+    if (!level_desc(ctx, slot, kind, level, d) || out_stride < (size_t)d.w) return SVO_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpy2DAsync(out, out_stride, d.ptr, d.pitch, d.w, d.h, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SVO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ helpers
+static int up(svo_ctx *ctx, size_t off, const void *src, size_t bytes)
+{
+    if (bytes == 0) return SVO_OK;
+    CK(cudaMemcpyAsync(ctx->d_io + off, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return SVO_OK;
+}
+static int down(svo_ctx *ctx, void *dst, size_t off, size_t bytes)
+{
+    if (bytes == 0) return SVO_OK;
+    CK(cudaMemcpyAsync(dst, ctx->d_io + off, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return SVO_OK;
+}
+static int set_n(svo_ctx *ctx, int n)
+{
+    int v[4] = {n, 0, 0, 0};
+    CK(cudaMemcpyAsync(ctx->d_io + ctx->lay.n, v, sizeof(v), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));  // v is on the stack
+    return SVO_OK;
+}
+#define DP(T, field) io_ptr<T>(ctx->d_io, ctx->lay.field)
+
+static int check_n(svo_ctx *ctx, int n)
+{
+    if (n < 0) return SVO_ERR_INVALID;
+    if (n > ctx->max_kps) { snprintf(ctx->err, sizeof(ctx->err), "%d keypoints exceed the context capacity %d", n, ctx->max_kps); return SVO_ERR_CAPACITY; }
+    return SVO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ stages
+extern "C" int svo_detect_keypoints(svo_ctx *ctx, int slot, int level, int grid_w, int grid_h, int max_out, float *xy, float *score,
+                                    int *type, int *n_out)
+{
+    if (!ctx || !slot_ok(ctx, slot) || level < 0 || level >= ctx->n_levels || grid_w < 1 || grid_h < 1 || !n_out) return SVO_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    DetectArgs a;
+    a.img = ctx->slots[slot].dev.left[level];
+    a.grid_w = grid_w; a.grid_h = grid_h; a.level = level;
+    a.cells_x = a.img.w / grid_w;
+    a.cells_y = a.img.h / grid_h;
+    if (a.cells_y < 1) a.cells_y = 1;  // the reference always emits the first cell row (corner_detector.cpp:27-31, :73-76)
+    int cells = a.cells_x * a.cells_y;
+    if (cells > ctx->cell_cap) { snprintf(ctx->err, sizeof(ctx->err), "%d grid cells exceed capacity %d", cells, ctx->cell_cap); return SVO_ERR_CAPACITY; }
+    a.score_map = reinterpret_cast<int *>(ctx->d_detect_scratch);
+    a.cell_xy = ctx->d_cell_xy; a.cell_score = ctx->d_cell_score; a.cell_type = ctx->d_cell_type;
+    launch_detect(a, ctx->stream);
+    CK(cudaGetLastError());
+    int m = cells < max_out ? cells : max_out;
+    if (m > 0) {
+        CK(cudaMemcpyAsync(xy, ctx->d_cell_xy, (size_t)m * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(score, ctx->d_cell_score, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(type, ctx->d_cell_type, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    *n_out = cells;
+    return SVO_OK;
+}
+
+extern "C" int svo_fast_corners(svo_ctx *ctx, int slot, int level, int max_out, int *xys, int *n_out)
+{
+    if (!ctx || !slot_ok(ctx, slot) || level < 0 || level >= ctx->n_levels || !n_out) return SVO_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    LevelDesc img = ctx->slots[slot].dev.left[level];
+    launch_fast_list(img, reinterpret_cast<int *>(ctx->d_detect_scratch), nullptr, 0, nullptr, ctx->stream);
+    CK(cudaGetLastError());
+    std::vector<uint8_t> nms((size_t)img.w * img.h);
+    CK(cudaMemcpyAsync(nms.data(), ctx->d_detect_scratch + (size_t)img.w * img.h, nms.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    int n = 0;
+    for (int y = 0; y < img.h; y++)
+        for (int x = 0; x < img.w; x++) {
+            int s = nms[(size_t)y * img.w + x];
+            if (!s) continue;
+            if (n < max_out) { xys[3 * n] = x; xys[3 * n + 1] = y; xys[3 * n + 2] = s; }
+            n++;
+        }
+    *n_out = n;
+    return SVO_OK;
+}
+
+extern "C" int svo_stereo_match(svo_ctx *ctx, int slot, const float *kps2d, int n, int mode, float *disparity)
+{
+    if (!ctx || !slot_ok(ctx, slot) || !kps2d || !disparity || (mode != 0 && mode != 1)) return SVO_ERR_INVALID;
+    int rc = check_n(ctx, n);
+    if (rc) return rc;
+    if (n == 0) return SVO_OK;
+    CK(cudaSetDevice(ctx->device));
+    if ((rc = set_n(ctx, n))) return rc;
+    if ((rc = up(ctx, ctx->lay.kps2d_ref_in, kps2d, (size_t)n * 8))) return rc;
+    SsdArgs a;
+    a.left0 = ctx->slots[slot].dev.left[0]; a.right0 = ctx->slots[slot].dev.right0;
+    a.kps2d = DP(float, kps2d_ref_in); a.n_ptr = DP(int, n); a.mode = mode; a.disparity = DP(float, disparity);
+    a.max_kps = n; a.cam = ctx->cam;
+    launch_stereo_ssd(a, ctx->stream);
+    CK(cudaGetLastError());
+    if ((rc = down(ctx, disparity, ctx->lay.disparity, (size_t)n * 4))) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SVO_OK;
+}
+
+static void fill_align_args(svo_ctx *ctx, int prev_slot, int cur_slot, AlignArgs &a, int n, bool use_flags)
+{
+    for (int l = 0; l < SVO_MAX_LEVELS; l++) { a.prev[l] = ctx->slots[prev_slot].dev.left[l]; a.cur[l] = ctx->slots[cur_slot].dev.left[l]; }
+    a.kps2d = DP(float, prev_kps2d); a.kps3d = DP(float, kps3d);
+    a.flags = use_flags ? DP(uint8_t, flags) : nullptr;
+    a.n_ptr = DP(int, n);
+    a.pose_in = DP(float, pose_prior); a.pose_out = DP(float, pose_aligned);
+    a.cost_out = DP(float, costs); a.evals_out = DP(int, evals);
+    a.scratch = ctx->d_align_scratch; a.max_kps = ctx->max_kps; a.cam = ctx->cam;
+    a.probe_level = -1; a.probe_grad = nullptr;
+    (void)n;
+}
+
+extern "C" int svo_align(svo_ctx *ctx, int prev_slot, int cur_slot, const float *kps2d, const float *kps3d, const uint8_t *flags, int n,
+                         const float pose_in[6], float pose_out[6], float *cost, int *evals16)
+{
+    if (!ctx || !slot_ok(ctx, prev_slot) || !slot_ok(ctx, cur_slot) || !kps2d || !kps3d || !pose_in || !pose_out) return SVO_ERR_INVALID;
+    int rc = check_n(ctx, n);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    if ((rc = set_n(ctx, n))) return rc;
+    if ((rc = up(ctx, ctx->lay.prev_kps2d, kps2d, (size_t)n * 8))) return rc;
+    if ((rc = up(ctx, ctx->lay.kps3d, kps3d, (size_t)n * 12))) return rc;
+    if (flags && (rc = up(ctx, ctx->lay.flags, flags, (size_t)n))) return rc;
+    if ((rc = up(ctx, ctx->lay.pose_prior, pose_in, 24))) return rc;
+    AlignArgs a;
+    fill_align_args(ctx, prev_slot, cur_slot, a, n, flags != nullptr);
+    launch_align(a, ctx->stream);
+    CK(cudaGetLastError());
+    if ((rc = down(ctx, pose_out, ctx->lay.pose_aligned, 24))) return rc;
+    if (cost && (rc = down(ctx, cost, ctx->lay.costs, 4))) return rc;
+    if (evals16 && (rc = down(ctx, evals16, ctx->lay.evals, 64))) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SVO_OK;
+}
+
+extern "C" int svo_align_probe(svo_ctx *ctx, int prev_slot, int cur_slot, const float *kps2d, const float *kps3d, int n, int level,
+                               const float pose[6], float *cost, float grad[6])
+{
+    if (!ctx || !slot_ok(ctx, prev_slot) || !slot_ok(ctx, cur_slot) || !kps2d || !kps3d || !pose || level < 0 || level >= ctx->n_levels)
+        return SVO_ERR_INVALID;
+    int rc = check_n(ctx, n);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    if ((rc = set_n(ctx, n))) return rc;
+    if ((rc = up(ctx, ctx->lay.prev_kps2d, kps2d, (size_t)n * 8))) return rc;
+    if ((rc = up(ctx, ctx->lay.kps3d, kps3d, (size_t)n * 12))) return rc;
+    if ((rc = up(ctx, ctx->lay.pose_prior, pose, 24))) return rc;
+    AlignArgs a;
+    fill_align_args(ctx, prev_slot, cur_slot, a, n, false);
+    a.probe_level = level;
+    a.probe_grad = DP(float, pose_refined);
+    launch_align(a, ctx->stream);
+    CK(cudaGetLastError());
+    if (cost && (rc = down(ctx, cost, ctx->lay.costs, 4))) return rc;
+    if (grad && (rc = down(ctx, grad, ctx->lay.pose_refined, 24))) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SVO_OK;
+}
+
+static int klt_common(svo_ctx *ctx, const int *keyframe_ids, int prev_slot, int cur_slot, const float *prev_pts, const float *init_pts, int n,
+                      float *next_pts, uint8_t *status, float *err)
+{
+    if (!prev_pts || !init_pts || !next_pts || !status || !err) return SVO_ERR_INVALID;
+    int rc = check_n(ctx, n);
+    if (rc) return rc;
+    if (n == 0) return SVO_OK;
+    CK(cudaSetDevice(ctx->device));
+    if ((rc = set_n(ctx, n))) return rc;
+    if ((rc = up(ctx, ctx->lay.ref_kps2d, prev_pts, (size_t)n * 8))) return rc;
+    if ((rc = up(ctx, ctx->lay.kps2d_ref_in, init_pts, (size_t)n * 8))) return rc;
+    KltArgs a;
+    memset(&a, 0, sizeof(a));
+    if (keyframe_ids) {
+        for (int i = 0; i < n; i++)
+            if (keyframe_ids[i] < 0 || keyframe_ids[i] >= ctx->kf_count) return SVO_ERR_INVALID;
+        if ((rc = up(ctx, ctx->lay.kf_id, keyframe_ids, (size_t)n * 4))) return rc;
+        a.kf_lk_table = ctx->d_kf_lk;
+        a.keyframe_ids = DP(int, kf_id);
+    } else {
+        for (int l = 0; l < SVO_LK_LEVELS; l++) a.prev_fixed[l] = ctx->slots[prev_slot].dev.lk[l];
+    }
+    for (int l = 0; l < SVO_LK_LEVELS; l++) a.cur[l] = ctx->slots[cur_slot].dev.lk[l];
+    a.prev_pts = DP(float, ref_kps2d); a.init_pts = DP(float, kps2d_ref_in);
+    a.n_ptr = DP(int, n);
+    a.next_pts = DP(float, klt_pts); a.status = DP(uint8_t, klt_status); a.err = DP(float, klt_err);
+    a.flags = nullptr; a.kps2d_out = nullptr;
+    a.max_kps = n; a.cam = ctx->cam;
+    launch_klt(a, ctx->stream);
+    CK(cudaGetLastError());
+    if ((rc = down(ctx, next_pts, ctx->lay.klt_pts, (size_t)n * 8))) return rc;
+    if ((rc = down(ctx, status, ctx->lay.klt_status, (size_t)n))) return rc;
+    if ((rc = down(ctx, err, ctx->lay.klt_err, (size_t)n * 4))) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SVO_OK;
+}
+
+extern "C" int svo_klt(svo_ctx *ctx, const int *keyframe_ids, int cur_slot, const float *prev_pts, const float *init_pts, int n,
+                       float *next_pts, uint8_t *status, float *err)
+{
+    if (!ctx || !keyframe_ids || !slot_ok(ctx, cur_slot)) return SVO_ERR_INVALID;
+    return klt_common(ctx, keyframe_ids, -1, cur_slot, prev_pts, init_pts, n, next_pts, status, err);
+}
+
+extern "C" int svo_klt_slots(svo_ctx *ctx, int prev_slot, int cur_slot, const float *prev_pts, const float *init_pts, int n, float *next_pts,
+                             uint8_t *status, float *err)
+{
+    if (!ctx || !slot_ok(ctx, prev_slot) || !slot_ok(ctx, cur_slot)) return SVO_ERR_INVALID;
+    return klt_common(ctx, nullptr, prev_slot, cur_slot, prev_pts, init_pts, n, next_pts, status, err);
+}
+
+extern "C" int svo_reproj_refine(svo_ctx *ctx, const float *kps2d, const float *kps3d, const uint8_t *flags, int n, const float pose_in[6],
+                                 float pose_out[6], float *cost, int *evals2)
+{
+    if (!ctx || !kps2d || !kps3d || !flags || !pose_in || !pose_out) return SVO_ERR_INVALID;
+    int rc = check_n(ctx, n);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    if ((rc = set_n(ctx, n))) return rc;
+    if ((rc = up(ctx, ctx->lay.kps2d_ref_in, kps2d, (size_t)n * 8))) return rc;
+    if ((rc = up(ctx, ctx->lay.kps3d, kps3d, (size_t)n * 12))) return rc;
+    if ((rc = up(ctx, ctx->lay.flags, flags, (size_t)n))) return rc;
+    if ((rc = up(ctx, ctx->lay.pose_aligned, pose_in, 24))) return rc;
+    RefineArgs a;
+    a.kps2d = DP(float, kps2d_ref_in); a.kps3d = DP(float, kps3d); a.flags = DP(uint8_t, flags); a.n_ptr = DP(int, n);
+    a.pose_in = DP(float, pose_aligned); a.pose_out = DP(float, pose_refined);
+    a.cost_out = DP(float, costs) + 1; a.evals_out = DP(int, evals) + 16; a.cam = ctx->cam;
+    launch_refine(a, ctx->stream);
+    CK(cudaGetLastError());
+    if ((rc = down(ctx, pose_out, ctx->lay.pose_refined, 24))) return rc;
+    if (cost && (rc = down(ctx, cost, ctx->lay.costs + 4, 4))) return rc;
+    if (evals2 && (rc = down(ctx, evals2, ctx->lay.evals + 64, 8))) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SVO_OK;
+}
+
+extern "C" int svo_project(svo_ctx *ctx, const float pose[6], const float *kps3d, int n, float *kps2d)
+{
+    if (!ctx || !pose || !kps3d || !kps2d) return SVO_ERR_INVALID;
+    int rc = check_n(ctx, n);
+    if (rc) return rc;
+    if (n == 0) return SVO_OK;
+    CK(cudaSetDevice(ctx->device));
+    if ((rc = set_n(ctx, n))) return rc;
+    if ((rc = up(ctx, ctx->lay.kps3d, kps3d, (size_t)n * 12))) return rc;
+    if ((rc = up(ctx, ctx->lay.pose_refined, pose, 24))) return rc;
+    launch_project(DP(float, pose_refined), DP(float, kps3d), DP(int, n), n, ctx->cam, DP(float, kps2d_out), ctx->stream);
+    CK(cudaGetLastError());
+    if ((rc = down(ctx, kps2d, ctx->lay.kps2d_out, (size_t)n * 8))) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SVO_OK;
+}
+
+// host Rodrigues (same expression order as cv::Rodrigues) for the keyframe pose table
+static void host_rodrigues_f(const float r[3], float R[9])
+{
+    double rx = r[0], ry = r[1], rz = r[2];
+    double theta = std::sqrt(rx * rx + ry * ry + rz * rz);
+    double Rd[9];
+    if (theta < 2.220446049250313e-16) {
+        for (int k = 0; k < 9; k++) Rd[k] = (k % 4 == 0) ? 1.0 : 0.0;
+    } else {
+        double c = std::cos(theta), s = std::sin(theta), c1 = 1. - c, it = 1. / theta;
+        rx *= it; ry *= it; rz *= it;
+        double rrt[9] = {rx * rx, rx * ry, rx * rz, rx * ry, ry * ry, ry * rz, rx * rz, ry * rz, rz * rz};
+        double r_x[9] = {0, -rz, ry, rz, 0, -rx, -ry, rx, 0};
+        for (int k = 0; k < 9; k++) Rd[k] = c * ((k % 4 == 0) ? 1.0 : 0.0) + c1 * rrt[k] + s * r_x[k];
+    }
+    for (int k = 0; k < 9; k++) R[k] = (float)Rd[k];
+}
+
+extern "C" int svo_keyframe_commit(svo_ctx *ctx, int slot, const float pose[6], int *keyframe_id_out)
+{
+    if (!ctx || !slot_ok(ctx, slot) || !pose || !keyframe_id_out) return SVO_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->kf_count == ctx->kf_cap) {
+        int ncap = ctx->kf_cap * 2;
+        LevelDesc *nl;
+        float *np;
+        CK(cudaMalloc(&nl, (size_t)ncap * SVO_LK_LEVELS * sizeof(LevelDesc)));
+        CK(cudaMalloc(&np, (size_t)ncap * 24 * sizeof(float)));
+        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaMemcpy(nl, ctx->d_kf_lk, (size_t)ctx->kf_cap * SVO_LK_LEVELS * sizeof(LevelDesc), cudaMemcpyDeviceToDevice));
+        CK(cudaMemcpy(np, ctx->d_kf_pose, (size_t)ctx->kf_cap * 24 * sizeof(float), cudaMemcpyDeviceToDevice));
+        cudaFree(ctx->d_kf_lk); cudaFree(ctx->d_kf_pose);
+        ctx->d_kf_lk = nl; ctx->d_kf_pose = np; ctx->kf_cap = ncap;
+    }
+    int id = ctx->kf_count;
+    float rec[24];
+    for (int k = 0; k < 6; k++) rec[k] = pose[k];
+    float rp[3] = {pose[3], pose[4], pose[5]}, rn[3] = {-pose[3], -pose[4], -pose[5]};
+    host_rodrigues_f(rp, rec + 6);
+    host_rodrigues_f(rn, rec + 15);
+    CK(cudaMemcpyAsync(ctx->d_kf_pose + (size_t)id * 24, rec, sizeof(rec), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_kf_lk + (size_t)id * SVO_LK_LEVELS, ctx->slots[slot].dev.lk, SVO_LK_LEVELS * sizeof(LevelDesc),
+                       cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));  // rec is on the stack
+    ctx->slots[slot].refcount++;
+    ctx->kf_slot.push_back(slot);
+    ctx->kf_count++;
+    *keyframe_id_out = id;
+    return SVO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ fused frame
+extern "C" int svo_track_frame_begin(svo_ctx *ctx, int prev_slot, int cur_slot, svo_track_io *io)
+{
+    if (!ctx || !io || !slot_ok(ctx, prev_slot) || !slot_ok(ctx, cur_slot)) return SVO_ERR_INVALID;
+    if (ctx->track_pending) { snprintf(ctx->err, sizeof(ctx->err), "svo_track_frame_begin called twice without _end"); return SVO_ERR_STATE; }
+    const int n = io->n;
+    int rc = check_n(ctx, n);
+    if (rc) return rc;
+    if (n > 0 && (!io->prev_kps2d || !io->kps3d || !io->ref_kps2d || !io->keyframe_id || !io->flags || !io->inlier_count ||
+                  !io->outlier_count || !io->kf_state || !io->kps2d))
+        return SVO_ERR_INVALID;
+    for (int i = 0; i < n; i++)
+        if (io->keyframe_id[i] < 0 || io->keyframe_id[i] >= ctx->kf_count) { snprintf(ctx->err, sizeof(ctx->err), "keypoint %d: unknown keyframe id %d", i, io->keyframe_id[i]); return SVO_ERR_INVALID; }
+    CK(cudaSetDevice(ctx->device));
+    const IoLayout &L = ctx->lay;
+    uint8_t *h = ctx->h_io;
+    *io_ptr<int>(h, L.n) = n;
+    memcpy(h + L.pose_prior, io->pose_prior, 24);
+    memcpy(h + L.prev_kps2d, io->prev_kps2d, (size_t)n * 8);
+    memcpy(h + L.ref_kps2d, io->ref_kps2d, (size_t)n * 8);
+    memcpy(h + L.kf_id, io->keyframe_id, (size_t)n * 4);
+    memcpy(h + L.kps3d, io->kps3d, (size_t)n * 12);
+    memcpy(h + L.flags, io->flags, (size_t)n);
+    memcpy(h + L.inlier, io->inlier_count, (size_t)n * 4);
+    memcpy(h + L.outlier, io->outlier_count, (size_t)n * 4);
+    memcpy(h + L.kf_state, io->kf_state, (size_t)n * 8);
+
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    // one H2D for all inputs (in + in/out regions are contiguous)
+    CK(cudaMemcpyAsync(ctx->d_io, h, L.pose_aligned, cudaMemcpyHostToDevice, ctx->stream));
+    int launches = 0;
+    // 1. sparse image alignment (stereo_slam.cpp:60-67)
+    AlignArgs aa;
+    fill_align_args(ctx, prev_slot, cur_slot, aa, n, true);
+    launch_align(aa, ctx->stream); launches++;
+    if (n > 0) {
+        // 2. projection with the aligned pose + KLT against the origin keyframes + gating (stereo_slam.cpp:71-83)
+        KltArgs ka;
+        memset(&ka, 0, sizeof(ka));
+        ka.kf_lk_table = ctx->d_kf_lk; ka.keyframe_ids = DP(int, kf_id);
+        for (int l = 0; l < SVO_LK_LEVELS; l++) ka.cur[l] = ctx->slots[cur_slot].dev.lk[l];
+        ka.prev_pts = DP(float, ref_kps2d); ka.init_pts = nullptr; ka.kps3d = DP(float, kps3d); ka.pose = DP(float, pose_aligned);
+        ka.n_ptr = DP(int, n); ka.next_pts = DP(float, klt_pts); ka.status = DP(uint8_t, klt_status); ka.err = DP(float, klt_err);
+        ka.flags = DP(uint8_t, flags); ka.kps2d_out = DP(float, kps2d_ref_in); ka.max_kps = n; ka.cam = ctx->cam;
+        launch_klt(ka, ctx->stream); launches++;
+    }
+    // 3. reprojection Gauss-Newton (pose_refinement.cpp:175-177)
+    RefineArgs ra;
+    ra.kps2d = DP(float, kps2d_ref_in); ra.kps3d = DP(float, kps3d); ra.flags = DP(uint8_t, flags); ra.n_ptr = DP(int, n);
+    ra.pose_in = DP(float, pose_aligned); ra.pose_out = DP(float, pose_refined);
+    ra.cost_out = DP(float, costs) + 1; ra.evals_out = DP(int, evals) + 16; ra.cam = ctx->cam;
+    launch_refine(ra, ctx->stream); launches++;
+    if (n > 0) {
+        // 4. depth filter: disparities on the current stereo pair, then vote / triangulate / Kalman / flags / re-project
+        SsdArgs sa;
+        sa.left0 = ctx->slots[cur_slot].dev.left[0]; sa.right0 = ctx->slots[cur_slot].dev.right0;
+        sa.kps2d = DP(float, kps2d_ref_in); sa.n_ptr = DP(int, n); sa.mode = 1; sa.disparity = DP(float, disparity);
+        sa.max_kps = n; sa.cam = ctx->cam;
+        launch_stereo_ssd(sa, ctx->stream); launches++;
+        FilterArgs fa;
+        fa.kf_pose_table = ctx->d_kf_pose; fa.keyframe_ids = DP(int, kf_id); fa.disparity = DP(float, disparity);
+        fa.kps2d = DP(float, kps2d_ref_in); fa.ref_kps2d = DP(float, ref_kps2d); fa.kps3d = DP(float, kps3d);
+        fa.flags = DP(uint8_t, flags); fa.inlier = DP(int, inlier); fa.outlier = DP(int, outlier); fa.kf_state = DP(float, kf_state);
+        fa.pose = DP(float, pose_refined); fa.kps2d_out = DP(float, kps2d_out); fa.n_ptr = DP(int, n); fa.max_kps = n; fa.cam = ctx->cam;
+        launch_depth_filter(fa, ctx->stream); launches++;
+    }
+    CK(cudaGetLastError());
+    // one D2H for all outputs (in/out + out regions are contiguous)
+    CK(cudaMemcpyAsync(h + L.inout_begin, ctx->d_io + L.inout_begin, L.total - L.inout_begin, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->last_launches = launches;
+    ctx->track_pending = true;
+    return SVO_OK;
+}
+
+extern "C" int svo_track_frame_end(svo_ctx *ctx, svo_track_io *io)
+{
+    if (!ctx || !io) return SVO_ERR_INVALID;
+    if (!ctx->track_pending) { snprintf(ctx->err, sizeof(ctx->err), "svo_track_frame_end without _begin"); return SVO_ERR_STATE; }
+    ctx->track_pending = false;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+    const IoLayout &L = ctx->lay;
+    const uint8_t *h = ctx->h_io;
+    const int n = io->n;
+    memcpy(io->kps3d, h + L.kps3d, (size_t)n * 12);
+    memcpy(io->flags, h + L.flags, (size_t)n);
+    memcpy(io->inlier_count, h + L.inlier, (size_t)n * 4);
+    memcpy(io->outlier_count, h + L.outlier, (size_t)n * 4);
+    memcpy(io->kf_state, h + L.kf_state, (size_t)n * 8);
+    memcpy(io->kps2d, h + L.kps2d_out, (size_t)n * 8);
+    memcpy(io->pose_aligned, h + L.pose_aligned, 24);
+    memcpy(io->pose_refined, h + L.pose_refined, 24);
+    io->align_cost = io_ptr<float>(const_cast<uint8_t *>(h), L.costs)[0];
+    io->refine_cost = io_ptr<float>(const_cast<uint8_t *>(h), L.costs)[1];
+    memcpy(io->align_evals, h + L.evals, 64);
+    memcpy(io->refine_evals, h + L.evals + 64, 8);
+    if (io->klt_pts) memcpy(io->klt_pts, h + L.klt_pts, (size_t)n * 8);
+    if (io->klt_err) memcpy(io->klt_err, h + L.klt_err, (size_t)n * 4);
+    if (io->klt_status) memcpy(io->klt_status, h + L.klt_status, (size_t)n);
+    if (io->disparity) memcpy(io->disparity, h + L.disparity, (size_t)n * 4);
+    if (io->kps2d_refine_in) memcpy(io->kps2d_refine_in, h + L.kps2d_ref_in, (size_t)n * 8);
+    return SVO_OK;
+}
+
+extern "C" int svo_track_frame(svo_ctx *ctx, int prev_slot, int cur_slot, svo_track_io *io)
+{
+    int rc = svo_track_frame_begin(ctx, prev_slot, cur_slot, io);
+    if (rc) return rc;
+    return svo_track_frame_end(ctx, io);
+}
+
+extern "C" int svo_last_track_timing(svo_ctx *ctx, float *gpu_ms, int *launches)
+{
+    if (!ctx) return SVO_ERR_INVALID;
+    if (gpu_ms) *gpu_ms = ctx->last_ms;
+    if (launches) *launches = ctx->last_launches;
+    return SVO_OK;
+}

@@ -1,0 +1,120 @@
+// Internal launcher interface between the C-ABI layer (context.cu) and the kernels.
+#pragma once
+#include "common.cuh"
+
+struct LevelDesc {  // one image level in device memory
+    uint8_t *ptr;   // first pixel of the logical image (for padded LK levels: points INSIDE the padded buffer)
+    int w, h, pitch;
+};
+
+struct ImageSetDev {  // device view of one stereo frame ("slot")
+    LevelDesc left[SVO_MAX_LEVELS];  // halfSample pyramid, pitch == w (contiguous rows)
+    LevelDesc right0;
+    LevelDesc lk[SVO_LK_LEVELS];     // LK pyramid, padded by SVO_LK_PAD px of REFLECT_101 border
+    int n_levels;
+};
+
+// ---- pyramid.cu
+void launch_pyr_halfsample(const ImageSetDev &s, cudaStream_t st);
+void launch_lk_pyramid(const ImageSetDev &s, cudaStream_t st);
+int pyr_launch_count(const ImageSetDev &s);
+
+// ---- align.cu
+struct AlignArgs {
+    LevelDesc prev[SVO_MAX_LEVELS], cur[SVO_MAX_LEVELS];
+    const float *kps2d;    // n*2 previous-frame positions (level 0)
+    const float *kps3d;    // n*3
+    const uint8_t *flags;  // n or null
+    const int *n_ptr;      // device pointer to n
+    const float *pose_in;  // 6
+    float *pose_out;       // 6
+    float *cost_out;       // 1
+    int *evals_out;        // 16
+    float *scratch;        // cache of reference-patch gradients / sums: 48 floats per keypoint (global)
+    int max_kps;
+    DevCam cam;
+    // probe mode: single level, single evaluation
+    int probe_level;       // -1 = normal
+    float *probe_grad;     // 6
+};
+void launch_align(const AlignArgs &a, cudaStream_t st);
+size_t align_smem_bytes(const AlignArgs &a);
+cudaError_t align_init_device();  // once per device: opt in to 227 KB dynamic shared memory
+
+// ---- klt.cu
+struct KltArgs {
+    const LevelDesc *kf_lk_table;  // device table: [keyframe_id][SVO_LK_LEVELS]
+    const int *keyframe_ids;       // n (device) or null => use prev_fixed
+    LevelDesc prev_fixed[SVO_LK_LEVELS];
+    LevelDesc cur[SVO_LK_LEVELS];
+    const float *prev_pts;         // n*2 (keyframe coordinates)
+    const float *init_pts;         // n*2 or null => project kps3d with *pose
+    const float *kps3d;            // n*3 (projection prologue)
+    const float *pose;             // 6   (projection prologue)
+    const int *n_ptr;
+    float *next_pts;               // n*2
+    uint8_t *status;               // n
+    float *err;                    // n
+    // gating epilogue (pose_refinement.cpp:125-150); null flags => no gating
+    uint8_t *flags;                // n in/out
+    float *kps2d_out;              // n*2: accepted tracked position, else the projected position
+    int max_kps;
+    DevCam cam;
+};
+void launch_klt(const KltArgs &a, cudaStream_t st);
+
+// ---- refine.cu
+struct RefineArgs {
+    const float *kps2d, *kps3d;
+    const uint8_t *flags;
+    const int *n_ptr;
+    const float *pose_in;
+    float *pose_out, *cost_out;
+    int *evals_out;  // 2
+    DevCam cam;
+};
+void launch_refine(const RefineArgs &a, cudaStream_t st);
+void launch_project(const float *pose, const float *kps3d, const int *n_ptr, int max_kps, DevCam cam, float *kps2d, cudaStream_t st);
+
+// ---- stereo.cu
+struct SsdArgs {
+    LevelDesc left0, right0;
+    const float *kps2d;
+    const int *n_ptr;
+    int mode;
+    float *disparity;
+    int max_kps;
+    DevCam cam;
+};
+void launch_stereo_ssd(const SsdArgs &a, cudaStream_t st);
+
+struct FilterArgs {
+    const float *kf_pose_table;   // [keyframe_id][6]
+    const int *keyframe_ids;
+    const float *disparity;       // n
+    const float *kps2d;           // n*2 positions used by the filter (KLT-refined or projected)
+    const float *ref_kps2d;       // n*2 position in origin keyframe
+    float *kps3d;                 // n*3 in/out
+    uint8_t *flags;               // n in/out
+    int *inlier, *outlier;        // n in/out
+    float *kf_state;              // n*2 in/out
+    const float *pose;            // 6 frame pose (refined)
+    float *kps2d_out;             // n*2 re-projection of the updated points
+    const int *n_ptr;
+    int max_kps;
+    DevCam cam;
+};
+void launch_depth_filter(const FilterArgs &a, cudaStream_t st);
+
+// ---- detect.cu
+struct DetectArgs {
+    LevelDesc img;
+    int grid_w, grid_h, level;
+    int *score_map;      // w*h ints scratch (FAST scores, 0 = not a corner)
+    float *cell_xy;      // cells*2
+    float *cell_score;   // cells
+    int *cell_type;      // cells
+    int cells_x, cells_y;
+};
+void launch_detect(const DetectArgs &a, cudaStream_t st);
+void launch_fast_list(const LevelDesc &img, int *score_map, int *xys, int max_out, int *count, cudaStream_t st);

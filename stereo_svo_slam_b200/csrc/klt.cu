@@ -1,0 +1,234 @@
+// Pyramidal Lucas-Kanade tracking of keyframe keypoints into the current frame.
+//
+// Replaces OpticalFlow::calculate_optical_flow -> cv::calcOpticalFlowPyrLK (src/lib/optical_flow.cpp:14-56),
+// called once per origin keyframe by PoseRefiner::refine_pose (src/lib/pose_refinement.cpp:102-118), and the
+// gating that follows it (pose_refinement.cpp:125-150).  Arithmetic follows OpenCV's LKTrackerInvoker
+// (video/src/lkpyramid.cpp, scalar path): Q14 bilinear weights (cvRound), Q5 window intensities, Scharr
+// derivatives descaled by 2^14, float 2x2 system, 30 iterations / eps 0.01^2, level-0 error = mean |dI| / 32.
+//
+// B200 design: one CTA per keypoint, all three levels in one launch.  The previous-image window (plus a
+// one-pixel Scharr halo) is staged in shared memory as u8; the Scharr derivative images that OpenCV
+// materialises per level (4 B/px of HBM) are never stored: derivatives are computed on the fly from the
+// staged tile with OpenCV's border rule (REFLECT_101 inside the level, 0 outside).  The window sums
+// (A11, A12, A22, b1, b2, err) are accumulated as exact 64-bit integers — the products are integers in
+// OpenCV too — and reduced with warp shuffles + one shared-memory pass, so the only rounding left is the
+// final int64 -> float conversion (OpenCV rounds after every add; difference <= 1e-5 px, tolerance 0.01 px).
+// Every thread redundantly performs the scalar 2x2 update from the reduced sums, which removes the broadcast
+// barrier: one __syncthreads per LK iteration.
+#include "kernels.cuh"
+
+#define KLT_THREADS 128
+#define KLT_MAXWIN 31
+#define KLT_TILE (KLT_MAXWIN + 3)  // window + bilinear (+1) + Scharr halo (+-1)
+
+struct KltShared {
+    uint8_t tile[KLT_TILE * KLT_TILE + 4];
+    short Iw[KLT_MAXWIN * KLT_MAXWIN];
+    short Ix[KLT_MAXWIN * KLT_MAXWIN];
+    short Iy[KLT_MAXWIN * KLT_MAXWIN];
+    long long part[2][3][KLT_THREADS / 32];
+    float init[2];
+};
+
+__device__ __forceinline__ long long warp_sum_ll(long long v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// reduce three int64 per thread over the block; every thread returns the totals. buf alternates per call.
+__device__ __forceinline__ void block_sum3(KltShared &sm, int buf, long long &a, long long &b, long long &c)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    a = warp_sum_ll(a); b = warp_sum_ll(b); c = warp_sum_ll(c);
+    if (lane == 0) { sm.part[buf][0][warp] = a; sm.part[buf][1][warp] = b; sm.part[buf][2][warp] = c; }
+    __syncthreads();
+    a = b = c = 0;
+#pragma unroll
+    for (int w = 0; w < KLT_THREADS / 32; w++) { a += sm.part[buf][0][w]; b += sm.part[buf][1][w]; c += sm.part[buf][2][w]; }
+}
+
+__device__ __forceinline__ void lk_weights(float a, float b, int &iw00, int &iw01, int &iw10, int &iw11)
+{
+    iw00 = __float2int_rn((1.f - a) * (1.f - b) * (float)(1 << 14));
+    iw01 = __float2int_rn(a * (1.f - b) * (float)(1 << 14));
+    iw10 = __float2int_rn((1.f - a) * b * (float)(1 << 14));
+    iw11 = (1 << 14) - iw00 - iw01 - iw10;
+}
+
+__global__ void __launch_bounds__(KLT_THREADS) klt_pyr_lk_kernel(KltArgs a)
+{
+    __shared__ KltShared sm;
+    const int i = blockIdx.x;
+    const int n = min(*a.n_ptr, a.max_kps);
+    if (i >= n) return;
+    const int tid = threadIdx.x;
+    const int win = a.cam.win_flow;
+    const int npx = win * win;
+    const float half = (float)(win - 1) * 0.5f;
+
+    // ---- initial guess: given, or project_keypoints(estimated pose) (stereo_slam.cpp:71-75)
+    if (tid == 0) {
+        float gx, gy;
+        if (a.init_pts) { gx = a.init_pts[2 * i]; gy = a.init_pts[2 * i + 1]; }
+        else {
+            double Rd[9];
+            const float *p = a.pose;
+            dev_rodrigues_d(-p[3], -p[4], -p[5], Rd);
+            dev_project(Rd, a.kps3d[3 * i], a.kps3d[3 * i + 1], a.kps3d[3 * i + 2], p[0], p[1], p[2], a.cam.fx, a.cam.fy, a.cam.cx,
+                        a.cam.cy, a.cam.k1, a.cam.k2, a.cam.p1, a.cam.p2, a.cam.k3, gx, gy);
+        }
+        sm.init[0] = gx; sm.init[1] = gy;
+    }
+    __syncthreads();
+    const float init_x = sm.init[0], init_y = sm.init[1];
+    const float ppx = a.prev_pts[2 * i], ppy = a.prev_pts[2 * i + 1];
+    const LevelDesc *prev_lv = a.keyframe_ids ? (a.kf_lk_table + (size_t)a.keyframe_ids[i] * SVO_LK_LEVELS) : a.prev_fixed;
+
+    float nx = init_x, ny = init_y;  // nextPts[i]
+    int status = 1;
+    float err = 0.f;
+    int buf = 0;
+
+    for (int level = SVO_LK_LEVELS - 1; level >= 0; level--) {
+        const LevelDesc I = prev_lv[level];
+        const LevelDesc J = a.cur[level];
+        const float scale = (float)(1. / (1 << level));
+        float px = ppx * scale, py = ppy * scale;
+        float qx, qy;
+        if (level == SVO_LK_LEVELS - 1) { qx = nx * scale; qy = ny * scale; }
+        else { qx = nx * 2.f; qy = ny * 2.f; }
+        nx = qx; ny = qy;
+        px -= half; py -= half;
+        const int ipx = (int)floorf(px), ipy = (int)floorf(py);
+        if (ipx < -win || ipx >= I.w || ipy < -win || ipy >= I.h) {
+            if (level == 0) { status = 0; err = 0.f; }
+            continue;
+        }
+        int iw00, iw01, iw10, iw11;
+        lk_weights(px - (float)ipx, py - (float)ipy, iw00, iw01, iw10, iw11);
+
+        // ---- stage the (win+3)^2 u8 tile: rows ipy-1 .. ipy+win+1, cols ipx-1 .. ipx+win+1 (padded level => no bounds tests)
+        const int T = win + 3;
+        __syncthreads();  // previous level's readers are done with tile/Iw/Ix/Iy
+        for (int k = tid; k < T * T; k += KLT_THREADS) {
+            int r = k / T, c = k - r * T;
+            sm.tile[k] = I.ptr[(ptrdiff_t)(ipy - 1 + r) * I.pitch + (ipx - 1 + c)];
+        }
+        __syncthreads();
+        // ---- window template: Iw (Q5), Ix, Iy, and the structure tensor
+        long long s11 = 0, s12 = 0, s22 = 0;
+        for (int k = tid; k < npx; k += KLT_THREADS) {
+            int y = k / win, x = k - y * win;
+            int ival = 0, ixv = 0, iyv = 0;
+#pragma unroll
+            for (int dy = 0; dy < 2; dy++)
+#pragma unroll
+                for (int dx = 0; dx < 2; dx++) {
+                    const int wgt = dy ? (dx ? iw11 : iw10) : (dx ? iw01 : iw00);
+                    const uint8_t *t = &sm.tile[(y + dy + 1) * T + (x + dx + 1)];
+                    ival += (int)t[0] * wgt;
+                    const int X = ipx + x + dx, Y = ipy + y + dy;
+                    if (X >= 0 && X < I.w && Y >= 0 && Y < I.h) {
+                        // Scharr: d/dx = [3 10 3]^T x [-1 0 1], d/dy = [-1 0 1]^T x [3 10 3]
+                        int tl = t[-T - 1], tc = t[-T], trr = t[-T + 1], ml = t[-1], mr = t[1], bl = t[T - 1], bc = t[T], br = t[T + 1];
+                        int gx = 3 * (trr + br) + 10 * mr - (3 * (tl + bl) + 10 * ml);
+                        int gy = 3 * ((bl - tl) + (br - trr)) + 10 * (bc - tc);
+                        ixv += gx * wgt;
+                        iyv += gy * wgt;
+                    }
+                }
+            ival = (ival + (1 << 8)) >> 9;
+            ixv = (ixv + (1 << 13)) >> 14;
+            iyv = (iyv + (1 << 13)) >> 14;
+            sm.Iw[k] = (short)ival; sm.Ix[k] = (short)ixv; sm.Iy[k] = (short)iyv;
+            s11 += (long long)(ixv * ixv); s12 += (long long)(ixv * iyv); s22 += (long long)(iyv * iyv);
+        }
+        block_sum3(sm, buf, s11, s12, s22);
+        buf ^= 1;
+        const float FLT_SCALE = 1.f / (1 << 20);
+        float A11 = (float)s11 * FLT_SCALE, A12 = (float)s12 * FLT_SCALE, A22 = (float)s22 * FLT_SCALE;
+        float D = A11 * A22 - A12 * A12;
+        float minEig = (A22 + A11 - sqrtf((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) / (float)(2 * win * win);
+        if ((double)minEig < 1e-4 || D < 1.1920929e-07f) {
+            if (level == 0) status = 0;
+            continue;
+        }
+        D = 1.f / D;
+        qx -= half; qy -= half;
+        float pdx = 0.f, pdy = 0.f;
+        for (int j = 0; j < 30; j++) {
+            const int iqx = (int)floorf(qx), iqy = (int)floorf(qy);
+            if (iqx < -win || iqx >= J.w || iqy < -win || iqy >= J.h) {
+                if (level == 0) status = 0;
+                break;
+            }
+            lk_weights(qx - (float)iqx, qy - (float)iqy, iw00, iw01, iw10, iw11);
+            long long b1 = 0, b2 = 0, dummy = 0;
+            const uint8_t *Jp = J.ptr + (ptrdiff_t)iqy * J.pitch + iqx;
+            for (int k = tid; k < npx; k += KLT_THREADS) {
+                int y = k / win, x = k - y * win;
+                const uint8_t *q = Jp + (ptrdiff_t)y * J.pitch + x;
+                int v = (int)q[0] * iw00 + (int)q[1] * iw01 + (int)q[J.pitch] * iw10 + (int)q[J.pitch + 1] * iw11;
+                int diff = ((v + (1 << 8)) >> 9) - (int)sm.Iw[k];
+                b1 += (long long)(diff * (int)sm.Ix[k]);
+                b2 += (long long)(diff * (int)sm.Iy[k]);
+            }
+            block_sum3(sm, buf, b1, b2, dummy);
+            buf ^= 1;
+            float fb1 = (float)b1 * FLT_SCALE, fb2 = (float)b2 * FLT_SCALE;
+            float dx = (float)((A12 * fb2 - A22 * fb1) * D);
+            float dy = (float)((A12 * fb1 - A11 * fb2) * D);
+            qx += dx; qy += dy;
+            nx = qx + half; ny = qy + half;
+            if ((double)dx * (double)dx + (double)dy * (double)dy <= 0.01 * 0.01) break;
+            if (j > 0 && fabs((double)(dx + pdx)) < 0.01 && fabs((double)(dy + pdy)) < 0.01) {
+                nx -= dx * 0.5f; ny -= dy * 0.5f;
+                break;
+            }
+            pdx = dx; pdy = dy;
+        }
+        if (status && level == 0) {
+            float ex = nx - half, ey = ny - half;
+            const int iex = (int)floorf(ex), iey = (int)floorf(ey);
+            if (iex < -win || iex >= J.w || iey < -win || iey >= J.h) { status = 0; continue; }
+            lk_weights(ex - (float)iex, ey - (float)iey, iw00, iw01, iw10, iw11);
+            long long e = 0, d1 = 0, d2 = 0;
+            const uint8_t *Jp = J.ptr + (ptrdiff_t)iey * J.pitch + iex;
+            for (int k = tid; k < npx; k += KLT_THREADS) {
+                int y = k / win, x = k - y * win;
+                const uint8_t *q = Jp + (ptrdiff_t)y * J.pitch + x;
+                int v = (int)q[0] * iw00 + (int)q[1] * iw01 + (int)q[J.pitch] * iw10 + (int)q[J.pitch + 1] * iw11;
+                int diff = ((v + (1 << 8)) >> 9) - (int)sm.Iw[k];
+                e += (long long)abs(diff);
+            }
+            block_sum3(sm, buf, e, d1, d2);
+            buf ^= 1;
+            err = (float)e * 1.f / (float)(32 * win * win);
+        }
+    }
+
+    if (tid == 0) {
+        if (status == 0) err = __int_as_float(0x7f800000);  // optical_flow.cpp:46-50
+        a.next_pts[2 * i] = nx; a.next_pts[2 * i + 1] = ny;
+        a.status[i] = (uint8_t)status;
+        a.err[i] = err;
+        if (a.flags) {  // pose_refinement.cpp:125-150
+            uint8_t f = a.flags[i];
+            float ox = init_x, oy = init_y;
+            float d = (init_x - nx) * (init_x - nx) + (init_y - ny) * (init_y - ny);
+            if (err > 20) f |= SVO_F_IGN_COMPLETE;
+            else if (d > 81) f |= SVO_F_IGN_REFINE;
+            else { f &= (uint8_t)~SVO_F_IGN_REFINE; ox = nx; oy = ny; }
+            a.flags[i] = f;
+            a.kps2d_out[2 * i] = ox; a.kps2d_out[2 * i + 1] = oy;
+        }
+    }
+}
+
+void launch_klt(const KltArgs &a, cudaStream_t st)
+{
+    if (a.max_kps <= 0) return;
+    klt_pyr_lk_kernel<<<a.max_kps, KLT_THREADS, 0, st>>>(a);
+}

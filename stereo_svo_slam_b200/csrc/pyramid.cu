@@ -1,0 +1,132 @@
+// Image pyramids of one stereo frame (stereo_slam.cpp:135-139).
+//
+// pyr_halfsample_kernel : createImgPyramid/halfSample (stereo_slam.cpp:93-121).  ONE launch produces every level:
+//   a CTA stages a 64x64 tile of level 0 in shared memory and reduces it level by level (truncating
+//   integer mean of 2x2, exactly the reference's arithmetic), so level 0 is read from HBM once and each
+//   coarser level is written once.  Pure streaming kernel -> HBM roofline (algorithmic bytes: SURVEY §8d).
+// lk_pad_level0_kernel / lk_pyrdown_kernel : cv::buildOpticalFlowPyramid(left, win, 2) image levels:
+//   level 0 copy, levels 1..2 = cv::pyrDown ([1 4 6 4 1]^2, (sum+128)>>8, even samples,
+//   size (w+1)/2 x (h+1)/2).  Every level is stored with a SVO_LK_PAD-pixel BORDER_REFLECT_101 frame, which
+//   is both pyrDown's border rule and the padding calcOpticalFlowPyrLK expects around its windows; the
+//   Scharr derivative images OpenCV stores next to them are NOT materialised (fused into the KLT kernel).
+#include "kernels.cuh"
+
+#define TILE 64
+
+__global__ void __launch_bounds__(256) pyr_halfsample_kernel(ImageSetDev s)
+{
+    __shared__ __align__(16) uint8_t t0[TILE * TILE];           // level 0 tile
+    __shared__ __align__(16) uint8_t tl[TILE / 2 * TILE / 2 + TILE / 4 * TILE / 4 + 256];  // coarser tiles, ping-pong free (sizes shrink)
+
+    const int tx0 = blockIdx.x * TILE, ty0 = blockIdx.y * TILE;
+    const LevelDesc L0 = s.left[0];
+    const int tid = threadIdx.x;
+
+    // ---- stage level 0 (16-byte vector loads when the row is aligned, zero fill outside the image)
+    const bool vec_ok = ((L0.pitch & 15) == 0) && ((reinterpret_cast<uintptr_t>(L0.ptr) & 15) == 0);
+    for (int i = tid; i < TILE * TILE / 16; i += blockDim.x) {
+        int r = i / (TILE / 16), c16 = (i % (TILE / 16)) * 16;
+        int gy = ty0 + r, gx = tx0 + c16;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (gy < L0.h) {
+            if (vec_ok && gx + 16 <= L0.w) {
+                v = __ldg(reinterpret_cast<const uint4 *>(L0.ptr + (size_t)gy * L0.pitch + gx));
+            } else {
+                uint8_t b[16];
+#pragma unroll
+                for (int k = 0; k < 16; k++) b[k] = (gx + k < L0.w) ? __ldg(L0.ptr + (size_t)gy * L0.pitch + gx + k) : 0;
+                v = *reinterpret_cast<uint4 *>(b);
+            }
+        }
+        *reinterpret_cast<uint4 *>(&t0[r * TILE + c16]) = v;
+    }
+    __syncthreads();
+
+    // ---- reduce level by level inside the tile
+    const uint8_t *src = t0;
+    int sw = TILE;  // source tile width/height
+    uint8_t *dst = tl;
+    for (int l = 1; l < s.n_levels; l++) {
+        const int dw = sw >> 1;
+        if (dw == 0) break;
+        const LevelDesc D = s.left[l];
+        const int gx0 = tx0 >> l, gy0 = ty0 >> l;
+        for (int i = tid; i < dw * dw; i += blockDim.x) {
+            int r = i / dw, c = i % dw;
+            const uint8_t *p = src + (2 * r) * sw + 2 * c;
+            uint8_t v = (uint8_t)((p[0] + p[1] + p[sw] + p[sw + 1]) / 4);
+            dst[r * dw + c] = v;
+            int gx = gx0 + c, gy = gy0 + r;
+            if (gx < D.w && gy < D.h) D.ptr[(size_t)gy * D.pitch + gx] = v;
+        }
+        __syncthreads();
+        src = dst;
+        dst = dst + dw * dw;
+        sw = dw;
+    }
+}
+
+void launch_pyr_halfsample(const ImageSetDev &s, cudaStream_t st)
+{
+    if (s.n_levels <= 1) return;
+    dim3 grid((s.left[0].w + TILE - 1) / TILE, (s.left[0].h + TILE - 1) / TILE);
+    pyr_halfsample_kernel<<<grid, 256, 0, st>>>(s);
+}
+
+// level 0 of the LK pyramid: copy of `left` with a REFLECT_101 frame of SVO_LK_PAD px
+__global__ void __launch_bounds__(256) lk_pad_level0_kernel(LevelDesc src, LevelDesc dst)
+{
+    const int PW = dst.w + 2 * SVO_LK_PAD, PH = dst.h + 2 * SVO_LK_PAD;
+    int xp = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    int yp = blockIdx.y;
+    if (xp >= PW || yp >= PH) return;
+    int y = dev_reflect101(yp - SVO_LK_PAD, dst.h);
+    const uint8_t *srow = src.ptr + (size_t)y * src.pitch;
+    uint8_t *drow = dst.ptr + ((ptrdiff_t)(yp - SVO_LK_PAD)) * dst.pitch - SVO_LK_PAD;
+    uint8_t b[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) b[k] = srow[dev_reflect101(xp + k - SVO_LK_PAD, dst.w)];
+    if (xp + 4 <= PW) *reinterpret_cast<uchar4 *>(drow + xp) = make_uchar4(b[0], b[1], b[2], b[3]);
+    else
+        for (int k = 0; k < 4 && xp + k < PW; k++) drow[xp + k] = b[k];
+}
+
+// cv::pyrDown of a padded level into the next padded level (interior AND border: border pixels are the
+// REFLECT_101 image of interior ones, recomputed instead of copied)
+__global__ void __launch_bounds__(256) lk_pyrdown_kernel(LevelDesc src, LevelDesc dst)
+{
+    const int PW = dst.w + 2 * SVO_LK_PAD, PH = dst.h + 2 * SVO_LK_PAD;
+    int xp = blockIdx.x * blockDim.x + threadIdx.x;
+    int yp = blockIdx.y;
+    if (xp >= PW || yp >= PH) return;
+    int x = dev_reflect101(xp - SVO_LK_PAD, dst.w), y = dev_reflect101(yp - SVO_LK_PAD, dst.h);
+    // taps 2x-2..2x+2 reach at most 2 px outside the source level: inside its reflected frame
+    const uint8_t *p = src.ptr + (ptrdiff_t)(2 * y - 2) * src.pitch + (2 * x - 2);
+    int acc = 0;
+    const int wgt[5] = {1, 4, 6, 4, 1};
+#pragma unroll
+    for (int r = 0; r < 5; r++) {
+        const uint8_t *q = p + (ptrdiff_t)r * src.pitch;
+        int row = q[0] + q[4] + 4 * (q[1] + q[3]) + 6 * q[2];
+        acc += wgt[r] * row;
+    }
+    dst.ptr[(ptrdiff_t)(yp - SVO_LK_PAD) * dst.pitch + (xp - SVO_LK_PAD)] = (uint8_t)((acc + 128) >> 8);
+}
+
+void launch_lk_pyramid(const ImageSetDev &s, cudaStream_t st)
+{
+    {
+        const LevelDesc &d = s.lk[0];
+        int PW = d.w + 2 * SVO_LK_PAD, PH = d.h + 2 * SVO_LK_PAD;
+        dim3 grid((PW / 4 + 1 + 255) / 256, PH);
+        lk_pad_level0_kernel<<<grid, 256, 0, st>>>(s.left[0], d);
+    }
+    for (int l = 1; l < SVO_LK_LEVELS; l++) {
+        const LevelDesc &d = s.lk[l];
+        int PW = d.w + 2 * SVO_LK_PAD, PH = d.h + 2 * SVO_LK_PAD;
+        dim3 grid((PW + 255) / 256, PH);
+        lk_pyrdown_kernel<<<grid, 256, 0, st>>>(s.lk[l - 1], d);
+    }
+}
+
+int pyr_launch_count(const ImageSetDev &s) { return (s.n_levels > 1 ? 1 : 0) + SVO_LK_LEVELS; }

@@ -1,0 +1,572 @@
+// Host facade: the reference's StereoSlam (src/lib/stereo_slam.cpp, src/include/stereo_slam.hpp:27-79)
+// re-implemented on top of the svo_* device C-ABI only.  This file contains no CUDA: it owns the
+// bookkeeping the reference does on the CPU between device stages — keypoint compaction
+// (remove_outliers, stereo_slam.cpp:43-56), keyframe store and keyframe decision (keyframe_manager.cpp),
+// cross-level keypoint selection / merge (depth_calculator.cpp:37-130), 3-D initialisation of new keypoints
+// (:240-289), write-back into origin keyframes (stereo_slam.cpp:205-226), the 12-state motion Kalman filter
+// (:29-41, :296-359) and the trajectory.  Keyframe ids are per instance (the reference's process-global
+// statics, depth_calculator.cpp:135 / keyframe_manager.cpp:8, would break multi-sequence use).
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+#include "../../include/svo_cuda.h"
+
+namespace {
+
+// ---- cv::Rodrigues semantics (double inside, float out) -------------------------------------------------
+void rodrigues_f(const float r[3], float R[9])
+{
+    double rx = r[0], ry = r[1], rz = r[2];
+    double theta = std::sqrt(rx * rx + ry * ry + rz * rz);
+    double Rd[9];
+    if (theta < 2.220446049250313e-16) {
+        for (int k = 0; k < 9; k++) Rd[k] = (k % 4 == 0) ? 1.0 : 0.0;
+    } else {
+        double c = std::cos(theta), s = std::sin(theta), c1 = 1. - c, it = 1. / theta;
+        rx *= it; ry *= it; rz *= it;
+        double rrt[9] = {rx * rx, rx * ry, rx * rz, rx * ry, ry * ry, ry * rz, rx * rz, ry * rz, rz * rz};
+        double r_x[9] = {0, -rz, ry, rz, 0, -rx, -ry, rx, 0};
+        for (int k = 0; k < 9; k++) Rd[k] = c * ((k % 4 == 0) ? 1.0 : 0.0) + c1 * rrt[k] + s * r_x[k];
+    }
+    for (int k = 0; k < 9; k++) R[k] = (float)Rd[k];
+}
+
+inline void m33v(const float M[9], const float v[3], float o[3])
+{
+    float t[3];
+    for (int i = 0; i < 3; i++) {
+        float s = 0;
+        for (int k = 0; k < 3; k++) s += M[i * 3 + k] * v[k];
+        t[i] = s;
+    }
+    o[0] = t[0]; o[1] = t[1]; o[2] = t[2];
+}
+
+// ---- cv::KalmanFilter (float matrices, products accumulated in double like cv::gemm) -----------------
+struct MotionFilter {
+    static const int N = 12;
+    float A[N * N], Q[N * N], R[N * N], Ppre[N * N], Ppost[N * N], xpre[N], xpost[N];
+    MotionFilter()
+    {
+        std::memset(this, 0, sizeof(*this));
+        for (int i = 0; i < N; i++) {
+            A[i * N + i] = 1;            // transitionMatrix = I      (stereo_slam.cpp:34)
+            Q[i * N + i] = 100.0f;       // processNoiseCov = 100 I   (:37)
+            R[i * N + i] = 1;            // KalmanFilter::init default
+            Ppost[i * N + i] = 1.0f;     // errorCovPost = I          (:38)
+        }
+    }
+    static void mul(const float *a, const float *b, const float *c, float *d, int m, int k, int n, bool tb, double alpha)
+    {
+        std::vector<float> tmp((size_t)m * n);
+        for (int i = 0; i < m; i++)
+            for (int j = 0; j < n; j++) {
+                double s = 0;
+                for (int l = 0; l < k; l++) s += (double)a[i * k + l] * (tb ? b[j * k + l] : b[l * n + j]);
+                tmp[i * n + j] = (float)(c ? s * alpha + (double)c[i * n + j] : s * alpha);
+            }
+        std::memcpy(d, tmp.data(), sizeof(float) * m * n);
+    }
+    void predict()
+    {
+        mul(A, xpost, nullptr, xpre, N, N, 1, false, 1.0);
+        float t1[N * N];
+        mul(A, Ppost, nullptr, t1, N, N, N, false, 1.0);
+        mul(t1, A, Q, Ppre, N, N, N, true, 1.0);
+        std::memcpy(xpost, xpre, sizeof(xpre));
+        std::memcpy(Ppost, Ppre, sizeof(Ppre));
+    }
+    // measurementMatrix = I (stereo_slam.cpp:35): gain = Ppre (Ppre + R)^-1, solved by Gaussian elimination in double
+    void correct(const float z[N])
+    {
+        double S[N][N], B[N][N];  // S X = B with B = Ppre ; gain = X^T
+        for (int i = 0; i < N; i++)
+            for (int j = 0; j < N; j++) {
+                S[i][j] = (double)(float)((double)Ppre[i * N + j] + (double)R[i * N + j]);
+                B[i][j] = Ppre[i * N + j];
+            }
+        for (int c = 0; c < N; c++) {
+            int p = c;
+            for (int r = c + 1; r < N; r++) if (std::fabs(S[r][c]) > std::fabs(S[p][c])) p = r;
+            if (p != c) for (int j = 0; j < N; j++) { std::swap(S[p][j], S[c][j]); std::swap(B[p][j], B[c][j]); }
+            double d = S[c][c];
+            if (d == 0) continue;
+            for (int r = 0; r < N; r++) {
+                if (r == c) continue;
+                double f = S[r][c] / d;
+                if (f == 0) continue;
+                for (int j = 0; j < N; j++) { S[r][j] -= f * S[c][j]; B[r][j] -= f * B[c][j]; }
+            }
+        }
+        float K[N * N];
+        for (int i = 0; i < N; i++)
+            for (int j = 0; j < N; j++) K[j * N + i] = (float)(S[i][i] != 0 ? B[i][j] / S[i][i] : 0.0);  // gain = X^T
+        float t5[N];
+        for (int i = 0; i < N; i++) t5[i] = (float)(-(double)xpre[i] + (double)z[i]);
+        mul(K, t5, xpre, xpost, N, N, 1, false, 1.0);
+        mul(K, Ppre, Ppre, Ppost, N, N, N, false, -1.0);
+    }
+};
+
+struct KeyPoints {
+    std::vector<float> kps2d, kps3d;
+    std::vector<svo_keypoint_info> info;
+    size_t size() const { return info.size(); }
+    void clear() { kps2d.clear(); kps3d.clear(); info.clear(); }
+};
+
+struct FrameH {
+    uint64_t id = 0;
+    float pose[6] = {0, 0, 0, 0, 0, 0};
+    int slot = -1;
+    KeyPoints kps;
+    double time_stamp = 0;
+};
+
+}  // namespace
+
+struct svo_slam {
+    svo_camera_settings cs;
+    int W = 0, H = 0;
+    svo_ctx *ctx = nullptr;
+    std::vector<std::unique_ptr<FrameH>> keyframes;
+    std::unique_ptr<FrameH> frame, previous;
+    std::vector<svo_pose> trajectory;
+    float motion[6] = {0, 0, 0, 0, 0, 0};
+    MotionFilter kf;
+    uint32_t rng = 0x2545F491u;
+    char err[256] = "";
+    // per-frame scratch (reused)
+    svo_track_io io;
+    std::vector<float> io_prev2d, io_kps3d, io_ref2d, io_kfstate, io_kps2d;
+    std::vector<int> io_kfid, io_inl, io_outl;
+    std::vector<uint8_t> io_flags;
+    bool pending = false;
+    bool pending_first = false;
+    int last_keyframe_created = 0;
+    float last_gpu_ms = 0;
+    int last_launches = 0;
+
+    int fail(int rc)
+    {
+        snprintf(err, sizeof(err), "%s", svo_last_error(ctx));
+        return rc;
+    }
+
+    // ---- DepthCalculator host parts -------------------------------------------------------------------------
+    // depth_calculator.cpp:67-86
+    void find_bad_keypoints(FrameH &f)
+    {
+        KeyPoints o;
+        for (size_t i = 0; i < f.kps.size(); i++) {
+            float x = f.kps.kps2d[2 * i], y = f.kps.kps2d[2 * i + 1];
+            const svo_keypoint_info &in = f.kps.info[i];
+            if ((x < 0) || (y < 0) || (x > W) || (y > H) || in.ignore_completely || in.ignore_during_refinement) continue;
+            o.kps2d.push_back(x); o.kps2d.push_back(y);
+            for (int k = 0; k < 3; k++) o.kps3d.push_back(f.kps.kps3d[3 * i + k]);
+            o.info.push_back(in);
+        }
+        f.kps = std::move(o);
+    }
+
+    // depth_calculator.cpp:11-65: per-level detection on the device, cross-level choice by cell index on the host
+    int detect_and_select(int slot, std::vector<float> &kps, std::vector<svo_keypoint_info> &info)
+    {
+        int gw = cs.grid_width, gh = cs.grid_height;
+        const int nl = cs.max_pyramid_levels / 2;  // `left.size()/2`
+        kps.clear(); info.clear();
+        for (int lv = 0; lv < nl; lv++) {
+            if (gw < 1 || gh < 1) break;
+            int lw, lh;
+            svo_slot_level_size(ctx, 0, lv, &lw, &lh);
+            int cap = (lw / gw + 1) * (lh / gh + 1) + 4;
+            std::vector<float> xy((size_t)cap * 2), sc(cap);
+            std::vector<int> ty(cap);
+            int n = 0;
+            int rc = svo_detect_keypoints(ctx, slot, lv, gw, gh, cap, xy.data(), sc.data(), ty.data(), &n);
+            if (rc) return rc;
+            if (lv == 0) {
+                kps.assign(xy.begin(), xy.begin() + 2 * n);
+                info.resize(n);
+                for (int j = 0; j < n; j++) {
+                    std::memset(&info[j], 0, sizeof(svo_keypoint_info));
+                    info[j].score = sc[j]; info[j].type = ty[j]; info[j].level = 0;
+                }
+            } else {
+                for (size_t j = 0; j < info.size(); j++) {
+                    if ((int)j >= n) continue;  // reference reads past the coarser level's list here (Q7)
+                    if (info[j].type == SVO_KP_FAST && ty[j] == SVO_KP_EDGELET) continue;
+                    if ((info[j].type == ty[j]) && (info[j].score > sc[j])) continue;
+                    kps[2 * j] = xy[2 * j] * (float)(1 << lv);
+                    kps[2 * j + 1] = xy[2 * j + 1] * (float)(1 << lv);
+                    info[j].score = sc[j]; info[j].type = ty[j]; info[j].level = lv;
+                }
+            }
+            gw /= 2; gh /= 2;
+        }
+        return SVO_OK;
+    }
+
+    // depth_calculator.cpp:88-130 — called with (grid_width, grid_height) bound to (grid_height, grid_width): Q6
+    void merge_keypoints(FrameH &f, const std::vector<float> &nk, const std::vector<svo_keypoint_info> &ni, int grid_height, int grid_width)
+    {
+        auto &k2 = f.kps.kps2d;
+        auto &info = f.kps.info;
+        for (int x = 0; x < W; x += grid_width) {
+            int left = x, right = left + grid_width;
+            for (int y = 0; y < H; y += grid_height) {
+                int top = y, bottom = y + grid_height;
+                bool match = false;
+                for (size_t i = 0; i < info.size(); i++) {
+                    float kx = k2[2 * i], ky = k2[2 * i + 1];
+                    if (kx > left && kx < right && ky > top && ky < bottom) { match = true; break; }
+                }
+                if (match) continue;
+                for (size_t i = 0; i < ni.size(); i++) {
+                    float kx = nk[2 * i], ky = nk[2 * i + 1];
+                    if (kx > left && kx < right && ky > top && ky < bottom) {
+                        k2.push_back(kx); k2.push_back(ky);
+                        info.push_back(ni[i]);
+                    }
+                }
+            }
+        }
+    }
+
+    // DepthCalculator::calculate_depth (depth_calculator.cpp:132-392) + KeyFrameManager::create_keyframe (keyframe_manager.cpp:15-32)
+    int create_keyframe(FrameH &f)
+    {
+        const float fx = cs.fx, fy = cs.fy, cx = cs.cx, cy = cs.cy, baseline = cs.baseline;
+        find_bad_keypoints(f);
+        std::vector<float> nk;
+        std::vector<svo_keypoint_info> ni;
+        int rc = detect_and_select(f.slot, nk, ni);
+        if (rc) return rc;
+        const size_t old_count = f.kps.size();
+        merge_keypoints(f, nk, ni, cs.grid_width, cs.grid_height);
+        const size_t n = f.kps.size();
+        f.kps.kps3d.resize(n * 3);
+        const size_t n_new = n - old_count;
+        std::vector<float> disp(n_new);
+        if (n_new > 0) {
+            rc = svo_stereo_match(ctx, f.slot, &f.kps.kps2d[2 * old_count], (int)n_new, 0, disp.data());
+            if (rc) return rc;
+        }
+        float R[9];
+        rodrigues_f(&f.pose[3], R);
+        const uint64_t kf_id = keyframes.size();
+        for (size_t i = old_count; i < n; i++) {
+            const float kx = f.kps.kps2d[2 * i], ky = f.kps.kps2d[2 * i + 1];
+            const float disparity = disp[i - old_count];
+            float _z = baseline / std::max<float>(0.5, disparity);
+            float _x = (kx - cx) / fx * _z;
+            float _y = (ky - cy) / fy * _z;
+            float loc[3] = {_x, _y, _z}, w3[3];
+            m33v(R, loc, w3);
+            for (int k = 0; k < 3; k++) f.kps.kps3d[3 * i + k] = w3[k] + f.pose[k];
+            svo_keypoint_info &in = f.kps.info[i];
+            rng = rng * 1664525u + 1013904223u;
+            in.color[0] = (rng >> 8) & 0xFF; in.color[1] = (rng >> 16) & 0xFF; in.color[2] = (rng >> 24) & 0xFF;
+            in.keyframe_id = kf_id;
+            in.keypoint_index = i;
+            in.ignore_completely = 0; in.ignore_temporary = 1; in.ignore_during_refinement = 0;
+            in.inlier_count = 0; in.outlier_count = 0;
+            float deviation = (float)(0.5 / (baseline / fx));  // depth_calculator.cpp:284-289
+            in.kf_variance = deviation * deviation;
+            in.kf_inv_depth = 1 / _z;
+        }
+        std::unique_ptr<FrameH> k(new FrameH());
+        k->id = kf_id;
+        std::memcpy(k->pose, f.pose, sizeof(f.pose));
+        k->slot = f.slot;
+        k->kps = f.kps;
+        k->time_stamp = f.time_stamp;
+        int id = -1;
+        rc = svo_keyframe_commit(ctx, f.slot, f.pose, &id);  // retains the slot
+        if (rc) return rc;
+        if ((uint64_t)id != kf_id) { snprintf(err, sizeof(err), "keyframe id mismatch"); return SVO_ERR_STATE; }
+        keyframes.push_back(std::move(k));
+        last_keyframe_created = 1;
+        return SVO_OK;
+    }
+
+    // keyframe_manager.cpp:47-74
+    bool keyframe_needed(const FrameH &f) const
+    {
+        int inside = 0;
+        for (size_t i = 0; i < f.kps.size(); i++) {
+            float x = f.kps.kps2d[2 * i], y = f.kps.kps2d[2 * i + 1];
+            if ((x > 0) && (y > 0) && (x < W) && (y < H) && !f.kps.info[i].ignore_completely) inside++;
+        }
+        int max_kps = (W / cs.grid_width) * (H / cs.grid_height);
+        return inside < 0.66 * max_kps;
+    }
+
+    // StereoSlam::update_pose (stereo_slam.cpp:296-359)
+    void update_pose(const float pose[6], const float speed[6], const float pv[6], const float sv[6], double dt, float out[6])
+    {
+        for (int i = 0; i < 6; i++) kf.A[i * 12 + (i + 6)] = (float)dt;
+        kf.predict();
+        for (int i = 0; i < 6; i++) { kf.R[i * 12 + i] = pv[i]; kf.R[(i + 6) * 12 + (i + 6)] = sv[i]; }
+        float z[12];
+        for (int i = 0; i < 6; i++) { z[i] = pose[i]; z[i + 6] = speed[i]; }
+        kf.correct(z);
+        for (int i = 0; i < 6; i++) out[i] = kf.xpost[i];
+    }
+
+    void finish_frame()
+    {
+        // stereo_slam.cpp:250-270
+        if (previous) {
+            double dt = frame->time_stamp - previous->time_stamp;
+            for (int i = 0; i < 6; i++) motion[i] = (float)((double)(frame->pose[i] - previous->pose[i]) * (1. / dt));
+            float pv[6] = {0.1f, 0.1f, 0.1f, 0.1f, 0.1f, 0.1f}, mv[6] = {1, 1, 1, 1, 1, 1}, fp[6];
+            update_pose(frame->pose, motion, pv, mv, 0.0, fp);
+            std::memcpy(frame->pose, fp, sizeof(fp));
+            svo_slot_release(ctx, previous->slot);
+            previous.reset();
+        }
+        svo_pose p = {frame->pose[0], frame->pose[1], frame->pose[2], frame->pose[3], frame->pose[4], frame->pose[5]};
+        trajectory.push_back(p);
+    }
+
+    int new_image_begin(const uint8_t *left, size_t ls, const uint8_t *right, size_t rs, float ts)
+    {
+        if (pending) { snprintf(err, sizeof(err), "new_image_begin called twice"); return SVO_ERR_STATE; }
+        last_keyframe_created = 0;
+        previous = std::move(frame);
+        frame.reset(new FrameH());
+        frame->time_stamp = ts;
+        int rc = svo_upload_stereo(ctx, left, ls, right, rs, &frame->slot);  // pyramids (stereo_slam.cpp:135-139)
+        if (rc) return fail(rc);
+        pending = true;
+        if (!previous) {  // first frame (stereo_slam.cpp:142-160)
+            frame->id = 0;
+            pending_first = true;
+            return SVO_OK;
+        }
+        pending_first = false;
+        frame->id = previous->id + 1;
+        for (int i = 0; i < 6; i++) frame->pose[i] = kf.xpre[i];  // kf.statePre (Q8)
+        // remove_outliers (stereo_slam.cpp:43-56)
+        {
+            KeyPoints u;
+            for (size_t i = 0; i < previous->kps.size(); i++) {
+                if (previous->kps.info[i].ignore_completely) continue;
+                u.kps2d.push_back(previous->kps.kps2d[2 * i]); u.kps2d.push_back(previous->kps.kps2d[2 * i + 1]);
+                for (int k = 0; k < 3; k++) u.kps3d.push_back(previous->kps.kps3d[3 * i + k]);
+                u.info.push_back(previous->kps.info[i]);
+            }
+            previous->kps = std::move(u);
+        }
+        const size_t n = previous->kps.size();
+        io_prev2d = previous->kps.kps2d;
+        io_kps3d = previous->kps.kps3d;
+        io_ref2d.resize(n * 2); io_kfid.resize(n); io_flags.resize(n); io_inl.resize(n); io_outl.resize(n); io_kfstate.resize(n * 2);
+        io_kps2d.resize(n * 2);
+        for (size_t i = 0; i < n; i++) {
+            const svo_keypoint_info &in = previous->kps.info[i];
+            const FrameH &k = *keyframes[in.keyframe_id];
+            io_ref2d[2 * i] = k.kps.kps2d[2 * in.keypoint_index];
+            io_ref2d[2 * i + 1] = k.kps.kps2d[2 * in.keypoint_index + 1];
+            io_kfid[i] = (int)in.keyframe_id;
+            io_flags[i] = (uint8_t)((in.ignore_during_refinement ? 1 : 0) | (in.ignore_completely ? 2 : 0) | (in.ignore_temporary ? 4 : 0));
+            io_inl[i] = in.inlier_count; io_outl[i] = in.outlier_count;
+            io_kfstate[2 * i] = in.kf_inv_depth; io_kfstate[2 * i + 1] = in.kf_variance;
+        }
+        std::memset(&io, 0, sizeof(io));
+        io.n = (int)n;
+        io.prev_kps2d = io_prev2d.data(); io.kps3d = io_kps3d.data(); io.ref_kps2d = io_ref2d.data(); io.keyframe_id = io_kfid.data();
+        io.flags = io_flags.data(); io.inlier_count = io_inl.data(); io.outlier_count = io_outl.data(); io.kf_state = io_kfstate.data();
+        io.kps2d = io_kps2d.data();
+        std::memcpy(io.pose_prior, frame->pose, sizeof(io.pose_prior));
+        rc = svo_track_frame_begin(ctx, previous->slot, frame->slot, &io);
+        if (rc) { pending = false; return fail(rc); }
+        return SVO_OK;
+    }
+
+    int new_image_end()
+    {
+        if (!pending) { snprintf(err, sizeof(err), "new_image_end without begin"); return SVO_ERR_STATE; }
+        pending = false;
+        int rc;
+        if (pending_first) {
+            rc = create_keyframe(*frame);
+            if (rc) return rc == SVO_ERR_STATE ? rc : fail(rc);
+            for (auto &in : frame->kps.info) in.ignore_temporary = 0;  // stereo_slam.cpp:157-159
+            last_gpu_ms = 0; last_launches = 0;
+            finish_frame();
+            return SVO_OK;
+        }
+        rc = svo_track_frame_end(ctx, &io);
+        if (rc) return fail(rc);
+        svo_last_track_timing(ctx, &last_gpu_ms, &last_launches);
+        const size_t n = (size_t)io.n;
+        std::memcpy(frame->pose, io.pose_refined, sizeof(frame->pose));
+        frame->kps.info = previous->kps.info;
+        frame->kps.kps3d = io_kps3d;
+        frame->kps.kps2d = io_kps2d;
+        // flags / counters / filter state come back from the device; write back into the origin keyframes
+        // (stereo_slam.cpp:205-226)
+        for (size_t i = 0; i < n; i++) {
+            svo_keypoint_info &in = frame->kps.info[i];
+            in.ignore_during_refinement = (io_flags[i] & 1) ? 1 : 0;
+            in.ignore_completely = (io_flags[i] & 2) ? 1 : 0;
+            in.ignore_temporary = (io_flags[i] & 4) ? 1 : 0;
+            in.inlier_count = io_inl[i]; in.outlier_count = io_outl[i];
+            in.kf_inv_depth = io_kfstate[2 * i]; in.kf_variance = io_kfstate[2 * i + 1];
+            FrameH &k = *keyframes[in.keyframe_id];
+            for (int q = 0; q < 3; q++) k.kps.kps3d[3 * in.keypoint_index + q] = io_kps3d[3 * i + q];
+            svo_keypoint_info &ki = k.kps.info[in.keypoint_index];
+            ki.ignore_temporary = in.ignore_temporary; ki.ignore_completely = in.ignore_completely;
+            ki.inlier_count = in.inlier_count; ki.outlier_count = in.outlier_count;
+            ki.kf_inv_depth = in.kf_inv_depth; ki.kf_variance = in.kf_variance;  // cv::KalmanFilter copies share state (Q13)
+        }
+        if (keyframe_needed(*frame)) {  // stereo_slam.cpp:231-246
+            rc = create_keyframe(*frame);
+            if (rc) return rc == SVO_ERR_STATE ? rc : fail(rc);
+            size_t c = 0;
+            for (auto &in : frame->kps.info) if (!in.ignore_temporary) c++;
+            if (c < frame->kps.info.size() / 4)
+                for (auto &in : frame->kps.info) in.ignore_temporary = 0;
+        }
+        finish_frame();
+        return SVO_OK;
+    }
+};
+
+// ================================================================================================ C exports
+extern "C" {
+
+static char g_slam_create_err[256] = "";
+
+int svo_slam_create(const svo_camera_settings *settings, int device, int width, int height, svo_slam **out)
+{
+    if (!settings || !out) return SVO_ERR_INVALID;
+    svo_slam *s = new svo_slam();
+    s->cs = *settings; s->W = width; s->H = height;
+    int rc = svo_ctx_create(settings, device, width, height, 0, &s->ctx);
+    if (rc) {
+        snprintf(g_slam_create_err, sizeof(g_slam_create_err), "%s", svo_last_error(nullptr));
+        delete s;
+        return rc;
+    }
+    *out = s;
+    return SVO_OK;
+}
+
+int svo_slam_destroy(svo_slam *s)
+{
+    if (!s) return SVO_ERR_INVALID;
+    if (s->ctx) svo_ctx_destroy(s->ctx);
+    delete s;
+    return SVO_OK;
+}
+
+const char *svo_slam_last_error(svo_slam *s) { return s ? s->err : g_slam_create_err; }
+svo_ctx *svo_slam_ctx(svo_slam *s) { return s ? s->ctx : nullptr; }
+
+int svo_slam_new_image_begin(svo_slam *s, const uint8_t *left, size_t ls, const uint8_t *right, size_t rs, float ts)
+{
+    if (!s || !left || !right) return SVO_ERR_INVALID;
+    return s->new_image_begin(left, ls, right, rs, ts);
+}
+int svo_slam_new_image_end(svo_slam *s)
+{
+    if (!s) return SVO_ERR_INVALID;
+    return s->new_image_end();
+}
+int svo_slam_new_image(svo_slam *s, const uint8_t *left, size_t ls, const uint8_t *right, size_t rs, float ts)
+{
+    int rc = svo_slam_new_image_begin(s, left, ls, right, rs, ts);
+    if (rc) return rc;
+    return svo_slam_new_image_end(s);
+}
+
+static int frame_meta(const FrameH *f, uint64_t *id, svo_pose *pose, double *ts, int *n)
+{
+    if (!f) return SVO_ERR_STATE;
+    if (id) *id = f->id;
+    if (pose) { pose->x = f->pose[0]; pose->y = f->pose[1]; pose->z = f->pose[2]; pose->rx = f->pose[3]; pose->ry = f->pose[4]; pose->rz = f->pose[5]; }
+    if (ts) *ts = f->time_stamp;
+    if (n) *n = (int)f->kps.size();
+    return SVO_OK;
+}
+static int frame_kps(const FrameH *f, int max, float *k2, float *k3, svo_keypoint_info *info)
+{
+    if (!f) return SVO_ERR_STATE;
+    size_t n = std::min<size_t>(f->kps.size(), (size_t)std::max(0, max));
+    if (k2) std::memcpy(k2, f->kps.kps2d.data(), n * 8);
+    if (k3) std::memcpy(k3, f->kps.kps3d.data(), n * 12);
+    if (info) std::memcpy(info, f->kps.info.data(), n * sizeof(svo_keypoint_info));
+    return SVO_OK;
+}
+
+int svo_slam_get_frame(svo_slam *s, uint64_t *id, svo_pose *pose, double *ts, int *n)
+{
+    if (!s) return SVO_ERR_INVALID;
+    return frame_meta(s->frame.get(), id, pose, ts, n);
+}
+int svo_slam_get_frame_keypoints(svo_slam *s, int max, float *k2, float *k3, svo_keypoint_info *info)
+{
+    if (!s) return SVO_ERR_INVALID;
+    return frame_kps(s->frame.get(), max, k2, k3, info);
+}
+int svo_slam_get_frame_image(svo_slam *s, int kind, int level, uint8_t *out, size_t stride)
+{
+    if (!s || !s->frame) return SVO_ERR_STATE;
+    return svo_download_level(s->ctx, s->frame->slot, kind, level, out, stride);
+}
+int svo_slam_keyframe_count(svo_slam *s) { return s ? (int)s->keyframes.size() : 0; }
+static const FrameH *kf_at(svo_slam *s, int index)
+{
+    if (!s || s->keyframes.empty()) return nullptr;
+    if (index < 0) index = (int)s->keyframes.size() - 1;
+    if (index >= (int)s->keyframes.size()) return nullptr;
+    return s->keyframes[index].get();
+}
+int svo_slam_get_keyframe(svo_slam *s, int index, uint64_t *id, svo_pose *pose, double *ts, int *n)
+{
+    if (!s) return SVO_ERR_INVALID;
+    return frame_meta(kf_at(s, index), id, pose, ts, n);
+}
+int svo_slam_get_keyframe_keypoints(svo_slam *s, int index, int max, float *k2, float *k3, svo_keypoint_info *info)
+{
+    if (!s) return SVO_ERR_INVALID;
+    return frame_kps(kf_at(s, index), max, k2, k3, info);
+}
+int svo_slam_get_keyframe_image(svo_slam *s, int index, int kind, int level, uint8_t *out, size_t stride)
+{
+    const FrameH *k = kf_at(s, index);
+    if (!k) return SVO_ERR_STATE;
+    return svo_download_level(s->ctx, k->slot, kind, level, out, stride);
+}
+int svo_slam_get_trajectory(svo_slam *s, int max, svo_pose *out)
+{
+    if (!s) return 0;
+    size_t n = std::min<size_t>(s->trajectory.size(), (size_t)std::max(0, max));
+    if (out && n) std::memcpy(out, s->trajectory.data(), n * sizeof(svo_pose));
+    return (int)s->trajectory.size();
+}
+int svo_slam_update_pose(svo_slam *s, const svo_pose *pose, const float speed[6], const float pv[6], const float sv[6], double dt,
+                         svo_pose *filtered)
+{
+    if (!s || !pose || !speed || !pv || !sv) return SVO_ERR_INVALID;
+    float p[6] = {pose->x, pose->y, pose->z, pose->rx, pose->ry, pose->rz}, o[6];
+    s->update_pose(p, speed, pv, sv, dt, o);
+    if (filtered) { filtered->x = o[0]; filtered->y = o[1]; filtered->z = o[2]; filtered->rx = o[3]; filtered->ry = o[4]; filtered->rz = o[5]; }
+    return SVO_OK;
+}
+int svo_slam_last_stats(svo_slam *s, float *gpu_ms, int *launches, int *keyframe_created)
+{
+    if (!s) return SVO_ERR_INVALID;
+    if (gpu_ms) *gpu_ms = s->last_gpu_ms;
+    if (launches) *launches = s->last_launches;
+    if (keyframe_created) *keyframe_created = s->last_keyframe_created;
+    return SVO_OK;
+}
+}  // extern "C"

@@ -1,0 +1,252 @@
+// Stereo SSD patch matching and the per-point depth filter.
+//
+// stereo_ssd_kernel replaces the template match in DepthCalculator::calculate_depth
+// (src/lib/depth_calculator.cpp:200-239, mode 0) and DepthFilter::calculate_disparities
+// (src/lib/depth_filter.cpp:259-327, mode 1): cv::matchTemplate(TM_SQDIFF) + cv::minMaxLoc + the
+// "mean column of the tied minima right/below the first minimum" rule.  The SSD is computed as exact
+// uint32 (the mathematical definition of TM_SQDIFF; OpenCV's float map carries +-40 units of DFT noise,
+// SURVEY.md Appendix B.5), so the result is bit-identical to the integer oracle.
+//   One CTA per keypoint; template and search ROI staged in shared memory; each thread owns result-map
+//   positions; arg-min by a (value, raster index) lexicographic block reduction = "first minimum in raster order".
+//   Bound: integer ALU / shared-memory bandwidth (~640 k multiply-adds per keypoint), not HBM.
+//
+// depth_filter_kernel replaces DepthFilter::outlier_check (:52-128), DepthFilter::update_kps3d (:130-257),
+// the flag post-processing in StereoSlam::new_image (src/lib/stereo_slam.cpp:205-226) and the final
+// re-projection (:228-229).  One thread per keypoint, reference float operation order.
+#include "kernels.cuh"
+
+#define SSD_THREADS 256
+
+struct SsdGeom { int x11, x12, y11, y12, x21, x22, y21, y22; };
+
+// window clipping rules of depth_calculator.cpp:205-214 / depth_filter.cpp:281-301; returns false => disparity -1
+__device__ __forceinline__ bool ssd_geometry(float kx, float ky, int W, int H, int win, int sx, int sy, int mode, SsdGeom &g)
+{
+    const int wb = win / 2, wa = (win + 1) / 2;
+    const int x = (int)kx, y = (int)ky;
+    g.x11 = max(0, x - wb); g.x12 = min(W - 1, x + wa);
+    g.y11 = max(0, y - wb); g.y12 = min(H, y + wa);
+    if (mode == 1 && (g.x12 <= 0 || g.y12 <= 0 || g.x11 >= (W - 1) || g.y11 >= (H - 1))) return false;
+    g.x21 = max(0, x - wb); g.x22 = min(W - 1, x + wa + sx);
+    g.y21 = max(0, y - wb - sy); g.y22 = min(H - 1, y + wa + sy);
+    if (mode == 1 && (g.x22 <= 0 || g.y22 <= 0 || g.x21 >= (W - 1) || g.y21 >= (H - 1))) return false;
+    const int tw = g.x12 - g.x11, th = g.y12 - g.y11, rw = g.x22 - g.x21, rh = g.y22 - g.y21;
+    if (tw <= 0 || th <= 0 || rw < tw || rh < th) return false;  // cv::matchTemplate would throw
+    return true;
+}
+
+__global__ void __launch_bounds__(SSD_THREADS) stereo_ssd_kernel(SsdArgs a, int tpitch, int rpitch, int map_cap)
+{
+    extern __shared__ __align__(16) uint8_t ssd_smem[];
+    const int win = a.cam.win_depth;
+    uint8_t *tpl = ssd_smem;                       // win rows x tpitch
+    uint8_t *roi = tpl + win * tpitch;             // (win + 2*sy) rows x rpitch
+    uint32_t *map = reinterpret_cast<uint32_t *>(roi + ((win + 2 * a.cam.search_y) * rpitch + 15) / 16 * 16);
+    __shared__ unsigned long long red[SSD_THREADS / 32];
+    __shared__ unsigned long long best_s;
+    __shared__ int cnt_s[SSD_THREADS / 32], sum_s[SSD_THREADS / 32];
+
+    const int i = blockIdx.x;
+    const int n = min(*a.n_ptr, a.max_kps);
+    if (i >= n) return;
+    const int tid = threadIdx.x;
+    const LevelDesc L = a.left0, R = a.right0;
+    SsdGeom g;
+    if (!ssd_geometry(a.kps2d[2 * i], a.kps2d[2 * i + 1], L.w, L.h, win, a.cam.search_x, a.cam.search_y, a.mode, g)) {
+        if (tid == 0) a.disparity[i] = -1.f;
+        return;
+    }
+    const int tw = g.x12 - g.x11, th = g.y12 - g.y11, rw = g.x22 - g.x21, rh = g.y22 - g.y21;
+    const int mw = rw - tw + 1, mh = rh - th + 1;
+
+    for (int k = tid; k < th * tw; k += SSD_THREADS) {
+        int r = k / tw, c = k - r * tw;
+        tpl[r * tpitch + c] = L.ptr[(size_t)(g.y11 + r) * L.pitch + g.x11 + c];
+    }
+    for (int k = tid; k < rh * rw; k += SSD_THREADS) {
+        int r = k / rw, c = k - r * rw;
+        roi[r * rpitch + c] = R.ptr[(size_t)(g.y21 + r) * R.pitch + g.x21 + c];
+    }
+    __syncthreads();
+
+    // ---- SSD map + running (value, index) minimum per thread
+    unsigned long long best = ~0ull;
+    for (int p = tid; p < mw * mh; p += SSD_THREADS) {
+        const int k = p / mw, j = p - k * mw;
+        uint32_t s = 0;
+        for (int y = 0; y < th; y++) {
+            const uint8_t *rr = roi + (k + y) * rpitch + j;
+            const uint8_t *tt = tpl + y * tpitch;
+            for (int x = 0; x < tw; x++) {
+                int d = (int)rr[x] - (int)tt[x];
+                s += (uint32_t)(d * d);
+            }
+        }
+        map[p] = s;
+        unsigned long long key = ((unsigned long long)s << 32) | (unsigned)p;
+        best = key < best ? key : best;
+    }
+    // block arg-min (smallest value, then smallest raster index == cv::minMaxLoc's first minimum)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long other = __shfl_down_sync(0xffffffffu, best, o);
+        best = other < best ? other : best;
+    }
+    if ((tid & 31) == 0) red[tid >> 5] = best;
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long b = red[0];
+        for (int w = 1; w < SSD_THREADS / 32; w++) b = red[w] < b ? red[w] : b;
+        best_s = b;
+    }
+    __syncthreads();
+    const uint32_t minv = (uint32_t)(best_s >> 32);
+    const int mp = (int)(best_s & 0xffffffffu);
+    const int mly = mp / mw, mlx = mp - mly * mw;
+    // ---- tie rule (depth_calculator.cpp:226-237): mean column index of entries <= min right/below the first minimum
+    int cnt = 0, sum = 0;
+    for (int p = tid; p < mw * mh; p += SSD_THREADS) {
+        const int k = p / mw, j = p - k * mw;
+        if (j >= mlx && k >= mly && map[p] <= minv) { cnt++; sum += j; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { cnt += __shfl_down_sync(0xffffffffu, cnt, o); sum += __shfl_down_sync(0xffffffffu, sum, o); }
+    if ((tid & 31) == 0) { cnt_s[tid >> 5] = cnt; sum_s[tid >> 5] = sum; }
+    __syncthreads();
+    if (tid == 0) {
+        int c = 0, s = 0;
+        for (int w = 0; w < SSD_THREADS / 32; w++) { c += cnt_s[w]; s += sum_s[w]; }
+        float minPos = (float)s / (float)c;  // float sum of small integers is exact
+        a.disparity[i] = (a.mode == 1) ? fmaxf(0.5f, minPos) : minPos;
+    }
+}
+
+void launch_stereo_ssd(const SsdArgs &a, cudaStream_t st)
+{
+    if (a.max_kps <= 0) return;
+    const int win = a.cam.win_depth;
+    const int tpitch = (win + 3) & ~3;
+    const int rpitch = (win + a.cam.search_x + 3) & ~3;
+    const int rows = win + 2 * a.cam.search_y;
+    const int map_cap = (a.cam.search_x + 1) * (2 * a.cam.search_y + 1);
+    size_t smem = (size_t)win * tpitch + ((size_t)rows * rpitch + 15) / 16 * 16 + (size_t)map_cap * 4 + 16;
+    stereo_ssd_kernel<<<a.max_kps, SSD_THREADS, smem, st>>>(a, tpitch, rpitch, map_cap);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// depth filter
+// ---------------------------------------------------------------------------------------------------------
+struct FrameMats { float R[9]; double Rdn[9]; };
+
+__global__ void __launch_bounds__(128) depth_filter_kernel(FilterArgs a)
+{
+    __shared__ FrameMats fm;
+    const int n = min(*a.n_ptr, a.max_kps);
+    if (threadIdx.x == 0) {
+        const float *p = a.pose;
+        dev_rodrigues_f(p[3], p[4], p[5], fm.R);
+        dev_rodrigues_d(-p[3], -p[4], -p[5], fm.Rdn);
+    }
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const DevCam cam = a.cam;
+    const float fx = cam.fx, fy = cam.fy, cx = cam.cx, cy = cam.cy, baseline = cam.baseline;
+    const float *c2 = a.pose;  // frame translation
+    const float *kfp = a.kf_pose_table + (size_t)a.keyframe_ids[i] * 24;  // pose(6) R(9) Ri(9)
+    const float *c1 = kfp, *Rk = kfp + 6, *Rik = kfp + 15;
+    const float u = a.kps2d[2 * i], v = a.kps2d[2 * i + 1];
+    uint8_t flags = a.flags[i];
+    int inl = a.inlier[i], outl = a.outlier[i];
+    float P0 = a.kps3d[3 * i], P1 = a.kps3d[3 * i + 1], P2 = a.kps3d[3 * i + 2];
+
+    // ---- outlier_check (depth_filter.cpp:52-128)
+    {
+        const float d = a.disparity[i];
+        const float _z = baseline / fmaxf(d, 0.5f);
+        const float _x = (u - cx) / fx * _z;
+        const float _y = (v - cy) / fy * _z;
+        float w0, w1, w2;
+        dev_m33v(fm.R, _x, _y, _z, w0, w1, w2);
+        w0 += c2[0]; w1 += c2[1]; w2 += c2[2];
+        float a0, a1, a2, b0, b1, b2;
+        dev_m33v(Rik, w0 - c1[0], w1 - c1[1], w2 - c1[2], a0, a1, a2);
+        dev_m33v(Rik, P0 - c1[0], P1 - c1[1], P2 - c1[2], b0, b1, b2);
+        const float disp_ref = baseline / b2;
+        const float disp = baseline / a2;
+        const float pixel_distance = disp - disp_ref;
+        if (fabsf(pixel_distance) > 5 * 0.5f) outl++;
+        else inl++;
+    }
+    // ---- update_kps3d (depth_filter.cpp:130-257)
+    float kx = a.kf_state[2 * i], kP = a.kf_state[2 * i + 1];
+    {
+        float d0, d1, d2;
+        dev_m33v(Rik, fabsf(c1[0] - c2[0]), fabsf(c1[1] - c2[1]), fabsf(c1[2] - c2[2]), d0, d1, d2);
+        if (flags & (SVO_F_IGN_COMPLETE | SVO_F_IGN_REFINE)) {
+            outl++;
+        } else if (!((double)d0 < 0.1 && (double)d1 < 0.1)) {
+            const float rfx = a.ref_kps2d[2 * i], rfy = a.ref_kps2d[2 * i + 1];
+            float p10, p11, p12, p20, p21, p22;
+            dev_m33v(Rk, rfx - cx, rfy - cy, fx, p10, p11, p12);
+            dev_m33v(fm.R, u - cx, v - cy, fx, p20, p21, p22);
+            // least squares [p1 -p2] l = c2 - c1 (cv::solve(DECOMP_SVD) in the reference; normal equations in double here)
+            const double y0 = (double)(c2[0] - c1[0]), y1 = (double)(c2[1] - c1[1]), y2 = (double)(c2[2] - c1[2]);
+            const double a00 = (double)p10 * p10 + (double)p11 * p11 + (double)p12 * p12;
+            const double a01 = -((double)p10 * p20 + (double)p11 * p21 + (double)p12 * p22);
+            const double a11 = (double)p20 * p20 + (double)p21 * p21 + (double)p22 * p22;
+            const double r0 = (double)p10 * y0 + (double)p11 * y1 + (double)p12 * y2;
+            const double r1 = -((double)p20 * y0 + (double)p21 * y1 + (double)p22 * y2);
+            const double det = a00 * a11 - a01 * a01;
+            const float l0 = (float)((a11 * r0 - a01 * r1) / det);
+            // 1x1 cv::KalmanFilter (A = H = 1, Q = 1e-4): predict + correct, OpenCV's float/double mix
+            const float dev = (float)(0.5 / (double)sqrtf(d0 * d0 + d1 * d1));
+            const float Rn = dev * dev;
+            const float xpre = kx;
+            const float Ppre = (float)((double)kP + (double)1e-4f);
+            // Vec3f new_p = inv_rotation_kf*l(0)*(p1-c1)  (matrix scaled first)
+            float Ms[9];
+#pragma unroll
+            for (int q = 0; q < 9; q++) Ms[q] = Rik[q] * l0;
+            float np0, np1, np2;
+            dev_m33v(Ms, p10 - c1[0], p11 - c1[1], p12 - c1[2], np0, np1, np2);
+            const float meas = 1 / np2;
+            const float t3 = (float)((double)Ppre + (double)Rn);
+            // gain through OpenCV's SVD solve of a 1x1 system
+            const double wd = sqrt((double)t3 * (double)t3);
+            const float uu = t3 * (float)(wd > 1.1754943508222875e-38 ? 1. / wd : 0.);
+            const float wf = (float)wd;
+            float K = 0.f;
+            if (fabs((double)wf) > (double)wf * (double)(float)(2.220446049250313e-16 * 2)) {
+                double s = (double)uu * (double)Ppre;
+                s *= 1. / (double)wf;
+                K = (float)(0.0 + s * 1.0);
+            }
+            const float t5 = (float)(-((double)xpre) + (double)meas);
+            kx = (float)((double)K * (double)t5 + (double)xpre);
+            kP = (float)(-((double)K * (double)Ppre) + (double)Ppre);
+            const float _z = (float)(1.0 / (double)kx);
+            const float _x = (rfx - cx) / fx * _z;
+            const float _y = (rfy - cy) / fy * _z;
+            float o0, o1, o2;
+            dev_m33v(Rk, _x, _y, _z, o0, o1, o2);
+            P0 = c1[0] + o0; P1 = c1[1] + o1; P2 = c1[2] + o2;
+        }
+    }
+    // ---- post-processing (stereo_slam.cpp:205-226)
+    if (outl > inl) flags |= SVO_F_IGN_COMPLETE;
+    if (inl > outl) flags &= (uint8_t)~SVO_F_IGN_TEMP;
+    a.kps3d[3 * i] = P0; a.kps3d[3 * i + 1] = P1; a.kps3d[3 * i + 2] = P2;
+    a.flags[i] = flags; a.inlier[i] = inl; a.outlier[i] = outl;
+    a.kf_state[2 * i] = kx; a.kf_state[2 * i + 1] = kP;
+    // ---- re-projection of the updated point (stereo_slam.cpp:228-229)
+    float ou, ov;
+    dev_project(fm.Rdn, P0, P1, P2, c2[0], c2[1], c2[2], fx, fy, cx, cy, cam.k1, cam.k2, cam.p1, cam.p2, cam.k3, ou, ov);
+    a.kps2d_out[2 * i] = ou; a.kps2d_out[2 * i + 1] = ov;
+}
+
+void launch_depth_filter(const FilterArgs &a, cudaStream_t st)
+{
+    if (a.max_kps <= 0) return;
+    depth_filter_kernel<<<(a.max_kps + 127) / 128, 128, 0, st>>>(a);
+}

@@ -1,0 +1,166 @@
+"""Python mirror of the reference's Python wrapper (src/python/wrapper/slam_accelerator.pyx:50-91):
+StereoSlam(camera_settings).new_image(left, right, time_stamp) / get_frame() / get_keyframe() /
+get_keyframes() / get_trajectory() / update_pose(...), backed by the svo_slam_* C-ABI (CUDA, sm_100a).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import CameraSettings, KeyPointInfo, Pose, SvoError  # noqa: F401  (re-exported, same names as the reference)
+
+_KP_DTYPE = np.dtype(KeyPointInfo)
+
+
+class KeyPoints:
+    """== struct KeyPoints (stereo_slam_types.hpp:108-112): kps2d (n,2), kps3d (n,3), info (structured array)."""
+
+    def __init__(self, kps2d, kps3d, info):
+        self.kps2d, self.kps3d, self.info = kps2d, kps3d, info
+
+    def __len__(self):
+        return len(self.info)
+
+
+class Frame:
+    """== struct Frame (stereo_slam_types.hpp:119-125). stereo_image levels are fetched lazily from the device."""
+
+    def __init__(self, slam, index, fid, pose, time_stamp, kps):
+        self._slam, self._index = slam, index
+        self.id, self.pose, self.time_stamp, self.kps = fid, pose, time_stamp, kps
+
+    def image(self, kind="left", level=0):
+        k = {"left": 0, "right": 1, "opt_flow": 2}[kind]
+        return self._slam._image(self._index, k, level)
+
+
+class KeyFrame(Frame):
+    pass
+
+
+class StereoSlam:
+    def __init__(self, camera_settings, width, height, device=0):
+        if isinstance(camera_settings, dict):
+            camera_settings = CameraSettings(**camera_settings)
+        self.camera_settings, self.width, self.height = camera_settings, width, height
+        out = C.c_void_p()
+        rc = capi.lib().svo_slam_create(C.byref(camera_settings), device, width, height, C.byref(out))
+        if rc:
+            raise SvoError(rc, capi.lib().svo_slam_last_error(None).decode())
+        self._h = out
+        self._keep = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            capi.lib().svo_slam_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc:
+            raise SvoError(rc, capi.lib().svo_slam_last_error(self._h).decode())
+
+    @staticmethod
+    def _img(a):
+        if a.dtype != np.uint8 or a.ndim != 2:
+            raise SvoError(capi.SVO_ERR_INVALID, "images must be 2-D uint8 (CV_8U single channel, stereo_slam.cpp:96)")
+        if a.strides[1] != 1:
+            a = np.ascontiguousarray(a)
+        return a
+
+    # ---- StereoSlam::new_image (stereo_slam.cpp:123)
+    def new_image(self, left, right, time_stamp):
+        left, right = self._img(left), self._img(right)
+        if left.shape != (self.height, self.width) or right.shape != left.shape:
+            raise SvoError(capi.SVO_ERR_INVALID, "image size differs from the size the instance was created with")
+        self._ck(capi.lib().svo_slam_new_image(self._h, left.ctypes.data_as(C.c_void_p), C.c_size_t(left.strides[0]),
+                                               right.ctypes.data_as(C.c_void_p), C.c_size_t(right.strides[0]),
+                                               C.c_float(time_stamp)))
+
+    # pipelined form for many independent sequences (one CUDA stream per instance)
+    def new_image_begin(self, left, right, time_stamp):
+        left, right = self._img(left), self._img(right)
+        self._keep = (left, right)
+        self._ck(capi.lib().svo_slam_new_image_begin(self._h, left.ctypes.data_as(C.c_void_p), C.c_size_t(left.strides[0]),
+                                                     right.ctypes.data_as(C.c_void_p), C.c_size_t(right.strides[0]),
+                                                     C.c_float(time_stamp)))
+
+    def new_image_end(self):
+        self._ck(capi.lib().svo_slam_new_image_end(self._h))
+        self._keep = None
+
+    def _image(self, index, kind, level):
+        ctx = capi.Context(self.camera_settings, self.width, self.height, _borrowed=capi.lib().svo_slam_ctx(self._h))
+        w, h = ctx.level_size(kind, level)
+        out = np.empty((h, w), np.uint8)
+        if index is None:
+            self._ck(capi.lib().svo_slam_get_frame_image(self._h, kind, level, out.ctypes.data_as(C.c_void_p), C.c_size_t(w)))
+        else:
+            self._ck(capi.lib().svo_slam_get_keyframe_image(self._h, index, kind, level, out.ctypes.data_as(C.c_void_p), C.c_size_t(w)))
+        return out
+
+    def _fetch(self, index):
+        fid, pose, ts, n = C.c_uint64(), Pose(), C.c_double(), C.c_int()
+        if index is None:
+            rc = capi.lib().svo_slam_get_frame(self._h, C.byref(fid), C.byref(pose), C.byref(ts), C.byref(n))
+        else:
+            rc = capi.lib().svo_slam_get_keyframe(self._h, index, C.byref(fid), C.byref(pose), C.byref(ts), C.byref(n))
+        if rc == capi.SVO_ERR_STATE:
+            return None
+        self._ck(rc)
+        k2, k3 = np.empty((n.value, 2), np.float32), np.empty((n.value, 3), np.float32)
+        info = np.zeros(n.value, _KP_DTYPE)
+        args = (n.value, k2.ctypes.data_as(C.c_void_p), k3.ctypes.data_as(C.c_void_p), info.ctypes.data_as(C.c_void_p))
+        if index is None:
+            self._ck(capi.lib().svo_slam_get_frame_keypoints(self._h, *args))
+        else:
+            self._ck(capi.lib().svo_slam_get_keyframe_keypoints(self._h, index, *args))
+        cls = Frame if index is None else KeyFrame
+        return cls(self, index, fid.value, pose.vec(), ts.value, KeyPoints(k2, k3, info))
+
+    def get_frame(self):
+        """StereoSlam::get_frame (stereo_slam.cpp:278-284): None before the first image."""
+        return self._fetch(None)
+
+    def get_keyframe(self):
+        return self._fetch(-1)
+
+    def get_keyframes(self):
+        return [self._fetch(i) for i in range(capi.lib().svo_slam_keyframe_count(self._h))]
+
+    def keyframe_count(self):
+        return capi.lib().svo_slam_keyframe_count(self._h)
+
+    def get_trajectory(self):
+        n = capi.lib().svo_slam_get_trajectory(self._h, 0, None)
+        out = np.empty((n, 6), np.float32)
+        if n:
+            capi.lib().svo_slam_get_trajectory(self._h, n, out.ctypes.data_as(C.c_void_p))
+        return out
+
+    def pose(self):
+        fid, pose, ts, n = C.c_uint64(), Pose(), C.c_double(), C.c_int()
+        self._ck(capi.lib().svo_slam_get_frame(self._h, C.byref(fid), C.byref(pose), C.byref(ts), C.byref(n)))
+        return pose.vec()
+
+    def update_pose(self, pose, speed, pose_variance, speed_variance, dt):
+        p = Pose(*[float(v) for v in pose])
+        arrs = [np.ascontiguousarray(a, dtype=np.float32) for a in (speed, pose_variance, speed_variance)]
+        out = Pose()
+        self._ck(capi.lib().svo_slam_update_pose(self._h, C.byref(p), *[a.ctypes.data_as(C.c_void_p) for a in arrs],
+                                                 C.c_double(dt), C.byref(out)))
+        return out.vec()
+
+    def last_stats(self):
+        ms, n, kf = C.c_float(), C.c_int(), C.c_int()
+        self._ck(capi.lib().svo_slam_last_stats(self._h, C.byref(ms), C.byref(n), C.byref(kf)))
+        return dict(gpu_ms=ms.value, launches=n.value, keyframe_created=bool(kf.value))
+
+    def context(self):
+        """The device context behind the facade (stage-level probes)."""
+        return capi.Context(self.camera_settings, self.width, self.height, _borrowed=capi.lib().svo_slam_ctx(self._h))

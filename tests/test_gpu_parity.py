@@ -1,0 +1,365 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu). Every test calls the CUDA path through the C-ABI
+(stereo_svo_slam_b200.capi -> libstereosvo_b200.so) and checks it against the CPU oracle on identical inputs.
+
+Bars (BASELINE.json north_star): bit-exact for integer work (pyramids, corner positions/scores, keypoint
+indexing, SSD disparities); floating point within tolerance — pose <= 1e-4 rad / 1e-4 m (relative), flow
+<= 0.01 px, depth <= 1e-3 relative.
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from stereo_svo_slam_b200 import capi, synth
+
+pytestmark = pytest.mark.gpu
+
+POSE_TOL_T = 1e-4   # metres, relative to max(1, |t|)
+POSE_TOL_R = 1e-4   # radians
+FLOW_TOL = 0.01     # pixels
+DEPTH_RTOL = 1e-3
+
+
+def mk(cfg_name, **over):
+    d = synth.settings_dict(cfg_name)
+    d.update(over)
+    return capi.CameraSettings(**d), orc.CameraSettings(**d)
+
+
+@pytest.fixture(scope="module")
+def c3ctx():
+    gcs, ocs = mk("C3")
+    ctx = capi.Context(gcs, 752, 480)
+    yield ctx, gcs, ocs
+    ctx.close()
+
+
+def pose_close(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    st = max(1.0, np.abs(b[:3]).max())
+    return np.abs(a[:3] - b[:3]).max() <= POSE_TOL_T * st and np.abs(a[3:] - b[3:]).max() <= POSE_TOL_R
+
+
+# ----------------------------------------------------------------------------------------------- pyramids
+def test_pyramids_bit_exact_fixture(c3ctx, fixture_images):
+    ctx, _, _ = c3ctx
+    L, R = fixture_images["left"], fixture_images["right"]
+    slot = ctx.upload(L, R)
+    lv = L
+    for l in range(4):
+        assert (ctx.download(slot, 0, l) == lv).all(), f"halfSample level {l}"
+        lv = orc.half_sample(lv)
+    assert (ctx.download(slot, 1, 0) == R).all()
+    lv = L
+    for l in range(3):
+        assert (ctx.download(slot, 2, l) == lv).all(), f"LK pyramid level {l}"
+        lv = orc.pyr_down(lv)
+    ctx.release(slot)
+
+
+@pytest.mark.parametrize("w,h,levels", [(330, 250, 5), (101, 77, 3), (1280, 720, 5), (64, 48, 2)])
+def test_pyramids_bit_exact_random_sizes(w, h, levels):
+    gcs, _ = mk("S", max_pyramid_levels=levels, min_pyramid_level_pose_estimation=min(2, levels - 1), grid_width=16, grid_height=16)
+    ctx = capi.Context(gcs, w, h)
+    rng = np.random.default_rng(w * 1000 + h)
+    L = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    R = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    # strided input (cv::Mat ROI): pass a view into a wider buffer
+    buf = np.zeros((h, w + 13), np.uint8)
+    buf[:, 5:5 + w] = L
+    slot = ctx.upload(buf[:, 5:5 + w], R)
+    lv = L
+    for l in range(levels):
+        assert (ctx.download(slot, 0, l) == lv).all(), f"halfSample level {l} of {w}x{h}"
+        lv = orc.half_sample(lv)
+    lv = L
+    for l in range(3):
+        assert (ctx.download(slot, 2, l) == lv).all(), f"LK level {l} of {w}x{h}"
+        lv = orc.pyr_down(lv)
+    ctx.close()
+
+
+# ----------------------------------------------------------------------------------------------- detection
+def test_fast_and_grid_detection_bit_exact(c3ctx, fixture_images, cv2_vectors):
+    ctx, _, _ = c3ctx
+    for name in ("left", "testimage0"):
+        img = fixture_images[name]
+        slot = ctx.upload(img, img)
+        got = ctx.fast_corners(slot, 0)
+        want = cv2_vectors[f"fast_{name}"].astype(np.int32)   # the REAL cv2 FAST output
+        assert got.shape == want.shape and (got == want).all()
+        lv = img
+        for level, (gw, gh) in enumerate([(30, 24), (15, 12)]):
+            xy, sc, ty = ctx.detect_keypoints(slot, level, gw, gh)
+            oxy, osc, oty = orc.detect_keypoints(lv, gw, gh, level)
+            assert xy.shape == oxy.shape
+            assert (xy == oxy).all() and (sc == osc).all() and (ty == oty).all()
+            lv = orc.half_sample(lv)
+        # non-square grids of the shipped YAMLs (Blender 75x48, EuRoC 54x48)
+        for gw, gh in [(75, 48), (54, 48), (16, 14)]:
+            xy, sc, ty = ctx.detect_keypoints(slot, 0, gw, gh)
+            oxy, osc, oty = orc.detect_keypoints(img, gw, gh, 0)
+            assert (xy == oxy).all() and (sc == osc).all() and (ty == oty).all()
+        ctx.release(slot)
+
+
+def test_detection_flat_image_edgelet_fallback(c3ctx):
+    ctx, _, _ = c3ctx
+    img = np.full((480, 752), 90, np.uint8)
+    img[:, 400:] = 130  # one vertical edge: most cells have neither corner nor gradient
+    slot = ctx.upload(img, img)
+    xy, sc, ty = ctx.detect_keypoints(slot, 0, 30, 24)
+    oxy, osc, oty = orc.detect_keypoints(img, 30, 24, 0)
+    assert (xy == oxy).all() and (sc == osc).all() and (ty == oty).all()
+    assert (ty == capi.KP_EDGELET).all()
+    ctx.release(slot)
+
+
+# ----------------------------------------------------------------------------------------------- stereo SSD
+def test_stereo_match_bit_exact(c3ctx, fixture_images):
+    ctx, _, ocs = c3ctx
+    L, R = fixture_images["left"], fixture_images["right"]
+    slot = ctx.upload(L, R)
+    rng = np.random.default_rng(5)
+    fk = orc.fast(L, 6)[:, :2].astype(np.float32)
+    pts = np.vstack([fk[rng.choice(len(fk), 300, replace=False)],
+                     rng.uniform([-40, -40], [800, 520], (200, 2)).astype(np.float32),   # partially / fully outside
+                     np.array([[0, 0], [751, 479], [751.9, 0.2], [3.5, 478.9], [736, 240], [720.2, 470.7]], np.float32)])
+    for mode in (0, 1):
+        sel = pts if mode == 1 else pts[(pts[:, 0] >= 0) & (pts[:, 1] >= 0) & (pts[:, 0] < 752) & (pts[:, 1] < 480)]
+        got = ctx.stereo_match(slot, sel, mode)
+        want = orc.ssd_disparity(L, R, ocs, sel, mode)
+        assert (got == want).all(), f"mode {mode}: {np.nonzero(got != want)[0][:10]}"
+    ctx.release(slot)
+
+
+# ----------------------------------------------------------------------------------------------- KLT
+def test_klt_matches_oracle_and_opencv(c3ctx, fixture_images, cv2_vectors):
+    ctx, _, _ = c3ctx
+    v = cv2_vectors
+    T, T2 = fixture_images["testimage0"], v["lk_img_next"]
+    s0, s1 = ctx.upload(T, T), ctx.upload(T2, T2)
+    nxt, st, err = ctx.klt_slots(s0, s1, v["lk_prev"], v["lk_init"])
+    onxt, ost, oerr = orc.lk(T, T2, v["lk_prev"], v["lk_init"], 31)
+    assert (st == ost).all() and (st == v["lk_status"]).all()
+    ok = st == 1
+    assert np.abs(nxt[ok] - onxt[ok]).max() <= FLOW_TOL
+    assert np.abs(nxt[ok] - v["lk_next"][ok]).max() <= FLOW_TOL      # vs the real cv2.calcOpticalFlowPyrLK
+    assert np.abs(nxt[ok] - onxt[ok]).max() < 2e-3                     # in practice far tighter than the bar
+    assert np.abs(err[ok] - oerr[ok]).max() < 1e-3
+    assert np.isinf(err[~ok]).all()                                    # optical_flow.cpp:46-50
+    assert np.abs(nxt[~ok] - onxt[~ok]).max() < 2e-3
+    ctx.release(s0)
+    ctx.release(s1)
+
+
+# ----------------------------------------------------------------------------------------------- projection
+def test_project_bit_exact(cv2_vectors):
+    v = cv2_vectors
+    d = synth.settings_dict("C3")
+    d.update(fx=float(v["proj_K"][0, 0]), fy=float(v["proj_K"][1, 1]), cx=float(v["proj_K"][0, 2]), cy=float(v["proj_K"][1, 2]),
+             k1=float(v["proj_D"][0]), k2=float(v["proj_D"][1]), p1=float(v["proj_D"][2]), p2=float(v["proj_D"][3]), k3=float(v["proj_D"][4]))
+    ctx = capi.Context(capi.CameraSettings(**d), 752, 480)
+    pose = np.concatenate([np.zeros(3, np.float32), -v["proj_r"]]).astype(np.float32)
+    got = ctx.project(pose, v["proj_P"])
+    assert np.abs(got - v["proj_out"]).max() <= 1e-4          # vs cv2.projectPoints with distortion
+    pose2 = np.array([0.3, -0.2, 0.1, 0.02, -0.05, 0.03], np.float32)
+    want = orc.project(orc.CameraSettings(**d), pose2, v["proj_P"])
+    got = ctx.project(pose2, v["proj_P"])
+    assert (got == want).mean() > 0.99 and np.abs(got - want).max() < 1e-4
+    ctx.close()
+
+
+# ----------------------------------------------------------------------------------------------- alignment
+def _scene(cfg, k0, k1):
+    seq = synth.make_sequence(cfg)
+    c = synth.CONFIGS[cfg]
+    L0, R0 = seq.render(k0)
+    L1, R1 = seq.render(k1)
+    return seq, c, (L0, R0), (L1, R1)
+
+
+def _keypoints_with_depth(seq, c, k, L, ocs):
+    xy, sc, ty = orc.detect_keypoints(L, c["grid_width"], c["grid_height"], 0)
+    p = seq.pose(k)
+    R = synth._rodrigues(p[3:])
+    P = []
+    for (u, v) in xy:
+        z = seq.depth_at(k, u, v)
+        pc = np.array([(u - c["cx"]) / c["fx"] * z, (v - c["cy"]) / c["fy"] * z, z])
+        P.append(R @ pc + p[:3])
+    return xy.astype(np.float32), np.array(P, np.float32)
+
+
+@pytest.mark.parametrize("cfg", ["S", "C3"])
+def test_align_probe_and_solve(cfg):
+    gcs, ocs = mk(cfg)
+    seq, c, (L0, R0), (L1, R1) = _scene(cfg, 3, 4)
+    ctx = capi.Context(gcs, c["width"], c["height"])
+    s0, s1 = ctx.upload(L0, R0), ctx.upload(L1, R1)
+    k2, k3 = _keypoints_with_depth(seq, c, 3, L0, ocs)
+    pose0 = seq.pose(3).astype(np.float32)
+    for level in range(c["min_pyramid_level_pose_estimation"], c["max_pyramid_levels"]):
+        cost, grad = ctx.align_probe(s0, s1, k2, k3, level, pose0)
+        ocost, ograd = orc.align_cost(L0, L1, ocs, k2, k3, pose0, level)
+        assert abs(cost - ocost) <= 2e-6 * abs(ocost) + 1e-3, (level, cost, ocost)
+        assert np.abs(grad - ograd).max() <= 2e-3 * np.abs(ograd).max() + 1e-7, (level, grad, ograd)
+    pose, cost, ev = ctx.align(s0, s1, k2, k3, pose0)
+    opose, ocost, oev = orc.align(L0, L1, ocs, k2, k3, pose0)
+    assert pose_close(pose, opose), (pose, opose, ev.tolist(), oev.tolist())
+    gt = seq.pose(4)
+    assert np.abs(pose[:3] - gt[:3]).max() < 0.02 and np.abs(pose[3:] - gt[3:]).max() < 0.004   # it actually aligns
+    # flags: keypoints marked ignore_temporary are left out (pose_estimator.cpp:238-245)
+    fl = np.zeros(len(k2), np.uint8)
+    fl[::3] = capi.FLAG_IGNORE_TEMPORARY
+    pose_f, _, _ = ctx.align(s0, s1, k2, k3, pose0, flags=fl)
+    keep = fl == 0
+    opose_f, _, _ = orc.align(L0, L1, ocs, k2[keep], k3[keep], pose0)
+    assert pose_close(pose_f, opose_f)
+    ctx.close()
+
+
+def test_align_no_keypoints_is_identity():
+    gcs, _ = mk("S")
+    c = synth.CONFIGS["S"]
+    ctx = capi.Context(gcs, c["width"], c["height"])
+    img = np.zeros((c["height"], c["width"]), np.uint8)
+    s0, s1 = ctx.upload(img, img), ctx.upload(img, img)
+    p0 = np.array([0.1, 0.2, 0.3, 0.01, 0.02, 0.03], np.float32)
+    pose, cost, ev = ctx.align(s0, s1, np.zeros((0, 2), np.float32), np.zeros((0, 3), np.float32), p0)
+    assert (pose == p0).all() and cost == 0
+    ctx.close()
+
+
+# ----------------------------------------------------------------------------------------------- refinement
+def test_reproj_refine_parity():
+    gcs, ocs = mk("C3")
+    ctx = capi.Context(gcs, 752, 480)
+    rng = np.random.default_rng(3)
+    n = 400
+    P = (rng.normal(0, 1, (n, 3)) * [2.0, 1.5, 0.8] + [0, 0, 5]).astype(np.float32)
+    true = np.array([0.04, -0.03, 0.05, 0.006, -0.008, 0.004], np.float32)
+    k2 = orc.project(ocs, true, P) + rng.normal(0, 0.15, (n, 2)).astype(np.float32)
+    k2[::17] += 12.0   # gross outliers: skipped by the |d| > 3 px gate
+    flags = np.zeros(n, np.uint8)
+    flags[::11] = capi.FLAG_IGNORE_REFINEMENT
+    flags[5::23] = capi.FLAG_IGNORE_TEMPORARY
+    guess = true + np.array([0.01, -0.01, 0.015, 0.002, 0.001, -0.002], np.float32)
+    pose, cost, ev = ctx.reproj_refine(k2, P, flags, guess)
+    opose, ocost, oev = orc.refine(ocs, k2, P, flags.astype(np.int32), guess)
+    assert pose_close(pose, opose), (pose, opose, ev, oev)
+    assert abs(cost - ocost) <= 1e-3 * max(1.0, abs(ocost))
+    ctx.close()
+
+
+# ----------------------------------------------------------------------------------------------- fused frame
+def _oracle_inputs(slam):
+    t = slam.trace
+    n = len(t("align_in_flags"))
+    kfid = t("align_in_kfid").astype(np.int32)
+    kpidx = t("align_in_kpidx").astype(np.int64)
+    ref2d = np.zeros((n, 2), np.float32)
+    for k in np.unique(kfid):
+        _, k2, _ = slam.keyframe(int(k))
+        m = kfid == k
+        ref2d[m] = k2[kpidx[m]]
+    return dict(prev_kps2d=t("align_in_kps2d").reshape(-1, 2), kps3d=t("align_in_kps3d").reshape(-1, 3), ref_kps2d=ref2d,
+                keyframe_id=kfid, flags=t("align_in_flags").astype(np.uint8), inlier=t("align_in_counts").reshape(-1, 2)[:, 0].astype(np.int32),
+                outlier=t("align_in_counts").reshape(-1, 2)[:, 1].astype(np.int32),
+                kf_state=np.stack([t("align_in_kfx"), t("align_in_kfP")], 1), pose_prior=t("align_pose_in"))
+
+
+@pytest.mark.parametrize("cfg,frames", [("S", 25), ("C3", 8)])
+def test_track_frame_teacher_forced(cfg, frames):
+    """Per-frame parity: the oracle pipeline runs freely; each tracking frame's inputs are fed to the fused
+    CUDA frame (svo_track_frame) and every stage output is compared with the oracle's trace."""
+    gcs, ocs = mk(cfg)
+    c = synth.CONFIGS[cfg]
+    seq = synth.make_sequence(cfg)
+    slam = orc.OracleSlam(ocs, c["width"], c["height"], tracing=True)
+    ctx = capi.Context(gcs, c["width"], c["height"])
+    prev_slot, n_kf = None, 0
+    flips = 0
+    for k in range(frames):
+        L, R = seq.render(k)
+        slam.new_image(L, R, k / 20.0)
+        slot = ctx.upload(L, R)
+        if k > 0:
+            inp = _oracle_inputs(slam)
+            out = ctx.track_frame(prev_slot, slot, **inp)
+            t = slam.trace
+            same_path = (out["align_evals"] == t("align_evals").reshape(8, 2).astype(np.int32)).all()
+            flips += 0 if same_path else 1
+            assert pose_close(out["pose_aligned"], t("align_pose_out")), (k, out["pose_aligned"], t("align_pose_out"))
+            st, ost = out["klt_status"], t("klt_status").astype(np.uint8)
+            assert (st == ost).mean() >= 0.995
+            ok = (st == 1) & (ost == 1)
+            assert np.abs(out["klt_pts"][ok] - t("klt_next").reshape(-1, 2)[ok]).max() <= FLOW_TOL
+            assert pose_close(out["pose_refined"], t("ref_pose_out")), (k, out["pose_refined"], t("ref_pose_out"))
+            # depth filter: disparities are integer-exact whenever the (float) keypoint lands on the same pixel
+            d, od = out["disparity"], t("df_disp")
+            assert (d == od).mean() >= 0.99, (k, (d == od).mean())
+            fl, ofl = out["flags"], t("df_out_flags").astype(np.uint8)
+            assert (fl == ofl).mean() >= 0.99
+            cnt = np.stack([out["inlier"], out["outlier"]], 1)
+            assert (cnt == t("df_out_counts").reshape(-1, 2).astype(np.int32)).mean() >= 0.99
+            z, oz = out["kps3d"], t("df_out_kps3d").reshape(-1, 3)
+            good = (fl == ofl) & (d == od)
+            rel = np.abs(z[good] - oz[good]).max(axis=1) / np.maximum(1.0, np.abs(oz[good]).max(axis=1))
+            assert np.quantile(rel, 0.99) <= DEPTH_RTOL, (k, np.quantile(rel, 0.99), rel.max())
+            kp, okp = out["kps2d"], t("df_out_kps2d").reshape(-1, 2)
+            assert np.quantile(np.abs(kp[good] - okp[good]).max(axis=1), 0.99) <= 0.05
+        # keyframes created by the oracle in this frame are registered on the device with the oracle's pose
+        while n_kf < slam.n_keyframes():
+            pose, _, _ = slam.keyframe(n_kf)
+            assert ctx.keyframe_commit(slot, pose) == n_kf
+            n_kf += 1
+        if prev_slot is not None:
+            ctx.release(prev_slot)
+        prev_slot = slot
+    assert flips <= max(1, frames // 4), f"solver iteration path differed from the oracle on {flips} of {frames - 1} frames"
+    ctx.close()
+
+
+# ----------------------------------------------------------------------------------------------- whole pipeline
+@pytest.mark.parametrize("cfg,frames", [("S", 30), ("C3", 12)])
+def test_slam_free_running_matches_oracle(cfg, frames):
+    from stereo_svo_slam_b200 import StereoSlam
+    gcs, ocs = mk(cfg)
+    c = synth.CONFIGS[cfg]
+    seq = synth.make_sequence(cfg)
+    o = orc.OracleSlam(ocs, c["width"], c["height"], tracing=False)
+    g = StereoSlam(gcs, c["width"], c["height"])
+    assert g.get_frame() is None
+    worst_t = worst_r = 0.0
+    for k in range(frames):
+        L, R = seq.render(k)
+        o.new_image(L, R, k / 20.0)
+        g.new_image(L, R, k / 20.0)
+        gp, op = g.pose(), o.pose()
+        st = max(1.0, np.abs(op[:3]).max())
+        worst_t = max(worst_t, np.abs(gp[:3] - op[:3]).max() / st)
+        worst_r = max(worst_r, np.abs(gp[3:] - op[3:]).max())
+        f = g.get_frame()
+        assert f.id == k and len(f.kps) == o.n_kps(), (k, len(f.kps), o.n_kps())
+        assert g.keyframe_count() == o.n_keyframes()
+    # free-running trajectories: the per-frame tolerance accumulates; allow 5x over the sequence
+    assert worst_t <= 5 * POSE_TOL_T and worst_r <= 5 * POSE_TOL_R, (worst_t, worst_r)
+    traj, otraj = g.get_trajectory(), o.trajectory()
+    assert traj.shape == otraj.shape == (frames, 6)
+    gt = np.array([seq.pose(k) for k in range(frames)])
+    assert np.abs(traj[:, :3] - gt[:, :3]).max() < 0.03 and np.abs(traj[:, 3:] - gt[:, 3:]).max() < 0.006
+    kf = g.get_keyframe()
+    assert kf is not None and (kf.image("left", 0) == seq.render(0)[0]).all() if g.keyframe_count() == 1 else True
+    g.close()
+
+
+def test_error_behaviour(c3ctx):
+    ctx, gcs, _ = c3ctx
+    with pytest.raises(capi.SvoError):
+        ctx.download(9999, 0, 0)
+    with pytest.raises(capi.SvoError):
+        ctx.stereo_match(0, np.zeros((10 ** 6, 2), np.float32), 1)  # capacity
+    bad = synth.settings_dict("C3")
+    bad["max_pyramid_levels"] = 9
+    with pytest.raises(capi.SvoError):
+        capi.Context(capi.CameraSettings(**bad), 752, 480)
