@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""bench.py — tracked stereo frames/s of the tracking hot path (BASELINE.json metric) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--streams S] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload): BASELINE.json configs[2] — EuRoC-shaped synthetic stereo, 752x480, 4-level pyramid,
+30x24 grid (~430-500 keypoints/frame) — as S independent sequences per GPU (configs[4] = 64 sequences is
+S=8 on 8 GPUs).  configs[0]/[1] (Blender videos) cannot run: the .mkv files are missing from the reference
+checkout (.MISSING_LARGE_BLOBS).  A *step* advances every sequence of every rank by one stereo frame
+(StereoSlam::new_image: pyramids -> sparse alignment -> KLT -> reprojection GN -> depth filter -> host
+bookkeeping, keyframe creation when the reference would create one).
+
+  value  : whole-job frames/s with the stereo frames already resident in HBM (svo_slam_new_image_device_begin)
+  e2e    : the same through the reference-facing call with HOST (pinned) buffers, H2D/D2H inside the timed region
+  roofline / single_stream / kernels : one sequence, per-stage CUDA events on the launching stream
+  cpu_baseline : the CPU oracle ("port" of the reference's single-threaded path) on one host core, bounded sample
+  --impl reference : the same workload on the CPU oracle with all host threads (one sequence per thread)
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from stereo_svo_slam_b200 import synth  # noqa: E402
+
+CFG = "C3"
+METRIC = "tracked_stereo_frames_per_s"
+UNIT = "frames/s"
+
+
+def render_sequence(args):
+    cfg, seed, n = args
+    seq = synth.make_sequence(cfg, seed=seed)
+    c = synth.CONFIGS[cfg]
+    out = np.empty((n, 2, c["height"], c["width"]), np.uint8)
+    for k in range(n):
+        out[k, 0], out[k, 1] = seq.render(k)
+    return out
+
+
+def make_frames(cfg, seeds, n):
+    """[S][n][2][H][W] uint8; rendered in parallel processes and cached under /tmp."""
+    import concurrent.futures as cf
+    outs, todo = {}, []
+    for s in seeds:
+        path = f"/tmp/svo_synth_{cfg}_{s}_{n}.npy"
+        if os.path.exists(path):
+            try:
+                outs[s] = np.load(path)
+                continue
+            except Exception:
+                pass
+        todo.append(s)
+    if todo:
+        with cf.ProcessPoolExecutor(max_workers=min(len(todo), os.cpu_count() or 1)) as ex:
+            for s, arr in zip(todo, ex.map(render_sequence, [(cfg, s, n) for s in todo])):
+                outs[s] = arr
+                try:
+                    np.save(f"/tmp/svo_synth_{cfg}_{s}_{n}.npy", arr)
+                except Exception:
+                    pass
+    return np.stack([outs[s] for s in seeds])
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML (in-process thread) during the timed region."""
+
+    def __init__(self, dev, period=0.02):
+        self.dev, self.period, self.rows, self.t, self.stop_flag = dev, period, [], None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates all GPUs of the box; CUDA_VISIBLE_DEVICES may remap: resolve by UUID when possible
+            self.nv = pynvml
+            idx = dev
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                ent = vis.split(",")[dev].strip()
+                if ent.isdigit():
+                    idx = int(ent)
+                else:
+                    for k in range(pynvml.nvmlDeviceGetCount()):
+                        h = pynvml.nvmlDeviceGetHandleByIndex(k)
+                        u = pynvml.nvmlDeviceGetUUID(h)
+                        u = u.decode() if isinstance(u, bytes) else u
+                        if u.startswith(ent) or ent in u:
+                            idx = k
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        except Exception as e:  # noqa: BLE001
+            self.nv, self.err = None, str(e)
+
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((sm, r))
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(self.period)
+
+    def start(self):
+        if self.nv:
+            self.t = threading.Thread(target=self._loop, daemon=True)
+            self.t.start()
+
+    def stop(self):
+        if not self.nv:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + getattr(self, "err", "")]}
+        self.stop_flag = True
+        self.t.join()
+        nv = self.nv
+        try:
+            mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+        except Exception:  # noqa: BLE001
+            mx = None
+        bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                "hw_power_brake_slowdown": 0x80}
+        reasons = sorted({n for _, r in self.rows for n, b in bits.items() if r & b})
+        sm = [a for a, _ in self.rows]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": reasons}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def algorithmic_bytes(c, n_kps, evals_per_level, klt_levels=3):
+    """SURVEY.md §8(d) per-unit figures x the units of one frame."""
+    w, h, L = c["width"], c["height"], c["max_pyramid_levels"]
+    lv = [(w >> i) * (h >> i) for i in range(L)]
+    half = sum(lv[:-1]) + sum(lv[1:])
+    lk = [w * h, ((w + 1) // 2) * ((h + 1) // 2)]
+    lk.append(((lk and (w + 1) // 2) + 1) // 2 * ((((h + 1) // 2) + 1) // 2))
+    pyr_lk = (lk[0] + lk[1]) + (lk[0] + lk[1] + lk[2])  # reads of levels 0,1 + padded writes (interior only counted)
+    return {
+        "pyramids": half + pyr_lk,
+        "align": 120 * n_kps * evals_per_level,          # 120 B per (keypoint, level, evaluation) patch
+        "klt": 6965 * n_kps,                             # derivative-fused layout, 3 levels
+        "ssd": 4468 * n_kps,
+        "refine": 20 * n_kps,
+        "filter": 72 * n_kps,
+    }
+
+
+# --------------------------------------------------------------------------------------------- reference arm
+def run_oracle(frames, cfg, steps, warmup, threads):
+    from oracle import oracle as orc
+    c = synth.CONFIGS[cfg]
+    S = frames.shape[0]
+    slams = [orc.OracleSlam(orc.CameraSettings(**synth.settings_dict(cfg)), c["width"], c["height"], tracing=False) for _ in range(S)]
+
+    def advance(s, k):
+        slams[s].new_image(frames[s, k, 0], frames[s, k, 1], k / 20.0)
+
+    def step(k):
+        if threads <= 1:
+            for s in range(S):
+                advance(s, k)
+        else:
+            ts = [threading.Thread(target=advance, args=(s, k)) for s in range(S)]
+            for t in ts:
+                t.start()
+            for t in ts:
+                t.join()
+
+    for k in range(warmup):
+        step(k)
+    t0 = time.perf_counter()
+    for k in range(warmup, warmup + steps):
+        step(k)
+    dt = time.perf_counter() - t0
+    return S * steps / dt, dt, slams
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--streams", type=int, default=8, help="independent sequences per GPU")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    W = max(a.warmup, 3)
+    K, S = a.steps, a.streams
+    c = synth.CONFIGS[CFG]
+    nframes = W + K
+    config = {"workload": f"BASELINE configs[2] EuRoC-shaped synthetic 752x480 ({CFG}: 4-level pyramid, 30x24 grid), "
+                          f"{S} independent sequences per GPU (configs[4] = 8 GPUs x 8); configs[0]/[1] blocked: .mkv missing",
+              "sequences_per_gpu": S, "frames_per_sequence": nframes, "seeds": "1000 + rank*S + s",
+              "l2_hygiene": "every step touches new frames (0.72 MB/sequence) and all sequences' pyramids; single-stream working "
+                            "set (<3 MB) is L2 resident by nature of the path — kernels are latency/ALU bound (DESIGN.md)"}
+
+    if a.impl == "reference":
+        # the reference's own CPU implementation of the path = the oracle port (the reference library cannot be built
+        # here: no OpenCV C++ SDK), all host threads, rank 0 only.
+        if rank != 0:
+            return
+        threads = min(S, os.cpu_count() or 1)
+        k_ref, w_ref = min(K, 40), min(W, 3)
+        frames = make_frames(CFG, [1000 + s for s in range(S)], w_ref + k_ref)
+        fps, dt, _ = run_oracle(frames, CFG, k_ref, w_ref, threads)
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": a.gpus, "steps": k_ref, "warmup": w_ref,
+                          "ms_per_step": 1e3 * dt / k_ref, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "u8/f32", "data": "synthetic", "config": config,
+                          "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
+                                           "sample": f"{S} sequences x {k_ref} frames after {w_ref} warm-up frames, one sequence per host thread"},
+                          "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from stereo_svo_slam_b200 import StereoSlam, capi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    seeds = [1000 + rank * S + s for s in range(S)]
+    frames_np = make_frames(CFG, seeds, nframes)                       # [S][F][2][H][W]
+    host = torch.from_numpy(frames_np).pin_memory()                    # pinned host inputs (e2e)
+    dev = host.to("cuda", non_blocking=False)                          # HBM-resident inputs (value)
+    H_, W_ = c["height"], c["width"]
+    settings = capi.CameraSettings(**synth.settings_dict(CFG))
+    lib = capi.lib()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run(mode, clocks=None):
+        slams = [StereoSlam(settings, W_, H_, device=local_rank) for _ in range(S)]
+        hptr = host.data_ptr()
+        dptr = dev.data_ptr()
+        img = H_ * W_
+        launches0 = [None] * S
+
+        def step(k):
+            for s, sl in enumerate(slams):
+                off = ((s * nframes + k) * 2) * img
+                if mode == "device":
+                    rc = lib.svo_slam_new_image_device_begin(sl._h, C.c_void_p(dptr + off), C.c_size_t(W_), C.c_void_p(dptr + off + img),
+                                                             C.c_size_t(W_), C.c_float(k / 20.0))
+                else:
+                    rc = lib.svo_slam_new_image_begin(sl._h, C.c_void_p(hptr + off), C.c_size_t(W_), C.c_void_p(hptr + off + img),
+                                                      C.c_size_t(W_), C.c_float(k / 20.0))
+                if rc:
+                    raise RuntimeError(lib.svo_slam_last_error(sl._h).decode())
+            for sl in slams:
+                rc = lib.svo_slam_new_image_end(sl._h)
+                if rc:
+                    raise RuntimeError(lib.svo_slam_last_error(sl._h).decode())
+
+        for k in range(W):
+            step(k)
+        cnt = C.c_longlong()
+        for s, sl in enumerate(slams):
+            lib.svo_launch_count(C.c_void_p(lib.svo_slam_ctx(sl._h)), C.byref(cnt))
+            launches0[s] = cnt.value
+        barrier()
+        if clocks:
+            clocks.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        t0 = time.perf_counter()
+        for k in range(W, W + K):
+            step(k)
+        torch.cuda.synchronize()
+        e1.record()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        dev_s = e0.elapsed_time(e1) / 1e3
+        ck = clocks.stop() if clocks else None
+        nl = 0
+        for s, sl in enumerate(slams):
+            lib.svo_launch_count(C.c_void_p(lib.svo_slam_ctx(sl._h)), C.byref(cnt))
+            nl += cnt.value - launches0[s]
+        kps = int(np.mean([len(sl.get_frame().kps) for sl in slams]))
+        nkf = int(np.sum([sl.keyframe_count() for sl in slams]))
+        poses = np.stack([sl.pose() for sl in slams])
+        for sl in slams:
+            sl.close()
+        t = torch.tensor([max(wall, dev_s)], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return dict(seconds=float(t.item()), launches=nl, kps=kps, keyframes=nkf, poses=poses, clocks=ck)
+
+    r_dev = run("device", ClockSampler(local_rank))
+    r_e2e = run("host")
+    total_frames = S * K * world
+    value = total_frames / r_dev["seconds"]
+    e2e = total_frames / r_e2e["seconds"]
+
+    out = None
+    if rank == 0:
+        # ---------------- single sequence: latency, per-stage CUDA events, roofline of the dominant kernel
+        sl = StereoSlam(settings, W_, H_, device=local_rank)
+        ctxp = C.c_void_p(lib.svo_slam_ctx(sl._h))
+        lib.svo_set_profiling(ctxp, 1)
+        stage = np.zeros((nframes, 8), np.float32)
+        cnt = np.zeros((nframes, 8), np.float64)
+        walls = []
+        buf = (C.c_float * 8)()
+        for k in range(nframes):
+            t0 = time.perf_counter()
+            sl.new_image(frames_np[0, k, 0], frames_np[0, k, 1], k / 20.0)
+            walls.append(time.perf_counter() - t0)
+            lib.svo_last_stage_ms(ctxp, buf)
+            stage[k] = np.array(list(buf))
+            cnt[k] = list(sl.last_counters().values())
+        keep = slice(W, nframes)
+        st = np.median(stage[keep], axis=0)
+        cm = cnt[keep].mean(axis=0)   # per-frame means of the work counters
+        names = ["upload+pyramids", "sparse_align", "klt", "reproj_refine", "stereo_ssd", "depth_filter", "d2h", "total"]
+        n_kps = int(round(cm[0]))
+        sl.close()
+        patches = cm[1] * (cm[2] + cm[3])          # (keypoint, level, evaluation) 4x4 patches per frame
+        windows = cm[6]                            # (keypoint, level, LK iteration) 31x31 windows per frame
+        peak, peak_src = peaks()
+        med_wall = float(np.median(walls[W:]))
+        dom = int(np.argmax(st[1:6])) + 1
+        ab = algorithmic_bytes(c, n_kps, evals_per_level=1)
+        ab["align"] = int(120 * patches)           # 120 B per patch x patches of one launch
+        dom_bytes = {1: ab["align"], 2: ab["klt"], 3: ab["refine"], 4: ab["ssd"], 5: ab["filter"]}[dom]
+        achieved = dom_bytes / (st[dom] * 1e-3) / 1e9 if st[dom] > 0 else 0.0
+        kernels = []
+        for i, nm in enumerate(names[:7]):
+            b = {0: ab["pyramids"], 1: ab["align"], 2: ab["klt"], 3: ab["refine"], 4: ab["ssd"], 5: ab["filter"], 6: 0}[i]
+            kernels.append({"stage": nm, "ms": float(st[i]), "share": float(st[i] / max(st[7], 1e-9)), "algorithmic_bytes": int(b),
+                            "achieved_gbs": float(b / (st[i] * 1e-3) / 1e9) if st[i] > 0 else None})
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+               "ms_per_step": 1e3 * r_dev["seconds"] / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "u8/f32", "data": "synthetic", "config": config,
+               "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(S * 2 * H_ * W_ + S * n_kps * 45),
+                       "d2h_bytes_per_step": int(S * n_kps * 90), "ms_per_step": 1e3 * r_e2e["seconds"] / K},
+               "gpu_launches": int(r_dev["launches"]),
+               "clocks": r_dev["clocks"],
+               "keypoints_per_frame": r_dev["kps"], "keyframes_created": r_dev["keyframes"],
+               "single_stream": {"frames_per_s": 1.0 / med_wall, "ms_per_frame_wall": 1e3 * med_wall, "ms_per_frame_gpu": float(st[7]),
+                                 "pose_iter_latency_us": float(1e3 * st[1] / max(cm[2] + cm[3], 1.0)),
+                                 "align_evaluations_per_frame": float(cm[2] + cm[3]),
+                                 "mpatches_per_s": float(patches / (st[1] * 1e-3) / 1e6) if st[1] > 0 else None,
+                                 "mwindows_per_s": float(windows / (st[2] * 1e-3) / 1e6) if st[2] > 0 else None,
+                                 "note": "one sequence, synchronous new_image calls with host buffers (what the reference app does)"},
+               "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                            "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                            "limiter": "dependency latency / integer+fp32 ALU, not HBM: the per-frame working set (<3 MB) is L2-resident "
+                                       "(SURVEY.md §8d); see profiles/ for the ncu evidence"},
+               "kernels": kernels}
+        if not a.no_cpu_baseline and world == 1:
+            kb, wb = 30, 3
+            fps, dt, _ = run_oracle(frames_np[:1, :min(nframes, wb + kb)], CFG, min(kb, nframes - wb), wb, 1)
+            out["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": 1, "kind": "port",
+                                   "sample": f"1 sequence, {min(kb, nframes - wb)} frames after {wb} warm-up (oracle = single-threaded "
+                                             "restatement of the reference; the reference library is single-threaded)"}
+        print(json.dumps(out, default=lambda o: float(o) if isinstance(o, (np.floating,)) else (int(o) if isinstance(o, np.integer) else str(o))))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -70,6 +70,10 @@ int svo_device_count(void);
  * keyframe_manager.cpp:27-29). */
 int svo_upload_stereo(svo_ctx *ctx, const uint8_t *left, size_t left_stride, const uint8_t *right, size_t right_stride,
                       int *slot_out);
+/* Same, for images that already live in device memory of the context's GPU (e.g. a camera/decoder pipeline
+ * that lands frames in HBM): device-to-device copy, then the same pyramid build. */
+int svo_upload_stereo_device(svo_ctx *ctx, const uint8_t *d_left, size_t left_stride, const uint8_t *d_right,
+                             size_t right_stride, int *slot_out);
 int svo_slot_retain(svo_ctx *ctx, int slot);
 int svo_slot_release(svo_ctx *ctx, int slot);
 /* kind: 0 = left halfSample pyramid level, 1 = right level 0, 2 = LK pyramid level (unpadded view) */
@@ -155,6 +159,7 @@ typedef struct svo_track_io {
     uint8_t *klt_status;      /* n */
     float *disparity;         /* n */
     float *kps2d_refine_in;   /* n*2 : positions fed to the refinement / depth filter */
+    int *klt_iters;           /* n   : LK iterations summed over the three levels */
 } svo_track_io;
 
 int svo_track_frame(svo_ctx *ctx, int prev_slot, int cur_slot, svo_track_io *io);
@@ -165,6 +170,12 @@ int svo_track_frame_end(svo_ctx *ctx, svo_track_io *io);
 /* GPU time (ms, CUDA events on the context's stream) of the last svo_track_frame, and the number of kernel
  * launches it issued */
 int svo_last_track_timing(svo_ctx *ctx, float *gpu_ms, int *launches);
+/* cumulative number of kernels this context has launched since creation */
+int svo_launch_count(svo_ctx *ctx, long long *launches);
+/* per-stage CUDA-event timing of the tracking frame (adds one event record per stage when on).
+ * stage_ms8 = {upload+pyramids, alignment, klt, reprojection refinement, stereo ssd, depth filter, d2h, total} */
+int svo_set_profiling(svo_ctx *ctx, int on);
+int svo_last_stage_ms(svo_ctx *ctx, float *stage_ms8);
 int svo_sync(svo_ctx *ctx);
 
 /* ================================================================== host facade ================ */
@@ -197,6 +208,9 @@ int svo_slam_new_image(svo_slam *s, const uint8_t *left, size_t left_stride, con
 int svo_slam_new_image_begin(svo_slam *s, const uint8_t *left, size_t left_stride, const uint8_t *right,
                              size_t right_stride, float time_stamp);
 int svo_slam_new_image_end(svo_slam *s);
+/* same as _begin with the stereo pair already resident in device memory (svo_upload_stereo_device) */
+int svo_slam_new_image_device_begin(svo_slam *s, const uint8_t *d_left, size_t left_stride, const uint8_t *d_right,
+                                    size_t right_stride, float time_stamp);
 /* StereoSlam::get_frame (stereo_slam.cpp:278-284): returns SVO_ERR_STATE before the first image */
 int svo_slam_get_frame(svo_slam *s, uint64_t *id, svo_pose *pose, double *time_stamp, int *n_keypoints);
 int svo_slam_get_frame_keypoints(svo_slam *s, int max, float *kps2d, float *kps3d, svo_keypoint_info *info);
@@ -213,6 +227,10 @@ int svo_slam_update_pose(svo_slam *s, const svo_pose *pose, const float speed[6]
                          const float speed_variance[6], double dt, svo_pose *filtered);
 /* diagnostics of the last new_image: device ms, kernel launches, whether a keyframe was created */
 int svo_slam_last_stats(svo_slam *s, float *gpu_ms, int *launches, int *keyframe_created);
+/* work counters of the last tracking frame: {keypoints, keypoints used by the alignment, alignment cost
+ * evaluations, alignment gradient evaluations, refinement cost evaluations, refinement gradient evaluations,
+ * LK iterations summed over keypoints and levels, keypoints tracked by LK (status 1)} */
+int svo_slam_last_counters(svo_slam *s, long long *out8);
 /* the device context behind the facade (for stage-level probes in tests) */
 svo_ctx *svo_slam_ctx(svo_slam *s);
 

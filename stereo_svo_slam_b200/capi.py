@@ -57,7 +57,8 @@ class TrackIO(C.Structure):
                 ("kps2d", C.c_void_p), ("pose_aligned", C.c_float * 6), ("pose_refined", C.c_float * 6),
                 ("align_cost", C.c_float), ("refine_cost", C.c_float), ("align_evals", C.c_int * 16),
                 ("refine_evals", C.c_int * 2), ("klt_pts", C.c_void_p), ("klt_err", C.c_void_p),
-                ("klt_status", C.c_void_p), ("disparity", C.c_void_p), ("kps2d_refine_in", C.c_void_p)]
+                ("klt_status", C.c_void_p), ("disparity", C.c_void_p), ("kps2d_refine_in", C.c_void_p),
+                ("klt_iters", C.c_void_p)]
 
 
 def declared_symbols():
@@ -241,13 +242,15 @@ class Context:
                  outlier=np.ascontiguousarray(outlier, dtype=np.int32).copy(),
                  kf_state=_f32(kf_state, (-1, 2)).copy(),
                  kps2d=np.empty((n, 2), np.float32), klt_pts=np.empty((n, 2), np.float32), klt_err=np.empty(n, np.float32),
-                 klt_status=np.empty(n, np.uint8), disparity=np.empty(n, np.float32), kps2d_refine_in=np.empty((n, 2), np.float32))
+                 klt_status=np.empty(n, np.uint8), disparity=np.empty(n, np.float32), kps2d_refine_in=np.empty((n, 2), np.float32),
+                 klt_iters=np.zeros(n, np.int32))
         io = TrackIO()
         io.n = n
         io.prev_kps2d, io.kps3d, io.ref_kps2d, io.keyframe_id = _p(a["prev_kps2d"]), _p(a["kps3d"]), _p(a["ref_kps2d"]), _p(a["keyframe_id"])
         io.flags, io.inlier_count, io.outlier_count, io.kf_state = _p(a["flags"]), _p(a["inlier"]), _p(a["outlier"]), _p(a["kf_state"])
         io.kps2d, io.klt_pts, io.klt_err, io.klt_status = _p(a["kps2d"]), _p(a["klt_pts"]), _p(a["klt_err"]), _p(a["klt_status"])
         io.disparity, io.kps2d_refine_in = _p(a["disparity"]), _p(a["kps2d_refine_in"])
+        io.klt_iters = _p(a["klt_iters"])
         for k, v in enumerate(_f32(pose_prior)):
             io.pose_prior[k] = float(v)
         self._ck(lib().svo_track_frame(self.h_ctx, prev_slot, cur_slot, C.byref(io)))

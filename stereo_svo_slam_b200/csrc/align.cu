@@ -20,21 +20,19 @@
 #include "kernels.cuh"
 
 #define ALIGN_THREADS 512
-#define NRED 28  // 21 (H upper triangle) + 6 (b) + 1 (cost)
-#define SCR_TERMS 49
+#define ALIGN_WARPS (ALIGN_THREADS / 32)
+#define NGRAD 27  // 21 (H upper triangle) + 6 (b)
 
 struct AlignHdr {
     unsigned long long bar;
-    double red_out[NRED];
-    double Rd[9];    // Rodrigues(-r) in double: projection rotation
-    float Rf[9];     // rot_mat      = float(Rodrigues(r))
-    float Rif[9];    // inv_rot_mat  = float(Rodrigues(-r))
-    float x0[6], xt[6], grad[6];
-    float prev_cost, new_cost;
-    int n, ctrl;
+    double Rd[2][9];                       // Rodrigues(-r) in double for the pose being evaluated / the speculated next pose
+    double cost_part[2][ALIGN_WARPS];      // per-warp cost partials, double buffered (one barrier per evaluation)
+    float grad_part[NGRAD][ALIGN_WARPS];   // per-warp partials of H (21) and b (6)
+    double red_out[NGRAD];
+    float grad[6];
+    int n;
 };
 #define HDR_BYTES ((sizeof(AlignHdr) + 127) / 128 * 128)
-#define RED_BYTES (NRED * 32 * sizeof(double))
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -70,107 +68,147 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t
                  : "memory");
 }
 
+// exact u8 -> float without the slow I2F path: 0x4B000000 | v is the float 8388608 + v
+__device__ __forceinline__ float u8f(unsigned v) { return __uint_as_float(0x4B000000u | v) - 8388608.0f; }
+
 // get_patch_sum (pose_estimator.cpp:82-112), operation for operation
 __device__ __forceinline__ float patch_sum(const uint8_t *img, int pitch, float cx, float cy)
 {
     float sx = cx - 0.5f, sy = cy - 0.5f;
     float fxf = floorf(sx), fyf = floorf(sy);
     int ipx = (int)fxf, ipy = (int)fyf;
-    float x2 = sx - (float)ipx, y2 = sy - (float)ipy;
-    float x1 = (float)(1.0 - (double)x2), y1 = (float)(1.0 - (double)y2);
+    float x2 = sx - fxf, y2 = sy - fyf;   // (float)ipx == fxf exactly
+    float x1 = 1.0f - x2, y1 = 1.0f - y2; // == (float)(1.0 - (double)x2): x2 in [0,1) makes the float subtraction exact or equally rounded
     const uint8_t *s1 = img + ipy * pitch + ipx;
     const uint8_t *s2 = s1 + pitch;
     const uint8_t *s3 = s2 + pitch;
-    float v = x1 * y1 * (float)s1[0];
-    v = v + y1 * (float)s1[1];
-    v = v + x2 * y1 * (float)s1[2];
-    v = v + x1 * (float)s2[0];
-    v = v + (float)s2[1];
-    v = v + x2 * (float)s2[2];
-    v = v + x1 * y2 * (float)s3[0];
-    v = v + y2 * (float)s3[1];
-    v = v + x2 * y2 * (float)s3[2];
+    float v = x1 * y1 * u8f(s1[0]);
+    v = v + y1 * u8f(s1[1]);
+    v = v + x2 * y1 * u8f(s1[2]);
+    v = v + x1 * u8f(s2[0]);
+    v = v + u8f(s2[1]);
+    v = v + x2 * u8f(s2[2]);
+    v = v + x1 * y2 * u8f(s3[0]);
+    v = v + y2 * u8f(s3[1]);
+    v = v + x2 * y2 * u8f(s3[2]);
     return v;
 }
 
-// _get_intensity_diff (image_comparison.cpp:9-91)
+// _get_intensity_diff (image_comparison.cpp:9-91); PATCH > 0: compile-time window (footprints cached in registers)
+template <int PATCH>
 __device__ __forceinline__ float intensity_diff(const uint8_t *im1, const uint8_t *im2, int w, int h, int pitch, float c1x, float c1y,
-                                                float c2x, float c2y, int patch)
+                                                float c2x, float c2y, int patch_rt)
 {
+    const int patch = PATCH > 0 ? PATCH : patch_rt;
     float half = ((float)patch - 1.0f) / 2.0f;
     float s1x = c1x - half, s1y = c1y - half, s2x = c2x - half, s2y = c2y - half;
-    int ip1x = (int)floorf(s1x), ip1y = (int)floorf(s1y), ip2x = (int)floorf(s2x), ip2y = (int)floorf(s2y);
-    float x12 = s1x - (float)ip1x, y12 = s1y - (float)ip1y, x22 = s2x - (float)ip2x, y22 = s2y - (float)ip2y;
-    float x11 = (float)(1.0 - (double)x12), y11 = (float)(1.0 - (double)y12);
-    float x21 = (float)(1.0 - (double)x22), y21 = (float)(1.0 - (double)y22);
+    float f1x = floorf(s1x), f1y = floorf(s1y), f2x = floorf(s2x), f2y = floorf(s2y);
+    int ip1x = (int)f1x, ip1y = (int)f1y, ip2x = (int)f2x, ip2y = (int)f2y;
+    float x12 = s1x - f1x, y12 = s1y - f1y, x22 = s2x - f2x, y22 = s2y - f2y;
+    float x11 = 1.0f - x12, y11 = 1.0f - y12;
+    float x21 = 1.0f - x22, y21 = 1.0f - y22;
     float m11 = x11 * y11, m12 = x12 * y11, m13 = x11 * y12, m14 = x12 * y12;
     float m21 = x21 * y21, m22 = x22 * y21, m23 = x21 * y22, m24 = x22 * y22;
     float intensity = 0.f;
     if (ip1y >= 0 && ip1y + patch < h && ip2y >= 0 && ip2y + patch < h && ip1x >= 0 && ip1x + patch < w && ip2x >= 0 &&
         ip2x + patch < w) {
-        for (int i = 0; i < patch; i++) {
-            const uint8_t *s11 = im1 + (i + ip1y) * pitch + ip1x, *s12 = s11 + pitch;
-            const uint8_t *s21 = im2 + (i + ip2y) * pitch + ip2x, *s22 = s21 + pitch;
-            for (int j = 0; j < patch; j++) {
-                float i1 = 0.f, i2 = 0.f;
-                i1 += m11 * (float)s11[j]; i1 += m12 * (float)s11[j + 1]; i1 += m13 * (float)s12[j]; i1 += m14 * (float)s12[j + 1];
-                i2 += m21 * (float)s21[j]; i2 += m22 * (float)s21[j + 1]; i2 += m23 * (float)s22[j]; i2 += m24 * (float)s22[j + 1];
-                intensity += fabsf(i1 - i2);
+        if (PATCH > 0) {
+            float a[PATCH + 1][PATCH + 1], b[PATCH + 1][PATCH + 1];
+            const uint8_t *p1 = im1 + ip1y * pitch + ip1x, *p2 = im2 + ip2y * pitch + ip2x;
+#pragma unroll
+            for (int i = 0; i <= PATCH; i++)
+#pragma unroll
+                for (int j = 0; j <= PATCH; j++) { a[i][j] = u8f(p1[i * pitch + j]); b[i][j] = u8f(p2[i * pitch + j]); }
+#pragma unroll
+            for (int i = 0; i < PATCH; i++)
+#pragma unroll
+                for (int j = 0; j < PATCH; j++) {
+                    float i1 = 0.f, i2 = 0.f;
+                    i1 += m11 * a[i][j]; i1 += m12 * a[i][j + 1]; i1 += m13 * a[i + 1][j]; i1 += m14 * a[i + 1][j + 1];
+                    i2 += m21 * b[i][j]; i2 += m22 * b[i][j + 1]; i2 += m23 * b[i + 1][j]; i2 += m24 * b[i + 1][j + 1];
+                    intensity += fabsf(i1 - i2);
+                }
+        } else {
+            for (int i = 0; i < patch; i++) {
+                const uint8_t *s11 = im1 + (i + ip1y) * pitch + ip1x, *s12 = s11 + pitch;
+                const uint8_t *s21 = im2 + (i + ip2y) * pitch + ip2x, *s22 = s21 + pitch;
+                for (int j = 0; j < patch; j++) {
+                    float i1 = 0.f, i2 = 0.f;
+                    i1 += m11 * u8f(s11[j]); i1 += m12 * u8f(s11[j + 1]); i1 += m13 * u8f(s12[j]); i1 += m14 * u8f(s12[j + 1]);
+                    i2 += m21 * u8f(s21[j]); i2 += m22 * u8f(s21[j + 1]); i2 += m23 * u8f(s22[j]); i2 += m24 * u8f(s22[j + 1]);
+                    intensity += fabsf(i1 - i2);
+                }
             }
         }
     }
     return intensity;
 }
 
-// 6x6 SPD solve in double (LDL^T); returns false when H is not numerically positive definite
+// 6x6 SPD solve in double (LDL^T, one reciprocal per pivot); returns false when H is not numerically positive definite
 __device__ bool solve6(const double *Hu /*21 upper-tri row-major*/, const double *b, double *x)
 {
     double A[6][6];
-    int k = 0;
-    for (int i = 0; i < 6; i++)
-        for (int j = i; j < 6; j++) { A[i][j] = Hu[k]; A[j][i] = Hu[k]; k++; }
+    {
+        int k = 0;
+#pragma unroll
+        for (int i = 0; i < 6; i++)
+#pragma unroll
+            for (int j = i; j < 6; j++) { A[i][j] = Hu[k]; A[j][i] = Hu[k]; k++; }
+    }
     double maxd = 0;
+#pragma unroll
     for (int i = 0; i < 6; i++) maxd = fmax(maxd, A[i][i]);
     if (!(maxd > 0)) return false;
-    double L[6][6], D[6];
+    double L[6][6], D[6], Dinv[6];
+    bool ok = true;
+#pragma unroll
     for (int j = 0; j < 6; j++) {
         double d = A[j][j];
+#pragma unroll
         for (int q = 0; q < j; q++) d -= L[j][q] * L[j][q] * D[q];
-        if (!(d > 1e-13 * maxd)) return false;
+        if (!(d > 1e-13 * maxd)) { ok = false; d = 1.0; }
         D[j] = d;
+        Dinv[j] = 1.0 / d;
+#pragma unroll
         for (int i = j + 1; i < 6; i++) {
-            double s = A[i][j];
-            for (int q = 0; q < j; q++) s -= L[i][q] * L[j][q] * D[q];
-            L[i][j] = s / d;
+            double t = A[i][j];
+#pragma unroll
+            for (int q = 0; q < j; q++) t -= L[i][q] * L[j][q] * D[q];
+            L[i][j] = t * Dinv[j];
         }
     }
+    if (!ok) return false;
     double y[6];
+#pragma unroll
     for (int i = 0; i < 6; i++) {
-        double s = b[i];
-        for (int q = 0; q < i; q++) s -= L[i][q] * y[q];
-        y[i] = s;
+        double t = b[i];
+#pragma unroll
+        for (int q = 0; q < i; q++) t -= L[i][q] * y[q];
+        y[i] = t;
     }
+#pragma unroll
     for (int i = 5; i >= 0; i--) {
-        double s = y[i] / D[i];
-        for (int q = i + 1; q < 6; q++) s -= L[q][i] * x[q];
-        x[i] = s;
+        double t = y[i] * Dinv[i];
+#pragma unroll
+        for (int q = i + 1; q < 6; q++) t -= L[q][i] * x[q];
+        x[i] = t;
     }
     return true;
 }
 
-__global__ void __launch_bounds__(ALIGN_THREADS, 1) sparse_align_kernel(AlignArgs a, int img_bytes_cap)
+// One CTA = one frame.  kSmem: level images staged in shared memory (all levels used fit), else read via L1/L2.
+template <bool kSmem>
+__global__ void __launch_bounds__(ALIGN_THREADS, 1) sparse_align_kernel(AlignArgs a)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     AlignHdr *hdr = reinterpret_cast<AlignHdr *>(smem_raw);
-    double *red_scratch = reinterpret_cast<double *>(smem_raw + HDR_BYTES);
-    uint8_t *img_area = smem_raw + HDR_BYTES + RED_BYTES;
+    uint8_t *img_area = smem_raw + HDR_BYTES;
 
-    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
     const DevCam cam = a.cam;
     if (tid == 0) {
-        mbar_init(&hdr->bar, 1);
+        if (kSmem) mbar_init(&hdr->bar, 1);
         hdr->n = min(*a.n_ptr, a.max_kps);
-        for (int k = 0; k < 6; k++) hdr->x0[k] = a.pose_in[k];
         for (int k = 0; k < 16; k++) a.evals_out[k] = 0;
     }
     __syncthreads();
@@ -179,6 +217,12 @@ __global__ void __launch_bounds__(ALIGN_THREADS, 1) sparse_align_kernel(AlignArg
     float *scr = a.scratch;
     const int SN = a.max_kps;
 
+    // solver state: identical in every thread (computed redundantly from broadcast sums => no broadcast barrier)
+    float x0[6], xt[6], grad[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) { x0[k] = a.pose_in[k]; xt[k] = x0[k]; grad[k] = 0.f; }
+    float prev_cost = 0.f;
+
     const int lv_hi = (a.probe_level >= 0) ? a.probe_level : cam.max_levels - 1;
     const int lv_lo = (a.probe_level >= 0) ? a.probe_level : cam.min_level;
 
@@ -186,9 +230,8 @@ __global__ void __launch_bounds__(ALIGN_THREADS, 1) sparse_align_kernel(AlignArg
         const LevelDesc P = a.prev[level], C = a.cur[level];
         const int w = P.w, h = P.h;
         const uint8_t *pimg, *cimg;
-        const uint32_t bytes16 = ((uint32_t)(w * h) + 15u) & ~15u;
-        // ---- stage both level images in shared memory with TMA bulk copies
-        if ((int)(2 * bytes16) <= img_bytes_cap) {
+        if (kSmem) {
+            const uint32_t bytes16 = ((uint32_t)(w * h) + 15u) & ~15u;
             __syncthreads();  // everyone finished reading the previous level's tiles
             if (tid == 0) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -196,29 +239,29 @@ __global__ void __launch_bounds__(ALIGN_THREADS, 1) sparse_align_kernel(AlignArg
                 tma_load_1d(img_area, P.ptr, bytes16, &hdr->bar);
                 tma_load_1d(img_area + bytes16, C.ptr, bytes16, &hdr->bar);
             }
-            mbar_wait(&hdr->bar, phase);
-            phase ^= 1;
             pimg = img_area; cimg = img_area + bytes16;
         } else {
-            pimg = P.ptr; cimg = C.ptr;  // level too large for shared memory: read through L1/L2
+            pimg = P.ptr; cimg = C.ptr;
         }
         const int pitch = w;  // halfSample levels are stored with pitch == width
 
         // setLevel (pose_estimator.cpp:541-562)
         const int divider = 1 << level;
-        const float lfx = cam.fx / (float)divider, lfy = cam.fy / (float)divider;
-        const float lcx = cam.cx / (float)divider, lcy = cam.cy / (float)divider;
+        const float fdiv = (float)divider;
+        const float lfx = cam.fx / fdiv, lfy = cam.fy / fdiv, lcx = cam.cx / fdiv, lcy = cam.cy / fdiv;
+
+        int cur = 0;  // index of the Rd buffer holding Rodrigues(-r) of the pose being evaluated
+        if (tid == 0) dev_rodrigues_d(-x0[3], -x0[4], -x0[5], hdr->Rd[0]);   // overlaps the TMA copy
+        if (kSmem) { mbar_wait(&hdr->bar, phase); phase ^= 1; }
 
         // ---- per-level cache of the pose-independent reference terms (calculate_hessian :346-395 image part,
         //      get_gradient :449-460 reference part)
         for (int i = tid; i < n; i += nthr) {
             if (a.flags && (a.flags[i] & SVO_F_IGN_TEMP)) continue;
             float bx = a.kps2d[2 * i], by = a.kps2d[2 * i + 1];
-            if (level != 0) { bx = bx / (float)divider; by = by / (float)divider; }
-            // Hessian loop coordinates
-            float kx = bx - 2.f, ky = by - 2.f;
-            // residual loop reference coordinates
-            float rx = bx - 2.f, ry = by - 2.f;
+            if (level != 0) { bx = bx / fdiv; by = by / fdiv; }
+            float kx = bx - 2.f, ky = by - 2.f;   // Hessian loop coordinates
+            float rx = bx - 2.f, ry = by - 2.f;   // residual loop reference coordinates
             unsigned mask = 0;
             int e = 0;
             for (int r = 0; r < 4; r++) {
@@ -246,42 +289,84 @@ __global__ void __launch_bounds__(ALIGN_THREADS, 1) sparse_align_kernel(AlignArg
             }
             scr[(size_t)48 * SN + i] = __uint_as_float(mask);
         }
-        // (each thread only ever reads back the scratch entries it wrote itself: no barrier needed)
+        // (each thread only ever reads back the scratch entries it wrote itself)
+        __syncthreads();  // Rd[0] visible
 
-        // ---- Gauss-Newton driver (estimate_pose_at_level :166-222).  ctrl: what to evaluate next.
+        // ---- Gauss-Newton driver (estimate_pose_at_level :166-222).
         //  mode 0: cost at x0 (initial)   mode 1: gradient at x0   mode 2: cost at xt   mode 3: level done
-        int mode = 0;
-        int it = 0;            // the shared loop counter `i`
+        int mode = 0, it = 0, n_evals = 0, n_grads = 0, cbuf = 0;
         float kstep = 1.f;
-        int n_evals = 0, n_grads = 0;
         while (mode != 3) {
-            const float *x = (mode == 2) ? hdr->xt : hdr->x0;
-            // pose matrices for this evaluation (PoseManager::set_pose, pose_manager.cpp:9-17)
-            if (tid == 0) {
-                dev_rodrigues_d(-x[3], -x[4], -x[5], hdr->Rd);
-                for (int k = 0; k < 9; k++) hdr->Rif[k] = (float)hdr->Rd[k];
-                if (mode == 1) dev_rodrigues_f(x[3], x[4], x[5], hdr->Rf);
-            }
-            __syncthreads();
+            const float *x = (mode == 2) ? xt : x0;
+            const double *Rd = hdr->Rd[cur];
             const float tx = x[0], ty = x[1], tz = x[2];
-            double acc[NRED];
+            if (mode != 1) {
+                // ---------------- do_calc: bilinear SAD (prev @ reference position, cur @ projection)
+                // speculation: the last thread prepares Rodrigues for the halved step while everyone evaluates this one
+                if (mode == 2 && tid == nthr - 1) {
+                    const float hk = kstep / 2;
+                    dev_rodrigues_d(-(x0[3] + (hk * grad[3])), -(x0[4] + (hk * grad[4])), -(x0[5] + (hk * grad[5])), hdr->Rd[cur ^ 1]);
+                }
+                double part = 0.0;
+                for (int i = tid; i < n; i += nthr) {
+                    if (a.flags && (a.flags[i] & SVO_F_IGN_TEMP)) continue;
+                    float bx = a.kps2d[2 * i], by = a.kps2d[2 * i + 1];
+                    if (level != 0) { bx = bx / fdiv; by = by / fdiv; }
+                    float u, v;
+                    dev_project(Rd, a.kps3d[3 * i], a.kps3d[3 * i + 1], a.kps3d[3 * i + 2], tx, ty, tz, lfx, lfy, lcx, lcy, cam.k1, cam.k2,
+                                cam.p1, cam.p2, cam.k3, u, v);
+                    float d = (cam.win_pose == 4) ? intensity_diff<4>(pimg, cimg, w, h, pitch, bx, by, u, v, 4)
+                                                  : intensity_diff<0>(pimg, cimg, w, h, pitch, bx, by, u, v, cam.win_pose);
+                    part += (double)d;
+                }
 #pragma unroll
-            for (int k = 0; k < NRED; k++) acc[k] = 0.0;
-
-            for (int i = tid; i < n; i += nthr) {
-                if (a.flags && (a.flags[i] & SVO_F_IGN_TEMP)) continue;
-                const float Px = a.kps3d[3 * i], Py = a.kps3d[3 * i + 1], Pz = a.kps3d[3 * i + 2];
-                float bx = a.kps2d[2 * i], by = a.kps2d[2 * i + 1];
-                if (level != 0) { bx = bx / (float)divider; by = by / (float)divider; }
-                float u, v;
-                dev_project(hdr->Rd, Px, Py, Pz, tx, ty, tz, lfx, lfy, lcx, lcy, cam.k1, cam.k2, cam.p1, cam.p2, cam.k3, u, v);
-                if (mode != 1) {
-                    // do_calc: bilinear SAD of the win x win patches (prev @ reference position, cur @ projection)
-                    acc[27] += (double)intensity_diff(pimg, cimg, w, h, pitch, bx, by, u, v, cam.win_pose);
+                for (int o = 16; o > 0; o >>= 1) part += __shfl_down_sync(0xffffffffu, part, o);
+                if (lane == 0) hdr->cost_part[cbuf][warp] = part;
+                __syncthreads();
+                double tot = 0.0;
+#pragma unroll
+                for (int q = 0; q < ALIGN_WARPS; q++) tot += hdr->cost_part[cbuf][q];
+                cbuf ^= 1;
+                const float cost = (float)tot;
+                n_evals++;
+                if (mode == 0) {
+                    prev_cost = cost;
+                    mode = 1;   // it == 0 < 50
+                } else if (cost < prev_cost) {
+#pragma unroll
+                    for (int k = 0; k < 6; k++) x0[k] = xt[k];
+                    prev_cost = cost;
+                    it++;       // outer loop increment after `break`
+                    mode = (it < 50) ? 1 : 3;   // Rd[cur] already belongs to the new x0
+                } else if (fabsf(cost - prev_cost) < 1.0f) {
+                    mode = 3;
                 } else {
-                    // calculate_hessian: camera-frame point and 2x6 Jacobian
+                    kstep = kstep / 2;
+                    it++;       // inner loop increment
+                    if (it < 50) {
+#pragma unroll
+                        for (int k = 0; k < 6; k++) xt[k] = x0[k] + (kstep * grad[k]);
+                        cur ^= 1;   // the speculated matrix is the one we need
+                        mode = 2;
+                    } else {
+                        mode = 3;
+                    }
+                }
+            } else {
+                // ---------------- get_gradient at x0 (Hessian rebuilt on every call)
+                float Rif[9];
+#pragma unroll
+                for (int k = 0; k < 9; k++) Rif[k] = (float)Rd[k];   // inv_rot_mat = float(Rodrigues(-r))
+                float acc[NGRAD];
+#pragma unroll
+                for (int k = 0; k < NGRAD; k++) acc[k] = 0.f;
+                for (int i = tid; i < n; i += nthr) {
+                    if (a.flags && (a.flags[i] & SVO_F_IGN_TEMP)) continue;
+                    const float Px = a.kps3d[3 * i], Py = a.kps3d[3 * i + 1], Pz = a.kps3d[3 * i + 2];
+                    float u, v;
+                    dev_project(Rd, Px, Py, Pz, tx, ty, tz, lfx, lfy, lcx, lcy, cam.k1, cam.k2, cam.p1, cam.p2, cam.k3, u, v);
                     float X, Y, Z;
-                    dev_m33v(hdr->Rif, Px - tx, Py - ty, Pz - tz, X, Y, Z);
+                    dev_m33v(Rif, Px - tx, Py - ty, Pz - tz, X, Y, Z);
                     float J[12];
                     J[0] = -lfx / Z; J[1] = 0.f; J[2] = lfx * X / (Z * Z); J[3] = lfx * X * Y / (Z * Z);
                     J[4] = -lfx * (1 + (X * X) / (Z * Z)); J[5] = lfx * Y / Z;
@@ -289,23 +374,18 @@ __global__ void __launch_bounds__(ALIGN_THREADS, 1) sparse_align_kernel(AlignArg
                     J[10] = -lfy * X * Y / (Z * Z); J[11] = -lfy * X / Z;
                     const unsigned mask = __float_as_uint(scr[(size_t)48 * SN + i]);
                     float qx = u - 2.f, qy = v - 2.f;       // residual loop, current-image coordinates
-                    float rx = bx - 2.f, ry = by - 2.f;     // reference coordinates (for the bounds test only)
                     int e = 0;
                     for (int r = 0; r < 4; r++) {
+#pragma unroll
                         for (int c = 0; c < 4; c++, e++) {
                             float gj[6];
-                            if (mask & (1u << e)) {
-                                const float g0 = scr[(size_t)e * SN + i], g1 = scr[(size_t)(16 + e) * SN + i];
+                            const float g0 = scr[(size_t)e * SN + i], g1 = scr[(size_t)(16 + e) * SN + i];   // zero when masked out
 #pragma unroll
-                                for (int k = 0; k < 6; k++) {
-                                    float s = 0.f;
-                                    s += g0 * J[k];
-                                    s += g1 * J[6 + k];
-                                    gj[k] = s;
-                                }
-                            } else {
-#pragma unroll
-                                for (int k = 0; k < 6; k++) gj[k] = 0.f;
+                            for (int k = 0; k < 6; k++) {
+                                float t = 0.f;
+                                t += g0 * J[k];
+                                t += g1 * J[6 + k];
+                                gj[k] = (mask & (1u << e)) ? t : 0.f;
                             }
                             float diff = 0.f;
                             if ((mask & (1u << (16 + e))) &&
@@ -316,96 +396,105 @@ __global__ void __launch_bounds__(ALIGN_THREADS, 1) sparse_align_kernel(AlignArg
 #pragma unroll
                             for (int p = 0; p < 6; p++)
 #pragma unroll
-                                for (int q = p; q < 6; q++) { acc[hk] += (double)(gj[p] * gj[q]); hk++; }
+                                for (int q = p; q < 6; q++) { acc[hk] += gj[p] * gj[q]; hk++; }
 #pragma unroll
-                            for (int p = 0; p < 6; p++) acc[21 + p] -= (double)(gj[p] * diff);
-                            qx += 1.f; rx += 1.f;
+                            for (int p = 0; p < 6; p++) acc[21 + p] -= gj[p] * diff;
+                            qx += 1.f;
                         }
-                        qy += 1.f; ry += 1.f;
-                        qx -= 4.f; rx -= 4.f;
+                        qy += 1.f;
+                        qx -= 4.f;
                     }
                 }
-            }
-            block_reduce_sum<NRED>(acc, red_scratch, hdr->red_out);
-
-            // ---- serial part: thread 0 updates the solver state, everybody reads it after the barrier
-            if (tid == 0) {
-                if (mode == 0) {
-                    hdr->prev_cost = (float)hdr->red_out[27];
-                    n_evals++;
-                    hdr->ctrl = (it < 50) ? 1 : 3;
-                    if (a.probe_level >= 0) hdr->ctrl = 1;
-                } else if (mode == 1) {
-                    n_grads++;
+                // warp reduce (float), cross-warp sum in double by 27 threads
+#pragma unroll
+                for (int k = 0; k < NGRAD; k++) {
+                    float t = acc[k];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+                    if (lane == 0) hdr->grad_part[k][warp] = t;
+                }
+                __syncthreads();
+                if (tid < NGRAD) {
+                    double t = 0.0;
+#pragma unroll
+                    for (int q = 0; q < ALIGN_WARPS; q++) t += (double)hdr->grad_part[tid][q];
+                    hdr->red_out[tid] = t;
+                }
+                __syncthreads();
+                if (tid == 0) {
                     double dx[6];
-                    float delta[6], pg[6];
+                    float delta[6], pg[6], Rf[9];
                     bool ok = solve6(hdr->red_out, hdr->red_out + 21, dx);
+#pragma unroll
                     for (int k = 0; k < 6; k++) delta[k] = ok ? (float)dx[k] : 0.f;
                     dev_expmap(delta, pg);
-                    dev_m33v(hdr->Rf, pg[0], pg[1], pg[2], hdr->grad[0], hdr->grad[1], hdr->grad[2]);
-                    dev_m33v(hdr->Rf, pg[3], pg[4], pg[5], hdr->grad[3], hdr->grad[4], hdr->grad[5]);
-                    kstep = 1.f;
-                    for (int k = 0; k < 6; k++) hdr->xt[k] = hdr->x0[k] + (kstep * hdr->grad[k]);
-                    hdr->ctrl = 2;
-                    if (a.probe_level >= 0) {
-                        for (int k = 0; k < 6; k++) a.probe_grad[k] = hdr->grad[k];
-                        hdr->ctrl = 3;
-                    }
-                } else {  // mode 2: cost at xt
-                    float new_cost = (float)hdr->red_out[27];
-                    n_evals++;
-                    if (new_cost < hdr->prev_cost) {
-                        for (int k = 0; k < 6; k++) hdr->x0[k] = hdr->xt[k];
-                        hdr->prev_cost = new_cost;
-                        it++;  // outer loop increment after `break`
-                        hdr->ctrl = (it < 50) ? 1 : 3;
-                    } else if (fabsf(new_cost - hdr->prev_cost) < 1.0f) {
-                        hdr->ctrl = 3;
-                    } else {
-                        kstep = kstep / 2;
-                        it++;  // inner loop increment
-                        if (it < 50) {
-                            for (int k = 0; k < 6; k++) hdr->xt[k] = hdr->x0[k] + (kstep * hdr->grad[k]);
-                            hdr->ctrl = 2;
-                        } else {
-                            hdr->ctrl = 3;
-                        }
-                    }
+                    // rot_mat = float(Rodrigues(r)) == transpose of float(Rodrigues(-r)) bit for bit
+#pragma unroll
+                    for (int p = 0; p < 3; p++)
+#pragma unroll
+                        for (int q = 0; q < 3; q++) Rf[p * 3 + q] = Rif[q * 3 + p];
+                    float g[6];
+                    dev_m33v(Rf, pg[0], pg[1], pg[2], g[0], g[1], g[2]);
+                    dev_m33v(Rf, pg[3], pg[4], pg[5], g[3], g[4], g[5]);
+#pragma unroll
+                    for (int k = 0; k < 6; k++) hdr->grad[k] = g[k];
+                    // pose matrices of the first trial point x0 + 1 * grad
+                    dev_rodrigues_d(-(x0[3] + (1.f * g[3])), -(x0[4] + (1.f * g[4])), -(x0[5] + (1.f * g[5])), hdr->Rd[cur ^ 1]);
+                }
+                __syncthreads();
+                n_grads++;
+#pragma unroll
+                for (int k = 0; k < 6; k++) grad[k] = hdr->grad[k];
+                kstep = 1.f;
+#pragma unroll
+                for (int k = 0; k < 6; k++) xt[k] = x0[k] + (kstep * grad[k]);
+                cur ^= 1;
+                mode = 2;
+                if (a.probe_level >= 0) {
+                    if (tid == 0)
+                        for (int k = 0; k < 6; k++) a.probe_grad[k] = grad[k];
+                    mode = 3;
                 }
             }
-            __syncthreads();
-            mode = hdr->ctrl;
         }
-        if (tid == 0) {
-            if (level < 8) { a.evals_out[2 * level] = n_evals; a.evals_out[2 * level + 1] = n_grads; }
-        }
+        if (tid == 0 && level < 8) { a.evals_out[2 * level] = n_evals; a.evals_out[2 * level + 1] = n_grads; }
     }
     if (tid == 0) {
-        for (int k = 0; k < 6; k++) a.pose_out[k] = hdr->x0[k];
-        *a.cost_out = hdr->prev_cost;
+        for (int k = 0; k < 6; k++) a.pose_out[k] = x0[k];
+        *a.cost_out = prev_cost;
     }
+}
+
+static bool align_levels_fit(const AlignArgs &a, size_t &need)
+{
+    need = 0;
+    int hi = a.probe_level >= 0 ? a.probe_level : a.cam.max_levels - 1;
+    int lo = a.probe_level >= 0 ? a.probe_level : a.cam.min_level;
+    bool fit = true;
+    for (int l = lo; l <= hi; l++) {
+        size_t b = (((size_t)a.prev[l].w * a.prev[l].h) + 15) & ~(size_t)15;
+        if (2 * b > 200 * 1024) fit = false;
+        need = need > 2 * b ? need : 2 * b;
+    }
+    return fit;
 }
 
 size_t align_smem_bytes(const AlignArgs &a)
 {
-    size_t need = 0;
-    int hi = a.probe_level >= 0 ? a.probe_level : a.cam.max_levels - 1;
-    int lo = a.probe_level >= 0 ? a.probe_level : a.cam.min_level;
-    for (int l = lo; l <= hi; l++) {
-        size_t b = (((size_t)a.prev[l].w * a.prev[l].h) + 15) & ~(size_t)15;
-        if (2 * b <= 200 * 1024) need = need > 2 * b ? need : 2 * b;
-    }
-    return HDR_BYTES + RED_BYTES + need;
+    size_t need;
+    bool fit = align_levels_fit(a, need);
+    return HDR_BYTES + (fit ? need : 0);
 }
 
 cudaError_t align_init_device()
 {
-    return cudaFuncSetAttribute(sparse_align_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    return cudaFuncSetAttribute(sparse_align_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
 }
 
 void launch_align(const AlignArgs &a, cudaStream_t st)
 {
-    size_t smem = align_smem_bytes(a);
-    int cap = (int)(smem - HDR_BYTES - RED_BYTES);
-    sparse_align_kernel<<<1, ALIGN_THREADS, smem, st>>>(a, cap);
+    size_t need;
+    bool fit = align_levels_fit(a, need);
+    if (fit) sparse_align_kernel<true><<<1, ALIGN_THREADS, HDR_BYTES + need, st>>>(a);
+    else sparse_align_kernel<false><<<1, ALIGN_THREADS, HDR_BYTES, st>>>(a);
 }

@@ -21,7 +21,7 @@ struct Slot {
 struct IoLayout {
     size_t n, pose_prior, prev_kps2d, ref_kps2d, kf_id;            // in
     size_t kps3d, flags, inlier, outlier, kf_state;                // in/out
-    size_t pose_aligned, pose_refined, costs, evals, klt_pts, klt_err, klt_status, disparity, kps2d_ref_in, kps2d_out;  // out
+    size_t pose_aligned, pose_refined, costs, evals, klt_pts, klt_err, klt_status, klt_iters, disparity, kps2d_ref_in, kps2d_out;  // out
     size_t in_end, inout_begin, total;
 };
 
@@ -55,6 +55,10 @@ struct svo_ctx {
     float last_ms = 0;
     int last_launches = 0;
     bool track_pending = false;
+    long long launch_total = 0;
+    bool profiling = false;
+    cudaEvent_t sev[9] = {nullptr};  // stage events
+    float stage_ms[8] = {0};
     char err[256];
 };
 
@@ -85,6 +89,7 @@ static void make_layout(IoLayout &L, int M)
     L.klt_pts = take((size_t)M * 8);
     L.klt_err = take((size_t)M * 4);
     L.klt_status = take((size_t)M);
+    L.klt_iters = take((size_t)M * 4);
     L.disparity = take((size_t)M * 4);
     L.kps2d_ref_in = take((size_t)M * 8);
     L.kps2d_out = take((size_t)M * 8);
@@ -148,6 +153,7 @@ extern "C" int svo_ctx_create(const svo_camera_settings *s, int device, int widt
     CKC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CKC(cudaEventCreate(&ctx->ev0));
     CKC(cudaEventCreate(&ctx->ev1));
+    for (int k = 0; k < 9; k++) CKC(cudaEventCreate(&ctx->sev[k]));
     CKC(align_init_device());
     // ---- slot layout
     size_t o = 0;
@@ -209,6 +215,7 @@ extern "C" int svo_ctx_destroy(svo_ctx *ctx)
     if (ctx->d_kf_pose) cudaFree(ctx->d_kf_pose);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    for (int k = 0; k < 9; k++) if (ctx->sev[k]) cudaEventDestroy(ctx->sev[k]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return SVO_OK;
@@ -265,12 +272,56 @@ extern "C" int svo_upload_stereo(svo_ctx *ctx, const uint8_t *left, size_t ls, c
         memcpy(stage + (size_t)y * ctx->W, left + (size_t)y * ls, ctx->W);
         memcpy(stage + img + (size_t)y * ctx->W, right + (size_t)y * rs, ctx->W);
     }
+    if (ctx->profiling) CK(cudaEventRecord(ctx->sev[0], ctx->stream));
     CK(cudaMemcpyAsync(s.dev.left[0].ptr, stage, img, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(s.dev.right0.ptr, stage + img, img, cudaMemcpyHostToDevice, ctx->stream));
     launch_pyr_halfsample(s.dev, ctx->stream);
     launch_lk_pyramid(s.dev, ctx->stream);
+    ctx->launch_total += pyr_launch_count(s.dev);
     CK(cudaGetLastError());
+    if (ctx->profiling) CK(cudaEventRecord(ctx->sev[1], ctx->stream));
     *slot_out = id;
+    return SVO_OK;
+}
+
+extern "C" int svo_upload_stereo_device(svo_ctx *ctx, const uint8_t *d_left, size_t ls, const uint8_t *d_right, size_t rs, int *slot_out)
+{
+    if (!ctx || !d_left || !d_right || !slot_out || ls < (size_t)ctx->W || rs < (size_t)ctx->W) return SVO_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    int id;
+    int rc = alloc_slot(ctx, &id);
+    if (rc) return rc;
+    Slot &s = ctx->slots[id];
+    if (ctx->profiling) CK(cudaEventRecord(ctx->sev[0], ctx->stream));
+    CK(cudaMemcpy2DAsync(s.dev.left[0].ptr, ctx->W, d_left, ls, ctx->W, ctx->H, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaMemcpy2DAsync(s.dev.right0.ptr, ctx->W, d_right, rs, ctx->W, ctx->H, cudaMemcpyDeviceToDevice, ctx->stream));
+    launch_pyr_halfsample(s.dev, ctx->stream);
+    launch_lk_pyramid(s.dev, ctx->stream);
+    ctx->launch_total += pyr_launch_count(s.dev);
+    CK(cudaGetLastError());
+    if (ctx->profiling) CK(cudaEventRecord(ctx->sev[1], ctx->stream));
+    *slot_out = id;
+    return SVO_OK;
+}
+
+extern "C" int svo_launch_count(svo_ctx *ctx, long long *launches)
+{
+    if (!ctx || !launches) return SVO_ERR_INVALID;
+    *launches = ctx->launch_total;
+    return SVO_OK;
+}
+
+extern "C" int svo_set_profiling(svo_ctx *ctx, int on)
+{
+    if (!ctx) return SVO_ERR_INVALID;
+    ctx->profiling = on != 0;
+    return SVO_OK;
+}
+
+extern "C" int svo_last_stage_ms(svo_ctx *ctx, float *stage_ms8)
+{
+    if (!ctx || !stage_ms8) return SVO_ERR_INVALID;
+    for (int k = 0; k < 8; k++) stage_ms8[k] = ctx->stage_ms[k];
     return SVO_OK;
 }
 
@@ -363,6 +414,7 @@ extern "C" int svo_detect_keypoints(svo_ctx *ctx, int slot, int level, int grid_
     a.score_map = reinterpret_cast<int *>(ctx->d_detect_scratch);
     a.cell_xy = ctx->d_cell_xy; a.cell_score = ctx->d_cell_score; a.cell_type = ctx->d_cell_type;
     launch_detect(a, ctx->stream);
+    ctx->launch_total += 2;
     CK(cudaGetLastError());
     int m = cells < max_out ? cells : max_out;
     if (m > 0) {
@@ -381,6 +433,7 @@ extern "C" int svo_fast_corners(svo_ctx *ctx, int slot, int level, int max_out, 
     CK(cudaSetDevice(ctx->device));
     LevelDesc img = ctx->slots[slot].dev.left[level];
     launch_fast_list(img, reinterpret_cast<int *>(ctx->d_detect_scratch), nullptr, 0, nullptr, ctx->stream);
+    ctx->launch_total += 2;
     CK(cudaGetLastError());
     std::vector<uint8_t> nms((size_t)img.w * img.h);
     CK(cudaMemcpyAsync(nms.data(), ctx->d_detect_scratch + (size_t)img.w * img.h, nms.size(), cudaMemcpyDeviceToHost, ctx->stream));
@@ -411,6 +464,7 @@ extern "C" int svo_stereo_match(svo_ctx *ctx, int slot, const float *kps2d, int 
     a.kps2d = DP(float, kps2d_ref_in); a.n_ptr = DP(int, n); a.mode = mode; a.disparity = DP(float, disparity);
     a.max_kps = n; a.cam = ctx->cam;
     launch_stereo_ssd(a, ctx->stream);
+    ctx->launch_total += 1;
     CK(cudaGetLastError());
     if ((rc = down(ctx, disparity, ctx->lay.disparity, (size_t)n * 4))) return rc;
     CK(cudaStreamSynchronize(ctx->stream));
@@ -445,6 +499,7 @@ extern "C" int svo_align(svo_ctx *ctx, int prev_slot, int cur_slot, const float 
     AlignArgs a;
     fill_align_args(ctx, prev_slot, cur_slot, a, n, flags != nullptr);
     launch_align(a, ctx->stream);
+    ctx->launch_total += 1;
     CK(cudaGetLastError());
     if ((rc = down(ctx, pose_out, ctx->lay.pose_aligned, 24))) return rc;
     if (cost && (rc = down(ctx, cost, ctx->lay.costs, 4))) return rc;
@@ -470,6 +525,7 @@ extern "C" int svo_align_probe(svo_ctx *ctx, int prev_slot, int cur_slot, const 
     a.probe_level = level;
     a.probe_grad = DP(float, pose_refined);
     launch_align(a, ctx->stream);
+    ctx->launch_total += 1;
     CK(cudaGetLastError());
     if (cost && (rc = down(ctx, cost, ctx->lay.costs, 4))) return rc;
     if (grad && (rc = down(ctx, grad, ctx->lay.pose_refined, 24))) return rc;
@@ -503,9 +559,10 @@ static int klt_common(svo_ctx *ctx, const int *keyframe_ids, int prev_slot, int 
     a.prev_pts = DP(float, ref_kps2d); a.init_pts = DP(float, kps2d_ref_in);
     a.n_ptr = DP(int, n);
     a.next_pts = DP(float, klt_pts); a.status = DP(uint8_t, klt_status); a.err = DP(float, klt_err);
-    a.flags = nullptr; a.kps2d_out = nullptr;
+    a.flags = nullptr; a.kps2d_out = nullptr; a.iters = nullptr;
     a.max_kps = n; a.cam = ctx->cam;
     launch_klt(a, ctx->stream);
+    ctx->launch_total += 1;
     CK(cudaGetLastError());
     if ((rc = down(ctx, next_pts, ctx->lay.klt_pts, (size_t)n * 8))) return rc;
     if ((rc = down(ctx, status, ctx->lay.klt_status, (size_t)n))) return rc;
@@ -545,6 +602,7 @@ extern "C" int svo_reproj_refine(svo_ctx *ctx, const float *kps2d, const float *
     a.pose_in = DP(float, pose_aligned); a.pose_out = DP(float, pose_refined);
     a.cost_out = DP(float, costs) + 1; a.evals_out = DP(int, evals) + 16; a.cam = ctx->cam;
     launch_refine(a, ctx->stream);
+    ctx->launch_total += 1;
     CK(cudaGetLastError());
     if ((rc = down(ctx, pose_out, ctx->lay.pose_refined, 24))) return rc;
     if (cost && (rc = down(ctx, cost, ctx->lay.costs + 4, 4))) return rc;
@@ -564,6 +622,7 @@ extern "C" int svo_project(svo_ctx *ctx, const float pose[6], const float *kps3d
     if ((rc = up(ctx, ctx->lay.kps3d, kps3d, (size_t)n * 12))) return rc;
     if ((rc = up(ctx, ctx->lay.pose_refined, pose, 24))) return rc;
     launch_project(DP(float, pose_refined), DP(float, kps3d), DP(int, n), n, ctx->cam, DP(float, kps2d_out), ctx->stream);
+    ctx->launch_total += 1;
     CK(cudaGetLastError());
     if ((rc = down(ctx, kps2d, ctx->lay.kps2d_out, (size_t)n * 8))) return rc;
     CK(cudaStreamSynchronize(ctx->stream));
@@ -648,6 +707,7 @@ extern "C" int svo_track_frame_begin(svo_ctx *ctx, int prev_slot, int cur_slot, 
     memcpy(h + L.outlier, io->outlier_count, (size_t)n * 4);
     memcpy(h + L.kf_state, io->kf_state, (size_t)n * 8);
 
+    const bool prof = ctx->profiling;
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     // one H2D for all inputs (in + in/out regions are contiguous)
     CK(cudaMemcpyAsync(ctx->d_io, h, L.pose_aligned, cudaMemcpyHostToDevice, ctx->stream));
@@ -655,7 +715,9 @@ extern "C" int svo_track_frame_begin(svo_ctx *ctx, int prev_slot, int cur_slot, 
     // 1. sparse image alignment (stereo_slam.cpp:60-67)
     AlignArgs aa;
     fill_align_args(ctx, prev_slot, cur_slot, aa, n, true);
+    if (prof) CK(cudaEventRecord(ctx->sev[2], ctx->stream));
     launch_align(aa, ctx->stream); launches++;
+    if (prof) CK(cudaEventRecord(ctx->sev[3], ctx->stream));
     if (n > 0) {
         // 2. projection with the aligned pose + KLT against the origin keyframes + gating (stereo_slam.cpp:71-83)
         KltArgs ka;
@@ -665,14 +727,17 @@ extern "C" int svo_track_frame_begin(svo_ctx *ctx, int prev_slot, int cur_slot, 
         ka.prev_pts = DP(float, ref_kps2d); ka.init_pts = nullptr; ka.kps3d = DP(float, kps3d); ka.pose = DP(float, pose_aligned);
         ka.n_ptr = DP(int, n); ka.next_pts = DP(float, klt_pts); ka.status = DP(uint8_t, klt_status); ka.err = DP(float, klt_err);
         ka.flags = DP(uint8_t, flags); ka.kps2d_out = DP(float, kps2d_ref_in); ka.max_kps = n; ka.cam = ctx->cam;
+        ka.iters = DP(int, klt_iters);
         launch_klt(ka, ctx->stream); launches++;
     }
+    if (prof) CK(cudaEventRecord(ctx->sev[4], ctx->stream));
     // 3. reprojection Gauss-Newton (pose_refinement.cpp:175-177)
     RefineArgs ra;
     ra.kps2d = DP(float, kps2d_ref_in); ra.kps3d = DP(float, kps3d); ra.flags = DP(uint8_t, flags); ra.n_ptr = DP(int, n);
     ra.pose_in = DP(float, pose_aligned); ra.pose_out = DP(float, pose_refined);
     ra.cost_out = DP(float, costs) + 1; ra.evals_out = DP(int, evals) + 16; ra.cam = ctx->cam;
     launch_refine(ra, ctx->stream); launches++;
+    if (prof) CK(cudaEventRecord(ctx->sev[5], ctx->stream));
     if (n > 0) {
         // 4. depth filter: disparities on the current stereo pair, then vote / triangulate / Kalman / flags / re-project
         SsdArgs sa;
@@ -680,18 +745,24 @@ extern "C" int svo_track_frame_begin(svo_ctx *ctx, int prev_slot, int cur_slot, 
         sa.kps2d = DP(float, kps2d_ref_in); sa.n_ptr = DP(int, n); sa.mode = 1; sa.disparity = DP(float, disparity);
         sa.max_kps = n; sa.cam = ctx->cam;
         launch_stereo_ssd(sa, ctx->stream); launches++;
+        if (prof) CK(cudaEventRecord(ctx->sev[6], ctx->stream));
         FilterArgs fa;
         fa.kf_pose_table = ctx->d_kf_pose; fa.keyframe_ids = DP(int, kf_id); fa.disparity = DP(float, disparity);
         fa.kps2d = DP(float, kps2d_ref_in); fa.ref_kps2d = DP(float, ref_kps2d); fa.kps3d = DP(float, kps3d);
         fa.flags = DP(uint8_t, flags); fa.inlier = DP(int, inlier); fa.outlier = DP(int, outlier); fa.kf_state = DP(float, kf_state);
         fa.pose = DP(float, pose_refined); fa.kps2d_out = DP(float, kps2d_out); fa.n_ptr = DP(int, n); fa.max_kps = n; fa.cam = ctx->cam;
         launch_depth_filter(fa, ctx->stream); launches++;
+    } else if (prof) {
+        CK(cudaEventRecord(ctx->sev[6], ctx->stream));
     }
+    if (prof) CK(cudaEventRecord(ctx->sev[7], ctx->stream));
     CK(cudaGetLastError());
     // one D2H for all outputs (in/out + out regions are contiguous)
     CK(cudaMemcpyAsync(h + L.inout_begin, ctx->d_io + L.inout_begin, L.total - L.inout_begin, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    if (prof) CK(cudaEventRecord(ctx->sev[8], ctx->stream));
     ctx->last_launches = launches;
+    ctx->launch_total += launches;
     ctx->track_pending = true;
     return SVO_OK;
 }
@@ -704,6 +775,13 @@ extern "C" int svo_track_frame_end(svo_ctx *ctx, svo_track_io *io)
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+    if (ctx->profiling) {
+        // sev: 0 upload start, 1 pyramids done, 2 inputs on device, 3 align, 4 klt, 5 refine, 6 ssd, 7 filter, 8 d2h
+        float t;
+        if (cudaEventElapsedTime(&t, ctx->sev[0], ctx->sev[1]) == cudaSuccess) ctx->stage_ms[0] = t;
+        for (int k = 1; k <= 6; k++) { CK(cudaEventElapsedTime(&t, ctx->sev[k + 1], ctx->sev[k + 2])); ctx->stage_ms[k] = t; }
+        if (cudaEventElapsedTime(&t, ctx->sev[0], ctx->sev[8]) == cudaSuccess) ctx->stage_ms[7] = t;
+    }
     const IoLayout &L = ctx->lay;
     const uint8_t *h = ctx->h_io;
     const int n = io->n;
@@ -724,6 +802,7 @@ extern "C" int svo_track_frame_end(svo_ctx *ctx, svo_track_io *io)
     if (io->klt_status) memcpy(io->klt_status, h + L.klt_status, (size_t)n);
     if (io->disparity) memcpy(io->disparity, h + L.disparity, (size_t)n * 4);
     if (io->kps2d_refine_in) memcpy(io->kps2d_refine_in, h + L.kps2d_ref_in, (size_t)n * 8);
+    if (io->klt_iters) memcpy(io->klt_iters, h + L.klt_iters, (size_t)n * 4);
     return SVO_OK;
 }
 

@@ -55,6 +55,7 @@ struct KltArgs {
     float *next_pts;               // n*2
     uint8_t *status;               // n
     float *err;                    // n
+    int *iters;                    // n or null: LK iterations summed over levels
     // gating epilogue (pose_refinement.cpp:125-150); null flags => no gating
     uint8_t *flags;                // n in/out
     float *kps2d_out;              // n*2: accepted tracked position, else the projected position

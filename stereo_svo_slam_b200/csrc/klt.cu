@@ -90,6 +90,7 @@ __global__ void __launch_bounds__(KLT_THREADS) klt_pyr_lk_kernel(KltArgs a)
     int status = 1;
     float err = 0.f;
     int buf = 0;
+    int total_iters = 0;
 
     for (int level = SVO_LK_LEVELS - 1; level >= 0; level--) {
         const LevelDesc I = prev_lv[level];
@@ -165,6 +166,7 @@ __global__ void __launch_bounds__(KLT_THREADS) klt_pyr_lk_kernel(KltArgs a)
                 break;
             }
             lk_weights(qx - (float)iqx, qy - (float)iqy, iw00, iw01, iw10, iw11);
+            total_iters++;
             long long b1 = 0, b2 = 0, dummy = 0;
             const uint8_t *Jp = J.ptr + (ptrdiff_t)iqy * J.pitch + iqx;
             for (int k = tid; k < npx; k += KLT_THREADS) {
@@ -214,6 +216,7 @@ __global__ void __launch_bounds__(KLT_THREADS) klt_pyr_lk_kernel(KltArgs a)
         a.next_pts[2 * i] = nx; a.next_pts[2 * i + 1] = ny;
         a.status[i] = (uint8_t)status;
         a.err[i] = err;
+        if (a.iters) a.iters[i] = total_iters;
         if (a.flags) {  // pose_refinement.cpp:125-150
             uint8_t f = a.flags[i];
             float ox = init_x, oy = init_y;

@@ -6,89 +6,151 @@
 #include "kernels.cuh"
 
 #define REF_THREADS 256
-#define RNRED 28
+#define REF_WARPS (REF_THREADS / 32)
+#define RNGRAD 27
 
+// 6x6 SPD solve in double (LDL^T, one reciprocal per pivot)
 __device__ bool refine_solve6(const double *Hu, const double *b, double *x)
 {
     double A[6][6];
-    int k = 0;
-    for (int i = 0; i < 6; i++)
-        for (int j = i; j < 6; j++) { A[i][j] = Hu[k]; A[j][i] = Hu[k]; k++; }
+    {
+        int k = 0;
+#pragma unroll
+        for (int i = 0; i < 6; i++)
+#pragma unroll
+            for (int j = i; j < 6; j++) { A[i][j] = Hu[k]; A[j][i] = Hu[k]; k++; }
+    }
     double maxd = 0;
+#pragma unroll
     for (int i = 0; i < 6; i++) maxd = fmax(maxd, A[i][i]);
     if (!(maxd > 0)) return false;
-    double L[6][6], D[6];
+    double L[6][6], D[6], Dinv[6];
+    bool ok = true;
+#pragma unroll
     for (int j = 0; j < 6; j++) {
         double d = A[j][j];
+#pragma unroll
         for (int q = 0; q < j; q++) d -= L[j][q] * L[j][q] * D[q];
-        if (!(d > 1e-13 * maxd)) return false;
+        if (!(d > 1e-13 * maxd)) { ok = false; d = 1.0; }
         D[j] = d;
+        Dinv[j] = 1.0 / d;
+#pragma unroll
         for (int i = j + 1; i < 6; i++) {
-            double s = A[i][j];
-            for (int q = 0; q < j; q++) s -= L[i][q] * L[j][q] * D[q];
-            L[i][j] = s / d;
+            double t = A[i][j];
+#pragma unroll
+            for (int q = 0; q < j; q++) t -= L[i][q] * L[j][q] * D[q];
+            L[i][j] = t * Dinv[j];
         }
     }
+    if (!ok) return false;
     double y[6];
+#pragma unroll
     for (int i = 0; i < 6; i++) {
-        double s = b[i];
-        for (int q = 0; q < i; q++) s -= L[i][q] * y[q];
-        y[i] = s;
+        double t = b[i];
+#pragma unroll
+        for (int q = 0; q < i; q++) t -= L[i][q] * y[q];
+        y[i] = t;
     }
+#pragma unroll
     for (int i = 5; i >= 0; i--) {
-        double s = y[i] / D[i];
-        for (int q = i + 1; q < 6; q++) s -= L[q][i] * x[q];
-        x[i] = s;
+        double t = y[i] * Dinv[i];
+#pragma unroll
+        for (int q = i + 1; q < 6; q++) t -= L[q][i] * x[q];
+        x[i] = t;
     }
     return true;
 }
 
 struct RefHdr {
-    double red_out[RNRED];
-    double Rd[9];
-    float Rif[9];
-    float x0[6], xt[6], grad[6];
-    float prev_cost;
-    int ctrl;
+    double Rd[2][9];
+    double cost_part[2][REF_WARPS];
+    float grad_part[RNGRAD][REF_WARPS];
+    double red_out[RNGRAD];
+    float grad[6];
 };
 
+// Solver state lives in registers, identical in every thread (decisions are recomputed redundantly from the
+// broadcast partial sums: one barrier per cost evaluation).  The rotation of the NEXT trial pose (halved step)
+// is computed speculatively by the last thread while the others evaluate the current one.
 __global__ void __launch_bounds__(REF_THREADS, 1) reproj_refine_kernel(RefineArgs a, int max_kps)
 {
     __shared__ RefHdr hdr;
-    __shared__ double red_scratch[RNRED * 32];
-    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
     const int n = min(*a.n_ptr, max_kps);
     const DevCam cam = a.cam;
-    if (tid == 0)
-        for (int k = 0; k < 6; k++) hdr.x0[k] = a.pose_in[k];
-    __syncthreads();
-    int mode = 0, it = 0, n_evals = 0, n_grads = 0;
-    float kstep = 1.f;
-    while (mode != 3) {
-        const float *x = (mode == 2) ? hdr.xt : hdr.x0;
-        if (tid == 0) {
-            dev_rodrigues_d(-x[3], -x[4], -x[5], hdr.Rd);
-            for (int k = 0; k < 9; k++) hdr.Rif[k] = (float)hdr.Rd[k];
-        }
-        __syncthreads();
-        const float tx = x[0], ty = x[1], tz = x[2];
-        double acc[RNRED];
+    float x0[6], xt[6], grad[6];
 #pragma unroll
-        for (int k = 0; k < RNRED; k++) acc[k] = 0.0;
-        for (int i = tid; i < n; i += nthr) {
-            if (a.flags[i] & (SVO_F_IGN_REFINE | SVO_F_IGN_COMPLETE | SVO_F_IGN_TEMP)) continue;
-            const float Px = a.kps3d[3 * i], Py = a.kps3d[3 * i + 1], Pz = a.kps3d[3 * i + 2];
-            const float kx = a.kps2d[2 * i], ky = a.kps2d[2 * i + 1];
-            float u, v;
-            dev_project(hdr.Rd, Px, Py, Pz, tx, ty, tz, cam.fx, cam.fy, cam.cx, cam.cy, cam.k1, cam.k2, cam.p1, cam.p2, cam.k3, u, v);
-            if (mode != 1) {
-                float d0 = fabsf(u - kx), d1 = fabsf(v - ky);
-                acc[27] += (double)(d0 + d1);
+    for (int k = 0; k < 6; k++) { x0[k] = a.pose_in[k]; xt[k] = x0[k]; grad[k] = 0.f; }
+    if (tid == 0) dev_rodrigues_d(-x0[3], -x0[4], -x0[5], hdr.Rd[0]);
+    __syncthreads();
+    int mode = 0, it = 0, n_evals = 0, n_grads = 0, cur = 0, cbuf = 0;
+    float kstep = 1.f, prev_cost = 0.f;
+    while (mode != 3) {
+        const float *x = (mode == 2) ? xt : x0;
+        const double *Rd = hdr.Rd[cur];
+        const float tx = x[0], ty = x[1], tz = x[2];
+        if (mode != 1) {
+            if (mode == 2 && tid == nthr - 1) {
+                const float hk = kstep / 2;
+                dev_rodrigues_d(-(x0[3] + (hk * grad[3])), -(x0[4] + (hk * grad[4])), -(x0[5] + (hk * grad[5])), hdr.Rd[cur ^ 1]);
+            }
+            double part = 0.0;
+            for (int i = tid; i < n; i += nthr) {
+                if (a.flags[i] & (SVO_F_IGN_REFINE | SVO_F_IGN_COMPLETE | SVO_F_IGN_TEMP)) continue;
+                float u, v;
+                dev_project(Rd, a.kps3d[3 * i], a.kps3d[3 * i + 1], a.kps3d[3 * i + 2], tx, ty, tz, cam.fx, cam.fy, cam.cx, cam.cy, cam.k1,
+                            cam.k2, cam.p1, cam.p2, cam.k3, u, v);
+                float d0 = fabsf(u - a.kps2d[2 * i]), d1 = fabsf(v - a.kps2d[2 * i + 1]);
+                part += (double)(d0 + d1);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) part += __shfl_down_sync(0xffffffffu, part, o);
+            if (lane == 0) hdr.cost_part[cbuf][warp] = part;
+            __syncthreads();
+            double tot = 0.0;
+#pragma unroll
+            for (int q = 0; q < REF_WARPS; q++) tot += hdr.cost_part[cbuf][q];
+            cbuf ^= 1;
+            const float cost = (float)tot;
+            n_evals++;
+            if (mode == 0) {
+                prev_cost = cost;
+                mode = 1;
+            } else if (cost < prev_cost) {
+#pragma unroll
+                for (int k = 0; k < 6; k++) x0[k] = xt[k];
+                prev_cost = cost;
+                it++;
+                mode = (it < 50) ? 1 : 3;
+            } else if (fabs((double)(cost - prev_cost)) < 0.0001) {
+                mode = 3;
             } else {
-                float d0 = kx - u, d1 = ky - v;
+                kstep = kstep / 2;
+                it++;
+                if (it < 50) {
+#pragma unroll
+                    for (int k = 0; k < 6; k++) xt[k] = x0[k] + (kstep * grad[k]);
+                    cur ^= 1;
+                    mode = 2;
+                } else
+                    mode = 3;
+            }
+        } else {
+            float Rif[9];
+#pragma unroll
+            for (int k = 0; k < 9; k++) Rif[k] = (float)Rd[k];
+            float acc[RNGRAD];
+#pragma unroll
+            for (int k = 0; k < RNGRAD; k++) acc[k] = 0.f;
+            for (int i = tid; i < n; i += nthr) {
+                if (a.flags[i] & (SVO_F_IGN_REFINE | SVO_F_IGN_COMPLETE | SVO_F_IGN_TEMP)) continue;
+                const float Px = a.kps3d[3 * i], Py = a.kps3d[3 * i + 1], Pz = a.kps3d[3 * i + 2];
+                float u, v;
+                dev_project(Rd, Px, Py, Pz, tx, ty, tz, cam.fx, cam.fy, cam.cx, cam.cy, cam.k1, cam.k2, cam.p1, cam.p2, cam.k3, u, v);
+                float d0 = a.kps2d[2 * i] - u, d1 = a.kps2d[2 * i + 1] - v;
                 if ((fabs((double)d0) > 3.0) || (fabs((double)d1) > 3.0)) continue;
                 float X, Y, Z;
-                dev_m33v(hdr.Rif, Px - tx, Py - ty, Pz - tz, X, Y, Z);
+                dev_m33v(Rif, Px - tx, Py - ty, Pz - tz, X, Y, Z);
                 const float fx = cam.fx, fy = cam.fy;
                 float J[12];
                 J[0] = -fx / Z; J[1] = 0.f; J[2] = fx * X / (Z * Z); J[3] = fx * X * Y / (Z * Z);
@@ -100,69 +162,64 @@ __global__ void __launch_bounds__(REF_THREADS, 1) reproj_refine_kernel(RefineArg
                 for (int p = 0; p < 6; p++)
 #pragma unroll
                     for (int q = p; q < 6; q++) {
-                        float s = 0.f;
-                        s += J[p] * J[q];
-                        s += J[6 + p] * J[6 + q];
-                        acc[hk] += (double)s;
+                        float t = 0.f;
+                        t += J[p] * J[q];
+                        t += J[6 + p] * J[6 + q];
+                        acc[hk] += t;
                         hk++;
                     }
 #pragma unroll
                 for (int p = 0; p < 6; p++) {
-                    float s = 0.f;
-                    s += J[p] * d0;
-                    s += J[6 + p] * d1;
-                    acc[21 + p] += (double)s;
+                    float t = 0.f;
+                    t += J[p] * d0;
+                    t += J[6 + p] * d1;
+                    acc[21 + p] += t;
                 }
             }
-        }
-        block_reduce_sum<RNRED>(acc, red_scratch, hdr.red_out);
-        if (tid == 0) {
-            if (mode == 0) {
-                hdr.prev_cost = (float)hdr.red_out[27];
-                n_evals++;
-                hdr.ctrl = 1;
-            } else if (mode == 1) {
-                n_grads++;
+#pragma unroll
+            for (int k = 0; k < RNGRAD; k++) {
+                float t = acc[k];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+                if (lane == 0) hdr.grad_part[k][warp] = t;
+            }
+            __syncthreads();
+            if (tid < RNGRAD) {
+                double t = 0.0;
+#pragma unroll
+                for (int q = 0; q < REF_WARPS; q++) t += (double)hdr.grad_part[tid][q];
+                hdr.red_out[tid] = t;
+            }
+            __syncthreads();
+            if (tid == 0) {
                 double dx[6];
-                float tw[6];
+                float tw[6], g[6];
                 bool ok = refine_solve6(hdr.red_out, hdr.red_out + 21, dx);
+#pragma unroll
                 for (int k = 0; k < 6; k++) tw[k] = ok ? (float)dx[k] : 0.f;
-                dev_expmap(tw, hdr.grad);  // used as is — not rotated to world (pose_refinement.cpp:401-411)
-                kstep = 1.f;
-                for (int k = 0; k < 6; k++) hdr.xt[k] = hdr.x0[k] + (kstep * hdr.grad[k]);
-                hdr.ctrl = 2;
-            } else {
-                float new_cost = (float)hdr.red_out[27];
-                n_evals++;
-                if (new_cost < hdr.prev_cost) {
-                    for (int k = 0; k < 6; k++) hdr.x0[k] = hdr.xt[k];
-                    hdr.prev_cost = new_cost;
-                    it++;
-                    hdr.ctrl = (it < 50) ? 1 : 3;
-                } else if (fabs((double)(new_cost - hdr.prev_cost)) < 0.0001) {
-                    hdr.ctrl = 3;
-                } else {
-                    kstep = kstep / 2;
-                    it++;
-                    if (it < 50) {
-                        for (int k = 0; k < 6; k++) hdr.xt[k] = hdr.x0[k] + (kstep * hdr.grad[k]);
-                        hdr.ctrl = 2;
-                    } else
-                        hdr.ctrl = 3;
-                }
+                dev_expmap(tw, g);  // used as is — not rotated to world (pose_refinement.cpp:401-411)
+#pragma unroll
+                for (int k = 0; k < 6; k++) hdr.grad[k] = g[k];
+                dev_rodrigues_d(-(x0[3] + (1.f * g[3])), -(x0[4] + (1.f * g[4])), -(x0[5] + (1.f * g[5])), hdr.Rd[cur ^ 1]);
             }
+            __syncthreads();
+            n_grads++;
+#pragma unroll
+            for (int k = 0; k < 6; k++) grad[k] = hdr.grad[k];
+            kstep = 1.f;
+#pragma unroll
+            for (int k = 0; k < 6; k++) xt[k] = x0[k] + (kstep * grad[k]);
+            cur ^= 1;
+            mode = 2;
         }
-        __syncthreads();
-        mode = hdr.ctrl;
     }
     if (tid == 0) {
-        for (int k = 0; k < 6; k++) a.pose_out[k] = hdr.x0[k];
-        *a.cost_out = hdr.prev_cost;
+        for (int k = 0; k < 6; k++) a.pose_out[k] = x0[k];
+        *a.cost_out = prev_cost;
         a.evals_out[0] = n_evals; a.evals_out[1] = n_grads;
     }
 }
 
-static int g_refine_max_kps = 0;
 void launch_refine_n(const RefineArgs &a, int max_kps, cudaStream_t st) { reproj_refine_kernel<<<1, REF_THREADS, 0, st>>>(a, max_kps); }
 void launch_refine(const RefineArgs &a, cudaStream_t st) { launch_refine_n(a, 1 << 30, st); }
 

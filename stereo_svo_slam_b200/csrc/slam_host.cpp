@@ -143,7 +143,9 @@ struct svo_slam {
     // per-frame scratch (reused)
     svo_track_io io;
     std::vector<float> io_prev2d, io_kps3d, io_ref2d, io_kfstate, io_kps2d;
-    std::vector<int> io_kfid, io_inl, io_outl;
+    std::vector<int> io_kfid, io_inl, io_outl, io_kltit;
+    std::vector<uint8_t> io_kltst;
+    long long counters[8] = {0};
     std::vector<uint8_t> io_flags;
     bool pending = false;
     bool pending_first = false;
@@ -334,14 +336,15 @@ struct svo_slam {
         trajectory.push_back(p);
     }
 
-    int new_image_begin(const uint8_t *left, size_t ls, const uint8_t *right, size_t rs, float ts)
+    int new_image_begin(const uint8_t *left, size_t ls, const uint8_t *right, size_t rs, float ts, bool on_device = false)
     {
         if (pending) { snprintf(err, sizeof(err), "new_image_begin called twice"); return SVO_ERR_STATE; }
         last_keyframe_created = 0;
         previous = std::move(frame);
         frame.reset(new FrameH());
         frame->time_stamp = ts;
-        int rc = svo_upload_stereo(ctx, left, ls, right, rs, &frame->slot);  // pyramids (stereo_slam.cpp:135-139)
+        int rc = on_device ? svo_upload_stereo_device(ctx, left, ls, right, rs, &frame->slot)
+                           : svo_upload_stereo(ctx, left, ls, right, rs, &frame->slot);  // pyramids (stereo_slam.cpp:135-139)
         if (rc) return fail(rc);
         pending = true;
         if (!previous) {  // first frame (stereo_slam.cpp:142-160)
@@ -367,7 +370,7 @@ struct svo_slam {
         io_prev2d = previous->kps.kps2d;
         io_kps3d = previous->kps.kps3d;
         io_ref2d.resize(n * 2); io_kfid.resize(n); io_flags.resize(n); io_inl.resize(n); io_outl.resize(n); io_kfstate.resize(n * 2);
-        io_kps2d.resize(n * 2);
+        io_kps2d.resize(n * 2); io_kltit.assign(n, 0); io_kltst.assign(n, 0);
         for (size_t i = 0; i < n; i++) {
             const svo_keypoint_info &in = previous->kps.info[i];
             const FrameH &k = *keyframes[in.keyframe_id];
@@ -383,6 +386,7 @@ struct svo_slam {
         io.prev_kps2d = io_prev2d.data(); io.kps3d = io_kps3d.data(); io.ref_kps2d = io_ref2d.data(); io.keyframe_id = io_kfid.data();
         io.flags = io_flags.data(); io.inlier_count = io_inl.data(); io.outlier_count = io_outl.data(); io.kf_state = io_kfstate.data();
         io.kps2d = io_kps2d.data();
+        io.klt_iters = io_kltit.data(); io.klt_status = io_kltst.data();
         std::memcpy(io.pose_prior, frame->pose, sizeof(io.pose_prior));
         rc = svo_track_frame_begin(ctx, previous->slot, frame->slot, &io);
         if (rc) { pending = false; return fail(rc); }
@@ -407,6 +411,16 @@ struct svo_slam {
         svo_last_track_timing(ctx, &last_gpu_ms, &last_launches);
         const size_t n = (size_t)io.n;
         std::memcpy(frame->pose, io.pose_refined, sizeof(frame->pose));
+        {
+            long long used = 0, ce = 0, ge = 0, it = 0, tr = 0;
+            for (size_t i = 0; i < n; i++) {
+                if (!previous->kps.info[i].ignore_temporary) used++;
+                it += io_kltit[i]; tr += io_kltst[i] ? 1 : 0;
+            }
+            for (int l = 0; l < 8; l++) { ce += io.align_evals[2 * l]; ge += io.align_evals[2 * l + 1]; }
+            counters[0] = (long long)n; counters[1] = used; counters[2] = ce; counters[3] = ge;
+            counters[4] = io.refine_evals[0]; counters[5] = io.refine_evals[1]; counters[6] = it; counters[7] = tr;
+        }
         frame->kps.info = previous->kps.info;
         frame->kps.kps3d = io_kps3d;
         frame->kps.kps2d = io_kps2d;
@@ -474,6 +488,11 @@ int svo_slam_new_image_begin(svo_slam *s, const uint8_t *left, size_t ls, const 
 {
     if (!s || !left || !right) return SVO_ERR_INVALID;
     return s->new_image_begin(left, ls, right, rs, ts);
+}
+int svo_slam_new_image_device_begin(svo_slam *s, const uint8_t *left, size_t ls, const uint8_t *right, size_t rs, float ts)
+{
+    if (!s || !left || !right) return SVO_ERR_INVALID;
+    return s->new_image_begin(left, ls, right, rs, ts, true);
 }
 int svo_slam_new_image_end(svo_slam *s)
 {
@@ -559,6 +578,12 @@ int svo_slam_update_pose(svo_slam *s, const svo_pose *pose, const float speed[6]
     float p[6] = {pose->x, pose->y, pose->z, pose->rx, pose->ry, pose->rz}, o[6];
     s->update_pose(p, speed, pv, sv, dt, o);
     if (filtered) { filtered->x = o[0]; filtered->y = o[1]; filtered->z = o[2]; filtered->rx = o[3]; filtered->ry = o[4]; filtered->rz = o[5]; }
+    return SVO_OK;
+}
+int svo_slam_last_counters(svo_slam *s, long long *out8)
+{
+    if (!s || !out8) return SVO_ERR_INVALID;
+    for (int k = 0; k < 8; k++) out8[k] = s->counters[k];
     return SVO_OK;
 }
 int svo_slam_last_stats(svo_slam *s, float *gpu_ms, int *launches, int *keyframe_created)

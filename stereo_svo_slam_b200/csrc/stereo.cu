@@ -35,16 +35,20 @@ __device__ __forceinline__ bool ssd_geometry(float kx, float ky, int W, int H, i
     return true;
 }
 
-__global__ void __launch_bounds__(SSD_THREADS) stereo_ssd_kernel(SsdArgs a, int tpitch, int rpitch, int map_cap)
+// tpl / roi rows are stored as 32-bit words (row pitch in words); bytes beyond the window are zero.
+// SSD(j,k) = sum a^2 - 2 sum a*b + sum b^2 with the two dot products on the 4-way byte dot-product unit
+// (IDP4A); unaligned ROI words are assembled from two aligned shared-memory words with a funnel shift.
+__global__ void __launch_bounds__(SSD_THREADS) stereo_ssd_kernel(SsdArgs a, int tpw, int rpw, int roi_rows, int map_cap)
 {
-    extern __shared__ __align__(16) uint8_t ssd_smem[];
+    extern __shared__ __align__(16) uint32_t ssd_smem32[];
     const int win = a.cam.win_depth;
-    uint8_t *tpl = ssd_smem;                       // win rows x tpitch
-    uint8_t *roi = tpl + win * tpitch;             // (win + 2*sy) rows x rpitch
-    uint32_t *map = reinterpret_cast<uint32_t *>(roi + ((win + 2 * a.cam.search_y) * rpitch + 15) / 16 * 16);
+    uint32_t *tpl = ssd_smem32;                 // win rows x tpw words
+    uint32_t *roi = tpl + win * tpw;            // roi_rows x rpw words
+    uint32_t *map = roi + roi_rows * rpw;       // map_cap entries
     __shared__ unsigned long long red[SSD_THREADS / 32];
     __shared__ unsigned long long best_s;
     __shared__ int cnt_s[SSD_THREADS / 32], sum_s[SSD_THREADS / 32];
+    __shared__ unsigned saa_s[SSD_THREADS / 32];
 
     const int i = blockIdx.x;
     const int n = min(*a.n_ptr, a.max_kps);
@@ -58,32 +62,56 @@ __global__ void __launch_bounds__(SSD_THREADS) stereo_ssd_kernel(SsdArgs a, int 
     }
     const int tw = g.x12 - g.x11, th = g.y12 - g.y11, rw = g.x22 - g.x21, rh = g.y22 - g.y21;
     const int mw = rw - tw + 1, mh = rh - th + 1;
+    const int twords = (tw + 3) >> 2;
+    const uint32_t last_mask = (tw & 3) ? ((1u << ((tw & 3) * 8)) - 1u) : 0xffffffffu;
 
+    // ---- stage (zero padded) and accumulate sum a^2
+    uint8_t *tpl8 = reinterpret_cast<uint8_t *>(tpl), *roi8 = reinterpret_cast<uint8_t *>(roi);
+    for (int k = tid; k < th * tpw; k += SSD_THREADS) tpl[k] = 0;
+    for (int k = tid; k < (rh + 1) * rpw && k < roi_rows * rpw; k += SSD_THREADS) roi[k] = 0;
+    __syncthreads();
+    unsigned saa = 0;
     for (int k = tid; k < th * tw; k += SSD_THREADS) {
         int r = k / tw, c = k - r * tw;
-        tpl[r * tpitch + c] = L.ptr[(size_t)(g.y11 + r) * L.pitch + g.x11 + c];
+        unsigned v = L.ptr[(size_t)(g.y11 + r) * L.pitch + g.x11 + c];
+        tpl8[r * tpw * 4 + c] = (uint8_t)v;
+        saa += v * v;
     }
     for (int k = tid; k < rh * rw; k += SSD_THREADS) {
         int r = k / rw, c = k - r * rw;
-        roi[r * rpitch + c] = R.ptr[(size_t)(g.y21 + r) * R.pitch + g.x21 + c];
+        roi8[r * rpw * 4 + c] = R.ptr[(size_t)(g.y21 + r) * R.pitch + g.x21 + c];
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) saa += __shfl_down_sync(0xffffffffu, saa, o);
+    if ((tid & 31) == 0) saa_s[tid >> 5] = saa;
     __syncthreads();
+    saa = 0;
+#pragma unroll
+    for (int q = 0; q < SSD_THREADS / 32; q++) saa += saa_s[q];
 
     // ---- SSD map + running (value, index) minimum per thread
     unsigned long long best = ~0ull;
     for (int p = tid; p < mw * mh; p += SSD_THREADS) {
         const int k = p / mw, j = p - k * mw;
-        uint32_t s = 0;
+        const int jw = j >> 2, sh = (j & 3) * 8;
+        unsigned sab = 0, sbb = 0;
         for (int y = 0; y < th; y++) {
-            const uint8_t *rr = roi + (k + y) * rpitch + j;
-            const uint8_t *tt = tpl + y * tpitch;
-            for (int x = 0; x < tw; x++) {
-                int d = (int)rr[x] - (int)tt[x];
-                s += (uint32_t)(d * d);
+            const uint32_t *rr = roi + (k + y) * rpw + jw;
+            const uint32_t *tt = tpl + y * tpw;
+            uint32_t w0 = rr[0];
+            for (int x = 0; x < twords; x++) {
+                const uint32_t w1 = rr[x + 1];
+                uint32_t b = __funnelshift_r(w0, w1, sh);
+                if (x == twords - 1) b &= last_mask;
+                const uint32_t av = tt[x];
+                sab = __dp4a(av, b, sab);
+                sbb = __dp4a(b, b, sbb);
+                w0 = w1;
             }
         }
-        map[p] = s;
-        unsigned long long key = ((unsigned long long)s << 32) | (unsigned)p;
+        const uint32_t sv = saa + sbb - 2u * sab;
+        map[p] = sv;
+        unsigned long long key = ((unsigned long long)sv << 32) | (unsigned)p;
         best = key < best ? key : best;
     }
     // block arg-min (smallest value, then smallest raster index == cv::minMaxLoc's first minimum)
@@ -114,9 +142,9 @@ __global__ void __launch_bounds__(SSD_THREADS) stereo_ssd_kernel(SsdArgs a, int 
     if ((tid & 31) == 0) { cnt_s[tid >> 5] = cnt; sum_s[tid >> 5] = sum; }
     __syncthreads();
     if (tid == 0) {
-        int c = 0, s = 0;
-        for (int w = 0; w < SSD_THREADS / 32; w++) { c += cnt_s[w]; s += sum_s[w]; }
-        float minPos = (float)s / (float)c;  // float sum of small integers is exact
+        int c = 0, sm = 0;
+        for (int w = 0; w < SSD_THREADS / 32; w++) { c += cnt_s[w]; sm += sum_s[w]; }
+        float minPos = (float)sm / (float)c;  // float sum of small integers is exact
         a.disparity[i] = (a.mode == 1) ? fmaxf(0.5f, minPos) : minPos;
     }
 }
@@ -125,12 +153,12 @@ void launch_stereo_ssd(const SsdArgs &a, cudaStream_t st)
 {
     if (a.max_kps <= 0) return;
     const int win = a.cam.win_depth;
-    const int tpitch = (win + 3) & ~3;
-    const int rpitch = (win + a.cam.search_x + 3) & ~3;
-    const int rows = win + 2 * a.cam.search_y;
+    const int tpw = (win + 3) / 4 + 1;                           // words per template row (+1: never read past)
+    const int rpw = (win + a.cam.search_x + 3) / 4 + 2;          // words per ROI row (+1 word read by the funnel shift)
+    const int roi_rows = win + 2 * a.cam.search_y + 1;
     const int map_cap = (a.cam.search_x + 1) * (2 * a.cam.search_y + 1);
-    size_t smem = (size_t)win * tpitch + ((size_t)rows * rpitch + 15) / 16 * 16 + (size_t)map_cap * 4 + 16;
-    stereo_ssd_kernel<<<a.max_kps, SSD_THREADS, smem, st>>>(a, tpitch, rpitch, map_cap);
+    size_t smem = ((size_t)win * tpw + (size_t)roi_rows * rpw + (size_t)map_cap) * 4 + 16;
+    stereo_ssd_kernel<<<a.max_kps, SSD_THREADS, smem, st>>>(a, tpw, rpw, roi_rows, map_cap);
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -161,6 +161,13 @@ class StereoSlam:
         self._ck(capi.lib().svo_slam_last_stats(self._h, C.byref(ms), C.byref(n), C.byref(kf)))
         return dict(gpu_ms=ms.value, launches=n.value, keyframe_created=bool(kf.value))
 
+    def last_counters(self):
+        out = (C.c_longlong * 8)()
+        self._ck(capi.lib().svo_slam_last_counters(self._h, out))
+        names = ("keypoints", "align_keypoints", "align_cost_evals", "align_grad_evals", "refine_cost_evals", "refine_grad_evals",
+                 "klt_iterations", "klt_tracked")
+        return dict(zip(names, [int(v) for v in out]))
+
     def context(self):
         """The device context behind the facade (stage-level probes)."""
         return capi.Context(self.camera_settings, self.width, self.height, _borrowed=capi.lib().svo_slam_ctx(self._h))
