@@ -396,9 +396,9 @@ __global__ void __launch_bounds__(ALIGN_THREADS, 1) sparse_align_kernel(AlignArg
 #pragma unroll
                             for (int p = 0; p < 6; p++)
 #pragma unroll
-                                for (int q = p; q < 6; q++) { acc[hk] += gj[p] * gj[q]; hk++; }
+                                for (int q = p; q < 6; q++) { acc[hk] = __fmaf_rn(gj[p], gj[q], acc[hk]); hk++; }   // sum order differs from the reference anyway
 #pragma unroll
-                            for (int p = 0; p < 6; p++) acc[21 + p] -= gj[p] * diff;
+                            for (int p = 0; p < 6; p++) acc[21 + p] = __fmaf_rn(-gj[p], diff, acc[21 + p]);
                             qx += 1.f;
                         }
                         qy += 1.f;

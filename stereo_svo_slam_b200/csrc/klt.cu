@@ -17,12 +17,14 @@
 // barrier: one __syncthreads per LK iteration.
 #include "kernels.cuh"
 
-#define KLT_THREADS 128
+#define KLT_THREADS 256
 #define KLT_MAXWIN 31
 #define KLT_TILE (KLT_MAXWIN + 3)  // window + bilinear (+1) + Scharr halo (+-1)
 
 struct KltShared {
     uint8_t tile[KLT_TILE * KLT_TILE + 4];
+    short gx[(KLT_MAXWIN + 1) * (KLT_MAXWIN + 1)];   // Scharr d/dx at the (win+1)^2 bilinear support positions
+    short gy[(KLT_MAXWIN + 1) * (KLT_MAXWIN + 1)];
     short Iw[KLT_MAXWIN * KLT_MAXWIN];
     short Ix[KLT_MAXWIN * KLT_MAXWIN];
     short Iy[KLT_MAXWIN * KLT_MAXWIN];
@@ -57,6 +59,7 @@ __device__ __forceinline__ void lk_weights(float a, float b, int &iw00, int &iw0
     iw11 = (1 << 14) - iw00 - iw01 - iw10;
 }
 
+template <int WIN>
 __global__ void __launch_bounds__(KLT_THREADS) klt_pyr_lk_kernel(KltArgs a)
 {
     __shared__ KltShared sm;
@@ -64,7 +67,7 @@ __global__ void __launch_bounds__(KLT_THREADS) klt_pyr_lk_kernel(KltArgs a)
     const int n = min(*a.n_ptr, a.max_kps);
     if (i >= n) return;
     const int tid = threadIdx.x;
-    const int win = a.cam.win_flow;
+    const int win = WIN > 0 ? WIN : a.cam.win_flow;   // compile-time window => divisions by constants
     const int npx = win * win;
     const float half = (float)(win - 1) * 0.5f;
 
@@ -118,28 +121,31 @@ __global__ void __launch_bounds__(KLT_THREADS) klt_pyr_lk_kernel(KltArgs a)
             sm.tile[k] = I.ptr[(ptrdiff_t)(ipy - 1 + r) * I.pitch + (ipx - 1 + c)];
         }
         __syncthreads();
+        // ---- Scharr derivatives at the (win+1)^2 support positions, OpenCV's border rule: REFLECT_101 inside the level
+        //      (already in the padded tile), constant 0 outside the level
+        const int W1 = win + 1;
+        for (int k = tid; k < W1 * W1; k += KLT_THREADS) {
+            int y = k / W1, x = k - y * W1;
+            const int X = ipx + x, Y = ipy + y;
+            int gxv = 0, gyv = 0;
+            if (X >= 0 && X < I.w && Y >= 0 && Y < I.h) {
+                const uint8_t *t = &sm.tile[(y + 1) * T + (x + 1)];
+                int tl = t[-T - 1], tc = t[-T], trr = t[-T + 1], ml = t[-1], mr = t[1], bl = t[T - 1], bc = t[T], br = t[T + 1];
+                gxv = 3 * (trr + br) + 10 * mr - (3 * (tl + bl) + 10 * ml);   // [3 10 3]^T x [-1 0 1]
+                gyv = 3 * ((bl - tl) + (br - trr)) + 10 * (bc - tc);          // [-1 0 1]^T x [3 10 3]
+            }
+            sm.gx[k] = (short)gxv; sm.gy[k] = (short)gyv;
+        }
+        __syncthreads();
         // ---- window template: Iw (Q5), Ix, Iy, and the structure tensor
         long long s11 = 0, s12 = 0, s22 = 0;
         for (int k = tid; k < npx; k += KLT_THREADS) {
             int y = k / win, x = k - y * win;
-            int ival = 0, ixv = 0, iyv = 0;
-#pragma unroll
-            for (int dy = 0; dy < 2; dy++)
-#pragma unroll
-                for (int dx = 0; dx < 2; dx++) {
-                    const int wgt = dy ? (dx ? iw11 : iw10) : (dx ? iw01 : iw00);
-                    const uint8_t *t = &sm.tile[(y + dy + 1) * T + (x + dx + 1)];
-                    ival += (int)t[0] * wgt;
-                    const int X = ipx + x + dx, Y = ipy + y + dy;
-                    if (X >= 0 && X < I.w && Y >= 0 && Y < I.h) {
-                        // Scharr: d/dx = [3 10 3]^T x [-1 0 1], d/dy = [-1 0 1]^T x [3 10 3]
-                        int tl = t[-T - 1], tc = t[-T], trr = t[-T + 1], ml = t[-1], mr = t[1], bl = t[T - 1], bc = t[T], br = t[T + 1];
-                        int gx = 3 * (trr + br) + 10 * mr - (3 * (tl + bl) + 10 * ml);
-                        int gy = 3 * ((bl - tl) + (br - trr)) + 10 * (bc - tc);
-                        ixv += gx * wgt;
-                        iyv += gy * wgt;
-                    }
-                }
+            const uint8_t *t = &sm.tile[(y + 1) * T + (x + 1)];
+            const short *px_ = &sm.gx[y * W1 + x], *py_ = &sm.gy[y * W1 + x];
+            int ival = (int)t[0] * iw00 + (int)t[1] * iw01 + (int)t[T] * iw10 + (int)t[T + 1] * iw11;
+            int ixv = (int)px_[0] * iw00 + (int)px_[1] * iw01 + (int)px_[W1] * iw10 + (int)px_[W1 + 1] * iw11;
+            int iyv = (int)py_[0] * iw00 + (int)py_[1] * iw01 + (int)py_[W1] * iw10 + (int)py_[W1 + 1] * iw11;
             ival = (ival + (1 << 8)) >> 9;
             ixv = (ixv + (1 << 13)) >> 14;
             iyv = (iyv + (1 << 13)) >> 14;
@@ -233,5 +239,6 @@ __global__ void __launch_bounds__(KLT_THREADS) klt_pyr_lk_kernel(KltArgs a)
 void launch_klt(const KltArgs &a, cudaStream_t st)
 {
     if (a.max_kps <= 0) return;
-    klt_pyr_lk_kernel<<<a.max_kps, KLT_THREADS, 0, st>>>(a);
+    if (a.cam.win_flow == 31) klt_pyr_lk_kernel<31><<<a.max_kps, KLT_THREADS, 0, st>>>(a);
+    else klt_pyr_lk_kernel<0><<<a.max_kps, KLT_THREADS, 0, st>>>(a);
 }
