@@ -30,6 +30,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# one hardware work queue per sequence: with the default of 8, sequences that share a queue serialise behind each
+# other's long solver kernels (must be set before the CUDA context exists)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 from stereo_svo_slam_b200 import synth  # noqa: E402
 
@@ -191,9 +194,10 @@ def run_oracle(frames, cfg, steps, warmup, threads):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--streams", type=int, default=8, help="independent sequences per GPU")
+    ap.add_argument("--streams", type=int, default=16, help="independent sequences per GPU")
+    ap.add_argument("--host-threads", type=int, default=4, help="host threads driving the sequences of one GPU")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
@@ -205,8 +209,8 @@ def main():
     c = synth.CONFIGS[CFG]
     nframes = W + K
     config = {"workload": f"BASELINE configs[2] EuRoC-shaped synthetic 752x480 ({CFG}: 4-level pyramid, 30x24 grid), "
-                          f"{S} independent sequences per GPU (configs[4] = 8 GPUs x 8); configs[0]/[1] blocked: .mkv missing",
-              "sequences_per_gpu": S, "frames_per_sequence": nframes, "seeds": "1000 + rank*S + s",
+                          f"{S} independent sequences per GPU (configs[4] = 8 GPUs x S); configs[0]/[1] blocked: .mkv missing",
+              "sequences_per_gpu": S, "host_threads_per_gpu": a.host_threads, "frames_per_sequence": nframes, "seeds": "1000 + rank*S + s",
               "l2_hygiene": "every step touches new frames (0.72 MB/sequence) and all sequences' pyramids; single-stream working "
                             "set (<3 MB) is L2 resident by nature of the path — kernels are latency/ALU bound (DESIGN.md)"}
 
@@ -257,8 +261,12 @@ def main():
         img = H_ * W_
         launches0 = [None] * S
 
-        def step(k):
-            for s, sl in enumerate(slams):
+        T = max(1, min(a.host_threads, S))
+        groups = [list(range(t, S, T)) for t in range(T)]
+
+        def advance(group, k):
+            for s in group:
+                sl = slams[s]
                 off = ((s * nframes + k) * 2) * img
                 if mode == "device":
                     rc = lib.svo_slam_new_image_device_begin(sl._h, C.c_void_p(dptr + off), C.c_size_t(W_), C.c_void_p(dptr + off + img),
@@ -268,13 +276,34 @@ def main():
                                                       C.c_size_t(W_), C.c_float(k / 20.0))
                 if rc:
                     raise RuntimeError(lib.svo_slam_last_error(sl._h).decode())
-            for sl in slams:
-                rc = lib.svo_slam_new_image_end(sl._h)
+            for s in group:
+                rc = lib.svo_slam_new_image_end(slams[s]._h)
                 if rc:
-                    raise RuntimeError(lib.svo_slam_last_error(sl._h).decode())
+                    raise RuntimeError(lib.svo_slam_last_error(slams[s]._h).decode())
 
-        for k in range(W):
-            step(k)
+        def drive(k0, k1):
+            """every host thread advances its own sequences frame by frame (ctypes releases the GIL)"""
+            errs = []
+
+            def work(group):
+                try:
+                    torch.cuda.set_device(local_rank)
+                    for k in range(k0, k1):
+                        advance(group, k)
+                except Exception as e:  # noqa: BLE001
+                    errs.append(e)
+            if T == 1:
+                work(groups[0])
+            else:
+                ts = [threading.Thread(target=work, args=(g,)) for g in groups]
+                for t in ts:
+                    t.start()
+                for t in ts:
+                    t.join()
+            if errs:
+                raise errs[0]
+
+        drive(0, W)
         cnt = C.c_longlong()
         for s, sl in enumerate(slams):
             lib.svo_launch_count(C.c_void_p(lib.svo_slam_ctx(sl._h)), C.byref(cnt))
@@ -285,8 +314,7 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         t0 = time.perf_counter()
-        for k in range(W, W + K):
-            step(k)
+        drive(W, W + K)
         torch.cuda.synchronize()
         e1.record()
         torch.cuda.synchronize()

@@ -264,17 +264,35 @@ extern "C" int svo_upload_stereo(svo_ctx *ctx, const uint8_t *left, size_t ls, c
     if (rc) return rc;
     Slot &s = ctx->slots[id];
     const size_t img = (size_t)ctx->W * ctx->H;
-    // the staging half used two uploads ago must have been consumed: uploads on one stream are ordered, and the
-    // caller synchronises once per frame (svo_track_frame / svo_sync), so double buffering is sufficient.
-    uint8_t *stage = ctx->h_stage[ctx->stage_idx];
-    ctx->stage_idx ^= 1;
-    for (int y = 0; y < ctx->H; y++) {
-        memcpy(stage + (size_t)y * ctx->W, left + (size_t)y * ls, ctx->W);
-        memcpy(stage + img + (size_t)y * ctx->W, right + (size_t)y * rs, ctx->W);
-    }
     if (ctx->profiling) CK(cudaEventRecord(ctx->sev[0], ctx->stream));
-    CK(cudaMemcpyAsync(s.dev.left[0].ptr, stage, img, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(s.dev.right0.ptr, stage + img, img, cudaMemcpyHostToDevice, ctx->stream));
+    // Page-locked caller memory (cudaHostAlloc / cudaHostRegister / torch pin_memory) is DMA'd directly; pageable
+    // memory goes through the context's own pinned staging buffer (double buffered; uploads on one stream are
+    // ordered and the caller synchronises once per frame).
+    cudaPointerAttributes al, ar;
+    bool pinned = cudaPointerGetAttributes(&al, left) == cudaSuccess && cudaPointerGetAttributes(&ar, right) == cudaSuccess &&
+                  al.type == cudaMemoryTypeHost && ar.type == cudaMemoryTypeHost;
+    cudaGetLastError();  // clear a possible "invalid value" from querying unregistered memory on old drivers
+    if (pinned) {
+        // contiguous rows: one linear DMA (a 2-D copy of 752-byte rows costs one descriptor per row)
+        if (ls == (size_t)ctx->W) CK(cudaMemcpyAsync(s.dev.left[0].ptr, left, img, cudaMemcpyHostToDevice, ctx->stream));
+        else CK(cudaMemcpy2DAsync(s.dev.left[0].ptr, ctx->W, left, ls, ctx->W, ctx->H, cudaMemcpyHostToDevice, ctx->stream));
+        if (rs == (size_t)ctx->W) CK(cudaMemcpyAsync(s.dev.right0.ptr, right, img, cudaMemcpyHostToDevice, ctx->stream));
+        else CK(cudaMemcpy2DAsync(s.dev.right0.ptr, ctx->W, right, rs, ctx->W, ctx->H, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        uint8_t *stage = ctx->h_stage[ctx->stage_idx];
+        ctx->stage_idx ^= 1;
+        if (ls == (size_t)ctx->W && rs == (size_t)ctx->W) {
+            memcpy(stage, left, img);
+            memcpy(stage + img, right, img);
+        } else {
+            for (int y = 0; y < ctx->H; y++) {
+                memcpy(stage + (size_t)y * ctx->W, left + (size_t)y * ls, ctx->W);
+                memcpy(stage + img + (size_t)y * ctx->W, right + (size_t)y * rs, ctx->W);
+            }
+        }
+        CK(cudaMemcpyAsync(s.dev.left[0].ptr, stage, img, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(s.dev.right0.ptr, stage + img, img, cudaMemcpyHostToDevice, ctx->stream));
+    }
     launch_pyr_halfsample(s.dev, ctx->stream);
     launch_lk_pyramid(s.dev, ctx->stream);
     ctx->launch_total += pyr_launch_count(s.dev);
@@ -293,8 +311,11 @@ extern "C" int svo_upload_stereo_device(svo_ctx *ctx, const uint8_t *d_left, siz
     if (rc) return rc;
     Slot &s = ctx->slots[id];
     if (ctx->profiling) CK(cudaEventRecord(ctx->sev[0], ctx->stream));
-    CK(cudaMemcpy2DAsync(s.dev.left[0].ptr, ctx->W, d_left, ls, ctx->W, ctx->H, cudaMemcpyDeviceToDevice, ctx->stream));
-    CK(cudaMemcpy2DAsync(s.dev.right0.ptr, ctx->W, d_right, rs, ctx->W, ctx->H, cudaMemcpyDeviceToDevice, ctx->stream));
+    const size_t img = (size_t)ctx->W * ctx->H;
+    if (ls == (size_t)ctx->W) CK(cudaMemcpyAsync(s.dev.left[0].ptr, d_left, img, cudaMemcpyDeviceToDevice, ctx->stream));
+    else CK(cudaMemcpy2DAsync(s.dev.left[0].ptr, ctx->W, d_left, ls, ctx->W, ctx->H, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (rs == (size_t)ctx->W) CK(cudaMemcpyAsync(s.dev.right0.ptr, d_right, img, cudaMemcpyDeviceToDevice, ctx->stream));
+    else CK(cudaMemcpy2DAsync(s.dev.right0.ptr, ctx->W, d_right, rs, ctx->W, ctx->H, cudaMemcpyDeviceToDevice, ctx->stream));
     launch_pyr_halfsample(s.dev, ctx->stream);
     launch_lk_pyramid(s.dev, ctx->stream);
     ctx->launch_total += pyr_launch_count(s.dev);
