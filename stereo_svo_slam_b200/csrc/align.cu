@@ -19,15 +19,20 @@
 // Bound: dependency latency (serial evaluations) and shared-memory/ALU throughput, not HBM.
 #include "kernels.cuh"
 
-#define ALIGN_THREADS 512
+#define CL 8                 // CTAs per cluster = SMs cooperating on one frame
+#define ALIGN_THREADS 256    // per CTA: 8 warps x 8 keypoints x 4 patch rows
 #define ALIGN_WARPS (ALIGN_THREADS / 32)
-#define NGRAD 27  // 21 (H upper triangle) + 6 (b)
+#define KPS_PER_PASS (CL * ALIGN_WARPS * 8)
+#define NGRAD 27             // 21 (H upper triangle) + 6 (b)
 
 struct AlignHdr {
-    unsigned long long bar;
-    double Rd[2][9];                       // Rodrigues(-r) in double for the pose being evaluated / the speculated next pose
-    double cost_part[2][ALIGN_WARPS];      // per-warp cost partials, double buffered (one barrier per evaluation)
-    float grad_part[NGRAD][ALIGN_WARPS];   // per-warp partials of H (21) and b (6)
+    unsigned long long bar;                // TMA completion barrier (level images)
+    unsigned long long xbar[3];            // DSMEM exchange barriers: cost (two, alternating) and gradient
+    double Rd[18][9];                      // Rodrigues(-r): two tables of 8 step sizes (k = 2^-j) + 2 spare slots, see rd_slot()
+    double warp_cost[ALIGN_WARPS];         // this CTA's per-warp cost partials
+    double cl_cost[2][CL];                 // per-CTA cost partials of the whole cluster (written through DSMEM), double buffered
+    float warp_grad[ALIGN_WARPS][NGRAD];   // this CTA's per-warp partials of H (21) and b (6)
+    double cl_grad[CL][NGRAD];             // per-CTA partials of the whole cluster (written through DSMEM)
     double red_out[NGRAD];
     float grad[6];
     int n;
@@ -65,6 +70,36 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ unsigned cluster_ctarank()
+{
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// store a double into the shared memory of CTA `rank` of this cluster (distributed shared memory)
+__device__ __forceinline__ void dsmem_store_f64(void *local_smem_ptr, unsigned rank, double v)
+{
+    uint32_t local = smem_u32(local_smem_ptr), remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(rank));
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(remote), "d"(v) : "memory");
+}
+
+// Push a double into CTA `rank`'s shared memory and signal that CTA's mbarrier with the 8 transferred bytes
+// (st.async + complete_tx): data and notification travel together, no cluster-scope fence or barrier is needed.
+__device__ __forceinline__ void dsmem_push_f64(void *local_slot, unsigned long long *local_bar, unsigned rank, double v)
+{
+    uint32_t slot = smem_u32(local_slot), bar = smem_u32(local_bar), rslot, rbar;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rslot) : "r"(slot), "r"(rank));
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(bar), "r"(rank));
+    asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(rslot), "l"(__double_as_longlong(v)), "r"(rbar)
                  : "memory");
 }
 
@@ -144,6 +179,42 @@ __device__ __forceinline__ float intensity_diff(const uint8_t *im1, const uint8_
     return intensity;
 }
 
+// One row (4 pixels) of _get_intensity_diff for the 4x4 window of the shipped configurations; other window sizes
+// use the generic whole-patch routine on lane 0 of the quad (d0 carries the whole patch sum, in the reference's order).
+__device__ __forceinline__ void intensity_diff_row(const uint8_t *im1, const uint8_t *im2, int w, int h, int pitch, float c1x, float c1y,
+                                                   float c2x, float c2y, int patch, int row, float &d0, float &d1, float &d2, float &d3)
+{
+    d0 = d1 = d2 = d3 = 0.f;
+    if (patch != 4) {
+        if (row == 0) d0 = intensity_diff<0>(im1, im2, w, h, pitch, c1x, c1y, c2x, c2y, patch);
+        return;
+    }
+    float half = ((float)4 - 1.0f) / 2.0f;
+    float s1x = c1x - half, s1y = c1y - half, s2x = c2x - half, s2y = c2y - half;
+    float f1x = floorf(s1x), f1y = floorf(s1y), f2x = floorf(s2x), f2y = floorf(s2y);
+    int ip1x = (int)f1x, ip1y = (int)f1y, ip2x = (int)f2x, ip2y = (int)f2y;
+    float x12 = s1x - f1x, y12 = s1y - f1y, x22 = s2x - f2x, y22 = s2y - f2y;
+    float x11 = 1.0f - x12, y11 = 1.0f - y12;
+    float x21 = 1.0f - x22, y21 = 1.0f - y22;
+    float m11 = x11 * y11, m12 = x12 * y11, m13 = x11 * y12, m14 = x12 * y12;
+    float m21 = x21 * y21, m22 = x22 * y21, m23 = x21 * y22, m24 = x22 * y22;
+    if (ip1y >= 0 && ip1y + 4 < h && ip2y >= 0 && ip2y + 4 < h && ip1x >= 0 && ip1x + 4 < w && ip2x >= 0 && ip2x + 4 < w) {
+        const uint8_t *p1 = im1 + (ip1y + row) * pitch + ip1x, *p2 = im2 + (ip2y + row) * pitch + ip2x;
+        float a0[5], a1[5], b0[5], b1[5];
+#pragma unroll
+        for (int j = 0; j < 5; j++) { a0[j] = u8f(p1[j]); a1[j] = u8f(p1[pitch + j]); b0[j] = u8f(p2[j]); b1[j] = u8f(p2[pitch + j]); }
+        float d[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            float i1 = 0.f, i2 = 0.f;
+            i1 += m11 * a0[j]; i1 += m12 * a0[j + 1]; i1 += m13 * a1[j]; i1 += m14 * a1[j + 1];
+            i2 += m21 * b0[j]; i2 += m22 * b0[j + 1]; i2 += m23 * b1[j]; i2 += m24 * b1[j + 1];
+            d[j] = fabsf(i1 - i2);
+        }
+        d0 = d[0]; d1 = d[1]; d2 = d[2]; d3 = d[3];
+    }
+}
+
 // 6x6 SPD solve in double (LDL^T, one reciprocal per pivot); returns false when H is not numerically positive definite
 __device__ bool solve6(const double *Hu /*21 upper-tri row-major*/, const double *b, double *x)
 {
@@ -196,7 +267,8 @@ __device__ bool solve6(const double *Hu /*21 upper-tri row-major*/, const double
     return true;
 }
 
-// One CTA = one frame.  kSmem: level images staged in shared memory (all levels used fit), else read via L1/L2.
+// One thread-block CLUSTER (8 CTAs x 256 threads) = one frame.  Four lanes share a keypoint: lane r of the quad owns
+// row r of its 4x4 patch.  kSmem: level images staged in every CTA's shared memory (TMA), else read via L1/L2.
 template <bool kSmem>
 __global__ void __launch_bounds__(ALIGN_THREADS, 1) sparse_align_kernel(AlignArgs a)
 {
@@ -204,24 +276,30 @@ __global__ void __launch_bounds__(ALIGN_THREADS, 1) sparse_align_kernel(AlignArg
     AlignHdr *hdr = reinterpret_cast<AlignHdr *>(smem_raw);
     uint8_t *img_area = smem_raw + HDR_BYTES;
 
-    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int quad = lane >> 2, row = lane & 3;
+    const unsigned crank = cluster_ctarank();
     const DevCam cam = a.cam;
     if (tid == 0) {
         if (kSmem) mbar_init(&hdr->bar, 1);
+        for (int k = 0; k < 3; k++) mbar_init(&hdr->xbar[k], 1);
         hdr->n = min(*a.n_ptr, a.max_kps);
-        for (int k = 0; k < 16; k++) a.evals_out[k] = 0;
+        if (crank == 0) for (int k = 0; k < 16; k++) a.evals_out[k] = 0;
     }
     __syncthreads();
+    cluster_sync_all();   // every CTA's shared memory is live before anyone writes into it remotely
     const int n = hdr->n;
-    uint32_t phase = 0;
-    float *scr = a.scratch;
-    const int SN = a.max_kps;
+    const int npass = (n + KPS_PER_PASS - 1) / KPS_PER_PASS;
+    uint32_t phase = 0, xphase[3] = {0, 0, 0};
+    float *scr = a.scratch;                 // [13][4 * max_kps]: per (keypoint,row): 4 x (g0, g1, Sprev) + mask
+    const size_t SN = (size_t)4 * a.max_kps;
 
-    // solver state: identical in every thread (computed redundantly from broadcast sums => no broadcast barrier)
+    // solver state: identical in every thread of every CTA (recomputed redundantly from the broadcast partial sums)
     float x0[6], xt[6], grad[6];
 #pragma unroll
     for (int k = 0; k < 6; k++) { x0[k] = a.pose_in[k]; xt[k] = x0[k]; grad[k] = 0.f; }
     float prev_cost = 0.f;
+    int x0slot = 16, sp = 1, tb = 0, xtslot = 0;
 
     const int lv_hi = (a.probe_level >= 0) ? a.probe_level : cam.max_levels - 1;
     const int lv_lo = (a.probe_level >= 0) ? a.probe_level : cam.min_level;
@@ -250,82 +328,106 @@ __global__ void __launch_bounds__(ALIGN_THREADS, 1) sparse_align_kernel(AlignArg
         const float fdiv = (float)divider;
         const float lfx = cam.fx / fdiv, lfy = cam.fy / fdiv, lcx = cam.cx / fdiv, lcy = cam.cy / fdiv;
 
-        int cur = 0;  // index of the Rd buffer holding Rodrigues(-r) of the pose being evaluated
-        if (tid == 0) dev_rodrigues_d(-x0[3], -x0[4], -x0[5], hdr->Rd[0]);   // overlaps the TMA copy
+        // Rodrigues matrices: after every gradient, 8 warps compute in parallel the matrices of the 8 trial poses
+        // x0 + 2^-j grad (table tb); cost evaluations then find theirs ready, and an accepted pose keeps its slot as
+        // "the matrix of x0" while the next gradient fills the other table.  j >= 8 falls back to a spare slot.
+        if (level == lv_hi) {
+            if (tid == 0) dev_rodrigues_d(-x0[3], -x0[4], -x0[5], hdr->Rd[16]);   // overlaps the TMA copy
+            x0slot = 16; sp = 1; tb = 0;
+        }
         if (kSmem) { mbar_wait(&hdr->bar, phase); phase ^= 1; }
 
-        // ---- per-level cache of the pose-independent reference terms (calculate_hessian :346-395 image part,
-        //      get_gradient :449-460 reference part)
-        for (int i = tid; i < n; i += nthr) {
+        // ---- per-level cache of the pose-independent reference terms of this lane's patch row
+        //      (calculate_hessian :346-395 image part, get_gradient :449-460 reference part)
+        for (int pass = 0; pass < npass; pass++) {
+            const int i = ((pass * ALIGN_WARPS + warp) * CL + (int)crank) * 8 + quad;
+            if (i >= n) continue;
             if (a.flags && (a.flags[i] & SVO_F_IGN_TEMP)) continue;
             float bx = a.kps2d[2 * i], by = a.kps2d[2 * i + 1];
             if (level != 0) { bx = bx / fdiv; by = by / fdiv; }
             float kx = bx - 2.f, ky = by - 2.f;   // Hessian loop coordinates
             float rx = bx - 2.f, ry = by - 2.f;   // residual loop reference coordinates
-            unsigned mask = 0;
-            int e = 0;
-            for (int r = 0; r < 4; r++) {
-                for (int c = 0; c < 4; c++, e++) {
-                    float g0 = 0.f, g1 = 0.f;
-                    if (!(((double)kx - 2.0) < 0 || ((double)ky - 2.0) < 0 || ((double)kx + 3.0) >= w || ((double)ky + 3.0) >= h)) {
-                        float i1 = patch_sum(pimg, pitch, kx + 1.f, ky), i2 = patch_sum(pimg, pitch, kx - 1.f, ky);
-                        float i3 = patch_sum(pimg, pitch, kx, ky + 1.f), i4 = patch_sum(pimg, pitch, kx, ky - 1.f);
-                        g0 = i1 - i2; g1 = i3 - i4;
-                        mask |= 1u << e;
-                    }
-                    scr[(size_t)e * SN + i] = g0;
-                    scr[(size_t)(16 + e) * SN + i] = g1;
-                    kx += 1.f;
-                    float sp = 0.f;
-                    if (!(((double)rx - 1.0) < 0 || ((double)ry - 1.0) < 0 || ((double)rx + 2.0) > w || ((double)ry + 2.0) > h)) {
-                        sp = patch_sum(pimg, pitch, rx, ry);
-                        mask |= 1u << (16 + e);
-                    }
-                    scr[(size_t)(32 + e) * SN + i] = sp;
-                    rx += 1.f;
-                }
-                kx -= 4.f; ky += 1.f;
-                ry += 1.f; rx -= 4.f;
+            // replay the reference's float increments of the rows above this lane's row
+            for (int r = 0; r < row; r++) {
+                kx += 1.f; kx += 1.f; kx += 1.f; kx += 1.f; kx -= 4.f; ky += 1.f;
+                rx += 1.f; rx += 1.f; rx += 1.f; rx += 1.f; ry += 1.f; rx -= 4.f;
             }
-            scr[(size_t)48 * SN + i] = __uint_as_float(mask);
+            unsigned mask = 0;
+            const size_t slot = (size_t)4 * i + row;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                float g0 = 0.f, g1 = 0.f;
+                if (!(((double)kx - 2.0) < 0 || ((double)ky - 2.0) < 0 || ((double)kx + 3.0) >= w || ((double)ky + 3.0) >= h)) {
+                    float i1 = patch_sum(pimg, pitch, kx + 1.f, ky), i2 = patch_sum(pimg, pitch, kx - 1.f, ky);
+                    float i3 = patch_sum(pimg, pitch, kx, ky + 1.f), i4 = patch_sum(pimg, pitch, kx, ky - 1.f);
+                    g0 = i1 - i2; g1 = i3 - i4;
+                    mask |= 1u << c;
+                }
+                scr[(size_t)c * SN + slot] = g0;
+                scr[(size_t)(4 + c) * SN + slot] = g1;
+                kx += 1.f;
+                float sp = 0.f;
+                if (!(((double)rx - 1.0) < 0 || ((double)ry - 1.0) < 0 || ((double)rx + 2.0) > w || ((double)ry + 2.0) > h)) {
+                    sp = patch_sum(pimg, pitch, rx, ry);
+                    mask |= 1u << (4 + c);
+                }
+                scr[(size_t)(8 + c) * SN + slot] = sp;
+                rx += 1.f;
+            }
+            scr[(size_t)12 * SN + slot] = __uint_as_float(mask);
         }
         // (each thread only ever reads back the scratch entries it wrote itself)
-        __syncthreads();  // Rd[0] visible
+        __syncthreads();  // Rd of x0 visible
 
         // ---- Gauss-Newton driver (estimate_pose_at_level :166-222).
         //  mode 0: cost at x0 (initial)   mode 1: gradient at x0   mode 2: cost at xt   mode 3: level done
-        int mode = 0, it = 0, n_evals = 0, n_grads = 0, cbuf = 0;
+        int mode = 0, it = 0, n_evals = 0, n_grads = 0, cbuf = 0, jstep = 0;
         float kstep = 1.f;
         while (mode != 3) {
             const float *x = (mode == 2) ? xt : x0;
-            const double *Rd = hdr->Rd[cur];
+            const double *Rd = hdr->Rd[(mode == 2) ? xtslot : x0slot];
             const float tx = x[0], ty = x[1], tz = x[2];
             if (mode != 1) {
                 // ---------------- do_calc: bilinear SAD (prev @ reference position, cur @ projection)
-                // speculation: the last thread prepares Rodrigues for the halved step while everyone evaluates this one
-                if (mode == 2 && tid == nthr - 1) {
-                    const float hk = kstep / 2;
-                    dev_rodrigues_d(-(x0[3] + (hk * grad[3])), -(x0[4] + (hk * grad[4])), -(x0[5] + (hk * grad[5])), hdr->Rd[cur ^ 1]);
-                }
                 double part = 0.0;
-                for (int i = tid; i < n; i += nthr) {
-                    if (a.flags && (a.flags[i] & SVO_F_IGN_TEMP)) continue;
-                    float bx = a.kps2d[2 * i], by = a.kps2d[2 * i + 1];
-                    if (level != 0) { bx = bx / fdiv; by = by / fdiv; }
-                    float u, v;
-                    dev_project(Rd, a.kps3d[3 * i], a.kps3d[3 * i + 1], a.kps3d[3 * i + 2], tx, ty, tz, lfx, lfy, lcx, lcy, cam.k1, cam.k2,
-                                cam.p1, cam.p2, cam.k3, u, v);
-                    float d = (cam.win_pose == 4) ? intensity_diff<4>(pimg, cimg, w, h, pitch, bx, by, u, v, 4)
-                                                  : intensity_diff<0>(pimg, cimg, w, h, pitch, bx, by, u, v, cam.win_pose);
-                    part += (double)d;
+                for (int pass = 0; pass < npass; pass++) {
+                    const int i = ((pass * ALIGN_WARPS + warp) * CL + (int)crank) * 8 + quad;
+                    const bool active = (i < n) && !(a.flags && (a.flags[i] & SVO_F_IGN_TEMP));
+                    float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+                    if (active) {
+                        float bx = a.kps2d[2 * i], by = a.kps2d[2 * i + 1];
+                        if (level != 0) { bx = bx / fdiv; by = by / fdiv; }
+                        float u, v;
+                        dev_project(Rd, a.kps3d[3 * i], a.kps3d[3 * i + 1], a.kps3d[3 * i + 2], tx, ty, tz, lfx, lfy, lcx, lcy, cam.k1, cam.k2,
+                                    cam.p1, cam.p2, cam.k3, u, v);
+                        intensity_diff_row(pimg, cimg, w, h, pitch, bx, by, u, v, cam.win_pose, row, d0, d1, d2, d3);
+                    }
+                    // the reference adds the 16 |dI| terms of a patch sequentially in raster order: chain the four rows
+                    float run = 0.f;
+#pragma unroll
+                    for (int rr = 0; rr < 4; rr++) {
+                        float mine = run;
+                        mine += d0; mine += d1; mine += d2; mine += d3;
+                        run = __shfl_sync(0xffffffffu, mine, (lane & ~3) | rr);
+                    }
+                    if (row == 0) part += (double)run;   // one lane per keypoint carries the patch cost
                 }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) part += __shfl_down_sync(0xffffffffu, part, o);
-                if (lane == 0) hdr->cost_part[cbuf][warp] = part;
+                if (lane == 0) hdr->warp_cost[warp] = part;
                 __syncthreads();
+                if (tid < CL) {   // lane t pushes this CTA's partial into CTA t's table and signals CTA t's barrier
+                    double cta = 0.0;
+#pragma unroll
+                    for (int q = 0; q < ALIGN_WARPS; q++) cta += hdr->warp_cost[q];
+                    dsmem_push_f64(&hdr->cl_cost[cbuf][crank], &hdr->xbar[cbuf], (unsigned)tid, cta);
+                    if (tid == 0) mbar_expect_tx(&hdr->xbar[cbuf], CL * 8);
+                }
+                mbar_wait(&hdr->xbar[cbuf], xphase[cbuf]);
+                xphase[cbuf] ^= 1;
                 double tot = 0.0;
 #pragma unroll
-                for (int q = 0; q < ALIGN_WARPS; q++) tot += hdr->cost_part[cbuf][q];
+                for (int q = 0; q < CL; q++) tot += hdr->cl_cost[cbuf][q];
                 cbuf ^= 1;
                 const float cost = (float)tot;
                 n_evals++;
@@ -337,16 +439,25 @@ __global__ void __launch_bounds__(ALIGN_THREADS, 1) sparse_align_kernel(AlignArg
                     for (int k = 0; k < 6; k++) x0[k] = xt[k];
                     prev_cost = cost;
                     it++;       // outer loop increment after `break`
-                    mode = (it < 50) ? 1 : 3;   // Rd[cur] already belongs to the new x0
+                    mode = (it < 50) ? 1 : 3;
+                    x0slot = xtslot;                 // the accepted pose keeps its matrix
+                    if (xtslot >= 16) sp ^= 1; else tb ^= 1;   // ... and the next gradient / fallback writes elsewhere
                 } else if (fabsf(cost - prev_cost) < 1.0f) {
                     mode = 3;
                 } else {
                     kstep = kstep / 2;
+                    jstep++;
                     it++;       // inner loop increment
                     if (it < 50) {
 #pragma unroll
                         for (int k = 0; k < 6; k++) xt[k] = x0[k] + (kstep * grad[k]);
-                        cur ^= 1;   // the speculated matrix is the one we need
+                        if (jstep < 8) {
+                            xtslot = tb * 8 + jstep;
+                        } else {   // rare: more than 7 halvings — compute on demand
+                            xtslot = 16 + sp;
+                            if (tid == 0) dev_rodrigues_d(-xt[3], -xt[4], -xt[5], hdr->Rd[xtslot]);
+                            __syncthreads();
+                        }
                         mode = 2;
                     } else {
                         mode = 3;
@@ -360,8 +471,15 @@ __global__ void __launch_bounds__(ALIGN_THREADS, 1) sparse_align_kernel(AlignArg
                 float acc[NGRAD];
 #pragma unroll
                 for (int k = 0; k < NGRAD; k++) acc[k] = 0.f;
-                for (int i = tid; i < n; i += nthr) {
+                for (int pass = 0; pass < npass; pass++) {
+                    const int i = ((pass * ALIGN_WARPS + warp) * CL + (int)crank) * 8 + quad;
+                    if (i >= n) continue;
                     if (a.flags && (a.flags[i] & SVO_F_IGN_TEMP)) continue;
+                    const size_t slot = (size_t)4 * i + row;
+                    const unsigned mask = __float_as_uint(scr[(size_t)12 * SN + slot]);
+                    float g0v[4], g1v[4], spv[4];
+#pragma unroll
+                    for (int c = 0; c < 4; c++) { g0v[c] = scr[(size_t)c * SN + slot]; g1v[c] = scr[(size_t)(4 + c) * SN + slot]; spv[c] = scr[(size_t)(8 + c) * SN + slot]; }
                     const float Px = a.kps3d[3 * i], Py = a.kps3d[3 * i + 1], Pz = a.kps3d[3 * i + 2];
                     float u, v;
                     dev_project(Rd, Px, Py, Pz, tx, ty, tz, lfx, lfy, lcx, lcy, cam.k1, cam.k2, cam.p1, cam.p2, cam.k3, u, v);
@@ -372,56 +490,60 @@ __global__ void __launch_bounds__(ALIGN_THREADS, 1) sparse_align_kernel(AlignArg
                     J[4] = -lfx * (1 + (X * X) / (Z * Z)); J[5] = lfx * Y / Z;
                     J[6] = 0.f; J[7] = -lfy / Z; J[8] = lfy * Y / (Z * Z); J[9] = lfy * (1 + (Y * Y) / (Z * Z));
                     J[10] = -lfy * X * Y / (Z * Z); J[11] = -lfy * X / Z;
-                    const unsigned mask = __float_as_uint(scr[(size_t)48 * SN + i]);
                     float qx = u - 2.f, qy = v - 2.f;       // residual loop, current-image coordinates
-                    int e = 0;
-                    for (int r = 0; r < 4; r++) {
+                    for (int r = 0; r < row; r++) { qx += 1.f; qx += 1.f; qx += 1.f; qx += 1.f; qy += 1.f; qx -= 4.f; }
 #pragma unroll
-                        for (int c = 0; c < 4; c++, e++) {
-                            float gj[6];
-                            const float g0 = scr[(size_t)e * SN + i], g1 = scr[(size_t)(16 + e) * SN + i];   // zero when masked out
+                    for (int c = 0; c < 4; c++) {
+                        float gj[6];
 #pragma unroll
-                            for (int k = 0; k < 6; k++) {
-                                float t = 0.f;
-                                t += g0 * J[k];
-                                t += g1 * J[6 + k];
-                                gj[k] = (mask & (1u << e)) ? t : 0.f;
-                            }
-                            float diff = 0.f;
-                            if ((mask & (1u << (16 + e))) &&
-                                !(((double)qx - 1.0) < 0 || ((double)qy - 1.0) < 0 || ((double)qx + 2.0) > w || ((double)qy + 2.0) > h)) {
-                                diff = patch_sum(cimg, pitch, qx, qy) - scr[(size_t)(32 + e) * SN + i];
-                            }
-                            int hk = 0;
-#pragma unroll
-                            for (int p = 0; p < 6; p++)
-#pragma unroll
-                                for (int q = p; q < 6; q++) { acc[hk] = __fmaf_rn(gj[p], gj[q], acc[hk]); hk++; }   // sum order differs from the reference anyway
-#pragma unroll
-                            for (int p = 0; p < 6; p++) acc[21 + p] = __fmaf_rn(-gj[p], diff, acc[21 + p]);
-                            qx += 1.f;
+                        for (int k = 0; k < 6; k++) {
+                            float t = 0.f;
+                            t += g0v[c] * J[k];
+                            t += g1v[c] * J[6 + k];
+                            gj[k] = (mask & (1u << c)) ? t : 0.f;
                         }
-                        qy += 1.f;
-                        qx -= 4.f;
+                        float diff = 0.f;
+                        if ((mask & (1u << (4 + c))) &&
+                            !(((double)qx - 1.0) < 0 || ((double)qy - 1.0) < 0 || ((double)qx + 2.0) > w || ((double)qy + 2.0) > h)) {
+                            diff = patch_sum(cimg, pitch, qx, qy) - spv[c];
+                        }
+                        int hk = 0;
+#pragma unroll
+                        for (int p = 0; p < 6; p++)
+#pragma unroll
+                            for (int q = p; q < 6; q++) { acc[hk] = __fmaf_rn(gj[p], gj[q], acc[hk]); hk++; }   // sum order differs from the reference anyway
+#pragma unroll
+                        for (int p = 0; p < 6; p++) acc[21 + p] = __fmaf_rn(-gj[p], diff, acc[21 + p]);
+                        qx += 1.f;
                     }
                 }
-                // warp reduce (float), cross-warp sum in double by 27 threads
+                // warp reduce (float) -> CTA partial (double, 27 threads) -> every CTA's table through DSMEM
 #pragma unroll
                 for (int k = 0; k < NGRAD; k++) {
                     float t = acc[k];
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
-                    if (lane == 0) hdr->grad_part[k][warp] = t;
+                    if (lane == 0) hdr->warp_grad[warp][k] = t;
                 }
                 __syncthreads();
                 if (tid < NGRAD) {
                     double t = 0.0;
 #pragma unroll
-                    for (int q = 0; q < ALIGN_WARPS; q++) t += (double)hdr->grad_part[tid][q];
+                    for (int q = 0; q < ALIGN_WARPS; q++) t += (double)hdr->warp_grad[q][tid];
+#pragma unroll
+                    for (unsigned dst = 0; dst < CL; dst++) dsmem_push_f64(&hdr->cl_grad[crank][tid], &hdr->xbar[2], dst, t);
+                    if (tid == 0) mbar_expect_tx(&hdr->xbar[2], CL * NGRAD * 8);
+                }
+                mbar_wait(&hdr->xbar[2], xphase[2]);
+                xphase[2] ^= 1;
+                if (tid < NGRAD) {
+                    double t = 0.0;
+#pragma unroll
+                    for (int q = 0; q < CL; q++) t += hdr->cl_grad[q][tid];
                     hdr->red_out[tid] = t;
                 }
                 __syncthreads();
-                if (tid == 0) {
+                if (tid == 0) {   // every CTA solves the same 6x6 system redundantly: no further cluster traffic
                     double dx[6];
                     float delta[6], pg[6], Rf[9];
                     bool ok = solve6(hdr->red_out, hdr->red_out + 21, dx);
@@ -438,31 +560,37 @@ __global__ void __launch_bounds__(ALIGN_THREADS, 1) sparse_align_kernel(AlignArg
                     dev_m33v(Rf, pg[3], pg[4], pg[5], g[3], g[4], g[5]);
 #pragma unroll
                     for (int k = 0; k < 6; k++) hdr->grad[k] = g[k];
-                    // pose matrices of the first trial point x0 + 1 * grad
-                    dev_rodrigues_d(-(x0[3] + (1.f * g[3])), -(x0[4] + (1.f * g[4])), -(x0[5] + (1.f * g[5])), hdr->Rd[cur ^ 1]);
                 }
                 __syncthreads();
                 n_grads++;
 #pragma unroll
                 for (int k = 0; k < 6; k++) grad[k] = hdr->grad[k];
+                if (lane == 0) {   // warp j prepares the matrix of x0 + 2^-j grad (same float expressions as the driver)
+                    float kj = 1.f;
+                    for (int q = 0; q < warp; q++) kj = kj / 2;
+                    dev_rodrigues_d(-(x0[3] + (kj * grad[3])), -(x0[4] + (kj * grad[4])), -(x0[5] + (kj * grad[5])), hdr->Rd[tb * 8 + warp]);
+                }
+                __syncthreads();
                 kstep = 1.f;
+                jstep = 0;
 #pragma unroll
                 for (int k = 0; k < 6; k++) xt[k] = x0[k] + (kstep * grad[k]);
-                cur ^= 1;
+                xtslot = tb * 8;
                 mode = 2;
                 if (a.probe_level >= 0) {
-                    if (tid == 0)
+                    if (tid == 0 && crank == 0)
                         for (int k = 0; k < 6; k++) a.probe_grad[k] = grad[k];
                     mode = 3;
                 }
             }
         }
-        if (tid == 0 && level < 8) { a.evals_out[2 * level] = n_evals; a.evals_out[2 * level + 1] = n_grads; }
+        if (tid == 0 && crank == 0 && level < 8) { a.evals_out[2 * level] = n_evals; a.evals_out[2 * level + 1] = n_grads; }
     }
-    if (tid == 0) {
+    if (tid == 0 && crank == 0) {
         for (int k = 0; k < 6; k++) a.pose_out[k] = x0[k];
         *a.cost_out = prev_cost;
     }
+    cluster_sync_all();   // no CTA exits while others may still write into its shared memory
 }
 
 static bool align_levels_fit(const AlignArgs &a, size_t &need)
@@ -486,15 +614,28 @@ size_t align_smem_bytes(const AlignArgs &a)
     return HDR_BYTES + (fit ? need : 0);
 }
 
+size_t align_scratch_floats(int max_kps) { return (size_t)13 * 4 * max_kps; }
+
 cudaError_t align_init_device()
 {
-    return cudaFuncSetAttribute(sparse_align_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    cudaError_t e = cudaFuncSetAttribute(sparse_align_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    return e;
 }
 
-void launch_align(const AlignArgs &a, cudaStream_t st)
+cudaError_t launch_align(const AlignArgs &a, cudaStream_t st)
 {
     size_t need;
     bool fit = align_levels_fit(a, need);
-    if (fit) sparse_align_kernel<true><<<1, ALIGN_THREADS, HDR_BYTES + need, st>>>(a);
-    else sparse_align_kernel<false><<<1, ALIGN_THREADS, HDR_BYTES, st>>>(a);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(CL, 1, 1);
+    cfg.blockDim = dim3(ALIGN_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = HDR_BYTES + (fit ? need : 0);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (fit) return cudaLaunchKernelEx(&cfg, sparse_align_kernel<true>, a);
+    return cudaLaunchKernelEx(&cfg, sparse_align_kernel<false>, a);
 }

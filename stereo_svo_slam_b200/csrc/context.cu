@@ -182,7 +182,7 @@ extern "C" int svo_ctx_create(const svo_camera_settings *s, int device, int widt
     CKC(cudaMemset(ctx->d_io, 0, ctx->lay.total));
     CKC(cudaMallocHost(&ctx->h_io, ctx->lay.total));
     memset(ctx->h_io, 0, ctx->lay.total);
-    CKC(cudaMalloc(&ctx->d_align_scratch, (size_t)49 * ctx->max_kps * sizeof(float)));
+    CKC(cudaMalloc(&ctx->d_align_scratch, align_scratch_floats(ctx->max_kps) * sizeof(float)));
     CKC(cudaMalloc(&ctx->d_detect_scratch, (size_t)2 * width * height + 64));
     ctx->cell_cap = (width / 2 + 1) * (height / 2 + 1) / 1 + 16;
     ctx->cell_cap = (width / s->grid_width + 2) * (height / s->grid_height + 2) * 4 + 64;
@@ -269,7 +269,8 @@ extern "C" int svo_upload_stereo(svo_ctx *ctx, const uint8_t *left, size_t ls, c
     // memory goes through the context's own pinned staging buffer (double buffered; uploads on one stream are
     // ordered and the caller synchronises once per frame).
     cudaPointerAttributes al, ar;
-    bool pinned = cudaPointerGetAttributes(&al, left) == cudaSuccess && cudaPointerGetAttributes(&ar, right) == cudaSuccess &&
+    static const bool skip_query = getenv("SVO_ASSUME_PAGEABLE") != nullptr;   // diagnostic switch
+    bool pinned = !skip_query && cudaPointerGetAttributes(&al, left) == cudaSuccess && cudaPointerGetAttributes(&ar, right) == cudaSuccess &&
                   al.type == cudaMemoryTypeHost && ar.type == cudaMemoryTypeHost;
     cudaGetLastError();  // clear a possible "invalid value" from querying unregistered memory on old drivers
     if (pinned) {
@@ -519,7 +520,7 @@ extern "C" int svo_align(svo_ctx *ctx, int prev_slot, int cur_slot, const float 
     if ((rc = up(ctx, ctx->lay.pose_prior, pose_in, 24))) return rc;
     AlignArgs a;
     fill_align_args(ctx, prev_slot, cur_slot, a, n, flags != nullptr);
-    launch_align(a, ctx->stream);
+    CK(launch_align(a, ctx->stream));
     ctx->launch_total += 1;
     CK(cudaGetLastError());
     if ((rc = down(ctx, pose_out, ctx->lay.pose_aligned, 24))) return rc;
@@ -545,7 +546,7 @@ extern "C" int svo_align_probe(svo_ctx *ctx, int prev_slot, int cur_slot, const 
     fill_align_args(ctx, prev_slot, cur_slot, a, n, false);
     a.probe_level = level;
     a.probe_grad = DP(float, pose_refined);
-    launch_align(a, ctx->stream);
+    CK(launch_align(a, ctx->stream));
     ctx->launch_total += 1;
     CK(cudaGetLastError());
     if (cost && (rc = down(ctx, cost, ctx->lay.costs, 4))) return rc;
@@ -737,7 +738,7 @@ extern "C" int svo_track_frame_begin(svo_ctx *ctx, int prev_slot, int cur_slot, 
     AlignArgs aa;
     fill_align_args(ctx, prev_slot, cur_slot, aa, n, true);
     if (prof) CK(cudaEventRecord(ctx->sev[2], ctx->stream));
-    launch_align(aa, ctx->stream); launches++;
+    CK(launch_align(aa, ctx->stream)); launches++;
     if (prof) CK(cudaEventRecord(ctx->sev[3], ctx->stream));
     if (n > 0) {
         // 2. projection with the aligned pose + KLT against the origin keyframes + gating (stereo_slam.cpp:71-83)

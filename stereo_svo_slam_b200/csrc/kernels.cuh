@@ -30,14 +30,15 @@ struct AlignArgs {
     float *pose_out;       // 6
     float *cost_out;       // 1
     int *evals_out;        // 16
-    float *scratch;        // cache of reference-patch gradients / sums: 48 floats per keypoint (global)
+    float *scratch;        // cache of reference-patch gradients / sums: align_scratch_floats(max_kps) floats (global, L2 resident)
     int max_kps;
     DevCam cam;
     // probe mode: single level, single evaluation
     int probe_level;       // -1 = normal
     float *probe_grad;     // 6
 };
-void launch_align(const AlignArgs &a, cudaStream_t st);
+cudaError_t launch_align(const AlignArgs &a, cudaStream_t st);
+size_t align_scratch_floats(int max_kps);
 size_t align_smem_bytes(const AlignArgs &a);
 cudaError_t align_init_device();  // once per device: opt in to 227 KB dynamic shared memory
 

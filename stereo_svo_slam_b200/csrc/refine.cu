@@ -62,7 +62,7 @@ __device__ bool refine_solve6(const double *Hu, const double *b, double *x)
 }
 
 struct RefHdr {
-    double Rd[2][9];
+    double Rd[18][9];   // two tables of 8 step sizes (x0 + 2^-j grad) + 2 spare slots, as in sparse_align_kernel
     double cost_part[2][REF_WARPS];
     float grad_part[RNGRAD][REF_WARPS];
     double red_out[RNGRAD];
@@ -81,19 +81,16 @@ __global__ void __launch_bounds__(REF_THREADS, 1) reproj_refine_kernel(RefineArg
     float x0[6], xt[6], grad[6];
 #pragma unroll
     for (int k = 0; k < 6; k++) { x0[k] = a.pose_in[k]; xt[k] = x0[k]; grad[k] = 0.f; }
-    if (tid == 0) dev_rodrigues_d(-x0[3], -x0[4], -x0[5], hdr.Rd[0]);
+    if (tid == 0) dev_rodrigues_d(-x0[3], -x0[4], -x0[5], hdr.Rd[16]);
     __syncthreads();
-    int mode = 0, it = 0, n_evals = 0, n_grads = 0, cur = 0, cbuf = 0;
+    int mode = 0, it = 0, n_evals = 0, n_grads = 0, cbuf = 0, jstep = 0;
+    int x0slot = 16, sp = 1, tb = 0, xtslot = 0;
     float kstep = 1.f, prev_cost = 0.f;
     while (mode != 3) {
         const float *x = (mode == 2) ? xt : x0;
-        const double *Rd = hdr.Rd[cur];
+        const double *Rd = hdr.Rd[(mode == 2) ? xtslot : x0slot];
         const float tx = x[0], ty = x[1], tz = x[2];
         if (mode != 1) {
-            if (mode == 2 && tid == nthr - 1) {
-                const float hk = kstep / 2;
-                dev_rodrigues_d(-(x0[3] + (hk * grad[3])), -(x0[4] + (hk * grad[4])), -(x0[5] + (hk * grad[5])), hdr.Rd[cur ^ 1]);
-            }
             double part = 0.0;
             for (int i = tid; i < n; i += nthr) {
                 if (a.flags[i] & (SVO_F_IGN_REFINE | SVO_F_IGN_COMPLETE | SVO_F_IGN_TEMP)) continue;
@@ -122,15 +119,24 @@ __global__ void __launch_bounds__(REF_THREADS, 1) reproj_refine_kernel(RefineArg
                 prev_cost = cost;
                 it++;
                 mode = (it < 50) ? 1 : 3;
+                x0slot = xtslot;
+                if (xtslot >= 16) sp ^= 1; else tb ^= 1;
             } else if (fabs((double)(cost - prev_cost)) < 0.0001) {
                 mode = 3;
             } else {
                 kstep = kstep / 2;
+                jstep++;
                 it++;
                 if (it < 50) {
 #pragma unroll
                     for (int k = 0; k < 6; k++) xt[k] = x0[k] + (kstep * grad[k]);
-                    cur ^= 1;
+                    if (jstep < 8) {
+                        xtslot = tb * 8 + jstep;
+                    } else {
+                        xtslot = 16 + sp;
+                        if (tid == 0) dev_rodrigues_d(-xt[3], -xt[4], -xt[5], hdr.Rd[xtslot]);
+                        __syncthreads();
+                    }
                     mode = 2;
                 } else
                     mode = 3;
@@ -200,16 +206,22 @@ __global__ void __launch_bounds__(REF_THREADS, 1) reproj_refine_kernel(RefineArg
                 dev_expmap(tw, g);  // used as is — not rotated to world (pose_refinement.cpp:401-411)
 #pragma unroll
                 for (int k = 0; k < 6; k++) hdr.grad[k] = g[k];
-                dev_rodrigues_d(-(x0[3] + (1.f * g[3])), -(x0[4] + (1.f * g[4])), -(x0[5] + (1.f * g[5])), hdr.Rd[cur ^ 1]);
             }
             __syncthreads();
             n_grads++;
 #pragma unroll
             for (int k = 0; k < 6; k++) grad[k] = hdr.grad[k];
+            if (lane == 0) {   // warp j prepares the matrix of x0 + 2^-j grad
+                float kj = 1.f;
+                for (int q = 0; q < warp; q++) kj = kj / 2;
+                dev_rodrigues_d(-(x0[3] + (kj * grad[3])), -(x0[4] + (kj * grad[4])), -(x0[5] + (kj * grad[5])), hdr.Rd[tb * 8 + warp]);
+            }
+            __syncthreads();
             kstep = 1.f;
+            jstep = 0;
 #pragma unroll
             for (int k = 0; k < 6; k++) xt[k] = x0[k] + (kstep * grad[k]);
-            cur ^= 1;
+            xtslot = tb * 8;
             mode = 2;
         }
     }
