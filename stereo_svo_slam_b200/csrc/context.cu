@@ -264,7 +264,6 @@ extern "C" int svo_upload_stereo(svo_ctx *ctx, const uint8_t *left, size_t ls, c
     if (rc) return rc;
     Slot &s = ctx->slots[id];
     const size_t img = (size_t)ctx->W * ctx->H;
-    if (ctx->profiling) CK(cudaEventRecord(ctx->sev[0], ctx->stream));
     // Page-locked caller memory (cudaHostAlloc / cudaHostRegister / torch pin_memory) is DMA'd directly; pageable
     // memory goes through the context's own pinned staging buffer (double buffered; uploads on one stream are
     // ordered and the caller synchronises once per frame).
@@ -274,6 +273,7 @@ extern "C" int svo_upload_stereo(svo_ctx *ctx, const uint8_t *left, size_t ls, c
                   al.type == cudaMemoryTypeHost && ar.type == cudaMemoryTypeHost;
     cudaGetLastError();  // clear a possible "invalid value" from querying unregistered memory on old drivers
     if (pinned) {
+        if (ctx->profiling) CK(cudaEventRecord(ctx->sev[0], ctx->stream));
         // contiguous rows: one linear DMA (a 2-D copy of 752-byte rows costs one descriptor per row)
         if (ls == (size_t)ctx->W) CK(cudaMemcpyAsync(s.dev.left[0].ptr, left, img, cudaMemcpyHostToDevice, ctx->stream));
         else CK(cudaMemcpy2DAsync(s.dev.left[0].ptr, ctx->W, left, ls, ctx->W, ctx->H, cudaMemcpyHostToDevice, ctx->stream));
@@ -291,6 +291,7 @@ extern "C" int svo_upload_stereo(svo_ctx *ctx, const uint8_t *left, size_t ls, c
                 memcpy(stage + img + (size_t)y * ctx->W, right + (size_t)y * rs, ctx->W);
             }
         }
+        if (ctx->profiling) CK(cudaEventRecord(ctx->sev[0], ctx->stream));
         CK(cudaMemcpyAsync(s.dev.left[0].ptr, stage, img, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemcpyAsync(s.dev.right0.ptr, stage + img, img, cudaMemcpyHostToDevice, ctx->stream));
     }

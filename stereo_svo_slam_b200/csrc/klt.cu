@@ -236,9 +236,244 @@ __global__ void __launch_bounds__(KLT_THREADS) klt_pyr_lk_kernel(KltArgs a)
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Specialisation for the 31x31 window of every shipped configuration (Blender/EuRoC/Econ.yaml): 256 threads,
+// thread t owns the 4-pixel run (row t/8, columns 4*(t%8) .. +3) of the window for the whole level, so the template
+// (Iw, Ix, Iy of its pixels) lives in registers, horizontally adjacent bilinear taps are shared (10 byte loads for
+// 4 pixels instead of 16) and every index is a shift.  Window sums fit 32 bits per thread and are widened to
+// 64 bits for the (exact) block reduction.
+// ---------------------------------------------------------------------------------------------------------
+struct Klt31Shared {
+    uint8_t tile[34 * 34 + 4];
+    short gx[32 * 32];
+    short gy[32 * 32];
+    long long part[2][3][KLT_THREADS / 32];
+    float init[2];
+};
+
+__device__ __forceinline__ void block_sum3_31(Klt31Shared &sm, int buf, long long &a, long long &b, long long &c)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    a = warp_sum_ll(a); b = warp_sum_ll(b); c = warp_sum_ll(c);
+    if (lane == 0) { sm.part[buf][0][warp] = a; sm.part[buf][1][warp] = b; sm.part[buf][2][warp] = c; }
+    __syncthreads();
+    a = b = c = 0;
+#pragma unroll
+    for (int w = 0; w < KLT_THREADS / 32; w++) { a += sm.part[buf][0][w]; b += sm.part[buf][1][w]; c += sm.part[buf][2][w]; }
+}
+__device__ __forceinline__ void block_sum2_31(Klt31Shared &sm, int buf, long long &a, long long &b)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    a = warp_sum_ll(a); b = warp_sum_ll(b);
+    if (lane == 0) { sm.part[buf][0][warp] = a; sm.part[buf][1][warp] = b; }
+    __syncthreads();
+    a = b = 0;
+#pragma unroll
+    for (int w = 0; w < KLT_THREADS / 32; w++) { a += sm.part[buf][0][w]; b += sm.part[buf][1][w]; }
+}
+
+__global__ void __launch_bounds__(KLT_THREADS) klt31_kernel(KltArgs a)
+{
+    __shared__ Klt31Shared sm;
+    const int i = blockIdx.x;
+    const int n = min(*a.n_ptr, a.max_kps);
+    if (i >= n) return;
+    const int tid = threadIdx.x;
+    constexpr int win = 31, T = 34, W1 = 32;
+    const float half = 15.0f;
+    const int ry = tid >> 3, rx = (tid & 7) << 2;      // this thread's run: row ry, columns rx .. rx+3
+    const bool have_row = ry < win;                     // rows 31 (threads 248..255) are idle
+    const int npx_run = (rx + 4 <= win) ? 4 : 3;        // the last run of a row has 3 pixels
+
+    if (tid == 0) {
+        float gx, gy;
+        if (a.init_pts) { gx = a.init_pts[2 * i]; gy = a.init_pts[2 * i + 1]; }
+        else {
+            double Rd[9];
+            const float *p = a.pose;
+            dev_rodrigues_d(-p[3], -p[4], -p[5], Rd);
+            dev_project(Rd, a.kps3d[3 * i], a.kps3d[3 * i + 1], a.kps3d[3 * i + 2], p[0], p[1], p[2], a.cam.fx, a.cam.fy, a.cam.cx,
+                        a.cam.cy, a.cam.k1, a.cam.k2, a.cam.p1, a.cam.p2, a.cam.k3, gx, gy);
+        }
+        sm.init[0] = gx; sm.init[1] = gy;
+    }
+    __syncthreads();
+    const float init_x = sm.init[0], init_y = sm.init[1];
+    const float ppx = a.prev_pts[2 * i], ppy = a.prev_pts[2 * i + 1];
+    const LevelDesc *prev_lv = a.keyframe_ids ? (a.kf_lk_table + (size_t)a.keyframe_ids[i] * SVO_LK_LEVELS) : a.prev_fixed;
+
+    float nx = init_x, ny = init_y;
+    int status = 1;
+    float err = 0.f;
+    int buf = 0, total_iters = 0;
+
+    for (int level = SVO_LK_LEVELS - 1; level >= 0; level--) {
+        const LevelDesc I = prev_lv[level];
+        const LevelDesc J = a.cur[level];
+        const float scale = (float)(1. / (1 << level));
+        float px = ppx * scale, py = ppy * scale;
+        float qx, qy;
+        if (level == SVO_LK_LEVELS - 1) { qx = nx * scale; qy = ny * scale; }
+        else { qx = nx * 2.f; qy = ny * 2.f; }
+        nx = qx; ny = qy;
+        px -= half; py -= half;
+        const int ipx = (int)floorf(px), ipy = (int)floorf(py);
+        if (ipx < -win || ipx >= I.w || ipy < -win || ipy >= I.h) {
+            if (level == 0) { status = 0; err = 0.f; }
+            continue;
+        }
+        int iw00, iw01, iw10, iw11;
+        lk_weights(px - (float)ipx, py - (float)ipy, iw00, iw01, iw10, iw11);
+
+        __syncthreads();  // previous level's readers are done with tile/gx/gy
+        for (int k = tid; k < T * T; k += KLT_THREADS) {
+            int r = k / T, c = k - r * T;
+            sm.tile[k] = I.ptr[(ptrdiff_t)(ipy - 1 + r) * I.pitch + (ipx - 1 + c)];
+        }
+        __syncthreads();
+        for (int k = tid; k < W1 * W1; k += KLT_THREADS) {
+            const int y = k >> 5, x = k & 31;
+            const int X = ipx + x, Y = ipy + y;
+            int gxv = 0, gyv = 0;
+            if (X >= 0 && X < I.w && Y >= 0 && Y < I.h) {
+                const uint8_t *t = &sm.tile[(y + 1) * T + (x + 1)];
+                int tl = t[-T - 1], tc = t[-T], trr = t[-T + 1], ml = t[-1], mr = t[1], bl = t[T - 1], bc = t[T], br = t[T + 1];
+                gxv = 3 * (trr + br) + 10 * mr - (3 * (tl + bl) + 10 * ml);
+                gyv = 3 * ((bl - tl) + (br - trr)) + 10 * (bc - tc);
+            }
+            sm.gx[k] = (short)gxv; sm.gy[k] = (short)gyv;
+        }
+        __syncthreads();
+        // ---- template of this thread's run, kept in registers for the whole level
+        int Iw[4] = {0, 0, 0, 0}, Ix[4] = {0, 0, 0, 0}, Iy[4] = {0, 0, 0, 0};
+        long long s11 = 0, s12 = 0, s22 = 0;
+        if (have_row) {
+            const uint8_t *t0 = &sm.tile[(ry + 1) * T + (rx + 1)];
+            const short *g0 = &sm.gx[ry * W1 + rx], *h0 = &sm.gy[ry * W1 + rx];
+            int a0[5], a1[5], gx0[5], gx1[5], gy0[5], gy1[5];
+#pragma unroll
+            for (int j = 0; j < 5; j++) {
+                a0[j] = t0[j]; a1[j] = t0[T + j];
+                // columns up to rx+4 <= 32: gx/gy have 32 columns (index 31 max) — the 5th tap of the last run is unused
+                const int jj = (rx + j < W1) ? j : 0;
+                gx0[j] = g0[jj]; gx1[j] = g0[W1 + jj]; gy0[j] = h0[jj]; gy1[j] = h0[W1 + jj];
+            }
+            int acc11 = 0, acc12 = 0, acc22 = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (j < npx_run) {
+                    int ival = a0[j] * iw00 + a0[j + 1] * iw01 + a1[j] * iw10 + a1[j + 1] * iw11;
+                    int ixv = gx0[j] * iw00 + gx0[j + 1] * iw01 + gx1[j] * iw10 + gx1[j + 1] * iw11;
+                    int iyv = gy0[j] * iw00 + gy0[j + 1] * iw01 + gy1[j] * iw10 + gy1[j + 1] * iw11;
+                    ival = (ival + (1 << 8)) >> 9;
+                    ixv = (ixv + (1 << 13)) >> 14;
+                    iyv = (iyv + (1 << 13)) >> 14;
+                    Iw[j] = ival; Ix[j] = ixv; Iy[j] = iyv;
+                    acc11 += ixv * ixv; acc12 += ixv * iyv; acc22 += iyv * iyv;   // <= 4 * 4080^2 < 2^31
+                }
+            }
+            s11 = acc11; s12 = acc12; s22 = acc22;
+        }
+        block_sum3_31(sm, buf, s11, s12, s22);
+        buf ^= 1;
+        const float FLT_SCALE = 1.f / (1 << 20);
+        float A11 = (float)s11 * FLT_SCALE, A12 = (float)s12 * FLT_SCALE, A22 = (float)s22 * FLT_SCALE;
+        float D = A11 * A22 - A12 * A12;
+        float minEig = (A22 + A11 - sqrtf((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) / (float)(2 * win * win);
+        if ((double)minEig < 1e-4 || D < 1.1920929e-07f) {
+            if (level == 0) status = 0;
+            continue;
+        }
+        D = 1.f / D;
+        qx -= half; qy -= half;
+        float pdx = 0.f, pdy = 0.f;
+        const ptrdiff_t run_off = (ptrdiff_t)ry * J.pitch + rx;
+        for (int j = 0; j < 30; j++) {
+            const int iqx = (int)floorf(qx), iqy = (int)floorf(qy);
+            if (iqx < -win || iqx >= J.w || iqy < -win || iqy >= J.h) {
+                if (level == 0) status = 0;
+                break;
+            }
+            lk_weights(qx - (float)iqx, qy - (float)iqy, iw00, iw01, iw10, iw11);
+            total_iters++;
+            long long b1 = 0, b2 = 0;
+            if (have_row) {
+                const uint8_t *q = J.ptr + (ptrdiff_t)iqy * J.pitch + iqx + run_off;
+                int c0[5], c1[5];
+#pragma unroll
+                for (int t = 0; t < 5; t++) { c0[t] = q[t]; c1[t] = q[J.pitch + t]; }
+                int acc1 = 0, acc2 = 0;
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    int v = c0[t] * iw00 + c0[t + 1] * iw01 + c1[t] * iw10 + c1[t + 1] * iw11;
+                    int diff = ((v + (1 << 8)) >> 9) - Iw[t];
+                    if (t >= npx_run) diff = 0;
+                    acc1 += diff * Ix[t]; acc2 += diff * Iy[t];   // <= 4 * 8160 * 4080 < 2^31
+                }
+                b1 = acc1; b2 = acc2;
+            }
+            block_sum2_31(sm, buf, b1, b2);
+            buf ^= 1;
+            float fb1 = (float)b1 * FLT_SCALE, fb2 = (float)b2 * FLT_SCALE;
+            float dx = (float)((A12 * fb2 - A22 * fb1) * D);
+            float dy = (float)((A12 * fb1 - A11 * fb2) * D);
+            qx += dx; qy += dy;
+            nx = qx + half; ny = qy + half;
+            if ((double)dx * (double)dx + (double)dy * (double)dy <= 0.01 * 0.01) break;
+            if (j > 0 && fabs((double)(dx + pdx)) < 0.01 && fabs((double)(dy + pdy)) < 0.01) {
+                nx -= dx * 0.5f; ny -= dy * 0.5f;
+                break;
+            }
+            pdx = dx; pdy = dy;
+        }
+        if (status && level == 0) {
+            float ex = nx - half, ey = ny - half;
+            const int iex = (int)floorf(ex), iey = (int)floorf(ey);
+            if (iex < -win || iex >= J.w || iey < -win || iey >= J.h) { status = 0; continue; }
+            lk_weights(ex - (float)iex, ey - (float)iey, iw00, iw01, iw10, iw11);
+            long long e = 0, d1 = 0;
+            if (have_row) {
+                const uint8_t *q = J.ptr + (ptrdiff_t)iey * J.pitch + iex + run_off;
+                int c0[5], c1[5];
+#pragma unroll
+                for (int t = 0; t < 5; t++) { c0[t] = q[t]; c1[t] = q[J.pitch + t]; }
+                int acc = 0;
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    int v = c0[t] * iw00 + c0[t + 1] * iw01 + c1[t] * iw10 + c1[t + 1] * iw11;
+                    int diff = ((v + (1 << 8)) >> 9) - Iw[t];
+                    if (t < npx_run) acc += abs(diff);
+                }
+                e = acc;
+            }
+            block_sum2_31(sm, buf, e, d1);
+            buf ^= 1;
+            err = (float)e * 1.f / (float)(32 * win * win);
+        }
+    }
+
+    if (tid == 0) {
+        if (status == 0) err = __int_as_float(0x7f800000);  // optical_flow.cpp:46-50
+        a.next_pts[2 * i] = nx; a.next_pts[2 * i + 1] = ny;
+        a.status[i] = (uint8_t)status;
+        a.err[i] = err;
+        if (a.iters) a.iters[i] = total_iters;
+        if (a.flags) {  // pose_refinement.cpp:125-150
+            uint8_t f = a.flags[i];
+            float ox = init_x, oy = init_y;
+            float d = (init_x - nx) * (init_x - nx) + (init_y - ny) * (init_y - ny);
+            if (err > 20) f |= SVO_F_IGN_COMPLETE;
+            else if (d > 81) f |= SVO_F_IGN_REFINE;
+            else { f &= (uint8_t)~SVO_F_IGN_REFINE; ox = nx; oy = ny; }
+            a.flags[i] = f;
+            a.kps2d_out[2 * i] = ox; a.kps2d_out[2 * i + 1] = oy;
+        }
+    }
+}
+
 void launch_klt(const KltArgs &a, cudaStream_t st)
 {
     if (a.max_kps <= 0) return;
-    if (a.cam.win_flow == 31) klt_pyr_lk_kernel<31><<<a.max_kps, KLT_THREADS, 0, st>>>(a);
+    if (a.cam.win_flow == 31) klt31_kernel<<<a.max_kps, KLT_THREADS, 0, st>>>(a);
     else klt_pyr_lk_kernel<0><<<a.max_kps, KLT_THREADS, 0, st>>>(a);
 }

@@ -152,6 +152,23 @@ def test_klt_matches_oracle_and_opencv(c3ctx, fixture_images, cv2_vectors):
     ctx.release(s1)
 
 
+def test_klt_generic_window_sizes(fixture_images, cv2_vectors):
+    # window sizes other than 31 take the generic kernel (window_size_opt_flow is a YAML setting)
+    v = cv2_vectors
+    T, T2 = fixture_images["testimage0"], v["lk_img_next"]
+    for win in (21, 15):
+        gcs, _ = mk("C3", window_size_opt_flow=win)
+        ctx = capi.Context(gcs, 752, 480)
+        s0, s1 = ctx.upload(T, T), ctx.upload(T2, T2)
+        nxt, st, err = ctx.klt_slots(s0, s1, v["lk_prev"], v["lk_init"])
+        onxt, ost, oerr = orc.lk(T, T2, v["lk_prev"], v["lk_init"], win)
+        assert (st == ost).all()
+        ok = st == 1
+        assert ok.sum() > 80
+        assert np.abs(nxt[ok] - onxt[ok]).max() < 2e-3 and np.abs(err[ok] - oerr[ok]).max() < 5e-3   # err quantum = 1/(32 win^2)
+        ctx.close()
+
+
 # ----------------------------------------------------------------------------------------------- projection
 def test_project_bit_exact(cv2_vectors):
     v = cv2_vectors
