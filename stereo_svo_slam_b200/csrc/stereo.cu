@@ -149,14 +149,160 @@ __global__ void __launch_bounds__(SSD_THREADS) stereo_ssd_kernel(SsdArgs a, int 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Column kernel (windows up to 32 px wide, up to 16 vertical search positions — every shipped configuration):
+// one thread owns one horizontal search position j and ALL vertical positions k of it.  Each ROI row is read and
+// funnel-shifted once and then dotted against the (up to 13) template rows it meets, so the shared-memory traffic
+// and shift work per SSD drop ~3x and the template rows arrive as broadcast 128-bit loads.  64 threads per keypoint.
+// ---------------------------------------------------------------------------------------------------------
+#define SSDC_THREADS 64
+#define SSDC_MAXK 16
+
+__global__ void __launch_bounds__(SSDC_THREADS) stereo_ssd_col_kernel(SsdArgs a, int rpw, int roi_rows, int map_cap)
+{
+    extern __shared__ __align__(16) uint32_t ssd_smem32[];
+    const int win = a.cam.win_depth;
+    uint32_t *tpl = ssd_smem32;                 // 32 rows x 8 words (16-byte aligned rows)
+    uint32_t *roi = tpl + 32 * 8;               // roi_rows x rpw words
+    uint32_t *map = roi + roi_rows * rpw;       // map_cap entries
+    __shared__ unsigned long long red[SSDC_THREADS / 32];
+    __shared__ unsigned long long best_s;
+    __shared__ int cnt_s[SSDC_THREADS / 32], sum_s[SSDC_THREADS / 32];
+    __shared__ unsigned saa_s[SSDC_THREADS / 32];
+
+    const int i = blockIdx.x;
+    const int n = min(*a.n_ptr, a.max_kps);
+    if (i >= n) return;
+    const int tid = threadIdx.x;
+    const LevelDesc L = a.left0, R = a.right0;
+    SsdGeom g;
+    if (!ssd_geometry(a.kps2d[2 * i], a.kps2d[2 * i + 1], L.w, L.h, win, a.cam.search_x, a.cam.search_y, a.mode, g)) {
+        if (tid == 0) a.disparity[i] = -1.f;
+        return;
+    }
+    const int tw = g.x12 - g.x11, th = g.y12 - g.y11, rw = g.x22 - g.x21, rh = g.y22 - g.y21;
+    const int mw = rw - tw + 1, mh = rh - th + 1;
+    const uint32_t last_mask = (tw & 3) ? ((1u << ((tw & 3) * 8)) - 1u) : 0xffffffffu;
+    const int twords = (tw + 3) >> 2;
+
+    uint8_t *tpl8 = reinterpret_cast<uint8_t *>(tpl), *roi8 = reinterpret_cast<uint8_t *>(roi);
+    for (int k = tid; k < 32 * 8; k += SSDC_THREADS) tpl[k] = 0;
+    for (int k = tid; k < roi_rows * rpw; k += SSDC_THREADS) roi[k] = 0;
+    __syncthreads();
+    unsigned saa = 0;
+    for (int k = tid; k < th * tw; k += SSDC_THREADS) {
+        int r = k / tw, c = k - r * tw;
+        unsigned v = L.ptr[(size_t)(g.y11 + r) * L.pitch + g.x11 + c];
+        tpl8[r * 32 + c] = (uint8_t)v;
+        saa += v * v;
+    }
+    for (int k = tid; k < rh * rw; k += SSDC_THREADS) {
+        int r = k / rw, c = k - r * rw;
+        roi8[r * rpw * 4 + c] = R.ptr[(size_t)(g.y21 + r) * R.pitch + g.x21 + c];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) saa += __shfl_down_sync(0xffffffffu, saa, o);
+    if ((tid & 31) == 0) saa_s[tid >> 5] = saa;
+    __syncthreads();
+    saa = 0;
+#pragma unroll
+    for (int q = 0; q < SSDC_THREADS / 32; q++) saa += saa_s[q];
+
+    unsigned long long best = ~0ull;
+    for (int j = tid; j < mw; j += SSDC_THREADS) {
+        const int jw = j >> 2, sh = (j & 3) * 8;
+        unsigned sab[SSDC_MAXK], sbb[SSDC_MAXK];
+#pragma unroll
+        for (int k = 0; k < SSDC_MAXK; k++) { sab[k] = 0; sbb[k] = 0; }
+        for (int r = 0; r < rh; r++) {
+            const uint32_t *rr = roi + r * rpw + jw;
+            uint32_t b[8];
+            uint32_t w0 = rr[0];
+#pragma unroll
+            for (int x = 0; x < 8; x++) {
+                const uint32_t w1 = rr[x + 1];
+                uint32_t v = __funnelshift_r(w0, w1, sh);
+                if (x == twords - 1) v &= last_mask;
+                if (x >= twords) v = 0;
+                b[x] = v;
+                w0 = w1;
+            }
+            unsigned bb = 0;
+#pragma unroll
+            for (int x = 0; x < 8; x++) bb = __dp4a(b[x], b[x], bb);
+#pragma unroll
+            for (int k = 0; k < SSDC_MAXK; k++) {
+                const int y = r - k;          // template row meeting ROI row r at vertical position k (uniform in the CTA)
+                if (k < mh && y >= 0 && y < th) {
+                    const uint4 t0 = *reinterpret_cast<const uint4 *>(tpl + y * 8);
+                    const uint4 t1 = *reinterpret_cast<const uint4 *>(tpl + y * 8 + 4);
+                    unsigned acc = sab[k];
+                    acc = __dp4a(t0.x, b[0], acc); acc = __dp4a(t0.y, b[1], acc); acc = __dp4a(t0.z, b[2], acc); acc = __dp4a(t0.w, b[3], acc);
+                    acc = __dp4a(t1.x, b[4], acc); acc = __dp4a(t1.y, b[5], acc); acc = __dp4a(t1.z, b[6], acc); acc = __dp4a(t1.w, b[7], acc);
+                    sab[k] = acc;
+                    sbb[k] += bb;
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < SSDC_MAXK; k++) {
+            if (k < mh) {
+                const uint32_t sv = saa + sbb[k] - 2u * sab[k];
+                const int p = k * mw + j;
+                map[p] = sv;
+                unsigned long long key = ((unsigned long long)sv << 32) | (unsigned)p;
+                best = key < best ? key : best;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long other = __shfl_down_sync(0xffffffffu, best, o);
+        best = other < best ? other : best;
+    }
+    if ((tid & 31) == 0) red[tid >> 5] = best;
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long b = red[0];
+        for (int w = 1; w < SSDC_THREADS / 32; w++) b = red[w] < b ? red[w] : b;
+        best_s = b;
+    }
+    __syncthreads();
+    const uint32_t minv = (uint32_t)(best_s >> 32);
+    const int mp = (int)(best_s & 0xffffffffu);
+    const int mly = mp / mw, mlx = mp - mly * mw;
+    int cnt = 0, sum = 0;
+    for (int p = tid; p < mw * mh; p += SSDC_THREADS) {
+        const int k = p / mw, j = p - k * mw;
+        if (j >= mlx && k >= mly && map[p] <= minv) { cnt++; sum += j; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { cnt += __shfl_down_sync(0xffffffffu, cnt, o); sum += __shfl_down_sync(0xffffffffu, sum, o); }
+    if ((tid & 31) == 0) { cnt_s[tid >> 5] = cnt; sum_s[tid >> 5] = sum; }
+    __syncthreads();
+    if (tid == 0) {
+        int c = 0, sm = 0;
+        for (int w = 0; w < SSDC_THREADS / 32; w++) { c += cnt_s[w]; sm += sum_s[w]; }
+        float minPos = (float)sm / (float)c;
+        a.disparity[i] = (a.mode == 1) ? fmaxf(0.5f, minPos) : minPos;
+    }
+}
+
 void launch_stereo_ssd(const SsdArgs &a, cudaStream_t st)
 {
     if (a.max_kps <= 0) return;
     const int win = a.cam.win_depth;
+    const int map_cap = (a.cam.search_x + 1) * (2 * a.cam.search_y + 1);
+    if (win <= 32 && 2 * a.cam.search_y + 1 <= SSDC_MAXK) {
+        const int rpw = (win + a.cam.search_x + 3) / 4 + 10;      // 9 words are read from the last search column
+        const int roi_rows = win + 2 * a.cam.search_y + 1;
+        size_t smem = ((size_t)32 * 8 + (size_t)roi_rows * rpw + (size_t)map_cap) * 4 + 16;
+        stereo_ssd_col_kernel<<<a.max_kps, SSDC_THREADS, smem, st>>>(a, rpw, roi_rows, map_cap);
+        return;
+    }
     const int tpw = (win + 3) / 4 + 1;                           // words per template row (+1: never read past)
     const int rpw = (win + a.cam.search_x + 3) / 4 + 2;          // words per ROI row (+1 word read by the funnel shift)
     const int roi_rows = win + 2 * a.cam.search_y + 1;
-    const int map_cap = (a.cam.search_x + 1) * (2 * a.cam.search_y + 1);
     size_t smem = ((size_t)win * tpw + (size_t)roi_rows * rpw + (size_t)map_cap) * 4 + 16;
     stereo_ssd_kernel<<<a.max_kps, SSD_THREADS, smem, st>>>(a, tpw, rpw, roi_rows, map_cap);
 }

@@ -132,6 +132,22 @@ def test_stereo_match_bit_exact(c3ctx, fixture_images):
     ctx.release(slot)
 
 
+@pytest.mark.parametrize("over", [dict(search_x=60, search_y=6), dict(search_x=40, search_y=9), dict(window_size_depth_calculator=21, search_x=30, search_y=3),
+                                  dict(window_size_depth_calculator=35, search_x=20, search_y=2)])
+def test_stereo_match_other_settings(fixture_images, over):
+    # EuRoC.yaml search range, a range that needs the generic kernel (more than 16 vertical positions), other windows
+    gcs, ocs = mk("C3", **over)
+    ctx = capi.Context(gcs, 752, 480)
+    L, R = fixture_images["left"], fixture_images["right"]
+    slot = ctx.upload(L, R)
+    rng = np.random.default_rng(11)
+    pts = rng.uniform([-20, -20], [770, 500], (300, 2)).astype(np.float32)
+    got = ctx.stereo_match(slot, pts, 1)
+    want = orc.ssd_disparity(L, R, ocs, pts, 1)
+    assert (got == want).all(), np.nonzero(got != want)[0][:10]
+    ctx.close()
+
+
 # ----------------------------------------------------------------------------------------------- KLT
 def test_klt_matches_oracle_and_opencv(c3ctx, fixture_images, cv2_vectors):
     ctx, _, _ = c3ctx
