@@ -124,8 +124,10 @@ int svo_reproj_refine(svo_ctx *ctx, const float *kps2d, const float *kps3d, cons
 int svo_project(svo_ctx *ctx, const float pose[6], const float *kps3d, int n, float *kps2d);
 
 /* Register the image set `slot` as keyframe (KeyFrameManager::create_keyframe, keyframe_manager.cpp:15-32):
- * the device keeps its LK pyramid and pose resident for svo_klt / the depth filter. */
+ * the device keeps a copy of the image set (LK pyramid for svo_klt, images for the getters) and the pose resident. */
 int svo_keyframe_commit(svo_ctx *ctx, int slot, const float pose[6], int *keyframe_id_out);
+/* slot holding keyframe `keyframe_id`'s own copy of the image set (for getters) */
+int svo_keyframe_slot(svo_ctx *ctx, int keyframe_id, int *slot_out);
 
 /* ------------------------------------------------------------------ fused per-frame tracking --- */
 /* Everything StereoSlam::new_image does on a tracking frame between the pyramid build and the keyframe
@@ -163,6 +165,15 @@ typedef struct svo_track_io {
 } svo_track_io;
 
 int svo_track_frame(svo_ctx *ctx, int prev_slot, int cur_slot, svo_track_io *io);
+/* svo_upload_stereo[_device] + svo_track_frame_begin in one call — everything new_image enqueues for a tracking frame
+ * (stereo_slam.cpp:135-139 and :196-229).  In steady state everything after the two image copies (4 pyramid kernels, keypoint
+ * H2D, 5 tracking kernels, D2H) is replayed as ONE CUDA graph launch; finish with svo_track_frame_end.
+ * on_device != 0: left/right are device pointers. */
+int svo_frame_begin(svo_ctx *ctx, const uint8_t *left, size_t left_stride, const uint8_t *right, size_t right_stride,
+                    int on_device, int prev_slot, svo_track_io *io, int *cur_slot_out);
+/* CUDA-graph replay on/off (default on; env SVO_NO_GRAPHS=1 turns it off); counters for tests */
+int svo_set_graphs(svo_ctx *ctx, int on);
+int svo_graph_stats(svo_ctx *ctx, long long *graph_launches, long long *graph_captures);
 /* asynchronous pair (multi-sequence throughput): enqueue on the context's stream / wait + unpack */
 int svo_track_frame_begin(svo_ctx *ctx, int prev_slot, int cur_slot, svo_track_io *io);
 int svo_track_frame_end(svo_ctx *ctx, svo_track_io *io);

@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <vector>
 
 #include "kernels.cuh"
@@ -58,9 +59,23 @@ struct svo_ctx {
     long long launch_total = 0;
     bool profiling = false;
     cudaEvent_t sev[9] = {nullptr};  // stage events
+    // CUDA-graph cache of the whole per-frame sequence (upload + pyramids + tracking), keyed by the fixed resources
+    struct FrameGraph {
+        int prev_slot, cur_slot, bucket, src_kind, stage_idx;
+        cudaGraphExec_t exec;
+        cudaGraphNode_t left_copy, right_copy;
+        unsigned long long last_use;
+        int launches;
+    };
+    std::vector<FrameGraph> graphs;
+    bool use_graphs = true;
+    unsigned long long graph_clock = 0;
+    long long graph_launches = 0, graph_captures = 0;
     float stage_ms[8] = {0};
     char err[256];
 };
+
+static void destroy_graph(svo_ctx::FrameGraph &g);
 
 template <class T> static T *io_ptr(uint8_t *base, size_t off) { return reinterpret_cast<T *>(base + off); }
 
@@ -135,6 +150,7 @@ extern "C" int svo_ctx_create(const svo_camera_settings *s, int device, int widt
     ctx->cam = make_devcam(*s);
     ctx->W = width; ctx->H = height;
     ctx->n_levels = s->max_pyramid_levels;
+    ctx->use_graphs = getenv("SVO_NO_GRAPHS") == nullptr;
     if (max_keypoints <= 0) {
         // one keypoint per grid cell per keyframe, surviving ones from older keyframes on top: 4x cells is ample
         max_keypoints = 4 * (width / s->grid_width + 1) * (height / s->grid_height + 1);
@@ -202,6 +218,7 @@ extern "C" int svo_ctx_destroy(svo_ctx *ctx)
     if (!ctx) return SVO_ERR_INVALID;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (auto &g : ctx->graphs) destroy_graph(g);
     for (auto &s : ctx->slots) if (s.base) cudaFree(s.base);
     for (int k = 0; k < 2; k++) if (ctx->h_stage[k]) cudaFreeHost(ctx->h_stage[k]);
     if (ctx->d_io) cudaFree(ctx->d_io);
@@ -255,76 +272,100 @@ static int alloc_slot(svo_ctx *ctx, int *slot_out)
     return SVO_OK;
 }
 
-extern "C" int svo_upload_stereo(svo_ctx *ctx, const uint8_t *left, size_t ls, const uint8_t *right, size_t rs, int *slot_out)
+// src_kind: 0 = pageable host memory (staged through the context's pinned buffer), 1 = page-locked host memory
+// (direct DMA), 2 = device memory
+static int classify_source(const uint8_t *left, const uint8_t *right)
 {
-    if (!ctx || !left || !right || !slot_out || ls < (size_t)ctx->W || rs < (size_t)ctx->W) return SVO_ERR_INVALID;
+    static const bool skip_query = getenv("SVO_ASSUME_PAGEABLE") != nullptr;   // diagnostic switch
+    if (skip_query) return 0;
+    cudaPointerAttributes al, ar;
+    bool ok = cudaPointerGetAttributes(&al, left) == cudaSuccess && cudaPointerGetAttributes(&ar, right) == cudaSuccess;
+    cudaGetLastError();  // clear a possible "invalid value" from querying unregistered memory on old drivers
+    if (!ok) return 0;
+    if (al.type == cudaMemoryTypeHost && ar.type == cudaMemoryTypeHost) return 1;
+    if ((al.type == cudaMemoryTypeDevice || al.type == cudaMemoryTypeManaged) && (ar.type == cudaMemoryTypeDevice || ar.type == cudaMemoryTypeManaged)) return 2;
+    return 0;
+}
+
+// host part of a staged upload: copy the caller's (possibly strided) rows into the pinned staging buffer
+static uint8_t *stage_images(svo_ctx *ctx, const uint8_t *left, size_t ls, const uint8_t *right, size_t rs, int stage_idx)
+{
+    const size_t img = (size_t)ctx->W * ctx->H;
+    uint8_t *stage = ctx->h_stage[stage_idx];
+    if (ls == (size_t)ctx->W && rs == (size_t)ctx->W) {
+        memcpy(stage, left, img);
+        memcpy(stage + img, right, img);
+    } else {
+        for (int y = 0; y < ctx->H; y++) {
+            memcpy(stage + (size_t)y * ctx->W, left + (size_t)y * ls, ctx->W);
+            memcpy(stage + img + (size_t)y * ctx->W, right + (size_t)y * rs, ctx->W);
+        }
+    }
+    return stage;
+}
+
+// stream part of an upload: copies + pyramid kernels (stereo_slam.cpp:135-139).  For src_kind 0 `left`/`right`
+// are the two halves of the staging buffer.
+static int enqueue_upload(svo_ctx *ctx, Slot &s, const uint8_t *left, size_t ls, const uint8_t *right, size_t rs, int src_kind,
+                          bool copies_only = false)
+{
+    const size_t img = (size_t)ctx->W * ctx->H;
+    const cudaMemcpyKind kind = src_kind == 2 ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    // contiguous rows: one linear DMA (a 2-D copy of 752-byte rows costs one descriptor per row)
+    if (ls == (size_t)ctx->W) CK(cudaMemcpyAsync(s.dev.left[0].ptr, left, img, kind, ctx->stream));
+    else CK(cudaMemcpy2DAsync(s.dev.left[0].ptr, ctx->W, left, ls, ctx->W, ctx->H, kind, ctx->stream));
+    if (rs == (size_t)ctx->W) CK(cudaMemcpyAsync(s.dev.right0.ptr, right, img, kind, ctx->stream));
+    else CK(cudaMemcpy2DAsync(s.dev.right0.ptr, ctx->W, right, rs, ctx->W, ctx->H, kind, ctx->stream));
+    if (copies_only) return SVO_OK;
+    launch_pyr_halfsample(s.dev, ctx->stream);
+    launch_lk_pyramid(s.dev, ctx->stream);
+    CK(cudaGetLastError());
+    return SVO_OK;
+}
+
+static int enqueue_pyramids(svo_ctx *ctx, Slot &s)
+{
+    launch_pyr_halfsample(s.dev, ctx->stream);
+    launch_lk_pyramid(s.dev, ctx->stream);
+    CK(cudaGetLastError());
+    return SVO_OK;
+}
+
+static int upload_common(svo_ctx *ctx, const uint8_t *left, size_t ls, const uint8_t *right, size_t rs, int src_kind, int *slot_out)
+{
     CK(cudaSetDevice(ctx->device));
     int id;
     int rc = alloc_slot(ctx, &id);
     if (rc) return rc;
     Slot &s = ctx->slots[id];
     const size_t img = (size_t)ctx->W * ctx->H;
-    // Page-locked caller memory (cudaHostAlloc / cudaHostRegister / torch pin_memory) is DMA'd directly; pageable
-    // memory goes through the context's own pinned staging buffer (double buffered; uploads on one stream are
-    // ordered and the caller synchronises once per frame).
-    cudaPointerAttributes al, ar;
-    static const bool skip_query = getenv("SVO_ASSUME_PAGEABLE") != nullptr;   // diagnostic switch
-    bool pinned = !skip_query && cudaPointerGetAttributes(&al, left) == cudaSuccess && cudaPointerGetAttributes(&ar, right) == cudaSuccess &&
-                  al.type == cudaMemoryTypeHost && ar.type == cudaMemoryTypeHost;
-    cudaGetLastError();  // clear a possible "invalid value" from querying unregistered memory on old drivers
-    if (pinned) {
-        if (ctx->profiling) CK(cudaEventRecord(ctx->sev[0], ctx->stream));
-        // contiguous rows: one linear DMA (a 2-D copy of 752-byte rows costs one descriptor per row)
-        if (ls == (size_t)ctx->W) CK(cudaMemcpyAsync(s.dev.left[0].ptr, left, img, cudaMemcpyHostToDevice, ctx->stream));
-        else CK(cudaMemcpy2DAsync(s.dev.left[0].ptr, ctx->W, left, ls, ctx->W, ctx->H, cudaMemcpyHostToDevice, ctx->stream));
-        if (rs == (size_t)ctx->W) CK(cudaMemcpyAsync(s.dev.right0.ptr, right, img, cudaMemcpyHostToDevice, ctx->stream));
-        else CK(cudaMemcpy2DAsync(s.dev.right0.ptr, ctx->W, right, rs, ctx->W, ctx->H, cudaMemcpyHostToDevice, ctx->stream));
-    } else {
-        uint8_t *stage = ctx->h_stage[ctx->stage_idx];
+    if (src_kind == 0) {
+        // pageable memory goes through the context's own pinned staging buffer (double buffered; uploads on one
+        // stream are ordered and the caller synchronises once per frame)
+        uint8_t *stage = stage_images(ctx, left, ls, right, rs, ctx->stage_idx);
         ctx->stage_idx ^= 1;
-        if (ls == (size_t)ctx->W && rs == (size_t)ctx->W) {
-            memcpy(stage, left, img);
-            memcpy(stage + img, right, img);
-        } else {
-            for (int y = 0; y < ctx->H; y++) {
-                memcpy(stage + (size_t)y * ctx->W, left + (size_t)y * ls, ctx->W);
-                memcpy(stage + img + (size_t)y * ctx->W, right + (size_t)y * rs, ctx->W);
-            }
-        }
-        if (ctx->profiling) CK(cudaEventRecord(ctx->sev[0], ctx->stream));
-        CK(cudaMemcpyAsync(s.dev.left[0].ptr, stage, img, cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaMemcpyAsync(s.dev.right0.ptr, stage + img, img, cudaMemcpyHostToDevice, ctx->stream));
+        left = stage; right = stage + img; ls = rs = (size_t)ctx->W;
     }
-    launch_pyr_halfsample(s.dev, ctx->stream);
-    launch_lk_pyramid(s.dev, ctx->stream);
+    if (ctx->profiling) CK(cudaEventRecord(ctx->sev[0], ctx->stream));
+    if ((rc = enqueue_upload(ctx, s, left, ls, right, rs, src_kind))) return rc;
     ctx->launch_total += pyr_launch_count(s.dev);
-    CK(cudaGetLastError());
     if (ctx->profiling) CK(cudaEventRecord(ctx->sev[1], ctx->stream));
     *slot_out = id;
     return SVO_OK;
 }
 
+extern "C" int svo_upload_stereo(svo_ctx *ctx, const uint8_t *left, size_t ls, const uint8_t *right, size_t rs, int *slot_out)
+{
+    if (!ctx || !left || !right || !slot_out || ls < (size_t)ctx->W || rs < (size_t)ctx->W) return SVO_ERR_INVALID;
+    int kind = classify_source(left, right);
+    if (kind == 2) kind = 0;  // a device pointer passed to the host entry point is a caller error; treat as host memory
+    return upload_common(ctx, left, ls, right, rs, kind, slot_out);
+}
+
 extern "C" int svo_upload_stereo_device(svo_ctx *ctx, const uint8_t *d_left, size_t ls, const uint8_t *d_right, size_t rs, int *slot_out)
 {
     if (!ctx || !d_left || !d_right || !slot_out || ls < (size_t)ctx->W || rs < (size_t)ctx->W) return SVO_ERR_INVALID;
-    CK(cudaSetDevice(ctx->device));
-    int id;
-    int rc = alloc_slot(ctx, &id);
-    if (rc) return rc;
-    Slot &s = ctx->slots[id];
-    if (ctx->profiling) CK(cudaEventRecord(ctx->sev[0], ctx->stream));
-    const size_t img = (size_t)ctx->W * ctx->H;
-    if (ls == (size_t)ctx->W) CK(cudaMemcpyAsync(s.dev.left[0].ptr, d_left, img, cudaMemcpyDeviceToDevice, ctx->stream));
-    else CK(cudaMemcpy2DAsync(s.dev.left[0].ptr, ctx->W, d_left, ls, ctx->W, ctx->H, cudaMemcpyDeviceToDevice, ctx->stream));
-    if (rs == (size_t)ctx->W) CK(cudaMemcpyAsync(s.dev.right0.ptr, d_right, img, cudaMemcpyDeviceToDevice, ctx->stream));
-    else CK(cudaMemcpy2DAsync(s.dev.right0.ptr, ctx->W, d_right, rs, ctx->W, ctx->H, cudaMemcpyDeviceToDevice, ctx->stream));
-    launch_pyr_halfsample(s.dev, ctx->stream);
-    launch_lk_pyramid(s.dev, ctx->stream);
-    ctx->launch_total += pyr_launch_count(s.dev);
-    CK(cudaGetLastError());
-    if (ctx->profiling) CK(cudaEventRecord(ctx->sev[1], ctx->stream));
-    *slot_out = id;
-    return SVO_OK;
+    return upload_common(ctx, d_left, ls, d_right, rs, 2, slot_out);
 }
 
 extern "C" int svo_launch_count(svo_ctx *ctx, long long *launches)
@@ -685,6 +726,16 @@ extern "C" int svo_keyframe_commit(svo_ctx *ctx, int slot, const float pose[6], 
         CK(cudaMemcpy(np, ctx->d_kf_pose, (size_t)ctx->kf_cap * 24 * sizeof(float), cudaMemcpyDeviceToDevice));
         cudaFree(ctx->d_kf_lk); cudaFree(ctx->d_kf_pose);
         ctx->d_kf_lk = nl; ctx->d_kf_pose = np; ctx->kf_cap = ncap;
+        for (auto &g : ctx->graphs) destroy_graph(g);   // captured kernels hold the old table pointers
+        ctx->graphs.clear();
+    }
+    // the keyframe gets its OWN copy of the image set (device-to-device, 1.5 MB): frame slots then keep alternating
+    // between two fixed buffers, which is what lets the per-frame sequence be replayed as a CUDA graph
+    int kslot;
+    {
+        int rc2 = alloc_slot(ctx, &kslot);
+        if (rc2) return rc2;
+        CK(cudaMemcpyAsync(ctx->slots[kslot].base, ctx->slots[slot].base, ctx->slot_bytes, cudaMemcpyDeviceToDevice, ctx->stream));
     }
     int id = ctx->kf_count;
     float rec[24];
@@ -693,21 +744,27 @@ extern "C" int svo_keyframe_commit(svo_ctx *ctx, int slot, const float pose[6], 
     host_rodrigues_f(rp, rec + 6);
     host_rodrigues_f(rn, rec + 15);
     CK(cudaMemcpyAsync(ctx->d_kf_pose + (size_t)id * 24, rec, sizeof(rec), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->d_kf_lk + (size_t)id * SVO_LK_LEVELS, ctx->slots[slot].dev.lk, SVO_LK_LEVELS * sizeof(LevelDesc),
+    CK(cudaMemcpyAsync(ctx->d_kf_lk + (size_t)id * SVO_LK_LEVELS, ctx->slots[kslot].dev.lk, SVO_LK_LEVELS * sizeof(LevelDesc),
                        cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));  // rec is on the stack
-    ctx->slots[slot].refcount++;
+    slot = kslot;
     ctx->kf_slot.push_back(slot);
     ctx->kf_count++;
     *keyframe_id_out = id;
     return SVO_OK;
 }
 
-// ------------------------------------------------------------------------------------------------ fused frame
-extern "C" int svo_track_frame_begin(svo_ctx *ctx, int prev_slot, int cur_slot, svo_track_io *io)
+extern "C" int svo_keyframe_slot(svo_ctx *ctx, int keyframe_id, int *slot_out)
 {
-    if (!ctx || !io || !slot_ok(ctx, prev_slot) || !slot_ok(ctx, cur_slot)) return SVO_ERR_INVALID;
-    if (ctx->track_pending) { snprintf(ctx->err, sizeof(ctx->err), "svo_track_frame_begin called twice without _end"); return SVO_ERR_STATE; }
+    if (!ctx || !slot_out || keyframe_id < 0 || keyframe_id >= ctx->kf_count) return SVO_ERR_INVALID;
+    *slot_out = ctx->kf_slot[keyframe_id];
+    return SVO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ fused frame
+static int validate_and_pack(svo_ctx *ctx, svo_track_io *io)
+{
+    if (ctx->track_pending) { snprintf(ctx->err, sizeof(ctx->err), "tracking frame begun twice without _end"); return SVO_ERR_STATE; }
     const int n = io->n;
     int rc = check_n(ctx, n);
     if (rc) return rc;
@@ -716,7 +773,6 @@ extern "C" int svo_track_frame_begin(svo_ctx *ctx, int prev_slot, int cur_slot, 
         return SVO_ERR_INVALID;
     for (int i = 0; i < n; i++)
         if (io->keyframe_id[i] < 0 || io->keyframe_id[i] >= ctx->kf_count) { snprintf(ctx->err, sizeof(ctx->err), "keypoint %d: unknown keyframe id %d", i, io->keyframe_id[i]); return SVO_ERR_INVALID; }
-    CK(cudaSetDevice(ctx->device));
     const IoLayout &L = ctx->lay;
     uint8_t *h = ctx->h_io;
     *io_ptr<int>(h, L.n) = n;
@@ -729,9 +785,15 @@ extern "C" int svo_track_frame_begin(svo_ctx *ctx, int prev_slot, int cur_slot, 
     memcpy(h + L.inlier, io->inlier_count, (size_t)n * 4);
     memcpy(h + L.outlier, io->outlier_count, (size_t)n * 4);
     memcpy(h + L.kf_state, io->kf_state, (size_t)n * 8);
+    return SVO_OK;
+}
 
-    const bool prof = ctx->profiling;
-    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+// stream part of a tracking frame; grid_n = number of per-keypoint CTAs to launch (>= n; the kernels read n from
+// device memory), prof = record the per-stage events
+static int enqueue_track(svo_ctx *ctx, int prev_slot, int cur_slot, int n, int grid_n, bool prof, int *launches_out)
+{
+    const IoLayout &L = ctx->lay;
+    uint8_t *h = ctx->h_io;
     // one H2D for all inputs (in + in/out regions are contiguous)
     CK(cudaMemcpyAsync(ctx->d_io, h, L.pose_aligned, cudaMemcpyHostToDevice, ctx->stream));
     int launches = 0;
@@ -749,7 +811,7 @@ extern "C" int svo_track_frame_begin(svo_ctx *ctx, int prev_slot, int cur_slot, 
         for (int l = 0; l < SVO_LK_LEVELS; l++) ka.cur[l] = ctx->slots[cur_slot].dev.lk[l];
         ka.prev_pts = DP(float, ref_kps2d); ka.init_pts = nullptr; ka.kps3d = DP(float, kps3d); ka.pose = DP(float, pose_aligned);
         ka.n_ptr = DP(int, n); ka.next_pts = DP(float, klt_pts); ka.status = DP(uint8_t, klt_status); ka.err = DP(float, klt_err);
-        ka.flags = DP(uint8_t, flags); ka.kps2d_out = DP(float, kps2d_ref_in); ka.max_kps = n; ka.cam = ctx->cam;
+        ka.flags = DP(uint8_t, flags); ka.kps2d_out = DP(float, kps2d_ref_in); ka.max_kps = grid_n; ka.cam = ctx->cam;
         ka.iters = DP(int, klt_iters);
         launch_klt(ka, ctx->stream); launches++;
     }
@@ -766,14 +828,14 @@ extern "C" int svo_track_frame_begin(svo_ctx *ctx, int prev_slot, int cur_slot, 
         SsdArgs sa;
         sa.left0 = ctx->slots[cur_slot].dev.left[0]; sa.right0 = ctx->slots[cur_slot].dev.right0;
         sa.kps2d = DP(float, kps2d_ref_in); sa.n_ptr = DP(int, n); sa.mode = 1; sa.disparity = DP(float, disparity);
-        sa.max_kps = n; sa.cam = ctx->cam;
+        sa.max_kps = grid_n; sa.cam = ctx->cam;
         launch_stereo_ssd(sa, ctx->stream); launches++;
         if (prof) CK(cudaEventRecord(ctx->sev[6], ctx->stream));
         FilterArgs fa;
         fa.kf_pose_table = ctx->d_kf_pose; fa.keyframe_ids = DP(int, kf_id); fa.disparity = DP(float, disparity);
         fa.kps2d = DP(float, kps2d_ref_in); fa.ref_kps2d = DP(float, ref_kps2d); fa.kps3d = DP(float, kps3d);
         fa.flags = DP(uint8_t, flags); fa.inlier = DP(int, inlier); fa.outlier = DP(int, outlier); fa.kf_state = DP(float, kf_state);
-        fa.pose = DP(float, pose_refined); fa.kps2d_out = DP(float, kps2d_out); fa.n_ptr = DP(int, n); fa.max_kps = n; fa.cam = ctx->cam;
+        fa.pose = DP(float, pose_refined); fa.kps2d_out = DP(float, kps2d_out); fa.n_ptr = DP(int, n); fa.max_kps = grid_n; fa.cam = ctx->cam;
         launch_depth_filter(fa, ctx->stream); launches++;
     } else if (prof) {
         CK(cudaEventRecord(ctx->sev[6], ctx->stream));
@@ -782,11 +844,135 @@ extern "C" int svo_track_frame_begin(svo_ctx *ctx, int prev_slot, int cur_slot, 
     CK(cudaGetLastError());
     // one D2H for all outputs (in/out + out regions are contiguous)
     CK(cudaMemcpyAsync(h + L.inout_begin, ctx->d_io + L.inout_begin, L.total - L.inout_begin, cudaMemcpyDeviceToHost, ctx->stream));
+    *launches_out = launches;
+    return SVO_OK;
+}
+
+extern "C" int svo_track_frame_begin(svo_ctx *ctx, int prev_slot, int cur_slot, svo_track_io *io)
+{
+    if (!ctx || !io || !slot_ok(ctx, prev_slot) || !slot_ok(ctx, cur_slot)) return SVO_ERR_INVALID;
+    int rc = validate_and_pack(ctx, io);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    const bool prof = ctx->profiling;
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    int launches = 0;
+    if ((rc = enqueue_track(ctx, prev_slot, cur_slot, io->n, io->n, prof, &launches))) return rc;
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     if (prof) CK(cudaEventRecord(ctx->sev[8], ctx->stream));
     ctx->last_launches = launches;
     ctx->launch_total += launches;
     ctx->track_pending = true;
+    return SVO_OK;
+}
+
+// ---- upload + tracking as one replayable CUDA graph ------------------------------------------------------------
+static void destroy_graph(svo_ctx::FrameGraph &g)
+{
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+    g.exec = nullptr;
+}
+
+static int capture_frame_graph(svo_ctx *ctx, svo_ctx::FrameGraph &g, int n)
+{
+    cudaGraph_t graph = nullptr;
+    Slot &s = ctx->slots[g.cur_slot];
+    CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    int launches = 0;
+    int rc = enqueue_pyramids(ctx, s);
+    if (!rc) rc = enqueue_track(ctx, g.prev_slot, g.cur_slot, n, g.bucket, false, &launches);
+    cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    CK(e);
+    g.launches = launches + pyr_launch_count(s.dev);
+    CK(cudaGraphInstantiate(&g.exec, graph, 0));
+    cudaGraphDestroy(graph);
+    ctx->graph_captures++;
+    return SVO_OK;
+}
+
+/* upload + pyramids + tracking in one call (what StereoSlam::new_image does for a tracking frame). */
+extern "C" int svo_frame_begin(svo_ctx *ctx, const uint8_t *left, size_t ls, const uint8_t *right, size_t rs, int on_device, int prev_slot,
+                               svo_track_io *io, int *cur_slot_out)
+{
+    if (!ctx || !left || !right || !io || !cur_slot_out || ls < (size_t)ctx->W || rs < (size_t)ctx->W || !slot_ok(ctx, prev_slot)) return SVO_ERR_INVALID;
+    int rc = validate_and_pack(ctx, io);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    int src_kind = on_device ? 2 : classify_source(left, right);
+    if (!on_device && src_kind == 2) src_kind = 0;
+    const int n = io->n;
+    const bool contiguous = ls == (size_t)ctx->W && rs == (size_t)ctx->W;
+    const bool graph_ok = ctx->use_graphs && !ctx->profiling && n > 0;
+    (void)contiguous;
+    int cur;
+    const size_t img = (size_t)ctx->W * ctx->H;
+    if (!graph_ok) {
+        if ((rc = upload_common(ctx, left, ls, right, rs, src_kind, &cur))) return rc;
+        *cur_slot_out = cur;
+        const bool prof = ctx->profiling;
+        CK(cudaEventRecord(ctx->ev0, ctx->stream));
+        int launches = 0;
+        if ((rc = enqueue_track(ctx, prev_slot, cur, n, n, prof, &launches))) return rc;
+        CK(cudaEventRecord(ctx->ev1, ctx->stream));
+        if (prof) CK(cudaEventRecord(ctx->sev[8], ctx->stream));
+        ctx->last_launches = launches;
+        ctx->launch_total += launches;
+        ctx->track_pending = true;
+        return SVO_OK;
+    }
+    if ((rc = alloc_slot(ctx, &cur))) return rc;
+    *cur_slot_out = cur;
+    int stage_idx = 0;
+    if (src_kind == 0) {
+        stage_idx = ctx->stage_idx;
+        uint8_t *stage = stage_images(ctx, left, ls, right, rs, stage_idx);
+        ctx->stage_idx ^= 1;
+        left = stage; right = stage + img; ls = rs = (size_t)ctx->W;
+    }
+    // the two image copies go on the stream directly (their source changes every frame); pyramids + tracking replay
+    if ((rc = enqueue_upload(ctx, ctx->slots[cur], left, ls, right, rs, src_kind, true))) return rc;
+    const int bucket = std::min(ctx->max_kps, (n + 127) / 128 * 128);
+    svo_ctx::FrameGraph *g = nullptr;
+    for (auto &c : ctx->graphs)
+        if (c.exec && c.prev_slot == prev_slot && c.cur_slot == cur && c.bucket == bucket) { g = &c; break; }
+    if (!g) {
+        if (ctx->graphs.size() >= 12) {  // evict the least recently used
+            size_t v = 0;
+            for (size_t k = 1; k < ctx->graphs.size(); k++) if (ctx->graphs[k].last_use < ctx->graphs[v].last_use) v = k;
+            destroy_graph(ctx->graphs[v]);
+            ctx->graphs.erase(ctx->graphs.begin() + v);
+        }
+        svo_ctx::FrameGraph ng;
+        ng.prev_slot = prev_slot; ng.cur_slot = cur; ng.bucket = bucket; ng.src_kind = src_kind; ng.stage_idx = stage_idx;
+        ng.exec = nullptr; ng.left_copy = ng.right_copy = nullptr; ng.last_use = 0; ng.launches = 0;
+        if ((rc = capture_frame_graph(ctx, ng, n))) return rc;
+        ctx->graphs.push_back(ng);
+        g = &ctx->graphs.back();
+    }
+    g->last_use = ++ctx->graph_clock;
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    CK(cudaGraphLaunch(g->exec, ctx->stream));
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->graph_launches++;
+    ctx->last_launches = g->launches;
+    ctx->launch_total += g->launches;
+    ctx->track_pending = true;
+    return SVO_OK;
+}
+
+extern "C" int svo_set_graphs(svo_ctx *ctx, int on)
+{
+    if (!ctx) return SVO_ERR_INVALID;
+    ctx->use_graphs = on != 0;
+    return SVO_OK;
+}
+
+extern "C" int svo_graph_stats(svo_ctx *ctx, long long *graph_launches, long long *graph_captures)
+{
+    if (!ctx) return SVO_ERR_INVALID;
+    if (graph_launches) *graph_launches = ctx->graph_launches;
+    if (graph_captures) *graph_captures = ctx->graph_captures;
     return SVO_OK;
 }
 

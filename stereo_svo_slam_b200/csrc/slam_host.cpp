@@ -291,6 +291,8 @@ struct svo_slam {
         rc = svo_keyframe_commit(ctx, f.slot, f.pose, &id);  // retains the slot
         if (rc) return rc;
         if ((uint64_t)id != kf_id) { snprintf(err, sizeof(err), "keyframe id mismatch"); return SVO_ERR_STATE; }
+        rc = svo_keyframe_slot(ctx, id, &k->slot);  // the device keeps its own copy of the keyframe's images
+        if (rc) return rc;
         keyframes.push_back(std::move(k));
         last_keyframe_created = 1;
         return SVO_OK;
@@ -343,11 +345,12 @@ struct svo_slam {
         previous = std::move(frame);
         frame.reset(new FrameH());
         frame->time_stamp = ts;
-        int rc = on_device ? svo_upload_stereo_device(ctx, left, ls, right, rs, &frame->slot)
-                           : svo_upload_stereo(ctx, left, ls, right, rs, &frame->slot);  // pyramids (stereo_slam.cpp:135-139)
-        if (rc) return fail(rc);
+        int rc = SVO_OK;
         pending = true;
-        if (!previous) {  // first frame (stereo_slam.cpp:142-160)
+        if (!previous) {  // first frame (stereo_slam.cpp:142-160): pyramids only, keyframe creation in _end
+            rc = on_device ? svo_upload_stereo_device(ctx, left, ls, right, rs, &frame->slot)
+                           : svo_upload_stereo(ctx, left, ls, right, rs, &frame->slot);  // pyramids (stereo_slam.cpp:135-139)
+            if (rc) { pending = false; return fail(rc); }
             frame->id = 0;
             pending_first = true;
             return SVO_OK;
@@ -388,7 +391,8 @@ struct svo_slam {
         io.kps2d = io_kps2d.data();
         io.klt_iters = io_kltit.data(); io.klt_status = io_kltst.data();
         std::memcpy(io.pose_prior, frame->pose, sizeof(io.pose_prior));
-        rc = svo_track_frame_begin(ctx, previous->slot, frame->slot, &io);
+        // pyramids (stereo_slam.cpp:135-139) + the whole tracking sequence, one CUDA graph launch in steady state
+        rc = svo_frame_begin(ctx, left, ls, right, rs, on_device ? 1 : 0, previous->slot, &io, &frame->slot);
         if (rc) { pending = false; return fail(rc); }
         return SVO_OK;
     }

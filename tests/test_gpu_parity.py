@@ -386,6 +386,35 @@ def test_slam_free_running_matches_oracle(cfg, frames):
     g.close()
 
 
+def test_cuda_graph_replay_is_bit_identical():
+    """The per-frame sequence replayed as a CUDA graph (default) and launched kernel by kernel give the same bits."""
+    import ctypes as C
+    from stereo_svo_slam_b200 import StereoSlam
+    gcs, _ = mk("S")
+    c = synth.CONFIGS["S"]
+    seq = synth.make_sequence("S")
+    runs = []
+    for graphs in (1, 0):
+        g = StereoSlam(gcs, c["width"], c["height"])
+        ctxp = C.c_void_p(capi.lib().svo_slam_ctx(g._h))
+        assert capi.lib().svo_set_graphs(ctxp, graphs) == 0
+        poses, kps = [], []
+        for k in range(25):
+            L, R = seq.render(k)
+            g.new_image(L, R, k / 20.0)
+            poses.append(g.pose())
+            kps.append(g.get_frame().kps.kps3d.copy())
+        gl, gc = C.c_longlong(), C.c_longlong()
+        capi.lib().svo_graph_stats(ctxp, C.byref(gl), C.byref(gc))
+        runs.append((np.array(poses), kps, gl.value, gc.value, g.keyframe_count()))
+        g.close()
+    (p1, k1, gl1, gc1, nk1), (p0, k0, gl0, gc0, nk0) = runs
+    assert gl1 >= 20 and gc1 <= 8 and gl0 == 0, (gl1, gc1, gl0)
+    assert nk1 == nk0 and (p1 == p0).all()
+    for a, b in zip(k1, k0):
+        assert a.shape == b.shape and (a == b).all()
+
+
 def test_error_behaviour(c3ctx):
     ctx, gcs, _ = c3ctx
     with pytest.raises(capi.SvoError):
