@@ -15,6 +15,7 @@
 // final int64 -> float conversion (OpenCV rounds after every add; difference <= 1e-5 px, tolerance 0.01 px).
 // Every thread redundantly performs the scalar 2x2 update from the reduced sums, which removes the broadcast
 // barrier: one __syncthreads per LK iteration.
+#include <cstdlib>
 #include "kernels.cuh"
 
 #define KLT_THREADS 256
@@ -471,9 +472,244 @@ __global__ void __launch_bounds__(KLT_THREADS) klt31_kernel(KltArgs a)
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Warp-per-keypoint kernel for the 31x31 window: lane l owns window row l for the whole level (31 template pixels
+// = Iw/Ix/Iy in registers), no block barrier anywhere.  Per LK iteration a lane fetches its 32-byte row of the next
+// image as aligned words (+ funnel shift), gets the row below from lane l+1 with shuffles, evaluates the Q14
+// bilinear taps two at a time on the 2-way 16x8-bit dot-product unit (IDP.2A: weights are <= 2^14, pixels 8 bit),
+// and the two window sums are reduced exactly with integer warp reductions (REDUX on 16-bit halves).  Every lane
+// then applies the 2x2 update redundantly.  4 keypoints per 128-thread CTA; the footprint per keypoint is one warp,
+// so kernels of many sequences overlap instead of queueing for CTA slots.
+// ---------------------------------------------------------------------------------------------------------
+#define KLTW_WARPS 4
+struct KltWarpShared {
+    __align__(16) uint8_t tile[34 * 36];
+    short gx[32 * 32];
+    short gy[32 * 32];
+};
+
+// exact warp-wide sum of a 32-bit signed value per lane (|v| < 2^31), returned as 64 bit to every lane
+__device__ __forceinline__ long long warp_sum_i32_exact(int v)
+{
+    const int lo = v & 0xFFFF, hi = v >> 16;   // v == (hi << 16) + lo
+    const int slo = __reduce_add_sync(0xffffffffu, lo);
+    const int shi = __reduce_add_sync(0xffffffffu, hi);
+    return ((long long)shi << 16) + (long long)slo;
+}
+
+__global__ void __launch_bounds__(32 * KLTW_WARPS) klt31w_kernel(KltArgs a)
+{
+    __shared__ KltWarpShared smw[KLTW_WARPS];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int i = blockIdx.x * KLTW_WARPS + wid;
+    const int n = min(*a.n_ptr, a.max_kps);
+    if (i >= n) return;   // whole warp exits together
+    KltWarpShared &sm = smw[wid];
+    constexpr int win = 31, T = 36, W1 = 32;   // tile rows padded to 36 bytes (9 words)
+    const float half = 15.0f;
+    const bool have_row = lane < win;
+
+    float init_x, init_y;
+    if (a.init_pts) { init_x = a.init_pts[2 * i]; init_y = a.init_pts[2 * i + 1]; }
+    else {
+        double Rd[9];
+        const float *p = a.pose;
+        dev_rodrigues_d(-p[3], -p[4], -p[5], Rd);
+        dev_project(Rd, a.kps3d[3 * i], a.kps3d[3 * i + 1], a.kps3d[3 * i + 2], p[0], p[1], p[2], a.cam.fx, a.cam.fy, a.cam.cx, a.cam.cy,
+                    a.cam.k1, a.cam.k2, a.cam.p1, a.cam.p2, a.cam.k3, init_x, init_y);
+    }
+    const float ppx = a.prev_pts[2 * i], ppy = a.prev_pts[2 * i + 1];
+    const LevelDesc *prev_lv = a.keyframe_ids ? (a.kf_lk_table + (size_t)a.keyframe_ids[i] * SVO_LK_LEVELS) : a.prev_fixed;
+
+    float nx = init_x, ny = init_y;
+    int status = 1;
+    float err = 0.f;
+    int total_iters = 0;
+
+    for (int level = SVO_LK_LEVELS - 1; level >= 0; level--) {
+        const LevelDesc I = prev_lv[level];
+        const LevelDesc J = a.cur[level];
+        const float scale = (float)(1. / (1 << level));
+        float px = ppx * scale, py = ppy * scale;
+        float qx, qy;
+        if (level == SVO_LK_LEVELS - 1) { qx = nx * scale; qy = ny * scale; }
+        else { qx = nx * 2.f; qy = ny * 2.f; }
+        nx = qx; ny = qy;
+        px -= half; py -= half;
+        const int ipx = (int)floorf(px), ipy = (int)floorf(py);
+        if (ipx < -win || ipx >= I.w || ipy < -win || ipy >= I.h) {
+            if (level == 0) { status = 0; err = 0.f; }
+            continue;
+        }
+        int iw00, iw01, iw10, iw11;
+        lk_weights(px - (float)ipx, py - (float)ipy, iw00, iw01, iw10, iw11);
+
+        __syncwarp();
+        // stage the 34x34 tile: one row per lane (rows 32,33 by lanes 0,1) as 10 independent aligned word loads
+        for (int r = lane; r < 34; r += 32) {
+            const uint8_t *rowp = I.ptr + (ptrdiff_t)(ipy - 1 + r) * I.pitch + (ipx - 1);
+            const uintptr_t addr = reinterpret_cast<uintptr_t>(rowp);
+            const uint32_t *base = reinterpret_cast<const uint32_t *>(addr & ~(uintptr_t)3);
+            const int sh = (int)(addr & 3) * 8;
+            uint32_t wv[10];
+#pragma unroll
+            for (int k = 0; k < 10; k++) wv[k] = base[k];
+            uint32_t *dst = reinterpret_cast<uint32_t *>(&sm.tile[r * T]);
+#pragma unroll
+            for (int k = 0; k < 9; k++) dst[k] = __funnelshift_r(wv[k], wv[k + 1], sh);
+        }
+        __syncwarp();
+        for (int y = 0; y < W1; y++) {   // lane = column
+            const int X = ipx + lane, Y = ipy + y;
+            int gxv = 0, gyv = 0;
+            if (X >= 0 && X < I.w && Y >= 0 && Y < I.h) {
+                const uint8_t *t = &sm.tile[(y + 1) * T + (lane + 1)];
+                int tl = t[-T - 1], tc = t[-T], trr = t[-T + 1], ml = t[-1], mr = t[1], bl = t[T - 1], bc = t[T], br = t[T + 1];
+                gxv = 3 * (trr + br) + 10 * mr - (3 * (tl + bl) + 10 * ml);
+                gyv = 3 * ((bl - tl) + (br - trr)) + 10 * (bc - tc);
+            }
+            sm.gx[y * W1 + lane] = (short)gxv; sm.gy[y * W1 + lane] = (short)gyv;
+        }
+        __syncwarp();
+        // ---- template of this lane's row in registers
+        int Iw[31], Ix[31], Iy[31];
+        int acc11 = 0, acc12 = 0, acc22 = 0;
+        {
+            const int row = have_row ? lane : 0;
+            const uint8_t *t0 = &sm.tile[(row + 1) * T + 1];
+            const short *g0 = &sm.gx[row * W1], *h0 = &sm.gy[row * W1];
+            int pa = t0[0], pb = t0[T], pgx0 = g0[0], pgx1 = g0[W1], pgy0 = h0[0], pgy1 = h0[W1];
+#pragma unroll
+            for (int x = 0; x < 31; x++) {
+                const int na = t0[x + 1], nb = t0[T + x + 1];
+                const int ngx0 = g0[x + 1], ngx1 = g0[W1 + x + 1], ngy0 = h0[x + 1], ngy1 = h0[W1 + x + 1];
+                int ival = pa * iw00 + na * iw01 + pb * iw10 + nb * iw11;
+                int ixv = pgx0 * iw00 + ngx0 * iw01 + pgx1 * iw10 + ngx1 * iw11;
+                int iyv = pgy0 * iw00 + ngy0 * iw01 + pgy1 * iw10 + ngy1 * iw11;
+                ival = (ival + (1 << 8)) >> 9;
+                ixv = (ixv + (1 << 13)) >> 14;
+                iyv = (iyv + (1 << 13)) >> 14;
+                if (!have_row) { ival = 0; ixv = 0; iyv = 0; }
+                Iw[x] = ival; Ix[x] = ixv; Iy[x] = iyv;
+                acc11 += ixv * ixv; acc12 += ixv * iyv; acc22 += iyv * iyv;   // <= 31 * 4080^2 < 2^31
+                pa = na; pb = nb; pgx0 = ngx0; pgx1 = ngx1; pgy0 = ngy0; pgy1 = ngy1;
+            }
+        }
+        const long long s11 = warp_sum_i32_exact(acc11), s12 = warp_sum_i32_exact(acc12), s22 = warp_sum_i32_exact(acc22);
+        const float FLT_SCALE = 1.f / (1 << 20);
+        float A11 = (float)s11 * FLT_SCALE, A12 = (float)s12 * FLT_SCALE, A22 = (float)s22 * FLT_SCALE;
+        float D = A11 * A22 - A12 * A12;
+        float minEig = (A22 + A11 - sqrtf((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) / (float)(2 * win * win);
+        if ((double)minEig < 1e-4 || D < 1.1920929e-07f) {
+            if (level == 0) status = 0;
+            continue;
+        }
+        D = 1.f / D;
+        qx -= half; qy -= half;
+        float pdx = 0.f, pdy = 0.f;
+        // one evaluation pass over the window at integer origin (ox, oy) with weights w*: MODE 0 -> b1/b2, MODE 1 -> sum |diff|
+        auto window_pass = [&](int ox, int oy, int w00, int w01, int w10, int w11, int &o1, int &o2, bool want_err) {
+            const uint8_t *rowp = J.ptr + (ptrdiff_t)(oy + lane) * J.pitch + ox;
+            const uintptr_t addr = reinterpret_cast<uintptr_t>(rowp);
+            const uint32_t *base = reinterpret_cast<const uint32_t *>(addr & ~(uintptr_t)3);
+            const int sh = (int)(addr & 3) * 8;
+            uint32_t wv[9];
+#pragma unroll
+            for (int k = 0; k < 9; k++) wv[k] = base[k];
+            uint32_t top[9], bot[9];
+#pragma unroll
+            for (int k = 0; k < 8; k++) top[k] = __funnelshift_r(wv[k], wv[k + 1], sh);
+            top[8] = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) bot[k] = __shfl_down_sync(0xffffffffu, top[k], 1);
+            bot[8] = 0;
+            const uint32_t Wt = (uint32_t)w00 | ((uint32_t)w01 << 16), Wb = (uint32_t)w10 | ((uint32_t)w11 << 16);
+            int acc1 = 0, acc2 = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const uint32_t ts = __funnelshift_r(top[k], top[k + 1], 8), bs = __funnelshift_r(bot[k], bot[k + 1], 8);
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int x = 4 * k + q;
+                    if (x < 31) {
+                        unsigned v;
+                        if (q == 0) v = __dp2a_lo(Wt, top[k], __dp2a_lo(Wb, bot[k], 0u));
+                        else if (q == 1) v = __dp2a_lo(Wt, ts, __dp2a_lo(Wb, bs, 0u));
+                        else if (q == 2) v = __dp2a_hi(Wt, top[k], __dp2a_hi(Wb, bot[k], 0u));
+                        else v = __dp2a_hi(Wt, ts, __dp2a_hi(Wb, bs, 0u));
+                        const int diff = (int)((v + (1u << 8)) >> 9) - Iw[x];
+                        if (want_err) acc1 += abs(diff);
+                        else { acc1 += diff * Ix[x]; acc2 += diff * Iy[x]; }   // <= 31 * 8160 * 4080 < 2^31
+                    }
+                }
+            }
+            if (!have_row) { acc1 = 0; acc2 = 0; }
+            o1 = acc1; o2 = acc2;
+        };
+        for (int j = 0; j < 30; j++) {
+            const int iqx = (int)floorf(qx), iqy = (int)floorf(qy);
+            if (iqx < -win || iqx >= J.w || iqy < -win || iqy >= J.h) {
+                if (level == 0) status = 0;
+                break;
+            }
+            lk_weights(qx - (float)iqx, qy - (float)iqy, iw00, iw01, iw10, iw11);
+            total_iters++;
+            int p1, p2;
+            window_pass(iqx, iqy, iw00, iw01, iw10, iw11, p1, p2, false);
+            const long long b1 = warp_sum_i32_exact(p1), b2 = warp_sum_i32_exact(p2);
+            float fb1 = (float)b1 * FLT_SCALE, fb2 = (float)b2 * FLT_SCALE;
+            float dx = (float)((A12 * fb2 - A22 * fb1) * D);
+            float dy = (float)((A12 * fb1 - A11 * fb2) * D);
+            qx += dx; qy += dy;
+            nx = qx + half; ny = qy + half;
+            if ((double)dx * (double)dx + (double)dy * (double)dy <= 0.01 * 0.01) break;
+            if (j > 0 && fabs((double)(dx + pdx)) < 0.01 && fabs((double)(dy + pdy)) < 0.01) {
+                nx -= dx * 0.5f; ny -= dy * 0.5f;
+                break;
+            }
+            pdx = dx; pdy = dy;
+        }
+        if (status && level == 0) {
+            float ex = nx - half, ey = ny - half;
+            const int iex = (int)floorf(ex), iey = (int)floorf(ey);
+            if (iex < -win || iex >= J.w || iey < -win || iey >= J.h) { status = 0; continue; }
+            lk_weights(ex - (float)iex, ey - (float)iey, iw00, iw01, iw10, iw11);
+            int e1, e2;
+            window_pass(iex, iey, iw00, iw01, iw10, iw11, e1, e2, true);
+            const long long e = warp_sum_i32_exact(e1);
+            err = (float)e * 1.f / (float)(32 * win * win);
+        }
+    }
+
+    if (lane == 0) {
+        if (status == 0) err = __int_as_float(0x7f800000);  // optical_flow.cpp:46-50
+        a.next_pts[2 * i] = nx; a.next_pts[2 * i + 1] = ny;
+        a.status[i] = (uint8_t)status;
+        a.err[i] = err;
+        if (a.iters) a.iters[i] = total_iters;
+        if (a.flags) {  // pose_refinement.cpp:125-150
+            uint8_t f = a.flags[i];
+            float ox = init_x, oy = init_y;
+            float d = (init_x - nx) * (init_x - nx) + (init_y - ny) * (init_y - ny);
+            if (err > 20) f |= SVO_F_IGN_COMPLETE;
+            else if (d > 81) f |= SVO_F_IGN_REFINE;
+            else { f &= (uint8_t)~SVO_F_IGN_REFINE; ox = nx; oy = ny; }
+            a.flags[i] = f;
+            a.kps2d_out[2 * i] = ox; a.kps2d_out[2 * i + 1] = oy;
+        }
+    }
+}
+
+static int g_klt_variant = -1;  // SVO_KLT_VARIANT=block selects the CTA-per-keypoint kernel (A/B measurements)
+
 void launch_klt(const KltArgs &a, cudaStream_t st)
 {
     if (a.max_kps <= 0) return;
-    if (a.cam.win_flow == 31) klt31_kernel<<<a.max_kps, KLT_THREADS, 0, st>>>(a);
+    if (g_klt_variant < 0) {
+        const char *e = getenv("SVO_KLT_VARIANT");
+        g_klt_variant = (e && e[0] == 'b') ? 1 : 0;
+    }
+    if (a.cam.win_flow == 31 && g_klt_variant == 0) klt31w_kernel<<<(a.max_kps + KLTW_WARPS - 1) / KLTW_WARPS, 32 * KLTW_WARPS, 0, st>>>(a);
+    else if (a.cam.win_flow == 31) klt31_kernel<<<a.max_kps, KLT_THREADS, 0, st>>>(a);
     else klt_pyr_lk_kernel<0><<<a.max_kps, KLT_THREADS, 0, st>>>(a);
 }
