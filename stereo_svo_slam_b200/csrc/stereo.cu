@@ -185,20 +185,41 @@ __global__ void __launch_bounds__(SSDC_THREADS) stereo_ssd_col_kernel(SsdArgs a,
     const uint32_t last_mask = (tw & 3) ? ((1u << ((tw & 3) * 8)) - 1u) : 0xffffffffu;
     const int twords = (tw + 3) >> 2;
 
-    uint8_t *tpl8 = reinterpret_cast<uint8_t *>(tpl), *roi8 = reinterpret_cast<uint8_t *>(roi);
-    for (int k = tid; k < 32 * 8; k += SSDC_THREADS) tpl[k] = 0;
-    for (int k = tid; k < roi_rows * rpw; k += SSDC_THREADS) roi[k] = 0;
-    __syncthreads();
+    // ---- stage template and ROI row-wise: every thread fetches whole rows as independent aligned word loads and
+    //      realigns them with funnel shifts (bytes past the window are masked where they are consumed)
     unsigned saa = 0;
-    for (int k = tid; k < th * tw; k += SSDC_THREADS) {
-        int r = k / tw, c = k - r * tw;
-        unsigned v = L.ptr[(size_t)(g.y11 + r) * L.pitch + g.x11 + c];
-        tpl8[r * 32 + c] = (uint8_t)v;
-        saa += v * v;
+    if (tid < th) {
+        const uint8_t *rowp = L.ptr + (size_t)(g.y11 + tid) * L.pitch + g.x11;
+        const uintptr_t addr = reinterpret_cast<uintptr_t>(rowp);
+        const uint32_t *base = reinterpret_cast<const uint32_t *>(addr & ~(uintptr_t)3);
+        const int sh = (int)(addr & 3) * 8;
+        uint32_t wv[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) wv[k] = base[k];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            uint32_t v = __funnelshift_r(wv[k], wv[k + 1], sh);
+            if (k == twords - 1) v &= last_mask;
+            if (k >= twords) v = 0;
+            tpl[tid * 8 + k] = v;
+            saa = __dp4a(v, v, saa);
+        }
     }
-    for (int k = tid; k < rh * rw; k += SSDC_THREADS) {
-        int r = k / rw, c = k - r * rw;
-        roi8[r * rpw * 4 + c] = R.ptr[(size_t)(g.y21 + r) * R.pitch + g.x21 + c];
+    const int rwords = min(rpw - 1, ((rw + 3) >> 2) + 1);   // words of a ROI row that any search position can touch
+    for (int r = tid; r < rh; r += SSDC_THREADS) {
+        const uint8_t *rowp = R.ptr + (size_t)(g.y21 + r) * R.pitch + g.x21;
+        const uintptr_t addr = reinterpret_cast<uintptr_t>(rowp);
+        const uint32_t *base = reinterpret_cast<const uint32_t *>(addr & ~(uintptr_t)3);
+        const int sh = (int)(addr & 3) * 8;
+        uint32_t w0 = base[0];
+        for (int k = 0; k < rwords; k += 4) {   // 4 independent loads per trip
+            uint32_t w1 = base[k + 1], w2 = base[k + 2], w3 = base[k + 3], w4 = base[k + 4];
+            roi[r * rpw + k] = __funnelshift_r(w0, w1, sh);
+            if (k + 1 < rpw) roi[r * rpw + k + 1] = __funnelshift_r(w1, w2, sh);
+            if (k + 2 < rpw) roi[r * rpw + k + 2] = __funnelshift_r(w2, w3, sh);
+            if (k + 3 < rpw) roi[r * rpw + k + 3] = __funnelshift_r(w3, w4, sh);
+            w0 = w4;
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) saa += __shfl_down_sync(0xffffffffu, saa, o);
