@@ -376,6 +376,13 @@ def main():
         patches = cm[1] * (cm[2] + cm[3])          # (keypoint, level, evaluation) 4x4 patches per frame
         windows = cm[6]                            # (keypoint, level, LK iteration) 31x31 windows per frame
         peak, peak_src = peaks()
+        # DRAM traffic per launch of each kernel, from the committed `ncu --set full` capture (profiles/r01_traffic.json)
+        traffic_tbl = {}
+        try:
+            traffic_tbl = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        except Exception:  # noqa: BLE001
+            pass
+        stage_kernel = {1: "sparse_align_kernel<1>", 2: "klt31w_kernel", 3: "reproj_refine_kernel", 4: "stereo_ssd_col_kernel", 5: "depth_filter_kernel"}
         med_wall = float(np.median(walls[W:]))
         dom = int(np.argmax(st[1:6])) + 1
         ab = algorithmic_bytes(c, n_kps, evals_per_level=1)
@@ -402,7 +409,10 @@ def main():
                                  "mwindows_per_s": float(windows / (st[2] * 1e-3) / 1e6) if st[2] > 0 else None,
                                  "note": "one sequence, synchronous new_image calls with host buffers (what the reference app does)"},
                "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                            "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                            "frac": achieved / peak,
+                            "traffic": traffic_tbl.get(stage_kernel.get(dom, ""), {}).get("dram_bytes_per_launch"),
+                            "traffic_source": "profiles/r01_traffic.json (ncu --set full, dram__bytes_read+write per launch)",
+                            "algorithmic_bytes_per_launch": int(dom_bytes), "peak_source": peak_src,
                             "limiter": "dependency latency / integer+fp32 ALU, not HBM: the per-frame working set (<3 MB) is L2-resident "
                                        "(SURVEY.md §8d); see profiles/ for the ncu evidence"},
                "kernels": kernels}
