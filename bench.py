@@ -33,6 +33,8 @@ sys.path.insert(0, ROOT)
 # one hardware work queue per sequence: with the default of 8, sequences that share a queue serialise behind each
 # other's long solver kernels (must be set before the CUDA context exists)
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the one JSON line (NCCL prints its version banner there)
 
 from stereo_svo_slam_b200 import synth  # noqa: E402
 
@@ -339,8 +341,11 @@ def main():
         for sl in slams:
             sl.close()
         t = torch.tensor([max(wall, dev_s)], device="cuda", dtype=torch.float64)
+        ln = torch.tensor([nl], device="cuda", dtype=torch.int64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(ln, op=dist.ReduceOp.SUM)
+        nl = int(ln.item())
         return dict(seconds=float(t.item()), launches=nl, kps=kps, keyframes=nkf, poses=poses, clocks=ck)
 
     r_dev = run("device", ClockSampler(local_rank))
