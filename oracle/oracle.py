@@ -152,6 +152,22 @@ def expmap(tw):
     return out
 
 
+def rectify_map(K, D, R, P, w, h):
+    a = [np.ascontiguousarray(x, dtype=np.float64).reshape(-1) for x in (K, D, R, np.asarray(P, np.float64)[:3, :3])]
+    m1, m2 = np.empty((h, w), np.float32), np.empty((h, w), np.float32)
+    lib().orc_rectify_map(_p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), w, h, _p(m1), _p(m2))
+    return m1, m2
+
+
+def remap(src, m1, m2):
+    src = _u8(src)
+    m1, m2 = _f32(m1), _f32(m2)
+    h, w = m1.shape
+    dst = np.empty((h, w), np.uint8)
+    lib().orc_remap(_p(src), src.shape[1], src.shape[0], _p(m1), _p(m2), w, h, _p(dst))
+    return dst
+
+
 class Kalman:
     NAMES = {"A": 0, "H": 1, "Q": 2, "R": 3, "Ppre": 4, "Ppost": 5, "xpre": 6, "xpost": 7, "K": 8}
 

@@ -1019,6 +1019,15 @@ int orc_invert_svd(const float *A, int n, float *Ainv) { return invert_svd_f(A, 
 void orc_solve_svd(const float *A, int m, int n, const float *B, int nb, float *X) { solve_svd_f(A, m, n, B, nb, X); }
 void orc_expmap(const float *tw, float *out) { exponential_map(tw, out); }
 
+void orc_rectify_map(const double *K, const double *D, const double *R, const double *P, int w, int h, float *m1, float *m2)
+{
+    init_undistort_rectify_map(K, D, R, P, w, h, m1, m2);
+}
+void orc_remap(const uint8_t *src, int sw, int sh, const float *m1, const float *m2, int w, int h, uint8_t *dst)
+{
+    remap_linear_u8(src, sw, sh, sw, m1, m2, w, h, dst, w);
+}
+
 // generic Kalman for pinning against cv2.KalmanFilter
 void *orc_kf_create(int n, int m) { Kalman *k = new Kalman(); k->init(n, m); return k; }
 void orc_kf_destroy(void *h) { delete (Kalman *)h; }

@@ -147,6 +147,26 @@ def main():
         k1.correct(z)
         seq.append([Rn, z[0, 0], k1.statePost[0, 0], k1.errorCovPost[0, 0]])
     out["kf1_seq"] = np.array(seq, np.float32)
+    # --- EuRoC rectification front end (src/app/euroc_input.cpp:48-49, :69-73), calibration of src/app/EuRoC.yaml
+    cal = {
+        "LEFT": dict(K=[458.654, 0.0, 367.215, 0.0, 457.296, 248.375, 0.0, 0.0, 1.0], D=[-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05, 0.0],
+                     R=[0.999966347530033, -0.001422739138722922, 0.008079580483432283, 0.001365741834644127, 0.9999741760894847,
+                        0.007055629199258132, -0.008089410156878961, -0.007044357138835809, 0.9999424675829176],
+                     P=[435.2046959714599, 0, 367.4517211914062, 0, 0, 435.2046959714599, 252.2008514404297, 0, 0, 0, 1, 0]),
+        "RIGHT": dict(K=[457.587, 0.0, 379.999, 0.0, 456.134, 255.238, 0.0, 0.0, 1], D=[-0.28368365, 0.07451284, -0.00010473, -3.555907e-05, 0.0],
+                      R=[0.9999633526194376, -0.003625811871560086, 0.007755443660172947, 0.003680398547259526, 0.9999684752771629,
+                         -0.007035845251224894, -0.007729688520722713, 0.007064130529506649, 0.999945173484644],
+                      P=[435.2046959714599, 0, 367.4517211914062, -47.90639384423901, 0, 435.2046959714599, 252.2008514404297, 0, 0, 0, 1, 0]),
+    }
+    for side, img in (("LEFT", L), ("RIGHT", R)):
+        c = cal[side]
+        K_, D_, R_, P_ = np.array(c["K"]).reshape(3, 3), np.array(c["D"]), np.array(c["R"]).reshape(3, 3), np.array(c["P"]).reshape(3, 4)
+        m1, m2 = cv2.initUndistortRectifyMap(K_, D_, R_, P_[:3, :3], (752, 480), cv2.CV_32F)
+        rect = cv2.remap(img, m1, m2, cv2.INTER_LINEAR)
+        out[f"rect_{side}_params"] = np.concatenate([K_.ravel(), D_.ravel(), R_.ravel(), P_[:3, :3].ravel()])
+        out[f"rect_{side}_map_sha"] = sha(np.stack([m1, m2]))
+        out[f"rect_{side}_img_sha"] = sha(rect)
+        out[f"rect_{side}_rows"] = rect[236:240].copy()
     out["cv2_version"] = np.frombuffer(cv2.__version__.encode(), np.uint8)
     np.savez_compressed(os.path.join(HERE, "cv2_vectors.npz"), **out)
     print("wrote golden fixtures:", {k: v.shape for k, v in out.items()})

@@ -146,3 +146,15 @@ def test_half_sample_truncates():
     a = img[:480, :752].astype(np.int32)
     want = (a[0::2, 0::2] + a[0::2, 1::2] + a[1::2, 0::2] + a[1::2, 1::2]) // 4
     assert out.shape == (240, 376) and (out == want).all()
+
+
+def test_rectification_bit_exact(fixture_images, cv2_vectors):
+    # cv::initUndistortRectifyMap + cv::remap(INTER_LINEAR) with the EuRoC.yaml calibration (euroc_input.cpp:48-49, :69-73)
+    for side, name in (("LEFT", "left"), ("RIGHT", "right")):
+        p = cv2_vectors[f"rect_{side}_params"]
+        K, D, R, P = p[:9].reshape(3, 3), p[9:14], p[14:23].reshape(3, 3), p[23:32].reshape(3, 3)
+        m1, m2 = orc.rectify_map(K, D, R, P, 752, 480)
+        assert (sha(np.stack([m1, m2])) == cv2_vectors[f"rect_{side}_map_sha"]).all()
+        rect = orc.remap(fixture_images[name], m1, m2)
+        assert (sha(rect) == cv2_vectors[f"rect_{side}_img_sha"]).all()
+        assert (rect[236:240] == cv2_vectors[f"rect_{side}_rows"]).all()
