@@ -74,6 +74,17 @@ int svo_upload_stereo(svo_ctx *ctx, const uint8_t *left, size_t left_stride, con
  * that lands frames in HBM): device-to-device copy, then the same pyramid build. */
 int svo_upload_stereo_device(svo_ctx *ctx, const uint8_t *d_left, size_t left_stride, const uint8_t *d_right,
                              size_t right_stride, int *slot_out);
+/* EuRoC front end (src/app/euroc_input.cpp:48-49, :69-73): cv::initUndistortRectifyMap(K, D, R, P[:3,:3], size, CV_32F)
+ * is evaluated once on the device; from then on every uploaded image `which` (0 = the `left` argument, 1 = `right`)
+ * is a raw camera image and goes through cv::remap(INTER_LINEAR, BORDER_CONSTANT 0) fused in front of the pyramid
+ * build (bit-exact with OpenCV's fixed-point remap).  K, R, P: row-major 3x3 (P = first three columns of the
+ * 3x4 projection), D = (k1, k2, p1, p2, k3).  Source and rectified size are the context's width x height.
+ * Note the reference feeds cam0 rectified with LEFT.* as `right` and cam1 with RIGHT.* as `left` (:69-70, :100-101). */
+int svo_set_rectification(svo_ctx *ctx, int which, const double K[9], const double D[5], const double R[9],
+                          const double P[9]);
+int svo_clear_rectification(svo_ctx *ctx);
+/* the float maps of input `which` (width*height each) — parity with cv::initUndistortRectifyMap */
+int svo_rectification_maps(svo_ctx *ctx, int which, float *map1, float *map2);
 int svo_slot_retain(svo_ctx *ctx, int slot);
 int svo_slot_release(svo_ctx *ctx, int slot);
 /* kind: 0 = left halfSample pyramid level, 1 = right level 0, 2 = LK pyramid level (unpadded view) */
@@ -222,6 +233,10 @@ int svo_slam_new_image_end(svo_slam *s);
 /* same as _begin with the stereo pair already resident in device memory (svo_upload_stereo_device) */
 int svo_slam_new_image_device_begin(svo_slam *s, const uint8_t *d_left, size_t left_stride, const uint8_t *d_right,
                                     size_t right_stride, float time_stamp);
+/* EurocInput's rectification (euroc_input.cpp:48-49, :69-73) applied on the device to every image passed as
+ * `left` (which = 0) / `right` (which = 1) from now on; see svo_set_rectification */
+int svo_slam_set_rectification(svo_slam *s, int which, const double K[9], const double D[5], const double R[9],
+                               const double P[9]);
 /* StereoSlam::get_frame (stereo_slam.cpp:278-284): returns SVO_ERR_STATE before the first image */
 int svo_slam_get_frame(svo_slam *s, uint64_t *id, svo_pose *pose, double *time_stamp, int *n_keypoints);
 int svo_slam_get_frame_keypoints(svo_slam *s, int max, float *kps2d, float *kps3d, svo_keypoint_info *info);

@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libstereosvo_b200.so")
-SOURCES = ["pyramid.cu", "align.cu", "klt.cu", "refine.cu", "stereo.cu", "detect.cu", "context.cu", "slam_host.cpp"]
+SOURCES = ["rectify.cu", "pyramid.cu", "align.cu", "klt.cu", "refine.cu", "stereo.cu", "detect.cu", "context.cu", "slam_host.cpp"]
 HEADERS = ["common.cuh", "kernels.cuh", os.path.join("..", "..", "include", "svo_cuda.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               # the reference's float arithmetic is un-fused scalar C++; keep per-keypoint values bit-comparable

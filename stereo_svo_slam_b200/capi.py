@@ -139,6 +139,20 @@ class Context:
                                          C.c_size_t(right.strides[0]), C.byref(slot)))
         return slot.value
 
+    def set_rectification(self, which, K, D, R, P):
+        """EuRoC front end (euroc_input.cpp:48-49): rectify every image uploaded as left (which=0) / right (which=1)."""
+        a = [np.ascontiguousarray(np.asarray(x, np.float64).reshape(-1)) for x in (K, D, R, np.asarray(P, np.float64).reshape(3, -1)[:, :3])]
+        assert a[0].size == 9 and a[1].size == 5 and a[2].size == 9 and a[3].size == 9
+        self._ck(lib().svo_set_rectification(self.h_ctx, which, _p(a[0]), _p(a[1]), _p(a[2]), _p(a[3])))
+
+    def clear_rectification(self):
+        self._ck(lib().svo_clear_rectification(self.h_ctx))
+
+    def rectification_maps(self, which):
+        m1, m2 = np.empty((self.h, self.w), np.float32), np.empty((self.h, self.w), np.float32)
+        self._ck(lib().svo_rectification_maps(self.h_ctx, which, _p(m1), _p(m2)))
+        return m1, m2
+
     def release(self, slot):
         self._ck(lib().svo_slot_release(self.h_ctx, slot))
 

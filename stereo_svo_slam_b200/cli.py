@@ -2,6 +2,7 @@
 
     python -m stereo_svo_slam_b200.cli --settings Blender.yaml --video blender-classroom.mkv --trajectory out.csv
     python -m stereo_svo_slam_b200.cli --settings EuRoC.yaml --pairs /data/mav0 --trajectory out.csv
+    python -m stereo_svo_slam_b200.cli --settings EuRoC.yaml --euroc /data/MH_02_easy/mav0/ --trajectory out.csv
     python -m stereo_svo_slam_b200.cli --synthetic C3 --frames 100 --trajectory out.csv
 
 * settings: the reference's OpenCV-YAML keys (src/app/image_input.cpp:13-37; examples src/app/Blender.yaml, EuRoC.yaml, Econ.yaml)
@@ -9,6 +10,9 @@
   (src/app/video_input.cpp:23-42); decoding needs cv2
 * --pairs: a directory with left/ and right/ (or EuRoC's cam0/data and cam1/data) holding equally named images; images are
   used as they are (already rectified)
+* --euroc: the reference's EurocInput (src/app/euroc_input.cpp): file list and timestamps from cam0/data.csv, cam0 -> `right`,
+  cam1 -> `left`, raw images rectified ON THE DEVICE with the LEFT.* / RIGHT.* matrices of the settings file
+  (initUndistortRectifyMap + remap, fused in front of the pyramid kernels)
 * trajectory CSV: `time,x,y,z,rx,ry,rz`, column 0 = cumulative seconds spent inside new_image, angles re-ordered for
   Blender exactly as src/app/slam_app.cpp:220-246 does (Rodrigues((Ry*Rx)*Rz))
 """
@@ -45,6 +49,32 @@ def read_settings(path):
     for name, _ in CameraSettings._fields_:
         v = vals.get(name, 0.0)
         out[name] = int(v) if name in _INT_FIELDS else float(v)
+    return out
+
+
+def read_rectification(path):
+    """LEFT.* / RIGHT.* `!!opencv-matrix` nodes of the settings file (src/app/euroc_input.cpp:24-46).
+    Returns {"LEFT": dict(K, D, R, P, width, height), "RIGHT": ...}; raises if a node is missing (the reference only
+    prints an error and then fails inside OpenCV)."""
+    text = open(path).read()
+    out = {}
+    for side in ("LEFT", "RIGHT"):
+        ent = {}
+        for key, n in (("K", 9), ("D", 5), ("R", 9), ("P", 12)):
+            m = re.search(rf"^{side}\.{key}\s*:\s*!!opencv-matrix(.*?)data\s*:\s*\[(.*?)\]", text, re.S | re.M)
+            if not m:
+                raise ValueError(f"{path}: calibration parameter {side}.{key} is missing")
+            vals = [float(v) for v in m.group(2).replace("\n", " ").split(",") if v.strip()]
+            if len(vals) < n:
+                raise ValueError(f"{path}: {side}.{key} has {len(vals)} values, expected {n}")
+            ent[key] = np.array(vals[:n], np.float64)
+        for key in ("width", "height"):
+            m = re.search(rf"^{side}\.{key}\s*:\s*([0-9]+)", text, re.M)
+            if not m:
+                raise ValueError(f"{path}: {side}.{key} is missing")
+            ent[key] = int(m.group(1))
+        ent["K"], ent["R"], ent["P"] = ent["K"].reshape(3, 3), ent["R"].reshape(3, 3), ent["P"].reshape(3, 4)
+        out[side] = ent
     return out
 
 
@@ -110,6 +140,23 @@ def iter_pairs(root):
         yield _imread_gray(os.path.join(dl, nm)), _imread_gray(os.path.join(dr, nm)), ts
 
 
+def iter_euroc(root):
+    """EurocInput::load_images / read (euroc_input.cpp:60-78, :87-116): cam0 is fed as `right`, cam1 as `left`; time stamps
+    are seconds since the first row of cam0/data.csv, as float.  Images are RAW: rectification happens on the device."""
+    rows = []
+    with open(os.path.join(root, "cam0", "data.csv")) as f:
+        for s in f:
+            s = s.strip().replace("\r", "")
+            if not s or s[0] == "#":
+                continue
+            rows.append((float(s.split(",")[0]) / 1.0e9, s.rsplit(",", 1)[-1]))
+    t0 = rows[0][0] if rows else 0.0
+    for t, name in rows:
+        right = _imread_gray(os.path.join(root, "cam0", "data", name))
+        left = _imread_gray(os.path.join(root, "cam1", "data", name))
+        yield left, right, float(np.float32(t - t0))
+
+
 def iter_video(path):
     import cv2
     cap = cv2.VideoCapture(path)
@@ -136,13 +183,18 @@ def iter_synthetic(cfg, frames):
         yield left, right, k / 20.0
 
 
-def run(frames, settings, device=0, trajectory=None, verbose=False):
+def run(frames, settings, device=0, trajectory=None, verbose=False, rectification=None):
     from .slam import StereoSlam
     slam, t_algo, stamps = None, 0.0, []
     for left, right, ts in frames:
         if slam is None:
             slam = StereoSlam(settings if isinstance(settings, CameraSettings) else CameraSettings(**settings), left.shape[1], left.shape[0],
                               device=device)
+            if rectification:
+                # euroc_input.cpp:69-70: the cam0 image (`right`) goes through the LEFT.* maps, cam1 (`left`) through RIGHT.*
+                for which, side in ((0, "RIGHT"), (1, "LEFT")):
+                    c = rectification[side]
+                    slam.set_rectification(which, c["K"], c["D"], c["R"], c["P"])
         t0 = time.perf_counter()
         slam.new_image(left, right, ts)
         t_algo += time.perf_counter() - t0           # the reference's TickMeter brackets exactly new_image (slam_app.cpp:187-190)
@@ -161,6 +213,7 @@ def main(argv=None):
     src = ap.add_mutually_exclusive_group(required=True)
     src.add_argument("--video", "-v")
     src.add_argument("--pairs")
+    src.add_argument("--euroc", help="EuRoC mav0/ directory with raw cam0/ and cam1/ (rectified on the device)")
     src.add_argument("--synthetic", choices=sorted(synth.CONFIGS))
     ap.add_argument("--frames", type=int, default=50, help="frames of the synthetic sequence")
     ap.add_argument("--trajectory", "-t", help="trajectory CSV to write")
@@ -172,10 +225,11 @@ def main(argv=None):
         frames = iter_synthetic(a.synthetic, a.frames)
     else:
         if not a.settings:
-            ap.error("--settings is required with --video / --pairs")
+            ap.error("--settings is required with --video / --pairs / --euroc")
         settings = read_settings(a.settings)
-        frames = iter_video(a.video) if a.video else iter_pairs(a.pairs)
-    traj, stamps, _ = run(frames, settings, a.device, a.trajectory, a.verbose)
+        frames = iter_video(a.video) if a.video else iter_euroc(a.euroc) if a.euroc else iter_pairs(a.pairs)
+    rect = read_rectification(a.settings) if a.euroc else None
+    traj, stamps, _ = run(frames, settings, a.device, a.trajectory, a.verbose, rect)
     if stamps:
         print(f"{len(stamps)} frames, {len(stamps) / stamps[-1]:.1f} frames/s (algorithm time, test/extract_fps.py definition)")
     return 0

@@ -72,6 +72,10 @@ struct svo_ctx {
     unsigned long long graph_clock = 0;
     long long graph_launches = 0, graph_captures = 0;
     float stage_ms[8] = {0};
+    // EuRoC rectification in front of the pyramid build (euroc_input.cpp:48-49, :69-73); [0] = left, [1] = right input
+    float *d_rect_map[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    uint32_t *d_rect_packed[2] = {nullptr, nullptr};
+    uint8_t *d_raw[2] = {nullptr, nullptr};   // raw (distorted) images of the frame being uploaded
     char err[256];
 };
 
@@ -230,6 +234,12 @@ extern "C" int svo_ctx_destroy(svo_ctx *ctx)
     if (ctx->d_cell_type) cudaFree(ctx->d_cell_type);
     if (ctx->d_kf_lk) cudaFree(ctx->d_kf_lk);
     if (ctx->d_kf_pose) cudaFree(ctx->d_kf_pose);
+    for (int k = 0; k < 2; k++) {
+        if (ctx->d_rect_map[k][0]) cudaFree(ctx->d_rect_map[k][0]);
+        if (ctx->d_rect_map[k][1]) cudaFree(ctx->d_rect_map[k][1]);
+        if (ctx->d_rect_packed[k]) cudaFree(ctx->d_rect_packed[k]);
+        if (ctx->d_raw[k]) cudaFree(ctx->d_raw[k]);
+    }
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     for (int k = 0; k < 9; k++) if (ctx->sev[k]) cudaEventDestroy(ctx->sev[k]);
@@ -306,25 +316,37 @@ static uint8_t *stage_images(svo_ctx *ctx, const uint8_t *left, size_t ls, const
 
 // stream part of an upload: copies + pyramid kernels (stereo_slam.cpp:135-139).  For src_kind 0 `left`/`right`
 // are the two halves of the staging buffer.
+static int enqueue_pyramids(svo_ctx *ctx, Slot &s);
 static int enqueue_upload(svo_ctx *ctx, Slot &s, const uint8_t *left, size_t ls, const uint8_t *right, size_t rs, int src_kind,
                           bool copies_only = false)
 {
     const size_t img = (size_t)ctx->W * ctx->H;
     const cudaMemcpyKind kind = src_kind == 2 ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    // a rectified input lands in the context's raw buffer; the remap kernel in front of the pyramids writes level 0
+    uint8_t *dl = ctx->d_rect_packed[0] ? ctx->d_raw[0] : s.dev.left[0].ptr;
+    uint8_t *dr = ctx->d_rect_packed[1] ? ctx->d_raw[1] : s.dev.right0.ptr;
     // contiguous rows: one linear DMA (a 2-D copy of 752-byte rows costs one descriptor per row)
-    if (ls == (size_t)ctx->W) CK(cudaMemcpyAsync(s.dev.left[0].ptr, left, img, kind, ctx->stream));
-    else CK(cudaMemcpy2DAsync(s.dev.left[0].ptr, ctx->W, left, ls, ctx->W, ctx->H, kind, ctx->stream));
-    if (rs == (size_t)ctx->W) CK(cudaMemcpyAsync(s.dev.right0.ptr, right, img, kind, ctx->stream));
-    else CK(cudaMemcpy2DAsync(s.dev.right0.ptr, ctx->W, right, rs, ctx->W, ctx->H, kind, ctx->stream));
+    if (ls == (size_t)ctx->W) CK(cudaMemcpyAsync(dl, left, img, kind, ctx->stream));
+    else CK(cudaMemcpy2DAsync(dl, ctx->W, left, ls, ctx->W, ctx->H, kind, ctx->stream));
+    if (rs == (size_t)ctx->W) CK(cudaMemcpyAsync(dr, right, img, kind, ctx->stream));
+    else CK(cudaMemcpy2DAsync(dr, ctx->W, right, rs, ctx->W, ctx->H, kind, ctx->stream));
     if (copies_only) return SVO_OK;
-    launch_pyr_halfsample(s.dev, ctx->stream);
-    launch_lk_pyramid(s.dev, ctx->stream);
-    CK(cudaGetLastError());
-    return SVO_OK;
+    return enqueue_pyramids(ctx, s);
 }
+
+static bool rectifying(const svo_ctx *ctx) { return ctx->d_rect_packed[0] || ctx->d_rect_packed[1]; }
+static int frame_pyr_launches(const svo_ctx *ctx, const Slot &s) { return pyr_launch_count(s.dev) + (rectifying(ctx) ? 1 : 0); }
 
 static int enqueue_pyramids(svo_ctx *ctx, Slot &s)
 {
+    if (rectifying(ctx)) {
+        RemapArgs ra;
+        ra.src[0] = ctx->d_raw[0]; ra.src[1] = ctx->d_raw[1];
+        ra.map[0] = ctx->d_rect_packed[0]; ra.map[1] = ctx->d_rect_packed[1];
+        ra.dst[0] = s.dev.left[0].ptr; ra.dst[1] = s.dev.right0.ptr;
+        ra.w = ra.sw = ctx->W; ra.h = ra.sh = ctx->H; ra.dpitch = ra.spitch = ctx->W;
+        launch_remap(ra, ctx->stream);
+    }
     launch_pyr_halfsample(s.dev, ctx->stream);
     launch_lk_pyramid(s.dev, ctx->stream);
     CK(cudaGetLastError());
@@ -348,7 +370,7 @@ static int upload_common(svo_ctx *ctx, const uint8_t *left, size_t ls, const uin
     }
     if (ctx->profiling) CK(cudaEventRecord(ctx->sev[0], ctx->stream));
     if ((rc = enqueue_upload(ctx, s, left, ls, right, rs, src_kind))) return rc;
-    ctx->launch_total += pyr_launch_count(s.dev);
+    ctx->launch_total += frame_pyr_launches(ctx, s);
     if (ctx->profiling) CK(cudaEventRecord(ctx->sev[1], ctx->stream));
     *slot_out = id;
     return SVO_OK;
@@ -372,6 +394,76 @@ extern "C" int svo_launch_count(svo_ctx *ctx, long long *launches)
 {
     if (!ctx || !launches) return SVO_ERR_INVALID;
     *launches = ctx->launch_total;
+    return SVO_OK;
+}
+
+// (P[:3,:3] * R)^-1 in double by the closed form cv::Matx33d::inv uses (euroc_input.cpp:48-49 -> initUndistortRectifyMap)
+static bool inv_pr(const double P[9], const double R[9], double ir[9])
+{
+    double M[9];
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) M[i * 3 + j] = P[i * 3 + 0] * R[0 * 3 + j] + P[i * 3 + 1] * R[1 * 3 + j] + P[i * 3 + 2] * R[2 * 3 + j];
+    const double det = M[0] * (M[4] * M[8] - M[5] * M[7]) - M[1] * (M[3] * M[8] - M[5] * M[6]) + M[2] * (M[3] * M[7] - M[4] * M[6]);
+    if (det == 0) return false;
+    const double id = 1.0 / det;
+    ir[0] = (M[4] * M[8] - M[5] * M[7]) * id; ir[1] = (M[2] * M[7] - M[1] * M[8]) * id; ir[2] = (M[1] * M[5] - M[2] * M[4]) * id;
+    ir[3] = (M[5] * M[6] - M[3] * M[8]) * id; ir[4] = (M[0] * M[8] - M[2] * M[6]) * id; ir[5] = (M[2] * M[3] - M[0] * M[5]) * id;
+    ir[6] = (M[3] * M[7] - M[4] * M[6]) * id; ir[7] = (M[1] * M[6] - M[0] * M[7]) * id; ir[8] = (M[0] * M[4] - M[1] * M[3]) * id;
+    return true;
+}
+
+extern "C" int svo_set_rectification(svo_ctx *ctx, int which, const double K[9], const double D[5], const double R[9], const double P[9])
+{
+    if (!ctx || (which != 0 && which != 1) || !K || !D || !R || !P) return SVO_ERR_INVALID;
+    if (ctx->W > 2046 || ctx->H > 2046) { snprintf(ctx->err, sizeof(ctx->err), "rectification supports images up to 2046x2046"); return SVO_ERR_INVALID; }
+    if (ctx->track_pending) { snprintf(ctx->err, sizeof(ctx->err), "svo_set_rectification while a frame is in flight"); return SVO_ERR_STATE; }
+    RectifyMapArgs a;
+    if (!inv_pr(P, R, a.ir)) { snprintf(ctx->err, sizeof(ctx->err), "P*R is singular"); return SVO_ERR_INVALID; }
+    CK(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)ctx->W * ctx->H;
+    for (int k = 0; k < 2; k++)
+        if (!ctx->d_rect_map[which][k]) CK(cudaMalloc(&ctx->d_rect_map[which][k], n * sizeof(float)));
+    uint32_t *packed = ctx->d_rect_packed[which];
+    if (!packed) CK(cudaMalloc(&packed, n * sizeof(uint32_t)));
+    if (!ctx->d_raw[which]) CK(cudaMalloc(&ctx->d_raw[which], n + 16));
+    for (int k = 0; k < 9; k++) a.K[k] = K[k];
+    for (int k = 0; k < 5; k++) a.D[k] = D[k];
+    a.w = ctx->W; a.h = ctx->H; a.map1 = ctx->d_rect_map[which][0]; a.map2 = ctx->d_rect_map[which][1];
+    launch_rectify_map(a, ctx->stream);
+    launch_rectify_pack(a.map1, a.map2, (int)n, ctx->W, ctx->H, packed, ctx->stream);
+    ctx->launch_total += 2;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->d_rect_packed[which] = packed;
+    for (auto &g : ctx->graphs) destroy_graph(g);   // captured frame sequences do not contain the remap node
+    ctx->graphs.clear();
+    return SVO_OK;
+}
+
+extern "C" int svo_clear_rectification(svo_ctx *ctx)
+{
+    if (!ctx) return SVO_ERR_INVALID;
+    if (ctx->track_pending) { snprintf(ctx->err, sizeof(ctx->err), "svo_clear_rectification while a frame is in flight"); return SVO_ERR_STATE; }
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < 2; k++) {
+        if (ctx->d_rect_packed[k]) cudaFree(ctx->d_rect_packed[k]);
+        ctx->d_rect_packed[k] = nullptr;
+    }
+    for (auto &g : ctx->graphs) destroy_graph(g);
+    ctx->graphs.clear();
+    return SVO_OK;
+}
+
+extern "C" int svo_rectification_maps(svo_ctx *ctx, int which, float *map1, float *map2)
+{
+    if (!ctx || (which != 0 && which != 1) || !map1 || !map2) return SVO_ERR_INVALID;
+    if (!ctx->d_rect_packed[which]) { snprintf(ctx->err, sizeof(ctx->err), "no rectification set for input %d", which); return SVO_ERR_STATE; }
+    CK(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)ctx->W * ctx->H * sizeof(float);
+    CK(cudaMemcpyAsync(map1, ctx->d_rect_map[which][0], n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(map2, ctx->d_rect_map[which][1], n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     return SVO_OK;
 }
 
@@ -830,6 +922,10 @@ static int enqueue_track(svo_ctx *ctx, int prev_slot, int cur_slot, int n, int g
         sa.kps2d = DP(float, kps2d_ref_in); sa.n_ptr = DP(int, n); sa.mode = 1; sa.disparity = DP(float, disparity);
         sa.max_kps = grid_n; sa.cam = ctx->cam;
         launch_stereo_ssd(sa, ctx->stream); launches++;
+        {   // diagnostic (tools/ only): repeat the idempotent SSD launch to probe whether throughput is GPU-issue bound
+            static const int dup = getenv("SVO_DIAG_DUP_SSD") ? atoi(getenv("SVO_DIAG_DUP_SSD")) : 0;
+            for (int k = 0; k < dup; k++) { launch_stereo_ssd(sa, ctx->stream); launches++; }
+        }
         if (prof) CK(cudaEventRecord(ctx->sev[6], ctx->stream));
         FilterArgs fa;
         fa.kf_pose_table = ctx->d_kf_pose; fa.keyframe_ids = DP(int, kf_id); fa.disparity = DP(float, disparity);
@@ -884,7 +980,7 @@ static int capture_frame_graph(svo_ctx *ctx, svo_ctx::FrameGraph &g, int n)
     cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
     if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
     CK(e);
-    g.launches = launches + pyr_launch_count(s.dev);
+    g.launches = launches + frame_pyr_launches(ctx, s);
     CK(cudaGraphInstantiate(&g.exec, graph, 0));
     cudaGraphDestroy(graph);
     ctx->graph_captures++;

@@ -19,6 +19,23 @@ void launch_pyr_halfsample(const ImageSetDev &s, cudaStream_t st);
 void launch_lk_pyramid(const ImageSetDev &s, cudaStream_t st);
 int pyr_launch_count(const ImageSetDev &s);
 
+// ---- rectify.cu (EuRoC front end, euroc_input.cpp:48-49, :69-73)
+struct RectifyMapArgs {
+    double K[9], D[5], ir[9];  // camera matrix, (k1,k2,p1,p2,k3), inverse of P[:3,:3]*R
+    int w, h;
+    float *map1, *map2;        // w*h each
+};
+void launch_rectify_map(const RectifyMapArgs &a, cudaStream_t st);
+void launch_rectify_pack(const float *map1, const float *map2, int n, int sw, int sh, uint32_t *packed, cudaStream_t st);
+struct RemapArgs {
+    const uint8_t *src[2];     // raw (distorted) images, left / right
+    const uint32_t *map[2];    // packed maps; null = that image is not rectified
+    uint8_t *dst[2];
+    int w, h, dpitch;          // output size
+    int sw, sh, spitch;        // source size
+};
+void launch_remap(const RemapArgs &a, cudaStream_t st);
+
 // ---- align.cu
 struct AlignArgs {
     LevelDesc prev[SVO_MAX_LEVELS], cur[SVO_MAX_LEVELS];

@@ -510,6 +510,14 @@ int svo_slam_new_image(svo_slam *s, const uint8_t *left, size_t ls, const uint8_
     return svo_slam_new_image_end(s);
 }
 
+int svo_slam_set_rectification(svo_slam *s, int which, const double K[9], const double D[5], const double R[9], const double P[9])
+{
+    if (!s) return SVO_ERR_INVALID;
+    if (s->pending) { snprintf(s->err, sizeof(s->err), "set_rectification while a frame is in flight"); return SVO_ERR_STATE; }
+    int rc = svo_set_rectification(s->ctx, which, K, D, R, P);
+    return rc ? s->fail(rc) : SVO_OK;
+}
+
 static int frame_meta(const FrameH *f, uint64_t *id, svo_pose *pose, double *ts, int *n)
 {
     if (!f) return SVO_ERR_STATE;

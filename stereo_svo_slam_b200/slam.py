@@ -73,6 +73,14 @@ class StereoSlam:
             a = np.ascontiguousarray(a)
         return a
 
+    def set_rectification(self, which, K, D, R, P):
+        """EurocInput's initUndistortRectifyMap + remap (src/app/euroc_input.cpp:48-49, :69-73) moved onto the device:
+        from now on the image passed as left (which=0) / right (which=1) is a raw camera image."""
+        a = [np.ascontiguousarray(np.asarray(x, np.float64).reshape(-1)) for x in (K, D, R, np.asarray(P, np.float64).reshape(3, -1)[:, :3])]
+        if (a[0].size, a[1].size, a[2].size, a[3].size) != (9, 5, 9, 9):
+            raise SvoError(capi.SVO_ERR_INVALID, "K, R: 3x3; D: 5 coefficients; P: 3x3 or 3x4")
+        self._ck(capi.lib().svo_slam_set_rectification(self._h, which, *[x.ctypes.data_as(C.c_void_p) for x in a]))
+
     # ---- StereoSlam::new_image (stereo_slam.cpp:123)
     def new_image(self, left, right, time_stamp):
         left, right = self._img(left), self._img(right)

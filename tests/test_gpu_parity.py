@@ -425,3 +425,103 @@ def test_error_behaviour(c3ctx):
     bad["max_pyramid_levels"] = 9
     with pytest.raises(capi.SvoError):
         capi.Context(capi.CameraSettings(**bad), 752, 480)
+
+
+# ----------------------------------------------------------------------------------------------- EuRoC rectification
+def sha(a):
+    import hashlib
+    return np.frombuffer(hashlib.sha1(np.ascontiguousarray(a).tobytes()).digest(), np.uint8)
+
+
+def _euroc_cal(cv2_vectors, side):
+    p = cv2_vectors[f"rect_{side}_params"]
+    return p[:9].reshape(3, 3), p[9:14], p[14:23].reshape(3, 3), p[23:32].reshape(3, 3)
+
+
+def test_rectification_bit_exact_vs_oracle_and_cv2(fixture_images, cv2_vectors):
+    """initUndistortRectifyMap + remap (euroc_input.cpp:48-49, :69-73) on the device, fused in front of the pyramids:
+    float maps and rectified images bit-exact against the oracle AND against cv2's own output (golden hashes)."""
+    gcs, _ = mk("C3")
+    ctx = capi.Context(gcs, 752, 480)
+    raw = {0: fixture_images["left"], 1: fixture_images["right"]}
+    sides = {0: "LEFT", 1: "RIGHT"}
+    want = {}
+    for which, side in sides.items():
+        K, D, R, P = _euroc_cal(cv2_vectors, side)
+        ctx.set_rectification(which, K, D, R, P)
+        m1, m2 = ctx.rectification_maps(which)
+        o1, o2 = orc.rectify_map(K, D, R, P, 752, 480)
+        assert (m1.view(np.uint32) == o1.view(np.uint32)).all() and (m2.view(np.uint32) == o2.view(np.uint32)).all()
+        assert (sha(np.stack([m1, m2])) == cv2_vectors[f"rect_{side}_map_sha"]).all()
+        want[which] = orc.remap(raw[which], o1, o2)
+    slot = ctx.upload(raw[0], raw[1])
+    gl, gr = ctx.download(slot, 0, 0), ctx.download(slot, 1, 0)
+    assert (gl == want[0]).all() and (gr == want[1]).all()
+    assert (sha(gl) == cv2_vectors["rect_LEFT_img_sha"]).all() and (sha(gr) == cv2_vectors["rect_RIGHT_img_sha"]).all()
+    # the pyramids are built from the rectified level 0
+    assert (ctx.download(slot, 0, 1) == orc.half_sample(want[0])).all()
+    assert (ctx.download(slot, 2, 1) == orc.pyr_down(want[0])).all()
+    ctx.release(slot)
+    # one side only + strided input + clearing
+    ctx.clear_rectification()
+    K, D, R, P = _euroc_cal(cv2_vectors, "LEFT")
+    ctx.set_rectification(1, K, D, R, P)
+    wide = np.zeros((480, 800), np.uint8)
+    wide[:, 11:763] = raw[1]
+    slot = ctx.upload(raw[0], wide[:, 11:763])
+    o1, o2 = orc.rectify_map(K, D, R, P, 752, 480)
+    assert (ctx.download(slot, 0, 0) == raw[0]).all() and (ctx.download(slot, 1, 0) == orc.remap(raw[1], o1, o2)).all()
+    ctx.release(slot)
+    ctx.clear_rectification()
+    slot = ctx.upload(raw[0], raw[1])
+    assert (ctx.download(slot, 1, 0) == raw[1]).all()
+    ctx.close()
+
+
+@pytest.mark.parametrize("w,h", [(101, 77), (640, 480)])
+def test_rectification_random_calibrations(w, h):
+    """strong distortion, maps leaving the image on all sides (BORDER_CONSTANT 0), odd widths (scalar store path)"""
+    rng = np.random.default_rng(w)
+    img = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    gcs, _ = mk("C3", max_pyramid_levels=2, min_pyramid_level_pose_estimation=1)
+    ctx = capi.Context(gcs, w, h)
+    for trial in range(3):
+        f = w * (0.6 + 0.3 * trial)
+        K = np.array([[f, 0, w / 2 + 3.3], [0, f * 1.01, h / 2 - 2.2], [0, 0, 1]])
+        D = np.array([-0.35, 0.12, 1e-3, -2e-3, 0.01]) * (1 + trial)
+        r = rng.normal(0, 0.02, 3)
+        R = synth._rodrigues(r)
+        P = np.array([[f * 0.7, 0, w / 2], [0, f * 0.7, h / 2], [0, 0, 1]])
+        ctx.set_rectification(0, K, D, R, P)
+        m1, m2 = ctx.rectification_maps(0)
+        o1, o2 = orc.rectify_map(K, D, R, P, w, h)
+        assert (m1.view(np.uint32) == o1.view(np.uint32)).all() and (m2.view(np.uint32) == o2.view(np.uint32)).all()
+        slot = ctx.upload(img, img)
+        assert (ctx.download(slot, 0, 0) == orc.remap(img, o1, o2)).all()
+        assert (ctx.download(slot, 1, 0) == img).all()
+        ctx.release(slot)
+    ctx.close()
+
+
+def test_rectified_sequence_matches_prerectified(cv2_vectors):
+    """the facade with device-side rectification of RAW frames == the facade fed with oracle-rectified frames (bit-identical
+    poses and keypoints): the remap node in the captured frame graph changes nothing else"""
+    from stereo_svo_slam_b200 import StereoSlam
+    seq = synth.make_sequence("C3", seed=77)
+    gcs, _ = mk("C3")
+    K, D, R, P = _euroc_cal(cv2_vectors, "LEFT")
+    D = D * 0.2   # mild distortion keeps the synthetic scene trackable
+    o1, o2 = orc.rectify_map(K, D, R, P, 752, 480)
+    a, b = StereoSlam(gcs, 752, 480), StereoSlam(gcs, 752, 480)
+    a.set_rectification(0, K, D, R, P)
+    a.set_rectification(1, K, D, R, P)
+    for k in range(8):
+        L, Rr = seq.render(k)
+        a.new_image(L, Rr, k / 20.0)
+        b.new_image(orc.remap(L, o1, o2), orc.remap(Rr, o1, o2), k / 20.0)
+        fa, fb = a.get_frame(), b.get_frame()
+        assert (fa.pose.view(np.uint32) == fb.pose.view(np.uint32)).all(), f"frame {k}"
+        assert (fa.kps.kps2d.view(np.uint32) == fb.kps.kps2d.view(np.uint32)).all()
+        assert (fa.image("left", 0) == fb.image("left", 0)).all()
+    a.close()
+    b.close()
