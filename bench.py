@@ -270,6 +270,7 @@ def main():
         dptr = dev.data_ptr()
         img = H_ * W_
         launches0 = [None] * S
+        step_times = []
 
         T = max(1, min(a.host_threads, S))
         groups = [list(range(t, S, T)) for t in range(T)]
@@ -299,7 +300,9 @@ def main():
                 try:
                     torch.cuda.set_device(local_rank)
                     for k in range(k0, k1):
+                        t_ = time.perf_counter()
                         advance(group, k)
+                        step_times.append((time.perf_counter() - t_, k, group[0]))
                 except Exception as e:  # noqa: BLE001
                     errs.append(e)
             if T == 1:
@@ -314,6 +317,7 @@ def main():
                 raise errs[0]
 
         drive(0, W)
+        step_times.clear()
         cnt = C.c_longlong()
         for s, sl in enumerate(slams):
             lib.svo_launch_count(C.c_void_p(lib.svo_slam_ctx(sl._h)), C.byref(cnt))
@@ -346,7 +350,10 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dist.all_reduce(ln, op=dist.ReduceOp.SUM)
         nl = int(ln.item())
-        return dict(seconds=float(t.item()), launches=nl, kps=kps, keyframes=nkf, poses=poses, clocks=ck)
+        st_ = sorted(step_times)
+        trace = {"host_step_ms_p50": 1e3 * st_[len(st_) // 2][0], "host_step_ms_p99": 1e3 * st_[int(len(st_) * 0.99)][0],
+                 "host_step_ms_max": 1e3 * st_[-1][0], "slowest_steps": [(round(1e3 * d, 2), k, g) for d, k, g in st_[-4:]]} if st_ else {}
+        return dict(seconds=float(t.item()), launches=nl, kps=kps, keyframes=nkf, poses=poses, clocks=ck, trace=trace)
 
     r_dev = run("device", ClockSampler(local_rank))
     r_e2e = run("host")
@@ -405,6 +412,7 @@ def main():
                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(S * 2 * H_ * W_ + S * n_kps * 45),
                        "d2h_bytes_per_step": int(S * n_kps * 90), "ms_per_step": 1e3 * r_e2e["seconds"] / K},
                "gpu_launches": int(r_dev["launches"]),
+               "host_step_trace": {"value": r_dev["trace"], "e2e": r_e2e["trace"]},
                "clocks": r_dev["clocks"],
                "keypoints_per_frame": r_dev["kps"], "keyframes_created": r_dev["keyframes"],
                "single_stream": {"frames_per_s": 1.0 / med_wall, "ms_per_frame_wall": 1e3 * med_wall, "ms_per_frame_gpu": float(st[7]),

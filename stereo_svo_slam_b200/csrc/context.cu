@@ -1043,6 +1043,7 @@ extern "C" int svo_frame_begin(svo_ctx *ctx, const uint8_t *left, size_t ls, con
         ng.prev_slot = prev_slot; ng.cur_slot = cur; ng.bucket = bucket; ng.src_kind = src_kind; ng.stage_idx = stage_idx;
         ng.exec = nullptr; ng.left_copy = ng.right_copy = nullptr; ng.last_use = 0; ng.launches = 0;
         if ((rc = capture_frame_graph(ctx, ng, n))) return rc;
+        if (getenv("SVO_TRACE_KF")) fprintf(stderr, "[graph] capture prev %d cur %d bucket %d (cache %zu)\n", prev_slot, cur, bucket, ctx->graphs.size());
         ctx->graphs.push_back(ng);
         g = &ctx->graphs.back();
     }

@@ -12,8 +12,14 @@
 #include <cstring>
 #include <memory>
 #include <vector>
+#include <chrono>
+#include <cstdlib>
 
 #include "../../include/svo_cuda.h"
+
+// developer trace (SVO_TRACE_KF=1): host time of the keyframe path, stage by stage
+static const bool g_trace_kf = getenv("SVO_TRACE_KF") != nullptr;
+static inline double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 namespace {
 
@@ -243,13 +249,16 @@ struct svo_slam {
     int create_keyframe(FrameH &f)
     {
         const float fx = cs.fx, fy = cs.fy, cx = cs.cx, cy = cs.cy, baseline = cs.baseline;
+        const double t0 = g_trace_kf ? now_ms() : 0;
         find_bad_keypoints(f);
         std::vector<float> nk;
         std::vector<svo_keypoint_info> ni;
         int rc = detect_and_select(f.slot, nk, ni);
         if (rc) return rc;
+        const double t1 = g_trace_kf ? now_ms() : 0;
         const size_t old_count = f.kps.size();
         merge_keypoints(f, nk, ni, cs.grid_width, cs.grid_height);
+        const double t2 = g_trace_kf ? now_ms() : 0;
         const size_t n = f.kps.size();
         f.kps.kps3d.resize(n * 3);
         const size_t n_new = n - old_count;
@@ -258,6 +267,7 @@ struct svo_slam {
             rc = svo_stereo_match(ctx, f.slot, &f.kps.kps2d[2 * old_count], (int)n_new, 0, disp.data());
             if (rc) return rc;
         }
+        const double t3 = g_trace_kf ? now_ms() : 0;
         float R[9];
         rodrigues_f(&f.pose[3], R);
         const uint64_t kf_id = keyframes.size();
@@ -295,6 +305,9 @@ struct svo_slam {
         if (rc) return rc;
         keyframes.push_back(std::move(k));
         last_keyframe_created = 1;
+        if (g_trace_kf)
+            fprintf(stderr, "[kf] detect %.3f merge %.3f match %.3f init+commit %.3f ms (n_old %zu n_new %zu)\n", t1 - t0, t2 - t1, t3 - t2,
+                    now_ms() - t3, old_count, n_new);
         return SVO_OK;
     }
 

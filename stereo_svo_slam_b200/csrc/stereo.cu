@@ -13,6 +13,7 @@
 // depth_filter_kernel replaces DepthFilter::outlier_check (:52-128), DepthFilter::update_kps3d (:130-257),
 // the flag post-processing in StereoSlam::new_image (src/lib/stereo_slam.cpp:205-226) and the final
 // re-projection (:228-229).  One thread per keypoint, reference float operation order.
+#include <cstdlib>
 #include "kernels.cuh"
 
 #define SSD_THREADS 256
@@ -309,11 +310,233 @@ __global__ void __launch_bounds__(SSDC_THREADS) stereo_ssd_col_kernel(SsdArgs a,
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Tensor-core kernel (windows up to 32 px, up to 16 vertical and 64 horizontal search positions — every shipped
+// configuration).  The cross term of the SSD is the one dense contraction on the tracking path: for a keypoint,
+//     C[k][j] = sum_r sum_x Tz[r - k][x] * R[r][x + j]         (Tz = template, zero outside its th rows / tw columns)
+// is, for every ROI row r, a 16 x 32 (vertical position k, x) times 32 x 8 (x, horizontal position j) product
+// accumulated over r — exact in the integer tensor core (mma.sync m16n8k32 u8*u8 -> s32; sums stay < 2^26).
+// One WARP owns one keypoint:
+//   * staging: lane = image row; a lane reads its row as aligned words, realigns it with funnel shifts and writes the
+//     ROI four times, shifted by 0..3 bytes, so that every B fragment (4 consecutive bytes at ANY byte offset x + j)
+//     is one aligned, conflict-free LDS.32.  The same pass leaves the running sum of squares of the row in shared
+//     memory (P[r][i] = sum_{i' < i} R[r][i']^2).
+//   * A fragments are template rows r - k: the template is stored once with 15 zero rows above and zero rows below,
+//     so moving to the next ROI row just moves the read pointer by one row (a Toeplitz operand never materialised).
+//   * sum b^2 of a window = vertical sliding sum of P[r][j + tw] - P[r][j]; lane = horizontal position.
+//   * arg-min (value, raster index) and the tie rule run on the accumulator fragments in registers.
+// ~2.8 k warp instructions per keypoint instead of ~25 k for the byte-dot-product kernel below.
+// ---------------------------------------------------------------------------------------------------------
+#define SSDM_TP 12    // template row pitch (words): rows r-g, g = 0..7 land in distinct banks
+#define SSDM_CP 24    // pitch of one shifted ROI copy (words); 4 copies + 1 pad word per ROI row
+#define SSDM_RPW (4 * SSDM_CP + 1)
+#define SSDM_TPAD 15  // zero rows above the template (k up to 15)
+
+__device__ __forceinline__ void mma_u8_16832(int (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1)
+{
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+template <int NT>
+__global__ void __launch_bounds__(32) stereo_ssd_mma_kernel(SsdArgs a, int roi_rows)
+{
+    extern __shared__ __align__(16) uint32_t ssd_smem32[];
+    constexpr int PP = 8 * NT + 33;               // pitch of the prefix-of-squares rows (odd)
+    const int win = a.cam.win_depth;
+    uint32_t *tpl = ssd_smem32;                               // (SSDM_TPAD + roi_rows + 1) x SSDM_TP
+    uint32_t *roi = tpl + (SSDM_TPAD + roi_rows + 1) * SSDM_TP;  // roi_rows x SSDM_RPW
+    uint32_t *psq = roi + roi_rows * SSDM_RPW;                // roi_rows x PP
+    uint32_t *sbb = psq + roi_rows * PP;                      // 16 x 8NT
+
+    const int i = blockIdx.x;
+    const int n = min(*a.n_ptr, a.max_kps);
+    if (i >= n) return;
+    const int lane = threadIdx.x;
+    const LevelDesc L = a.left0, R = a.right0;
+    SsdGeom g;
+    if (!ssd_geometry(a.kps2d[2 * i], a.kps2d[2 * i + 1], L.w, L.h, win, a.cam.search_x, a.cam.search_y, a.mode, g)) {
+        if (lane == 0) a.disparity[i] = -1.f;
+        return;
+    }
+    const int tw = g.x12 - g.x11, th = g.y12 - g.y11, rw = g.x22 - g.x21, rh = g.y22 - g.y21;
+    const int mw = rw - tw + 1, mh = rh - th + 1;
+    const uint32_t last_mask = (tw & 3) ? ((1u << ((tw & 3) * 8)) - 1u) : 0xffffffffu;
+    const int twords = (tw + 3) >> 2;
+
+    // ---- template: zero frame, then lane = template row
+    for (int k = lane; k < (SSDM_TPAD + rh + 1) * SSDM_TP; k += 32) tpl[k] = 0;
+    __syncwarp();
+    unsigned saa = 0;
+    if (lane < th) {
+        const uint8_t *rowp = L.ptr + (size_t)(g.y11 + lane) * L.pitch + g.x11;
+        const uintptr_t addr = reinterpret_cast<uintptr_t>(rowp);
+        const uint32_t *base = reinterpret_cast<const uint32_t *>(addr & ~(uintptr_t)3);
+        const int sh = (int)(addr & 3) * 8;
+        uint32_t wv[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) wv[k] = base[k];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            uint32_t v = __funnelshift_r(wv[k], wv[k + 1], sh);
+            if (k == twords - 1) v &= last_mask;
+            if (k >= twords) v = 0;
+            tpl[(SSDM_TPAD + lane) * SSDM_TP + k] = v;
+            saa = __dp4a(v, v, saa);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) saa += __shfl_xor_sync(0xffffffffu, saa, o);
+
+    // ---- ROI: lane = ROI row (two passes when rh > 32)
+    constexpr int NW = 2 * NT + 8;               // copy words any fragment can touch: (g>>2) + 2nt + tig + 4 <= 2NT + 6
+    for (int r = lane; r < rh; r += 32) {
+        const uint8_t *rowp = R.ptr + (size_t)(g.y21 + r) * R.pitch + g.x21;
+        const uintptr_t addr = reinterpret_cast<uintptr_t>(rowp);
+        const uint32_t *base = reinterpret_cast<const uint32_t *>(addr & ~(uintptr_t)3);
+        const int sh = (int)(addr & 3) * 8;
+        const int wlast = ((int)(addr & 3) + rw - 1) >> 2;   // last aligned word holding a byte of the ROI row
+        uint32_t v0[NW + 1];
+        {
+            uint32_t w0 = base[0];
+#pragma unroll
+            for (int k = 0; k < NW + 1; k++) {
+                const uint32_t w1 = base[min(k + 1, wlast)];
+                v0[k] = __funnelshift_r(w0, w1, sh);
+                w0 = w1;
+            }
+        }
+        uint32_t *dst = roi + r * SSDM_RPW;
+#pragma unroll
+        for (int k = 0; k < NW; k++) {
+            dst[k] = v0[k];
+            dst[SSDM_CP + k] = __funnelshift_r(v0[k], v0[k + 1], 8);
+            dst[2 * SSDM_CP + k] = __funnelshift_r(v0[k], v0[k + 1], 16);
+            dst[3 * SSDM_CP + k] = __funnelshift_r(v0[k], v0[k + 1], 24);
+        }
+        // exclusive prefix of squares along the row: psq[r][i] = sum_{i' < i} R[r][i']^2, i = 0 .. 8NT+31
+        uint32_t *pp = psq + r * PP;
+        unsigned acc = 0;
+#pragma unroll
+        for (int k = 0; k < 2 * NT + 8; k++) {
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                pp[4 * k + b] = acc;
+                const unsigned px = (v0[k] >> (8 * b)) & 255u;
+                acc += px * px;
+            }
+        }
+        pp[8 * NT + 32] = acc;
+    }
+    __syncwarp();
+
+    // ---- sum b^2 per search position: lane = horizontal position j, vertical sliding window over th rows
+    for (int j = lane; j < 8 * NT; j += 32) {
+        if (j < mw) {
+            unsigned v = 0;
+            for (int r = 0; r < th; r++) v += psq[r * PP + j + tw] - psq[r * PP + j];
+            sbb[j] = v;
+            for (int k = 1; k < mh; k++) {
+                v += psq[(k + th - 1) * PP + j + tw] - psq[(k + th - 1) * PP + j];
+                v -= psq[(k - 1) * PP + j + tw] - psq[(k - 1) * PP + j];
+                sbb[k * 8 * NT + j] = v;
+            }
+        }
+    }
+
+    // ---- cross term on the tensor core
+    const int gid = lane >> 2, tig = lane & 3;
+    int acc[NT][4];
+#pragma unroll
+    for (int t = 0; t < NT; t++) { acc[t][0] = 0; acc[t][1] = 0; acc[t][2] = 0; acc[t][3] = 0; }
+    const int ntiles = (mw + 7) >> 3;            // tiles holding at least one valid position (warp uniform)
+    const uint32_t *ta = tpl + (SSDM_TPAD - gid) * SSDM_TP + tig;
+    const uint32_t *rb = roi + (gid & 3) * SSDM_CP + (gid >> 2) + tig;
+    for (int r = 0; r < rh; r++) {
+        const uint32_t a0 = ta[0], a2 = ta[4], a1 = ta[-8 * SSDM_TP], a3 = ta[-8 * SSDM_TP + 4];
+#pragma unroll
+        for (int t = 0; t < NT; t++) {
+            if (t < ntiles) mma_u8_16832(acc[t], a0, a1, a2, a3, rb[2 * t], rb[2 * t + 4]);
+        }
+        ta += SSDM_TP;
+        rb += SSDM_RPW;
+    }
+    __syncwarp();
+
+    // ---- SSD = sum a^2 + sum b^2 - 2 sum ab; arg-min by (value, raster index) == cv::minMaxLoc's first minimum
+    unsigned long long best = ~0ull;
+    uint32_t sv[NT][4];
+#pragma unroll
+    for (int t = 0; t < NT; t++) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int k = gid + (q >> 1) * 8, j = 8 * t + 2 * tig + (q & 1);
+            sv[t][q] = 0xffffffffu;
+            if (k < mh && j < mw) {
+                const uint32_t v = saa + sbb[k * 8 * NT + j] - 2u * (uint32_t)acc[t][q];
+                sv[t][q] = v;
+                const unsigned long long key = ((unsigned long long)v << 32) | (unsigned)(k * mw + j);
+                best = key < best ? key : best;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+        best = other < best ? other : best;
+    }
+    const uint32_t minv = (uint32_t)(best >> 32);
+    const int mp = (int)(best & 0xffffffffu);
+    const int mly = mp / mw, mlx = mp - mly * mw;
+    // ---- tie rule (depth_calculator.cpp:226-237): mean column index of entries <= min right/below the first minimum
+    int cnt = 0, sum = 0;
+#pragma unroll
+    for (int t = 0; t < NT; t++) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int k = gid + (q >> 1) * 8, j = 8 * t + 2 * tig + (q & 1);
+            if (k < mh && j < mw && j >= mlx && k >= mly && sv[t][q] <= minv) { cnt++; sum += j; }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { cnt += __shfl_xor_sync(0xffffffffu, cnt, o); sum += __shfl_xor_sync(0xffffffffu, sum, o); }
+    if (lane == 0) {
+        const float minPos = (float)sum / (float)cnt;  // float sum of small integers is exact
+        a.disparity[i] = (a.mode == 1) ? fmaxf(0.5f, minPos) : minPos;
+    }
+}
+
+template <int NT>
+static void launch_ssd_mma(const SsdArgs &a, int roi_rows, cudaStream_t st)
+{
+    const size_t smem = ((size_t)(SSDM_TPAD + roi_rows + 1) * SSDM_TP + (size_t)roi_rows * SSDM_RPW + (size_t)roi_rows * (8 * NT + 33) +
+                         (size_t)16 * 8 * NT) * 4;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(stereo_ssd_mma_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    stereo_ssd_mma_kernel<NT><<<a.max_kps, 32, smem, st>>>(a, roi_rows);
+}
+
 void launch_stereo_ssd(const SsdArgs &a, cudaStream_t st)
 {
     if (a.max_kps <= 0) return;
     const int win = a.cam.win_depth;
     const int map_cap = (a.cam.search_x + 1) * (2 * a.cam.search_y + 1);
+    static const bool no_mma = getenv("SVO_SSD_NO_MMA") != nullptr;   // A/B switch for profiling
+    if (!no_mma && win <= 32 && 2 * a.cam.search_y + 1 <= 16 && a.cam.search_x + 1 <= 64) {
+        const int roi_rows = win + 2 * a.cam.search_y + 1;
+        switch ((a.cam.search_x + 8) / 8) {   // ceil((search_x + 1) / 8) tiles of 8 horizontal positions
+        case 1: launch_ssd_mma<1>(a, roi_rows, st); break;
+        case 2: launch_ssd_mma<2>(a, roi_rows, st); break;
+        case 3: launch_ssd_mma<3>(a, roi_rows, st); break;
+        case 4: launch_ssd_mma<4>(a, roi_rows, st); break;
+        case 5: launch_ssd_mma<5>(a, roi_rows, st); break;
+        case 6: launch_ssd_mma<6>(a, roi_rows, st); break;
+        case 7: launch_ssd_mma<7>(a, roi_rows, st); break;
+        default: launch_ssd_mma<8>(a, roi_rows, st); break;
+        }
+        return;
+    }
     if (win <= 32 && 2 * a.cam.search_y + 1 <= SSDC_MAXK) {
         const int rpw = (win + a.cam.search_x + 3) / 4 + 10;      // 9 words are read from the last search column
         const int roi_rows = win + 2 * a.cam.search_y + 1;
