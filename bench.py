@@ -314,8 +314,34 @@ def main():
                 for t in ts:
                     t.join()
             if errs:
+                if os.environ.get("SVO_DEBUG_MARKS"):
+                    b64 = (C.c_int * 64)()
+                    for s_, sl_ in enumerate(slams):
+                        lib.svo_debug_marks(C.c_void_p(lib.svo_slam_ctx(sl_._h)), b64)
+                        if b64[16]:
+                            sys.stderr.write(f"[align timeout] mode {mode} seq {s_}: {list(b64)}\n")
                 raise errs[0]
 
+        wd_sec = float(os.environ.get("BENCH_WATCHDOG", "0"))
+        wd = {"stop": False}
+        if wd_sec > 0:   # developer aid: report where every sequence stands if the run stops making progress
+            def watchdog():
+                last, t_last = -1, time.perf_counter()
+                while not wd["stop"]:
+                    time.sleep(1.0)
+                    cur = len(step_times)
+                    if cur != last:
+                        last, t_last = cur, time.perf_counter()
+                    elif time.perf_counter() - t_last > wd_sec:
+                        buf16 = (C.c_int * 64)()
+                        for s_, sl_ in enumerate(slams):
+                            if getattr(sl_, "_h", None):
+                                lib.svo_debug_marks(C.c_void_p(lib.svo_slam_ctx(sl_._h)), buf16)
+                                sys.stderr.write(f"[watchdog] mode {mode} seq {s_}: marks {list(buf16)}\n")
+                        sys.stderr.write(f"[watchdog] steps done {cur}, per-thread last k: {sorted((g, k) for _, k, g in step_times[-64:])[-16:]}\n")
+                        sys.stderr.flush()
+                        os._exit(3)
+            threading.Thread(target=watchdog, daemon=True).start()
         drive(0, W)
         step_times.clear()
         cnt = C.c_longlong()
@@ -333,6 +359,7 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
+        wd["stop"] = True
         dev_s = e0.elapsed_time(e1) / 1e3
         ck = clocks.stop() if clocks else None
         nl = 0
@@ -355,7 +382,11 @@ def main():
                  "host_step_ms_max": 1e3 * st_[-1][0], "slowest_steps": [(round(1e3 * d, 2), k, g) for d, k, g in st_[-4:]]} if st_ else {}
         return dict(seconds=float(t.item()), launches=nl, kps=kps, keyframes=nkf, poses=poses, clocks=ck, trace=trace)
 
-    r_dev = run("device", ClockSampler(local_rank))
+    r_dev = run("device", None if os.environ.get("BENCH_NO_NVML") else ClockSampler(local_rank))
+    if os.environ.get("BENCH_ONLY") == "device":   # developer switch: whole-job device-resident run only
+        if rank == 0:
+            print(json.dumps({"value": S * K * world / r_dev["seconds"], "trace": r_dev["trace"]}))
+        return
     r_e2e = run("host")
     total_frames = S * K * world
     value = total_frames / r_dev["seconds"]

@@ -199,6 +199,12 @@ int svo_launch_count(svo_ctx *ctx, long long *launches);
 int svo_set_profiling(svo_ctx *ctx, int on);
 int svo_last_stage_ms(svo_ctx *ctx, float *stage_ms8);
 int svo_sync(svo_ctx *ctx);
+/* developer aid (env SVO_DEBUG_MARKS=1 at context creation): progress stamps written by the device between the stages
+ * of a frame: out16[s] = sequence number of the last stamp of stage s (1 ingest start, 2 ingest done, 3 pyramids,
+ * 4 inputs on device, 5 alignment, 6 KLT, 7 refinement, 8 SSD, 9 depth filter, 10 D2H enqueued), out16[0] = latest stamp,
+ * out16[15] = stamps enqueued by the host, [16..63] = record of a barrier wait of the alignment kernel that timed out;
+ * all -1 when the aid is off */
+int svo_debug_marks(svo_ctx *ctx, int *out64);
 
 /* ================================================================== host facade ================ */
 /* StereoSlam (src/include/stereo_slam.hpp:27-79) with plain-C types. */

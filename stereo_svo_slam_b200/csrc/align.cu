@@ -66,6 +66,37 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
             : "memory");
     }
 }
+// developer aid: same wait, but after ~2 s of polling it records where it was stuck in dbg[] (mapped host memory) and traps
+__device__ __noinline__ void mbar_wait_dbg(unsigned long long *bar, uint32_t parity, int *dbg, int tag, int crank, int level, int mode, int evals, int grads)
+{
+    uint32_t ok = 0;
+    const uint32_t addr = smem_u32(bar);
+    long long t0 = clock64();
+    while (!ok) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (!ok && clock64() - t0 > 4000000000ll) {
+            if (atomicAdd(dbg, 1) < 4) {
+                int *q = dbg + 1 + 10 * (crank & 3);
+                q[0] = tag; q[1] = crank; q[2] = threadIdx.x; q[3] = (int)parity; q[4] = level; q[5] = mode; q[6] = evals; q[7] = grads;
+                unsigned long long st;
+                asm volatile("ld.shared.b64 %0, [%1];" : "=l"(st) : "r"(addr));
+                q[8] = (int)(st & 0xffffffffu); q[9] = (int)(st >> 32);
+                __threadfence_system();
+            }
+            __nanosleep(1000000);
+            __trap();
+        }
+    }
+}
+
 __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, unsigned long long *bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
@@ -291,6 +322,10 @@ __global__ void __launch_bounds__(ALIGN_THREADS, 1) sparse_align_kernel(AlignArg
     const int n = hdr->n;
     const int npass = (n + KPS_PER_PASS - 1) / KPS_PER_PASS;
     uint32_t phase = 0, xphase[3] = {0, 0, 0};
+    // cost-exchange buffer / barrier of the NEXT evaluation.  It must keep alternating across level boundaries: a CTA may
+    // push evaluation e+2 into a peer only after passing the wait of e+1, and every peer pushes e+1 only after all its
+    // threads have read the table of e — so buffer e % 2 is free again exactly two evaluations later, never one.
+    int cbuf = 0;
     float *scr = a.scratch;                 // [13][4 * max_kps]: per (keypoint,row): 4 x (g0, g1, Sprev) + mask
     const size_t SN = (size_t)4 * a.max_kps;
 
@@ -335,7 +370,11 @@ __global__ void __launch_bounds__(ALIGN_THREADS, 1) sparse_align_kernel(AlignArg
             if (tid == 0) dev_rodrigues_d(-x0[3], -x0[4], -x0[5], hdr->Rd[16]);   // overlaps the TMA copy
             x0slot = 16; sp = 1; tb = 0;
         }
-        if (kSmem) { mbar_wait(&hdr->bar, phase); phase ^= 1; }
+        if (kSmem) {
+            if (a.dbg) mbar_wait_dbg(&hdr->bar, phase, a.dbg, 1, (int)crank, level, -1, 0, 0);
+            else mbar_wait(&hdr->bar, phase);
+            phase ^= 1;
+        }
 
         // ---- per-level cache of the pose-independent reference terms of this lane's patch row
         //      (calculate_hessian :346-395 image part, get_gradient :449-460 reference part)
@@ -381,7 +420,7 @@ __global__ void __launch_bounds__(ALIGN_THREADS, 1) sparse_align_kernel(AlignArg
 
         // ---- Gauss-Newton driver (estimate_pose_at_level :166-222).
         //  mode 0: cost at x0 (initial)   mode 1: gradient at x0   mode 2: cost at xt   mode 3: level done
-        int mode = 0, it = 0, n_evals = 0, n_grads = 0, cbuf = 0, jstep = 0;
+        int mode = 0, it = 0, n_evals = 0, n_grads = 0, jstep = 0;
         float kstep = 1.f;
         while (mode != 3) {
             const float *x = (mode == 2) ? xt : x0;
@@ -423,7 +462,8 @@ __global__ void __launch_bounds__(ALIGN_THREADS, 1) sparse_align_kernel(AlignArg
                     dsmem_push_f64(&hdr->cl_cost[cbuf][crank], &hdr->xbar[cbuf], (unsigned)tid, cta);
                     if (tid == 0) mbar_expect_tx(&hdr->xbar[cbuf], CL * 8);
                 }
-                mbar_wait(&hdr->xbar[cbuf], xphase[cbuf]);
+                if (a.dbg) mbar_wait_dbg(&hdr->xbar[cbuf], xphase[cbuf], a.dbg, 2 + cbuf, (int)crank, level, mode, n_evals, n_grads);
+                else mbar_wait(&hdr->xbar[cbuf], xphase[cbuf]);
                 xphase[cbuf] ^= 1;
                 double tot = 0.0;
 #pragma unroll
@@ -534,7 +574,8 @@ __global__ void __launch_bounds__(ALIGN_THREADS, 1) sparse_align_kernel(AlignArg
                     for (unsigned dst = 0; dst < CL; dst++) dsmem_push_f64(&hdr->cl_grad[crank][tid], &hdr->xbar[2], dst, t);
                     if (tid == 0) mbar_expect_tx(&hdr->xbar[2], CL * NGRAD * 8);
                 }
-                mbar_wait(&hdr->xbar[2], xphase[2]);
+                if (a.dbg) mbar_wait_dbg(&hdr->xbar[2], xphase[2], a.dbg, 4, (int)crank, level, mode, n_evals, n_grads);
+                else mbar_wait(&hdr->xbar[2], xphase[2]);
                 xphase[2] ^= 1;
                 if (tid < NGRAD) {
                     double t = 0.0;

@@ -11,6 +11,13 @@
 #include "kernels.cuh"
 
 static char g_create_err[256] = "";
+#include <chrono>
+static const bool g_trace = getenv("SVO_TRACE_KF") != nullptr;   // developer trace of slow host-side calls
+static inline double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+// developer aid (SVO_DEBUG_MARKS=1): single-thread kernels that stamp a progress id into mapped host memory between the
+// stages of a frame, so a stuck stream can be attributed to a stage from the host (svo_debug_marks)
+__global__ void mark_kernel(volatile int *p, int slot, int v) { p[slot] = v; p[0] = v; }
 
 struct Slot {
     uint8_t *base = nullptr;
@@ -69,6 +76,7 @@ struct svo_ctx {
     };
     std::vector<FrameGraph> graphs;
     bool use_graphs = true;
+    bool use_ingest = true;   // SM-driven frame ingest instead of copy-engine DMA (SVO_NO_INGEST=1 turns it off)
     unsigned long long graph_clock = 0;
     long long graph_launches = 0, graph_captures = 0;
     float stage_ms[8] = {0};
@@ -76,8 +84,15 @@ struct svo_ctx {
     float *d_rect_map[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
     uint32_t *d_rect_packed[2] = {nullptr, nullptr};
     uint8_t *d_raw[2] = {nullptr, nullptr};   // raw (distorted) images of the frame being uploaded
+    int *h_marks = nullptr, *d_marks = nullptr;   // SVO_DEBUG_MARKS
+    int mark_seq = 0;
     char err[256];
 };
+
+static void mark(svo_ctx *ctx, int id)
+{
+    if (ctx->d_marks) mark_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d_marks, id, ++ctx->mark_seq);
+}
 
 static void destroy_graph(svo_ctx::FrameGraph &g);
 
@@ -155,6 +170,13 @@ extern "C" int svo_ctx_create(const svo_camera_settings *s, int device, int widt
     ctx->W = width; ctx->H = height;
     ctx->n_levels = s->max_pyramid_levels;
     ctx->use_graphs = getenv("SVO_NO_GRAPHS") == nullptr;
+    ctx->use_ingest = getenv("SVO_NO_INGEST") == nullptr;
+    if (getenv("SVO_DEBUG_MARKS")) {
+        if (cudaHostAlloc(&ctx->h_marks, 64 * sizeof(int), cudaHostAllocMapped) == cudaSuccess) {
+            memset(ctx->h_marks, 0, 64 * sizeof(int));
+            cudaHostGetDevicePointer((void **)&ctx->d_marks, ctx->h_marks, 0);
+        }
+    }
     if (max_keypoints <= 0) {
         // one keypoint per grid cell per keyframe, surviving ones from older keyframes on top: 4x cells is ample
         max_keypoints = 4 * (width / s->grid_width + 1) * (height / s->grid_height + 1);
@@ -325,6 +347,29 @@ static int enqueue_upload(svo_ctx *ctx, Slot &s, const uint8_t *left, size_t ls,
     // a rectified input lands in the context's raw buffer; the remap kernel in front of the pyramids writes level 0
     uint8_t *dl = ctx->d_rect_packed[0] ? ctx->d_raw[0] : s.dev.left[0].ptr;
     uint8_t *dr = ctx->d_rect_packed[1] ? ctx->d_raw[1] : s.dev.right0.ptr;
+    // preferred path: the SMs fetch the pair themselves (zero-copy from page-locked host memory, or device memory)
+    if (ctx->use_ingest) {
+        IngestArgs ia;
+        ia.dst[0] = dl; ia.dst[1] = dr; ia.w = ctx->W; ia.h = ctx->H; ia.spitch[0] = ls; ia.spitch[1] = rs;
+        bool ok = true;
+        if (src_kind == 2) { ia.src[0] = left; ia.src[1] = right; }
+        else {
+            void *pl = nullptr, *pr = nullptr;
+            ok = cudaHostGetDevicePointer(&pl, const_cast<uint8_t *>(left), 0) == cudaSuccess &&
+                 cudaHostGetDevicePointer(&pr, const_cast<uint8_t *>(right), 0) == cudaSuccess;
+            if (!ok) cudaGetLastError();
+            ia.src[0] = (const uint8_t *)pl; ia.src[1] = (const uint8_t *)pr;
+        }
+        if (ok && ingest_supported(ia)) {
+            mark(ctx, 1);
+            launch_ingest(ia, ctx->stream);
+            mark(ctx, 2);
+            ctx->launch_total += 1;
+            CK(cudaGetLastError());
+            if (copies_only) return SVO_OK;
+            return enqueue_pyramids(ctx, s);
+        }
+    }
     // contiguous rows: one linear DMA (a 2-D copy of 752-byte rows costs one descriptor per row)
     if (ls == (size_t)ctx->W) CK(cudaMemcpyAsync(dl, left, img, kind, ctx->stream));
     else CK(cudaMemcpy2DAsync(dl, ctx->W, left, ls, ctx->W, ctx->H, kind, ctx->stream));
@@ -349,6 +394,7 @@ static int enqueue_pyramids(svo_ctx *ctx, Slot &s)
     }
     launch_pyr_halfsample(s.dev, ctx->stream);
     launch_lk_pyramid(s.dev, ctx->stream);
+    mark(ctx, 3);
     CK(cudaGetLastError());
     return SVO_OK;
 }
@@ -464,6 +510,14 @@ extern "C" int svo_rectification_maps(svo_ctx *ctx, int which, float *map1, floa
     CK(cudaMemcpyAsync(map1, ctx->d_rect_map[which][0], n, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(map2, ctx->d_rect_map[which][1], n, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    return SVO_OK;
+}
+
+extern "C" int svo_debug_marks(svo_ctx *ctx, int *out64)
+{
+    if (!ctx || !out64) return SVO_ERR_INVALID;
+    for (int k = 0; k < 64; k++) out64[k] = ctx->h_marks ? ((volatile int *)ctx->h_marks)[k] : -1;
+    out64[15] = ctx->mark_seq;
     return SVO_OK;
 }
 
@@ -637,6 +691,7 @@ static void fill_align_args(svo_ctx *ctx, int prev_slot, int cur_slot, AlignArgs
     a.cost_out = DP(float, costs); a.evals_out = DP(int, evals);
     a.scratch = ctx->d_align_scratch; a.max_kps = ctx->max_kps; a.cam = ctx->cam;
     a.probe_level = -1; a.probe_grad = nullptr;
+    a.dbg = ctx->d_marks ? ctx->d_marks + 16 : nullptr;
     (void)n;
 }
 
@@ -893,7 +948,9 @@ static int enqueue_track(svo_ctx *ctx, int prev_slot, int cur_slot, int n, int g
     AlignArgs aa;
     fill_align_args(ctx, prev_slot, cur_slot, aa, n, true);
     if (prof) CK(cudaEventRecord(ctx->sev[2], ctx->stream));
+    mark(ctx, 4);
     CK(launch_align(aa, ctx->stream)); launches++;
+    mark(ctx, 5);
     if (prof) CK(cudaEventRecord(ctx->sev[3], ctx->stream));
     if (n > 0) {
         // 2. projection with the aligned pose + KLT against the origin keyframes + gating (stereo_slam.cpp:71-83)
@@ -906,6 +963,7 @@ static int enqueue_track(svo_ctx *ctx, int prev_slot, int cur_slot, int n, int g
         ka.flags = DP(uint8_t, flags); ka.kps2d_out = DP(float, kps2d_ref_in); ka.max_kps = grid_n; ka.cam = ctx->cam;
         ka.iters = DP(int, klt_iters);
         launch_klt(ka, ctx->stream); launches++;
+        mark(ctx, 6);
     }
     if (prof) CK(cudaEventRecord(ctx->sev[4], ctx->stream));
     // 3. reprojection Gauss-Newton (pose_refinement.cpp:175-177)
@@ -914,6 +972,7 @@ static int enqueue_track(svo_ctx *ctx, int prev_slot, int cur_slot, int n, int g
     ra.pose_in = DP(float, pose_aligned); ra.pose_out = DP(float, pose_refined);
     ra.cost_out = DP(float, costs) + 1; ra.evals_out = DP(int, evals) + 16; ra.cam = ctx->cam;
     launch_refine(ra, ctx->stream); launches++;
+    mark(ctx, 7);
     if (prof) CK(cudaEventRecord(ctx->sev[5], ctx->stream));
     if (n > 0) {
         // 4. depth filter: disparities on the current stereo pair, then vote / triangulate / Kalman / flags / re-project
@@ -932,7 +991,9 @@ static int enqueue_track(svo_ctx *ctx, int prev_slot, int cur_slot, int n, int g
         fa.kps2d = DP(float, kps2d_ref_in); fa.ref_kps2d = DP(float, ref_kps2d); fa.kps3d = DP(float, kps3d);
         fa.flags = DP(uint8_t, flags); fa.inlier = DP(int, inlier); fa.outlier = DP(int, outlier); fa.kf_state = DP(float, kf_state);
         fa.pose = DP(float, pose_refined); fa.kps2d_out = DP(float, kps2d_out); fa.n_ptr = DP(int, n); fa.max_kps = grid_n; fa.cam = ctx->cam;
+        mark(ctx, 8);
         launch_depth_filter(fa, ctx->stream); launches++;
+        mark(ctx, 9);
     } else if (prof) {
         CK(cudaEventRecord(ctx->sev[6], ctx->stream));
     }
@@ -940,6 +1001,7 @@ static int enqueue_track(svo_ctx *ctx, int prev_slot, int cur_slot, int n, int g
     CK(cudaGetLastError());
     // one D2H for all outputs (in/out + out regions are contiguous)
     CK(cudaMemcpyAsync(h + L.inout_begin, ctx->d_io + L.inout_begin, L.total - L.inout_begin, cudaMemcpyDeviceToHost, ctx->stream));
+    mark(ctx, 10);
     *launches_out = launches;
     return SVO_OK;
 }
@@ -992,6 +1054,7 @@ extern "C" int svo_frame_begin(svo_ctx *ctx, const uint8_t *left, size_t ls, con
                                svo_track_io *io, int *cur_slot_out)
 {
     if (!ctx || !left || !right || !io || !cur_slot_out || ls < (size_t)ctx->W || rs < (size_t)ctx->W || !slot_ok(ctx, prev_slot)) return SVO_ERR_INVALID;
+    const double tt0 = g_trace ? now_ms() : 0;
     int rc = validate_and_pack(ctx, io);
     if (rc) return rc;
     CK(cudaSetDevice(ctx->device));
@@ -1027,7 +1090,9 @@ extern "C" int svo_frame_begin(svo_ctx *ctx, const uint8_t *left, size_t ls, con
         left = stage; right = stage + img; ls = rs = (size_t)ctx->W;
     }
     // the two image copies go on the stream directly (their source changes every frame); pyramids + tracking replay
+    const double tt1 = g_trace ? now_ms() : 0;
     if ((rc = enqueue_upload(ctx, ctx->slots[cur], left, ls, right, rs, src_kind, true))) return rc;
+    const double tt2 = g_trace ? now_ms() : 0;
     const int bucket = std::min(ctx->max_kps, (n + 127) / 128 * 128);
     svo_ctx::FrameGraph *g = nullptr;
     for (auto &c : ctx->graphs)
@@ -1048,9 +1113,12 @@ extern "C" int svo_frame_begin(svo_ctx *ctx, const uint8_t *left, size_t ls, con
         g = &ctx->graphs.back();
     }
     g->last_use = ++ctx->graph_clock;
+    const double tt3 = g_trace ? now_ms() : 0;
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     CK(cudaGraphLaunch(g->exec, ctx->stream));
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    if (g_trace && now_ms() - tt0 > 3.0)
+        fprintf(stderr, "[slow frame_begin] pack+alloc %.2f upload %.2f graph lookup/capture %.2f launch %.2f ms\n", tt1 - tt0, tt2 - tt1, tt3 - tt2, now_ms() - tt3);
     ctx->graph_launches++;
     ctx->last_launches = g->launches;
     ctx->launch_total += g->launches;
@@ -1079,7 +1147,9 @@ extern "C" int svo_track_frame_end(svo_ctx *ctx, svo_track_io *io)
     if (!ctx->track_pending) { snprintf(ctx->err, sizeof(ctx->err), "svo_track_frame_end without _begin"); return SVO_ERR_STATE; }
     ctx->track_pending = false;
     CK(cudaSetDevice(ctx->device));
+    const double ts0 = g_trace ? now_ms() : 0;
     CK(cudaStreamSynchronize(ctx->stream));
+    if (g_trace && now_ms() - ts0 > 20.0) fprintf(stderr, "[slow frame_end] stream sync %.2f ms\n", now_ms() - ts0);
     CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
     if (ctx->profiling) {
         // sev: 0 upload start, 1 pyramids done, 2 inputs on device, 3 align, 4 klt, 5 refine, 6 ssd, 7 filter, 8 d2h

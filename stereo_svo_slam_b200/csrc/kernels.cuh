@@ -18,6 +18,14 @@ struct ImageSetDev {  // device view of one stereo frame ("slot")
 void launch_pyr_halfsample(const ImageSetDev &s, cudaStream_t st);
 void launch_lk_pyramid(const ImageSetDev &s, cudaStream_t st);
 int pyr_launch_count(const ImageSetDev &s);
+struct IngestArgs {
+    const uint8_t *src[2];   // left / right source (device pointers: device memory or mapped page-locked host memory)
+    size_t spitch[2];
+    uint8_t *dst[2];         // contiguous rows (pitch == w)
+    int w, h;
+};
+bool ingest_supported(const IngestArgs &a);
+void launch_ingest(const IngestArgs &a, cudaStream_t st);
 
 // ---- rectify.cu (EuRoC front end, euroc_input.cpp:48-49, :69-73)
 struct RectifyMapArgs {
@@ -53,6 +61,7 @@ struct AlignArgs {
     // probe mode: single level, single evaluation
     int probe_level;       // -1 = normal
     float *probe_grad;     // 6
+    int *dbg;              // developer aid (SVO_DEBUG_MARKS): where a stuck barrier wait was, else null
 };
 cudaError_t launch_align(const AlignArgs &a, cudaStream_t st);
 size_t align_scratch_floats(int max_kps);

@@ -129,4 +129,37 @@ void launch_lk_pyramid(const ImageSetDev &s, cudaStream_t st)
     }
 }
 
+// Frame ingest: both images of a stereo pair, from ANY device-visible memory — page-locked host memory read by the SMs
+// over PCIe (zero-copy; a 361 KB cudaMemcpyAsync costs ~25 us of copy-engine time, of which ~18 us is fixed overhead,
+// so two copies per frame cap one engine at ~20 k frames/s) or device memory — into level 0 of the image set (or into
+// the raw buffers of the rectifier).  One 16-byte load per thread, all 722 KB of a C3 pair in flight at once.
+__global__ void __launch_bounds__(256) ingest_kernel(IngestArgs a)
+{
+    const int z = blockIdx.y;
+    const uint8_t *__restrict__ src = z ? a.src[1] : a.src[0];
+    uint8_t *__restrict__ dst = z ? a.dst[1] : a.dst[0];
+    const size_t sp = z ? a.spitch[1] : a.spitch[0];
+    const int c16 = a.w >> 4;                        // 16-byte chunks per row
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= c16 * a.h) return;
+    const int row = idx / c16, col = (idx - row * c16) << 4;
+    const uint4 v = __ldcs(reinterpret_cast<const uint4 *>(src + (size_t)row * sp + col));
+    *reinterpret_cast<uint4 *>(dst + (size_t)row * a.w + col) = v;
+}
+
+bool ingest_supported(const IngestArgs &a)
+{
+    if (a.w & 15) return false;
+    for (int z = 0; z < 2; z++)
+        if ((reinterpret_cast<uintptr_t>(a.src[z]) & 15) || (a.spitch[z] & 15) || (reinterpret_cast<uintptr_t>(a.dst[z]) & 15)) return false;
+    return true;
+}
+
+void launch_ingest(const IngestArgs &a, cudaStream_t st)
+{
+    const int total = (a.w >> 4) * a.h;
+    dim3 grid((total + 255) / 256, 2);
+    ingest_kernel<<<grid, 256, 0, st>>>(a);
+}
+
 int pyr_launch_count(const ImageSetDev &s) { return (s.n_levels > 1 ? 1 : 0) + SVO_LK_LEVELS; }

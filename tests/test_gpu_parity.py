@@ -525,3 +525,36 @@ def test_rectified_sequence_matches_prerectified(cv2_vectors):
         assert (fa.image("left", 0) == fb.image("left", 0)).all()
     a.close()
     b.close()
+
+
+def test_ingest_from_pinned_and_device_memory(c3ctx, fixture_images):
+    """the SM-driven ingest kernel (zero-copy from page-locked host memory / device memory) lands the same bytes as
+    the staged upload of pageable memory, also for strided sources that fall back to the 2-D DMA"""
+    import ctypes as C
+    import torch
+    ctx, _, _ = c3ctx
+    L, R = fixture_images["left"], fixture_images["right"]
+    pin = torch.from_numpy(np.stack([L, R])).pin_memory()
+    pl, pr = pin[0].numpy(), pin[1].numpy()
+    slot = ctx.upload(pl, pr)
+    assert (ctx.download(slot, 0, 0) == L).all() and (ctx.download(slot, 1, 0) == R).all()
+    assert (ctx.download(slot, 0, 2) == orc.half_sample(orc.half_sample(L))).all()
+    ctx.release(slot)
+    dev = pin.cuda()
+    out = C.c_int()
+    rc = capi.lib().svo_upload_stereo_device(ctx.h_ctx, C.c_void_p(dev[0].data_ptr()), C.c_size_t(752), C.c_void_p(dev[1].data_ptr()),
+                                             C.c_size_t(752), C.byref(out))
+    assert rc == 0
+    assert (ctx.download(out.value, 0, 0) == L).all() and (ctx.download(out.value, 1, 0) == R).all()
+    ctx.release(out.value)
+    wide = torch.zeros((2, 480, 800), dtype=torch.uint8).pin_memory()
+    wide[:, :, 5:757] = torch.from_numpy(np.stack([L, R]))      # unaligned, strided rows -> DMA fallback
+    wl, wr = wide[0].numpy()[:, 5:757], wide[1].numpy()[:, 5:757]
+    slot = ctx.upload(wl, wr)
+    assert (ctx.download(slot, 0, 0) == L).all() and (ctx.download(slot, 1, 0) == R).all()
+    ctx.release(slot)
+    wide[:, :, 16:768] = torch.from_numpy(np.stack([L, R]))     # aligned strided rows -> ingest kernel with a pitch
+    wl, wr = wide[0].numpy()[:, 16:768], wide[1].numpy()[:, 16:768]
+    slot = ctx.upload(wl, wr)
+    assert (ctx.download(slot, 0, 0) == L).all() and (ctx.download(slot, 1, 0) == R).all()
+    ctx.release(slot)
