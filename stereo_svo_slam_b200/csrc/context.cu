@@ -19,6 +19,58 @@ static inline double now_ms() { return std::chrono::duration<double, std::milli>
 // stages of a frame, so a stuck stream can be attributed to a stage from the host (svo_debug_marks)
 __global__ void mark_kernel(volatile int *p, int slot, int v) { p[slot] = v; p[0] = v; }
 
+// Image-set arena: all contexts of one device and one image geometry carve their slots out of shared chunks, so that a
+// keyframe (which needs a new image set) does not call cudaMalloc in steady state — an allocation under load stalls every
+// stream of the process for milliseconds (tens to hundreds of ms with 32 sequences in flight).
+#include <mutex>
+struct SlotArena {
+    int device; size_t slot_bytes; int users;
+    std::vector<uint8_t *> chunks, free_list;
+};
+static std::mutex g_arena_mu;
+static std::vector<SlotArena *> g_arenas;
+#define ARENA_CHUNK_SLOTS 32
+
+static SlotArena *arena_get(int device, size_t slot_bytes)
+{
+    std::lock_guard<std::mutex> lk(g_arena_mu);
+    for (SlotArena *a : g_arenas)
+        if (a->device == device && a->slot_bytes == slot_bytes) { a->users++; return a; }
+    SlotArena *a = new SlotArena{device, slot_bytes, 1, {}, {}};
+    g_arenas.push_back(a);
+    return a;
+}
+static cudaError_t arena_take(SlotArena *a, uint8_t **out)
+{
+    std::lock_guard<std::mutex> lk(g_arena_mu);
+    if (a->free_list.empty()) {
+        uint8_t *c = nullptr;
+        cudaError_t e = cudaMalloc(&c, a->slot_bytes * ARENA_CHUNK_SLOTS);
+        if (e != cudaSuccess) return e;
+        e = cudaMemset(c, 0, a->slot_bytes * ARENA_CHUNK_SLOTS);
+        if (e != cudaSuccess) { cudaFree(c); return e; }
+        a->chunks.push_back(c);
+        for (int k = ARENA_CHUNK_SLOTS - 1; k >= 0; k--) a->free_list.push_back(c + (size_t)k * a->slot_bytes);
+    }
+    *out = a->free_list.back();
+    a->free_list.pop_back();
+    return cudaSuccess;
+}
+static void arena_give(SlotArena *a, uint8_t *p)
+{
+    std::lock_guard<std::mutex> lk(g_arena_mu);
+    a->free_list.push_back(p);
+}
+static void arena_release(SlotArena *a)
+{
+    std::lock_guard<std::mutex> lk(g_arena_mu);
+    if (--a->users > 0) return;
+    for (uint8_t *c : a->chunks) cudaFree(c);
+    for (size_t k = 0; k < g_arenas.size(); k++)
+        if (g_arenas[k] == a) { g_arenas.erase(g_arenas.begin() + k); break; }
+    delete a;
+}
+
 struct Slot {
     uint8_t *base = nullptr;
     ImageSetDev dev;
@@ -44,6 +96,7 @@ struct svo_ctx {
     size_t off_left[SVO_MAX_LEVELS], off_right0, off_lk[SVO_LK_LEVELS];
     int lw[SVO_MAX_LEVELS], lh[SVO_MAX_LEVELS], lkw[SVO_LK_LEVELS], lkh[SVO_LK_LEVELS], lkpitch[SVO_LK_LEVELS];
     std::vector<Slot> slots;
+    SlotArena *arena = nullptr;
     uint8_t *h_stage[2] = {nullptr, nullptr};  // pinned upload staging (double buffered)
     int stage_idx = 0;
     // keyframe tables
@@ -78,7 +131,7 @@ struct svo_ctx {
     bool use_graphs = true;
     bool use_ingest = true;   // SM-driven frame ingest instead of copy-engine DMA (SVO_NO_INGEST=1 turns it off)
     unsigned long long graph_clock = 0;
-    long long graph_launches = 0, graph_captures = 0;
+    long long graph_launches = 0, graph_captures = 0, graph_updates = 0;
     float stage_ms[8] = {0};
     // EuRoC rectification in front of the pyramid build (euroc_input.cpp:48-49, :69-73); [0] = left, [1] = right input
     float *d_rect_map[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
@@ -141,6 +194,7 @@ extern "C" int svo_device_count(void)
 
 extern "C" const char *svo_last_error(svo_ctx *ctx) { return ctx ? ctx->err : g_create_err; }
 
+static int alloc_slot(svo_ctx *ctx, int *slot_out);
 static int fail_create(svo_ctx *ctx, int code, const char *msg)
 {
     snprintf(g_create_err, sizeof(g_create_err), "%s", msg);
@@ -218,6 +272,12 @@ extern "C" int svo_ctx_create(const svo_camera_settings *s, int device, int widt
         w = (w + 1) / 2; h = (h + 1) / 2;
     }
     ctx->slot_bytes = o;
+    ctx->arena = arena_get(device, ctx->slot_bytes);
+    {   // two frame slots + the first keyframes up front: steady-state tracking never allocates
+        int ids[6];
+        for (int k = 0; k < 6; k++) { int rc0 = alloc_slot(ctx, &ids[k]); if (rc0) return fail_create(ctx, rc0, ctx->err); }
+        for (int k = 0; k < 6; k++) ctx->slots[ids[k]].refcount = 0;
+    }
     for (int k = 0; k < 2; k++) CKC(cudaMallocHost(&ctx->h_stage[k], (size_t)2 * width * height));
     make_layout(ctx->lay, ctx->max_kps);
     CKC(cudaMalloc(&ctx->d_io, ctx->lay.total));
@@ -245,7 +305,10 @@ extern "C" int svo_ctx_destroy(svo_ctx *ctx)
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (auto &g : ctx->graphs) destroy_graph(g);
-    for (auto &s : ctx->slots) if (s.base) cudaFree(s.base);
+    if (ctx->arena) {
+        for (auto &s : ctx->slots) if (s.base) arena_give(ctx->arena, s.base);
+        arena_release(ctx->arena);
+    }
     for (int k = 0; k < 2; k++) if (ctx->h_stage[k]) cudaFreeHost(ctx->h_stage[k]);
     if (ctx->d_io) cudaFree(ctx->d_io);
     if (ctx->h_io) cudaFreeHost(ctx->h_io);
@@ -287,8 +350,7 @@ static int alloc_slot(svo_ctx *ctx, int *slot_out)
         if (ctx->slots[i].refcount == 0) { id = (int)i; break; }
     if (id < 0) {
         Slot s;
-        CK(cudaMalloc(&s.base, ctx->slot_bytes));
-        CK(cudaMemsetAsync(s.base, 0, ctx->slot_bytes, ctx->stream));
+        CK(arena_take(ctx->arena, &s.base));
         ImageSetDev &d = s.dev;
         d.n_levels = ctx->n_levels;
         for (int l = 0; l < SVO_MAX_LEVELS; l++) d.left[l] = LevelDesc{nullptr, 0, 0, 0};
@@ -1031,7 +1093,7 @@ static void destroy_graph(svo_ctx::FrameGraph &g)
     g.exec = nullptr;
 }
 
-static int capture_frame_graph(svo_ctx *ctx, svo_ctx::FrameGraph &g, int n)
+static int capture_frame_graph(svo_ctx *ctx, svo_ctx::FrameGraph &g, int n, cudaGraph_t *graph_out)
 {
     cudaGraph_t graph = nullptr;
     Slot &s = ctx->slots[g.cur_slot];
@@ -1043,9 +1105,7 @@ static int capture_frame_graph(svo_ctx *ctx, svo_ctx::FrameGraph &g, int n)
     if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
     CK(e);
     g.launches = launches + frame_pyr_launches(ctx, s);
-    CK(cudaGraphInstantiate(&g.exec, graph, 0));
-    cudaGraphDestroy(graph);
-    ctx->graph_captures++;
+    *graph_out = graph;
     return SVO_OK;
 }
 
@@ -1094,9 +1154,32 @@ extern "C" int svo_frame_begin(svo_ctx *ctx, const uint8_t *left, size_t ls, con
     if ((rc = enqueue_upload(ctx, ctx->slots[cur], left, ls, right, rs, src_kind, true))) return rc;
     const double tt2 = g_trace ? now_ms() : 0;
     const int bucket = std::min(ctx->max_kps, (n + 127) / 128 * 128);
+    // one executable graph per (previous, current) image-set pair; when the keypoint count moves to another grid-size
+    // bucket the sequence is re-captured (cheap) and the executable is UPDATED in place (cudaGraphExecUpdate: same
+    // topology, new grid sizes) — no instantiation, hence no device allocation, after the first two tracking frames
     svo_ctx::FrameGraph *g = nullptr;
     for (auto &c : ctx->graphs)
-        if (c.exec && c.prev_slot == prev_slot && c.cur_slot == cur && c.bucket == bucket) { g = &c; break; }
+        if (c.exec && c.prev_slot == prev_slot && c.cur_slot == cur) { g = &c; break; }
+    if (g && g->bucket != bucket) {
+        svo_ctx::FrameGraph ng = *g;
+        ng.bucket = bucket; ng.exec = nullptr;
+        cudaGraph_t graph = nullptr;
+        if ((rc = capture_frame_graph(ctx, ng, n, &graph))) return rc;
+        cudaGraphExecUpdateResultInfo info;
+        cudaError_t ue = cudaGraphExecUpdate(g->exec, graph, &info);
+        if (ue == cudaSuccess) {
+            g->bucket = bucket; g->launches = ng.launches;
+            ctx->graph_updates++;
+        } else {
+            cudaGetLastError();
+            destroy_graph(*g);
+            CK(cudaGraphInstantiate(&g->exec, graph, 0));
+            g->bucket = bucket; g->launches = ng.launches;
+            ctx->graph_captures++;
+        }
+        cudaGraphDestroy(graph);
+        if (g_trace) fprintf(stderr, "[graph] update prev %d cur %d bucket %d (%s)\n", prev_slot, cur, bucket, ue == cudaSuccess ? "in place" : "re-instantiated");
+    }
     if (!g) {
         if (ctx->graphs.size() >= 12) {  // evict the least recently used
             size_t v = 0;
@@ -1107,8 +1190,13 @@ extern "C" int svo_frame_begin(svo_ctx *ctx, const uint8_t *left, size_t ls, con
         svo_ctx::FrameGraph ng;
         ng.prev_slot = prev_slot; ng.cur_slot = cur; ng.bucket = bucket; ng.src_kind = src_kind; ng.stage_idx = stage_idx;
         ng.exec = nullptr; ng.left_copy = ng.right_copy = nullptr; ng.last_use = 0; ng.launches = 0;
-        if ((rc = capture_frame_graph(ctx, ng, n))) return rc;
-        if (getenv("SVO_TRACE_KF")) fprintf(stderr, "[graph] capture prev %d cur %d bucket %d (cache %zu)\n", prev_slot, cur, bucket, ctx->graphs.size());
+        cudaGraph_t graph = nullptr;
+        if ((rc = capture_frame_graph(ctx, ng, n, &graph))) return rc;
+        cudaError_t ie = cudaGraphInstantiate(&ng.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        CK(ie);
+        ctx->graph_captures++;
+        if (g_trace) fprintf(stderr, "[graph] capture prev %d cur %d bucket %d (cache %zu)\n", prev_slot, cur, bucket, ctx->graphs.size());
         ctx->graphs.push_back(ng);
         g = &ctx->graphs.back();
     }
