@@ -201,6 +201,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--streams", type=int, default=16, help="independent sequences per GPU")
     ap.add_argument("--host-threads", type=int, default=4, help="host threads driving the sequences of one GPU")
+    ap.add_argument("--align-cluster", type=int, default=2, choices=[1, 2, 4, 8],
+                    help="SMs per alignment solve in the multi-sequence runs (the single-sequence latency run always uses 8)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
@@ -266,6 +268,8 @@ def main():
 
     def run(mode, clocks=None):
         slams = [StereoSlam(settings, W_, H_, device=local_rank) for _ in range(S)]
+        for sl in slams:   # many sequences share the GPU: SM time per frame matters, not the latency of one solve
+            sl.set_align_cluster(a.align_cluster)
         hptr = host.data_ptr()
         dptr = dev.data_ptr()
         img = H_ * W_

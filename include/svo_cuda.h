@@ -182,6 +182,11 @@ int svo_track_frame(svo_ctx *ctx, int prev_slot, int cur_slot, svo_track_io *io)
  * on_device != 0: left/right are device pointers. */
 int svo_frame_begin(svo_ctx *ctx, const uint8_t *left, size_t left_stride, const uint8_t *right, size_t right_stride,
                     int on_device, int prev_slot, svo_track_io *io, int *cur_slot_out);
+/* Number of SMs (CTAs of one thread-block cluster: 1, 2, 4 or 8) that share the alignment solve of a frame.  8 (default)
+ * minimises the latency of one sequence; 1 or 2 minimise the SM time per frame, which is what bounds the aggregate
+ * throughput when many sequences share the GPU.  Results agree within the pose tolerance (the cross-keypoint sums
+ * are grouped differently), each setting is deterministic.  Env SVO_ALIGN_CLUSTER sets the default. */
+int svo_set_align_cluster(svo_ctx *ctx, int ctas);
 /* CUDA-graph replay on/off (default on; env SVO_NO_GRAPHS=1 turns it off); counters for tests */
 int svo_set_graphs(svo_ctx *ctx, int on);
 int svo_graph_stats(svo_ctx *ctx, long long *graph_launches, long long *graph_captures);
@@ -205,6 +210,9 @@ int svo_sync(svo_ctx *ctx);
  * out16[15] = stamps enqueued by the host, [16..63] = record of a barrier wait of the alignment kernel that timed out;
  * all -1 when the aid is off */
 int svo_debug_marks(svo_ctx *ctx, int *out64);
+/* developer probe: bandwidth (GB/s) at which `ctas` CTAs of 256 threads read page-locked host memory over PCIe with the
+ * access pattern of the frame-ingest kernel (16-byte loads) — the e2e roofline of zero-copy ingest */
+int svo_debug_zero_copy_bandwidth(svo_ctx *ctx, const void *pinned_host, size_t bytes, int ctas, int reps, float *gb_per_s);
 
 /* ================================================================== host facade ================ */
 /* StereoSlam (src/include/stereo_slam.hpp:27-79) with plain-C types. */

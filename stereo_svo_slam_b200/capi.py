@@ -153,6 +153,10 @@ class Context:
         self._ck(lib().svo_rectification_maps(self.h_ctx, which, _p(m1), _p(m2)))
         return m1, m2
 
+    def set_align_cluster(self, ctas):
+        """SMs sharing the alignment solve of a frame: 8 = lowest latency (default), 1-2 = lowest SM time per frame."""
+        self._ck(lib().svo_set_align_cluster(self.h_ctx, ctas))
+
     def release(self, slot):
         self._ck(lib().svo_slot_release(self.h_ctx, slot))
 

@@ -19,10 +19,9 @@
 // Bound: dependency latency (serial evaluations) and shared-memory/ALU throughput, not HBM.
 #include "kernels.cuh"
 
-#define CL 8                 // CTAs per cluster = SMs cooperating on one frame
+#define CLMAX 8              // largest cluster: CTAs (= SMs) cooperating on one frame; the kernel is instantiated for 1, 2, 4, 8
 #define ALIGN_THREADS 256    // per CTA: 8 warps x 8 keypoints x 4 patch rows
 #define ALIGN_WARPS (ALIGN_THREADS / 32)
-#define KPS_PER_PASS (CL * ALIGN_WARPS * 8)
 #define NGRAD 27             // 21 (H upper triangle) + 6 (b)
 
 struct AlignHdr {
@@ -30,9 +29,9 @@ struct AlignHdr {
     unsigned long long xbar[3];            // DSMEM exchange barriers: cost (two, alternating) and gradient
     double Rd[18][9];                      // Rodrigues(-r): two tables of 8 step sizes (k = 2^-j) + 2 spare slots, see rd_slot()
     double warp_cost[ALIGN_WARPS];         // this CTA's per-warp cost partials
-    double cl_cost[2][CL];                 // per-CTA cost partials of the whole cluster (written through DSMEM), double buffered
+    double cl_cost[2][CLMAX];                 // per-CTA cost partials of the whole cluster (written through DSMEM), double buffered
     float warp_grad[ALIGN_WARPS][NGRAD];   // this CTA's per-warp partials of H (21) and b (6)
-    double cl_grad[CL][NGRAD];             // per-CTA partials of the whole cluster (written through DSMEM)
+    double cl_grad[CLMAX][NGRAD];             // per-CTA partials of the whole cluster (written through DSMEM)
     double red_out[NGRAD];
     float grad[6];
     int n;
@@ -300,9 +299,10 @@ __device__ bool solve6(const double *Hu /*21 upper-tri row-major*/, const double
 
 // One thread-block CLUSTER (8 CTAs x 256 threads) = one frame.  Four lanes share a keypoint: lane r of the quad owns
 // row r of its 4x4 patch.  kSmem: level images staged in every CTA's shared memory (TMA), else read via L1/L2.
-template <bool kSmem>
+template <bool kSmem, int CL>
 __global__ void __launch_bounds__(ALIGN_THREADS, 1) sparse_align_kernel(AlignArgs a)
 {
+    constexpr int KPS_PER_PASS = CL * ALIGN_WARPS * 8;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     AlignHdr *hdr = reinterpret_cast<AlignHdr *>(smem_raw);
     uint8_t *img_area = smem_raw + HDR_BYTES;
@@ -659,14 +659,16 @@ size_t align_scratch_floats(int max_kps) { return (size_t)13 * 4 * max_kps; }
 
 cudaError_t align_init_device()
 {
-    cudaError_t e = cudaFuncSetAttribute(sparse_align_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    cudaError_t e = cudaSuccess;
+#define ALIGN_OPT_IN(c) if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_kernel<true, c>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024))
+    ALIGN_OPT_IN(1); ALIGN_OPT_IN(2); ALIGN_OPT_IN(4); ALIGN_OPT_IN(8);
+#undef ALIGN_OPT_IN
     return e;
 }
 
-cudaError_t launch_align(const AlignArgs &a, cudaStream_t st)
+template <int CL>
+static cudaError_t launch_align_cl(const AlignArgs &a, bool fit, size_t need, cudaStream_t st)
 {
-    size_t need;
-    bool fit = align_levels_fit(a, need);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(CL, 1, 1);
     cfg.blockDim = dim3(ALIGN_THREADS, 1, 1);
@@ -677,6 +679,21 @@ cudaError_t launch_align(const AlignArgs &a, cudaStream_t st)
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (fit) return cudaLaunchKernelEx(&cfg, sparse_align_kernel<true>, a);
-    return cudaLaunchKernelEx(&cfg, sparse_align_kernel<false>, a);
+    if (fit) return cudaLaunchKernelEx(&cfg, sparse_align_kernel<true, CL>, a);
+    return cudaLaunchKernelEx(&cfg, sparse_align_kernel<false, CL>, a);
+}
+
+// cluster = number of SMs that share one frame's solve: 8 minimises the latency of a single sequence (75 us), 1-2
+// minimise the SM time per frame when many sequences are in flight (the solve is a chain of ~28 dependent evaluations,
+// so SMs x duration is what a frame costs the GPU)
+cudaError_t launch_align(const AlignArgs &a, cudaStream_t st)
+{
+    size_t need;
+    bool fit = align_levels_fit(a, need);
+    switch (a.cluster) {
+    case 1: return launch_align_cl<1>(a, fit, need, st);
+    case 2: return launch_align_cl<2>(a, fit, need, st);
+    case 4: return launch_align_cl<4>(a, fit, need, st);
+    default: return launch_align_cl<8>(a, fit, need, st);
+    }
 }

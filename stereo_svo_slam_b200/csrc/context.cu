@@ -129,6 +129,7 @@ struct svo_ctx {
     };
     std::vector<FrameGraph> graphs;
     bool use_graphs = true;
+    int align_cluster = 8;    // SMs per alignment solve (svo_set_align_cluster)
     bool use_ingest = true;   // SM-driven frame ingest instead of copy-engine DMA (SVO_NO_INGEST=1 turns it off)
     unsigned long long graph_clock = 0;
     long long graph_launches = 0, graph_captures = 0, graph_updates = 0;
@@ -141,6 +142,17 @@ struct svo_ctx {
     int mark_seq = 0;
     char err[256];
 };
+
+// diagnostic (tools/ only): SVO_DIAG_DUP=<stage>:<count> repeats an idempotent stage of the frame sequence so that its
+// marginal GPU cost at saturation can be read off the throughput (stages: pyr, align, klt, refine, ssd)
+static int diag_dup(const char *stage)
+{
+    static const char *env = getenv("SVO_DIAG_DUP");
+    if (!env) return 0;
+    const size_t l = strlen(stage);
+    if (strncmp(env, stage, l) == 0 && env[l] == ':') return atoi(env + l + 1);
+    return 0;
+}
 
 static void mark(svo_ctx *ctx, int id)
 {
@@ -225,6 +237,10 @@ extern "C" int svo_ctx_create(const svo_camera_settings *s, int device, int widt
     ctx->n_levels = s->max_pyramid_levels;
     ctx->use_graphs = getenv("SVO_NO_GRAPHS") == nullptr;
     ctx->use_ingest = getenv("SVO_NO_INGEST") == nullptr;
+    if (getenv("SVO_ALIGN_CLUSTER")) {
+        const int c = atoi(getenv("SVO_ALIGN_CLUSTER"));
+        if (c == 1 || c == 2 || c == 4 || c == 8) ctx->align_cluster = c;
+    }
     if (getenv("SVO_DEBUG_MARKS")) {
         if (cudaHostAlloc(&ctx->h_marks, 64 * sizeof(int), cudaHostAllocMapped) == cudaSuccess) {
             memset(ctx->h_marks, 0, 64 * sizeof(int));
@@ -454,8 +470,10 @@ static int enqueue_pyramids(svo_ctx *ctx, Slot &s)
         ra.w = ra.sw = ctx->W; ra.h = ra.sh = ctx->H; ra.dpitch = ra.spitch = ctx->W;
         launch_remap(ra, ctx->stream);
     }
-    launch_pyr_halfsample(s.dev, ctx->stream);
-    launch_lk_pyramid(s.dev, ctx->stream);
+    for (int k = 0; k <= diag_dup("pyr"); k++) {
+        launch_pyr_halfsample(s.dev, ctx->stream);
+        launch_lk_pyramid(s.dev, ctx->stream);
+    }
     mark(ctx, 3);
     CK(cudaGetLastError());
     return SVO_OK;
@@ -575,11 +593,42 @@ extern "C" int svo_rectification_maps(svo_ctx *ctx, int which, float *map1, floa
     return SVO_OK;
 }
 
+extern "C" int svo_debug_zero_copy_bandwidth(svo_ctx *ctx, const void *pinned_host, size_t bytes, int ctas, int reps, float *gb_per_s)
+{
+    if (!ctx || !pinned_host || !gb_per_s || bytes < 16 || ctas < 1 || reps < 1) return SVO_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    void *dp = nullptr, *dst = nullptr;
+    CK(cudaHostGetDevicePointer(&dp, const_cast<void *>(pinned_host), 0));
+    CK(cudaMalloc(&dst, bytes));
+    launch_copy16(dp, dst, bytes, ctas, ctx->stream);
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    for (int k = 0; k < reps; k++) launch_copy16(dp, dst, bytes, ctas, ctx->stream);
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    cudaFree(dst);
+    *gb_per_s = (float)((double)bytes * reps / (ms * 1e-3) / 1e9);
+    return SVO_OK;
+}
+
 extern "C" int svo_debug_marks(svo_ctx *ctx, int *out64)
 {
     if (!ctx || !out64) return SVO_ERR_INVALID;
     for (int k = 0; k < 64; k++) out64[k] = ctx->h_marks ? ((volatile int *)ctx->h_marks)[k] : -1;
     out64[15] = ctx->mark_seq;
+    return SVO_OK;
+}
+
+extern "C" int svo_set_align_cluster(svo_ctx *ctx, int ctas)
+{
+    if (!ctx || (ctas != 1 && ctas != 2 && ctas != 4 && ctas != 8)) return SVO_ERR_INVALID;
+    if (ctx->track_pending) { snprintf(ctx->err, sizeof(ctx->err), "svo_set_align_cluster while a frame is in flight"); return SVO_ERR_STATE; }
+    if (ctas != ctx->align_cluster) {
+        ctx->align_cluster = ctas;
+        for (auto &g : ctx->graphs) destroy_graph(g);   // captured sequences hold the old launch shape
+        ctx->graphs.clear();
+    }
     return SVO_OK;
 }
 
@@ -754,6 +803,7 @@ static void fill_align_args(svo_ctx *ctx, int prev_slot, int cur_slot, AlignArgs
     a.scratch = ctx->d_align_scratch; a.max_kps = ctx->max_kps; a.cam = ctx->cam;
     a.probe_level = -1; a.probe_grad = nullptr;
     a.dbg = ctx->d_marks ? ctx->d_marks + 16 : nullptr;
+    a.cluster = ctx->align_cluster;
     (void)n;
 }
 
@@ -1012,6 +1062,7 @@ static int enqueue_track(svo_ctx *ctx, int prev_slot, int cur_slot, int n, int g
     if (prof) CK(cudaEventRecord(ctx->sev[2], ctx->stream));
     mark(ctx, 4);
     CK(launch_align(aa, ctx->stream)); launches++;
+    for (int k = 0; k < diag_dup("align"); k++) CK(launch_align(aa, ctx->stream));
     mark(ctx, 5);
     if (prof) CK(cudaEventRecord(ctx->sev[3], ctx->stream));
     if (n > 0) {
@@ -1025,6 +1076,7 @@ static int enqueue_track(svo_ctx *ctx, int prev_slot, int cur_slot, int n, int g
         ka.flags = DP(uint8_t, flags); ka.kps2d_out = DP(float, kps2d_ref_in); ka.max_kps = grid_n; ka.cam = ctx->cam;
         ka.iters = DP(int, klt_iters);
         launch_klt(ka, ctx->stream); launches++;
+        for (int k = 0; k < diag_dup("klt"); k++) launch_klt(ka, ctx->stream);
         mark(ctx, 6);
     }
     if (prof) CK(cudaEventRecord(ctx->sev[4], ctx->stream));
@@ -1034,6 +1086,7 @@ static int enqueue_track(svo_ctx *ctx, int prev_slot, int cur_slot, int n, int g
     ra.pose_in = DP(float, pose_aligned); ra.pose_out = DP(float, pose_refined);
     ra.cost_out = DP(float, costs) + 1; ra.evals_out = DP(int, evals) + 16; ra.cam = ctx->cam;
     launch_refine(ra, ctx->stream); launches++;
+    for (int k = 0; k < diag_dup("refine"); k++) launch_refine(ra, ctx->stream);
     mark(ctx, 7);
     if (prof) CK(cudaEventRecord(ctx->sev[5], ctx->stream));
     if (n > 0) {
@@ -1043,10 +1096,7 @@ static int enqueue_track(svo_ctx *ctx, int prev_slot, int cur_slot, int n, int g
         sa.kps2d = DP(float, kps2d_ref_in); sa.n_ptr = DP(int, n); sa.mode = 1; sa.disparity = DP(float, disparity);
         sa.max_kps = grid_n; sa.cam = ctx->cam;
         launch_stereo_ssd(sa, ctx->stream); launches++;
-        {   // diagnostic (tools/ only): repeat the idempotent SSD launch to probe whether throughput is GPU-issue bound
-            static const int dup = getenv("SVO_DIAG_DUP_SSD") ? atoi(getenv("SVO_DIAG_DUP_SSD")) : 0;
-            for (int k = 0; k < dup; k++) { launch_stereo_ssd(sa, ctx->stream); launches++; }
-        }
+        for (int k = 0; k < diag_dup("ssd"); k++) { launch_stereo_ssd(sa, ctx->stream); launches++; }
         if (prof) CK(cudaEventRecord(ctx->sev[6], ctx->stream));
         FilterArgs fa;
         fa.kf_pose_table = ctx->d_kf_pose; fa.keyframe_ids = DP(int, kf_id); fa.disparity = DP(float, disparity);

@@ -26,6 +26,7 @@ struct IngestArgs {
 };
 bool ingest_supported(const IngestArgs &a);
 void launch_ingest(const IngestArgs &a, cudaStream_t st);
+void launch_copy16(const void *src, void *dst, size_t bytes, int ctas, cudaStream_t st);
 
 // ---- rectify.cu (EuRoC front end, euroc_input.cpp:48-49, :69-73)
 struct RectifyMapArgs {
@@ -61,6 +62,7 @@ struct AlignArgs {
     // probe mode: single level, single evaluation
     int probe_level;       // -1 = normal
     float *probe_grad;     // 6
+    int cluster;           // CTAs (SMs) cooperating on the frame: 1, 2, 4 or 8
     int *dbg;              // developer aid (SVO_DEBUG_MARKS): where a stuck barrier wait was, else null
 };
 cudaError_t launch_align(const AlignArgs &a, cudaStream_t st);

@@ -497,7 +497,7 @@ __device__ __forceinline__ long long warp_sum_i32_exact(int v)
     return ((long long)shi << 16) + (long long)slo;
 }
 
-__global__ void __launch_bounds__(32 * KLTW_WARPS) klt31w_kernel(KltArgs a)
+__global__ void __launch_bounds__(32 * KLTW_WARPS, 4) klt31w_kernel(KltArgs a)
 {
     __shared__ KltWarpShared smw[KLTW_WARPS];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;

@@ -133,18 +133,35 @@ void launch_lk_pyramid(const ImageSetDev &s, cudaStream_t st)
 // over PCIe (zero-copy; a 361 KB cudaMemcpyAsync costs ~25 us of copy-engine time, of which ~18 us is fixed overhead,
 // so two copies per frame cap one engine at ~20 k frames/s) or device memory — into level 0 of the image set (or into
 // the raw buffers of the rectifier).  One 16-byte load per thread, all 722 KB of a C3 pair in flight at once.
-__global__ void __launch_bounds__(256) ingest_kernel(IngestArgs a)
+#define INGEST_UNROLL 8   // independent 16-byte loads per thread: the bytes in flight come from few, fat threads, so a
+                          // kernel that sits ~20 us on PCIe latency holds ~1/8 of the thread slots a load-per-thread grid would
+__global__ void __launch_bounds__(128) ingest_kernel(IngestArgs a)
 {
     const int z = blockIdx.y;
     const uint8_t *__restrict__ src = z ? a.src[1] : a.src[0];
     uint8_t *__restrict__ dst = z ? a.dst[1] : a.dst[0];
     const size_t sp = z ? a.spitch[1] : a.spitch[0];
     const int c16 = a.w >> 4;                        // 16-byte chunks per row
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= c16 * a.h) return;
-    const int row = idx / c16, col = (idx - row * c16) << 4;
-    const uint4 v = __ldcs(reinterpret_cast<const uint4 *>(src + (size_t)row * sp + col));
-    *reinterpret_cast<uint4 *>(dst + (size_t)row * a.w + col) = v;
+    const int total = c16 * a.h;
+    // chunk k of this thread = base + k * blockDim.x: every load instruction of a warp covers 512 contiguous bytes
+    const int base = blockIdx.x * (blockDim.x * INGEST_UNROLL) + threadIdx.x;
+    uint4 v[INGEST_UNROLL];
+#pragma unroll
+    for (int k = 0; k < INGEST_UNROLL; k++) {
+        const int idx = base + k * blockDim.x;
+        if (idx < total) {
+            const int row = idx / c16, col = (idx - row * c16) << 4;
+            v[k] = __ldcs(reinterpret_cast<const uint4 *>(src + (size_t)row * sp + col));
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < INGEST_UNROLL; k++) {
+        const int idx = base + k * blockDim.x;
+        if (idx < total) {
+            const int row = idx / c16, col = (idx - row * c16) << 4;
+            *reinterpret_cast<uint4 *>(dst + (size_t)row * a.w + col) = v[k];
+        }
+    }
 }
 
 bool ingest_supported(const IngestArgs &a)
@@ -158,8 +175,18 @@ bool ingest_supported(const IngestArgs &a)
 void launch_ingest(const IngestArgs &a, cudaStream_t st)
 {
     const int total = (a.w >> 4) * a.h;
-    dim3 grid((total + 255) / 256, 2);
-    ingest_kernel<<<grid, 256, 0, st>>>(a);
+    dim3 grid((total + 128 * INGEST_UNROLL - 1) / (128 * INGEST_UNROLL), 2);
+    ingest_kernel<<<grid, 128, 0, st>>>(a);
+}
+
+// developer probe: zero-copy read bandwidth of the SMs (same access pattern as ingest_kernel) over a large buffer
+__global__ void __launch_bounds__(256) copy16_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ dst, size_t n16)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) dst[i] = __ldcs(src + i);
+}
+void launch_copy16(const void *src, void *dst, size_t bytes, int ctas, cudaStream_t st)
+{
+    copy16_kernel<<<ctas, 256, 0, st>>>((const uint4 *)src, (uint4 *)dst, bytes / 16);
 }
 
 int pyr_launch_count(const ImageSetDev &s) { return (s.n_levels > 1 ? 1 : 0) + SVO_LK_LEVELS; }

@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(SSDC_THREADS) stereo_ssd_col_kernel(SsdArgs a,
 //     C[k][j] = sum_r sum_x Tz[r - k][x] * R[r][x + j]         (Tz = template, zero outside its th rows / tw columns)
 // is, for every ROI row r, a 16 x 32 (vertical position k, x) times 32 x 8 (x, horizontal position j) product
 // accumulated over r — exact in the integer tensor core (mma.sync m16n8k32 u8*u8 -> s32; sums stay < 2^26).
-// One WARP owns one keypoint:
+// Stages (the kernel below gives one keypoint to four warps):
 //   * staging: lane = image row; a lane reads its row as aligned words, realigns it with funnel shifts and writes the
 //     ROI four times, shifted by 0..3 bytes, so that every B fragment (4 consecutive bytes at ANY byte offset x + j)
 //     is one aligned, conflict-free LDS.32.  The same pass leaves the running sum of squares of the row in shared
@@ -329,9 +329,10 @@ __global__ void __launch_bounds__(SSDC_THREADS) stereo_ssd_col_kernel(SsdArgs a,
 // ~2.8 k warp instructions per keypoint instead of ~25 k for the byte-dot-product kernel below.
 // ---------------------------------------------------------------------------------------------------------
 #define SSDM_TP 12    // template row pitch (words): rows r-g, g = 0..7 land in distinct banks
-#define SSDM_CP 24    // pitch of one shifted ROI copy (words); 4 copies + 1 pad word per ROI row
-#define SSDM_RPW (4 * SSDM_CP + 1)
+#define SSDM_CP 24    // pitch of one shifted ROI copy (words); 4 copies + 2 pad words per ROI row
+#define SSDM_RPW (4 * SSDM_CP + 2)
 #define SSDM_TPAD 15  // zero rows above the template (k up to 15)
+#define SSDM_THREADS 128
 
 __device__ __forceinline__ void mma_u8_16832(int (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1)
 {
@@ -340,25 +341,34 @@ __device__ __forceinline__ void mma_u8_16832(int (&d)[4], uint32_t a0, uint32_t 
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
+// Four warps own one keypoint (the ~38 KB of staged data is what limits how many keypoints an SM holds, so the time a
+// keypoint keeps it is what counts): staging is split over (ROI row, row half) pairs, the sum-b^2 pass runs in warps
+// 0-1 while warps 2-3 already issue their MMA tiles, the tiles of 8 horizontal positions are dealt out two per warp.
 template <int NT>
-__global__ void __launch_bounds__(32) stereo_ssd_mma_kernel(SsdArgs a, int roi_rows)
+__global__ void __launch_bounds__(SSDM_THREADS) stereo_ssd_mma_kernel(SsdArgs a, int roi_rows)
 {
     extern __shared__ __align__(16) uint32_t ssd_smem32[];
-    constexpr int PP = 8 * NT + 33;               // pitch of the prefix-of-squares rows (odd)
+    constexpr int PP = 8 * NT + 33;               // pitch of the prefix-of-squares rows
+    constexpr int NW = 2 * NT + 8;                // words of a shifted copy any fragment can touch: (g>>2) + 2nt + tig + 4 <= 2NT + 6
+    constexpr int HW = NW / 2;                    // ... per row half
+    constexpr int MT = (NT + 3) / 4;              // MMA tiles per warp
     const int win = a.cam.win_depth;
     uint32_t *tpl = ssd_smem32;                               // (SSDM_TPAD + roi_rows + 1) x SSDM_TP
     uint32_t *roi = tpl + (SSDM_TPAD + roi_rows + 1) * SSDM_TP;  // roi_rows x SSDM_RPW
     uint32_t *psq = roi + roi_rows * SSDM_RPW;                // roi_rows x PP
     uint32_t *sbb = psq + roi_rows * PP;                      // 16 x 8NT
+    __shared__ unsigned s_saa;
+    __shared__ unsigned long long s_best[SSDM_THREADS / 32];
+    __shared__ int s_cnt[SSDM_THREADS / 32], s_sum[SSDM_THREADS / 32];
 
     const int i = blockIdx.x;
     const int n = min(*a.n_ptr, a.max_kps);
     if (i >= n) return;
-    const int lane = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const LevelDesc L = a.left0, R = a.right0;
     SsdGeom g;
-    if (!ssd_geometry(a.kps2d[2 * i], a.kps2d[2 * i + 1], L.w, L.h, win, a.cam.search_x, a.cam.search_y, a.mode, g)) {
-        if (lane == 0) a.disparity[i] = -1.f;
+    if (!ssd_geometry(a.kps2d[2 * i], a.kps2d[2 * i + 1], L.w, L.h, win, a.cam.search_x, a.cam.search_y, a.mode, g)) {   // CTA uniform
+        if (tid == 0) a.disparity[i] = -1.f;
         return;
     }
     const int tw = g.x12 - g.x11, th = g.y12 - g.y11, rw = g.x22 - g.x21, rh = g.y22 - g.y21;
@@ -366,113 +376,130 @@ __global__ void __launch_bounds__(32) stereo_ssd_mma_kernel(SsdArgs a, int roi_r
     const uint32_t last_mask = (tw & 3) ? ((1u << ((tw & 3) * 8)) - 1u) : 0xffffffffu;
     const int twords = (tw + 3) >> 2;
 
-    // ---- template: zero frame, then lane = template row
-    for (int k = lane; k < (SSDM_TPAD + rh + 1) * SSDM_TP; k += 32) tpl[k] = 0;
-    __syncwarp();
-    unsigned saa = 0;
-    if (lane < th) {
-        const uint8_t *rowp = L.ptr + (size_t)(g.y11 + lane) * L.pitch + g.x11;
-        const uintptr_t addr = reinterpret_cast<uintptr_t>(rowp);
-        const uint32_t *base = reinterpret_cast<const uint32_t *>(addr & ~(uintptr_t)3);
-        const int sh = (int)(addr & 3) * 8;
-        uint32_t wv[9];
+    // ---- zero frame of the template
+    for (int k = tid; k < (SSDM_TPAD + rh + 1) * SSDM_TP; k += SSDM_THREADS) tpl[k] = 0;
+    __syncthreads();
+    if (warp == 3) {
+        // ---- template: lane = template row (th <= 32); this warp has no ROI rows to stage
+        unsigned saa = 0;
+        if (lane < th) {
+            const uint8_t *rowp = L.ptr + (size_t)(g.y11 + lane) * L.pitch + g.x11;
+            const uintptr_t addr = reinterpret_cast<uintptr_t>(rowp);
+            const uint32_t *base = reinterpret_cast<const uint32_t *>(addr & ~(uintptr_t)3);
+            const int sh = (int)(addr & 3) * 8;
+            uint32_t wv[9];
 #pragma unroll
-        for (int k = 0; k < 9; k++) wv[k] = base[k];
+            for (int k = 0; k < 9; k++) wv[k] = base[k];
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            uint32_t v = __funnelshift_r(wv[k], wv[k + 1], sh);
-            if (k == twords - 1) v &= last_mask;
-            if (k >= twords) v = 0;
-            tpl[(SSDM_TPAD + lane) * SSDM_TP + k] = v;
-            saa = __dp4a(v, v, saa);
-        }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) saa += __shfl_xor_sync(0xffffffffu, saa, o);
-
-    // ---- ROI: lane = ROI row (two passes when rh > 32)
-    constexpr int NW = 2 * NT + 8;               // copy words any fragment can touch: (g>>2) + 2nt + tig + 4 <= 2NT + 6
-    for (int r = lane; r < rh; r += 32) {
-        const uint8_t *rowp = R.ptr + (size_t)(g.y21 + r) * R.pitch + g.x21;
-        const uintptr_t addr = reinterpret_cast<uintptr_t>(rowp);
-        const uint32_t *base = reinterpret_cast<const uint32_t *>(addr & ~(uintptr_t)3);
-        const int sh = (int)(addr & 3) * 8;
-        const int wlast = ((int)(addr & 3) + rw - 1) >> 2;   // last aligned word holding a byte of the ROI row
-        uint32_t v0[NW + 1];
-        {
-            uint32_t w0 = base[0];
-#pragma unroll
-            for (int k = 0; k < NW + 1; k++) {
-                const uint32_t w1 = base[min(k + 1, wlast)];
-                v0[k] = __funnelshift_r(w0, w1, sh);
-                w0 = w1;
+            for (int k = 0; k < 8; k++) {
+                uint32_t v = __funnelshift_r(wv[k], wv[k + 1], sh);
+                if (k == twords - 1) v &= last_mask;
+                if (k >= twords) v = 0;
+                tpl[(SSDM_TPAD + lane) * SSDM_TP + k] = v;
+                saa = __dp4a(v, v, saa);
             }
         }
-        uint32_t *dst = roi + r * SSDM_RPW;
 #pragma unroll
-        for (int k = 0; k < NW; k++) {
-            dst[k] = v0[k];
-            dst[SSDM_CP + k] = __funnelshift_r(v0[k], v0[k + 1], 8);
-            dst[2 * SSDM_CP + k] = __funnelshift_r(v0[k], v0[k + 1], 16);
-            dst[3 * SSDM_CP + k] = __funnelshift_r(v0[k], v0[k + 1], 24);
-        }
-        // exclusive prefix of squares along the row: psq[r][i] = sum_{i' < i} R[r][i']^2, i = 0 .. 8NT+31
-        uint32_t *pp = psq + r * PP;
-        unsigned acc = 0;
+        for (int o = 16; o > 0; o >>= 1) saa += __shfl_xor_sync(0xffffffffu, saa, o);
+        if (lane == 0) s_saa = saa;
+    } else {
+        // ---- ROI: thread = (row, half of the row); rows beyond 48 (never with the supported settings) loop
+        for (int it0 = 0; it0 < 2 * rh; it0 += 96) {   // warp-uniform trip count: the partner shuffle below needs every lane
+            const int item = it0 + tid;
+            const bool active = item < 2 * rh;
+            const int r = active ? (item >> 1) : 0, hf = item & 1;
+            const uint8_t *rowp = R.ptr + (size_t)(g.y21 + r) * R.pitch + g.x21;
+            const uintptr_t addr = reinterpret_cast<uintptr_t>(rowp);
+            const uint32_t *base = reinterpret_cast<const uint32_t *>(addr & ~(uintptr_t)3);
+            const int sh = (int)(addr & 3) * 8;
+            const int wlast = ((int)(addr & 3) + rw - 1) >> 2;   // last aligned word holding a byte of the ROI row
+            const int k0 = hf * HW;
+            uint32_t v0[HW + 1];                                 // bytes 4(k0+k) .. of the row, realigned
+            {
+                uint32_t w0 = base[min(k0, wlast)];
 #pragma unroll
-        for (int k = 0; k < 2 * NT + 8; k++) {
-#pragma unroll
-            for (int b = 0; b < 4; b++) {
-                pp[4 * k + b] = acc;
-                const unsigned px = (v0[k] >> (8 * b)) & 255u;
-                acc += px * px;
+                for (int k = 0; k < HW + 1; k++) {
+                    const uint32_t w1 = base[min(k0 + k + 1, wlast)];
+                    v0[k] = __funnelshift_r(w0, w1, sh);
+                    w0 = w1;
+                }
             }
-        }
-        pp[8 * NT + 32] = acc;
-    }
-    __syncwarp();
-
-    // ---- sum b^2 per search position: lane = horizontal position j, vertical sliding window over th rows
-    for (int j = lane; j < 8 * NT; j += 32) {
-        if (j < mw) {
-            unsigned v = 0;
-            for (int r = 0; r < th; r++) v += psq[r * PP + j + tw] - psq[r * PP + j];
-            sbb[j] = v;
-            for (int k = 1; k < mh; k++) {
-                v += psq[(k + th - 1) * PP + j + tw] - psq[(k + th - 1) * PP + j];
-                v -= psq[(k - 1) * PP + j + tw] - psq[(k - 1) * PP + j];
-                sbb[k * 8 * NT + j] = v;
+            uint32_t *dst = roi + r * SSDM_RPW + k0;
+#pragma unroll
+            for (int k = 0; k < HW; k++) {
+                if (!active) break;
+                dst[k] = v0[k];
+                dst[SSDM_CP + k] = __funnelshift_r(v0[k], v0[k + 1], 8);
+                dst[2 * SSDM_CP + k] = __funnelshift_r(v0[k], v0[k + 1], 16);
+                dst[3 * SSDM_CP + k] = __funnelshift_r(v0[k], v0[k + 1], 24);
             }
+            // exclusive prefix of squares along the row: psq[r][i] = sum_{i' < i} R[r][i']^2, i = 0 .. 4NW; the second half
+            // starts from the first half's total (its partner is the neighbouring lane)
+            unsigned tot = 0;
+#pragma unroll
+            for (int k = 0; k < HW; k++) tot = __dp4a(v0[k], v0[k], tot);
+            const unsigned left = __shfl_up_sync(0xffffffffu, tot, 1);
+            unsigned acc = hf ? left : 0u;
+            uint32_t *pp = psq + r * PP + 4 * k0;
+            if (!active) continue;
+#pragma unroll
+            for (int k = 0; k < HW; k++) {
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    pp[4 * k + b] = acc;
+                    const unsigned px = (v0[k] >> (8 * b)) & 255u;
+                    acc += px * px;
+                }
+            }
+            if (hf) pp[4 * HW] = acc;
+        }
+    }
+    __syncthreads();
+
+    // ---- sum b^2 per search position (warps 0-1: thread = horizontal position j, vertical sliding window over th rows)
+    if (tid < 8 * NT && tid < mw) {
+        const int j = tid;
+        unsigned v = 0;
+        for (int r = 0; r < th; r++) v += psq[r * PP + j + tw] - psq[r * PP + j];
+        sbb[j] = v;
+        for (int k = 1; k < mh; k++) {
+            v += psq[(k + th - 1) * PP + j + tw] - psq[(k + th - 1) * PP + j];
+            v -= psq[(k - 1) * PP + j + tw] - psq[(k - 1) * PP + j];
+            sbb[k * 8 * NT + j] = v;
         }
     }
 
-    // ---- cross term on the tensor core
+    // ---- cross term on the tensor core: warp w' = (warp + 2) & 3 owns tiles w' * MT .. w' * MT + MT - 1
     const int gid = lane >> 2, tig = lane & 3;
-    int acc[NT][4];
+    const int t0 = ((warp + 2) & 3) * MT;
+    int acc[MT][4];
 #pragma unroll
-    for (int t = 0; t < NT; t++) { acc[t][0] = 0; acc[t][1] = 0; acc[t][2] = 0; acc[t][3] = 0; }
-    const int ntiles = (mw + 7) >> 3;            // tiles holding at least one valid position (warp uniform)
-    const uint32_t *ta = tpl + (SSDM_TPAD - gid) * SSDM_TP + tig;
-    const uint32_t *rb = roi + (gid & 3) * SSDM_CP + (gid >> 2) + tig;
-    for (int r = 0; r < rh; r++) {
-        const uint32_t a0 = ta[0], a2 = ta[4], a1 = ta[-8 * SSDM_TP], a3 = ta[-8 * SSDM_TP + 4];
+    for (int t = 0; t < MT; t++) { acc[t][0] = 0; acc[t][1] = 0; acc[t][2] = 0; acc[t][3] = 0; }
+    const int ntiles = min(NT, (mw + 7) >> 3);   // tiles holding at least one valid position (CTA uniform)
+    if (t0 < ntiles) {
+        const uint32_t *ta = tpl + (SSDM_TPAD - gid) * SSDM_TP + tig;
+        const uint32_t *rb = roi + (gid & 3) * SSDM_CP + (gid >> 2) + tig + 2 * t0;
+        for (int r = 0; r < rh; r++) {
+            const uint32_t a0 = ta[0], a2 = ta[4], a1 = ta[-8 * SSDM_TP], a3 = ta[-8 * SSDM_TP + 4];
 #pragma unroll
-        for (int t = 0; t < NT; t++) {
-            if (t < ntiles) mma_u8_16832(acc[t], a0, a1, a2, a3, rb[2 * t], rb[2 * t + 4]);
+            for (int t = 0; t < MT; t++) {
+                if (t0 + t < ntiles) mma_u8_16832(acc[t], a0, a1, a2, a3, rb[2 * t], rb[2 * t + 4]);
+            }
+            ta += SSDM_TP;
+            rb += SSDM_RPW;
         }
-        ta += SSDM_TP;
-        rb += SSDM_RPW;
     }
-    __syncwarp();
+    __syncthreads();
 
     // ---- SSD = sum a^2 + sum b^2 - 2 sum ab; arg-min by (value, raster index) == cv::minMaxLoc's first minimum
+    const unsigned saa = s_saa;
     unsigned long long best = ~0ull;
-    uint32_t sv[NT][4];
+    uint32_t sv[MT][4];
 #pragma unroll
-    for (int t = 0; t < NT; t++) {
+    for (int t = 0; t < MT; t++) {
 #pragma unroll
         for (int q = 0; q < 4; q++) {
-            const int k = gid + (q >> 1) * 8, j = 8 * t + 2 * tig + (q & 1);
+            const int k = gid + (q >> 1) * 8, j = 8 * (t0 + t) + 2 * tig + (q & 1);
             sv[t][q] = 0xffffffffu;
             if (k < mh && j < mw) {
                 const uint32_t v = saa + sbb[k * 8 * NT + j] - 2u * (uint32_t)acc[t][q];
@@ -487,23 +514,32 @@ __global__ void __launch_bounds__(32) stereo_ssd_mma_kernel(SsdArgs a, int roi_r
         const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
         best = other < best ? other : best;
     }
+    if (lane == 0) s_best[warp] = best;
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < SSDM_THREADS / 32; w++) best = s_best[w] < best ? s_best[w] : best;
     const uint32_t minv = (uint32_t)(best >> 32);
     const int mp = (int)(best & 0xffffffffu);
     const int mly = mp / mw, mlx = mp - mly * mw;
     // ---- tie rule (depth_calculator.cpp:226-237): mean column index of entries <= min right/below the first minimum
     int cnt = 0, sum = 0;
 #pragma unroll
-    for (int t = 0; t < NT; t++) {
+    for (int t = 0; t < MT; t++) {
 #pragma unroll
         for (int q = 0; q < 4; q++) {
-            const int k = gid + (q >> 1) * 8, j = 8 * t + 2 * tig + (q & 1);
+            const int k = gid + (q >> 1) * 8, j = 8 * (t0 + t) + 2 * tig + (q & 1);
             if (k < mh && j < mw && j >= mlx && k >= mly && sv[t][q] <= minv) { cnt++; sum += j; }
         }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { cnt += __shfl_xor_sync(0xffffffffu, cnt, o); sum += __shfl_xor_sync(0xffffffffu, sum, o); }
-    if (lane == 0) {
-        const float minPos = (float)sum / (float)cnt;  // float sum of small integers is exact
+    if (lane == 0) { s_cnt[warp] = cnt; s_sum[warp] = sum; }
+    __syncthreads();
+    if (tid == 0) {
+        int c = 0, sm = 0;
+#pragma unroll
+        for (int w = 0; w < SSDM_THREADS / 32; w++) { c += s_cnt[w]; sm += s_sum[w]; }
+        const float minPos = (float)sm / (float)c;  // float sum of small integers is exact
         a.disparity[i] = (a.mode == 1) ? fmaxf(0.5f, minPos) : minPos;
     }
 }
@@ -514,7 +550,7 @@ static void launch_ssd_mma(const SsdArgs &a, int roi_rows, cudaStream_t st)
     const size_t smem = ((size_t)(SSDM_TPAD + roi_rows + 1) * SSDM_TP + (size_t)roi_rows * SSDM_RPW + (size_t)roi_rows * (8 * NT + 33) +
                          (size_t)16 * 8 * NT) * 4;
     if (smem > 48 * 1024) cudaFuncSetAttribute(stereo_ssd_mma_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    stereo_ssd_mma_kernel<NT><<<a.max_kps, 32, smem, st>>>(a, roi_rows);
+    stereo_ssd_mma_kernel<NT><<<a.max_kps, SSDM_THREADS, smem, st>>>(a, roi_rows);
 }
 
 void launch_stereo_ssd(const SsdArgs &a, cudaStream_t st)

@@ -81,6 +81,11 @@ class StereoSlam:
             raise SvoError(capi.SVO_ERR_INVALID, "K, R: 3x3; D: 5 coefficients; P: 3x3 or 3x4")
         self._ck(capi.lib().svo_slam_set_rectification(self._h, which, *[x.ctypes.data_as(C.c_void_p) for x in a]))
 
+    def set_align_cluster(self, ctas):
+        """Latency/throughput knob of the alignment kernel (svo_set_align_cluster): 8 SMs per frame for one live sequence,
+        1-2 when many sequences share the GPU."""
+        self.context().set_align_cluster(ctas)
+
     # ---- StereoSlam::new_image (stereo_slam.cpp:123)
     def new_image(self, left, right, time_stamp):
         left, right = self._img(left), self._img(right)

@@ -223,11 +223,12 @@ def _keypoints_with_depth(seq, c, k, L, ocs):
     return xy.astype(np.float32), np.array(P, np.float32)
 
 
-@pytest.mark.parametrize("cfg", ["S", "C3"])
-def test_align_probe_and_solve(cfg):
+@pytest.mark.parametrize("cfg,cluster", [("S", 8), ("C3", 8), ("C3", 4), ("C3", 2), ("C3", 1), ("S", 1)])
+def test_align_probe_and_solve(cfg, cluster):
     gcs, ocs = mk(cfg)
     seq, c, (L0, R0), (L1, R1) = _scene(cfg, 3, 4)
     ctx = capi.Context(gcs, c["width"], c["height"])
+    ctx.set_align_cluster(cluster)
     s0, s1 = ctx.upload(L0, R0), ctx.upload(L1, R1)
     k2, k3 = _keypoints_with_depth(seq, c, 3, L0, ocs)
     pose0 = seq.pose(3).astype(np.float32)
@@ -354,14 +355,15 @@ def test_track_frame_teacher_forced(cfg, frames):
 
 
 # ----------------------------------------------------------------------------------------------- whole pipeline
-@pytest.mark.parametrize("cfg,frames", [("S", 30), ("C3", 12)])
-def test_slam_free_running_matches_oracle(cfg, frames):
+@pytest.mark.parametrize("cfg,frames,cluster", [("S", 30, 8), ("C3", 12, 8), ("C3", 12, 2), ("C3", 12, 1)])
+def test_slam_free_running_matches_oracle(cfg, frames, cluster):
     from stereo_svo_slam_b200 import StereoSlam
     gcs, ocs = mk(cfg)
     c = synth.CONFIGS[cfg]
     seq = synth.make_sequence(cfg)
     o = orc.OracleSlam(ocs, c["width"], c["height"], tracing=False)
     g = StereoSlam(gcs, c["width"], c["height"])
+    g.set_align_cluster(cluster)
     assert g.get_frame() is None
     worst_t = worst_r = 0.0
     for k in range(frames):
