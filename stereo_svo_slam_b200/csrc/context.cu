@@ -24,19 +24,19 @@ __global__ void mark_kernel(volatile int *p, int slot, int v) { p[slot] = v; p[0
 // stream of the process for milliseconds (tens to hundreds of ms with 32 sequences in flight).
 #include <mutex>
 struct SlotArena {
-    int device; size_t slot_bytes; int users;
+    int device; size_t slot_bytes; long long geom; int users;   // geom: image size and level count (same layout => zero frames stay valid)
     std::vector<uint8_t *> chunks, free_list;
 };
 static std::mutex g_arena_mu;
 static std::vector<SlotArena *> g_arenas;
 #define ARENA_CHUNK_SLOTS 32
 
-static SlotArena *arena_get(int device, size_t slot_bytes)
+static SlotArena *arena_get(int device, size_t slot_bytes, long long geom)
 {
     std::lock_guard<std::mutex> lk(g_arena_mu);
     for (SlotArena *a : g_arenas)
-        if (a->device == device && a->slot_bytes == slot_bytes) { a->users++; return a; }
-    SlotArena *a = new SlotArena{device, slot_bytes, 1, {}, {}};
+        if (a->device == device && a->slot_bytes == slot_bytes && a->geom == geom) { a->users++; return a; }
+    SlotArena *a = new SlotArena{device, slot_bytes, geom, 1, {}, {}};
     g_arenas.push_back(a);
     return a;
 }
@@ -75,6 +75,7 @@ struct Slot {
     uint8_t *base = nullptr;
     ImageSetDev dev;
     int refcount = 0;
+    bool derivs_valid = false;   // lkd[] holds the Scharr derivatives of lk[]
 };
 
 // layout of the keypoint I/O block (same offsets on device and in the pinned host mirror)
@@ -93,7 +94,8 @@ struct svo_ctx {
     int W = 0, H = 0, max_kps = 0, n_levels = 0;
     // slot layout
     size_t slot_bytes = 0;
-    size_t off_left[SVO_MAX_LEVELS], off_right0, off_lk[SVO_LK_LEVELS];
+    size_t off_left[SVO_MAX_LEVELS], off_right0, off_lk[SVO_LK_LEVELS], off_lkd[SVO_LK_LEVELS], image_bytes;
+    int lkdpitch[SVO_LK_LEVELS];
     int lw[SVO_MAX_LEVELS], lh[SVO_MAX_LEVELS], lkw[SVO_LK_LEVELS], lkh[SVO_LK_LEVELS], lkpitch[SVO_LK_LEVELS];
     std::vector<Slot> slots;
     SlotArena *arena = nullptr;
@@ -237,6 +239,10 @@ extern "C" int svo_ctx_create(const svo_camera_settings *s, int device, int widt
     ctx->n_levels = s->max_pyramid_levels;
     ctx->use_graphs = getenv("SVO_NO_GRAPHS") == nullptr;
     ctx->use_ingest = getenv("SVO_NO_INGEST") == nullptr;
+    if (getenv("SVO_INGEST_MIX")) {   // developer experiment: every second context uploads by copy-engine DMA
+        static int counter = 0;
+        ctx->use_ingest = (counter++ & 1) == 0;
+    }
     if (getenv("SVO_ALIGN_CLUSTER")) {
         const int c = atoi(getenv("SVO_ALIGN_CLUSTER"));
         if (c == 1 || c == 2 || c == 4 || c == 8) ctx->align_cluster = c;
@@ -287,8 +293,14 @@ extern "C" int svo_ctx_create(const svo_camera_settings *s, int device, int widt
         o = align_up(o + (size_t)ctx->lkpitch[l] * (h + 2 * SVO_LK_PAD) + 16, 256);
         w = (w + 1) / 2; h = (h + 1) / 2;
     }
+    ctx->image_bytes = o;   // everything a keyframe copies; the derivative levels below are rebuilt from the copy
+    for (int l = 0; l < SVO_LK_LEVELS; l++) {
+        ctx->lkdpitch[l] = (int)align_up(((size_t)ctx->lkw[l] + 2 * SVO_LK_PAD) * 4, 16);
+        ctx->off_lkd[l] = o;
+        o = align_up(o + (size_t)ctx->lkdpitch[l] * (ctx->lkh[l] + 2 * SVO_LK_PAD) + 16, 256);
+    }
     ctx->slot_bytes = o;
-    ctx->arena = arena_get(device, ctx->slot_bytes);
+    ctx->arena = arena_get(device, ctx->slot_bytes, ((long long)width << 40) | ((long long)height << 16) | ctx->n_levels);
     {   // two frame slots + the first keyframes up front: steady-state tracking never allocates
         int ids[6];
         for (int k = 0; k < 6; k++) { int rc0 = alloc_slot(ctx, &ids[k]); if (rc0) return fail_create(ctx, rc0, ctx->err); }
@@ -308,7 +320,7 @@ extern "C" int svo_ctx_create(const svo_camera_settings *s, int device, int widt
     CKC(cudaMalloc(&ctx->d_cell_score, (size_t)ctx->cell_cap * 4));
     CKC(cudaMalloc(&ctx->d_cell_type, (size_t)ctx->cell_cap * 4));
     ctx->kf_cap = 64;
-    CKC(cudaMalloc(&ctx->d_kf_lk, (size_t)ctx->kf_cap * SVO_LK_LEVELS * sizeof(LevelDesc)));
+    CKC(cudaMalloc(&ctx->d_kf_lk, (size_t)ctx->kf_cap * 2 * SVO_LK_LEVELS * sizeof(LevelDesc)));
     CKC(cudaMalloc(&ctx->d_kf_pose, (size_t)ctx->kf_cap * 24 * sizeof(float)));
 #undef CKC
     *out = ctx;
@@ -374,11 +386,27 @@ static int alloc_slot(svo_ctx *ctx, int *slot_out)
         d.right0 = LevelDesc{s.base + ctx->off_right0, ctx->W, ctx->H, ctx->W};
         for (int l = 0; l < SVO_LK_LEVELS; l++)
             d.lk[l] = LevelDesc{s.base + ctx->off_lk[l] + (size_t)SVO_LK_PAD * ctx->lkpitch[l] + SVO_LK_PAD, ctx->lkw[l], ctx->lkh[l], ctx->lkpitch[l]};
+        for (int l = 0; l < SVO_LK_LEVELS; l++)   // the zero frame comes from the arena's one-off memset; only the interior is ever written
+            d.lkd[l] = LevelDesc{s.base + ctx->off_lkd[l] + (size_t)SVO_LK_PAD * ctx->lkdpitch[l] + (size_t)SVO_LK_PAD * 4, ctx->lkw[l], ctx->lkh[l], ctx->lkdpitch[l]};
         ctx->slots.push_back(s);
         id = (int)ctx->slots.size() - 1;
     }
     ctx->slots[id].refcount = 1;
+    ctx->slots[id].derivs_valid = false;
     *slot_out = id;
+    return SVO_OK;
+}
+
+// Scharr derivative levels of a slot (cv::buildOpticalFlowPyramid stores them next to every image level; here they
+// are only built for image sets that serve as the REFERENCE of an optical-flow call, i.e. keyframes)
+static int ensure_derivs(svo_ctx *ctx, int slot)
+{
+    Slot &s = ctx->slots[slot];
+    if (s.derivs_valid) return SVO_OK;
+    launch_lk_scharr(s.dev, ctx->stream);
+    ctx->launch_total += SVO_LK_LEVELS;
+    CK(cudaGetLastError());
+    s.derivs_valid = true;
     return SVO_OK;
 }
 
@@ -876,7 +904,8 @@ static int klt_common(svo_ctx *ctx, const int *keyframe_ids, int prev_slot, int 
         a.kf_lk_table = ctx->d_kf_lk;
         a.keyframe_ids = DP(int, kf_id);
     } else {
-        for (int l = 0; l < SVO_LK_LEVELS; l++) a.prev_fixed[l] = ctx->slots[prev_slot].dev.lk[l];
+        if ((rc = ensure_derivs(ctx, prev_slot))) return rc;
+        for (int l = 0; l < SVO_LK_LEVELS; l++) { a.prev_fixed[l] = ctx->slots[prev_slot].dev.lk[l]; a.prev_fixed_deriv[l] = ctx->slots[prev_slot].dev.lkd[l]; }
     }
     for (int l = 0; l < SVO_LK_LEVELS; l++) a.cur[l] = ctx->slots[cur_slot].dev.lk[l];
     a.prev_pts = DP(float, ref_kps2d); a.init_pts = DP(float, kps2d_ref_in);
@@ -978,10 +1007,10 @@ extern "C" int svo_keyframe_commit(svo_ctx *ctx, int slot, const float pose[6], 
         int ncap = ctx->kf_cap * 2;
         LevelDesc *nl;
         float *np;
-        CK(cudaMalloc(&nl, (size_t)ncap * SVO_LK_LEVELS * sizeof(LevelDesc)));
+        CK(cudaMalloc(&nl, (size_t)ncap * 2 * SVO_LK_LEVELS * sizeof(LevelDesc)));
         CK(cudaMalloc(&np, (size_t)ncap * 24 * sizeof(float)));
         CK(cudaStreamSynchronize(ctx->stream));
-        CK(cudaMemcpy(nl, ctx->d_kf_lk, (size_t)ctx->kf_cap * SVO_LK_LEVELS * sizeof(LevelDesc), cudaMemcpyDeviceToDevice));
+        CK(cudaMemcpy(nl, ctx->d_kf_lk, (size_t)ctx->kf_cap * 2 * SVO_LK_LEVELS * sizeof(LevelDesc), cudaMemcpyDeviceToDevice));
         CK(cudaMemcpy(np, ctx->d_kf_pose, (size_t)ctx->kf_cap * 24 * sizeof(float), cudaMemcpyDeviceToDevice));
         cudaFree(ctx->d_kf_lk); cudaFree(ctx->d_kf_pose);
         ctx->d_kf_lk = nl; ctx->d_kf_pose = np; ctx->kf_cap = ncap;
@@ -994,7 +1023,8 @@ extern "C" int svo_keyframe_commit(svo_ctx *ctx, int slot, const float pose[6], 
     {
         int rc2 = alloc_slot(ctx, &kslot);
         if (rc2) return rc2;
-        CK(cudaMemcpyAsync(ctx->slots[kslot].base, ctx->slots[slot].base, ctx->slot_bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->slots[kslot].base, ctx->slots[slot].base, ctx->image_bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+        if ((rc2 = ensure_derivs(ctx, kslot))) return rc2;
     }
     int id = ctx->kf_count;
     float rec[24];
@@ -1003,8 +1033,9 @@ extern "C" int svo_keyframe_commit(svo_ctx *ctx, int slot, const float pose[6], 
     host_rodrigues_f(rp, rec + 6);
     host_rodrigues_f(rn, rec + 15);
     CK(cudaMemcpyAsync(ctx->d_kf_pose + (size_t)id * 24, rec, sizeof(rec), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->d_kf_lk + (size_t)id * SVO_LK_LEVELS, ctx->slots[kslot].dev.lk, SVO_LK_LEVELS * sizeof(LevelDesc),
-                       cudaMemcpyHostToDevice, ctx->stream));
+    LevelDesc kfd[2 * SVO_LK_LEVELS];
+    for (int l = 0; l < SVO_LK_LEVELS; l++) { kfd[l] = ctx->slots[kslot].dev.lk[l]; kfd[SVO_LK_LEVELS + l] = ctx->slots[kslot].dev.lkd[l]; }
+    CK(cudaMemcpyAsync(ctx->d_kf_lk + (size_t)id * 2 * SVO_LK_LEVELS, kfd, sizeof(kfd), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));  // rec is on the stack
     slot = kslot;
     ctx->kf_slot.push_back(slot);

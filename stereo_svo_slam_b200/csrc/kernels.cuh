@@ -11,12 +11,16 @@ struct ImageSetDev {  // device view of one stereo frame ("slot")
     LevelDesc left[SVO_MAX_LEVELS];  // halfSample pyramid, pitch == w (contiguous rows)
     LevelDesc right0;
     LevelDesc lk[SVO_LK_LEVELS];     // LK pyramid, padded by SVO_LK_PAD px of REFLECT_101 border
+    LevelDesc lkd[SVO_LK_LEVELS];    // Scharr derivatives of the LK levels: (Ix, Iy) int16 pairs, 4 bytes per pixel, pitch in BYTES,
+                                     // SVO_LK_PAD px of zeros around (cv::buildOpticalFlowPyramid's deriv border is CONSTANT 0);
+                                     // filled on demand (keyframes), see launch_lk_scharr
     int n_levels;
 };
 
 // ---- pyramid.cu
 void launch_pyr_halfsample(const ImageSetDev &s, cudaStream_t st);
 void launch_lk_pyramid(const ImageSetDev &s, cudaStream_t st);
+void launch_lk_scharr(const ImageSetDev &s, cudaStream_t st);   // derivative images of the three LK levels
 int pyr_launch_count(const ImageSetDev &s);
 struct IngestArgs {
     const uint8_t *src[2];   // left / right source (device pointers: device memory or mapped page-locked host memory)
@@ -72,9 +76,10 @@ cudaError_t align_init_device();  // once per device: opt in to 227 KB dynamic s
 
 // ---- klt.cu
 struct KltArgs {
-    const LevelDesc *kf_lk_table;  // device table: [keyframe_id][SVO_LK_LEVELS]
+    const LevelDesc *kf_lk_table;  // device table: [keyframe_id][2 * SVO_LK_LEVELS]: image levels, then derivative levels
     const int *keyframe_ids;       // n (device) or null => use prev_fixed
     LevelDesc prev_fixed[SVO_LK_LEVELS];
+    LevelDesc prev_fixed_deriv[SVO_LK_LEVELS];
     LevelDesc cur[SVO_LK_LEVELS];
     const float *prev_pts;         // n*2 (keyframe coordinates)
     const float *init_pts;         // n*2 or null => project kps3d with *pose

@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(KLT_THREADS) klt_pyr_lk_kernel(KltArgs a)
     __syncthreads();
     const float init_x = sm.init[0], init_y = sm.init[1];
     const float ppx = a.prev_pts[2 * i], ppy = a.prev_pts[2 * i + 1];
-    const LevelDesc *prev_lv = a.keyframe_ids ? (a.kf_lk_table + (size_t)a.keyframe_ids[i] * SVO_LK_LEVELS) : a.prev_fixed;
+    const LevelDesc *prev_lv = a.keyframe_ids ? (a.kf_lk_table + (size_t)a.keyframe_ids[i] * 2 * SVO_LK_LEVELS) : a.prev_fixed;
 
     float nx = init_x, ny = init_y;  // nextPts[i]
     int status = 1;
@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(KLT_THREADS) klt31_kernel(KltArgs a)
     __syncthreads();
     const float init_x = sm.init[0], init_y = sm.init[1];
     const float ppx = a.prev_pts[2 * i], ppy = a.prev_pts[2 * i + 1];
-    const LevelDesc *prev_lv = a.keyframe_ids ? (a.kf_lk_table + (size_t)a.keyframe_ids[i] * SVO_LK_LEVELS) : a.prev_fixed;
+    const LevelDesc *prev_lv = a.keyframe_ids ? (a.kf_lk_table + (size_t)a.keyframe_ids[i] * 2 * SVO_LK_LEVELS) : a.prev_fixed;
 
     float nx = init_x, ny = init_y;
     int status = 1;
@@ -474,19 +474,15 @@ __global__ void __launch_bounds__(KLT_THREADS) klt31_kernel(KltArgs a)
 
 // ---------------------------------------------------------------------------------------------------------
 // Warp-per-keypoint kernel for the 31x31 window: lane l owns window row l for the whole level (31 template pixels
-// = Iw/Ix/Iy in registers), no block barrier anywhere.  Per LK iteration a lane fetches its 32-byte row of the next
-// image as aligned words (+ funnel shift), gets the row below from lane l+1 with shuffles, evaluates the Q14
-// bilinear taps two at a time on the 2-way 16x8-bit dot-product unit (IDP.2A: weights are <= 2^14, pixels 8 bit),
-// and the two window sums are reduced exactly with integer warp reductions (REDUX on 16-bit halves).  Every lane
-// then applies the 2x2 update redundantly.  4 keypoints per 128-thread CTA; the footprint per keypoint is one warp,
-// so kernels of many sequences overlap instead of queueing for CTA slots.
+// = Iw/Ix/Iy in registers), no block barrier and no shared memory anywhere.  The template is built from the keyframe's
+// image level and its Scharr derivative level (materialised once per keyframe, lk_scharr_kernel): a lane fetches its own
+// row and takes the row below from lane l+1 with shuffles.  Per LK iteration a lane fetches its 32-byte row of the next
+// image as aligned words (+ funnel shift), gets the row below the same way, evaluates the Q14 bilinear taps two at a time
+// on the 2-way 16x8-bit dot-product unit (IDP.2A: weights are <= 2^14, pixels 8 bit), and the two window sums are
+// reduced exactly with integer warp reductions (REDUX on 16-bit halves).  Every lane then applies the 2x2 update
+// redundantly.  4 keypoints per 128-thread CTA; the footprint per keypoint is one warp.
 // ---------------------------------------------------------------------------------------------------------
 #define KLTW_WARPS 4
-struct KltWarpShared {
-    __align__(16) uint8_t tile[34 * 36];
-    short gx[32 * 32];
-    short gy[32 * 32];
-};
 
 // exact warp-wide sum of a 32-bit signed value per lane (|v| < 2^31), returned as 64 bit to every lane
 __device__ __forceinline__ long long warp_sum_i32_exact(int v)
@@ -499,13 +495,11 @@ __device__ __forceinline__ long long warp_sum_i32_exact(int v)
 
 __global__ void __launch_bounds__(32 * KLTW_WARPS, 4) klt31w_kernel(KltArgs a)
 {
-    __shared__ KltWarpShared smw[KLTW_WARPS];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int i = blockIdx.x * KLTW_WARPS + wid;
     const int n = min(*a.n_ptr, a.max_kps);
     if (i >= n) return;   // whole warp exits together
-    KltWarpShared &sm = smw[wid];
-    constexpr int win = 31, T = 36, W1 = 32;   // tile rows padded to 36 bytes (9 words)
+    constexpr int win = 31;
     const float half = 15.0f;
     const bool have_row = lane < win;
 
@@ -519,7 +513,8 @@ __global__ void __launch_bounds__(32 * KLTW_WARPS, 4) klt31w_kernel(KltArgs a)
                     a.cam.k1, a.cam.k2, a.cam.p1, a.cam.p2, a.cam.k3, init_x, init_y);
     }
     const float ppx = a.prev_pts[2 * i], ppy = a.prev_pts[2 * i + 1];
-    const LevelDesc *prev_lv = a.keyframe_ids ? (a.kf_lk_table + (size_t)a.keyframe_ids[i] * SVO_LK_LEVELS) : a.prev_fixed;
+    const LevelDesc *prev_lv = a.keyframe_ids ? (a.kf_lk_table + (size_t)a.keyframe_ids[i] * 2 * SVO_LK_LEVELS) : a.prev_fixed;
+    const LevelDesc *prev_dv = a.keyframe_ids ? (prev_lv + SVO_LK_LEVELS) : a.prev_fixed_deriv;
 
     float nx = init_x, ny = init_y;
     int status = 1;
@@ -528,6 +523,7 @@ __global__ void __launch_bounds__(32 * KLTW_WARPS, 4) klt31w_kernel(KltArgs a)
 
     for (int level = SVO_LK_LEVELS - 1; level >= 0; level--) {
         const LevelDesc I = prev_lv[level];
+        const LevelDesc Dv = prev_dv[level];
         const LevelDesc J = a.cur[level];
         const float scale = (float)(1. / (1 << level));
         float px = ppx * scale, py = ppy * scale;
@@ -544,45 +540,33 @@ __global__ void __launch_bounds__(32 * KLTW_WARPS, 4) klt31w_kernel(KltArgs a)
         int iw00, iw01, iw10, iw11;
         lk_weights(px - (float)ipx, py - (float)ipy, iw00, iw01, iw10, iw11);
 
-        __syncwarp();
-        // stage the 34x34 tile: one row per lane (rows 32,33 by lanes 0,1) as 10 independent aligned word loads
-        for (int r = lane; r < 34; r += 32) {
-            const uint8_t *rowp = I.ptr + (ptrdiff_t)(ipy - 1 + r) * I.pitch + (ipx - 1);
-            const uintptr_t addr = reinterpret_cast<uintptr_t>(rowp);
-            const uint32_t *base = reinterpret_cast<const uint32_t *>(addr & ~(uintptr_t)3);
-            const int sh = (int)(addr & 3) * 8;
-            uint32_t wv[10];
-#pragma unroll
-            for (int k = 0; k < 10; k++) wv[k] = base[k];
-            uint32_t *dst = reinterpret_cast<uint32_t *>(&sm.tile[r * T]);
-#pragma unroll
-            for (int k = 0; k < 9; k++) dst[k] = __funnelshift_r(wv[k], wv[k + 1], sh);
-        }
-        __syncwarp();
-        for (int y = 0; y < W1; y++) {   // lane = column
-            const int X = ipx + lane, Y = ipy + y;
-            int gxv = 0, gyv = 0;
-            if (X >= 0 && X < I.w && Y >= 0 && Y < I.h) {
-                const uint8_t *t = &sm.tile[(y + 1) * T + (lane + 1)];
-                int tl = t[-T - 1], tc = t[-T], trr = t[-T + 1], ml = t[-1], mr = t[1], bl = t[T - 1], bc = t[T], br = t[T + 1];
-                gxv = 3 * (trr + br) + 10 * mr - (3 * (tl + bl) + 10 * ml);
-                gyv = 3 * ((bl - tl) + (br - trr)) + 10 * (bc - tc);
-            }
-            sm.gx[y * W1 + lane] = (short)gxv; sm.gy[y * W1 + lane] = (short)gyv;
-        }
-        __syncwarp();
-        // ---- template of this lane's row in registers
+        // ---- template of this lane's row in registers (lane 31 only feeds lane 30 with the row below)
         int Iw[31], Ix[31], Iy[31];
         int acc11 = 0, acc12 = 0, acc22 = 0;
         {
-            const int row = have_row ? lane : 0;
-            const uint8_t *t0 = &sm.tile[(row + 1) * T + 1];
-            const short *g0 = &sm.gx[row * W1], *h0 = &sm.gy[row * W1];
-            int pa = t0[0], pb = t0[T], pgx0 = g0[0], pgx1 = g0[W1], pgy0 = h0[0], pgy1 = h0[W1];
+            // image row ipy + lane, pixels ipx .. ipx + 31 (inside the level's REFLECT_101 frame), as 8 realigned words
+            const uint8_t *rowp = I.ptr + (ptrdiff_t)(ipy + lane) * I.pitch + ipx;
+            const uintptr_t addr = reinterpret_cast<uintptr_t>(rowp);
+            const uint32_t *base = reinterpret_cast<const uint32_t *>(addr & ~(uintptr_t)3);
+            const int sh = (int)(addr & 3) * 8;
+            uint32_t wv[9], ta[8], tb[8];
+#pragma unroll
+            for (int k = 0; k < 9; k++) wv[k] = base[k];
+#pragma unroll
+            for (int k = 0; k < 8; k++) ta[k] = __funnelshift_r(wv[k], wv[k + 1], sh);
+#pragma unroll
+            for (int k = 0; k < 8; k++) tb[k] = __shfl_down_sync(0xffffffffu, ta[k], 1);
+            // derivative row (Ix | Iy << 16 per pixel; zero outside the image), same pixels
+            const uint32_t *drow = reinterpret_cast<const uint32_t *>(Dv.ptr + (ptrdiff_t)(ipy + lane) * Dv.pitch) + ipx;
+            uint32_t da = drow[0], db = __shfl_down_sync(0xffffffffu, da, 1);
+            int pa = (int)(ta[0] & 255u), pb = (int)(tb[0] & 255u);
 #pragma unroll
             for (int x = 0; x < 31; x++) {
-                const int na = t0[x + 1], nb = t0[T + x + 1];
-                const int ngx0 = g0[x + 1], ngx1 = g0[W1 + x + 1], ngy0 = h0[x + 1], ngy1 = h0[W1 + x + 1];
+                const uint32_t na_w = drow[x + 1];
+                const uint32_t nb_w = __shfl_down_sync(0xffffffffu, na_w, 1);
+                const int na = (int)((ta[(x + 1) >> 2] >> (8 * ((x + 1) & 3))) & 255u), nb = (int)((tb[(x + 1) >> 2] >> (8 * ((x + 1) & 3))) & 255u);
+                const int pgx0 = (int)(short)(da & 0xffffu), pgy0 = (int)da >> 16, pgx1 = (int)(short)(db & 0xffffu), pgy1 = (int)db >> 16;
+                const int ngx0 = (int)(short)(na_w & 0xffffu), ngy0 = (int)na_w >> 16, ngx1 = (int)(short)(nb_w & 0xffffu), ngy1 = (int)nb_w >> 16;
                 int ival = pa * iw00 + na * iw01 + pb * iw10 + nb * iw11;
                 int ixv = pgx0 * iw00 + ngx0 * iw01 + pgx1 * iw10 + ngx1 * iw11;
                 int iyv = pgy0 * iw00 + ngy0 * iw01 + pgy1 * iw10 + ngy1 * iw11;
@@ -592,7 +576,7 @@ __global__ void __launch_bounds__(32 * KLTW_WARPS, 4) klt31w_kernel(KltArgs a)
                 if (!have_row) { ival = 0; ixv = 0; iyv = 0; }
                 Iw[x] = ival; Ix[x] = ixv; Iy[x] = iyv;
                 acc11 += ixv * ixv; acc12 += ixv * iyv; acc22 += iyv * iyv;   // <= 31 * 4080^2 < 2^31
-                pa = na; pb = nb; pgx0 = ngx0; pgx1 = ngx1; pgy0 = ngy0; pgy1 = ngy1;
+                pa = na; pb = nb; da = na_w; db = nb_w;
             }
         }
         const long long s11 = warp_sum_i32_exact(acc11), s12 = warp_sum_i32_exact(acc12), s22 = warp_sum_i32_exact(acc22);
@@ -633,11 +617,12 @@ __global__ void __launch_bounds__(32 * KLTW_WARPS, 4) klt31w_kernel(KltArgs a)
                     const int x = 4 * k + q;
                     if (x < 31) {
                         unsigned v;
-                        if (q == 0) v = __dp2a_lo(Wt, top[k], __dp2a_lo(Wb, bot[k], 0u));
-                        else if (q == 1) v = __dp2a_lo(Wt, ts, __dp2a_lo(Wb, bs, 0u));
-                        else if (q == 2) v = __dp2a_hi(Wt, top[k], __dp2a_hi(Wb, bot[k], 0u));
-                        else v = __dp2a_hi(Wt, ts, __dp2a_hi(Wb, bs, 0u));
-                        const int diff = (int)((v + (1u << 8)) >> 9) - Iw[x];
+                        // the rounding constant of (v + 2^8) >> 9 rides in as the accumulator of the first dot product
+                        if (q == 0) v = __dp2a_lo(Wt, top[k], __dp2a_lo(Wb, bot[k], 1u << 8));
+                        else if (q == 1) v = __dp2a_lo(Wt, ts, __dp2a_lo(Wb, bs, 1u << 8));
+                        else if (q == 2) v = __dp2a_hi(Wt, top[k], __dp2a_hi(Wb, bot[k], 1u << 8));
+                        else v = __dp2a_hi(Wt, ts, __dp2a_hi(Wb, bs, 1u << 8));
+                        const int diff = (int)(v >> 9) - Iw[x];
                         if (want_err) acc1 += abs(diff);
                         else { acc1 += diff * Ix[x]; acc2 += diff * Iy[x]; }   // <= 31 * 8160 * 4080 < 2^31
                     }

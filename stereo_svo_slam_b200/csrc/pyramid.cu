@@ -189,4 +189,36 @@ void launch_copy16(const void *src, void *dst, size_t bytes, int ctas, cudaStrea
     copy16_kernel<<<ctas, 256, 0, st>>>((const uint4 *)src, (uint4 *)dst, bytes / 16);
 }
 
+// Scharr derivatives of one padded LK level (calcScharrDeriv inside cv::buildOpticalFlowPyramid): (Ix, Iy) as an int16
+// pair per pixel, taps through the level's REFLECT_101 frame, only the interior is written (the frame of the derivative
+// level stays 0 = BORDER_CONSTANT).  Runs once per KEYFRAME, not per frame: a thread makes 4 pixels (one 16-byte store).
+__global__ void __launch_bounds__(128) lk_scharr_kernel(LevelDesc src, LevelDesc dst)
+{
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y;
+    if (x0 >= src.w) return;
+    const uint8_t *r0 = src.ptr + (ptrdiff_t)(y - 1) * src.pitch + x0 - 1, *r1 = r0 + src.pitch, *r2 = r1 + src.pitch;
+    int t[6], m[6], b[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) { t[k] = r0[k]; m[k] = r1[k]; b[k] = r2[k]; }   // up to 2 px past the row end: inside the frame
+    uint32_t out[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int gx = 3 * (t[k + 2] + b[k + 2]) + 10 * m[k + 2] - (3 * (t[k] + b[k]) + 10 * m[k]);
+        const int gy = 3 * ((b[k] - t[k]) + (b[k + 2] - t[k + 2])) + 10 * (b[k + 1] - t[k + 1]);
+        out[k] = ((uint32_t)gx & 0xffffu) | ((uint32_t)gy << 16);
+    }
+    uint32_t *d = reinterpret_cast<uint32_t *>(dst.ptr + (size_t)y * dst.pitch) + x0;
+    if (x0 + 4 <= src.w) *reinterpret_cast<uint4 *>(d) = make_uint4(out[0], out[1], out[2], out[3]);
+    else
+        for (int k = 0; k < 4 && x0 + k < src.w; k++) d[k] = out[k];
+}
+
+void launch_lk_scharr(const ImageSetDev &s, cudaStream_t st)
+{
+    for (int l = 0; l < SVO_LK_LEVELS; l++) {
+        dim3 grid(((s.lk[l].w + 3) / 4 + 127) / 128, s.lk[l].h);
+        lk_scharr_kernel<<<grid, 128, 0, st>>>(s.lk[l], s.lkd[l]);
+    }
+}
+
 int pyr_launch_count(const ImageSetDev &s) { return (s.n_levels > 1 ? 1 : 0) + SVO_LK_LEVELS; }

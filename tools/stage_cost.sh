@@ -1,9 +1,12 @@
-# developer script: throughput vs alignment cluster size
 python bench.py --steps 5 --warmup 3 --streams 32 --host-threads 16 --no-cpu-baseline > /dev/null 2>&1
-for c in 8 4 2 1; do
-  BENCH_ONLY=device timeout 100 python bench.py --steps 200 --warmup 3 --streams 32 --host-threads 16 --align-cluster $c --no-cpu-baseline 2>/dev/null | python -c "
+for st in "8 8" "16 16" "32 16"; do set -- $st
+  BENCH_ONLY=device timeout 100 python bench.py --steps 200 --warmup 3 --streams $1 --host-threads $2 --align-cluster 8 --no-cpu-baseline 2>/dev/null | python -c "
 import sys, json
-d = json.loads(sys.stdin.read().strip().splitlines()[-1]); print('cluster $c', round(d['value']), 'frames/s', round(1e6 / d['value'], 2), 'us/frame')"
+d = json.loads(sys.stdin.read().strip().splitlines()[-1]); print('S=$1 T=$2 value', round(d['value']), 'p50 step ms', round(d['trace']['host_step_ms_p50'],3))"
 done
-for c in 8 4 2 1; do SVO_ALIGN_CLUSTER=$c python tools/quick_time.py C3 40 | tail -2; done
-timeout 100 python bench.py --steps 200 --warmup 3 --streams 32 --host-threads 16 --align-cluster 2 --no-cpu-baseline > gpurun_out/cl2.json 2>gpurun_out/cl2.err
+SVO_INGEST_MIX=1 timeout 100 python bench.py --steps 200 --warmup 3 --streams 32 --host-threads 16 --align-cluster 8 --no-cpu-baseline 2>/dev/null | python -c "
+import sys, json
+d = json.loads(sys.stdin.read().strip().splitlines()[-1]); print('mix value', round(d['value']), 'e2e', round(d['e2e']['value']))"
+SVO_NO_INGEST=1 timeout 100 python bench.py --steps 200 --warmup 3 --streams 32 --host-threads 16 --align-cluster 8 --no-cpu-baseline 2>/dev/null | python -c "
+import sys, json
+d = json.loads(sys.stdin.read().strip().splitlines()[-1]); print('dma value', round(d['value']), 'e2e', round(d['e2e']['value']))"
