@@ -12,7 +12,8 @@ checkout (.MISSING_LARGE_BLOBS).  A *step* advances every sequence of every rank
 bookkeeping, keyframe creation when the reference would create one).
 
   value  : whole-job frames/s with the stereo frames already resident in HBM (svo_slam_new_image_device_begin)
-  e2e    : the same through the reference-facing call with HOST (pinned) buffers, H2D/D2H inside the timed region
+  e2e    : the same through the reference-facing call with HOST (pinned) buffers; every frame crosses PCIe inside the timed
+           region (the ingest kernel reads the page-locked images over PCIe, results come back by DMA)
   roofline / single_stream / kernels : one sequence, per-stage CUDA events on the launching stream
   cpu_baseline : the CPU oracle ("port" of the reference's single-threaded path) on one host core, bounded sample
   --impl reference : the same workload on the CPU oracle with all host threads (one sequence per thread)
@@ -66,6 +67,13 @@ def make_frames(cfg, seeds, n):
             except Exception:
                 pass
         todo.append(s)
+    if len(todo) == 1:   # rendered in-process (also the only safe way once CUDA is initialised: no fork)
+        outs[todo[0]] = render_sequence((cfg, todo[0], n))
+        try:
+            np.save(f"/tmp/svo_synth_{cfg}_{todo[0]}_{n}.npy", outs[todo[0]])
+        except Exception:
+            pass
+        todo = []
     if todo:
         with cf.ProcessPoolExecutor(max_workers=min(len(todo), os.cpu_count() or 1)) as ex:
             for s, arr in zip(todo, ex.map(render_sequence, [(cfg, s, n) for s in todo])):
@@ -156,7 +164,7 @@ def algorithmic_bytes(c, n_kps, evals_per_level, klt_levels=3):
     return {
         "pyramids": half + pyr_lk,
         "align": 120 * n_kps * evals_per_level,          # 120 B per (keypoint, level, evaluation) patch
-        "klt": 6965 * n_kps,                             # derivative-fused layout, 3 levels
+        "klt": (3 * 6144 + 29) * n_kps,                  # 3 levels x (32x32 u8 + 32x32 s16x2 of the keyframe + 32x32 u8 of the frame) + I/O
         "ssd": 4468 * n_kps,
         "refine": 20 * n_kps,
         "filter": 72 * n_kps,
@@ -199,10 +207,10 @@ def main():
     ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--frames", type=int, default=64, help="rendered frames per sequence (played forward/backward: continuous motion)")
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--streams", type=int, default=16, help="independent sequences per GPU")
-    ap.add_argument("--host-threads", type=int, default=4, help="host threads driving the sequences of one GPU")
-    ap.add_argument("--align-cluster", type=int, default=2, choices=[1, 2, 4, 8],
-                    help="SMs per alignment solve in the multi-sequence runs (the single-sequence latency run always uses 8)")
+    ap.add_argument("--streams", type=int, default=32, help="independent sequences per GPU")
+    ap.add_argument("--host-threads", type=int, default=0, help="host threads driving the sequences of one GPU (0 = min(16, cores / ranks))")
+    ap.add_argument("--align-cluster", type=int, default=8, choices=[1, 2, 4, 8],
+                    help="SMs per alignment solve in the multi-sequence runs (measured: 8 and 4 give the same aggregate throughput, 1 is 20 %% slower)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
@@ -211,6 +219,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     W = max(a.warmup, 3)
     K, S = a.steps, a.streams
+    if a.host_threads <= 0:
+        a.host_threads = max(1, min(16, (os.cpu_count() or 1) // max(1, world)))
     c = synth.CONFIGS[CFG]
     nframes = min(a.frames, W + K)   # rendered frames; step t shows frame tri(t) = forward/backward sweep (continuous motion)
 
@@ -429,7 +439,13 @@ def main():
             traffic_tbl = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
         except Exception:  # noqa: BLE001
             pass
-        stage_kernel = {1: "sparse_align_kernel<1>", 2: "klt31w_kernel", 3: "reproj_refine_kernel", 4: "stereo_ssd_col_kernel", 5: "depth_filter_kernel"}
+
+        def traffic_of(kernel):
+            for name, rec in traffic_tbl.items():
+                if name.startswith(kernel):
+                    return rec.get("dram_bytes_per_launch")
+            return None
+        stage_kernel = {1: "sparse_align_kernel", 2: "klt31w_kernel", 3: "reproj_refine_kernel", 4: "stereo_ssd_mma_kernel", 5: "depth_filter_kernel"}
         med_wall = float(np.median(walls[W:]))
         dom = int(np.argmax(st[1:6])) + 1
         ab = algorithmic_bytes(c, n_kps, evals_per_level=1)
@@ -458,12 +474,35 @@ def main():
                                  "note": "one sequence, synchronous new_image calls with host buffers (what the reference app does)"},
                "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
                             "frac": achieved / peak,
-                            "traffic": traffic_tbl.get(stage_kernel.get(dom, ""), {}).get("dram_bytes_per_launch"),
+                            "traffic": traffic_of(stage_kernel.get(dom, "?")),
                             "traffic_source": "profiles/r01_traffic.json (ncu --set full, dram__bytes_read+write per launch)",
                             "algorithmic_bytes_per_launch": int(dom_bytes), "peak_source": peak_src,
                             "limiter": "dependency latency / integer+fp32 ALU, not HBM: the per-frame working set (<3 MB) is L2-resident "
                                        "(SURVEY.md §8d); see profiles/ for the ncu evidence"},
                "kernels": kernels}
+        if world == 1 and not os.environ.get("BENCH_NO_C4"):
+            # ---------------- BASELINE configs[3]: high-density stress (1280x720, 5 levels, ~3-4k keypoints), one sequence
+            c4 = synth.CONFIGS["C4"]
+            f4 = make_frames("C4", [c4["seed"]], 20)[0]
+            s4 = StereoSlam(capi.CameraSettings(**synth.settings_dict("C4")), c4["width"], c4["height"], device=local_rank)
+            ctx4 = C.c_void_p(lib.svo_slam_ctx(s4._h))
+            lib.svo_set_profiling(ctx4, 1)
+            st4, cn4 = [], []
+            for k in range(20):
+                s4.new_image(f4[k, 0], f4[k, 1], k / 20.0)
+                lib.svo_last_stage_ms(ctx4, buf)
+                st4.append(list(buf))
+                cn4.append(list(s4.last_counters().values()))
+            st4, cn4 = np.median(np.array(st4[4:]), axis=0), np.array(cn4[4:], np.float64).mean(axis=0)
+            s4.close()
+            out["stress_c4"] = {"workload": "BASELINE configs[3]: 1280x720 synthetic stereo, 5-level pyramid, 16x14 grid, one sequence, per-stage CUDA events",
+                                "keypoints_per_frame": int(cn4[0]), "ms_per_frame_gpu": float(st4[7]),
+                                "stage_ms": {nm: float(st4[i]) for i, nm in enumerate(names[:7])},
+                                "pose_iter_latency_us": float(1e3 * st4[1] / max(cn4[2] + cn4[3], 1.0)),
+                                "mpatches_per_s": float(cn4[1] * (cn4[2] + cn4[3]) / (st4[1] * 1e-3) / 1e6) if st4[1] > 0 else None,
+                                "mwindows_per_s": float(cn4[6] / (st4[2] * 1e-3) / 1e6) if st4[2] > 0 else None,
+                                "align_gbs": float(120 * cn4[1] * (cn4[2] + cn4[3]) / (st4[1] * 1e-3) / 1e9) if st4[1] > 0 else None,
+                                "klt_gbs": float((3 * 6144 + 29) * cn4[0] / (st4[2] * 1e-3) / 1e9) if st4[2] > 0 else None}
         if not a.no_cpu_baseline and world == 1:
             kb, wb = 30, 3
             fps, dt, _ = run_oracle(frames_np[:1], CFG, kb, wb, 1, tri)
