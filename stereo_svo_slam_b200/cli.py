@@ -13,6 +13,7 @@
 * --euroc: the reference's EurocInput (src/app/euroc_input.cpp): file list and timestamps from cam0/data.csv, cam0 -> `right`,
   cam1 -> `left`, raw images rectified ON THE DEVICE with the LEFT.* / RIGHT.* matrices of the settings file
   (initUndistortRectifyMap + remap, fused in front of the pyramid kernels)
+* --websocket PORT: the reference app's WebSocket JSON backend (src/app/svo_slam_backend.cpp) for src/qt-viewer
 * trajectory CSV: `time,x,y,z,rx,ry,rz`, column 0 = cumulative seconds spent inside new_image, angles re-ordered for
   Blender exactly as src/app/slam_app.cpp:220-246 does (Rodrigues((Ry*Rx)*Rz))
 """
@@ -183,9 +184,9 @@ def iter_synthetic(cfg, frames):
         yield left, right, k / 20.0
 
 
-def run(frames, settings, device=0, trajectory=None, verbose=False, rectification=None):
+def run(frames, settings, device=0, trajectory=None, verbose=False, rectification=None, websocket_port=None):
     from .slam import StereoSlam
-    slam, t_algo, stamps = None, 0.0, []
+    slam, t_algo, stamps, server = None, 0.0, [], None
     for left, right, ts in frames:
         if slam is None:
             slam = StereoSlam(settings if isinstance(settings, CameraSettings) else CameraSettings(**settings), left.shape[1], left.shape[0],
@@ -195,12 +196,19 @@ def run(frames, settings, device=0, trajectory=None, verbose=False, rectificatio
                 for which, side in ((0, "RIGHT"), (1, "LEFT")):
                     c = rectification[side]
                     slam.set_rectification(which, c["K"], c["D"], c["R"], c["P"])
+            if websocket_port is not None:
+                from .backend import WebSocketServer     # the reference app's server (src/app/main.cpp:208), for qt-viewer
+                server = WebSocketServer(slam, websocket_port)
         t0 = time.perf_counter()
         slam.new_image(left, right, ts)
         t_algo += time.perf_counter() - t0           # the reference's TickMeter brackets exactly new_image (slam_app.cpp:187-190)
         stamps.append(t_algo)
+        if server:
+            server.serve_pending()                   # same thread as new_image, like the reference's Qt event loop
         if verbose:
             print(f"frame {len(stamps) - 1}: pose {slam.pose()} keypoints {len(slam.get_frame().kps)} keyframes {slam.keyframe_count()}")
+    if server:
+        server.close()
     traj = slam.get_trajectory() if slam else np.zeros((0, 6), np.float32)
     if trajectory:
         write_trajectory_csv(trajectory, traj, stamps)
@@ -218,6 +226,7 @@ def main(argv=None):
     ap.add_argument("--frames", type=int, default=50, help="frames of the synthetic sequence")
     ap.add_argument("--trajectory", "-t", help="trajectory CSV to write")
     ap.add_argument("--device", type=int, default=0)
+    ap.add_argument("--websocket", type=int, metavar="PORT", help="serve the reference's /keyframes, /pose, /trajectory JSON (qt-viewer uses 8001)")
     ap.add_argument("--verbose", action="store_true")
     a = ap.parse_args(argv)
     if a.synthetic:
@@ -229,7 +238,7 @@ def main(argv=None):
         settings = read_settings(a.settings)
         frames = iter_video(a.video) if a.video else iter_euroc(a.euroc) if a.euroc else iter_pairs(a.pairs)
     rect = read_rectification(a.settings) if a.euroc else None
-    traj, stamps, _ = run(frames, settings, a.device, a.trajectory, a.verbose, rect)
+    traj, stamps, _ = run(frames, settings, a.device, a.trajectory, a.verbose, rect, a.websocket)
     if stamps:
         print(f"{len(stamps)} frames, {len(stamps) / stamps[-1]:.1f} frames/s (algorithm time, test/extract_fps.py definition)")
     return 0
