@@ -396,6 +396,11 @@ def main():
                  "host_step_ms_max": 1e3 * st_[-1][0], "slowest_steps": [(round(1e3 * d, 2), k, g) for d, k, g in st_[-4:]]} if st_ else {}
         return dict(seconds=float(t.item()), launches=nl, kps=kps, keyframes=nkf, poses=poses, clocks=ck, trace=trace)
 
+    if os.environ.get("BENCH_ONLY") == "host":     # developer switch: end-to-end run only
+        r = run("host")
+        if rank == 0:
+            print(json.dumps({"e2e": S * K * world / r["seconds"], "trace": r["trace"]}))
+        return
     r_dev = run("device", None if os.environ.get("BENCH_NO_NVML") else ClockSampler(local_rank))
     if os.environ.get("BENCH_ONLY") == "device":   # developer switch: whole-job device-resident run only
         if rank == 0:

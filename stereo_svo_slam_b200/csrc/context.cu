@@ -100,6 +100,8 @@ struct svo_ctx {
     std::vector<Slot> slots;
     SlotArena *arena = nullptr;
     uint8_t *h_stage[2] = {nullptr, nullptr};  // pinned upload staging (double buffered)
+    uint8_t *d_stage[2] = {nullptr, nullptr};  // ... as the device sees them (zero-copy ingest)
+    const uint8_t *zc_left = nullptr, *zc_right = nullptr;   // device-visible addresses of the host images being uploaded
     int stage_idx = 0;
     // keyframe tables
     LevelDesc *d_kf_lk = nullptr;
@@ -306,7 +308,10 @@ extern "C" int svo_ctx_create(const svo_camera_settings *s, int device, int widt
         for (int k = 0; k < 6; k++) { int rc0 = alloc_slot(ctx, &ids[k]); if (rc0) return fail_create(ctx, rc0, ctx->err); }
         for (int k = 0; k < 6; k++) ctx->slots[ids[k]].refcount = 0;
     }
-    for (int k = 0; k < 2; k++) CKC(cudaMallocHost(&ctx->h_stage[k], (size_t)2 * width * height));
+    for (int k = 0; k < 2; k++) {
+        CKC(cudaMallocHost(&ctx->h_stage[k], (size_t)2 * width * height));
+        if (cudaHostGetDevicePointer((void **)&ctx->d_stage[k], ctx->h_stage[k], 0) != cudaSuccess) { ctx->d_stage[k] = nullptr; cudaGetLastError(); }
+    }
     make_layout(ctx->lay, ctx->max_kps);
     CKC(cudaMalloc(&ctx->d_io, ctx->lay.total));
     CKC(cudaMemset(ctx->d_io, 0, ctx->lay.total));
@@ -412,15 +417,28 @@ static int ensure_derivs(svo_ctx *ctx, int slot)
 
 // src_kind: 0 = pageable host memory (staged through the context's pinned buffer), 1 = page-locked host memory
 // (direct DMA), 2 = device memory
-static int classify_source(const uint8_t *left, const uint8_t *right)
+static int classify_source(const uint8_t *left, const uint8_t *right, const uint8_t **dev_left = nullptr, const uint8_t **dev_right = nullptr)
 {
-    static const bool skip_query = getenv("SVO_ASSUME_PAGEABLE") != nullptr;   // diagnostic switch
+    static const bool skip_query = getenv("SVO_ASSUME_PAGEABLE") != nullptr;   // diagnostic switches
+    static const bool assume_pinned = getenv("SVO_ASSUME_PINNED") != nullptr;  // (measures the cost of the two queries)
+    if (dev_left) *dev_left = nullptr;
+    if (dev_right) *dev_right = nullptr;
     if (skip_query) return 0;
+    if (assume_pinned) {
+        if (dev_left) *dev_left = left;
+        if (dev_right) *dev_right = right;
+        return 1;
+    }
     cudaPointerAttributes al, ar;
     bool ok = cudaPointerGetAttributes(&al, left) == cudaSuccess && cudaPointerGetAttributes(&ar, right) == cudaSuccess;
     cudaGetLastError();  // clear a possible "invalid value" from querying unregistered memory on old drivers
     if (!ok) return 0;
-    if (al.type == cudaMemoryTypeHost && ar.type == cudaMemoryTypeHost) return 1;
+    if (al.type == cudaMemoryTypeHost && ar.type == cudaMemoryTypeHost) {
+        // the same query yields the address at which the device sees the page-locked buffer (zero-copy ingest)
+        if (dev_left) *dev_left = (const uint8_t *)al.devicePointer;
+        if (dev_right) *dev_right = (const uint8_t *)ar.devicePointer;
+        return 1;
+    }
     if ((al.type == cudaMemoryTypeDevice || al.type == cudaMemoryTypeManaged) && (ar.type == cudaMemoryTypeDevice || ar.type == cudaMemoryTypeManaged)) return 2;
     return 0;
 }
@@ -459,13 +477,7 @@ static int enqueue_upload(svo_ctx *ctx, Slot &s, const uint8_t *left, size_t ls,
         ia.dst[0] = dl; ia.dst[1] = dr; ia.w = ctx->W; ia.h = ctx->H; ia.spitch[0] = ls; ia.spitch[1] = rs;
         bool ok = true;
         if (src_kind == 2) { ia.src[0] = left; ia.src[1] = right; }
-        else {
-            void *pl = nullptr, *pr = nullptr;
-            ok = cudaHostGetDevicePointer(&pl, const_cast<uint8_t *>(left), 0) == cudaSuccess &&
-                 cudaHostGetDevicePointer(&pr, const_cast<uint8_t *>(right), 0) == cudaSuccess;
-            if (!ok) cudaGetLastError();
-            ia.src[0] = (const uint8_t *)pl; ia.src[1] = (const uint8_t *)pr;
-        }
+        else { ia.src[0] = ctx->zc_left; ia.src[1] = ctx->zc_right; ok = ctx->zc_left && ctx->zc_right; }
         if (ok && ingest_supported(ia)) {
             mark(ctx, 1);
             launch_ingest(ia, ctx->stream);
@@ -519,6 +531,8 @@ static int upload_common(svo_ctx *ctx, const uint8_t *left, size_t ls, const uin
         // pageable memory goes through the context's own pinned staging buffer (double buffered; uploads on one
         // stream are ordered and the caller synchronises once per frame)
         uint8_t *stage = stage_images(ctx, left, ls, right, rs, ctx->stage_idx);
+        ctx->zc_left = ctx->d_stage[ctx->stage_idx];
+        ctx->zc_right = ctx->zc_left ? ctx->zc_left + img : nullptr;
         ctx->stage_idx ^= 1;
         left = stage; right = stage + img; ls = rs = (size_t)ctx->W;
     }
@@ -533,7 +547,7 @@ static int upload_common(svo_ctx *ctx, const uint8_t *left, size_t ls, const uin
 extern "C" int svo_upload_stereo(svo_ctx *ctx, const uint8_t *left, size_t ls, const uint8_t *right, size_t rs, int *slot_out)
 {
     if (!ctx || !left || !right || !slot_out || ls < (size_t)ctx->W || rs < (size_t)ctx->W) return SVO_ERR_INVALID;
-    int kind = classify_source(left, right);
+    int kind = classify_source(left, right, &ctx->zc_left, &ctx->zc_right);
     if (kind == 2) kind = 0;  // a device pointer passed to the host entry point is a caller error; treat as host memory
     return upload_common(ctx, left, ls, right, rs, kind, slot_out);
 }
@@ -1199,7 +1213,7 @@ extern "C" int svo_frame_begin(svo_ctx *ctx, const uint8_t *left, size_t ls, con
     int rc = validate_and_pack(ctx, io);
     if (rc) return rc;
     CK(cudaSetDevice(ctx->device));
-    int src_kind = on_device ? 2 : classify_source(left, right);
+    int src_kind = on_device ? 2 : classify_source(left, right, &ctx->zc_left, &ctx->zc_right);
     if (!on_device && src_kind == 2) src_kind = 0;
     const int n = io->n;
     const bool contiguous = ls == (size_t)ctx->W && rs == (size_t)ctx->W;
@@ -1227,6 +1241,8 @@ extern "C" int svo_frame_begin(svo_ctx *ctx, const uint8_t *left, size_t ls, con
     if (src_kind == 0) {
         stage_idx = ctx->stage_idx;
         uint8_t *stage = stage_images(ctx, left, ls, right, rs, stage_idx);
+        ctx->zc_left = ctx->d_stage[stage_idx];
+        ctx->zc_right = ctx->zc_left ? ctx->zc_left + img : nullptr;
         ctx->stage_idx ^= 1;
         left = stage; right = stage + img; ls = rs = (size_t)ctx->W;
     }

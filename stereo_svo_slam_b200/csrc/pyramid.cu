@@ -9,6 +9,7 @@
 //   size (w+1)/2 x (h+1)/2).  Every level is stored with a SVO_LK_PAD-pixel BORDER_REFLECT_101 frame, which
 //   is both pyrDown's border rule and the padding calcOpticalFlowPyrLK expects around its windows; the
 //   Scharr derivative images OpenCV stores next to them are NOT materialised (fused into the KLT kernel).
+#include <cstdlib>
 #include "kernels.cuh"
 
 #define TILE 64
@@ -133,33 +134,43 @@ void launch_lk_pyramid(const ImageSetDev &s, cudaStream_t st)
 // over PCIe (zero-copy; a 361 KB cudaMemcpyAsync costs ~25 us of copy-engine time, of which ~18 us is fixed overhead,
 // so two copies per frame cap one engine at ~20 k frames/s) or device memory — into level 0 of the image set (or into
 // the raw buffers of the rectifier).  One 16-byte load per thread, all 722 KB of a C3 pair in flight at once.
-#define INGEST_UNROLL 8   // independent 16-byte loads per thread: the bytes in flight come from few, fat threads, so a
-                          // kernel that sits ~20 us on PCIe latency holds ~1/8 of the thread slots a load-per-thread grid would
-__global__ void __launch_bounds__(128) ingest_kernel(IngestArgs a)
+#define INGEST_CH 24      // cap on 16-byte chunks in flight per thread (128 threads x 24 x 16 B = 48 KB of shared memory per CTA)
+// The bytes in flight over PCIe are parked in SHARED memory by cp.async (LDGSTS), not in registers, and there are FEW of
+// them: 4 persistent CTAs per image x 128 threads x 3 chunks = 49 KB per stereo pair.  Measured with 32 sequences per GPU
+// (end-to-end frames/s): one 16-byte load per thread, 722 KB in flight 37.2 k; 4 CTAs of 8 register-held loads 42.4 k;
+// this kernel 41.4-42.9 k for 25-100 KB in flight, 38.9 k at 290 KB.  More outstanding system-memory reads than the link
+// needs (bandwidth x ~2 us) only queue in front of the other kernels' memory traffic; a sequence running alone pays
+// ~15 us per frame for the shallow queue (the kernel takes 36 us instead of 21 us).  Every thread reads back only the
+// chunks it fetched itself, so there is no barrier.  SVO_INGEST_CTAS / SVO_INGEST_DEPTH override the two numbers.
+__global__ void __launch_bounds__(128) ingest_kernel(IngestArgs a, int depth)
 {
+    extern __shared__ __align__(16) uint4 ingest_buf[];
     const int z = blockIdx.y;
     const uint8_t *__restrict__ src = z ? a.src[1] : a.src[0];
     uint8_t *__restrict__ dst = z ? a.dst[1] : a.dst[0];
     const size_t sp = z ? a.spitch[1] : a.spitch[0];
     const int c16 = a.w >> 4;                        // 16-byte chunks per row
     const int total = c16 * a.h;
-    // chunk k of this thread = base + k * blockDim.x: every load instruction of a warp covers 512 contiguous bytes
-    const int base = blockIdx.x * (blockDim.x * INGEST_UNROLL) + threadIdx.x;
-    uint4 v[INGEST_UNROLL];
-#pragma unroll
-    for (int k = 0; k < INGEST_UNROLL; k++) {
-        const int idx = base + k * blockDim.x;
-        if (idx < total) {
-            const int row = idx / c16, col = (idx - row * c16) << 4;
-            v[k] = __ldcs(reinterpret_cast<const uint4 *>(src + (size_t)row * sp + col));
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(ingest_buf) + threadIdx.x * 16;
+    for (int base = blockIdx.x * (128 * depth) + threadIdx.x; base < total; base += gridDim.x * 128 * depth) {
+        // chunk k of this thread = base + k * 128: every instruction of a warp covers 512 contiguous bytes
+#pragma unroll 4
+        for (int k = 0; k < depth; k++) {
+            const int idx = base + k * 128;
+            if (idx < total) {
+                const int row = idx / c16, col = (idx - row * c16) << 4;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + k * 128 * 16), "l"(src + (size_t)row * sp + col) : "memory");
+            }
         }
-    }
-#pragma unroll
-    for (int k = 0; k < INGEST_UNROLL; k++) {
-        const int idx = base + k * blockDim.x;
-        if (idx < total) {
-            const int row = idx / c16, col = (idx - row * c16) << 4;
-            *reinterpret_cast<uint4 *>(dst + (size_t)row * a.w + col) = v[k];
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll 4
+        for (int k = 0; k < depth; k++) {
+            const int idx = base + k * 128;
+            if (idx < total) {
+                const int row = idx / c16, col = (idx - row * c16) << 4;
+                *reinterpret_cast<uint4 *>(dst + (size_t)row * a.w + col) = ingest_buf[k * 128 + threadIdx.x];
+            }
         }
     }
 }
@@ -175,8 +186,12 @@ bool ingest_supported(const IngestArgs &a)
 void launch_ingest(const IngestArgs &a, cudaStream_t st)
 {
     const int total = (a.w >> 4) * a.h;
-    dim3 grid((total + 128 * INGEST_UNROLL - 1) / (128 * INGEST_UNROLL), 2);
-    ingest_kernel<<<grid, 128, 0, st>>>(a);
+    static const int max_ctas = getenv("SVO_INGEST_CTAS") ? atoi(getenv("SVO_INGEST_CTAS")) : 4;   // per image
+    static const int depth_env = getenv("SVO_INGEST_DEPTH") ? atoi(getenv("SVO_INGEST_DEPTH")) : 3;
+    const int depth = depth_env < 1 ? 1 : (depth_env > INGEST_CH ? INGEST_CH : depth_env);
+    const int need = (total + 128 * depth - 1) / (128 * depth);
+    dim3 grid(need < max_ctas ? need : (max_ctas < 1 ? 1 : max_ctas), 2);
+    ingest_kernel<<<grid, 128, 128 * depth * 16, st>>>(a, depth);
 }
 
 // developer probe: zero-copy read bandwidth of the SMs (same access pattern as ingest_kernel) over a large buffer
