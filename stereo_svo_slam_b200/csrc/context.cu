@@ -117,6 +117,8 @@ struct svo_ctx {
     int *d_cell_type = nullptr;
     int cell_cap = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t stream2 = nullptr;            // side branch of the captured frame graph (LK pyramid || alignment, SSD || refinement)
+    cudaEvent_t fev[4] = {nullptr, nullptr, nullptr, nullptr};
     float last_ms = 0;
     int last_launches = 0;
     bool track_pending = false;
@@ -134,6 +136,7 @@ struct svo_ctx {
     std::vector<FrameGraph> graphs;
     bool use_graphs = true;
     int align_cluster = 8;    // SMs per alignment solve (svo_set_align_cluster)
+    bool use_fork = true;     // two-branch frame graph (SVO_NO_FORK=1: linear chain)
     bool use_ingest = true;   // SM-driven frame ingest instead of copy-engine DMA (SVO_NO_INGEST=1 turns it off)
     unsigned long long graph_clock = 0;
     long long graph_launches = 0, graph_captures = 0, graph_updates = 0;
@@ -241,6 +244,7 @@ extern "C" int svo_ctx_create(const svo_camera_settings *s, int device, int widt
     ctx->n_levels = s->max_pyramid_levels;
     ctx->use_graphs = getenv("SVO_NO_GRAPHS") == nullptr;
     ctx->use_ingest = getenv("SVO_NO_INGEST") == nullptr;
+    ctx->use_fork = getenv("SVO_NO_FORK") == nullptr;
     if (getenv("SVO_INGEST_MIX")) {   // developer experiment: every second context uploads by copy-engine DMA
         static int counter = 0;
         ctx->use_ingest = (counter++ & 1) == 0;
@@ -271,6 +275,8 @@ extern "C" int svo_ctx_create(const svo_camera_settings *s, int device, int widt
     } while (0)
     CKC(cudaSetDevice(device));
     CKC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CKC(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+    for (int k = 0; k < 4; k++) CKC(cudaEventCreateWithFlags(&ctx->fev[k], cudaEventDisableTiming));
     CKC(cudaEventCreate(&ctx->ev0));
     CKC(cudaEventCreate(&ctx->ev1));
     for (int k = 0; k < 9; k++) CKC(cudaEventCreate(&ctx->sev[k]));
@@ -358,6 +364,8 @@ extern "C" int svo_ctx_destroy(svo_ctx *ctx)
         if (ctx->d_rect_packed[k]) cudaFree(ctx->d_rect_packed[k]);
         if (ctx->d_raw[k]) cudaFree(ctx->d_raw[k]);
     }
+    for (int k = 0; k < 4; k++) if (ctx->fev[k]) cudaEventDestroy(ctx->fev[k]);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     for (int k = 0; k < 9; k++) if (ctx->sev[k]) cudaEventDestroy(ctx->sev[k]);
@@ -462,7 +470,7 @@ static uint8_t *stage_images(svo_ctx *ctx, const uint8_t *left, size_t ls, const
 
 // stream part of an upload: copies + pyramid kernels (stereo_slam.cpp:135-139).  For src_kind 0 `left`/`right`
 // are the two halves of the staging buffer.
-static int enqueue_pyramids(svo_ctx *ctx, Slot &s);
+static int enqueue_pyramids(svo_ctx *ctx, Slot &s, bool forked = false);
 static int enqueue_upload(svo_ctx *ctx, Slot &s, const uint8_t *left, size_t ls, const uint8_t *right, size_t rs, int src_kind,
                           bool copies_only = false)
 {
@@ -480,7 +488,8 @@ static int enqueue_upload(svo_ctx *ctx, Slot &s, const uint8_t *left, size_t ls,
         else { ia.src[0] = ctx->zc_left; ia.src[1] = ctx->zc_right; ok = ctx->zc_left && ctx->zc_right; }
         if (ok && ingest_supported(ia)) {
             mark(ctx, 1);
-            launch_ingest(ia, ctx->stream);
+            // fewer than four live sequences of this geometry on the device: latency matters more than the other streams' traffic
+            launch_ingest(ia, ctx->arena->users < 4, ctx->stream);
             mark(ctx, 2);
             ctx->launch_total += 1;
             CK(cudaGetLastError());
@@ -500,7 +509,9 @@ static int enqueue_upload(svo_ctx *ctx, Slot &s, const uint8_t *left, size_t ls,
 static bool rectifying(const svo_ctx *ctx) { return ctx->d_rect_packed[0] || ctx->d_rect_packed[1]; }
 static int frame_pyr_launches(const svo_ctx *ctx, const Slot &s) { return pyr_launch_count(s.dev) + (rectifying(ctx) ? 1 : 0); }
 
-static int enqueue_pyramids(svo_ctx *ctx, Slot &s)
+// forked (only while capturing the frame graph): the LK pyramid goes to a side branch that rejoins in front of the KLT
+// kernel, so it runs beside the half-sample pyramid, the keypoint upload and the alignment solve instead of before them
+static int enqueue_pyramids(svo_ctx *ctx, Slot &s, bool forked)
 {
     if (rectifying(ctx)) {
         RemapArgs ra;
@@ -510,10 +521,17 @@ static int enqueue_pyramids(svo_ctx *ctx, Slot &s)
         ra.w = ra.sw = ctx->W; ra.h = ra.sh = ctx->H; ra.dpitch = ra.spitch = ctx->W;
         launch_remap(ra, ctx->stream);
     }
+    cudaStream_t lk_stream = ctx->stream;
+    if (forked) {
+        CK(cudaEventRecord(ctx->fev[0], ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->stream2, ctx->fev[0], 0));
+        lk_stream = ctx->stream2;
+    }
     for (int k = 0; k <= diag_dup("pyr"); k++) {
         launch_pyr_halfsample(s.dev, ctx->stream);
-        launch_lk_pyramid(s.dev, ctx->stream);
+        launch_lk_pyramid(s.dev, lk_stream);
     }
+    if (forked) CK(cudaEventRecord(ctx->fev[1], ctx->stream2));
     mark(ctx, 3);
     CK(cudaGetLastError());
     return SVO_OK;
@@ -1094,7 +1112,7 @@ static int validate_and_pack(svo_ctx *ctx, svo_track_io *io)
 
 // stream part of a tracking frame; grid_n = number of per-keypoint CTAs to launch (>= n; the kernels read n from
 // device memory), prof = record the per-stage events
-static int enqueue_track(svo_ctx *ctx, int prev_slot, int cur_slot, int n, int grid_n, bool prof, int *launches_out)
+static int enqueue_track(svo_ctx *ctx, int prev_slot, int cur_slot, int n, int grid_n, bool prof, int *launches_out, bool forked = false)
 {
     const IoLayout &L = ctx->lay;
     uint8_t *h = ctx->h_io;
@@ -1110,6 +1128,7 @@ static int enqueue_track(svo_ctx *ctx, int prev_slot, int cur_slot, int n, int g
     for (int k = 0; k < diag_dup("align"); k++) CK(launch_align(aa, ctx->stream));
     mark(ctx, 5);
     if (prof) CK(cudaEventRecord(ctx->sev[3], ctx->stream));
+    if (forked) CK(cudaStreamWaitEvent(ctx->stream, ctx->fev[1], 0));   // LK pyramid branch rejoins
     if (n > 0) {
         // 2. projection with the aligned pose + KLT against the origin keyframes + gating (stereo_slam.cpp:71-83)
         KltArgs ka;
@@ -1124,6 +1143,21 @@ static int enqueue_track(svo_ctx *ctx, int prev_slot, int cur_slot, int n, int g
         for (int k = 0; k < diag_dup("klt"); k++) launch_klt(ka, ctx->stream);
         mark(ctx, 6);
     }
+    // the stereo SSD of the depth filter only needs the positions the KLT stage left: with `forked` it runs beside the
+    // reprojection refinement and rejoins in front of the filter update
+    SsdArgs sa;
+    if (n > 0) {
+        sa.left0 = ctx->slots[cur_slot].dev.left[0]; sa.right0 = ctx->slots[cur_slot].dev.right0;
+        sa.kps2d = DP(float, kps2d_ref_in); sa.n_ptr = DP(int, n); sa.mode = 1; sa.disparity = DP(float, disparity);
+        sa.max_kps = grid_n; sa.cam = ctx->cam;
+        if (forked) {
+            CK(cudaEventRecord(ctx->fev[2], ctx->stream));
+            CK(cudaStreamWaitEvent(ctx->stream2, ctx->fev[2], 0));
+            launch_stereo_ssd(sa, ctx->stream2); launches++;
+            for (int k = 0; k < diag_dup("ssd"); k++) { launch_stereo_ssd(sa, ctx->stream2); launches++; }
+            CK(cudaEventRecord(ctx->fev[3], ctx->stream2));
+        }
+    }
     if (prof) CK(cudaEventRecord(ctx->sev[4], ctx->stream));
     // 3. reprojection Gauss-Newton (pose_refinement.cpp:175-177)
     RefineArgs ra;
@@ -1136,12 +1170,12 @@ static int enqueue_track(svo_ctx *ctx, int prev_slot, int cur_slot, int n, int g
     if (prof) CK(cudaEventRecord(ctx->sev[5], ctx->stream));
     if (n > 0) {
         // 4. depth filter: disparities on the current stereo pair, then vote / triangulate / Kalman / flags / re-project
-        SsdArgs sa;
-        sa.left0 = ctx->slots[cur_slot].dev.left[0]; sa.right0 = ctx->slots[cur_slot].dev.right0;
-        sa.kps2d = DP(float, kps2d_ref_in); sa.n_ptr = DP(int, n); sa.mode = 1; sa.disparity = DP(float, disparity);
-        sa.max_kps = grid_n; sa.cam = ctx->cam;
-        launch_stereo_ssd(sa, ctx->stream); launches++;
-        for (int k = 0; k < diag_dup("ssd"); k++) { launch_stereo_ssd(sa, ctx->stream); launches++; }
+        if (forked) {
+            CK(cudaStreamWaitEvent(ctx->stream, ctx->fev[3], 0));
+        } else {
+            launch_stereo_ssd(sa, ctx->stream); launches++;
+            for (int k = 0; k < diag_dup("ssd"); k++) { launch_stereo_ssd(sa, ctx->stream); launches++; }
+        }
         if (prof) CK(cudaEventRecord(ctx->sev[6], ctx->stream));
         FilterArgs fa;
         fa.kf_pose_table = ctx->d_kf_pose; fa.keyframe_ids = DP(int, kf_id); fa.disparity = DP(float, disparity);
@@ -1194,8 +1228,9 @@ static int capture_frame_graph(svo_ctx *ctx, svo_ctx::FrameGraph &g, int n, cuda
     Slot &s = ctx->slots[g.cur_slot];
     CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
     int launches = 0;
-    int rc = enqueue_pyramids(ctx, s);
-    if (!rc) rc = enqueue_track(ctx, g.prev_slot, g.cur_slot, n, g.bucket, false, &launches);
+    const bool forked = ctx->use_fork;
+    int rc = enqueue_pyramids(ctx, s, forked);
+    if (!rc) rc = enqueue_track(ctx, g.prev_slot, g.cur_slot, n, g.bucket, false, &launches, forked);
     cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
     if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
     CK(e);
@@ -1222,10 +1257,10 @@ extern "C" int svo_frame_begin(svo_ctx *ctx, const uint8_t *left, size_t ls, con
     int cur;
     const size_t img = (size_t)ctx->W * ctx->H;
     if (!graph_ok) {
+        CK(cudaEventRecord(ctx->ev0, ctx->stream));
         if ((rc = upload_common(ctx, left, ls, right, rs, src_kind, &cur))) return rc;
         *cur_slot_out = cur;
         const bool prof = ctx->profiling;
-        CK(cudaEventRecord(ctx->ev0, ctx->stream));
         int launches = 0;
         if ((rc = enqueue_track(ctx, prev_slot, cur, n, n, prof, &launches))) return rc;
         CK(cudaEventRecord(ctx->ev1, ctx->stream));
@@ -1248,6 +1283,7 @@ extern "C" int svo_frame_begin(svo_ctx *ctx, const uint8_t *left, size_t ls, con
     }
     // the two image copies go on the stream directly (their source changes every frame); pyramids + tracking replay
     const double tt1 = g_trace ? now_ms() : 0;
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));   // the frame's device time starts with its ingest
     if ((rc = enqueue_upload(ctx, ctx->slots[cur], left, ls, right, rs, src_kind, true))) return rc;
     const double tt2 = g_trace ? now_ms() : 0;
     const int bucket = std::min(ctx->max_kps, (n + 127) / 128 * 128);
@@ -1299,7 +1335,6 @@ extern "C" int svo_frame_begin(svo_ctx *ctx, const uint8_t *left, size_t ls, con
     }
     g->last_use = ++ctx->graph_clock;
     const double tt3 = g_trace ? now_ms() : 0;
-    CK(cudaEventRecord(ctx->ev0, ctx->stream));
     CK(cudaGraphLaunch(g->exec, ctx->stream));
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     if (g_trace && now_ms() - tt0 > 3.0)

@@ -29,7 +29,7 @@ struct IngestArgs {
     int w, h;
 };
 bool ingest_supported(const IngestArgs &a);
-void launch_ingest(const IngestArgs &a, cudaStream_t st);
+void launch_ingest(const IngestArgs &a, bool deep_queue, cudaStream_t st);
 void launch_copy16(const void *src, void *dst, size_t bytes, int ctas, cudaStream_t st);
 
 // ---- rectify.cu (EuRoC front end, euroc_input.cpp:48-49, :69-73)

@@ -139,9 +139,10 @@ void launch_lk_pyramid(const ImageSetDev &s, cudaStream_t st)
 // them: 4 persistent CTAs per image x 128 threads x 3 chunks = 49 KB per stereo pair.  Measured with 32 sequences per GPU
 // (end-to-end frames/s): one 16-byte load per thread, 722 KB in flight 37.2 k; 4 CTAs of 8 register-held loads 42.4 k;
 // this kernel 41.4-42.9 k for 25-100 KB in flight, 38.9 k at 290 KB.  More outstanding system-memory reads than the link
-// needs (bandwidth x ~2 us) only queue in front of the other kernels' memory traffic; a sequence running alone pays
-// ~15 us per frame for the shallow queue (the kernel takes 36 us instead of 21 us).  Every thread reads back only the
-// chunks it fetched itself, so there is no barrier.  SVO_INGEST_CTAS / SVO_INGEST_DEPTH override the two numbers.
+// needs (bandwidth x ~2 us) only queue in front of the other kernels' memory traffic.  A shallow queue costs a sequence
+// that runs alone ~15 us per frame, so contexts that have the GPU (almost) to themselves use a deep one (deep_queue: every
+// chunk of the pair in flight at once).  Every thread reads back only the chunks it fetched itself, so there is no
+// barrier.  SVO_INGEST_CTAS / SVO_INGEST_DEPTH override the two numbers of the shallow configuration.
 __global__ void __launch_bounds__(128) ingest_kernel(IngestArgs a, int depth)
 {
     extern __shared__ __align__(16) uint4 ingest_buf[];
@@ -183,14 +184,16 @@ bool ingest_supported(const IngestArgs &a)
     return true;
 }
 
-void launch_ingest(const IngestArgs &a, cudaStream_t st)
+void launch_ingest(const IngestArgs &a, bool deep_queue, cudaStream_t st)
 {
     const int total = (a.w >> 4) * a.h;
     static const int max_ctas = getenv("SVO_INGEST_CTAS") ? atoi(getenv("SVO_INGEST_CTAS")) : 4;   // per image
     static const int depth_env = getenv("SVO_INGEST_DEPTH") ? atoi(getenv("SVO_INGEST_DEPTH")) : 3;
-    const int depth = depth_env < 1 ? 1 : (depth_env > INGEST_CH ? INGEST_CH : depth_env);
+    int depth = depth_env < 1 ? 1 : (depth_env > INGEST_CH ? INGEST_CH : depth_env);
+    int ctas = max_ctas < 1 ? 1 : max_ctas;
+    if (deep_queue) { depth = 8; ctas = 1 << 20; }   // a sequence running alone: everything in flight at once (lowest latency)
     const int need = (total + 128 * depth - 1) / (128 * depth);
-    dim3 grid(need < max_ctas ? need : (max_ctas < 1 ? 1 : max_ctas), 2);
+    dim3 grid(need < ctas ? need : ctas, 2);
     ingest_kernel<<<grid, 128, 128 * depth * 16, st>>>(a, depth);
 }
 
