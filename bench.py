@@ -209,7 +209,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--streams", type=int, default=32, help="independent sequences per GPU")
     ap.add_argument("--host-threads", type=int, default=0, help="host threads driving the sequences of one GPU (0 = min(16, cores / ranks))")
-    ap.add_argument("--align-cluster", type=int, default=8, choices=[1, 2, 4, 8],
+    ap.add_argument("--align-cluster", type=int, default=0, choices=[0, 1, 2, 4, 8, 16],
                     help="SMs per alignment solve in the multi-sequence runs (measured: 8 and 4 give the same aggregate throughput, 1 is 20 %% slower)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -507,6 +507,8 @@ def main():
             f4 = make_frames("C4", [c4["seed"]], 20)[0]
             s4 = StereoSlam(capi.CameraSettings(**synth.settings_dict("C4")), c4["width"], c4["height"], device=local_rank)
             ctx4 = C.c_void_p(lib.svo_slam_ctx(s4._h))
+            c4_cluster = int(os.environ.get("BENCH_C4_CLUSTER", "0"))   # 0 = library default: 16 SMs per solve above 1024 keypoints
+            s4.set_align_cluster(c4_cluster)
             lib.svo_set_profiling(ctx4, 1)
             st4, cn4 = [], []
             for k in range(20):
@@ -517,7 +519,7 @@ def main():
             st4, cn4 = np.median(np.array(st4[4:]), axis=0), np.array(cn4[4:], np.float64).mean(axis=0)
             s4.close()
             out["stress_c4"] = {"workload": "BASELINE configs[3]: 1280x720 synthetic stereo, 5-level pyramid, 16x14 grid, one sequence, per-stage CUDA events",
-                                "keypoints_per_frame": int(cn4[0]), "ms_per_frame_gpu": float(st4[7]),
+                                "keypoints_per_frame": int(cn4[0]), "align_cluster": c4_cluster, "ms_per_frame_gpu": float(st4[7]),
                                 "stage_ms": {nm: float(st4[i]) for i, nm in enumerate(names[:7])},
                                 "pose_iter_latency_us": float(1e3 * st4[1] / max(cn4[2] + cn4[3], 1.0)),
                                 "mpatches_per_s": float(cn4[1] * (cn4[2] + cn4[3]) / (st4[1] * 1e-3) / 1e6) if st4[1] > 0 else None,

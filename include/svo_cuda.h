@@ -182,9 +182,10 @@ int svo_track_frame(svo_ctx *ctx, int prev_slot, int cur_slot, svo_track_io *io)
  * on_device != 0: left/right are device pointers. */
 int svo_frame_begin(svo_ctx *ctx, const uint8_t *left, size_t left_stride, const uint8_t *right, size_t right_stride,
                     int on_device, int prev_slot, svo_track_io *io, int *cur_slot_out);
-/* Number of SMs (CTAs of one thread-block cluster: 1, 2, 4 or 8) that share the alignment solve of a frame.  8 (default)
- * minimises the latency of one sequence; 1 or 2 minimise the SM time per frame, which is what bounds the aggregate
- * throughput when many sequences share the GPU.  Results agree within the pose tolerance (the cross-keypoint sums
+/* Number of SMs (CTAs of one thread-block cluster: 1, 2, 4, 8 or 16) that share the alignment solve of a frame.  8
+ * minimises the latency of one sequence with a few hundred keypoints; 16 (a non-portable cluster size) pays with
+ * thousands of keypoints per frame; 1-4 hold fewer SMs per solve when many sequences share the GPU.  0 (default) picks
+ * 8, or 16 for frames with more than 1024 keypoints.  Results agree within the pose tolerance (the cross-keypoint sums
  * are grouped differently), each setting is deterministic.  Env SVO_ALIGN_CLUSTER sets the default. */
 int svo_set_align_cluster(svo_ctx *ctx, int ctas);
 /* CUDA-graph replay on/off (default on; env SVO_NO_GRAPHS=1 turns it off); counters for tests */

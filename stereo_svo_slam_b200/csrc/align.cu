@@ -19,7 +19,8 @@
 // Bound: dependency latency (serial evaluations) and shared-memory/ALU throughput, not HBM.
 #include "kernels.cuh"
 
-#define CLMAX 8              // largest cluster: CTAs (= SMs) cooperating on one frame; the kernel is instantiated for 1, 2, 4, 8
+#define CLMAX 16             // largest cluster: CTAs (= SMs) cooperating on one frame; the kernel is instantiated for 1, 2, 4, 8, 16
+                             // (16 is a non-portable cluster size: opt-in attribute, for frames with thousands of keypoints)
 #define ALIGN_THREADS 256    // per CTA: 8 warps x 8 keypoints x 4 patch rows
 #define ALIGN_WARPS (ALIGN_THREADS / 32)
 #define NGRAD 27             // 21 (H upper triangle) + 6 (b)
@@ -661,8 +662,10 @@ cudaError_t align_init_device()
 {
     cudaError_t e = cudaSuccess;
 #define ALIGN_OPT_IN(c) if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_kernel<true, c>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024))
-    ALIGN_OPT_IN(1); ALIGN_OPT_IN(2); ALIGN_OPT_IN(4); ALIGN_OPT_IN(8);
+    ALIGN_OPT_IN(1); ALIGN_OPT_IN(2); ALIGN_OPT_IN(4); ALIGN_OPT_IN(8); ALIGN_OPT_IN(16);
 #undef ALIGN_OPT_IN
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_kernel<true, 16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_kernel<false, 16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     return e;
 }
 
@@ -694,6 +697,7 @@ cudaError_t launch_align(const AlignArgs &a, cudaStream_t st)
     case 1: return launch_align_cl<1>(a, fit, need, st);
     case 2: return launch_align_cl<2>(a, fit, need, st);
     case 4: return launch_align_cl<4>(a, fit, need, st);
+    case 16: return launch_align_cl<16>(a, fit, need, st);
     default: return launch_align_cl<8>(a, fit, need, st);
     }
 }

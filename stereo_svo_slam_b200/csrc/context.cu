@@ -135,7 +135,7 @@ struct svo_ctx {
     };
     std::vector<FrameGraph> graphs;
     bool use_graphs = true;
-    int align_cluster = 8;    // SMs per alignment solve (svo_set_align_cluster)
+    int align_cluster = 0;    // SMs per alignment solve (svo_set_align_cluster); 0 = by keypoint count: 8, or 16 above 1024 keypoints
     bool use_fork = true;     // two-branch frame graph (SVO_NO_FORK=1: linear chain)
     bool use_ingest = true;   // SM-driven frame ingest instead of copy-engine DMA (SVO_NO_INGEST=1 turns it off)
     unsigned long long graph_clock = 0;
@@ -251,7 +251,7 @@ extern "C" int svo_ctx_create(const svo_camera_settings *s, int device, int widt
     }
     if (getenv("SVO_ALIGN_CLUSTER")) {
         const int c = atoi(getenv("SVO_ALIGN_CLUSTER"));
-        if (c == 1 || c == 2 || c == 4 || c == 8) ctx->align_cluster = c;
+        if (c == 1 || c == 2 || c == 4 || c == 8 || c == 16) ctx->align_cluster = c;
     }
     if (getenv("SVO_DEBUG_MARKS")) {
         if (cudaHostAlloc(&ctx->h_marks, 64 * sizeof(int), cudaHostAllocMapped) == cudaSuccess) {
@@ -682,7 +682,7 @@ extern "C" int svo_debug_marks(svo_ctx *ctx, int *out64)
 
 extern "C" int svo_set_align_cluster(svo_ctx *ctx, int ctas)
 {
-    if (!ctx || (ctas != 1 && ctas != 2 && ctas != 4 && ctas != 8)) return SVO_ERR_INVALID;
+    if (!ctx || (ctas != 0 && ctas != 1 && ctas != 2 && ctas != 4 && ctas != 8 && ctas != 16)) return SVO_ERR_INVALID;
     if (ctx->track_pending) { snprintf(ctx->err, sizeof(ctx->err), "svo_set_align_cluster while a frame is in flight"); return SVO_ERR_STATE; }
     if (ctas != ctx->align_cluster) {
         ctx->align_cluster = ctas;
@@ -863,7 +863,7 @@ static void fill_align_args(svo_ctx *ctx, int prev_slot, int cur_slot, AlignArgs
     a.scratch = ctx->d_align_scratch; a.max_kps = ctx->max_kps; a.cam = ctx->cam;
     a.probe_level = -1; a.probe_grad = nullptr;
     a.dbg = ctx->d_marks ? ctx->d_marks + 16 : nullptr;
-    a.cluster = ctx->align_cluster;
+    a.cluster = ctx->align_cluster ? ctx->align_cluster : (n > 1024 ? 16 : 8);
     (void)n;
 }
 
@@ -1121,7 +1121,7 @@ static int enqueue_track(svo_ctx *ctx, int prev_slot, int cur_slot, int n, int g
     int launches = 0;
     // 1. sparse image alignment (stereo_slam.cpp:60-67)
     AlignArgs aa;
-    fill_align_args(ctx, prev_slot, cur_slot, aa, n, true);
+    fill_align_args(ctx, prev_slot, cur_slot, aa, grid_n, true);   // grid_n: the keypoint bucket (decides the cluster size with the graph)
     if (prof) CK(cudaEventRecord(ctx->sev[2], ctx->stream));
     mark(ctx, 4);
     CK(launch_align(aa, ctx->stream)); launches++;

@@ -223,7 +223,7 @@ def _keypoints_with_depth(seq, c, k, L, ocs):
     return xy.astype(np.float32), np.array(P, np.float32)
 
 
-@pytest.mark.parametrize("cfg,cluster", [("S", 8), ("C3", 8), ("C3", 4), ("C3", 2), ("C3", 1), ("S", 1)])
+@pytest.mark.parametrize("cfg,cluster", [("S", 8), ("C3", 8), ("C3", 4), ("C3", 2), ("C3", 1), ("S", 1), ("C3", 16)])
 def test_align_probe_and_solve(cfg, cluster):
     gcs, ocs = mk(cfg)
     seq, c, (L0, R0), (L1, R1) = _scene(cfg, 3, 4)
@@ -359,7 +359,7 @@ def test_track_frame_teacher_forced(cfg, frames):
 
 
 # ----------------------------------------------------------------------------------------------- whole pipeline
-@pytest.mark.parametrize("cfg,frames,cluster", [("S", 30, 8), ("C3", 12, 8), ("C3", 12, 2), ("C3", 12, 1), ("C4", 5, 8)])
+@pytest.mark.parametrize("cfg,frames,cluster", [("S", 30, 8), ("C3", 12, 8), ("C3", 12, 2), ("C3", 12, 1), ("C4", 5, 8), ("C4", 5, 16)])
 def test_slam_free_running_matches_oracle(cfg, frames, cluster):
     from stereo_svo_slam_b200 import StereoSlam
     gcs, ocs = mk(cfg)
