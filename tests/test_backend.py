@@ -108,3 +108,26 @@ def test_websocket_round_trip(resource, message, key):
     srv.close()
     msg = json.loads(got["text"])
     assert (isinstance(msg, list) and len(msg) == 2) if key is None else key in msg
+
+
+def test_slam_accelerator_views_follow_the_cython_wrapper():
+    """slam_accelerator drop-in: attribute-style access of src/python/wrapper/slam_accelerator.pyx
+    (draw_kps.py reads kps2d[i].x, info[i].color['r'], info[i].type == KeyPointType.KP_FAST, pose.x, id)."""
+    from stereo_svo_slam_b200 import slam_accelerator as sa
+    cs = sa.CameraSettings()
+    cs.fx, cs.grid_width, cs.max_pyramid_levels = 470.0, 40, 5            # fields assigned one by one (src/python/main.py:28-46)
+    assert cs.fx == 470.0 and cs.grid_width == 40 and cs.baseline == 0.0
+    s = FakeSlam()
+    f = s.kfs[1]
+    f.id = 7
+    f.kps.kps2d = np.array([[1.5, 2.5], [3.0, 4.0], [5.0, 6.0]], np.float32)
+    f.kps.info["type"][1] = 1
+    f.kps.info["keyframe_id"][2] = 3
+    f.image = lambda kind, level: np.full((4 >> level, 6 >> level), 9, np.uint8)
+    v = sa.KeyFrame(f, levels=2)
+    assert v.id == 7 and v.pose.x == 1.0 and abs(v.pose.rz - 0.3) < 1e-6
+    assert len(v.kps.kps2d) == 3 and v.kps.kps2d[0].x == 1.5 and v.kps.kps3d[2].z == 4.0
+    assert v.kps.info[1].type == sa.KeyPointType.KP_EDGELET and v.kps.info[0].type == sa.KeyPointType.KP_FAST
+    assert v.kps.info[1].color == {"r": 3, "g": 4, "b": 5} and v.kps.info[2].keyframe_id == 3
+    assert [im.shape for im in v.stereo_image.left] == [(4, 6), (2, 3)] and len(v.stereo_image.right) == 1
+    assert sa.StereoSlam(cs).get_frame() is None and sa.StereoSlam(cs).get_keyframes() == []

@@ -564,3 +564,27 @@ def test_ingest_from_pinned_and_device_memory(c3ctx, fixture_images):
     slot = ctx.upload(wl, wr)
     assert (ctx.download(slot, 0, 0) == L).all() and (ctx.download(slot, 1, 0) == R).all()
     ctx.release(slot)
+
+
+def test_slam_accelerator_drop_in_runs_the_cuda_path():
+    """the reference's Python entry points (slam_accelerator.pyx:50-91) over the CUDA library: same results as the facade"""
+    from stereo_svo_slam_b200 import StereoSlam, slam_accelerator as sa
+    seq = synth.make_sequence("S")
+    c = synth.CONFIGS["S"]
+    cs = sa.CameraSettings()
+    for k, v in synth.settings_dict("S").items():
+        setattr(cs, k, v)
+    a, b = sa.StereoSlam(cs), StereoSlam(capi.CameraSettings(**synth.settings_dict("S")), c["width"], c["height"])
+    assert a.get_frame() is None
+    for k in range(5):
+        L, R = seq.render(k)
+        a.new_image(L, R, k / 20.0)
+        b.new_image(L, R, k / 20.0)
+    fa, fb = a.get_frame(), b.get_frame()
+    assert fa.id == fb.id == 4 and np.allclose([fa.pose.x, fa.pose.y, fa.pose.z, fa.pose.rx, fa.pose.ry, fa.pose.rz], fb.pose, atol=0)
+    assert len(fa.kps.kps2d) == len(fb.kps) and fa.kps.kps2d[3].x == float(fb.kps.kps2d[3, 0]) and fa.kps.kps3d[3].z == float(fb.kps.kps3d[3, 2])
+    kf = a.get_keyframe()
+    assert (kf.stereo_image.left[0] == seq.render(0)[0]).all() and kf.stereo_image.left[1].shape == (c["height"] // 2, c["width"] // 2)
+    assert kf.kps.info[0].type in (sa.KeyPointType.KP_FAST, sa.KeyPointType.KP_EDGELET) and set(kf.kps.info[0].color) == {"r", "g", "b"}
+    assert len(a.get_keyframes()) == b.keyframe_count() and len(a.get_trajectory()) == 5
+    b.close()
