@@ -71,53 +71,7 @@ static void arena_release(SlotArena *a)
     delete a;
 }
 
-// Keypoint-block transfer between the page-locked host mirror and the device block, by the SMs instead of the copy engines:
-// the block is laid out for the context's keypoint CAPACITY (C3: 115 KB in, 133 KB out), a DMA copy moves all of it and
-// costs ~10-15 us of engine time per frame and direction (at 50 k frames/s the D2H engine would be ~75 % busy); this
-// kernel moves the n live entries of every array (C3, 430 keypoints: 21 KB in, 28 KB out) with 16-byte accesses.
-struct IoCopyArgs {
-    const uint8_t *src;
-    uint8_t *dst;
-    const int *n_ptr;        // live keypoints (in `src`'s header for the import, in device memory for the export)
-    int max_n, narr;
-    struct { unsigned off, elem, per_n; } arr[20];   // per_n: n * elem bytes, else elem bytes
-};
-__global__ void __launch_bounds__(256) io_copy_kernel(IoCopyArgs a)
-{
-    __shared__ unsigned first[21];   // first 16-byte chunk of every array in the flattened chunk list
-    const int n = min(max(*a.n_ptr, 0), a.max_n);
-    if (threadIdx.x == 0) {
-        unsigned acc = 0;
-        for (int k = 0; k < a.narr; k++) {
-            first[k] = acc;
-            acc += ((a.arr[k].per_n ? (unsigned)n * a.arr[k].elem : a.arr[k].elem) + 15) / 16;   // arrays are 64-byte aligned and padded
-        }
-        first[a.narr] = acc;
-    }
-    __syncthreads();
-    const unsigned total = first[a.narr];
-    // all loads of a batch are issued before the first store: when `src` is host memory the whole block costs about one
-    // PCIe round trip after the one that fetched n
-    for (unsigned base = threadIdx.x; base < total; base += 256 * 8) {
-        uint4 v[8];
-        unsigned off[8];
-#pragma unroll
-        for (int q = 0; q < 8; q++) {
-            const unsigned c = base + q * 256;
-            off[q] = 0xffffffffu;
-            if (c < total) {
-                int k = 0;
-                while (c >= first[k + 1]) k++;
-                off[q] = a.arr[k].off + (c - first[k]) * 16;
-                v[q] = *reinterpret_cast<const uint4 *>(a.src + off[q]);
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < 8; q++)
-            if (off[q] != 0xffffffffu) *reinterpret_cast<uint4 *>(a.dst + off[q]) = v[q];
-
-    }
-}
+__global__ void __launch_bounds__(256) io_copy_kernel(IoCopyArgs a) { io_copy_block(a); }
 
 struct Slot {
     uint8_t *base = nullptr;
@@ -168,7 +122,7 @@ struct svo_ctx {
     int cell_cap = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaStream_t stream2 = nullptr;            // side branch of the captured frame graph (LK pyramid || alignment, SSD || refinement)
-    cudaEvent_t fev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t fev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     float last_ms = 0;
     int last_launches = 0;
     bool track_pending = false;
@@ -326,7 +280,7 @@ extern "C" int svo_ctx_create(const svo_camera_settings *s, int device, int widt
     CKC(cudaSetDevice(device));
     CKC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CKC(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
-    for (int k = 0; k < 4; k++) CKC(cudaEventCreateWithFlags(&ctx->fev[k], cudaEventDisableTiming));
+    for (int k = 0; k < 5; k++) CKC(cudaEventCreateWithFlags(&ctx->fev[k], cudaEventDisableTiming));
     CKC(cudaEventCreate(&ctx->ev0));
     CKC(cudaEventCreate(&ctx->ev1));
     for (int k = 0; k < 9; k++) CKC(cudaEventCreate(&ctx->sev[k]));
@@ -431,7 +385,7 @@ extern "C" int svo_ctx_destroy(svo_ctx *ctx)
         if (ctx->d_rect_packed[k]) cudaFree(ctx->d_rect_packed[k]);
         if (ctx->d_raw[k]) cudaFree(ctx->d_raw[k]);
     }
-    for (int k = 0; k < 4; k++) if (ctx->fev[k]) cudaEventDestroy(ctx->fev[k]);
+    for (int k = 0; k < 5; k++) if (ctx->fev[k]) cudaEventDestroy(ctx->fev[k]);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -537,7 +491,7 @@ static uint8_t *stage_images(svo_ctx *ctx, const uint8_t *left, size_t ls, const
 
 // stream part of an upload: copies + pyramid kernels (stereo_slam.cpp:135-139).  For src_kind 0 `left`/`right`
 // are the two halves of the staging buffer.
-static int enqueue_pyramids(svo_ctx *ctx, Slot &s, bool forked = false);
+static int enqueue_pyramids(svo_ctx *ctx, Slot &s, bool forked = false, bool with_import = false);
 static int enqueue_upload(svo_ctx *ctx, Slot &s, const uint8_t *left, size_t ls, const uint8_t *right, size_t rs, int src_kind,
                           bool copies_only = false)
 {
@@ -578,7 +532,8 @@ static int frame_pyr_launches(const svo_ctx *ctx, const Slot &s) { return pyr_la
 
 // forked (only while capturing the frame graph): the LK pyramid goes to a side branch that rejoins in front of the KLT
 // kernel, so it runs beside the half-sample pyramid, the keypoint upload and the alignment solve instead of before them
-static int enqueue_pyramids(svo_ctx *ctx, Slot &s, bool forked)
+// with_import (forked only): the keypoint block is fetched at the head of the side branch, beside the half-sample pyramid
+static int enqueue_pyramids(svo_ctx *ctx, Slot &s, bool forked, bool with_import)
 {
     if (rectifying(ctx)) {
         RemapArgs ra;
@@ -593,6 +548,10 @@ static int enqueue_pyramids(svo_ctx *ctx, Slot &s, bool forked)
         CK(cudaEventRecord(ctx->fev[0], ctx->stream));
         CK(cudaStreamWaitEvent(ctx->stream2, ctx->fev[0], 0));
         lk_stream = ctx->stream2;
+        if (with_import) {
+            io_copy_kernel<<<1, 256, 0, ctx->stream2>>>(ctx->io_in);
+            CK(cudaEventRecord(ctx->fev[4], ctx->stream2));
+        }
     }
     for (int k = 0; k <= diag_dup("pyr"); k++) {
         launch_pyr_halfsample(s.dev, ctx->stream);
@@ -1179,14 +1138,16 @@ static int validate_and_pack(svo_ctx *ctx, svo_track_io *io)
 
 // stream part of a tracking frame; grid_n = number of per-keypoint CTAs to launch (>= n; the kernels read n from
 // device memory), prof = record the per-stage events
-static int enqueue_track(svo_ctx *ctx, int prev_slot, int cur_slot, int n, int grid_n, bool prof, int *launches_out, bool forked = false)
+static int enqueue_track(svo_ctx *ctx, int prev_slot, int cur_slot, int n, int grid_n, bool prof, int *launches_out, bool forked = false,
+                         bool import_on_branch = false)
 {
     const IoLayout &L = ctx->lay;
     uint8_t *h = ctx->h_io;
     int launches = 0;
     // all inputs: the live entries by an SM-driven copy from the page-locked mirror, else one DMA of the whole capacity
     // (in + in/out regions are contiguous)
-    if (ctx->d_hio) { io_copy_kernel<<<1, 256, 0, ctx->stream>>>(ctx->io_in); launches++; }
+    if (import_on_branch) { CK(cudaStreamWaitEvent(ctx->stream, ctx->fev[4], 0)); launches++; }
+    else if (ctx->d_hio) { io_copy_kernel<<<1, 256, 0, ctx->stream>>>(ctx->io_in); launches++; }
     else CK(cudaMemcpyAsync(ctx->d_io, h, L.pose_aligned, cudaMemcpyHostToDevice, ctx->stream));
     // 1. sparse image alignment (stereo_slam.cpp:60-67)
     AlignArgs aa;
@@ -1251,6 +1212,7 @@ static int enqueue_track(svo_ctx *ctx, int prev_slot, int cur_slot, int n, int g
         fa.kps2d = DP(float, kps2d_ref_in); fa.ref_kps2d = DP(float, ref_kps2d); fa.kps3d = DP(float, kps3d);
         fa.flags = DP(uint8_t, flags); fa.inlier = DP(int, inlier); fa.outlier = DP(int, outlier); fa.kf_state = DP(float, kf_state);
         fa.pose = DP(float, pose_refined); fa.kps2d_out = DP(float, kps2d_out); fa.n_ptr = DP(int, n); fa.max_kps = grid_n; fa.cam = ctx->cam;
+        fa.do_export = ctx->d_hio != nullptr; fa.exp = ctx->io_out;   // results go to the host mirror from the same kernel
         mark(ctx, 8);
         launch_depth_filter(fa, ctx->stream); launches++;
         mark(ctx, 9);
@@ -1260,7 +1222,7 @@ static int enqueue_track(svo_ctx *ctx, int prev_slot, int cur_slot, int n, int g
     if (prof) CK(cudaEventRecord(ctx->sev[7], ctx->stream));
     CK(cudaGetLastError());
     // all outputs back to the page-locked mirror (in/out + out regions are contiguous)
-    if (ctx->d_hio) { io_copy_kernel<<<1, 256, 0, ctx->stream>>>(ctx->io_out); launches++; }
+    if (ctx->d_hio) { if (n <= 0) { io_copy_kernel<<<1, 256, 0, ctx->stream>>>(ctx->io_out); launches++; } }
     else CK(cudaMemcpyAsync(h + L.inout_begin, ctx->d_io + L.inout_begin, L.total - L.inout_begin, cudaMemcpyDeviceToHost, ctx->stream));
     mark(ctx, 10);
     *launches_out = launches;
@@ -1298,9 +1260,9 @@ static int capture_frame_graph(svo_ctx *ctx, svo_ctx::FrameGraph &g, int n, cuda
     Slot &s = ctx->slots[g.cur_slot];
     CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
     int launches = 0;
-    const bool forked = ctx->use_fork;
-    int rc = enqueue_pyramids(ctx, s, forked);
-    if (!rc) rc = enqueue_track(ctx, g.prev_slot, g.cur_slot, n, g.bucket, false, &launches, forked);
+    const bool forked = ctx->use_fork, branch_import = forked && ctx->d_hio != nullptr;
+    int rc = enqueue_pyramids(ctx, s, forked, branch_import);
+    if (!rc) rc = enqueue_track(ctx, g.prev_slot, g.cur_slot, n, g.bucket, false, &launches, forked, branch_import);
     cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
     if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
     CK(e);

@@ -592,7 +592,10 @@ void launch_stereo_ssd(const SsdArgs &a, cudaStream_t st)
 // ---------------------------------------------------------------------------------------------------------
 struct FrameMats { float R[9]; double Rdn[9]; };
 
-__global__ void __launch_bounds__(128) depth_filter_kernel(FilterArgs a)
+// One CTA walks all keypoints (a thread per keypoint, grid-stride), so that the kernel can finish with the export of the
+// frame's results to the host mirror (io_copy_block) without a grid-wide barrier — one launch less per frame.
+#define DF_THREADS 512
+__global__ void __launch_bounds__(DF_THREADS) depth_filter_kernel(FilterArgs a)
 {
     __shared__ FrameMats fm;
     const int n = min(*a.n_ptr, a.max_kps);
@@ -602,105 +605,109 @@ __global__ void __launch_bounds__(128) depth_filter_kernel(FilterArgs a)
         dev_rodrigues_d(-p[3], -p[4], -p[5], fm.Rdn);
     }
     __syncthreads();
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const DevCam cam = a.cam;
-    const float fx = cam.fx, fy = cam.fy, cx = cam.cx, cy = cam.cy, baseline = cam.baseline;
-    const float *c2 = a.pose;  // frame translation
-    const float *kfp = a.kf_pose_table + (size_t)a.keyframe_ids[i] * 24;  // pose(6) R(9) Ri(9)
-    const float *c1 = kfp, *Rk = kfp + 6, *Rik = kfp + 15;
-    const float u = a.kps2d[2 * i], v = a.kps2d[2 * i + 1];
-    uint8_t flags = a.flags[i];
-    int inl = a.inlier[i], outl = a.outlier[i];
-    float P0 = a.kps3d[3 * i], P1 = a.kps3d[3 * i + 1], P2 = a.kps3d[3 * i + 2];
+    for (int i = threadIdx.x; i < n; i += DF_THREADS) {
+        const DevCam cam = a.cam;
+        const float fx = cam.fx, fy = cam.fy, cx = cam.cx, cy = cam.cy, baseline = cam.baseline;
+        const float *c2 = a.pose;  // frame translation
+        const float *kfp = a.kf_pose_table + (size_t)a.keyframe_ids[i] * 24;  // pose(6) R(9) Ri(9)
+        const float *c1 = kfp, *Rk = kfp + 6, *Rik = kfp + 15;
+        const float u = a.kps2d[2 * i], v = a.kps2d[2 * i + 1];
+        uint8_t flags = a.flags[i];
+        int inl = a.inlier[i], outl = a.outlier[i];
+        float P0 = a.kps3d[3 * i], P1 = a.kps3d[3 * i + 1], P2 = a.kps3d[3 * i + 2];
 
-    // ---- outlier_check (depth_filter.cpp:52-128)
-    {
-        const float d = a.disparity[i];
-        const float _z = baseline / fmaxf(d, 0.5f);
-        const float _x = (u - cx) / fx * _z;
-        const float _y = (v - cy) / fy * _z;
-        float w0, w1, w2;
-        dev_m33v(fm.R, _x, _y, _z, w0, w1, w2);
-        w0 += c2[0]; w1 += c2[1]; w2 += c2[2];
-        float a0, a1, a2, b0, b1, b2;
-        dev_m33v(Rik, w0 - c1[0], w1 - c1[1], w2 - c1[2], a0, a1, a2);
-        dev_m33v(Rik, P0 - c1[0], P1 - c1[1], P2 - c1[2], b0, b1, b2);
-        const float disp_ref = baseline / b2;
-        const float disp = baseline / a2;
-        const float pixel_distance = disp - disp_ref;
-        if (fabsf(pixel_distance) > 5 * 0.5f) outl++;
-        else inl++;
-    }
-    // ---- update_kps3d (depth_filter.cpp:130-257)
-    float kx = a.kf_state[2 * i], kP = a.kf_state[2 * i + 1];
-    {
-        float d0, d1, d2;
-        dev_m33v(Rik, fabsf(c1[0] - c2[0]), fabsf(c1[1] - c2[1]), fabsf(c1[2] - c2[2]), d0, d1, d2);
-        if (flags & (SVO_F_IGN_COMPLETE | SVO_F_IGN_REFINE)) {
-            outl++;
-        } else if (!((double)d0 < 0.1 && (double)d1 < 0.1)) {
-            const float rfx = a.ref_kps2d[2 * i], rfy = a.ref_kps2d[2 * i + 1];
-            float p10, p11, p12, p20, p21, p22;
-            dev_m33v(Rk, rfx - cx, rfy - cy, fx, p10, p11, p12);
-            dev_m33v(fm.R, u - cx, v - cy, fx, p20, p21, p22);
-            // least squares [p1 -p2] l = c2 - c1 (cv::solve(DECOMP_SVD) in the reference; normal equations in double here)
-            const double y0 = (double)(c2[0] - c1[0]), y1 = (double)(c2[1] - c1[1]), y2 = (double)(c2[2] - c1[2]);
-            const double a00 = (double)p10 * p10 + (double)p11 * p11 + (double)p12 * p12;
-            const double a01 = -((double)p10 * p20 + (double)p11 * p21 + (double)p12 * p22);
-            const double a11 = (double)p20 * p20 + (double)p21 * p21 + (double)p22 * p22;
-            const double r0 = (double)p10 * y0 + (double)p11 * y1 + (double)p12 * y2;
-            const double r1 = -((double)p20 * y0 + (double)p21 * y1 + (double)p22 * y2);
-            const double det = a00 * a11 - a01 * a01;
-            const float l0 = (float)((a11 * r0 - a01 * r1) / det);
-            // 1x1 cv::KalmanFilter (A = H = 1, Q = 1e-4): predict + correct, OpenCV's float/double mix
-            const float dev = (float)(0.5 / (double)sqrtf(d0 * d0 + d1 * d1));
-            const float Rn = dev * dev;
-            const float xpre = kx;
-            const float Ppre = (float)((double)kP + (double)1e-4f);
-            // Vec3f new_p = inv_rotation_kf*l(0)*(p1-c1)  (matrix scaled first)
-            float Ms[9];
-#pragma unroll
-            for (int q = 0; q < 9; q++) Ms[q] = Rik[q] * l0;
-            float np0, np1, np2;
-            dev_m33v(Ms, p10 - c1[0], p11 - c1[1], p12 - c1[2], np0, np1, np2);
-            const float meas = 1 / np2;
-            const float t3 = (float)((double)Ppre + (double)Rn);
-            // gain through OpenCV's SVD solve of a 1x1 system
-            const double wd = sqrt((double)t3 * (double)t3);
-            const float uu = t3 * (float)(wd > 1.1754943508222875e-38 ? 1. / wd : 0.);
-            const float wf = (float)wd;
-            float K = 0.f;
-            if (fabs((double)wf) > (double)wf * (double)(float)(2.220446049250313e-16 * 2)) {
-                double s = (double)uu * (double)Ppre;
-                s *= 1. / (double)wf;
-                K = (float)(0.0 + s * 1.0);
-            }
-            const float t5 = (float)(-((double)xpre) + (double)meas);
-            kx = (float)((double)K * (double)t5 + (double)xpre);
-            kP = (float)(-((double)K * (double)Ppre) + (double)Ppre);
-            const float _z = (float)(1.0 / (double)kx);
-            const float _x = (rfx - cx) / fx * _z;
-            const float _y = (rfy - cy) / fy * _z;
-            float o0, o1, o2;
-            dev_m33v(Rk, _x, _y, _z, o0, o1, o2);
-            P0 = c1[0] + o0; P1 = c1[1] + o1; P2 = c1[2] + o2;
+        // ---- outlier_check (depth_filter.cpp:52-128)
+        {
+            const float d = a.disparity[i];
+            const float _z = baseline / fmaxf(d, 0.5f);
+            const float _x = (u - cx) / fx * _z;
+            const float _y = (v - cy) / fy * _z;
+            float w0, w1, w2;
+            dev_m33v(fm.R, _x, _y, _z, w0, w1, w2);
+            w0 += c2[0]; w1 += c2[1]; w2 += c2[2];
+            float a0, a1, a2, b0, b1, b2;
+            dev_m33v(Rik, w0 - c1[0], w1 - c1[1], w2 - c1[2], a0, a1, a2);
+            dev_m33v(Rik, P0 - c1[0], P1 - c1[1], P2 - c1[2], b0, b1, b2);
+            const float disp_ref = baseline / b2;
+            const float disp = baseline / a2;
+            const float pixel_distance = disp - disp_ref;
+            if (fabsf(pixel_distance) > 5 * 0.5f) outl++;
+            else inl++;
         }
+        // ---- update_kps3d (depth_filter.cpp:130-257)
+        float kx = a.kf_state[2 * i], kP = a.kf_state[2 * i + 1];
+        {
+            float d0, d1, d2;
+            dev_m33v(Rik, fabsf(c1[0] - c2[0]), fabsf(c1[1] - c2[1]), fabsf(c1[2] - c2[2]), d0, d1, d2);
+            if (flags & (SVO_F_IGN_COMPLETE | SVO_F_IGN_REFINE)) {
+                outl++;
+            } else if (!((double)d0 < 0.1 && (double)d1 < 0.1)) {
+                const float rfx = a.ref_kps2d[2 * i], rfy = a.ref_kps2d[2 * i + 1];
+                float p10, p11, p12, p20, p21, p22;
+                dev_m33v(Rk, rfx - cx, rfy - cy, fx, p10, p11, p12);
+                dev_m33v(fm.R, u - cx, v - cy, fx, p20, p21, p22);
+                // least squares [p1 -p2] l = c2 - c1 (cv::solve(DECOMP_SVD) in the reference; normal equations in double here)
+                const double y0 = (double)(c2[0] - c1[0]), y1 = (double)(c2[1] - c1[1]), y2 = (double)(c2[2] - c1[2]);
+                const double a00 = (double)p10 * p10 + (double)p11 * p11 + (double)p12 * p12;
+                const double a01 = -((double)p10 * p20 + (double)p11 * p21 + (double)p12 * p22);
+                const double a11 = (double)p20 * p20 + (double)p21 * p21 + (double)p22 * p22;
+                const double r0 = (double)p10 * y0 + (double)p11 * y1 + (double)p12 * y2;
+                const double r1 = -((double)p20 * y0 + (double)p21 * y1 + (double)p22 * y2);
+                const double det = a00 * a11 - a01 * a01;
+                const float l0 = (float)((a11 * r0 - a01 * r1) / det);
+                // 1x1 cv::KalmanFilter (A = H = 1, Q = 1e-4): predict + correct, OpenCV's float/double mix
+                const float dev = (float)(0.5 / (double)sqrtf(d0 * d0 + d1 * d1));
+                const float Rn = dev * dev;
+                const float xpre = kx;
+                const float Ppre = (float)((double)kP + (double)1e-4f);
+                // Vec3f new_p = inv_rotation_kf*l(0)*(p1-c1)  (matrix scaled first)
+                float Ms[9];
+    #pragma unroll
+                for (int q = 0; q < 9; q++) Ms[q] = Rik[q] * l0;
+                float np0, np1, np2;
+                dev_m33v(Ms, p10 - c1[0], p11 - c1[1], p12 - c1[2], np0, np1, np2);
+                const float meas = 1 / np2;
+                const float t3 = (float)((double)Ppre + (double)Rn);
+                // gain through OpenCV's SVD solve of a 1x1 system
+                const double wd = sqrt((double)t3 * (double)t3);
+                const float uu = t3 * (float)(wd > 1.1754943508222875e-38 ? 1. / wd : 0.);
+                const float wf = (float)wd;
+                float K = 0.f;
+                if (fabs((double)wf) > (double)wf * (double)(float)(2.220446049250313e-16 * 2)) {
+                    double s = (double)uu * (double)Ppre;
+                    s *= 1. / (double)wf;
+                    K = (float)(0.0 + s * 1.0);
+                }
+                const float t5 = (float)(-((double)xpre) + (double)meas);
+                kx = (float)((double)K * (double)t5 + (double)xpre);
+                kP = (float)(-((double)K * (double)Ppre) + (double)Ppre);
+                const float _z = (float)(1.0 / (double)kx);
+                const float _x = (rfx - cx) / fx * _z;
+                const float _y = (rfy - cy) / fy * _z;
+                float o0, o1, o2;
+                dev_m33v(Rk, _x, _y, _z, o0, o1, o2);
+                P0 = c1[0] + o0; P1 = c1[1] + o1; P2 = c1[2] + o2;
+            }
+        }
+        // ---- post-processing (stereo_slam.cpp:205-226)
+        if (outl > inl) flags |= SVO_F_IGN_COMPLETE;
+        if (inl > outl) flags &= (uint8_t)~SVO_F_IGN_TEMP;
+        a.kps3d[3 * i] = P0; a.kps3d[3 * i + 1] = P1; a.kps3d[3 * i + 2] = P2;
+        a.flags[i] = flags; a.inlier[i] = inl; a.outlier[i] = outl;
+        a.kf_state[2 * i] = kx; a.kf_state[2 * i + 1] = kP;
+        // ---- re-projection of the updated point (stereo_slam.cpp:228-229)
+        float ou, ov;
+        dev_project(fm.Rdn, P0, P1, P2, c2[0], c2[1], c2[2], fx, fy, cx, cy, cam.k1, cam.k2, cam.p1, cam.p2, cam.k3, ou, ov);
+        a.kps2d_out[2 * i] = ou; a.kps2d_out[2 * i + 1] = ov;
     }
-    // ---- post-processing (stereo_slam.cpp:205-226)
-    if (outl > inl) flags |= SVO_F_IGN_COMPLETE;
-    if (inl > outl) flags &= (uint8_t)~SVO_F_IGN_TEMP;
-    a.kps3d[3 * i] = P0; a.kps3d[3 * i + 1] = P1; a.kps3d[3 * i + 2] = P2;
-    a.flags[i] = flags; a.inlier[i] = inl; a.outlier[i] = outl;
-    a.kf_state[2 * i] = kx; a.kf_state[2 * i + 1] = kP;
-    // ---- re-projection of the updated point (stereo_slam.cpp:228-229)
-    float ou, ov;
-    dev_project(fm.Rdn, P0, P1, P2, c2[0], c2[1], c2[2], fx, fy, cx, cy, cam.k1, cam.k2, cam.p1, cam.p2, cam.k3, ou, ov);
-    a.kps2d_out[2 * i] = ou; a.kps2d_out[2 * i + 1] = ov;
+    if (a.do_export) {
+        __syncthreads();   // this CTA wrote the last results of the frame; everything earlier in the stream is complete
+        io_copy_block(a.exp);
+    }
 }
 
 void launch_depth_filter(const FilterArgs &a, cudaStream_t st)
 {
-    if (a.max_kps <= 0) return;
-    depth_filter_kernel<<<(a.max_kps + 127) / 128, 128, 0, st>>>(a);
+    if (a.max_kps <= 0 && !a.do_export) return;
+    depth_filter_kernel<<<1, DF_THREADS, 0, st>>>(a);
 }
