@@ -588,3 +588,24 @@ def test_slam_accelerator_drop_in_runs_the_cuda_path():
     assert kf.kps.info[0].type in (sa.KeyPointType.KP_FAST, sa.KeyPointType.KP_EDGELET) and set(kf.kps.info[0].color) == {"r", "g", "b"}
     assert len(a.get_keyframes()) == b.keyframe_count() and len(a.get_trajectory()) == 5
     b.close()
+
+
+def test_free_running_with_euroc_yaml_settings():
+    """the shipped src/app/EuRoC.yaml algorithm settings (grid 54x48, search 60/6, 6 pyramid levels, alignment down to
+    level 2): 8 tiles of horizontal SSD positions, three alignment levels, 23x15-pixel top level"""
+    from stereo_svo_slam_b200 import StereoSlam
+    over = dict(grid_width=54, grid_height=48, search_x=60, search_y=6, max_pyramid_levels=6, min_pyramid_level_pose_estimation=2)
+    gcs, ocs = mk("C3", **over)
+    seq = synth.make_sequence("C3", seed=4)
+    o = orc.OracleSlam(ocs, 752, 480, tracing=False)
+    g = StereoSlam(gcs, 752, 480)
+    for k in range(8):
+        L, R = seq.render(k)
+        o.new_image(L, R, k / 20.0)
+        g.new_image(L, R, k / 20.0)
+        gp, op = g.pose(), o.pose()
+        assert pose_close(gp, op) or (np.abs(gp[:3] - op[:3]).max() <= 5 * POSE_TOL_T and np.abs(gp[3:] - op[3:]).max() <= 5 * POSE_TOL_R), (k, gp, op)
+        assert len(g.get_frame().kps) == o.n_kps() and g.keyframe_count() == o.n_keyframes()
+    gt = seq.pose(7)
+    assert np.abs(g.pose()[:3] - gt[:3]).max() < 0.05
+    g.close()
