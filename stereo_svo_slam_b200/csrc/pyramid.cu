@@ -114,13 +114,54 @@ __global__ void __launch_bounds__(256) lk_pyrdown_kernel(LevelDesc src, LevelDes
     dst.ptr[(ptrdiff_t)(yp - SVO_LK_PAD) * dst.pitch + (xp - SVO_LK_PAD)] = (uint8_t)((acc + 128) >> 8);
 }
 
+// 16 bytes per thread.  Blocks with blockIdx.y < padded height copy the interior chunks of one row (one aligned 16-byte load
+// each: the 32-pixel frame is two chunks wide, so chunk c of the padded row is source bytes 16(c-2) ..); the blocks after
+// them assemble the four frame chunks of every row byte by byte through the reflection — kept in warps of their own so
+// that the copy warps never run the slow path.  Needs width, source pitch and both base addresses to be multiples of 16
+// (the per-byte kernel covers the rest).
+__global__ void __launch_bounds__(64) lk_pad_level0_vec_kernel(LevelDesc src, LevelDesc dst)
+{
+    const int PH = dst.h + 2 * SVO_LK_PAD;
+    const int chunks = (dst.w + 2 * SVO_LK_PAD) >> 4;
+    if ((int)blockIdx.y < PH) {
+        const int yp = blockIdx.y;
+        const int y = dev_reflect101(yp - SVO_LK_PAD, dst.h);
+        const uint8_t *srow = src.ptr + (size_t)y * src.pitch;
+        uint8_t *drow = dst.ptr + ((ptrdiff_t)(yp - SVO_LK_PAD)) * dst.pitch - SVO_LK_PAD;
+        for (int c = 2 + threadIdx.x; c < chunks - 2; c += blockDim.x)
+            *reinterpret_cast<uint4 *>(drow + c * 16) = __ldg(reinterpret_cast<const uint4 *>(srow + (c - 2) * 16));
+        return;
+    }
+    const int item = ((int)blockIdx.y - PH) * blockDim.x + threadIdx.x;   // (row, one of the four frame chunks)
+    const int yp = item >> 2, which = item & 3;
+    if (yp >= PH) return;
+    const int c = which < 2 ? which : chunks - 4 + which;
+    const int y = dev_reflect101(yp - SVO_LK_PAD, dst.h);
+    const uint8_t *srow = src.ptr + (size_t)y * src.pitch;
+    uint8_t *drow = dst.ptr + ((ptrdiff_t)(yp - SVO_LK_PAD)) * dst.pitch - SVO_LK_PAD;
+    const int x0 = c * 16 - SVO_LK_PAD;
+    uint8_t b[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) b[k] = srow[dev_reflect101(x0 + k, dst.w)];
+    *reinterpret_cast<uint4 *>(drow + c * 16) = *reinterpret_cast<uint4 *>(b);
+}
+
 void launch_lk_pyramid(const ImageSetDev &s, cudaStream_t st)
 {
     {
         const LevelDesc &d = s.lk[0];
-        int PW = d.w + 2 * SVO_LK_PAD, PH = d.h + 2 * SVO_LK_PAD;
-        dim3 grid((PW / 4 + 1 + 255) / 256, PH);
-        lk_pad_level0_kernel<<<grid, 256, 0, st>>>(s.left[0], d);
+        const int PW = d.w + 2 * SVO_LK_PAD, PH = d.h + 2 * SVO_LK_PAD;
+        const LevelDesc &l0 = s.left[0];
+        const uint8_t *dorigin = d.ptr - (ptrdiff_t)SVO_LK_PAD * d.pitch - SVO_LK_PAD;
+        const bool vec = (d.w % 16 == 0) && (l0.pitch % 16 == 0) && (d.pitch % 16 == 0) && ((reinterpret_cast<uintptr_t>(l0.ptr) & 15) == 0) &&
+                         ((reinterpret_cast<uintptr_t>(dorigin) & 15) == 0);
+        if (vec) {
+            dim3 grid(1, PH + (PH * 4 + 63) / 64);
+            lk_pad_level0_vec_kernel<<<grid, 64, 0, st>>>(l0, d);
+        } else {
+            dim3 grid((PW / 4 + 1 + 255) / 256, PH);
+            lk_pad_level0_kernel<<<grid, 256, 0, st>>>(l0, d);
+        }
     }
     for (int l = 1; l < SVO_LK_LEVELS; l++) {
         const LevelDesc &d = s.lk[l];
