@@ -131,6 +131,15 @@ int svo_klt_slots(svo_ctx *ctx, int prev_slot, int cur_slot, const float *prev_p
 int svo_reproj_refine(svo_ctx *ctx, const float *kps2d, const float *kps3d, const uint8_t *flags, int n,
                       const float pose_in[6], float pose_out[6], float *cost, int *evals2);
 
+/* DepthFilter::update_depth (depth_filter.cpp:40-50) as one stage: stereo SSD disparities at kps2d on image set `slot`
+ * (calculate_disparities :259-327), outlier vote (:52-128), triangulation against the origin keyframe + 1x1 Kalman update
+ * on the inverse depth (:130-257), then the flag post-processing and the re-projection with `pose` that
+ * StereoSlam::new_image applies right after (stereo_slam.cpp:205-229).  kps3d / flags / counters / kf_state are updated in
+ * place; disparity and kps2d_out may be NULL.  keyframe_ids refer to keyframes registered with svo_keyframe_commit. */
+int svo_depth_filter_update(svo_ctx *ctx, int slot, int n, const float *kps2d, const float *ref_kps2d, const int *keyframe_ids,
+                            float *kps3d, uint8_t *flags, int *inlier_count, int *outlier_count, float *kf_state,
+                            const float pose[6], float *disparity, float *kps2d_out);
+
 /* project_keypoints (transform_keypoints.cpp:11-47) */
 int svo_project(svo_ctx *ctx, const float pose[6], const float *kps3d, int n, float *kps2d);
 

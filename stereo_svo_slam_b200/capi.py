@@ -236,6 +236,20 @@ class Context:
                                          C.byref(cost), _p(ev)))
         return pose_out, cost.value, ev
 
+    def depth_filter_update(self, slot, kps2d, ref_kps2d, keyframe_id, kps3d, flags, inlier, outlier, kf_state, pose):
+        """DepthFilter::update_depth + post-processing as one stage (svo_depth_filter_update); inputs are not modified."""
+        a = dict(kps2d=_f32(kps2d, (-1, 2)).copy(), ref_kps2d=_f32(ref_kps2d, (-1, 2)).copy(),
+                 keyframe_id=np.ascontiguousarray(keyframe_id, dtype=np.int32).copy(), kps3d=_f32(kps3d, (-1, 3)).copy(),
+                 flags=np.ascontiguousarray(flags, dtype=np.uint8).copy(), inlier=np.ascontiguousarray(inlier, dtype=np.int32).copy(),
+                 outlier=np.ascontiguousarray(outlier, dtype=np.int32).copy(), kf_state=_f32(kf_state, (-1, 2)).copy())
+        n = len(a["flags"])
+        a["disparity"], a["kps2d_out"] = np.empty(n, np.float32), np.empty((n, 2), np.float32)
+        pose = _f32(pose)
+        self._ck(lib().svo_depth_filter_update(self.h_ctx, slot, n, _p(a["kps2d"]), _p(a["ref_kps2d"]), _p(a["keyframe_id"]), _p(a["kps3d"]),
+                                               _p(a["flags"]), _p(a["inlier"]), _p(a["outlier"]), _p(a["kf_state"]), _p(pose),
+                                               _p(a["disparity"]), _p(a["kps2d_out"])))
+        return a
+
     def project(self, pose, kps3d):
         kps3d, pose = _f32(kps3d, (-1, 3)), _f32(pose)
         out = np.empty((kps3d.shape[0], 2), np.float32)

@@ -1021,6 +1021,53 @@ extern "C" int svo_reproj_refine(svo_ctx *ctx, const float *kps2d, const float *
     return SVO_OK;
 }
 
+extern "C" int svo_depth_filter_update(svo_ctx *ctx, int slot, int n, const float *kps2d, const float *ref_kps2d, const int *keyframe_ids,
+                                       float *kps3d, uint8_t *flags, int *inlier_count, int *outlier_count, float *kf_state,
+                                       const float pose[6], float *disparity, float *kps2d_out)
+{
+    if (!ctx || !slot_ok(ctx, slot) || !pose) return SVO_ERR_INVALID;
+    int rc = check_n(ctx, n);
+    if (rc) return rc;
+    if (n == 0) return SVO_OK;
+    if (!kps2d || !ref_kps2d || !keyframe_ids || !kps3d || !flags || !inlier_count || !outlier_count || !kf_state) return SVO_ERR_INVALID;
+    for (int i = 0; i < n; i++)
+        if (keyframe_ids[i] < 0 || keyframe_ids[i] >= ctx->kf_count) { snprintf(ctx->err, sizeof(ctx->err), "keypoint %d: unknown keyframe id %d", i, keyframe_ids[i]); return SVO_ERR_INVALID; }
+    CK(cudaSetDevice(ctx->device));
+    if ((rc = set_n(ctx, n))) return rc;
+    if ((rc = up(ctx, ctx->lay.kps2d_ref_in, kps2d, (size_t)n * 8))) return rc;
+    if ((rc = up(ctx, ctx->lay.ref_kps2d, ref_kps2d, (size_t)n * 8))) return rc;
+    if ((rc = up(ctx, ctx->lay.kf_id, keyframe_ids, (size_t)n * 4))) return rc;
+    if ((rc = up(ctx, ctx->lay.kps3d, kps3d, (size_t)n * 12))) return rc;
+    if ((rc = up(ctx, ctx->lay.flags, flags, (size_t)n))) return rc;
+    if ((rc = up(ctx, ctx->lay.inlier, inlier_count, (size_t)n * 4))) return rc;
+    if ((rc = up(ctx, ctx->lay.outlier, outlier_count, (size_t)n * 4))) return rc;
+    if ((rc = up(ctx, ctx->lay.kf_state, kf_state, (size_t)n * 8))) return rc;
+    if ((rc = up(ctx, ctx->lay.pose_refined, pose, 24))) return rc;
+    SsdArgs sa;
+    sa.left0 = ctx->slots[slot].dev.left[0]; sa.right0 = ctx->slots[slot].dev.right0;
+    sa.kps2d = DP(float, kps2d_ref_in); sa.n_ptr = DP(int, n); sa.mode = 1; sa.disparity = DP(float, disparity);
+    sa.max_kps = n; sa.cam = ctx->cam;
+    launch_stereo_ssd(sa, ctx->stream);
+    FilterArgs fa;
+    fa.kf_pose_table = ctx->d_kf_pose; fa.keyframe_ids = DP(int, kf_id); fa.disparity = DP(float, disparity);
+    fa.kps2d = DP(float, kps2d_ref_in); fa.ref_kps2d = DP(float, ref_kps2d); fa.kps3d = DP(float, kps3d);
+    fa.flags = DP(uint8_t, flags); fa.inlier = DP(int, inlier); fa.outlier = DP(int, outlier); fa.kf_state = DP(float, kf_state);
+    fa.pose = DP(float, pose_refined); fa.kps2d_out = DP(float, kps2d_out); fa.n_ptr = DP(int, n); fa.max_kps = n; fa.cam = ctx->cam;
+    fa.do_export = 0;
+    launch_depth_filter(fa, ctx->stream);
+    ctx->launch_total += 2;
+    CK(cudaGetLastError());
+    if ((rc = down(ctx, kps3d, ctx->lay.kps3d, (size_t)n * 12))) return rc;
+    if ((rc = down(ctx, flags, ctx->lay.flags, (size_t)n))) return rc;
+    if ((rc = down(ctx, inlier_count, ctx->lay.inlier, (size_t)n * 4))) return rc;
+    if ((rc = down(ctx, outlier_count, ctx->lay.outlier, (size_t)n * 4))) return rc;
+    if ((rc = down(ctx, kf_state, ctx->lay.kf_state, (size_t)n * 8))) return rc;
+    if (disparity && (rc = down(ctx, disparity, ctx->lay.disparity, (size_t)n * 4))) return rc;
+    if (kps2d_out && (rc = down(ctx, kps2d_out, ctx->lay.kps2d_out, (size_t)n * 8))) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SVO_OK;
+}
+
 extern "C" int svo_project(svo_ctx *ctx, const float pose[6], const float *kps3d, int n, float *kps2d)
 {
     if (!ctx || !pose || !kps3d || !kps2d) return SVO_ERR_INVALID;

@@ -342,6 +342,18 @@ def test_track_frame_teacher_forced(cfg, frames):
             assert np.quantile(rel, 0.99) <= DEPTH_RTOL, (k, np.quantile(rel, 0.99), rel.max())
             kp, okp = out["kps2d"], t("df_out_kps2d").reshape(-1, 2)
             assert np.quantile(np.abs(kp[good] - okp[good]).max(axis=1), 0.99) <= 0.05
+            # the depth filter as a stand-alone stage on the ORACLE's own stage inputs (svo_depth_filter_update): here the
+            # positions are identical, so disparities, votes and flags must agree exactly and depths to the float tolerance
+            cin = t("df_in_counts").reshape(-1, 2).astype(np.int32)
+            s = ctx.depth_filter_update(slot, t("df_in_kps2d").reshape(-1, 2), inp["ref_kps2d"], inp["keyframe_id"], t("df_in_kps3d").reshape(-1, 3),
+                                        t("df_in_flags").astype(np.uint8), cin[:, 0], cin[:, 1], np.stack([t("df_in_kfx"), t("df_in_kfP")], 1),
+                                        t("df_pose"))
+            assert (s["disparity"] == od).all(), (k, np.nonzero(s["disparity"] != od)[0][:8])
+            assert (s["flags"] == ofl).all() and (np.stack([s["inlier"], s["outlier"]], 1) == t("df_out_counts").reshape(-1, 2).astype(np.int32)).all()
+            rel = np.abs(s["kps3d"] - oz).max(axis=1) / np.maximum(1.0, np.abs(oz).max(axis=1))
+            assert rel.max() <= DEPTH_RTOL, (k, rel.max())
+            assert np.abs(s["kf_state"][:, 0] - t("df_out_kfx")).max() <= 1e-3 * np.abs(t("df_out_kfx")).max()
+            assert np.abs(s["kps2d_out"] - okp).max() <= 0.05
         # keyframes created by the oracle in this frame are registered on the device with the oracle's pose
         while n_kf < slam.n_keyframes():
             pose, _, _ = slam.keyframe(n_kf)
