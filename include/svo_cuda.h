@@ -148,6 +148,13 @@ int svo_project(svo_ctx *ctx, const float pose[6], const float *kps3d, int n, fl
 int svo_keyframe_commit(svo_ctx *ctx, int slot, const float pose[6], int *keyframe_id_out);
 /* slot holding keyframe `keyframe_id`'s own copy of the image set (for getters) */
 int svo_keyframe_slot(svo_ctx *ctx, int keyframe_id, int *slot_out);
+/* Build and keep the 31x31 LK templates (window samples, Scharr derivatives, structure tensor; all three levels) of the
+ * keypoints keyframe `keyframe_id` introduced: entries first .. first + count - 1 of its keypoint list, at kps2d (count*2,
+ * keyframe coordinates).  cv::calcOpticalFlowPyrLK (optical_flow.cpp:41-44) rebuilds them from the keyframe's pyramid for
+ * every frame; pyramid and positions never change after KeyFrameManager::create_keyframe, so svo_frame_begin /
+ * svo_track_frame fetch them instead when svo_track_io::keypoint_index is given (same bits either way).  No-op unless
+ * window_size_opt_flow == 31 (env SVO_NO_TEMPLATES=1 turns the cache off). */
+int svo_keyframe_set_templates(svo_ctx *ctx, int keyframe_id, const float *kps2d, int first, int count);
 
 /* ------------------------------------------------------------------ fused per-frame tracking --- */
 /* Everything StereoSlam::new_image does on a tracking frame between the pyramid build and the keyframe
@@ -182,6 +189,9 @@ typedef struct svo_track_io {
     float *disparity;         /* n */
     float *kps2d_refine_in;   /* n*2 : positions fed to the refinement / depth filter */
     int *klt_iters;           /* n   : LK iterations summed over the three levels */
+    /* optional input (NULL: the LK templates are rebuilt from the keyframe pyramids for every frame) */
+    const int *keypoint_index; /* n  in : index of the keypoint in its origin keyframe's list (KeyPointInformation::keypoint_index,
+                                *         stereo_slam_types.hpp:93) — the key of the template cache, svo_keyframe_set_templates */
 } svo_track_io;
 
 int svo_track_frame(svo_ctx *ctx, int prev_slot, int cur_slot, svo_track_io *io);

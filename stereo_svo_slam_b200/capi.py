@@ -58,7 +58,7 @@ class TrackIO(C.Structure):
                 ("align_cost", C.c_float), ("refine_cost", C.c_float), ("align_evals", C.c_int * 16),
                 ("refine_evals", C.c_int * 2), ("klt_pts", C.c_void_p), ("klt_err", C.c_void_p),
                 ("klt_status", C.c_void_p), ("disparity", C.c_void_p), ("kps2d_refine_in", C.c_void_p),
-                ("klt_iters", C.c_void_p)]
+                ("klt_iters", C.c_void_p), ("keypoint_index", C.c_void_p)]
 
 
 def declared_symbols():
@@ -262,8 +262,13 @@ class Context:
         self._ck(lib().svo_keyframe_commit(self.h_ctx, slot, _p(pose), C.byref(out)))
         return out.value
 
+    def keyframe_set_templates(self, keyframe_id, kps2d, first=0):
+        """LK template cache of the keypoints a keyframe introduced (svo_keyframe_set_templates)."""
+        kps2d = _f32(kps2d, (-1, 2))
+        self._ck(lib().svo_keyframe_set_templates(self.h_ctx, keyframe_id, _p(kps2d), first, kps2d.shape[0]))
+
     def track_frame(self, prev_slot, cur_slot, prev_kps2d, kps3d, ref_kps2d, keyframe_id, flags, inlier, outlier, kf_state,
-                    pose_prior):
+                    pose_prior, keypoint_index=None):
         """Fused per-frame tracking (svo_track_frame). Returns a dict of outputs; inputs are not modified."""
         n = len(flags)
         a = dict(prev_kps2d=_f32(prev_kps2d, (-1, 2)).copy(), kps3d=_f32(kps3d, (-1, 3)).copy(),
@@ -283,6 +288,9 @@ class Context:
         io.kps2d, io.klt_pts, io.klt_err, io.klt_status = _p(a["kps2d"]), _p(a["klt_pts"]), _p(a["klt_err"]), _p(a["klt_status"])
         io.disparity, io.kps2d_refine_in = _p(a["disparity"]), _p(a["kps2d_refine_in"])
         io.klt_iters = _p(a["klt_iters"])
+        if keypoint_index is not None:
+            a["keypoint_index"] = np.ascontiguousarray(keypoint_index, dtype=np.int32).copy()
+            io.keypoint_index = _p(a["keypoint_index"])
         for k, v in enumerate(_f32(pose_prior)):
             io.pose_prior[k] = float(v)
         self._ck(lib().svo_track_frame(self.h_ctx, prev_slot, cur_slot, C.byref(io)))

@@ -82,7 +82,7 @@ struct Slot {
 
 // layout of the keypoint I/O block (same offsets on device and in the pinned host mirror)
 struct IoLayout {
-    size_t n, pose_prior, prev_kps2d, ref_kps2d, kf_id;            // in
+    size_t n, pose_prior, prev_kps2d, ref_kps2d, kf_id, kp_index;  // in
     size_t kps3d, flags, inlier, outlier, kf_state;                // in/out
     size_t pose_aligned, pose_refined, costs, evals, klt_pts, klt_err, klt_status, klt_iters, disparity, kps2d_ref_in, kps2d_out;  // out
     size_t in_end, inout_begin, total;
@@ -108,6 +108,11 @@ struct svo_ctx {
     // keyframe tables
     LevelDesc *d_kf_lk = nullptr;
     float *d_kf_pose = nullptr;
+    KfTemplates *d_kf_tpl = nullptr;           // per keyframe: LK templates of the keypoints it introduced (svo_keyframe_set_templates)
+    bool use_templates = true;
+    std::vector<uint8_t *> tpl_chunks;         // bump-allocated, never freed before the context goes (keyframes live forever)
+    size_t tpl_chunk_bytes = 0, tpl_chunk_used = 0;
+    float *d_tpl_kps = nullptr;                // cell_cap * 2 floats: keyframe positions handed to klt_template_kernel
     int kf_cap = 0, kf_count = 0;
     std::vector<int> kf_slot;
     // keypoint I/O
@@ -185,6 +190,7 @@ static void make_layout(IoLayout &L, int M)
     L.prev_kps2d = take((size_t)M * 8);
     L.ref_kps2d = take((size_t)M * 8);
     L.kf_id = take((size_t)M * 4);
+    L.kp_index = take((size_t)M * 4);
     L.in_end = o;
     L.inout_begin = o;
     L.kps3d = take((size_t)M * 12);
@@ -335,7 +341,7 @@ extern "C" int svo_ctx_create(const svo_camera_settings *s, int device, int widt
         out.src = ctx->d_io; out.dst = ctx->d_hio; out.n_ptr = reinterpret_cast<const int *>(ctx->d_io + L.n); out.max_n = ctx->max_kps;
         int k = 0;
         auto add = [&](IoCopyArgs &a, size_t off, unsigned elem, unsigned per_n) { a.arr[k].off = (unsigned)off; a.arr[k].elem = elem; a.arr[k].per_n = per_n; k++; };
-        add(in, L.n, 16, 0); add(in, L.pose_prior, 24, 0); add(in, L.prev_kps2d, 8, 1); add(in, L.ref_kps2d, 8, 1); add(in, L.kf_id, 4, 1);
+        add(in, L.n, 16, 0); add(in, L.pose_prior, 24, 0); add(in, L.prev_kps2d, 8, 1); add(in, L.ref_kps2d, 8, 1); add(in, L.kf_id, 4, 1); add(in, L.kp_index, 4, 1);
         add(in, L.kps3d, 12, 1); add(in, L.flags, 1, 1); add(in, L.inlier, 4, 1); add(in, L.outlier, 4, 1); add(in, L.kf_state, 8, 1);
         in.narr = k; k = 0;
         add(out, L.kps3d, 12, 1); add(out, L.flags, 1, 1); add(out, L.inlier, 4, 1); add(out, L.outlier, 4, 1); add(out, L.kf_state, 8, 1);
@@ -354,6 +360,10 @@ extern "C" int svo_ctx_create(const svo_camera_settings *s, int device, int widt
     ctx->kf_cap = 64;
     CKC(cudaMalloc(&ctx->d_kf_lk, (size_t)ctx->kf_cap * 2 * SVO_LK_LEVELS * sizeof(LevelDesc)));
     CKC(cudaMalloc(&ctx->d_kf_pose, (size_t)ctx->kf_cap * 24 * sizeof(float)));
+    CKC(cudaMalloc(&ctx->d_kf_tpl, (size_t)ctx->kf_cap * sizeof(KfTemplates)));
+    CKC(cudaMemset(ctx->d_kf_tpl, 0, (size_t)ctx->kf_cap * sizeof(KfTemplates)));
+    CKC(cudaMalloc(&ctx->d_tpl_kps, (size_t)ctx->cell_cap * 8));
+    ctx->use_templates = getenv("SVO_NO_TEMPLATES") == nullptr && s->window_size_opt_flow == 31;
 #undef CKC
     *out = ctx;
     return SVO_OK;
@@ -379,6 +389,9 @@ extern "C" int svo_ctx_destroy(svo_ctx *ctx)
     if (ctx->d_cell_type) cudaFree(ctx->d_cell_type);
     if (ctx->d_kf_lk) cudaFree(ctx->d_kf_lk);
     if (ctx->d_kf_pose) cudaFree(ctx->d_kf_pose);
+    if (ctx->d_kf_tpl) cudaFree(ctx->d_kf_tpl);
+    if (ctx->d_tpl_kps) cudaFree(ctx->d_tpl_kps);
+    for (uint8_t *c : ctx->tpl_chunks) cudaFree(c);
     for (int k = 0; k < 2; k++) {
         if (ctx->d_rect_map[k][0]) cudaFree(ctx->d_rect_map[k][0]);
         if (ctx->d_rect_map[k][1]) cudaFree(ctx->d_rect_map[k][1]);
@@ -1112,9 +1125,15 @@ extern "C" int svo_keyframe_commit(svo_ctx *ctx, int slot, const float pose[6], 
         int ncap = ctx->kf_cap * 2;
         LevelDesc *nl;
         float *np;
+        KfTemplates *nt;
         CK(cudaMalloc(&nl, (size_t)ncap * 2 * SVO_LK_LEVELS * sizeof(LevelDesc)));
         CK(cudaMalloc(&np, (size_t)ncap * 24 * sizeof(float)));
+        CK(cudaMalloc(&nt, (size_t)ncap * sizeof(KfTemplates)));
         CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaMemset(nt, 0, (size_t)ncap * sizeof(KfTemplates)));
+        CK(cudaMemcpy(nt, ctx->d_kf_tpl, (size_t)ctx->kf_cap * sizeof(KfTemplates), cudaMemcpyDeviceToDevice));
+        cudaFree(ctx->d_kf_tpl);
+        ctx->d_kf_tpl = nt;
         CK(cudaMemcpy(nl, ctx->d_kf_lk, (size_t)ctx->kf_cap * 2 * SVO_LK_LEVELS * sizeof(LevelDesc), cudaMemcpyDeviceToDevice));
         CK(cudaMemcpy(np, ctx->d_kf_pose, (size_t)ctx->kf_cap * 24 * sizeof(float), cudaMemcpyDeviceToDevice));
         cudaFree(ctx->d_kf_lk); cudaFree(ctx->d_kf_pose);
@@ -1156,6 +1175,43 @@ extern "C" int svo_keyframe_slot(svo_ctx *ctx, int keyframe_id, int *slot_out)
     return SVO_OK;
 }
 
+// LK templates of the keypoints a keyframe introduced (indices first .. first + count - 1 of its keypoint list, positions
+// kps2d in keyframe coordinates).  calcOpticalFlowPyrLK rebuilds the 31x31 template (Iw, Ix, Iy and the structure tensor) of
+// every keypoint on every level for every frame from the keyframe's pyramid (optical_flow.cpp:41-44); position and pyramid
+// never change after the keyframe is created, so the templates are built once here and the tracking kernel fetches them.
+extern "C" int svo_keyframe_set_templates(svo_ctx *ctx, int keyframe_id, const float *kps2d, int first, int count)
+{
+    if (!ctx || keyframe_id < 0 || keyframe_id >= ctx->kf_count || first < 0 || count < 0 || (count > 0 && !kps2d)) return SVO_ERR_INVALID;
+    if (!ctx->use_templates || count == 0) return SVO_OK;
+    if (count > ctx->cell_cap) { snprintf(ctx->err, sizeof(ctx->err), "%d templates exceed the cell capacity %d", count, ctx->cell_cap); return SVO_ERR_CAPACITY; }
+    CK(cudaSetDevice(ctx->device));
+    const size_t data_bytes = (size_t)count * SVO_LK_LEVELS * KLT_TPL_BYTES, hdr_bytes = align_up((size_t)count * SVO_LK_LEVELS * sizeof(float4), 256);
+    const size_t need = data_bytes + hdr_bytes;
+    if (ctx->tpl_chunks.empty() || ctx->tpl_chunk_used + need > ctx->tpl_chunk_bytes) {
+        const size_t chunk = std::max(need, (size_t)32 << 20);
+        uint8_t *c = nullptr;
+        CK(cudaMalloc(&c, chunk));
+        ctx->tpl_chunks.push_back(c);
+        ctx->tpl_chunk_bytes = chunk; ctx->tpl_chunk_used = 0;
+    }
+    uint8_t *base = ctx->tpl_chunks.back() + ctx->tpl_chunk_used;
+    ctx->tpl_chunk_used += need;
+    CK(cudaMemcpyAsync(ctx->d_tpl_kps, kps2d, (size_t)count * 8, cudaMemcpyHostToDevice, ctx->stream));
+    const Slot &ks = ctx->slots[ctx->kf_slot[keyframe_id]];
+    KltTemplateArgs ta;
+    for (int l = 0; l < SVO_LK_LEVELS; l++) { ta.lk[l] = ks.dev.lk[l]; ta.lkd[l] = ks.dev.lkd[l]; }
+    ta.kps2d = ctx->d_tpl_kps; ta.n = count;
+    ta.data = reinterpret_cast<uint4 *>(base); ta.hdr = reinterpret_cast<float4 *>(base + data_bytes);
+    launch_klt_templates(ta, ctx->stream);
+    ctx->launch_total += 1;
+    CK(cudaGetLastError());
+    KfTemplates rec;
+    rec.data = ta.data; rec.hdr = ta.hdr; rec.first = first; rec.count = count;
+    CK(cudaMemcpyAsync(ctx->d_kf_tpl + keyframe_id, &rec, sizeof(rec), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));   // rec is on the stack, kps2d is the caller's
+    return SVO_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ fused frame
 static int validate_and_pack(svo_ctx *ctx, svo_track_io *io)
 {
@@ -1175,6 +1231,8 @@ static int validate_and_pack(svo_ctx *ctx, svo_track_io *io)
     memcpy(h + L.prev_kps2d, io->prev_kps2d, (size_t)n * 8);
     memcpy(h + L.ref_kps2d, io->ref_kps2d, (size_t)n * 8);
     memcpy(h + L.kf_id, io->keyframe_id, (size_t)n * 4);
+    if (io->keypoint_index) memcpy(h + L.kp_index, io->keypoint_index, (size_t)n * 4);
+    else memset(h + L.kp_index, 0xff, (size_t)n * 4);   // -1: no template lookup
     memcpy(h + L.kps3d, io->kps3d, (size_t)n * 12);
     memcpy(h + L.flags, io->flags, (size_t)n);
     memcpy(h + L.inlier, io->inlier_count, (size_t)n * 4);
@@ -1211,6 +1269,7 @@ static int enqueue_track(svo_ctx *ctx, int prev_slot, int cur_slot, int n, int g
         KltArgs ka;
         memset(&ka, 0, sizeof(ka));
         ka.kf_lk_table = ctx->d_kf_lk; ka.keyframe_ids = DP(int, kf_id);
+        if (ctx->use_templates) { ka.kf_tpl_table = ctx->d_kf_tpl; ka.kp_index = DP(int, kp_index); }
         for (int l = 0; l < SVO_LK_LEVELS; l++) ka.cur[l] = ctx->slots[cur_slot].dev.lk[l];
         ka.prev_pts = DP(float, ref_kps2d); ka.init_pts = nullptr; ka.kps3d = DP(float, kps3d); ka.pose = DP(float, pose_aligned);
         ka.n_ptr = DP(int, n); ka.next_pts = DP(float, klt_pts); ka.status = DP(uint8_t, klt_status); ka.err = DP(float, klt_err);

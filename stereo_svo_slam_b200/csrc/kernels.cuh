@@ -126,9 +126,26 @@ size_t align_smem_bytes(const AlignArgs &a);
 cudaError_t align_init_device();  // once per device: opt in to 227 KB dynamic shared memory
 
 // ---- klt.cu
+#define KLT_TPL_CHUNKS 12                               // 16-byte chunks per lane: 3 planes x 32 int16
+#define KLT_TPL_BYTES (KLT_TPL_CHUNKS * 32 * 16)        // per (keypoint, level)
+struct KfTemplates {       // template cache of one keyframe: its keypoints with index first .. first + count - 1
+    const uint4 *data;     // null: none (templates are built per frame)
+    const float4 *hdr;
+    int first, count;
+};
+struct KltTemplateArgs {
+    LevelDesc lk[SVO_LK_LEVELS], lkd[SVO_LK_LEVELS];
+    const float *kps2d;    // n*2 keyframe positions (device)
+    int n;
+    uint4 *data;
+    float4 *hdr;
+};
+void launch_klt_templates(const KltTemplateArgs &a, cudaStream_t st);
 struct KltArgs {
     const LevelDesc *kf_lk_table;  // device table: [keyframe_id][2 * SVO_LK_LEVELS]: image levels, then derivative levels
     const int *keyframe_ids;       // n (device) or null => use prev_fixed
+    const KfTemplates *kf_tpl_table;  // device table [keyframe_id] or null
+    const int *kp_index;           // n (device): index of the keypoint in its origin keyframe (template cache lookup) or null
     LevelDesc prev_fixed[SVO_LK_LEVELS];
     LevelDesc prev_fixed_deriv[SVO_LK_LEVELS];
     LevelDesc cur[SVO_LK_LEVELS];

@@ -493,6 +493,107 @@ __device__ __forceinline__ long long warp_sum_i32_exact(int v)
     return ((long long)shi << 16) + (long long)slo;
 }
 
+// Template of one window row (lane = row; lane 31 only feeds lane 30 with the row below): the 31 bilinear samples of the
+// keyframe level (Iw, Q5) and of its Scharr derivative level (Ix, Iy) at the sub-pixel position given by the weights, plus this
+// lane's share of the structure-tensor sums.  Used per frame (keyframes without cached templates) and once per keyframe by
+// klt_template_kernel — the same code, so both ways give the same bits.
+__device__ __forceinline__ void klt31_build_row(const LevelDesc &I, const LevelDesc &Dv, int ipx, int ipy, int iw00, int iw01, int iw10, int iw11,
+                                                int lane, bool have_row, int (&Iw)[31], int (&Ix)[31], int (&Iy)[31], int &acc11, int &acc12,
+                                                int &acc22)
+{
+    // image row ipy + lane, pixels ipx .. ipx + 31 (inside the level's REFLECT_101 frame), as 8 realigned words
+    const uint8_t *rowp = I.ptr + (ptrdiff_t)(ipy + lane) * I.pitch + ipx;
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(rowp);
+    const uint32_t *base = reinterpret_cast<const uint32_t *>(addr & ~(uintptr_t)3);
+    const int sh = (int)(addr & 3) * 8;
+    uint32_t wv[9], ta[8], tb[8];
+#pragma unroll
+    for (int k = 0; k < 9; k++) wv[k] = base[k];
+#pragma unroll
+    for (int k = 0; k < 8; k++) ta[k] = __funnelshift_r(wv[k], wv[k + 1], sh);
+#pragma unroll
+    for (int k = 0; k < 8; k++) tb[k] = __shfl_down_sync(0xffffffffu, ta[k], 1);
+    // derivative row (Ix | Iy << 16 per pixel; zero outside the image), same pixels
+    const uint32_t *drow = reinterpret_cast<const uint32_t *>(Dv.ptr + (ptrdiff_t)(ipy + lane) * Dv.pitch) + ipx;
+    uint32_t da = drow[0], db = __shfl_down_sync(0xffffffffu, da, 1);
+    int pa = (int)(ta[0] & 255u), pb = (int)(tb[0] & 255u);
+    acc11 = 0; acc12 = 0; acc22 = 0;
+#pragma unroll
+    for (int x = 0; x < 31; x++) {
+        const uint32_t na_w = drow[x + 1];
+        const uint32_t nb_w = __shfl_down_sync(0xffffffffu, na_w, 1);
+        const int na = (int)((ta[(x + 1) >> 2] >> (8 * ((x + 1) & 3))) & 255u), nb = (int)((tb[(x + 1) >> 2] >> (8 * ((x + 1) & 3))) & 255u);
+        const int pgx0 = (int)(short)(da & 0xffffu), pgy0 = (int)da >> 16, pgx1 = (int)(short)(db & 0xffffu), pgy1 = (int)db >> 16;
+        const int ngx0 = (int)(short)(na_w & 0xffffu), ngy0 = (int)na_w >> 16, ngx1 = (int)(short)(nb_w & 0xffffu), ngy1 = (int)nb_w >> 16;
+        int ival = pa * iw00 + na * iw01 + pb * iw10 + nb * iw11;
+        int ixv = pgx0 * iw00 + ngx0 * iw01 + pgx1 * iw10 + ngx1 * iw11;
+        int iyv = pgy0 * iw00 + ngy0 * iw01 + pgy1 * iw10 + ngy1 * iw11;
+        ival = (ival + (1 << 8)) >> 9;
+        ixv = (ixv + (1 << 13)) >> 14;
+        iyv = (iyv + (1 << 13)) >> 14;
+        if (!have_row) { ival = 0; ixv = 0; iyv = 0; }
+        Iw[x] = ival; Ix[x] = ixv; Iy[x] = iyv;
+        acc11 += ixv * ixv; acc12 += ixv * iyv; acc22 += iyv * iyv;   // <= 31 * 4080^2 < 2^31
+        pa = na; pb = nb; da = na_w; db = nb_w;
+    }
+}
+
+// Once per KEYFRAME: the templates of its new keypoints on all three levels, stored so that a lane fetches its row with
+// twelve coalesced 16-byte loads: data[((keypoint * 3 + level) * 12 + chunk) * 32 + lane], chunks 0-3 = Iw[0..31) as int16 (one
+// pad), 4-7 = Ix, 8-11 = Iy; hdr[keypoint * 3 + level] = (A11, A12, A22, flag) with flag 1 = window outside the level.
+// The keyframe position of a keypoint never changes, so what calcOpticalFlowPyrLK rebuilds for every frame (and the first
+// versions of klt31w_kernel did too: 46 % of the kernel's time) is a per-keyframe constant.
+__global__ void __launch_bounds__(32 * KLTW_WARPS) klt_template_kernel(KltTemplateArgs a)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int i = blockIdx.x * KLTW_WARPS + wid;
+    if (i >= a.n) return;
+    constexpr int win = 31;
+    const float half = 15.0f;
+    const bool have_row = lane < win;
+    const float ppx = a.kps2d[2 * i], ppy = a.kps2d[2 * i + 1];
+    for (int level = 0; level < SVO_LK_LEVELS; level++) {
+        const LevelDesc I = a.lk[level], Dv = a.lkd[level];
+        const float scale = (float)(1. / (1 << level));
+        float px = ppx * scale, py = ppy * scale;
+        px -= half; py -= half;
+        const int ipx = (int)floorf(px), ipy = (int)floorf(py);
+        float4 h = make_float4(0.f, 0.f, 0.f, __int_as_float(1));
+        if (!(ipx < -win || ipx >= I.w || ipy < -win || ipy >= I.h)) {
+            int iw00, iw01, iw10, iw11;
+            lk_weights(px - (float)ipx, py - (float)ipy, iw00, iw01, iw10, iw11);
+            int Iw[31], Ix[31], Iy[31], acc11, acc12, acc22;
+            klt31_build_row(I, Dv, ipx, ipy, iw00, iw01, iw10, iw11, lane, have_row, Iw, Ix, Iy, acc11, acc12, acc22);
+            const long long s11 = warp_sum_i32_exact(acc11), s12 = warp_sum_i32_exact(acc12), s22 = warp_sum_i32_exact(acc22);
+            const float FLT_SCALE = 1.f / (1 << 20);
+            h = make_float4((float)s11 * FLT_SCALE, (float)s12 * FLT_SCALE, (float)s22 * FLT_SCALE, __int_as_float(0));
+            uint4 *dst = a.data + ((size_t)(i * SVO_LK_LEVELS + level) * KLT_TPL_CHUNKS) * 32 + lane;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                uint32_t w[3][4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int x0 = 8 * c + 2 * q, x1 = x0 + 1;
+                    const int a0 = Iw[x0], a1 = x1 < 31 ? Iw[x1] : 0, b0 = Ix[x0], b1 = x1 < 31 ? Ix[x1] : 0, c0 = Iy[x0], c1 = x1 < 31 ? Iy[x1] : 0;
+                    w[0][q] = ((uint32_t)a0 & 0xffffu) | ((uint32_t)a1 << 16);
+                    w[1][q] = ((uint32_t)b0 & 0xffffu) | ((uint32_t)b1 << 16);
+                    w[2][q] = ((uint32_t)c0 & 0xffffu) | ((uint32_t)c1 << 16);
+                }
+                dst[(size_t)c * 32] = make_uint4(w[0][0], w[0][1], w[0][2], w[0][3]);
+                dst[(size_t)(4 + c) * 32] = make_uint4(w[1][0], w[1][1], w[1][2], w[1][3]);
+                dst[(size_t)(8 + c) * 32] = make_uint4(w[2][0], w[2][1], w[2][2], w[2][3]);
+            }
+        }
+        if (lane == 0) a.hdr[i * SVO_LK_LEVELS + level] = h;
+    }
+}
+
+void launch_klt_templates(const KltTemplateArgs &a, cudaStream_t st)
+{
+    if (a.n <= 0) return;
+    klt_template_kernel<<<(a.n + KLTW_WARPS - 1) / KLTW_WARPS, 32 * KLTW_WARPS, 0, st>>>(a);
+}
+
 __global__ void __launch_bounds__(32 * KLTW_WARPS, 4) klt31w_kernel(KltArgs a)
 {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -515,6 +616,15 @@ __global__ void __launch_bounds__(32 * KLTW_WARPS, 4) klt31w_kernel(KltArgs a)
     const float ppx = a.prev_pts[2 * i], ppy = a.prev_pts[2 * i + 1];
     const LevelDesc *prev_lv = a.keyframe_ids ? (a.kf_lk_table + (size_t)a.keyframe_ids[i] * 2 * SVO_LK_LEVELS) : a.prev_fixed;
     const LevelDesc *prev_dv = a.keyframe_ids ? (prev_lv + SVO_LK_LEVELS) : a.prev_fixed_deriv;
+    // template cache of the origin keyframe (svo_keyframe_set_templates): slot of this keypoint, if it has one
+    const uint4 *tpl_data = nullptr;
+    const float4 *tpl_hdr = nullptr;
+    int tpl_slot = 0;
+    if (a.kf_tpl_table && a.kp_index && a.keyframe_ids) {
+        const KfTemplates t = a.kf_tpl_table[a.keyframe_ids[i]];
+        const int idx = a.kp_index[i] - t.first;
+        if (t.data && idx >= 0 && idx < t.count) { tpl_data = t.data; tpl_hdr = t.hdr; tpl_slot = idx; }
+    }
 
     float nx = init_x, ny = init_y;
     int status = 1;
@@ -540,48 +650,32 @@ __global__ void __launch_bounds__(32 * KLTW_WARPS, 4) klt31w_kernel(KltArgs a)
         int iw00, iw01, iw10, iw11;
         lk_weights(px - (float)ipx, py - (float)ipy, iw00, iw01, iw10, iw11);
 
-        // ---- template of this lane's row in registers (lane 31 only feeds lane 30 with the row below)
+        // ---- template of this lane's row in registers: fetched from the keyframe's template cache, else built here
         int Iw[31], Ix[31], Iy[31];
-        int acc11 = 0, acc12 = 0, acc22 = 0;
-        {
-            // image row ipy + lane, pixels ipx .. ipx + 31 (inside the level's REFLECT_101 frame), as 8 realigned words
-            const uint8_t *rowp = I.ptr + (ptrdiff_t)(ipy + lane) * I.pitch + ipx;
-            const uintptr_t addr = reinterpret_cast<uintptr_t>(rowp);
-            const uint32_t *base = reinterpret_cast<const uint32_t *>(addr & ~(uintptr_t)3);
-            const int sh = (int)(addr & 3) * 8;
-            uint32_t wv[9], ta[8], tb[8];
+        float A11, A12, A22;
+        if (tpl_data) {
+            const uint4 *src = tpl_data + ((size_t)(tpl_slot * SVO_LK_LEVELS + level) * KLT_TPL_CHUNKS) * 32 + lane;
+            const float4 h = tpl_hdr[tpl_slot * SVO_LK_LEVELS + level];
+            A11 = h.x; A12 = h.y; A22 = h.z;
 #pragma unroll
-            for (int k = 0; k < 9; k++) wv[k] = base[k];
+            for (int c = 0; c < 4; c++) {
+                const uint4 wa = src[(size_t)c * 32], wb = src[(size_t)(4 + c) * 32], wc = src[(size_t)(8 + c) * 32];
+                const uint32_t ua[4] = {wa.x, wa.y, wa.z, wa.w}, ub[4] = {wb.x, wb.y, wb.z, wb.w}, uc[4] = {wc.x, wc.y, wc.z, wc.w};
 #pragma unroll
-            for (int k = 0; k < 8; k++) ta[k] = __funnelshift_r(wv[k], wv[k + 1], sh);
-#pragma unroll
-            for (int k = 0; k < 8; k++) tb[k] = __shfl_down_sync(0xffffffffu, ta[k], 1);
-            // derivative row (Ix | Iy << 16 per pixel; zero outside the image), same pixels
-            const uint32_t *drow = reinterpret_cast<const uint32_t *>(Dv.ptr + (ptrdiff_t)(ipy + lane) * Dv.pitch) + ipx;
-            uint32_t da = drow[0], db = __shfl_down_sync(0xffffffffu, da, 1);
-            int pa = (int)(ta[0] & 255u), pb = (int)(tb[0] & 255u);
-#pragma unroll
-            for (int x = 0; x < 31; x++) {
-                const uint32_t na_w = drow[x + 1];
-                const uint32_t nb_w = __shfl_down_sync(0xffffffffu, na_w, 1);
-                const int na = (int)((ta[(x + 1) >> 2] >> (8 * ((x + 1) & 3))) & 255u), nb = (int)((tb[(x + 1) >> 2] >> (8 * ((x + 1) & 3))) & 255u);
-                const int pgx0 = (int)(short)(da & 0xffffu), pgy0 = (int)da >> 16, pgx1 = (int)(short)(db & 0xffffu), pgy1 = (int)db >> 16;
-                const int ngx0 = (int)(short)(na_w & 0xffffu), ngy0 = (int)na_w >> 16, ngx1 = (int)(short)(nb_w & 0xffffu), ngy1 = (int)nb_w >> 16;
-                int ival = pa * iw00 + na * iw01 + pb * iw10 + nb * iw11;
-                int ixv = pgx0 * iw00 + ngx0 * iw01 + pgx1 * iw10 + ngx1 * iw11;
-                int iyv = pgy0 * iw00 + ngy0 * iw01 + pgy1 * iw10 + ngy1 * iw11;
-                ival = (ival + (1 << 8)) >> 9;
-                ixv = (ixv + (1 << 13)) >> 14;
-                iyv = (iyv + (1 << 13)) >> 14;
-                if (!have_row) { ival = 0; ixv = 0; iyv = 0; }
-                Iw[x] = ival; Ix[x] = ixv; Iy[x] = iyv;
-                acc11 += ixv * ixv; acc12 += ixv * iyv; acc22 += iyv * iyv;   // <= 31 * 4080^2 < 2^31
-                pa = na; pb = nb; da = na_w; db = nb_w;
+                for (int q = 0; q < 4; q++) {
+                    const int x0 = 8 * c + 2 * q, x1 = x0 + 1;
+                    Iw[x0] = (int)(short)(ua[q] & 0xffffu); Ix[x0] = (int)(short)(ub[q] & 0xffffu); Iy[x0] = (int)(short)(uc[q] & 0xffffu);
+                    if (x1 < 31) { Iw[x1] = (int)ua[q] >> 16; Ix[x1] = (int)ub[q] >> 16; Iy[x1] = (int)uc[q] >> 16; }
+                }
             }
+        } else {
+            int acc11, acc12, acc22;
+            klt31_build_row(I, Dv, ipx, ipy, iw00, iw01, iw10, iw11, lane, have_row, Iw, Ix, Iy, acc11, acc12, acc22);
+            const long long s11 = warp_sum_i32_exact(acc11), s12 = warp_sum_i32_exact(acc12), s22 = warp_sum_i32_exact(acc22);
+            const float FLT_SCALE0 = 1.f / (1 << 20);
+            A11 = (float)s11 * FLT_SCALE0; A12 = (float)s12 * FLT_SCALE0; A22 = (float)s22 * FLT_SCALE0;
         }
-        const long long s11 = warp_sum_i32_exact(acc11), s12 = warp_sum_i32_exact(acc12), s22 = warp_sum_i32_exact(acc22);
         const float FLT_SCALE = 1.f / (1 << 20);
-        float A11 = (float)s11 * FLT_SCALE, A12 = (float)s12 * FLT_SCALE, A22 = (float)s22 * FLT_SCALE;
         float D = A11 * A22 - A12 * A12;
         float minEig = (A22 + A11 - sqrtf((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) / (float)(2 * win * win);
         if ((double)minEig < 1e-4 || D < 1.1920929e-07f) {

@@ -149,7 +149,7 @@ struct svo_slam {
     // per-frame scratch (reused)
     svo_track_io io;
     std::vector<float> io_prev2d, io_kps3d, io_ref2d, io_kfstate, io_kps2d;
-    std::vector<int> io_kfid, io_inl, io_outl, io_kltit;
+    std::vector<int> io_kfid, io_kpidx, io_inl, io_outl, io_kltit;
     std::vector<uint8_t> io_kltst;
     long long counters[8] = {0};
     std::vector<uint8_t> io_flags;
@@ -303,6 +303,8 @@ struct svo_slam {
         if ((uint64_t)id != kf_id) { snprintf(err, sizeof(err), "keyframe id mismatch"); return SVO_ERR_STATE; }
         rc = svo_keyframe_slot(ctx, id, &k->slot);  // the device keeps its own copy of the keyframe's images
         if (rc) return rc;
+        // the LK templates of the keypoints this keyframe introduced never change: build them once (optical_flow.cpp:41-44)
+        if (n_new > 0 && (rc = svo_keyframe_set_templates(ctx, id, &f.kps.kps2d[2 * old_count], (int)old_count, (int)n_new))) return rc;
         keyframes.push_back(std::move(k));
         last_keyframe_created = 1;
         if (g_trace_kf)
@@ -385,7 +387,7 @@ struct svo_slam {
         const size_t n = previous->kps.size();
         io_prev2d = previous->kps.kps2d;
         io_kps3d = previous->kps.kps3d;
-        io_ref2d.resize(n * 2); io_kfid.resize(n); io_flags.resize(n); io_inl.resize(n); io_outl.resize(n); io_kfstate.resize(n * 2);
+        io_ref2d.resize(n * 2); io_kfid.resize(n); io_kpidx.resize(n); io_flags.resize(n); io_inl.resize(n); io_outl.resize(n); io_kfstate.resize(n * 2);
         io_kps2d.resize(n * 2); io_kltit.assign(n, 0); io_kltst.assign(n, 0);
         for (size_t i = 0; i < n; i++) {
             const svo_keypoint_info &in = previous->kps.info[i];
@@ -393,6 +395,7 @@ struct svo_slam {
             io_ref2d[2 * i] = k.kps.kps2d[2 * in.keypoint_index];
             io_ref2d[2 * i + 1] = k.kps.kps2d[2 * in.keypoint_index + 1];
             io_kfid[i] = (int)in.keyframe_id;
+            io_kpidx[i] = (int)in.keypoint_index;
             io_flags[i] = (uint8_t)((in.ignore_during_refinement ? 1 : 0) | (in.ignore_completely ? 2 : 0) | (in.ignore_temporary ? 4 : 0));
             io_inl[i] = in.inlier_count; io_outl[i] = in.outlier_count;
             io_kfstate[2 * i] = in.kf_inv_depth; io_kfstate[2 * i + 1] = in.kf_variance;
@@ -403,6 +406,7 @@ struct svo_slam {
         io.flags = io_flags.data(); io.inlier_count = io_inl.data(); io.outlier_count = io_outl.data(); io.kf_state = io_kfstate.data();
         io.kps2d = io_kps2d.data();
         io.klt_iters = io_kltit.data(); io.klt_status = io_kltst.data();
+        io.keypoint_index = io_kpidx.data();
         std::memcpy(io.pose_prior, frame->pose, sizeof(io.pose_prior));
         // pyramids (stereo_slam.cpp:135-139) + the whole tracking sequence, one CUDA graph launch in steady state
         rc = svo_frame_begin(ctx, left, ls, right, rs, on_device ? 1 : 0, previous->slot, &io, &frame->slot);

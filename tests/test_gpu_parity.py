@@ -302,10 +302,11 @@ def _oracle_inputs(slam):
                 kf_state=np.stack([t("align_in_kfx"), t("align_in_kfP")], 1), pose_prior=t("align_pose_in"))
 
 
-@pytest.mark.parametrize("cfg,frames", [("S", 25), ("C3", 8), ("C4", 4)])
-def test_track_frame_teacher_forced(cfg, frames):
+@pytest.mark.parametrize("cfg,frames,templates", [("S", 25, True), ("C3", 8, True), ("C3", 8, False), ("C4", 4, True)])
+def test_track_frame_teacher_forced(cfg, frames, templates):
     """Per-frame parity: the oracle pipeline runs freely; each tracking frame's inputs are fed to the fused
-    CUDA frame (svo_track_frame) and every stage output is compared with the oracle's trace."""
+    CUDA frame (svo_track_frame) and every stage output is compared with the oracle's trace.  templates: the LK
+    templates come from the per-keyframe cache (svo_keyframe_set_templates) instead of being rebuilt per frame."""
     gcs, ocs = mk(cfg)
     c = synth.CONFIGS[cfg]
     seq = synth.make_sequence(cfg)
@@ -319,7 +320,7 @@ def test_track_frame_teacher_forced(cfg, frames):
         slot = ctx.upload(L, R)
         if k > 0:
             inp = _oracle_inputs(slam)
-            out = ctx.track_frame(prev_slot, slot, **inp)
+            out = ctx.track_frame(prev_slot, slot, keypoint_index=slam.trace("align_in_kpidx").astype(np.int32) if templates else None, **inp)
             t = slam.trace
             same_path = (out["align_evals"] == t("align_evals").reshape(8, 2).astype(np.int32)).all()
             flips += 0 if same_path else 1
@@ -356,8 +357,10 @@ def test_track_frame_teacher_forced(cfg, frames):
             assert np.abs(s["kps2d_out"] - okp).max() <= 0.05
         # keyframes created by the oracle in this frame are registered on the device with the oracle's pose
         while n_kf < slam.n_keyframes():
-            pose, _, _ = slam.keyframe(n_kf)
+            pose, k2, _ = slam.keyframe(n_kf)
             assert ctx.keyframe_commit(slot, pose) == n_kf
+            if templates:
+                ctx.keyframe_set_templates(n_kf, k2, 0)
             n_kf += 1
         if prev_slot is not None:
             ctx.release(prev_slot)
@@ -431,6 +434,35 @@ def test_cuda_graph_replay_is_bit_identical():
     assert nk1 == nk0 and (p1 == p0).all()
     for a, b in zip(k1, k0):
         assert a.shape == b.shape and (a == b).all()
+
+
+def test_lk_template_cache_is_bit_identical(monkeypatch):
+    """LK templates fetched from the per-keyframe cache (default) and rebuilt from the keyframe pyramids for every frame
+    (SVO_NO_TEMPLATES=1, what calcOpticalFlowPyrLK does) give the same bits over a free-running sequence."""
+    from stereo_svo_slam_b200 import StereoSlam
+    gcs, _ = mk("C3")
+    c = synth.CONFIGS["C3"]
+    seq = synth.make_sequence("C3")
+    runs = []
+    for off in (False, True):
+        if off:
+            monkeypatch.setenv("SVO_NO_TEMPLATES", "1")
+        else:
+            monkeypatch.delenv("SVO_NO_TEMPLATES", raising=False)
+        g = StereoSlam(gcs, c["width"], c["height"])
+        poses, kps = [], []
+        for k in range(14):
+            L, R = seq.render(k)
+            g.new_image(L, R, k / 20.0)
+            poses.append(g.pose())
+            f = g.get_frame()
+            kps.append((f.kps.kps2d.copy(), f.kps.kps3d.copy()))
+        runs.append((np.array(poses), kps, g.keyframe_count()))
+        g.close()
+    (p1, k1, n1), (p0, k0, n0) = runs
+    assert n1 == n0 and (p1 == p0).all()
+    for (a2, a3), (b2, b3) in zip(k1, k0):
+        assert a2.shape == b2.shape and (a2 == b2).all() and (a3 == b3).all()
 
 
 def test_error_behaviour(c3ctx):
