@@ -322,6 +322,7 @@ __global__ void __launch_bounds__(ALIGN_THREADS, 1) sparse_align_kernel(AlignArg
     cluster_sync_all();   // every CTA's shared memory is live before anyone writes into it remotely
     const int n = hdr->n;
     const int npass = (n + KPS_PER_PASS - 1) / KPS_PER_PASS;
+    const bool nodist = dev_cam_nodist(cam);
     uint32_t phase = 0, xphase[3] = {0, 0, 0};
     // cost-exchange buffer / barrier of the NEXT evaluation.  It must keep alternating across level boundaries: a CTA may
     // push evaluation e+2 into a peer only after passing the wait of e+1, and every peer pushes e+1 only after all its
@@ -438,8 +439,7 @@ __global__ void __launch_bounds__(ALIGN_THREADS, 1) sparse_align_kernel(AlignArg
                         float bx = a.kps2d[2 * i], by = a.kps2d[2 * i + 1];
                         if (level != 0) { bx = bx / fdiv; by = by / fdiv; }
                         float u, v;
-                        dev_project(Rd, a.kps3d[3 * i], a.kps3d[3 * i + 1], a.kps3d[3 * i + 2], tx, ty, tz, lfx, lfy, lcx, lcy, cam.k1, cam.k2,
-                                    cam.p1, cam.p2, cam.k3, u, v);
+                        dev_project_nd(nodist, Rd, a.kps3d[3 * i], a.kps3d[3 * i + 1], a.kps3d[3 * i + 2], tx, ty, tz, lfx, lfy, lcx, lcy, cam, u, v);
                         intensity_diff_row(pimg, cimg, w, h, pitch, bx, by, u, v, cam.win_pose, row, d0, d1, d2, d3);
                     }
                     // the reference adds the 16 |dI| terms of a patch sequentially in raster order: chain the four rows
@@ -523,7 +523,7 @@ __global__ void __launch_bounds__(ALIGN_THREADS, 1) sparse_align_kernel(AlignArg
                     for (int c = 0; c < 4; c++) { g0v[c] = scr[(size_t)c * SN + slot]; g1v[c] = scr[(size_t)(4 + c) * SN + slot]; spv[c] = scr[(size_t)(8 + c) * SN + slot]; }
                     const float Px = a.kps3d[3 * i], Py = a.kps3d[3 * i + 1], Pz = a.kps3d[3 * i + 2];
                     float u, v;
-                    dev_project(Rd, Px, Py, Pz, tx, ty, tz, lfx, lfy, lcx, lcy, cam.k1, cam.k2, cam.p1, cam.p2, cam.k3, u, v);
+                    dev_project_nd(nodist, Rd, Px, Py, Pz, tx, ty, tz, lfx, lfy, lcx, lcy, cam, u, v);
                     float X, Y, Z;
                     dev_m33v(Rif, Px - tx, Py - ty, Pz - tz, X, Y, Z);
                     float J[12];

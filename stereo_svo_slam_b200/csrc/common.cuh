@@ -93,6 +93,30 @@ __device__ __forceinline__ void dev_project(const double *Rd, float px, float py
     v = (float)(yd0 * (double)fy + (double)cy);
 }
 
+// dev_project with a fast path for a camera without lens distortion (k1 = k2 = p1 = p2 = k3 = 0, all shipped settings): with
+// zero coefficients cv::projectPoints' distortion polynomial multiplies by exactly 1 and adds exactly 0, so dropping it leaves
+// every finite result bit-identical — and takes a dozen dependent double-precision operations out of every cost evaluation.
+__device__ __forceinline__ bool dev_cam_nodist(const DevCam &cam)
+{
+    return cam.k1 == 0.f && cam.k2 == 0.f && cam.p1 == 0.f && cam.p2 == 0.f && cam.k3 == 0.f;
+}
+__device__ __forceinline__ void dev_project_nd(bool nodist, const double *Rd, float px, float py, float pz, float tx, float ty, float tz,
+                                               float fx, float fy, float cx, float cy, const DevCam &cam, float &u, float &v)
+{
+    if (!nodist) {
+        dev_project(Rd, px, py, pz, tx, ty, tz, fx, fy, cx, cy, cam.k1, cam.k2, cam.p1, cam.p2, cam.k3, u, v);
+        return;
+    }
+    double X = (double)(px - tx), Y = (double)(py - ty), Z = (double)(pz - tz);
+    double x = Rd[0] * X + Rd[1] * Y + Rd[2] * Z + 0.0;
+    double y = Rd[3] * X + Rd[4] * Y + Rd[5] * Z + 0.0;
+    double z = Rd[6] * X + Rd[7] * Y + Rd[8] * Z + 0.0;
+    z = z ? 1. / z : 1;
+    x *= z; y *= z;
+    u = (float)(x * (double)fx + (double)cx);
+    v = (float)(y * (double)fy + (double)cy);
+}
+
 // exponential_map.hpp:12-37 — norm fixed to 1, w unchanged; Matx * double -> float rounding as in OpenCV
 __device__ __forceinline__ void dev_expmap(const float tw[6], float out[6])
 {

@@ -1024,7 +1024,7 @@ extern "C" int svo_reproj_refine(svo_ctx *ctx, const float *kps2d, const float *
     a.kps2d = DP(float, kps2d_ref_in); a.kps3d = DP(float, kps3d); a.flags = DP(uint8_t, flags); a.n_ptr = DP(int, n);
     a.pose_in = DP(float, pose_aligned); a.pose_out = DP(float, pose_refined);
     a.cost_out = DP(float, costs) + 1; a.evals_out = DP(int, evals) + 16; a.cam = ctx->cam;
-    launch_refine(a, ctx->stream);
+    launch_refine(a, (n + 127) / 128 * 128, ctx->stream);
     ctx->launch_total += 1;
     CK(cudaGetLastError());
     if ((rc = down(ctx, pose_out, ctx->lay.pose_refined, 24))) return rc;
@@ -1300,8 +1300,9 @@ static int enqueue_track(svo_ctx *ctx, int prev_slot, int cur_slot, int n, int g
     ra.kps2d = DP(float, kps2d_ref_in); ra.kps3d = DP(float, kps3d); ra.flags = DP(uint8_t, flags); ra.n_ptr = DP(int, n);
     ra.pose_in = DP(float, pose_aligned); ra.pose_out = DP(float, pose_refined);
     ra.cost_out = DP(float, costs) + 1; ra.evals_out = DP(int, evals) + 16; ra.cam = ctx->cam;
-    launch_refine(ra, ctx->stream); launches++;
-    for (int k = 0; k < diag_dup("refine"); k++) launch_refine(ra, ctx->stream);
+    const int ref_bucket = std::min(ctx->max_kps, (grid_n + 127) / 128 * 128);   // == the graph's bucket
+    launch_refine(ra, ref_bucket, ctx->stream); launches++;
+    for (int k = 0; k < diag_dup("refine"); k++) launch_refine(ra, ref_bucket, ctx->stream);
     mark(ctx, 7);
     if (prof) CK(cudaEventRecord(ctx->sev[5], ctx->stream));
     if (n > 0) {

@@ -176,7 +176,7 @@ struct RefineArgs {
     int *evals_out;  // 2
     DevCam cam;
 };
-void launch_refine(const RefineArgs &a, cudaStream_t st);
+void launch_refine(const RefineArgs &a, int bucket, cudaStream_t st);
 void launch_project(const float *pose, const float *kps3d, const int *n_ptr, int max_kps, DevCam cam, float *kps2d, cudaStream_t st);
 
 // ---- stereo.cu

@@ -5,8 +5,7 @@
 // Plus project_keypoints (src/lib/transform_keypoints.cpp:11-47) as a stand-alone kernel.
 #include "kernels.cuh"
 
-#define REF_THREADS 256
-#define REF_WARPS (REF_THREADS / 32)
+#define REF_MAX_WARPS 16   // CTAs of 256 threads, or 512 for frames with more than 1024 keypoints
 #define RNGRAD 27
 
 // 6x6 SPD solve in double (LDL^T, one reciprocal per pivot)
@@ -63,8 +62,8 @@ __device__ bool refine_solve6(const double *Hu, const double *b, double *x)
 
 struct RefHdr {
     double Rd[18][9];   // two tables of 8 step sizes (x0 + 2^-j grad) + 2 spare slots, as in sparse_align_kernel
-    double cost_part[2][REF_WARPS];
-    float grad_part[RNGRAD][REF_WARPS];
+    double cost_part[2][REF_MAX_WARPS];
+    float grad_part[RNGRAD][REF_MAX_WARPS];
     double red_out[RNGRAD];
     float grad[6];
 };
@@ -72,12 +71,15 @@ struct RefHdr {
 // Solver state lives in registers, identical in every thread (decisions are recomputed redundantly from the
 // broadcast partial sums: one barrier per cost evaluation).  The rotation of the NEXT trial pose (halved step)
 // is computed speculatively by the last thread while the others evaluate the current one.
+template <int REF_THREADS>
 __global__ void __launch_bounds__(REF_THREADS, 1) reproj_refine_kernel(RefineArgs a, int max_kps)
 {
+    constexpr int REF_WARPS = REF_THREADS / 32;
     __shared__ RefHdr hdr;
-    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, nthr = REF_THREADS, lane = tid & 31, warp = tid >> 5;
     const int n = min(*a.n_ptr, max_kps);
     const DevCam cam = a.cam;
+    const bool nodist = dev_cam_nodist(cam);   // 40 % fewer double-precision instructions, which bound this one-CTA kernel (64 FP64 results per clock per SM)
     float x0[6], xt[6], grad[6];
 #pragma unroll
     for (int k = 0; k < 6; k++) { x0[k] = a.pose_in[k]; xt[k] = x0[k]; grad[k] = 0.f; }
@@ -95,8 +97,7 @@ __global__ void __launch_bounds__(REF_THREADS, 1) reproj_refine_kernel(RefineArg
             for (int i = tid; i < n; i += nthr) {
                 if (a.flags[i] & (SVO_F_IGN_REFINE | SVO_F_IGN_COMPLETE | SVO_F_IGN_TEMP)) continue;
                 float u, v;
-                dev_project(Rd, a.kps3d[3 * i], a.kps3d[3 * i + 1], a.kps3d[3 * i + 2], tx, ty, tz, cam.fx, cam.fy, cam.cx, cam.cy, cam.k1,
-                            cam.k2, cam.p1, cam.p2, cam.k3, u, v);
+                dev_project_nd(nodist, Rd, a.kps3d[3 * i], a.kps3d[3 * i + 1], a.kps3d[3 * i + 2], tx, ty, tz, cam.fx, cam.fy, cam.cx, cam.cy, cam, u, v);
                 float d0 = fabsf(u - a.kps2d[2 * i]), d1 = fabsf(v - a.kps2d[2 * i + 1]);
                 part += (double)(d0 + d1);
             }
@@ -152,7 +153,7 @@ __global__ void __launch_bounds__(REF_THREADS, 1) reproj_refine_kernel(RefineArg
                 if (a.flags[i] & (SVO_F_IGN_REFINE | SVO_F_IGN_COMPLETE | SVO_F_IGN_TEMP)) continue;
                 const float Px = a.kps3d[3 * i], Py = a.kps3d[3 * i + 1], Pz = a.kps3d[3 * i + 2];
                 float u, v;
-                dev_project(Rd, Px, Py, Pz, tx, ty, tz, cam.fx, cam.fy, cam.cx, cam.cy, cam.k1, cam.k2, cam.p1, cam.p2, cam.k3, u, v);
+                dev_project_nd(nodist, Rd, Px, Py, Pz, tx, ty, tz, cam.fx, cam.fy, cam.cx, cam.cy, cam, u, v);
                 float d0 = a.kps2d[2 * i] - u, d1 = a.kps2d[2 * i + 1] - v;
                 if ((fabs((double)d0) > 3.0) || (fabs((double)d1) > 3.0)) continue;
                 float X, Y, Z;
@@ -211,7 +212,7 @@ __global__ void __launch_bounds__(REF_THREADS, 1) reproj_refine_kernel(RefineArg
             n_grads++;
 #pragma unroll
             for (int k = 0; k < 6; k++) grad[k] = hdr.grad[k];
-            if (lane == 0) {   // warp j prepares the matrix of x0 + 2^-j grad
+            if (lane == 0 && warp < 8) {   // warp j prepares the matrix of x0 + 2^-j grad
                 float kj = 1.f;
                 for (int q = 0; q < warp; q++) kj = kj / 2;
                 dev_rodrigues_d(-(x0[3] + (kj * grad[3])), -(x0[4] + (kj * grad[4])), -(x0[5] + (kj * grad[5])), hdr.Rd[tb * 8 + warp]);
@@ -232,8 +233,13 @@ __global__ void __launch_bounds__(REF_THREADS, 1) reproj_refine_kernel(RefineArg
     }
 }
 
-void launch_refine_n(const RefineArgs &a, int max_kps, cudaStream_t st) { reproj_refine_kernel<<<1, REF_THREADS, 0, st>>>(a, max_kps); }
-void launch_refine(const RefineArgs &a, cudaStream_t st) { launch_refine_n(a, 1 << 30, st); }
+// bucket: upper bound of the keypoint count known at launch (graph capture) time; it picks the CTA size, so that a frame gives
+// the same bits whether it is replayed from a graph or launched directly
+void launch_refine(const RefineArgs &a, int bucket, cudaStream_t st)
+{
+    if (bucket > 1024) reproj_refine_kernel<512><<<1, 512, 0, st>>>(a, 1 << 30);   // C4: 114 instead of 128 us; no gain for a few hundred keypoints
+    else reproj_refine_kernel<256><<<1, 256, 0, st>>>(a, 1 << 30);
+}
 
 __global__ void __launch_bounds__(128) project_kernel(const float *pose, const float *kps3d, const int *n_ptr, int max_kps, DevCam cam,
                                                       float *kps2d)

@@ -436,9 +436,11 @@ def test_cuda_graph_replay_is_bit_identical():
         assert a.shape == b.shape and (a == b).all()
 
 
-def test_lk_template_cache_is_bit_identical(monkeypatch):
-    """LK templates fetched from the per-keyframe cache (default) and rebuilt from the keyframe pyramids for every frame
-    (SVO_NO_TEMPLATES=1, what calcOpticalFlowPyrLK does) give the same bits over a free-running sequence."""
+@pytest.mark.parametrize("knob,setting", [("SVO_NO_TEMPLATES", "1")])
+def test_scheduling_knobs_are_bit_identical(monkeypatch, knob, setting):
+    """Knobs that only change WHEN something is computed give the same bits over a free-running sequence as the defaults:
+    LK templates fetched from the per-keyframe cache (default) or rebuilt from the keyframe pyramids for every frame
+    (SVO_NO_TEMPLATES=1, what calcOpticalFlowPyrLK does)."""
     from stereo_svo_slam_b200 import StereoSlam
     gcs, _ = mk("C3")
     c = synth.CONFIGS["C3"]
@@ -446,9 +448,9 @@ def test_lk_template_cache_is_bit_identical(monkeypatch):
     runs = []
     for off in (False, True):
         if off:
-            monkeypatch.setenv("SVO_NO_TEMPLATES", "1")
+            monkeypatch.setenv(knob, setting)
         else:
-            monkeypatch.delenv("SVO_NO_TEMPLATES", raising=False)
+            monkeypatch.delenv(knob, raising=False)
         g = StereoSlam(gcs, c["width"], c["height"])
         poses, kps = [], []
         for k in range(14):
