@@ -483,6 +483,8 @@ __global__ void __launch_bounds__(KLT_THREADS) klt31_kernel(KltArgs a)
 // redundantly.  4 keypoints per 128-thread CTA; the footprint per keypoint is one warp.
 // ---------------------------------------------------------------------------------------------------------
 #define KLTW_WARPS 4
+#define KLTW_REG_ROWS 48     // staged search region per warp: 32 window rows + 8 above + 8 below
+#define KLTW_REG_PITCH 17    // words per staged row: 64 bytes + 1 word (odd pitch: the 32 rows of a warp-wide load hit 32 banks)
 
 // exact warp-wide sum of a 32-bit signed value per lane (|v| < 2^31), returned as 64 bit to every lane
 __device__ __forceinline__ long long warp_sum_i32_exact(int v)
@@ -631,10 +633,47 @@ __global__ void __launch_bounds__(32 * KLTW_WARPS, 4) klt31w_kernel(KltArgs a)
     float err = 0.f;
     int total_iters = 0;
 
+    // Search region of the current level in shared memory: KLTW_REG_ROWS rows x 64 bytes around the start position (the
+    // window moves by a fraction of a pixel per iteration), re-staged if the window ever leaves it.  A lane reads ITS row
+    // of the window, so a 4-byte global load of the warp touches 32 cache lines (32 L1 wavefronts); the same load from
+    // shared memory with an odd word pitch is one conflict-free wavefront — 9 loads per iteration, ~27 iterations per keypoint.
+    __shared__ uint32_t s_win[KLTW_WARPS][KLTW_REG_ROWS * KLTW_REG_PITCH];
+    uint32_t *swin = s_win[wid];
+    int reg_x0 = 0, reg_y0 = 0;
+    bool staged = false;
+    auto stage = [&](const LevelDesc &J, int ox, int oy) {
+        // origin: 8 px left of / above the window, 16-byte aligned in x, clamped to the level's padded buffer
+        // (rows -32 .. h + 31, bytes -32 .. pitch - 33 of every row)
+        const int x0 = min(max(((ox - 8) >> 4) << 4, -SVO_LK_PAD), J.pitch - SVO_LK_PAD - 64);
+        const int y0 = min(max(oy - 8, -SVO_LK_PAD), J.h + SVO_LK_PAD - KLTW_REG_ROWS);
+        __syncwarp();   // every lane is done with the previous region
+        uint4 v[KLTW_REG_ROWS * 4 / 32];
+#pragma unroll
+        for (int t = 0; t < KLTW_REG_ROWS * 4 / 32; t++) {
+            const int idx = lane + 32 * t, r = idx >> 2, c = idx & 3;
+            v[t] = *reinterpret_cast<const uint4 *>(J.ptr + (ptrdiff_t)(y0 + r) * J.pitch + x0 + 16 * c);
+        }
+#pragma unroll
+        for (int t = 0; t < KLTW_REG_ROWS * 4 / 32; t++) {
+            const int idx = lane + 32 * t, r = idx >> 2, c = idx & 3;
+            uint32_t *d = swin + r * KLTW_REG_PITCH + 4 * c;
+            d[0] = v[t].x; d[1] = v[t].y; d[2] = v[t].z; d[3] = v[t].w;
+        }
+        __syncwarp();
+        reg_x0 = x0; reg_y0 = y0; staged = true;
+    };
+    // window origin (ox, oy) inside the staged region?  9 words from the aligned-down byte must fit the 64-byte row,
+    // rows oy .. oy + 31 the KLTW_REG_ROWS rows
+    auto ensure_staged = [&](const LevelDesc &J, int ox, int oy) {
+        const int rx = ox - reg_x0, ry = oy - reg_y0;
+        if (!staged || rx < 0 || rx > 31 || ry < 0 || ry > KLTW_REG_ROWS - 32) stage(J, ox, oy);
+    };
+
     for (int level = SVO_LK_LEVELS - 1; level >= 0; level--) {
         const LevelDesc I = prev_lv[level];
         const LevelDesc Dv = prev_dv[level];
         const LevelDesc J = a.cur[level];
+        staged = false;
         const float scale = (float)(1. / (1 << level));
         float px = ppx * scale, py = ppy * scale;
         float qx, qy;
@@ -657,6 +696,11 @@ __global__ void __launch_bounds__(32 * KLTW_WARPS, 4) klt31w_kernel(KltArgs a)
             const uint4 *src = tpl_data + ((size_t)(tpl_slot * SVO_LK_LEVELS + level) * KLT_TPL_CHUNKS) * 32 + lane;
             const float4 h = tpl_hdr[tpl_slot * SVO_LK_LEVELS + level];
             A11 = h.x; A12 = h.y; A22 = h.z;
+            if (level > 0) {   // next level's template (48 lines of 128 bytes) on its way from DRAM while this level iterates
+                const char *nxt = reinterpret_cast<const char *>(tpl_data + ((size_t)(tpl_slot * SVO_LK_LEVELS + level - 1) * KLT_TPL_CHUNKS) * 32);
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + 128 * lane));
+                if (lane < 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + 128 * (32 + lane)));
+            }
 #pragma unroll
             for (int c = 0; c < 4; c++) {
                 const uint4 wa = src[(size_t)c * 32], wb = src[(size_t)(4 + c) * 32], wc = src[(size_t)(8 + c) * 32];
@@ -687,10 +731,11 @@ __global__ void __launch_bounds__(32 * KLTW_WARPS, 4) klt31w_kernel(KltArgs a)
         float pdx = 0.f, pdy = 0.f;
         // one evaluation pass over the window at integer origin (ox, oy) with weights w*: MODE 0 -> b1/b2, MODE 1 -> sum |diff|
         auto window_pass = [&](int ox, int oy, int w00, int w01, int w10, int w11, int &o1, int &o2, bool want_err) {
-            const uint8_t *rowp = J.ptr + (ptrdiff_t)(oy + lane) * J.pitch + ox;
-            const uintptr_t addr = reinterpret_cast<uintptr_t>(rowp);
-            const uint32_t *base = reinterpret_cast<const uint32_t *>(addr & ~(uintptr_t)3);
-            const int sh = (int)(addr & 3) * 8;
+            ensure_staged(J, ox, oy);
+            // row oy + lane, bytes ox .. ox + 32 (region origin and level rows are 16-byte aligned, so ox and rx share their low bits)
+            const int rx = ox - reg_x0, ry = oy - reg_y0;
+            const uint32_t *base = swin + (ry + lane) * KLTW_REG_PITCH + (rx >> 2);
+            const int sh = (rx & 3) * 8;
             uint32_t wv[9];
 #pragma unroll
             for (int k = 0; k < 9; k++) wv[k] = base[k];
