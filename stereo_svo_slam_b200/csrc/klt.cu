@@ -729,6 +729,10 @@ __global__ void __launch_bounds__(32 * KLTW_WARPS, 4) klt31w_kernel(KltArgs a)
         D = 1.f / D;
         qx -= half; qy -= half;
         float pdx = 0.f, pdy = 0.f;
+        // the template value enters the window passes as the accumulator of the bilinear dot product: with
+        // c = 2^8 - 2^9 Iw,  (taps + c) >> 9  ==  ((taps + 2^8) >> 9) - Iw  exactly (2^9 Iw is a multiple of the divisor)
+#pragma unroll
+        for (int x = 0; x < 31; x++) Iw[x] = (1 << 8) - (Iw[x] << 9);
         // one evaluation pass over the window at integer origin (ox, oy) with weights w*: MODE 0 -> b1/b2, MODE 1 -> sum |diff|
         auto window_pass = [&](int ox, int oy, int w00, int w01, int w10, int w11, int &o1, int &o2, bool want_err) {
             ensure_staged(J, ox, oy);
@@ -756,12 +760,13 @@ __global__ void __launch_bounds__(32 * KLTW_WARPS, 4) klt31w_kernel(KltArgs a)
                     const int x = 4 * k + q;
                     if (x < 31) {
                         unsigned v;
-                        // the rounding constant of (v + 2^8) >> 9 rides in as the accumulator of the first dot product
-                        if (q == 0) v = __dp2a_lo(Wt, top[k], __dp2a_lo(Wb, bot[k], 1u << 8));
-                        else if (q == 1) v = __dp2a_lo(Wt, ts, __dp2a_lo(Wb, bs, 1u << 8));
-                        else if (q == 2) v = __dp2a_hi(Wt, top[k], __dp2a_hi(Wb, bot[k], 1u << 8));
-                        else v = __dp2a_hi(Wt, ts, __dp2a_hi(Wb, bs, 1u << 8));
-                        const int diff = (int)(v >> 9) - Iw[x];
+                        // rounding constant and template value ride in as the accumulator of the first dot product
+                        const unsigned c0 = (unsigned)Iw[x];
+                        if (q == 0) v = __dp2a_lo(Wt, top[k], __dp2a_lo(Wb, bot[k], c0));
+                        else if (q == 1) v = __dp2a_lo(Wt, ts, __dp2a_lo(Wb, bs, c0));
+                        else if (q == 2) v = __dp2a_hi(Wt, top[k], __dp2a_hi(Wb, bot[k], c0));
+                        else v = __dp2a_hi(Wt, ts, __dp2a_hi(Wb, bs, c0));
+                        const int diff = (int)v >> 9;
                         if (want_err) acc1 += abs(diff);
                         else { acc1 += diff * Ix[x]; acc2 += diff * Iy[x]; }   // <= 31 * 8160 * 4080 < 2^31
                     }
