@@ -146,6 +146,7 @@ struct svo_ctx {
     bool use_graphs = true;
     int align_cluster = 0;    // SMs per alignment solve (svo_set_align_cluster); 0 = by keypoint count: 8, or 16 above 1024 keypoints
     bool use_fork = true;     // two-branch frame graph (SVO_NO_FORK=1: linear chain)
+    bool import_rode = false; // the keypoint import of the frame being captured is part of lk_side_kernel (no launch of its own)
     bool use_ingest = true;   // SM-driven frame ingest instead of copy-engine DMA (SVO_NO_INGEST=1 turns it off)
     unsigned long long graph_clock = 0;
     long long graph_launches = 0, graph_captures = 0, graph_updates = 0;
@@ -561,14 +562,19 @@ static int enqueue_pyramids(svo_ctx *ctx, Slot &s, bool forked, bool with_import
         CK(cudaEventRecord(ctx->fev[0], ctx->stream));
         CK(cudaStreamWaitEvent(ctx->stream2, ctx->fev[0], 0));
         lk_stream = ctx->stream2;
-        if (with_import) {
-            io_copy_kernel<<<1, 256, 0, ctx->stream2>>>(ctx->io_in);
-            CK(cudaEventRecord(ctx->fev[4], ctx->stream2));
-        }
     }
     for (int k = 0; k <= diag_dup("pyr"); k++) {
         launch_pyr_halfsample(s.dev, ctx->stream);
-        launch_lk_pyramid(s.dev, lk_stream);
+        if (k == 0 && forked && with_import) {
+            // the keypoint import rides in the first kernel of the side branch (lk_side_kernel); if that kernel cannot be used
+            // for this geometry it goes ahead of the pyramid as a kernel of its own
+            const bool fusable = lk_side_fusable(s.dev);
+            if (!fusable) io_copy_kernel<<<1, 256, 0, ctx->stream2>>>(ctx->io_in);
+            launch_lk_pyramid(s.dev, lk_stream, fusable ? &ctx->io_in : nullptr);
+            ctx->import_rode = fusable;
+            CK(cudaEventRecord(ctx->fev[4], ctx->stream2));
+        } else
+            launch_lk_pyramid(s.dev, lk_stream);
     }
     if (forked) CK(cudaEventRecord(ctx->fev[1], ctx->stream2));
     mark(ctx, 3);
@@ -1251,7 +1257,7 @@ static int enqueue_track(svo_ctx *ctx, int prev_slot, int cur_slot, int n, int g
     int launches = 0;
     // all inputs: the live entries by an SM-driven copy from the page-locked mirror, else one DMA of the whole capacity
     // (in + in/out regions are contiguous)
-    if (import_on_branch) { CK(cudaStreamWaitEvent(ctx->stream, ctx->fev[4], 0)); launches++; }
+    if (import_on_branch) { CK(cudaStreamWaitEvent(ctx->stream, ctx->fev[4], 0)); if (!ctx->import_rode) launches++; }
     else if (ctx->d_hio) { io_copy_kernel<<<1, 256, 0, ctx->stream>>>(ctx->io_in); launches++; }
     else CK(cudaMemcpyAsync(ctx->d_io, h, L.pose_aligned, cudaMemcpyHostToDevice, ctx->stream));
     // 1. sparse image alignment (stereo_slam.cpp:60-67)

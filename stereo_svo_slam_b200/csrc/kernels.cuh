@@ -70,7 +70,8 @@ __device__ __forceinline__ void io_copy_block(const IoCopyArgs &a)   // whole CT
 
 // ---- pyramid.cu
 void launch_pyr_halfsample(const ImageSetDev &s, cudaStream_t st);
-void launch_lk_pyramid(const ImageSetDev &s, cudaStream_t st);
+bool launch_lk_pyramid(const ImageSetDev &s, cudaStream_t st, const IoCopyArgs *io = nullptr);
+bool lk_side_fusable(const ImageSetDev &s);   // pad + level 1 (+ keypoint import) in one launch
 void launch_lk_scharr(const ImageSetDev &s, cudaStream_t st);   // derivative images of the three LK levels
 int pyr_launch_count(const ImageSetDev &s);
 struct IngestArgs {

@@ -119,20 +119,27 @@ __global__ void __launch_bounds__(256) lk_pyrdown_kernel(LevelDesc src, LevelDes
 // them assemble the four frame chunks of every row byte by byte through the reflection — kept in warps of their own so
 // that the copy warps never run the slow path.  Needs width, source pitch and both base addresses to be multiples of 16
 // (the per-byte kernel covers the rest).
+__device__ __forceinline__ void lk_pad_rows_job(const LevelDesc &src, const LevelDesc &dst, int job, int nthreads, int tid);
 __global__ void __launch_bounds__(64) lk_pad_level0_vec_kernel(LevelDesc src, LevelDesc dst)
+{
+    lk_pad_rows_job(src, dst, (int)blockIdx.y, 64, threadIdx.x);
+}
+
+// ---- device bodies shared by the stand-alone kernels above and the fused side-branch kernel below
+__device__ __forceinline__ void lk_pad_rows_job(const LevelDesc &src, const LevelDesc &dst, int job, int nthreads, int tid)
 {
     const int PH = dst.h + 2 * SVO_LK_PAD;
     const int chunks = (dst.w + 2 * SVO_LK_PAD) >> 4;
-    if ((int)blockIdx.y < PH) {
-        const int yp = blockIdx.y;
+    if (job < PH) {
+        const int yp = job;
         const int y = dev_reflect101(yp - SVO_LK_PAD, dst.h);
         const uint8_t *srow = src.ptr + (size_t)y * src.pitch;
         uint8_t *drow = dst.ptr + ((ptrdiff_t)(yp - SVO_LK_PAD)) * dst.pitch - SVO_LK_PAD;
-        for (int c = 2 + threadIdx.x; c < chunks - 2; c += blockDim.x)
+        for (int c = 2 + tid; c < chunks - 2; c += nthreads)
             *reinterpret_cast<uint4 *>(drow + c * 16) = __ldg(reinterpret_cast<const uint4 *>(srow + (c - 2) * 16));
         return;
     }
-    const int item = ((int)blockIdx.y - PH) * blockDim.x + threadIdx.x;   // (row, one of the four frame chunks)
+    const int item = (job - PH) * nthreads + tid;   // (row, one of the four frame chunks)
     const int yp = item >> 2, which = item & 3;
     if (yp >= PH) return;
     const int c = which < 2 ? which : chunks - 4 + which;
@@ -146,16 +153,78 @@ __global__ void __launch_bounds__(64) lk_pad_level0_vec_kernel(LevelDesc src, Le
     *reinterpret_cast<uint4 *>(drow + c * 16) = *reinterpret_cast<uint4 *>(b);
 }
 
-void launch_lk_pyramid(const ImageSetDev &s, cudaStream_t st)
+// cv::pyrDown of the UNPADDED source image into padded LK level 1: the same taps as lk_pyrdown_kernel on padded level 0, whose
+// frame is the REFLECT_101 image of this source — read through the reflection here, so level 1 does not wait for level 0
+__device__ __forceinline__ void lk_pyrdown_from_source(const LevelDesc &src, const LevelDesc &dst, int xp, int yp)
 {
-    {
+    const int PW = dst.w + 2 * SVO_LK_PAD, PH = dst.h + 2 * SVO_LK_PAD;
+    if (xp >= PW || yp >= PH) return;
+    const int x = dev_reflect101(xp - SVO_LK_PAD, dst.w), y = dev_reflect101(yp - SVO_LK_PAD, dst.h);
+    int cx[5], acc = 0;
+#pragma unroll
+    for (int k = 0; k < 5; k++) cx[k] = dev_reflect101(2 * x - 2 + k, src.w);
+    const int wgt[5] = {1, 4, 6, 4, 1};
+#pragma unroll
+    for (int r = 0; r < 5; r++) {
+        const uint8_t *q = src.ptr + (size_t)dev_reflect101(2 * y - 2 + r, src.h) * src.pitch;
+        int row = q[cx[0]] + q[cx[4]] + 4 * (q[cx[1]] + q[cx[3]]) + 6 * q[cx[2]];
+        acc += wgt[r] * row;
+    }
+    dst.ptr[(ptrdiff_t)(yp - SVO_LK_PAD) * dst.pitch + (xp - SVO_LK_PAD)] = (uint8_t)((acc + 128) >> 8);
+}
+
+// The side branch of a tracking frame in ONE launch (a kernel launch costs ~0.27 us of GPU front end at saturation, whatever
+// its size): CTAs [0, n_pad) pad level 0, [n_pad, n_pad + n_down) make padded level 1 straight from the source image, and the
+// last CTA (if any) imports the keypoint block.  Nothing in here depends on anything else in here.
+__global__ void __launch_bounds__(256) lk_side_kernel(LevelDesc l0, LevelDesc lk0, LevelDesc lk1, int n_pad, int n_down, int down_bx, IoCopyArgs io,
+                                                      int with_import)
+{
+    const int b = blockIdx.x;
+    if (b < n_pad) { lk_pad_rows_job(l0, lk0, b, 256, threadIdx.x); return; }
+    if (b < n_pad + n_down) {
+        const int j = b - n_pad;
+        lk_pyrdown_from_source(l0, lk1, (j % down_bx) * 256 + threadIdx.x, j / down_bx);
+        return;
+    }
+    if (with_import) io_copy_block(io);
+}
+
+static bool lk_pad_vec_ok(const ImageSetDev &s)
+{
+    const LevelDesc &d = s.lk[0];
+    const LevelDesc &l0 = s.left[0];
+    const uint8_t *dorigin = d.ptr - (ptrdiff_t)SVO_LK_PAD * d.pitch - SVO_LK_PAD;
+    return (d.w % 16 == 0) && (l0.pitch % 16 == 0) && (d.pitch % 16 == 0) && ((reinterpret_cast<uintptr_t>(l0.ptr) & 15) == 0) &&
+           ((reinterpret_cast<uintptr_t>(dorigin) & 15) == 0);
+}
+
+bool lk_side_fusable(const ImageSetDev &s)
+{
+    static const bool no_fuse = getenv("SVO_NO_SIDE_FUSION") != nullptr;
+    return lk_pad_vec_ok(s) && SVO_LK_LEVELS >= 2 && !no_fuse;
+}
+
+// io != null: the keypoint import rides along if the fused kernel is used; returns whether it did
+bool launch_lk_pyramid(const ImageSetDev &s, cudaStream_t st, const IoCopyArgs *io)
+{
+    bool imported = false;
+    int first = 1;
+    if (lk_side_fusable(s)) {
+        const LevelDesc &d0 = s.lk[0], &d1 = s.lk[1];
+        const int PH0 = d0.h + 2 * SVO_LK_PAD;
+        const int n_pad = PH0 + (PH0 * 4 + 255) / 256;
+        const int PW1 = d1.w + 2 * SVO_LK_PAD, PH1 = d1.h + 2 * SVO_LK_PAD;
+        const int down_bx = (PW1 + 255) / 256, n_down = down_bx * PH1;
+        IoCopyArgs none;
+        memset(&none, 0, sizeof(none));
+        lk_side_kernel<<<n_pad + n_down + (io ? 1 : 0), 256, 0, st>>>(s.left[0], d0, d1, n_pad, n_down, down_bx, io ? *io : none, io ? 1 : 0);
+        imported = io != nullptr;
+        first = 2;
+    } else {
         const LevelDesc &d = s.lk[0];
         const int PW = d.w + 2 * SVO_LK_PAD, PH = d.h + 2 * SVO_LK_PAD;
         const LevelDesc &l0 = s.left[0];
-        const uint8_t *dorigin = d.ptr - (ptrdiff_t)SVO_LK_PAD * d.pitch - SVO_LK_PAD;
-        const bool vec = (d.w % 16 == 0) && (l0.pitch % 16 == 0) && (d.pitch % 16 == 0) && ((reinterpret_cast<uintptr_t>(l0.ptr) & 15) == 0) &&
-                         ((reinterpret_cast<uintptr_t>(dorigin) & 15) == 0);
-        if (vec) {
+        if (lk_pad_vec_ok(s)) {
             dim3 grid(1, PH + (PH * 4 + 63) / 64);
             lk_pad_level0_vec_kernel<<<grid, 64, 0, st>>>(l0, d);
         } else {
@@ -163,12 +232,13 @@ void launch_lk_pyramid(const ImageSetDev &s, cudaStream_t st)
             lk_pad_level0_kernel<<<grid, 256, 0, st>>>(l0, d);
         }
     }
-    for (int l = 1; l < SVO_LK_LEVELS; l++) {
+    for (int l = first; l < SVO_LK_LEVELS; l++) {
         const LevelDesc &d = s.lk[l];
         int PW = d.w + 2 * SVO_LK_PAD, PH = d.h + 2 * SVO_LK_PAD;
         dim3 grid((PW + 255) / 256, PH);
         lk_pyrdown_kernel<<<grid, 256, 0, st>>>(s.lk[l - 1], d);
     }
+    return imported;
 }
 
 // Frame ingest: both images of a stereo pair, from ANY device-visible memory — page-locked host memory read by the SMs
@@ -280,4 +350,4 @@ void launch_lk_scharr(const ImageSetDev &s, cudaStream_t st)
     }
 }
 
-int pyr_launch_count(const ImageSetDev &s) { return (s.n_levels > 1 ? 1 : 0) + SVO_LK_LEVELS; }
+int pyr_launch_count(const ImageSetDev &s) { return (s.n_levels > 1 ? 1 : 0) + SVO_LK_LEVELS - (lk_side_fusable(s) ? 1 : 0); }
