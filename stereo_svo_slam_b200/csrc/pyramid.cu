@@ -313,8 +313,61 @@ __global__ void __launch_bounds__(256) copy16_kernel(const uint4 *__restrict__ s
 {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) dst[i] = __ldcs(src + i);
 }
+// A linear copy driven by the TMA unit: cp.async.bulk in (system or device memory -> shared), cp.async.bulk out (shared -> global),
+// ONE thread, a 4-stage ring with two loads in flight.  Chunks first, first + stride, ... of `chunk` bytes.
+__device__ __forceinline__ void bulk_copy_thread(const uint8_t *src, uint8_t *dst, size_t bytes, int chunk, long long first, long long stride,
+                                                 uint8_t *ring, unsigned long long *bar)
+{
+    for (int s = 0; s < 4; s++) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(&bar[s])), "r"(1) : "memory");
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const long long nchunks = (long long)((bytes + chunk - 1) / chunk);
+    const long long mine = first < nchunks ? (nchunks - first + stride - 1) / stride : 0;
+    auto issue = [&](long long k) {
+        const size_t off = (size_t)(first + k * stride) * chunk;
+        const uint32_t n = (uint32_t)((bytes - off < (size_t)chunk) ? (bytes - off) : (size_t)chunk);
+        const int s = (int)(k & 3);
+        const uint32_t b = (uint32_t)__cvta_generic_to_shared(&bar[s]), d = (uint32_t)__cvta_generic_to_shared(ring + (size_t)s * chunk);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(n) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d), "l"(src + off), "r"(n), "r"(b) : "memory");
+    };
+    for (long long k = 0; k < mine && k < 2; k++) issue(k);
+    for (long long k = 0; k < mine; k++) {
+        const int s = (int)(k & 3);
+        const uint32_t b = (uint32_t)__cvta_generic_to_shared(&bar[s]), parity = (uint32_t)((k >> 2) & 1);
+        uint32_t ok = 0;
+        while (!ok)
+            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(b), "r"(parity) : "memory");
+        const size_t off = (size_t)(first + k * stride) * chunk;
+        const uint32_t n = (uint32_t)((bytes - off < (size_t)chunk) ? (bytes - off) : (size_t)chunk);
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + off), "r"((uint32_t)__cvta_generic_to_shared(ring + (size_t)s * chunk)), "r"(n) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");   // the store of chunk k - 2 has read its stage: reload it
+        if (k + 2 < mine) issue(k + 2);
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// developer probe (SVO_ZC_BULK=<chunk bytes>): does the bulk-copy engine read system memory faster than the SMs' 16-byte loads?
+// (No: both reach the link's 51 GB/s; the TMA gets there with 4 single-thread CTAs instead of 32 CTAs of 256 threads.)
+__global__ void __launch_bounds__(32) copy_bulk_kernel(const uint8_t *src, uint8_t *dst, size_t bytes, int chunk)
+{
+    extern __shared__ __align__(128) uint8_t bulk_buf[];
+    __shared__ unsigned long long bar[4];
+    if (threadIdx.x != 0) return;
+    bulk_copy_thread(src, dst, bytes, chunk, blockIdx.x, gridDim.x, bulk_buf, bar);
+}
+
 void launch_copy16(const void *src, void *dst, size_t bytes, int ctas, cudaStream_t st)
 {
+    static const int bulk = getenv("SVO_ZC_BULK") ? atoi(getenv("SVO_ZC_BULK")) : 0;
+    if (bulk >= 16 && bulk <= 48 * 1024 && bulk % 16 == 0) {
+        static bool once = false;
+        if (!once) { cudaFuncSetAttribute(copy_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); once = true; }
+        copy_bulk_kernel<<<ctas, 32, 4 * (size_t)bulk, st>>>((const uint8_t *)src, (uint8_t *)dst, bytes, bulk);
+        return;
+    }
     copy16_kernel<<<ctas, 256, 0, st>>>((const uint4 *)src, (uint4 *)dst, bytes / 16);
 }
 
