@@ -160,15 +160,26 @@ __device__ __forceinline__ void lk_pyrdown_from_source(const LevelDesc &src, con
     const int PW = dst.w + 2 * SVO_LK_PAD, PH = dst.h + 2 * SVO_LK_PAD;
     if (xp >= PW || yp >= PH) return;
     const int x = dev_reflect101(xp - SVO_LK_PAD, dst.w), y = dev_reflect101(yp - SVO_LK_PAD, dst.h);
-    int cx[5], acc = 0;
-#pragma unroll
-    for (int k = 0; k < 5; k++) cx[k] = dev_reflect101(2 * x - 2 + k, src.w);
+    int acc = 0;
     const int wgt[5] = {1, 4, 6, 4, 1};
+    if (2 * x - 2 >= 0 && 2 * x + 2 < src.w && 2 * y - 2 >= 0 && 2 * y + 2 < src.h) {   // all 25 taps inside the image: no reflection
+        const uint8_t *p = src.ptr + (size_t)(2 * y - 2) * src.pitch + (2 * x - 2);
 #pragma unroll
-    for (int r = 0; r < 5; r++) {
-        const uint8_t *q = src.ptr + (size_t)dev_reflect101(2 * y - 2 + r, src.h) * src.pitch;
-        int row = q[cx[0]] + q[cx[4]] + 4 * (q[cx[1]] + q[cx[3]]) + 6 * q[cx[2]];
-        acc += wgt[r] * row;
+        for (int r = 0; r < 5; r++) {
+            const uint8_t *q = p + (size_t)r * src.pitch;
+            int row = q[0] + q[4] + 4 * (q[1] + q[3]) + 6 * q[2];
+            acc += wgt[r] * row;
+        }
+    } else {
+        int cx[5];
+#pragma unroll
+        for (int k = 0; k < 5; k++) cx[k] = dev_reflect101(2 * x - 2 + k, src.w);
+#pragma unroll
+        for (int r = 0; r < 5; r++) {
+            const uint8_t *q = src.ptr + (size_t)dev_reflect101(2 * y - 2 + r, src.h) * src.pitch;
+            int row = q[cx[0]] + q[cx[4]] + 4 * (q[cx[1]] + q[cx[3]]) + 6 * q[cx[2]];
+            acc += wgt[r] * row;
+        }
     }
     dst.ptr[(ptrdiff_t)(yp - SVO_LK_PAD) * dst.pitch + (xp - SVO_LK_PAD)] = (uint8_t)((acc + 128) >> 8);
 }
