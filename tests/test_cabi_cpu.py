@@ -26,6 +26,34 @@ def test_struct_layouts_match_reference():
     assert capi.KPINFO_DTYPE.itemsize == C.sizeof(capi.KeyPointInfo) == 56
 
 
+def test_ctypes_structs_match_the_header(tmp_path):
+    """sizeof / offsetof of every struct the Python binding mirrors, taken from include/svo_cuda.h by the C compiler"""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "layout.c"
+    probes = [("svo_camera_settings", capi.CameraSettings, ["baseline", "grid_height", "min_pyramid_level_pose_estimation"]),
+              ("svo_pose", capi.Pose, ["x", "rz"]),
+              ("svo_keypoint_info", capi.KeyPointInfo, ["keyframe_id", "keypoint_index", "outlier_count", "kf_variance"]),
+              ("svo_track_io", capi.TrackIO, ["n", "prev_kps2d", "pose_prior", "kps2d", "pose_aligned", "align_evals", "refine_evals",
+                                              "klt_pts", "klt_iters", "keypoint_index"])]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "svo_cuda.h"', 'int main(void) {']
+    for cname, _, fields in probes:
+        lines.append(f'  printf("{cname} %zu", sizeof({cname}));')
+        for f in fields:
+            lines.append(f'  printf(" %zu", offsetof({cname}, {f}));')
+        lines.append('  printf("\\n");')
+    lines += ['  return 0;', '}']
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.strip().splitlines()
+    for line, (cname, ctype, fields) in zip(out, probes):
+        vals = line.split()
+        assert vals[0] == cname and int(vals[1]) == C.sizeof(ctype), (cname, vals[1], C.sizeof(ctype))
+        for v, f in zip(vals[2:], fields):
+            assert int(v) == getattr(ctype, f).offset, (cname, f, v, getattr(ctype, f).offset)
+
+
 def test_product_path_does_not_import_oracle():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     pkg = os.path.join(root, "stereo_svo_slam_b200")
