@@ -365,6 +365,14 @@ extern "C" int svo_ctx_create(const svo_camera_settings *s, int device, int widt
     CKC(cudaMemset(ctx->d_kf_tpl, 0, (size_t)ctx->kf_cap * sizeof(KfTemplates)));
     CKC(cudaMalloc(&ctx->d_tpl_kps, (size_t)ctx->cell_cap * 8));
     ctx->use_templates = getenv("SVO_NO_TEMPLATES") == nullptr && s->window_size_opt_flow == 31;
+    if (ctx->use_templates) {   // first chunk of the template cache up front: the first keyframes do not allocate
+        const size_t cells = (size_t)(width / s->grid_width + 1) * (height / s->grid_height + 1);   // a first keyframe fills every cell
+        const size_t first = std::max((size_t)32 << 20, align_up(cells * (SVO_LK_LEVELS * (KLT_TPL_BYTES + sizeof(float4))) * 5 / 4, 1 << 20));
+        uint8_t *c = nullptr;
+        CKC(cudaMalloc(&c, first));
+        ctx->tpl_chunks.push_back(c);
+        ctx->tpl_chunk_bytes = first; ctx->tpl_chunk_used = 0;
+    }
 #undef CKC
     *out = ctx;
     return SVO_OK;
