@@ -477,6 +477,26 @@ def test_error_behaviour(c3ctx):
     bad["max_pyramid_levels"] = 9
     with pytest.raises(capi.SvoError):
         capi.Context(capi.CameraSettings(**bad), 752, 480)
+    # template cache: unknown keyframe, more templates than grid cells allow; a keyframe without templates still tracks
+    # (the kernel then builds the templates per frame), as does a keypoint index the cache does not cover
+    with pytest.raises(capi.SvoError):
+        ctx.keyframe_set_templates(12345, np.zeros((4, 2), np.float32))
+    img = (np.random.default_rng(5).integers(0, 256, (480, 752))).astype(np.uint8)
+    s0, s1 = ctx.upload(img, img), ctx.upload(img, img)
+    kf = ctx.keyframe_commit(s0, np.zeros(6, np.float32))
+    with pytest.raises(capi.SvoError):
+        ctx.keyframe_set_templates(kf, np.zeros((10 ** 6, 2), np.float32))
+    n = 40
+    k2 = np.stack([np.linspace(60, 700, n), np.linspace(50, 430, n)], 1).astype(np.float32)
+    k3 = np.concatenate([(k2 - [367.45, 252.2]) / 435.2 * 4.0, np.full((n, 1), 4.0)], 1).astype(np.float32)
+    args = dict(prev_kps2d=k2, kps3d=k3, ref_kps2d=k2, keyframe_id=np.full(n, kf, np.int32), flags=np.zeros(n, np.uint8),
+                inlier=np.zeros(n, np.int32), outlier=np.zeros(n, np.int32), kf_state=np.tile(np.float32([0.25, 10.0]), (n, 1)),
+                pose_prior=np.zeros(6, np.float32))
+    plain = ctx.track_frame(s0, s1, **args)
+    ctx.keyframe_set_templates(kf, k2[:20], first=0)            # only the first 20 keypoints are cached
+    mixed = ctx.track_frame(s0, s1, keypoint_index=np.arange(n, dtype=np.int32), **args)
+    assert (mixed["klt_pts"] == plain["klt_pts"]).all() and (mixed["klt_status"] == plain["klt_status"]).all()
+    assert (mixed["pose_refined"] == plain["pose_refined"]).all()
 
 
 # ----------------------------------------------------------------------------------------------- EuRoC rectification
