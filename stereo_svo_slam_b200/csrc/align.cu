@@ -632,6 +632,7 @@ __global__ void __launch_bounds__(ALIGN_THREADS, 1) sparse_align_kernel(AlignArg
         for (int k = 0; k < 6; k++) a.pose_out[k] = x0[k];
         *a.cost_out = prev_cost;
     }
+    if (a.rd_out && crank == 0 && tid < 9) a.rd_out[tid] = hdr->Rd[x0slot][tid];   // the matrix of the final pose, for KLT / refinement
     cluster_sync_all();   // no CTA exits while others may still write into its shared memory
 }
 

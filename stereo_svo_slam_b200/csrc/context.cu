@@ -84,7 +84,7 @@ struct Slot {
 struct IoLayout {
     size_t n, pose_prior, prev_kps2d, ref_kps2d, kf_id, kp_index;  // in
     size_t kps3d, flags, inlier, outlier, kf_state;                // in/out
-    size_t pose_aligned, pose_refined, costs, evals, klt_pts, klt_err, klt_status, klt_iters, disparity, kps2d_ref_in, kps2d_out;  // out
+    size_t pose_aligned, pose_refined, rd_aligned, rd_refined, costs, evals, klt_pts, klt_err, klt_status, klt_iters, disparity, kps2d_ref_in, kps2d_out;  // out
     size_t in_end, inout_begin, total;
 };
 
@@ -201,6 +201,8 @@ static void make_layout(IoLayout &L, int M)
     L.kf_state = take((size_t)M * 8);
     L.pose_aligned = take(6 * 4);
     L.pose_refined = take(6 * 4);
+    L.rd_aligned = take(9 * 8);     // Rodrigues(-r) of the two poses in double, handed from kernel to kernel (device only)
+    L.rd_refined = take(9 * 8);
     L.costs = take(2 * 4);
     L.evals = take(18 * 4);
     L.klt_pts = take((size_t)M * 8);
@@ -917,6 +919,7 @@ static void fill_align_args(svo_ctx *ctx, int prev_slot, int cur_slot, AlignArgs
     a.probe_level = -1; a.probe_grad = nullptr;
     a.dbg = ctx->d_marks ? ctx->d_marks + 16 : nullptr;
     a.cluster = ctx->align_cluster ? ctx->align_cluster : (n > 1024 ? 16 : 8);
+    a.rd_out = nullptr;
     (void)n;
 }
 
@@ -1038,6 +1041,7 @@ extern "C" int svo_reproj_refine(svo_ctx *ctx, const float *kps2d, const float *
     a.kps2d = DP(float, kps2d_ref_in); a.kps3d = DP(float, kps3d); a.flags = DP(uint8_t, flags); a.n_ptr = DP(int, n);
     a.pose_in = DP(float, pose_aligned); a.pose_out = DP(float, pose_refined);
     a.cost_out = DP(float, costs) + 1; a.evals_out = DP(int, evals) + 16; a.cam = ctx->cam;
+    a.rd_in = nullptr; a.rd_out = nullptr;
     launch_refine(a, (n + 127) / 128 * 128, ctx->stream);
     ctx->launch_total += 1;
     CK(cudaGetLastError());
@@ -1080,7 +1084,7 @@ extern "C" int svo_depth_filter_update(svo_ctx *ctx, int slot, int n, const floa
     fa.kps2d = DP(float, kps2d_ref_in); fa.ref_kps2d = DP(float, ref_kps2d); fa.kps3d = DP(float, kps3d);
     fa.flags = DP(uint8_t, flags); fa.inlier = DP(int, inlier); fa.outlier = DP(int, outlier); fa.kf_state = DP(float, kf_state);
     fa.pose = DP(float, pose_refined); fa.kps2d_out = DP(float, kps2d_out); fa.n_ptr = DP(int, n); fa.max_kps = n; fa.cam = ctx->cam;
-    fa.do_export = 0;
+    fa.do_export = 0; fa.rdn_in = nullptr;
     launch_depth_filter(fa, ctx->stream);
     ctx->launch_total += 2;
     CK(cudaGetLastError());
@@ -1271,6 +1275,7 @@ static int enqueue_track(svo_ctx *ctx, int prev_slot, int cur_slot, int n, int g
     // 1. sparse image alignment (stereo_slam.cpp:60-67)
     AlignArgs aa;
     fill_align_args(ctx, prev_slot, cur_slot, aa, grid_n, true);   // grid_n: the keypoint bucket (decides the cluster size with the graph)
+    aa.rd_out = DP(double, rd_aligned);
     if (prof) CK(cudaEventRecord(ctx->sev[2], ctx->stream));
     mark(ctx, 4);
     CK(launch_align(aa, ctx->stream)); launches++;
@@ -1286,6 +1291,7 @@ static int enqueue_track(svo_ctx *ctx, int prev_slot, int cur_slot, int n, int g
         if (ctx->use_templates) { ka.kf_tpl_table = ctx->d_kf_tpl; ka.kp_index = DP(int, kp_index); }
         for (int l = 0; l < SVO_LK_LEVELS; l++) ka.cur[l] = ctx->slots[cur_slot].dev.lk[l];
         ka.prev_pts = DP(float, ref_kps2d); ka.init_pts = nullptr; ka.kps3d = DP(float, kps3d); ka.pose = DP(float, pose_aligned);
+        ka.pose_rd = DP(double, rd_aligned);
         ka.n_ptr = DP(int, n); ka.next_pts = DP(float, klt_pts); ka.status = DP(uint8_t, klt_status); ka.err = DP(float, klt_err);
         ka.flags = DP(uint8_t, flags); ka.kps2d_out = DP(float, kps2d_ref_in); ka.max_kps = grid_n; ka.cam = ctx->cam;
         ka.iters = DP(int, klt_iters);
@@ -1314,6 +1320,7 @@ static int enqueue_track(svo_ctx *ctx, int prev_slot, int cur_slot, int n, int g
     ra.kps2d = DP(float, kps2d_ref_in); ra.kps3d = DP(float, kps3d); ra.flags = DP(uint8_t, flags); ra.n_ptr = DP(int, n);
     ra.pose_in = DP(float, pose_aligned); ra.pose_out = DP(float, pose_refined);
     ra.cost_out = DP(float, costs) + 1; ra.evals_out = DP(int, evals) + 16; ra.cam = ctx->cam;
+    ra.rd_in = DP(double, rd_aligned); ra.rd_out = DP(double, rd_refined);
     const int ref_bucket = std::min(ctx->max_kps, (grid_n + 127) / 128 * 128);   // == the graph's bucket
     launch_refine(ra, ref_bucket, ctx->stream); launches++;
     for (int k = 0; k < diag_dup("refine"); k++) launch_refine(ra, ref_bucket, ctx->stream);
@@ -1334,6 +1341,7 @@ static int enqueue_track(svo_ctx *ctx, int prev_slot, int cur_slot, int n, int g
         fa.flags = DP(uint8_t, flags); fa.inlier = DP(int, inlier); fa.outlier = DP(int, outlier); fa.kf_state = DP(float, kf_state);
         fa.pose = DP(float, pose_refined); fa.kps2d_out = DP(float, kps2d_out); fa.n_ptr = DP(int, n); fa.max_kps = grid_n; fa.cam = ctx->cam;
         fa.do_export = ctx->d_hio != nullptr; fa.exp = ctx->io_out;   // results go to the host mirror from the same kernel
+        fa.rdn_in = DP(double, rd_refined);
         mark(ctx, 8);
         launch_depth_filter(fa, ctx->stream); launches++;
         mark(ctx, 9);

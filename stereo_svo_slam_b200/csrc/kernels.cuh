@@ -119,6 +119,7 @@ struct AlignArgs {
     int probe_level;       // -1 = normal
     float *probe_grad;     // 6
     int cluster;           // CTAs (SMs) cooperating on the frame: 1, 2, 4 or 8
+    double *rd_out;        // 9: Rodrigues(-r) of pose_out in double, for the kernels that project with the aligned pose next (or null)
     int *dbg;              // developer aid (SVO_DEBUG_MARKS): where a stuck barrier wait was, else null
 };
 cudaError_t launch_align(const AlignArgs &a, cudaStream_t st);
@@ -154,6 +155,7 @@ struct KltArgs {
     const float *init_pts;         // n*2 or null => project kps3d with *pose
     const float *kps3d;            // n*3 (projection prologue)
     const float *pose;             // 6   (projection prologue)
+    const double *pose_rd;         // 9: Rodrigues(-r) of *pose as the alignment kernel left it, or null (computed per warp)
     const int *n_ptr;
     float *next_pts;               // n*2
     uint8_t *status;               // n
@@ -176,6 +178,8 @@ struct RefineArgs {
     float *pose_out, *cost_out;
     int *evals_out;  // 2
     DevCam cam;
+    const double *rd_in;   // 9: Rodrigues(-r) of pose_in as the alignment kernel left it (or null: computed here)
+    double *rd_out;        // 9: Rodrigues(-r) of pose_out (or null)
 };
 void launch_refine(const RefineArgs &a, int bucket, cudaStream_t st);
 void launch_project(const float *pose, const float *kps3d, const int *n_ptr, int max_kps, DevCam cam, float *kps2d, cudaStream_t st);
@@ -207,6 +211,7 @@ struct FilterArgs {
     const int *n_ptr;
     int max_kps;
     DevCam cam;
+    const double *rdn_in;         // 9: Rodrigues(-r) of `pose` as the refinement kernel left it (or null: computed here)
     int do_export;                // run io_copy_block(exp) when the update is done (results straight to the host mirror)
     IoCopyArgs exp;
 };

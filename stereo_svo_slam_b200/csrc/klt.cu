@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(KLT_THREADS) klt_pyr_lk_kernel(KltArgs a)
         else {
             double Rd[9];
             const float *p = a.pose;
-            dev_rodrigues_d(-p[3], -p[4], -p[5], Rd);
+            if (a.pose_rd) { for (int k = 0; k < 9; k++) Rd[k] = a.pose_rd[k]; } else dev_rodrigues_d(-p[3], -p[4], -p[5], Rd);
             dev_project(Rd, a.kps3d[3 * i], a.kps3d[3 * i + 1], a.kps3d[3 * i + 2], p[0], p[1], p[2], a.cam.fx, a.cam.fy, a.cam.cx,
                         a.cam.cy, a.cam.k1, a.cam.k2, a.cam.p1, a.cam.p2, a.cam.k3, gx, gy);
         }
@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(KLT_THREADS) klt31_kernel(KltArgs a)
         else {
             double Rd[9];
             const float *p = a.pose;
-            dev_rodrigues_d(-p[3], -p[4], -p[5], Rd);
+            if (a.pose_rd) { for (int k = 0; k < 9; k++) Rd[k] = a.pose_rd[k]; } else dev_rodrigues_d(-p[3], -p[4], -p[5], Rd);
             dev_project(Rd, a.kps3d[3 * i], a.kps3d[3 * i + 1], a.kps3d[3 * i + 2], p[0], p[1], p[2], a.cam.fx, a.cam.fy, a.cam.cx,
                         a.cam.cy, a.cam.k1, a.cam.k2, a.cam.p1, a.cam.p2, a.cam.k3, gx, gy);
         }
@@ -611,7 +611,7 @@ __global__ void __launch_bounds__(32 * KLTW_WARPS, 4) klt31w_kernel(KltArgs a)
     else {
         double Rd[9];
         const float *p = a.pose;
-        dev_rodrigues_d(-p[3], -p[4], -p[5], Rd);
+        if (a.pose_rd) { for (int k = 0; k < 9; k++) Rd[k] = a.pose_rd[k]; } else dev_rodrigues_d(-p[3], -p[4], -p[5], Rd);
         dev_project(Rd, a.kps3d[3 * i], a.kps3d[3 * i + 1], a.kps3d[3 * i + 2], p[0], p[1], p[2], a.cam.fx, a.cam.fy, a.cam.cx, a.cam.cy,
                     a.cam.k1, a.cam.k2, a.cam.p1, a.cam.p2, a.cam.k3, init_x, init_y);
     }

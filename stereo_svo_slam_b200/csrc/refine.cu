@@ -83,7 +83,8 @@ __global__ void __launch_bounds__(REF_THREADS, 1) reproj_refine_kernel(RefineArg
     float x0[6], xt[6], grad[6];
 #pragma unroll
     for (int k = 0; k < 6; k++) { x0[k] = a.pose_in[k]; xt[k] = x0[k]; grad[k] = 0.f; }
-    if (tid == 0) dev_rodrigues_d(-x0[3], -x0[4], -x0[5], hdr.Rd[16]);
+    if (a.rd_in) { if (tid < 9) hdr.Rd[16][tid] = a.rd_in[tid]; }
+    else if (tid == 0) dev_rodrigues_d(-x0[3], -x0[4], -x0[5], hdr.Rd[16]);
     __syncthreads();
     int mode = 0, it = 0, n_evals = 0, n_grads = 0, cbuf = 0, jstep = 0;
     int x0slot = 16, sp = 1, tb = 0, xtslot = 0;
@@ -231,6 +232,7 @@ __global__ void __launch_bounds__(REF_THREADS, 1) reproj_refine_kernel(RefineArg
         *a.cost_out = prev_cost;
         a.evals_out[0] = n_evals; a.evals_out[1] = n_grads;
     }
+    if (a.rd_out && tid < 9) a.rd_out[tid] = hdr.Rd[x0slot][tid];   // the matrix of the refined pose, for the depth filter
 }
 
 // bucket: upper bound of the keypoint count known at launch (graph capture) time; it picks the CTA size, so that a frame gives

@@ -599,7 +599,14 @@ __global__ void __launch_bounds__(DF_THREADS) depth_filter_kernel(FilterArgs a)
 {
     __shared__ FrameMats fm;
     const int n = min(*a.n_ptr, a.max_kps);
-    if (threadIdx.x == 0) {
+    if (a.rdn_in) {
+        // Rodrigues(-r) in double as the refinement kernel left it; float(Rodrigues(r)) is its transpose bit for bit
+        if (threadIdx.x < 9) {
+            const double v = a.rdn_in[threadIdx.x];
+            fm.Rdn[threadIdx.x] = v;
+            fm.R[(threadIdx.x % 3) * 3 + threadIdx.x / 3] = (float)v;
+        }
+    } else if (threadIdx.x == 0) {
         const float *p = a.pose;
         dev_rodrigues_f(p[3], p[4], p[5], fm.R);
         dev_rodrigues_d(-p[3], -p[4], -p[5], fm.Rdn);
