@@ -559,12 +559,9 @@ __global__ void __launch_bounds__(ALIGN_THREADS, 1) sparse_align_kernel(AlignArg
                     }
                 }
                 // warp reduce (float) -> CTA partial (double, 27 threads) -> every CTA's table through DSMEM
-#pragma unroll
-                for (int k = 0; k < NGRAD; k++) {
-                    float t = acc[k];
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
-                    if (lane == 0) hdr->warp_grad[warp][k] = t;
+                {
+                    const float t = warp_sum_scatter<NGRAD>(acc, lane);   // lane k: warp sum of term k
+                    if (lane < NGRAD) hdr->warp_grad[warp][lane] = t;
                 }
                 __syncthreads();
                 if (tid < NGRAD) {

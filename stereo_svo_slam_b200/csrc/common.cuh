@@ -149,6 +149,40 @@ __device__ __forceinline__ int dev_reflect101(int p, int len)
     return p;
 }
 
+// Warp-wide sums of N <= 32 per-lane values at once: lane l ends with the sum over all lanes of value l.  Every step halves the
+// number of values a lane still carries (the half whose index bit matches the lane's), so 31 shuffles do what N x 5 do when each
+// value is reduced on its own — and the additions pair up exactly as in the shfl_down tree (l with l^16, then ^8, ^4, ^2, ^1),
+// so the result has the same bits.
+template <int N>
+__device__ __forceinline__ float warp_sum_scatter(const float (&v)[N], int lane)
+{
+    float a16[16], a8[8], a4[4], a2[2];
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2, b0 = lane & 1;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const float lo = k < N ? v[k] : 0.f, hi = k + 16 < N ? v[k + 16] : 0.f;
+        const float mine = b4 ? hi : lo, send = b4 ? lo : hi;
+        a16[k] = mine + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const float mine = b3 ? a16[k + 8] : a16[k], send = b3 ? a16[k] : a16[k + 8];
+        a8[k] = mine + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const float mine = b2 ? a8[k + 4] : a8[k], send = b2 ? a8[k] : a8[k + 4];
+        a4[k] = mine + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const float mine = b1 ? a4[k + 2] : a4[k], send = b1 ? a4[k] : a4[k + 2];
+        a2[k] = mine + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    const float mine = b0 ? a2[1] : a2[0], send = b0 ? a2[0] : a2[1];
+    return mine + __shfl_xor_sync(0xffffffffu, send, 1);
+}
+
 // block-wide sum of `NV` doubles per thread; result valid in ALL threads of warp 0 lane 0 -> written to out[]
 // (fixed reduction tree => deterministic). scratch must hold NV * 32 doubles.
 template <int NV>

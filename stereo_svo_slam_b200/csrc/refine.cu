@@ -184,12 +184,9 @@ __global__ void __launch_bounds__(REF_THREADS, 1) reproj_refine_kernel(RefineArg
                     acc[21 + p] += t;
                 }
             }
-#pragma unroll
-            for (int k = 0; k < RNGRAD; k++) {
-                float t = acc[k];
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
-                if (lane == 0) hdr.grad_part[k][warp] = t;
+            {
+                const float t = warp_sum_scatter<RNGRAD>(acc, lane);   // lane k: warp sum of term k
+                if (lane < RNGRAD) hdr.grad_part[lane][warp] = t;
             }
             __syncthreads();
             if (tid < RNGRAD) {
