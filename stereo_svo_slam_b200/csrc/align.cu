@@ -137,6 +137,25 @@ __device__ __forceinline__ void dsmem_push_f64(void *local_slot, unsigned long l
 // exact u8 -> float without the slow I2F path: 0x4B000000 | v is the float 8388608 + v
 __device__ __forceinline__ float u8f(unsigned v) { return __uint_as_float(0x4B000000u | v) - 8388608.0f; }
 
+// five consecutive pixels at any byte address as exact floats: two aligned word loads instead of five byte loads (the lanes of a
+// warp read scattered patches, so every load instruction costs its wavefronts on the one shared-memory pipe of the SM), the bytes
+// picked out with PRMT straight into the 0x4B000000 | v form of u8f.  Reads up to 3 bytes past the fifth pixel: inside the
+// 16 bytes of slack every staged / stored level has.
+__device__ __forceinline__ void load5f(const uint8_t *p, float (&o)[5])
+{
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(p);
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(addr & ~(uintptr_t)3);
+    const uint32_t w0 = w[0], w1 = w[1];
+    const int sh = (int)(addr & 3) * 8;
+    const uint32_t t0 = __funnelshift_r(w0, w1, sh);        // pixels 0..3
+    const uint32_t t1 = sh ? (w1 >> sh) : w1;                // pixel 4 in its low byte (sh == 0: first byte of the second word)
+    o[0] = __uint_as_float(__byte_perm(t0, 0x4B000000u, 0x7440)) - 8388608.0f;
+    o[1] = __uint_as_float(__byte_perm(t0, 0x4B000000u, 0x7441)) - 8388608.0f;
+    o[2] = __uint_as_float(__byte_perm(t0, 0x4B000000u, 0x7442)) - 8388608.0f;
+    o[3] = __uint_as_float(__byte_perm(t0, 0x4B000000u, 0x7443)) - 8388608.0f;
+    o[4] = __uint_as_float(__byte_perm(t1, 0x4B000000u, 0x7440)) - 8388608.0f;
+}
+
 // get_patch_sum (pose_estimator.cpp:82-112), operation for operation
 __device__ __forceinline__ float patch_sum(const uint8_t *img, int pitch, float cx, float cy)
 {
@@ -233,7 +252,8 @@ __device__ __forceinline__ void intensity_diff_row(const uint8_t *im1, const uin
         const uint8_t *p1 = im1 + (ip1y + row) * pitch + ip1x, *p2 = im2 + (ip2y + row) * pitch + ip2x;
         float a0[5], a1[5], b0[5], b1[5];
 #pragma unroll
-        for (int j = 0; j < 5; j++) { a0[j] = u8f(p1[j]); a1[j] = u8f(p1[pitch + j]); b0[j] = u8f(p2[j]); b1[j] = u8f(p2[pitch + j]); }
+        for (int j = 0; j < 5; j++) { a0[j] = 0.f; a1[j] = 0.f; b0[j] = 0.f; b1[j] = 0.f; }
+        load5f(p1, a0); load5f(p1 + pitch, a1); load5f(p2, b0); load5f(p2 + pitch, b1);
         float d[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
@@ -644,6 +664,7 @@ static bool align_levels_fit(const AlignArgs &a, size_t &need)
         if (2 * b > 200 * 1024) fit = false;
         need = need > 2 * b ? need : 2 * b;
     }
+    need += 16;   // load5f reads whole words: up to 3 bytes past the last pixel of the second image
     return fit;
 }
 
