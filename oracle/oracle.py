@@ -11,6 +11,9 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "_build", "libsvo_oracle.so")
+# the reference itself (unmodified /root/reference/src/lib/*.cpp against oracle/cvshim), see oracle/Makefile
+_REF_PATH = os.path.join(_HERE, "_ref", "libstereosvo_ref.so")
+_REF_SOURCES = "/root/reference/src/lib"
 
 
 class CameraSettings(C.Structure):
@@ -26,8 +29,25 @@ def build(force=False):
     src = [os.path.join(_HERE, f) for f in ("svo_oracle.cpp", "ocv_prims.hpp", "Makefile")]
     if force or not os.path.exists(_LIB_PATH) or any(
             os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in src):
-        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+        subprocess.check_call(["make", "-C", _HERE, "-s", "_build/libsvo_oracle.so"] + (["-B"] if force else []))
+    build_ref(force)
     return _LIB_PATH
+
+
+def build_ref(force=False):
+    """oracle/_ref/libstereosvo_ref.so from the reference's own sources; only where /root/reference exists (this
+    container) — the GPU box uses the prebuilt file that travelled with the snapshot. Returns the path or None."""
+    if os.path.isdir(_REF_SOURCES):
+        src = [os.path.join(_HERE, f) for f in ("ref_capi.cpp", "ocv_prims.hpp", "Makefile",
+                                                os.path.join("cvshim", "opencv2", "opencv.hpp"))]
+        if force or not os.path.exists(_REF_PATH) or any(
+                os.path.getmtime(s) > os.path.getmtime(_REF_PATH) for s in src):
+            subprocess.check_call(["make", "-C", _HERE, "-s", "ref"] + (["-B"] if force else []))
+    return _REF_PATH if os.path.exists(_REF_PATH) else None
+
+
+def have_ref():
+    return build_ref() is not None
 
 
 _lib = None
@@ -314,6 +334,13 @@ class OracleSlam:
         lib().orc_slam_trace(self.h, name.encode(), _p(out), n)
         return out
 
+    def frame(self):
+        """Current frame as a dict (pose, id, ts, kps2d, kps3d, info columns) — same shape as RefSlam.frame()."""
+        return _dump(lambda *a: lib().orc_slam_frame(self.h, *a), True)
+
+    def keyframe_full(self, k):
+        return _dump(lambda *a: lib().orc_slam_keyframe_full(self.h, k, *a), False)
+
     def keyframe(self, k):
         n = lib().orc_slam_keyframe(self.h, k, None, None, None, 0)
         if n < 0:
@@ -323,3 +350,134 @@ class OracleSlam:
         k3 = np.empty((n, 3), np.float32)
         lib().orc_slam_keyframe(self.h, k, _p(pose), _p(k2), _p(k3), n)
         return pose, k2, k3
+
+
+INFO_COLS = ("level", "type", "keyframe_id", "keypoint_index", "flags", "inlier_count", "outlier_count", "color")
+
+
+def _dump(call, is_frame):
+    """Two-pass flat dump (count, then arrays) shared by the oracle and the reference handle APIs."""
+    pose = np.zeros(6, np.float32)
+    fid = C.c_uint64(0)
+    ts = C.c_double(0)
+    head = (_p(pose), C.byref(fid)) + ((C.byref(ts),) if is_frame else ())
+    n = call(*head, None, None, None, None, 0)
+    if n < 0:
+        return None
+    k2, k3 = np.zeros((n, 2), np.float32), np.zeros((n, 3), np.float32)
+    info, finfo = np.zeros((n, 8), np.int32), np.zeros((n, 3), np.float32)
+    call(*head, _p(k2), _p(k3), _p(info), _p(finfo), n)
+    d = {"pose": pose, "id": int(fid.value), "kps2d": k2, "kps3d": k3, "score": finfo[:, 0].copy(),
+         "kf_state": finfo[:, 1].copy(), "kf_cov": finfo[:, 2].copy()}
+    if is_frame:
+        d["ts"] = float(ts.value)
+    for i, c in enumerate(INFO_COLS):
+        d[c] = info[:, i].copy()
+    return d
+
+
+class RefSlam:
+    """The reference's own StereoSlam (oracle/_ref, built from the unmodified /root/reference/src/lib sources).
+
+    The library keeps process-global counters (depth_calculator.cpp:135, keyframe_manager.cpp:8), so every instance
+    loads a private copy of the shared object."""
+
+    def __init__(self, cs, width, height, quiet=True):
+        import shutil
+        import tempfile
+        path = build_ref()
+        if path is None:
+            raise RuntimeError("oracle/_ref/libstereosvo_ref.so is not built and /root/reference is absent")
+        fd, self._tmp = tempfile.mkstemp(prefix="libstereosvo_ref_", suffix=".so")
+        os.close(fd)
+        shutil.copyfile(path, self._tmp)
+        self.l = C.CDLL(self._tmp)
+        self.l.ref_slam_create.restype = C.c_void_p
+        assert self.l.ref_sizeof_camera_settings() == C.sizeof(CameraSettings)
+        self.l.ref_set_quiet(1 if quiet else 0)
+        self.cs, self.w, self.h_ = cs, width, height
+        self.h = C.c_void_p(self.l.ref_slam_create(C.byref(cs), width, height))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.l.ref_slam_destroy(self.h)
+            self.h = None
+        if getattr(self, "_tmp", None):
+            try:
+                os.unlink(self._tmp)
+            except OSError:
+                pass
+            self._tmp = None
+
+    __del__ = close
+
+    def new_image(self, left, right, ts):
+        left, right = _u8(left), _u8(right)
+        assert left.shape == (self.h_, self.w) and right.shape == left.shape
+        if self.l.ref_slam_new_image(self.h, _p(left), _p(right), self.w, C.c_float(ts)) != 0:
+            raise RuntimeError("reference new_image threw")
+
+    def update_pose(self, pose, speed, pose_var, speed_var, dt):
+        out = np.empty(6, np.float32)
+        a = [_f32(x) for x in (pose, speed, pose_var, speed_var)]
+        self.l.ref_slam_update_pose(self.h, _p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), C.c_double(dt), _p(out))
+        return out
+
+    def pose(self):
+        p = np.zeros(6, np.float32)
+        self.l.ref_slam_get_pose(self.h, _p(p))
+        return p
+
+    def frame(self):
+        return _dump(lambda *a: self.l.ref_slam_frame(self.h, *a), True)
+
+    def n_kps(self):
+        return self.l.ref_slam_frame(self.h, None, None, None, None, None, None, None, 0)
+
+    def n_keyframes(self):
+        return self.l.ref_slam_n_keyframes(self.h)
+
+    def keyframe_full(self, k):
+        return _dump(lambda *a: self.l.ref_slam_keyframe(self.h, k, *a), False)
+
+    def keyframe_image(self, which, level):
+        """which: 0 left halfSample level, 1 right, 2 LK pyramid image level, 3 LK Scharr level (int16, 2 channels)."""
+        w, h = C.c_int(0), C.c_int(0)
+        nb = self.l.ref_slam_keyframe_image(self.h, which, level, None, 0, C.byref(w), C.byref(h))
+        if nb < 0:
+            return None
+        buf = np.empty(nb, np.uint8)
+        self.l.ref_slam_keyframe_image(self.h, which, level, _p(buf), nb, C.byref(w), C.byref(h))
+        if which == 3:
+            return buf.view(np.int16).reshape(h.value, w.value, 2)
+        return buf.reshape(h.value, w.value)
+
+    def trajectory(self):
+        n = self.l.ref_slam_trajectory(self.h, None, 0)
+        out = np.empty((n, 6), np.float32)
+        self.l.ref_slam_trajectory(self.h, _p(out), n)
+        return out
+
+    # stage entry points of the reference (stateless)
+    def expmap(self, tw):
+        tw = _f32(tw)
+        out = np.empty(6, np.float32)
+        self.l.ref_expmap(_p(tw), _p(out))
+        return out
+
+    def project(self, pose6, pts3):
+        pts3 = _f32(pts3).reshape(-1, 3)
+        pose6 = _f32(pose6)
+        out = np.empty((pts3.shape[0], 2), np.float32)
+        self.l.ref_project(C.byref(self.cs), _p(pose6), _p(pts3), pts3.shape[0], _p(out))
+        return out
+
+    def detect_keypoints(self, img, grid_w, grid_h, level=0):
+        img = _u8(img)
+        h, w = img.shape
+        mx = (w // max(1, grid_w) + 1) * (h // max(1, grid_h) + 1) + 8
+        xy = np.empty((mx, 2), np.float32)
+        sc = np.empty(mx, np.float32)
+        ty = np.empty(mx, np.int32)
+        n = self.l.ref_detect_keypoints(_p(img), w, h, grid_w, grid_h, level, mx, _p(xy), _p(sc), _p(ty))
+        return xy[:n].copy(), sc[:n].copy(), ty[:n].copy()

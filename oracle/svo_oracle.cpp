@@ -61,7 +61,9 @@ struct PoseM {
     }
 };
 
-// exponential_map.hpp:12-37 (norm fixed to 1; w unchanged)
+// exponential_map.hpp:12-37 (norm fixed to 1; w unchanged).  `cos(_norm)` on a float: with <opencv2/opencv.hpp> included
+// (it pulls in <math.h>, i.e. libstdc++'s global float overloads) this is the float cosine, so both scale factors are float
+// and `scalar * Matx33f` multiplies in float — pinned against the reference itself (oracle/_ref, tests/test_ref_pin.py).
 static void exponential_map(const float twist[6], float out[6])
 {
     const float *v = twist, *w = twist + 3;
@@ -73,13 +75,13 @@ static void exponential_map(const float twist[6], float out[6])
             for (int k = 0; k < 3; k++) s += K[i * 3 + k] * K[k * 3 + j];
             K2[i * 3 + j] = s;
         }
-    float norm = 1.0f;
-    double c1 = 1 - cos((double)norm), c2 = (double)norm - sin((double)norm);
+    volatile float norm = 1.0f;
+    float c1 = 1 - cosf(norm), c2 = norm - sinf(norm);
     float M[9];
     for (int i = 0; i < 9; i++) {
         float e = ((i % 4 == 0) ? 1.f : 0.f) * norm;
-        float a = (float)((double)K[i] * c1);    // Matx * double -> saturate_cast<float>
-        float b = (float)((double)K2[i] * c2);
+        float a = K[i] * c1;
+        float b = K2[i] * c2;
         M[i] = (e + a) + b;
     }
     float t[3];
@@ -1141,6 +1143,42 @@ int orc_slam_trace(void *h, const char *name, float *out, int max)
     int n = (int)std::min<size_t>(it->second.size(), (size_t)max);
     if (out) memcpy(out, it->second.data(), sizeof(float) * n);
     return (int)it->second.size();
+}
+// flat dump of a keypoint set, same layout as oracle/ref_capi.cpp's dump_kps (colour is not modelled: rand())
+static int dump_kps(const KeyPoints &k, float *kps2d, float *kps3d, int32_t *info8, float *finfo3, int max)
+{
+    int n = (int)k.size(), c = std::min(n, max);
+    for (int i = 0; i < c; i++) {
+        if (kps2d && (size_t)(2 * i + 1) < k.kps2d.size()) { kps2d[2 * i] = k.kps2d[2 * i]; kps2d[2 * i + 1] = k.kps2d[2 * i + 1]; }
+        if (kps3d && (size_t)(3 * i + 2) < k.kps3d.size()) for (int q = 0; q < 3; q++) kps3d[3 * i + q] = k.kps3d[3 * i + q];
+        const KpInfo &in = k.info[i];
+        if (info8) {
+            int32_t *o = info8 + 8 * i;
+            o[0] = in.level; o[1] = in.type; o[2] = (int32_t)in.keyframe_id; o[3] = (int32_t)in.keypoint_index;
+            o[4] = (in.ignore_during_refinement ? 1 : 0) | (in.ignore_completely ? 2 : 0) | (in.ignore_temporary ? 4 : 0);
+            o[5] = in.inlier_count; o[6] = in.outlier_count; o[7] = 0;
+        }
+        if (finfo3) { finfo3[3 * i] = in.score; finfo3[3 * i + 1] = in.kf ? in.kf->k.xpost[0] : 0.f; finfo3[3 * i + 2] = in.kf ? in.kf->k.Ppost[0] : 0.f; }
+    }
+    return n;
+}
+int orc_slam_frame(void *h, float *p6, uint64_t *id, double *ts, float *kps2d, float *kps3d, int32_t *info8, float *finfo3, int max)
+{
+    OracleSlam *s = (OracleSlam *)h;
+    if (!s->frame) return -1;
+    if (p6) for (int i = 0; i < 6; i++) p6[i] = s->frame->pose.p[i];
+    if (id) *id = s->frame->id;
+    if (ts) *ts = s->frame->time_stamp;
+    return dump_kps(s->frame->kps, kps2d, kps3d, info8, finfo3, max);
+}
+int orc_slam_keyframe_full(void *h, int k, float *p6, uint64_t *id, float *kps2d, float *kps3d, int32_t *info8, float *finfo3, int max)
+{
+    OracleSlam *s = (OracleSlam *)h;
+    if (k < 0 || k >= (int)s->keyframes.size()) return -1;
+    KeyFrame &f = *s->keyframes[k];
+    if (p6) for (int i = 0; i < 6; i++) p6[i] = f.pose.p[i];
+    if (id) *id = f.id;
+    return dump_kps(f.kps, kps2d, kps3d, info8, finfo3, max);
 }
 // keyframe k: pose (6) ; kps2d/kps3d of the keyframe's own arrays
 int orc_slam_keyframe(void *h, int k, float *pose6, float *kps2d, float *kps3d, int max)

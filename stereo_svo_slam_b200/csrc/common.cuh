@@ -117,11 +117,14 @@ __device__ __forceinline__ void dev_project_nd(bool nodist, const double *Rd, fl
     v = (float)(y * (double)fy + (double)cy);
 }
 
-// exponential_map.hpp:12-37 — norm fixed to 1, w unchanged; Matx * double -> float rounding as in OpenCV
+// exponential_map.hpp:12-37 — norm fixed to 1, w unchanged.  `cos(_norm)` / `sin(_norm)` take a float there, and under
+// <opencv2/opencv.hpp> (which pulls in <math.h>, hence libstdc++'s global float overloads) they are float calls, so the two
+// scale factors are the FLOAT values 1 - cosf(1) and 1 - sinf(1) and `scalar * Matx33f` rounds float products — pinned against
+// the reference itself (oracle/_ref, tests/test_ref_pin.py).
 __device__ __forceinline__ void dev_expmap(const float tw[6], float out[6])
 {
-    const double C1 = 0.45969769413186023;  // 1 - cos(1)
-    const double C2 = 0.1585290151921035;   // 1 - sin(1)
+    const float C1 = 0x1.d6bbp-2f;   // 1.f - cosf(1.f)
+    const float C2 = 0x1.44aaep-3f;  // 1.f - sinf(1.f)
     float w0 = tw[3], w1 = tw[4], w2 = tw[5];
     float K[9] = {0.f, -w2, w1, w2, 0.f, -w0, -w1, w0, 0.f};
     float M[9];
@@ -134,8 +137,8 @@ __device__ __forceinline__ void dev_expmap(const float tw[6], float out[6])
             s += K[i * 3 + 1] * K[1 * 3 + j];
             s += K[i * 3 + 2] * K[2 * 3 + j];
             float e = (i == j) ? 1.f : 0.f;
-            float a = (float)((double)K[i * 3 + j] * C1);
-            float b = (float)((double)s * C2);
+            float a = K[i * 3 + j] * C1;
+            float b = s * C2;
             M[i * 3 + j] = (e + a) + b;
         }
     dev_m33v(M, tw[0], tw[1], tw[2], out[0], out[1], out[2]);

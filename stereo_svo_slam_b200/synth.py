@@ -117,6 +117,11 @@ CONFIGS = {
     "S": dict(width=320, height=240, fx=220.0, fy=220.0, cx=160.0, cy=120.0, baseline=22.0,
               grid_width=32, grid_height=24, search_x=30, search_y=4, max_pyramid_levels=4,
               min_pyramid_level_pose_estimation=2, seed=77, frames=30),
+    # the small case with four times the camera motion: keyframes #2 and #3 appear at frames 68 and 89, so 100 frames cover
+    # find_bad_keypoints / merge_keypoints with old keypoints and frames whose keypoints come from three origin keyframes
+    "SF": dict(width=320, height=240, fx=220.0, fy=220.0, cx=160.0, cy=120.0, baseline=22.0,
+               grid_width=32, grid_height=24, search_x=30, search_y=4, max_pyramid_levels=4,
+               min_pyramid_level_pose_estimation=2, seed=77, frames=100, max_step_m=0.12, max_step_deg=1.2),
 }
 
 
@@ -132,4 +137,4 @@ def settings_dict(cfg):
 def make_sequence(cfg, seed=None):
     c = CONFIGS[cfg] if isinstance(cfg, str) else cfg
     return SyntheticStereo(c["width"], c["height"], c["fx"], c["fy"], c["cx"], c["cy"], c["baseline"],
-                           c["seed"] if seed is None else seed)
+                           c["seed"] if seed is None else seed, c.get("max_step_m", 0.03), c.get("max_step_deg", 0.3))
