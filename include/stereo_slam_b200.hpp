@@ -201,7 +201,7 @@ private:
         };
         pull(0, camera_settings.max_pyramid_levels, f.stereo_image.left);
         pull(1, 1, f.stereo_image.right);
-        pull(2, 3, f.stereo_image.opt_flow);  // image levels only: the Scharr planes are fused into the KLT kernel
+        pull(2, 3, f.stereo_image.opt_flow);  // image levels only (the Scharr levels live on the device: svo_download_level kind 3)
         return true;
     }
 

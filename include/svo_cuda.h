@@ -65,9 +65,11 @@ int svo_device_count(void);
 /* Upload one stereo pair and build, on the device, everything new_image builds per frame
  * (stereo_slam.cpp:135-139): the halfSample pyramid of `left` (max_pyramid_levels levels, :93-121),
  * level 0 of `right`, and the 3-level LK pyramid of `left` (cv::buildOpticalFlowPyramid(left, win, 2):
- * Gaussian pyrDown, REFLECT_101 border; Scharr derivatives are fused into svo_klt, not stored).
- * Returns a slot id; slots are reference counted (a keyframe shares its frame's images,
- * keyframe_manager.cpp:27-29). */
+ * Gaussian pyrDown, every level stored with its REFLECT_101 frame).  The Scharr derivative levels of that pyramid are
+ * materialised only for image sets that become keyframes (svo_keyframe_commit) — OpenCV builds them for every frame, but
+ * only a keyframe's are ever read (optical_flow.cpp:41-44) — or on demand (svo_download_level kind 3, svo_klt_slots).
+ * Returns a slot id; slots are reference counted.  A keyframe owns a COPY of its frame's image set (the reference
+ * shares the cv::Mat buffers, keyframe_manager.cpp:27-29; a copy lets frames alternate between two fixed slots). */
 int svo_upload_stereo(svo_ctx *ctx, const uint8_t *left, size_t left_stride, const uint8_t *right, size_t right_stride,
                       int *slot_out);
 /* Same, for images that already live in device memory of the context's GPU (e.g. a camera/decoder pipeline
@@ -85,9 +87,17 @@ int svo_set_rectification(svo_ctx *ctx, int which, const double K[9], const doub
 int svo_clear_rectification(svo_ctx *ctx);
 /* the float maps of input `which` (width*height each) — parity with cv::initUndistortRectifyMap */
 int svo_rectification_maps(svo_ctx *ctx, int which, float *map1, float *map2);
+/* number of keypoints a tracking frame / a keyframe may hold (max_keypoints of svo_ctx_create rounded up to 32; default 4 per
+ * grid cell) */
+int svo_keypoint_capacity(svo_ctx *ctx, int *max_keypoints);
 int svo_slot_retain(svo_ctx *ctx, int slot);
 int svo_slot_release(svo_ctx *ctx, int slot);
-/* kind: 0 = left halfSample pyramid level, 1 = right level 0, 2 = LK pyramid level (unpadded view) */
+/* kind: 0 = left halfSample pyramid level, 1 = right level 0, 2 = LK pyramid level (unpadded view),
+ *       3 = Scharr derivative level of the LK pyramid: (Ix, Iy) int16 pairs, 4 bytes per pixel (built on demand — the
+ *           tracking path only materialises them for keyframes, the only image sets ever used as LK reference),
+ *       4 / 5 = the LK image level / the Scharr level TOGETHER WITH the 32-pixel frame kept around them: BORDER_REFLECT_101
+ *           pixels around the image, BORDER_CONSTANT zeros around the derivatives (cv::buildOpticalFlowPyramid's pyrBorder /
+ *           derivBorder defaults, stereo_slam.cpp:139).  Sizes are in pixels; out_stride in bytes. */
 int svo_slot_level_size(svo_ctx *ctx, int kind, int level, int *width, int *height);
 int svo_download_level(svo_ctx *ctx, int slot, int kind, int level, uint8_t *out, size_t out_stride);
 
@@ -196,8 +206,9 @@ typedef struct svo_track_io {
 
 int svo_track_frame(svo_ctx *ctx, int prev_slot, int cur_slot, svo_track_io *io);
 /* svo_upload_stereo[_device] + svo_track_frame_begin in one call — everything new_image enqueues for a tracking frame
- * (stereo_slam.cpp:135-139 and :196-229).  In steady state everything after the two image copies (4 pyramid kernels, keypoint
- * H2D, 5 tracking kernels, D2H) is replayed as ONE CUDA graph launch; finish with svo_track_frame_end.
+ * (stereo_slam.cpp:135-139 and :196-229).  In steady state everything after the frame ingest (half-sample pyramid, the LK
+ * pyramid's two kernels with the keypoint import, alignment, KLT, refinement, stereo SSD, depth filter with the result
+ * export: 8 kernels on two graph branches) is replayed as ONE CUDA graph launch; finish with svo_track_frame_end.
  * on_device != 0: left/right are device pointers. */
 int svo_frame_begin(svo_ctx *ctx, const uint8_t *left, size_t left_stride, const uint8_t *right, size_t right_stride,
                     int on_device, int prev_slot, svo_track_io *io, int *cur_slot_out);
@@ -255,6 +266,9 @@ typedef struct svo_keypoint_info {  /* KeyPointInformation without the cv::Kalma
 } svo_keypoint_info;
 
 int svo_slam_create(const svo_camera_settings *settings, int device, int width, int height, svo_slam **out);
+/* same, with an explicit keypoint capacity (max_keypoints of svo_ctx_create; 0 = default) */
+int svo_slam_create_with_capacity(const svo_camera_settings *settings, int device, int width, int height, int max_keypoints,
+                                  svo_slam **out);
 int svo_slam_destroy(svo_slam *s);
 const char *svo_slam_last_error(svo_slam *s);
 /* StereoSlam::new_image (stereo_slam.cpp:123-271) */
@@ -293,6 +307,37 @@ int svo_slam_last_stats(svo_slam *s, float *gpu_ms, int *launches, int *keyframe
 int svo_slam_last_counters(svo_slam *s, long long *out8);
 /* the device context behind the facade (for stage-level probes in tests) */
 svo_ctx *svo_slam_ctx(svo_slam *s);
+/* new keypoints that keyframes could not take because the device keypoint block (svo_keypoint_capacity) was full; the
+ * reference's lists are unbounded, here a keyframe then keeps its best-scored new keypoints (0 in every tested sequence) */
+int svo_slam_dropped_keypoints(svo_slam *s, long long *dropped);
+
+/* ================================================================== host stages ================ */
+/* The bookkeeping of DepthCalculator / KeyFrameManager / StereoSlam that stays on the CPU between the device stages, one
+ * entry point each.  Pure host code: no context, no device — they run (and are tested against the reference) without a GPU.
+ * The facade calls the same functions. */
+/* select_best_keypoints (depth_calculator.cpp:37-65): the per-level lists of CornerDetector::detect_keypoints folded into
+ * one choice per LIST INDEX (entry j of every level competes with entry j of level 0): FAST beats edgelet, within a type the
+ * coarser level wins unless the finer score is strictly higher; coarser positions are scaled by 2^level. */
+int svo_host_select_best_keypoints(int n_levels, const int *n_per_level, const float *const *xy, const float *const *score,
+                                   const int *const *type, int max_out, float *kps2d, float *score_out, int *type_out,
+                                   int *level_out, int *n_out);
+/* find_bad_keypoints (depth_calculator.cpp:67-86): keep[i] = 0 for keypoints outside [0, width] x [0, height] or flagged
+ * ignore_completely / ignore_during_refinement */
+int svo_host_find_bad_keypoints(int width, int height, int n, const float *kps2d, const uint8_t *flags, uint8_t *keep);
+/* merge_keypoints (depth_calculator.cpp:88-130) as DepthCalculator::calculate_depth calls it (:179-180, grid arguments
+ * swapped): appended[] = indices into the new list of the keypoints that join the old ones, in the order they are appended */
+int svo_host_merge_keypoints(int width, int height, int grid_width, int grid_height, int n_old, const float *old_kps2d,
+                             int n_new, const float *new_kps2d, int max_out, int *appended, int *n_out);
+/* KeyFrameManager::keyframe_needed (keyframe_manager.cpp:47-74) */
+int svo_host_keyframe_needed(int width, int height, int grid_width, int grid_height, int n, const float *kps2d,
+                             const uint8_t *flags, int *needed);
+/* the 12-state motion filter of StereoSlam (cv::KalmanFilter(12, 12), stereo_slam.cpp:29-41) and one
+ * StereoSlam::update_pose step (:296-359); state_pre12 (may be NULL) = kf.statePre, the pose prior of the next image (:184-189) */
+typedef struct svo_motion_filter svo_motion_filter;
+int svo_motion_filter_create(svo_motion_filter **out);
+int svo_motion_filter_destroy(svo_motion_filter *m);
+int svo_motion_filter_update(svo_motion_filter *m, const svo_pose *pose, const float speed[6], const float pose_variance[6],
+                             const float speed_variance[6], double dt, svo_pose *filtered, float state_pre12[12]);
 
 #ifdef __cplusplus
 }

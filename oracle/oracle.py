@@ -279,6 +279,45 @@ def refine(cs, kps2d, kps3d, flags, pose_in):
     return pose_out, float(cost), ev
 
 
+def _pp(arrs, ctype):
+    """array of pointers to the rows of a ragged list"""
+    return (C.POINTER(ctype) * len(arrs))(*[a.ctypes.data_as(C.POINTER(ctype)) for a in arrs])
+
+
+def select_best(levels):
+    """select_best_keypoints (depth_calculator.cpp:37-65); levels = [(xy (n,2) f32, score (n) f32, type (n) i32), ...]."""
+    xy = [_f32(l[0]).reshape(-1, 2) for l in levels]
+    sc = [_f32(l[1]) for l in levels]
+    ty = [np.ascontiguousarray(l[2], dtype=np.int32) for l in levels]
+    n0 = len(sc[0])
+    cnt = np.array([len(x) for x in sc], np.int32)
+    k2, so, to, lo = np.zeros((n0, 2), np.float32), np.zeros(n0, np.float32), np.zeros(n0, np.int32), np.zeros(n0, np.int32)
+    n = lib().orc_select_best(len(levels), _p(cnt), _pp(xy, C.c_float), _pp(sc, C.c_float), _pp(ty, C.c_int), _p(k2), _p(so), _p(to), _p(lo))
+    assert n == n0
+    return k2, so, to, lo
+
+
+def find_bad(w, h, kps2d, flags):
+    kps2d = _f32(kps2d).reshape(-1, 2)
+    flags = np.ascontiguousarray(flags, dtype=np.uint8)
+    keep = np.zeros(len(flags), np.uint8)
+    lib().orc_find_bad(w, h, len(flags), _p(kps2d), _p(flags), _p(keep))
+    return keep
+
+
+def merge(w, h, grid_width, grid_height, old2d, new2d):
+    old2d, new2d = _f32(old2d).reshape(-1, 2), _f32(new2d).reshape(-1, 2)
+    app = np.zeros(max(1, 64 * len(new2d) + 64), np.int32)
+    n = lib().orc_merge(w, h, grid_width, grid_height, len(old2d), _p(old2d), len(new2d), _p(new2d), _p(app))
+    return app[:n].copy()
+
+
+def keyframe_needed(w, h, grid_width, grid_height, kps2d, flags):
+    kps2d = _f32(kps2d).reshape(-1, 2)
+    flags = np.ascontiguousarray(flags, dtype=np.uint8)
+    return bool(lib().orc_keyframe_needed(w, h, grid_width, grid_height, len(flags), _p(kps2d), _p(flags)))
+
+
 class OracleSlam:
     """CPU restatement of the reference's StereoSlam (new_image / pose / trajectory / keyframes)."""
 

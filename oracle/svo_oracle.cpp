@@ -1144,6 +1144,71 @@ int orc_slam_trace(void *h, const char *name, float *out, int max)
     if (out) memcpy(out, it->second.data(), sizeof(float) * n);
     return (int)it->second.size();
 }
+// ---- DepthCalculator / KeyFrameManager bookkeeping on its own (the functions OracleSlam uses), for the host-stage tests ----
+int orc_select_best(int n_levels, const int *n_per_level, const float *const *xy, const float *const *score, const int *const *type,
+                    float *kps2d, float *score_out, int *type_out, int *level_out)
+{
+    std::vector<std::vector<float>> kp(n_levels);
+    std::vector<std::vector<KpInfo>> inf(n_levels);
+    for (int l = 0; l < n_levels; l++) {
+        kp[l].assign(xy[l], xy[l] + 2 * (size_t)n_per_level[l]);
+        inf[l].resize(n_per_level[l]);
+        for (int j = 0; j < n_per_level[l]; j++) { inf[l][j].score = score[l][j]; inf[l][j].type = type[l][j]; inf[l][j].level = l; }
+    }
+    std::vector<float> k;
+    std::vector<KpInfo> in;
+    OracleSlam::select_best_keypoints(kp, inf, k, in);
+    for (size_t j = 0; j < in.size(); j++) {
+        kps2d[2 * j] = k[2 * j]; kps2d[2 * j + 1] = k[2 * j + 1];
+        score_out[j] = in[j].score; type_out[j] = in[j].type; level_out[j] = in[j].level;
+    }
+    return (int)in.size();
+}
+static void flat_frame(Frame &f, int n, const float *kps2d, const uint8_t *flags)
+{
+    f.kps.kps2d.assign(kps2d, kps2d + 2 * (size_t)n);
+    f.kps.kps3d.assign(3 * (size_t)n, 0.f);
+    f.kps.info.resize(n);
+    for (int i = 0; i < n; i++) {
+        f.kps.info[i].keypoint_index = (size_t)i;   // remembers the original position
+        if (flags) { f.kps.info[i].ignore_during_refinement = flags[i] & 1; f.kps.info[i].ignore_completely = flags[i] & 2; f.kps.info[i].ignore_temporary = flags[i] & 4; }
+    }
+}
+void orc_find_bad(int w, int h, int n, const float *kps2d, const uint8_t *flags, uint8_t *keep)
+{
+    Settings cs = {};
+    OracleSlam s(cs, w, h);
+    Frame f;
+    flat_frame(f, n, kps2d, flags);
+    s.find_bad_keypoints(f);
+    for (int i = 0; i < n; i++) keep[i] = 0;
+    for (auto &in : f.kps.info) keep[in.keypoint_index] = 1;
+}
+// merge as calculate_depth calls it (grid arguments swapped); appended = indices into the new list
+int orc_merge(int w, int h, int grid_width, int grid_height, int n_old, const float *old2d, int n_new, const float *new2d, int *appended)
+{
+    Settings cs = {};
+    OracleSlam s(cs, w, h);
+    Frame f;
+    flat_frame(f, n_old, old2d, nullptr);
+    std::vector<float> nk(new2d, new2d + 2 * (size_t)n_new);
+    std::vector<KpInfo> ni(n_new);
+    for (int i = 0; i < n_new; i++) ni[i].keypoint_index = (size_t)i;
+    s.merge_keypoints(f, nk, ni, grid_width, grid_height);
+    int c = 0;
+    for (size_t i = (size_t)n_old; i < f.kps.size(); i++) appended[c++] = (int)f.kps.info[i].keypoint_index;
+    return c;
+}
+int orc_keyframe_needed(int w, int h, int grid_width, int grid_height, int n, const float *kps2d, const uint8_t *flags)
+{
+    Settings cs = {};
+    cs.grid_width = grid_width; cs.grid_height = grid_height;
+    OracleSlam s(cs, w, h);
+    Frame f;
+    flat_frame(f, n, kps2d, flags);
+    return s.keyframe_needed(f) ? 1 : 0;
+}
+
 // flat dump of a keypoint set, same layout as oracle/ref_capi.cpp's dump_kps (colour is not modelled: rand())
 static int dump_kps(const KeyPoints &k, float *kps2d, float *kps3d, int32_t *info8, float *finfo3, int max)
 {

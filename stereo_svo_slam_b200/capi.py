@@ -169,7 +169,12 @@ class Context:
         return w.value, h.value
 
     def download(self, slot, kind, level):
+        """kind 0/1/2: u8 level; 3: Scharr level (h, w, 2) int16; 4: LK image level with its 32-px frame; 5: Scharr level with its frame."""
         w, h = self.level_size(kind, level)
+        if kind in (3, 5):
+            out = np.empty((h, w, 2), np.int16)
+            self._ck(lib().svo_download_level(self.h_ctx, slot, kind, level, _p(out), C.c_size_t(4 * w)))
+            return out
         out = np.empty((h, w), np.uint8)
         self._ck(lib().svo_download_level(self.h_ctx, slot, kind, level, _p(out), C.c_size_t(w)))
         return out
@@ -309,3 +314,75 @@ class Context:
 
 def device_count():
     return lib().svo_device_count()
+
+
+# ---- host stages (svo_host_*, svo_motion_filter_*): pure host code of the library, no device needed --------------------
+def _pp(arrs, ctype):
+    return (C.POINTER(ctype) * len(arrs))(*[a.ctypes.data_as(C.POINTER(ctype)) for a in arrs])
+
+
+def _host_ck(rc):
+    if rc:
+        raise SvoError(rc, "host stage: invalid argument")
+
+
+def host_select_best_keypoints(levels):
+    """select_best_keypoints (depth_calculator.cpp:37-65); levels = [(xy (n,2), score (n), type (n)), ...] finest first."""
+    xy = [_f32(l[0], (-1, 2)) for l in levels]
+    sc = [_f32(l[1]) for l in levels]
+    ty = [np.ascontiguousarray(l[2], dtype=np.int32) for l in levels]
+    cnt = np.array([len(x) for x in sc], np.int32)
+    n0 = int(cnt[0])
+    k2, so, to, lo = np.zeros((n0, 2), np.float32), np.zeros(n0, np.float32), np.zeros(n0, np.int32), np.zeros(n0, np.int32)
+    n = C.c_int()
+    _host_ck(lib().svo_host_select_best_keypoints(len(levels), _p(cnt), _pp(xy, C.c_float), _pp(sc, C.c_float), _pp(ty, C.c_int), n0,
+                                                  _p(k2), _p(so), _p(to), _p(lo), C.byref(n)))
+    assert n.value == n0
+    return k2, so, to, lo
+
+
+def host_find_bad_keypoints(width, height, kps2d, flags):
+    kps2d = _f32(kps2d, (-1, 2))
+    flags = np.ascontiguousarray(flags, dtype=np.uint8)
+    keep = np.zeros(len(flags), np.uint8)
+    _host_ck(lib().svo_host_find_bad_keypoints(width, height, len(flags), _p(kps2d), _p(flags), _p(keep)))
+    return keep
+
+
+def host_merge_keypoints(width, height, grid_width, grid_height, old_kps2d, new_kps2d):
+    old, new = _f32(old_kps2d, (-1, 2)), _f32(new_kps2d, (-1, 2))
+    n = C.c_int()
+    _host_ck(lib().svo_host_merge_keypoints(width, height, grid_width, grid_height, len(old), _p(old), len(new), _p(new), 0, None, C.byref(n)))
+    app = np.zeros(max(1, n.value), np.int32)
+    _host_ck(lib().svo_host_merge_keypoints(width, height, grid_width, grid_height, len(old), _p(old), len(new), _p(new), len(app), _p(app),
+                                            C.byref(n)))
+    return app[:n.value].copy()
+
+
+def host_keyframe_needed(width, height, grid_width, grid_height, kps2d, flags):
+    kps2d = _f32(kps2d, (-1, 2))
+    flags = np.ascontiguousarray(flags, dtype=np.uint8)
+    out = C.c_int()
+    _host_ck(lib().svo_host_keyframe_needed(width, height, grid_width, grid_height, len(flags), _p(kps2d), _p(flags), C.byref(out)))
+    return bool(out.value)
+
+
+class MotionFilter:
+    """The 12-state cv::KalmanFilter of StereoSlam and StereoSlam::update_pose (stereo_slam.cpp:29-41, :296-359)."""
+
+    def __init__(self):
+        self._h = C.c_void_p()
+        _host_ck(lib().svo_motion_filter_create(C.byref(self._h)))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().svo_motion_filter_destroy(self._h)
+            self._h = None
+
+    def update(self, pose, speed, pose_variance, speed_variance, dt):
+        """-> (filtered pose (6), kf.statePre (12))"""
+        p = Pose(*[float(v) for v in pose])
+        a = [_f32(x) for x in (speed, pose_variance, speed_variance)]
+        out, pre = Pose(), np.zeros(12, np.float32)
+        _host_ck(lib().svo_motion_filter_update(self._h, C.byref(p), _p(a[0]), _p(a[1]), _p(a[2]), C.c_double(dt), C.byref(out), _p(pre)))
+        return out.vec(), pre

@@ -7,14 +7,15 @@
 //   calculate_hessian        :312-416   box-sum gradients x 2x6 Jacobian, H = sum (gJ)^T(gJ), rebuilt every call (Q1)
 //   get_gradient             :418-539   residuals, b = -sum (gJ) r, delta = H^-1 b, exponential_map, rotate to world
 //
-// B200 design: one CTA owns the whole solve of one frame.  Per level the two level images are staged in
-// shared memory with TMA bulk copies (cp.async.bulk + mbarrier), every thread owns keypoints (strided), does
-// the photometric residuals and 1x6 Jacobian rows in registers with the reference's exact float operation
-// order, and the 21+6+1 normal-equation terms are reduced with warp shuffles and one block-level pass in a
-// fixed tree (deterministic).  The 6x6 solve, the exponential map and the accept/halve/stop decisions run in
-// the kernel: there is no host round trip anywhere inside a frame.  Pose-independent reference-patch terms
-// (box-sum gradients and reference box sums, 48 floats + validity mask per keypoint) are computed once per
-// level and cached in an L2-resident scratch array laid out [term][keypoint] for coalesced access.
+// B200 design: one thread-block CLUSTER (1, 2, 4, 8 or 16 CTAs = SMs) owns the whole solve of one frame.  Per level every
+// CTA stages the two level images in its shared memory with TMA bulk copies (cp.async.bulk + mbarrier); four lanes share a
+// keypoint (lane r owns row r of its 4x4 patch) and do the photometric residuals and 1x6 Jacobian rows in registers with the
+// reference's exact float operation order; the 21+6+1 normal-equation terms are reduced with warp shuffles, one pass per
+// CTA and one DSMEM exchange per evaluation (st.async + mbarrier complete_tx) in a fixed tree (deterministic).  The 6x6
+// solve (double LDL^T; the reference's float pseudo-inverse when H is not positive definite), the exponential map and the
+// accept/halve/stop decisions run in the kernel, redundantly in every CTA: there is no host round trip anywhere inside a
+// frame.  Pose-independent reference-patch terms (box-sum gradients and reference box sums, 48 floats + validity mask per
+// keypoint) are computed once per level and cached in an L2-resident scratch array laid out [term][keypoint].
 //
 // Bound: dependency latency (serial evaluations) and shared-memory/ALU throughput, not HBM.
 #include "kernels.cuh"
@@ -605,9 +606,12 @@ __global__ void __launch_bounds__(ALIGN_THREADS, 1) sparse_align_kernel(AlignArg
                 if (tid == 0) {   // every CTA solves the same 6x6 system redundantly: no further cluster traffic
                     double dx[6];
                     float delta[6], pg[6], Rf[9];
-                    bool ok = solve6(hdr->red_out, hdr->red_out + 21, dx);
+                    if (solve6(hdr->red_out, hdr->red_out + 21, dx)) {
 #pragma unroll
-                    for (int k = 0; k < 6; k++) delta[k] = ok ? (float)dx[k] : 0.f;
+                        for (int k = 0; k < 6; k++) delta[k] = (float)dx[k];
+                    } else {
+                        dev_pinv_step(hdr->red_out, hdr->red_out + 21, delta);   // rank-deficient H: the reference's pseudo-inverse step
+                    }
                     dev_expmap(delta, pg);
                     // rot_mat = float(Rodrigues(r)) == transpose of float(Rodrigues(-r)) bit for bit
 #pragma unroll

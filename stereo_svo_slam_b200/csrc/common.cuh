@@ -145,6 +145,126 @@ __device__ __forceinline__ void dev_expmap(const float tw[6], float out[6])
     out[3] = w0; out[4] = w1; out[5] = w2;
 }
 
+// cv::Matx66f::inv(DECOMP_SVD) (pose_estimator.cpp:405, pose_refinement.cpp:398) for a Hessian the double LDL^T of the solvers
+// rejects (not numerically positive definite: fewer than three usable keypoints, collinear points, ...).  The reference
+// then still takes the step its FLOAT pseudo-inverse gives: one-sided Jacobi SVD (OpenCV JacobiSVDImpl_<float>: rotations in
+// float, norms and dot products in double), 1/w for every singular value above 2*DBL_EPSILON*sum(w) (SVBkSbImpl_), and an
+// all-zero inverse when cv::invert reports singularity (smallest singular value exactly 0, or largest < FLT_EPSILON).
+// Same operation order as OpenCV so that an identical float H gives the identical inverse; one thread, rarely executed.
+static __device__ __noinline__ bool dev_invert_svd6(const float *A /*6x6 row-major*/, float *Ainv)
+{
+    const int n = 6;
+    float At[36], Vt[36];
+    double W[6];
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < n; j++) At[i * n + j] = A[j * n + i];
+    const float eps = 1.1920929e-07f * 2;
+    for (int i = 0; i < n; i++) {
+        double sd = 0;
+        for (int k = 0; k < n; k++) { const float t = At[i * n + k]; sd += (double)t * t; }
+        W[i] = sd;
+        for (int k = 0; k < n; k++) Vt[i * n + k] = 0.f;
+        Vt[i * n + i] = 1.f;
+    }
+    for (int iter = 0; iter < 30; iter++) {
+        bool changed = false;
+        for (int i = 0; i < n - 1; i++)
+            for (int j = i + 1; j < n; j++) {
+                float *Ai = At + i * n, *Aj = At + j * n;
+                double a = W[i], p = 0, b = W[j];
+                for (int k = 0; k < n; k++) p += (double)Ai[k] * Aj[k];
+                if (fabs(p) <= eps * sqrt(a * b)) continue;
+                p *= 2;
+                const double beta = a - b, gamma = hypot(p, beta);
+                float c, s;
+                if (beta < 0) {
+                    const double delta = (gamma - beta) * 0.5;
+                    s = (float)sqrt(delta / gamma);
+                    c = (float)(p / (gamma * s * 2));
+                } else {
+                    c = (float)sqrt((gamma + beta) / (gamma * 2));
+                    s = (float)(p / (gamma * c * 2));
+                }
+                a = b = 0;
+                for (int k = 0; k < n; k++) {
+                    const float t0 = c * Ai[k] + s * Aj[k];
+                    const float t1 = -s * Ai[k] + c * Aj[k];
+                    Ai[k] = t0; Aj[k] = t1;
+                    a += (double)t0 * t0; b += (double)t1 * t1;
+                }
+                W[i] = a; W[j] = b;
+                changed = true;
+                float *Vi = Vt + i * n, *Vj = Vt + j * n;
+                for (int k = 0; k < n; k++) {
+                    const float t0 = c * Vi[k] + s * Vj[k];
+                    const float t1 = -s * Vi[k] + c * Vj[k];
+                    Vi[k] = t0; Vj[k] = t1;
+                }
+            }
+        if (!changed) break;
+    }
+    for (int i = 0; i < n; i++) {
+        double sd = 0;
+        for (int k = 0; k < n; k++) { const float t = At[i * n + k]; sd += (double)t * t; }
+        W[i] = sqrt(sd);
+    }
+    for (int i = 0; i < n - 1; i++) {   // descending singular values
+        int j = i;
+        for (int k = i + 1; k < n; k++) if (W[j] < W[k]) j = k;
+        if (i != j) {
+            const double t = W[i]; W[i] = W[j]; W[j] = t;
+            for (int k = 0; k < n; k++) {
+                float u = At[i * n + k]; At[i * n + k] = At[j * n + k]; At[j * n + k] = u;
+                u = Vt[i * n + k]; Vt[i * n + k] = Vt[j * n + k]; Vt[j * n + k] = u;
+            }
+        }
+    }
+    float w[6];
+    for (int i = 0; i < n; i++) {
+        w[i] = (float)W[i];
+        const float sc = (float)(W[i] > 1.17549435e-38 ? 1 / W[i] : 0.);   // unit left vectors (zero singular value: left as zero)
+        for (int k = 0; k < n; k++) At[i * n + k] *= sc;
+    }
+    // back substitution with the identity as right-hand side: X = sum_i v_i (u_i^T / w_i)
+    double threshold = 0;
+    for (int i = 0; i < n; i++) threshold += w[i];
+    threshold *= (double)(float)(2.220446049250313e-16 * 2);
+    for (int i = 0; i < n * n; i++) Ainv[i] = 0.f;
+    for (int i = 0; i < n; i++) {
+        double wi = w[i];
+        if (fabs(wi) <= threshold) continue;
+        wi = 1 / wi;
+        double buf[6];
+        for (int j = 0; j < n; j++) buf[j] = At[i * n + j] * wi;
+        for (int r = 0; r < n; r++) {
+            const float sv = Vt[i * n + r];
+            for (int j = 0; j < n; j++) Ainv[r * n + j] = (float)(Ainv[r * n + j] + (double)sv * buf[j]);
+        }
+    }
+    const double ratio = w[0] >= 1.1920929e-07f ? (double)(w[n - 1] / w[0]) : 0;
+    if (ratio == 0) {
+        for (int i = 0; i < n * n; i++) Ainv[i] = 0.f;
+        return false;
+    }
+    return true;
+}
+
+// The Gauss-Newton step of a solver whose LDL^T failed: delta = inv(H) * b as the reference computes it (float pseudo-inverse,
+// Matx66f * Matx61f in float).  Hu: 21 upper-triangular sums, b: 6 sums (both double, rounded to float here).
+static __device__ __noinline__ void dev_pinv_step(const double *Hu, const double *b, float delta[6])
+{
+    float H[36], Hi[36];
+    int k = 0;
+    for (int i = 0; i < 6; i++)
+        for (int j = i; j < 6; j++) { H[i * 6 + j] = (float)Hu[k]; H[j * 6 + i] = (float)Hu[k]; k++; }
+    dev_invert_svd6(H, Hi);   // all zeros when singular
+    for (int i = 0; i < 6; i++) {
+        float s = 0.f;
+        for (int q = 0; q < 6; q++) s += Hi[i * 6 + q] * (float)b[q];
+        delta[i] = s;
+    }
+}
+
 __device__ __forceinline__ int dev_reflect101(int p, int len)
 {
     if (len == 1) return 0;

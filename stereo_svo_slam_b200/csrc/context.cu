@@ -227,10 +227,11 @@ extern "C" int svo_device_count(void)
 extern "C" const char *svo_last_error(svo_ctx *ctx) { return ctx ? ctx->err : g_create_err; }
 
 static int alloc_slot(svo_ctx *ctx, int *slot_out);
+extern "C" int svo_ctx_destroy(svo_ctx *ctx);
 static int fail_create(svo_ctx *ctx, int code, const char *msg)
 {
     snprintf(g_create_err, sizeof(g_create_err), "%s", msg);
-    delete ctx;
+    if (ctx) svo_ctx_destroy(ctx);   // null-safe per member: streams, events, pinned and device buffers, arena share
     return code;
 }
 
@@ -610,7 +611,7 @@ static int upload_common(svo_ctx *ctx, const uint8_t *left, size_t ls, const uin
         left = stage; right = stage + img; ls = rs = (size_t)ctx->W;
     }
     if (ctx->profiling) CK(cudaEventRecord(ctx->sev[0], ctx->stream));
-    if ((rc = enqueue_upload(ctx, s, left, ls, right, rs, src_kind))) return rc;
+    if ((rc = enqueue_upload(ctx, s, left, ls, right, rs, src_kind))) { s.refcount = 0; return rc; }
     ctx->launch_total += frame_pyr_launches(ctx, s);
     if (ctx->profiling) CK(cudaEventRecord(ctx->sev[1], ctx->stream));
     *slot_out = id;
@@ -619,16 +620,28 @@ static int upload_common(svo_ctx *ctx, const uint8_t *left, size_t ls, const uin
 
 extern "C" int svo_upload_stereo(svo_ctx *ctx, const uint8_t *left, size_t ls, const uint8_t *right, size_t rs, int *slot_out)
 {
+    if (ctx) ctx->err[0] = 0;   // a failure below reports its own message, never a stale one
     if (!ctx || !left || !right || !slot_out || ls < (size_t)ctx->W || rs < (size_t)ctx->W) return SVO_ERR_INVALID;
     int kind = classify_source(left, right, &ctx->zc_left, &ctx->zc_right);
-    if (kind == 2) kind = 0;  // a device pointer passed to the host entry point is a caller error; treat as host memory
+    if (kind == 2) {  // device memory must come through svo_upload_stereo_device: the host path would memcpy() from it
+        snprintf(ctx->err, sizeof(ctx->err), "svo_upload_stereo: device pointer passed to the host entry point");
+        return SVO_ERR_INVALID;
+    }
     return upload_common(ctx, left, ls, right, rs, kind, slot_out);
 }
 
 extern "C" int svo_upload_stereo_device(svo_ctx *ctx, const uint8_t *d_left, size_t ls, const uint8_t *d_right, size_t rs, int *slot_out)
 {
+    if (ctx) ctx->err[0] = 0;   // a failure below reports its own message, never a stale one
     if (!ctx || !d_left || !d_right || !slot_out || ls < (size_t)ctx->W || rs < (size_t)ctx->W) return SVO_ERR_INVALID;
     return upload_common(ctx, d_left, ls, d_right, rs, 2, slot_out);
+}
+
+extern "C" int svo_keypoint_capacity(svo_ctx *ctx, int *max_keypoints)
+{
+    if (!ctx || !max_keypoints) return SVO_ERR_INVALID;
+    *max_keypoints = ctx->max_kps;
+    return SVO_OK;
 }
 
 extern "C" int svo_launch_count(svo_ctx *ctx, long long *launches)
@@ -789,16 +802,33 @@ extern "C" int svo_slot_level_size(svo_ctx *ctx, int kind, int level, int *width
     if (!ctx || !width || !height) return SVO_ERR_INVALID;
     if (kind == 0 && level >= 0 && level < ctx->n_levels) { *width = ctx->lw[level]; *height = ctx->lh[level]; return SVO_OK; }
     if (kind == 1 && level == 0) { *width = ctx->W; *height = ctx->H; return SVO_OK; }
-    if (kind == 2 && level >= 0 && level < SVO_LK_LEVELS) { *width = ctx->lkw[level]; *height = ctx->lkh[level]; return SVO_OK; }
+    if ((kind == 2 || kind == 3) && level >= 0 && level < SVO_LK_LEVELS) { *width = ctx->lkw[level]; *height = ctx->lkh[level]; return SVO_OK; }
+    if ((kind == 4 || kind == 5) && level >= 0 && level < SVO_LK_LEVELS) { *width = ctx->lkw[level] + 2 * SVO_LK_PAD; *height = ctx->lkh[level] + 2 * SVO_LK_PAD; return SVO_OK; }
     return SVO_ERR_INVALID;
 }
 
 extern "C" int svo_download_level(svo_ctx *ctx, int slot, int kind, int level, uint8_t *out, size_t out_stride)
 {
     if (!ctx || !out || !slot_ok(ctx, slot)) return SVO_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    if (kind >= 3 && kind <= 5) {
+        // 3: Scharr level (Ix, Iy int16 pairs, 4 bytes per pixel); 4 / 5: LK image level / Scharr level WITH the SVO_LK_PAD frame
+        // cv::buildOpticalFlowPyramid keeps around them (BORDER_REFLECT_101 pixels / BORDER_CONSTANT zeros), stereo_slam.cpp:139
+        if (level < 0 || level >= SVO_LK_LEVELS) return SVO_ERR_INVALID;
+        if (kind != 4) { int rc = ensure_derivs(ctx, slot); if (rc) return rc; }
+        const ImageSetDev &s = ctx->slots[slot].dev;
+        const LevelDesc d = kind == 4 ? s.lk[level] : s.lkd[level];
+        const size_t esz = kind == 4 ? 1 : 4;
+        const int pad = kind == 3 ? 0 : SVO_LK_PAD;
+        const size_t row = (size_t)(d.w + 2 * pad) * esz;
+        if (out_stride < row) return SVO_ERR_INVALID;
+        const uint8_t *src = d.ptr - (size_t)pad * d.pitch - (size_t)pad * esz;
+        CK(cudaMemcpy2DAsync(out, out_stride, src, d.pitch, row, d.h + 2 * pad, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        return SVO_OK;
+    }
     LevelDesc d;
     if (!level_desc(ctx, slot, kind, level, d) || out_stride < (size_t)d.w) return SVO_ERR_INVALID;
-    CK(cudaSetDevice(ctx->device));
     CK(cudaMemcpy2DAsync(out, out_stride, d.ptr, d.pitch, d.w, d.h, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return SVO_OK;
@@ -837,6 +867,7 @@ static int check_n(svo_ctx *ctx, int n)
 extern "C" int svo_detect_keypoints(svo_ctx *ctx, int slot, int level, int grid_w, int grid_h, int max_out, float *xy, float *score,
                                     int *type, int *n_out)
 {
+    if (ctx) ctx->err[0] = 0;   // a failure below reports its own message, never a stale one
     if (!ctx || !slot_ok(ctx, slot) || level < 0 || level >= ctx->n_levels || grid_w < 1 || grid_h < 1 || !n_out) return SVO_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
     DetectArgs a;
@@ -888,6 +919,7 @@ extern "C" int svo_fast_corners(svo_ctx *ctx, int slot, int level, int max_out, 
 
 extern "C" int svo_stereo_match(svo_ctx *ctx, int slot, const float *kps2d, int n, int mode, float *disparity)
 {
+    if (ctx) ctx->err[0] = 0;   // a failure below reports its own message, never a stale one
     if (!ctx || !slot_ok(ctx, slot) || !kps2d || !disparity || (mode != 0 && mode != 1)) return SVO_ERR_INVALID;
     int rc = check_n(ctx, n);
     if (rc) return rc;
@@ -1137,6 +1169,7 @@ static void host_rodrigues_f(const float r[3], float R[9])
 
 extern "C" int svo_keyframe_commit(svo_ctx *ctx, int slot, const float pose[6], int *keyframe_id_out)
 {
+    if (ctx) ctx->err[0] = 0;   // a failure below reports its own message, never a stale one
     if (!ctx || !slot_ok(ctx, slot) || !pose || !keyframe_id_out) return SVO_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
     if (ctx->kf_count == ctx->kf_cap) {
@@ -1188,6 +1221,7 @@ extern "C" int svo_keyframe_commit(svo_ctx *ctx, int slot, const float pose[6], 
 
 extern "C" int svo_keyframe_slot(svo_ctx *ctx, int keyframe_id, int *slot_out)
 {
+    if (ctx) ctx->err[0] = 0;   // a failure below reports its own message, never a stale one
     if (!ctx || !slot_out || keyframe_id < 0 || keyframe_id >= ctx->kf_count) return SVO_ERR_INVALID;
     *slot_out = ctx->kf_slot[keyframe_id];
     return SVO_OK;
@@ -1199,6 +1233,7 @@ extern "C" int svo_keyframe_slot(svo_ctx *ctx, int keyframe_id, int *slot_out)
 // never change after the keyframe is created, so the templates are built once here and the tracking kernel fetches them.
 extern "C" int svo_keyframe_set_templates(svo_ctx *ctx, int keyframe_id, const float *kps2d, int first, int count)
 {
+    if (ctx) ctx->err[0] = 0;   // a failure below reports its own message, never a stale one
     if (!ctx || keyframe_id < 0 || keyframe_id >= ctx->kf_count || first < 0 || count < 0 || (count > 0 && !kps2d)) return SVO_ERR_INVALID;
     if (!ctx->use_templates || count == 0) return SVO_OK;
     if (count > ctx->cell_cap) { snprintf(ctx->err, sizeof(ctx->err), "%d templates exceed the cell capacity %d", count, ctx->cell_cap); return SVO_ERR_CAPACITY; }
@@ -1360,6 +1395,7 @@ static int enqueue_track(svo_ctx *ctx, int prev_slot, int cur_slot, int n, int g
 
 extern "C" int svo_track_frame_begin(svo_ctx *ctx, int prev_slot, int cur_slot, svo_track_io *io)
 {
+    if (ctx) ctx->err[0] = 0;   // a failure below reports its own message, never a stale one
     if (!ctx || !io || !slot_ok(ctx, prev_slot) || !slot_ok(ctx, cur_slot)) return SVO_ERR_INVALID;
     int rc = validate_and_pack(ctx, io);
     if (rc) return rc;
@@ -1404,13 +1440,26 @@ static int capture_frame_graph(svo_ctx *ctx, svo_ctx::FrameGraph &g, int n, cuda
 extern "C" int svo_frame_begin(svo_ctx *ctx, const uint8_t *left, size_t ls, const uint8_t *right, size_t rs, int on_device, int prev_slot,
                                svo_track_io *io, int *cur_slot_out)
 {
-    if (!ctx || !left || !right || !io || !cur_slot_out || ls < (size_t)ctx->W || rs < (size_t)ctx->W || !slot_ok(ctx, prev_slot)) return SVO_ERR_INVALID;
+    if (ctx) ctx->err[0] = 0;   // a failure below reports its own message, never a stale one
+    if (!ctx) return SVO_ERR_INVALID;
+    if (!left || !right || !io || !cur_slot_out || ls < (size_t)ctx->W || rs < (size_t)ctx->W || !slot_ok(ctx, prev_slot)) {
+        snprintf(ctx->err, sizeof(ctx->err), "svo_frame_begin: null argument, row stride below the image width, or previous slot %d not live", prev_slot);
+        return SVO_ERR_INVALID;
+    }
     const double tt0 = g_trace ? now_ms() : 0;
     int rc = validate_and_pack(ctx, io);
     if (rc) return rc;
     CK(cudaSetDevice(ctx->device));
     int src_kind = on_device ? 2 : classify_source(left, right, &ctx->zc_left, &ctx->zc_right);
-    if (!on_device && src_kind == 2) src_kind = 0;
+    if (!on_device && src_kind == 2) {
+        snprintf(ctx->err, sizeof(ctx->err), "svo_frame_begin: device pointer passed with on_device == 0");
+        return SVO_ERR_INVALID;
+    }
+    // a frame that fails after its image set was taken gives the set back
+    struct SlotGuard {
+        svo_ctx *c; int id; bool keep;
+        ~SlotGuard() { if (!keep && id >= 0) c->slots[id].refcount = 0; }
+    } guard{ctx, -1, false};
     const int n = io->n;
     const bool contiguous = ls == (size_t)ctx->W && rs == (size_t)ctx->W;
     const bool graph_ok = ctx->use_graphs && !ctx->profiling && n > 0;
@@ -1420,6 +1469,7 @@ extern "C" int svo_frame_begin(svo_ctx *ctx, const uint8_t *left, size_t ls, con
     if (!graph_ok) {
         CK(cudaEventRecord(ctx->ev0, ctx->stream));
         if ((rc = upload_common(ctx, left, ls, right, rs, src_kind, &cur))) return rc;
+        guard.id = cur;
         *cur_slot_out = cur;
         const bool prof = ctx->profiling;
         int launches = 0;
@@ -1429,9 +1479,11 @@ extern "C" int svo_frame_begin(svo_ctx *ctx, const uint8_t *left, size_t ls, con
         ctx->last_launches = launches;
         ctx->launch_total += launches;
         ctx->track_pending = true;
+        guard.keep = true;
         return SVO_OK;
     }
     if ((rc = alloc_slot(ctx, &cur))) return rc;
+    guard.id = cur;
     *cur_slot_out = cur;
     int stage_idx = 0;
     if (src_kind == 0) {
@@ -1504,6 +1556,7 @@ extern "C" int svo_frame_begin(svo_ctx *ctx, const uint8_t *left, size_t ls, con
     ctx->last_launches = g->launches;
     ctx->launch_total += g->launches;
     ctx->track_pending = true;
+    guard.keep = true;
     return SVO_OK;
 }
 
@@ -1524,6 +1577,7 @@ extern "C" int svo_graph_stats(svo_ctx *ctx, long long *graph_launches, long lon
 
 extern "C" int svo_track_frame_end(svo_ctx *ctx, svo_track_io *io)
 {
+    if (ctx) ctx->err[0] = 0;   // a failure below reports its own message, never a stale one
     if (!ctx || !io) return SVO_ERR_INVALID;
     if (!ctx->track_pending) { snprintf(ctx->err, sizeof(ctx->err), "svo_track_frame_end without _begin"); return SVO_ERR_STATE; }
     ctx->track_pending = false;

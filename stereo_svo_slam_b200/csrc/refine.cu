@@ -199,9 +199,12 @@ __global__ void __launch_bounds__(REF_THREADS, 1) reproj_refine_kernel(RefineArg
             if (tid == 0) {
                 double dx[6];
                 float tw[6], g[6];
-                bool ok = refine_solve6(hdr.red_out, hdr.red_out + 21, dx);
+                if (refine_solve6(hdr.red_out, hdr.red_out + 21, dx)) {
 #pragma unroll
-                for (int k = 0; k < 6; k++) tw[k] = ok ? (float)dx[k] : 0.f;
+                    for (int k = 0; k < 6; k++) tw[k] = (float)dx[k];
+                } else {
+                    dev_pinv_step(hdr.red_out, hdr.red_out + 21, tw);   // rank-deficient H: the reference's pseudo-inverse step
+                }
                 dev_expmap(tw, g);  // used as is — not rotated to world (pose_refinement.cpp:401-411)
 #pragma unroll
                 for (int k = 0; k < 6; k++) hdr.grad[k] = g[k];

@@ -133,6 +133,77 @@ struct FrameH {
     double time_stamp = 0;
 };
 
+// ---- DepthCalculator / KeyFrameManager host logic on flat arrays (also exported one by one as svo_host_*) ---------
+// depth_calculator.cpp:67-86: a keypoint is dropped when it left the image (note `> width`, `> height`) or carries
+// ignore_completely / ignore_during_refinement
+inline bool host_is_bad(float x, float y, int W, int H, bool ignore_completely, bool ignore_during_refinement)
+{
+    return (x < 0) || (y < 0) || (x > W) || (y > H) || ignore_completely || ignore_during_refinement;
+}
+
+// depth_calculator.cpp:37-65, one coarser level folded into the running choice: entry j of EVERY level is compared with
+// entry j of level 0 (the lists are indexed by position, not by cell — SURVEY Q7); a FAST corner beats an edgelet,
+// within a type the coarser level wins unless the finer score is strictly higher
+void host_select_level(int lv, int n, const float *xy, const float *sc, const int *ty, std::vector<float> &kps,
+                       std::vector<svo_keypoint_info> &info)
+{
+    if (lv == 0) {
+        kps.assign(xy, xy + 2 * (size_t)n);
+        info.resize(n);
+        for (int j = 0; j < n; j++) {
+            std::memset(&info[j], 0, sizeof(svo_keypoint_info));
+            info[j].score = sc[j]; info[j].type = ty[j]; info[j].level = 0;
+        }
+        return;
+    }
+    for (size_t j = 0; j < info.size(); j++) {
+        if ((int)j >= n) continue;  // the reference reads past the coarser level's list here (Q7)
+        if (info[j].type == SVO_KP_FAST && ty[j] == SVO_KP_EDGELET) continue;
+        if ((info[j].type == ty[j]) && (info[j].score > sc[j])) continue;
+        kps[2 * j] = xy[2 * j] * (float)(1 << lv);
+        kps[2 * j + 1] = xy[2 * j + 1] * (float)(1 << lv);
+        info[j].score = sc[j]; info[j].type = ty[j]; info[j].level = lv;
+    }
+}
+
+// depth_calculator.cpp:88-130.  The caller passes (grid_width, grid_height) into the parameters named (grid_height,
+// grid_width) (:179-180), so the cells walked here are grid_height wide and grid_width tall; cell membership
+// is by strict inequalities on all four sides.  Returns, in order, the indices of the new keypoints that are appended.
+void host_merge(int W, int H, int cell_w, int cell_h, const float *old2d, size_t n_old, const float *new2d, size_t n_new,
+                std::vector<int> &appended)
+{
+    appended.clear();
+    for (int x = 0; x < W; x += cell_w) {
+        const int left = x, right = left + cell_w;
+        for (int y = 0; y < H; y += cell_h) {
+            const int top = y, bottom = y + cell_h;
+            bool match = false;
+            // kps2d grows while the loops run: keypoints appended for earlier cells are looked at as well
+            for (size_t i = 0; i < n_old + appended.size(); i++) {
+                const float *p = i < n_old ? old2d + 2 * i : new2d + 2 * (size_t)appended[i - n_old];
+                if (p[0] > left && p[0] < right && p[1] > top && p[1] < bottom) { match = true; break; }
+            }
+            if (match) continue;
+            for (size_t i = 0; i < n_new; i++) {
+                const float kx = new2d[2 * i], ky = new2d[2 * i + 1];
+                if (kx > left && kx < right && ky > top && ky < bottom) appended.push_back((int)i);
+            }
+        }
+    }
+}
+
+// keyframe_manager.cpp:47-74
+bool host_keyframe_needed(int W, int H, int grid_width, int grid_height, const float *k2, const uint8_t *ignore_completely, size_t stride, size_t n)
+{
+    int inside = 0;
+    for (size_t i = 0; i < n; i++) {
+        const float x = k2[2 * i], y = k2[2 * i + 1];
+        if ((x > 0) && (y > 0) && (x < W) && (y < H) && !ignore_completely[i * stride]) inside++;
+    }
+    const int max_kps = (W / grid_width) * (H / grid_height);
+    return inside < 0.66 * max_kps;
+}
+
 }  // namespace
 
 struct svo_slam {
@@ -156,12 +227,15 @@ struct svo_slam {
     bool pending = false;
     bool pending_first = false;
     int last_keyframe_created = 0;
+    long long dropped_for_capacity = 0;  // new keypoints a keyframe could not take (device keypoint block full)
     float last_gpu_ms = 0;
     int last_launches = 0;
 
     int fail(int rc)
     {
-        snprintf(err, sizeof(err), "%s", svo_last_error(ctx));
+        const char *m = svo_last_error(ctx);
+        static const char *const generic[] = {"ok", "invalid argument", "CUDA error", "no CUDA device", "capacity exceeded", "call order violated"};
+        snprintf(err, sizeof(err), "%s", (m && m[0]) ? m : generic[rc >= 0 && rc <= 5 ? rc : 1]);
         return rc;
     }
 
@@ -173,7 +247,7 @@ struct svo_slam {
         for (size_t i = 0; i < f.kps.size(); i++) {
             float x = f.kps.kps2d[2 * i], y = f.kps.kps2d[2 * i + 1];
             const svo_keypoint_info &in = f.kps.info[i];
-            if ((x < 0) || (y < 0) || (x > W) || (y > H) || in.ignore_completely || in.ignore_during_refinement) continue;
+            if (host_is_bad(x, y, W, H, in.ignore_completely, in.ignore_during_refinement)) continue;
             o.kps2d.push_back(x); o.kps2d.push_back(y);
             for (int k = 0; k < 3; k++) o.kps3d.push_back(f.kps.kps3d[3 * i + k]);
             o.info.push_back(in);
@@ -181,7 +255,7 @@ struct svo_slam {
         f.kps = std::move(o);
     }
 
-    // depth_calculator.cpp:11-65: per-level detection on the device, cross-level choice by cell index on the host
+    // depth_calculator.cpp:11-65: per-level detection on the device, cross-level choice by list index on the host
     int detect_and_select(int slot, std::vector<float> &kps, std::vector<svo_keypoint_info> &info)
     {
         int gw = cs.grid_width, gh = cs.grid_height;
@@ -197,23 +271,7 @@ struct svo_slam {
             int n = 0;
             int rc = svo_detect_keypoints(ctx, slot, lv, gw, gh, cap, xy.data(), sc.data(), ty.data(), &n);
             if (rc) return rc;
-            if (lv == 0) {
-                kps.assign(xy.begin(), xy.begin() + 2 * n);
-                info.resize(n);
-                for (int j = 0; j < n; j++) {
-                    std::memset(&info[j], 0, sizeof(svo_keypoint_info));
-                    info[j].score = sc[j]; info[j].type = ty[j]; info[j].level = 0;
-                }
-            } else {
-                for (size_t j = 0; j < info.size(); j++) {
-                    if ((int)j >= n) continue;  // reference reads past the coarser level's list here (Q7)
-                    if (info[j].type == SVO_KP_FAST && ty[j] == SVO_KP_EDGELET) continue;
-                    if ((info[j].type == ty[j]) && (info[j].score > sc[j])) continue;
-                    kps[2 * j] = xy[2 * j] * (float)(1 << lv);
-                    kps[2 * j + 1] = xy[2 * j + 1] * (float)(1 << lv);
-                    info[j].score = sc[j]; info[j].type = ty[j]; info[j].level = lv;
-                }
-            }
+            host_select_level(lv, n, xy.data(), sc.data(), ty.data(), kps, info);
             gw /= 2; gh /= 2;
         }
         return SVO_OK;
@@ -222,26 +280,11 @@ struct svo_slam {
     // depth_calculator.cpp:88-130 — called with (grid_width, grid_height) bound to (grid_height, grid_width): Q6
     void merge_keypoints(FrameH &f, const std::vector<float> &nk, const std::vector<svo_keypoint_info> &ni, int grid_height, int grid_width)
     {
-        auto &k2 = f.kps.kps2d;
-        auto &info = f.kps.info;
-        for (int x = 0; x < W; x += grid_width) {
-            int left = x, right = left + grid_width;
-            for (int y = 0; y < H; y += grid_height) {
-                int top = y, bottom = y + grid_height;
-                bool match = false;
-                for (size_t i = 0; i < info.size(); i++) {
-                    float kx = k2[2 * i], ky = k2[2 * i + 1];
-                    if (kx > left && kx < right && ky > top && ky < bottom) { match = true; break; }
-                }
-                if (match) continue;
-                for (size_t i = 0; i < ni.size(); i++) {
-                    float kx = nk[2 * i], ky = nk[2 * i + 1];
-                    if (kx > left && kx < right && ky > top && ky < bottom) {
-                        k2.push_back(kx); k2.push_back(ky);
-                        info.push_back(ni[i]);
-                    }
-                }
-            }
+        std::vector<int> app;
+        host_merge(W, H, grid_width, grid_height, f.kps.kps2d.data(), f.kps.size(), nk.data(), ni.size(), app);
+        for (int i : app) {
+            f.kps.kps2d.push_back(nk[2 * i]); f.kps.kps2d.push_back(nk[2 * i + 1]);
+            f.kps.info.push_back(ni[i]);
         }
     }
 
@@ -258,6 +301,29 @@ struct svo_slam {
         const double t1 = g_trace_kf ? now_ms() : 0;
         const size_t old_count = f.kps.size();
         merge_keypoints(f, nk, ni, cs.grid_width, cs.grid_height);
+        // The reference's lists are unbounded; the device keypoint block is sized at context creation (4 keypoints per grid
+        // cell by default).  A keyframe that would exceed it keeps its best-scored NEW keypoints only — tracking goes on
+        // instead of every later frame failing with SVO_ERR_CAPACITY (never reached in any tested sequence; counted).
+        int cap = 0;
+        svo_keypoint_capacity(ctx, &cap);
+        if (cap > 0 && f.kps.size() > (size_t)cap) {
+            const size_t keep_new = (size_t)cap > old_count ? (size_t)cap - old_count : 0;
+            std::vector<size_t> order(f.kps.size() - old_count);
+            for (size_t i = 0; i < order.size(); i++) order[i] = old_count + i;
+            std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return f.kps.info[a].score > f.kps.info[b].score; });
+            order.resize(keep_new);
+            std::sort(order.begin(), order.end());
+            KeyPoints kept;
+            kept.kps2d.assign(f.kps.kps2d.begin(), f.kps.kps2d.begin() + 2 * old_count);
+            kept.info.assign(f.kps.info.begin(), f.kps.info.begin() + old_count);
+            for (size_t i : order) {
+                kept.kps2d.push_back(f.kps.kps2d[2 * i]); kept.kps2d.push_back(f.kps.kps2d[2 * i + 1]);
+                kept.info.push_back(f.kps.info[i]);
+            }
+            kept.kps3d = f.kps.kps3d;
+            dropped_for_capacity += (long long)(f.kps.size() - kept.size());
+            f.kps = std::move(kept);
+        }
         const double t2 = g_trace_kf ? now_ms() : 0;
         const size_t n = f.kps.size();
         f.kps.kps3d.resize(n * 3);
@@ -298,7 +364,7 @@ struct svo_slam {
         k->kps = f.kps;
         k->time_stamp = f.time_stamp;
         int id = -1;
-        rc = svo_keyframe_commit(ctx, f.slot, f.pose, &id);  // retains the slot
+        rc = svo_keyframe_commit(ctx, f.slot, f.pose, &id);  // the device copies the image set into a slot of the keyframe
         if (rc) return rc;
         if ((uint64_t)id != kf_id) { snprintf(err, sizeof(err), "keyframe id mismatch"); return SVO_ERR_STATE; }
         rc = svo_keyframe_slot(ctx, id, &k->slot);  // the device keeps its own copy of the keyframe's images
@@ -316,13 +382,8 @@ struct svo_slam {
     // keyframe_manager.cpp:47-74
     bool keyframe_needed(const FrameH &f) const
     {
-        int inside = 0;
-        for (size_t i = 0; i < f.kps.size(); i++) {
-            float x = f.kps.kps2d[2 * i], y = f.kps.kps2d[2 * i + 1];
-            if ((x > 0) && (y > 0) && (x < W) && (y < H) && !f.kps.info[i].ignore_completely) inside++;
-        }
-        int max_kps = (W / cs.grid_width) * (H / cs.grid_height);
-        return inside < 0.66 * max_kps;
+        const uint8_t *ic = f.kps.info.empty() ? nullptr : &f.kps.info[0].ignore_completely;
+        return host_keyframe_needed(W, H, cs.grid_width, cs.grid_height, f.kps.kps2d.data(), ic, sizeof(svo_keypoint_info), f.kps.size());
     }
 
     // StereoSlam::update_pose (stereo_slam.cpp:296-359)
@@ -353,44 +414,46 @@ struct svo_slam {
         trajectory.push_back(p);
     }
 
+    // Nothing of the instance's state changes unless the frame was enqueued: a failed call (bad stride, capacity, CUDA
+    // error) leaves `frame` the current frame and the sequence can go on with the next image.
     int new_image_begin(const uint8_t *left, size_t ls, const uint8_t *right, size_t rs, float ts, bool on_device = false)
     {
         if (pending) { snprintf(err, sizeof(err), "new_image_begin called twice"); return SVO_ERR_STATE; }
+        if (ls < (size_t)W || rs < (size_t)W) { snprintf(err, sizeof(err), "row stride smaller than the image width %d", W); return SVO_ERR_INVALID; }
         last_keyframe_created = 0;
-        previous = std::move(frame);
-        frame.reset(new FrameH());
-        frame->time_stamp = ts;
+        std::unique_ptr<FrameH> nf(new FrameH());
+        nf->time_stamp = ts;
         int rc = SVO_OK;
-        pending = true;
-        if (!previous) {  // first frame (stereo_slam.cpp:142-160): pyramids only, keyframe creation in _end
-            rc = on_device ? svo_upload_stereo_device(ctx, left, ls, right, rs, &frame->slot)
-                           : svo_upload_stereo(ctx, left, ls, right, rs, &frame->slot);  // pyramids (stereo_slam.cpp:135-139)
-            if (rc) { pending = false; return fail(rc); }
-            frame->id = 0;
+        if (!frame) {  // first frame (stereo_slam.cpp:142-160): pyramids only, keyframe creation in _end
+            rc = on_device ? svo_upload_stereo_device(ctx, left, ls, right, rs, &nf->slot)
+                           : svo_upload_stereo(ctx, left, ls, right, rs, &nf->slot);  // pyramids (stereo_slam.cpp:135-139)
+            if (rc) return fail(rc);
+            nf->id = 0;
+            frame = std::move(nf);
+            pending = true;
             pending_first = true;
             return SVO_OK;
         }
-        pending_first = false;
-        frame->id = previous->id + 1;
-        for (int i = 0; i < 6; i++) frame->pose[i] = kf.xpre[i];  // kf.statePre (Q8)
-        // remove_outliers (stereo_slam.cpp:43-56)
+        nf->id = frame->id + 1;
+        for (int i = 0; i < 6; i++) nf->pose[i] = kf.xpre[i];  // kf.statePre (Q8)
+        // remove_outliers (stereo_slam.cpp:43-56) on what is about to become the previous frame (idempotent)
         {
             KeyPoints u;
-            for (size_t i = 0; i < previous->kps.size(); i++) {
-                if (previous->kps.info[i].ignore_completely) continue;
-                u.kps2d.push_back(previous->kps.kps2d[2 * i]); u.kps2d.push_back(previous->kps.kps2d[2 * i + 1]);
-                for (int k = 0; k < 3; k++) u.kps3d.push_back(previous->kps.kps3d[3 * i + k]);
-                u.info.push_back(previous->kps.info[i]);
+            for (size_t i = 0; i < frame->kps.size(); i++) {
+                if (frame->kps.info[i].ignore_completely) continue;
+                u.kps2d.push_back(frame->kps.kps2d[2 * i]); u.kps2d.push_back(frame->kps.kps2d[2 * i + 1]);
+                for (int k = 0; k < 3; k++) u.kps3d.push_back(frame->kps.kps3d[3 * i + k]);
+                u.info.push_back(frame->kps.info[i]);
             }
-            previous->kps = std::move(u);
+            frame->kps = std::move(u);
         }
-        const size_t n = previous->kps.size();
-        io_prev2d = previous->kps.kps2d;
-        io_kps3d = previous->kps.kps3d;
+        const size_t n = frame->kps.size();
+        io_prev2d = frame->kps.kps2d;
+        io_kps3d = frame->kps.kps3d;
         io_ref2d.resize(n * 2); io_kfid.resize(n); io_kpidx.resize(n); io_flags.resize(n); io_inl.resize(n); io_outl.resize(n); io_kfstate.resize(n * 2);
         io_kps2d.resize(n * 2); io_kltit.assign(n, 0); io_kltst.assign(n, 0);
         for (size_t i = 0; i < n; i++) {
-            const svo_keypoint_info &in = previous->kps.info[i];
+            const svo_keypoint_info &in = frame->kps.info[i];
             const FrameH &k = *keyframes[in.keyframe_id];
             io_ref2d[2 * i] = k.kps.kps2d[2 * in.keypoint_index];
             io_ref2d[2 * i + 1] = k.kps.kps2d[2 * in.keypoint_index + 1];
@@ -407,10 +470,14 @@ struct svo_slam {
         io.kps2d = io_kps2d.data();
         io.klt_iters = io_kltit.data(); io.klt_status = io_kltst.data();
         io.keypoint_index = io_kpidx.data();
-        std::memcpy(io.pose_prior, frame->pose, sizeof(io.pose_prior));
+        std::memcpy(io.pose_prior, nf->pose, sizeof(io.pose_prior));
         // pyramids (stereo_slam.cpp:135-139) + the whole tracking sequence, one CUDA graph launch in steady state
-        rc = svo_frame_begin(ctx, left, ls, right, rs, on_device ? 1 : 0, previous->slot, &io, &frame->slot);
-        if (rc) { pending = false; return fail(rc); }
+        rc = svo_frame_begin(ctx, left, ls, right, rs, on_device ? 1 : 0, frame->slot, &io, &nf->slot);
+        if (rc) return fail(rc);
+        previous = std::move(frame);
+        frame = std::move(nf);
+        pending = true;
+        pending_first = false;
         return SVO_OK;
     }
 
@@ -421,7 +488,12 @@ struct svo_slam {
         int rc;
         if (pending_first) {
             rc = create_keyframe(*frame);
-            if (rc) return rc == SVO_ERR_STATE ? rc : fail(rc);
+            if (rc) {  // no first keyframe: the next image starts the sequence again
+                if (rc != SVO_ERR_STATE) fail(rc);
+                svo_slot_release(ctx, frame->slot);
+                frame.reset();
+                return rc;
+            }
             for (auto &in : frame->kps.info) in.ignore_temporary = 0;  // stereo_slam.cpp:157-159
             last_gpu_ms = 0; last_launches = 0;
             finish_frame();
@@ -479,12 +551,12 @@ extern "C" {
 
 static char g_slam_create_err[256] = "";
 
-int svo_slam_create(const svo_camera_settings *settings, int device, int width, int height, svo_slam **out)
+int svo_slam_create_with_capacity(const svo_camera_settings *settings, int device, int width, int height, int max_keypoints, svo_slam **out)
 {
     if (!settings || !out) return SVO_ERR_INVALID;
     svo_slam *s = new svo_slam();
     s->cs = *settings; s->W = width; s->H = height;
-    int rc = svo_ctx_create(settings, device, width, height, 0, &s->ctx);
+    int rc = svo_ctx_create(settings, device, width, height, max_keypoints, &s->ctx);
     if (rc) {
         snprintf(g_slam_create_err, sizeof(g_slam_create_err), "%s", svo_last_error(nullptr));
         delete s;
@@ -492,6 +564,11 @@ int svo_slam_create(const svo_camera_settings *settings, int device, int width, 
     }
     *out = s;
     return SVO_OK;
+}
+
+int svo_slam_create(const svo_camera_settings *settings, int device, int width, int height, svo_slam **out)
+{
+    return svo_slam_create_with_capacity(settings, device, width, height, 0, out);
 }
 
 int svo_slam_destroy(svo_slam *s)
@@ -609,10 +686,92 @@ int svo_slam_update_pose(svo_slam *s, const svo_pose *pose, const float speed[6]
     if (filtered) { filtered->x = o[0]; filtered->y = o[1]; filtered->z = o[2]; filtered->rx = o[3]; filtered->ry = o[4]; filtered->rz = o[5]; }
     return SVO_OK;
 }
+// ---- host stages on their own (no device, no context): the bookkeeping of DepthCalculator / KeyFrameManager / StereoSlam
+// that stays on the CPU, exported so that it can be checked against the reference without a GPU ---------------------------
+int svo_host_select_best_keypoints(int n_levels, const int *n_per_level, const float *const *xy, const float *const *score,
+                                   const int *const *type, int max_out, float *kps2d, float *score_out, int *type_out, int *level_out,
+                                   int *n_out)
+{
+    if (n_levels < 1 || !n_per_level || !xy || !score || !type || !n_out) return SVO_ERR_INVALID;
+    std::vector<float> kps;
+    std::vector<svo_keypoint_info> info;
+    for (int lv = 0; lv < n_levels; lv++) {
+        if (n_per_level[lv] < 0 || (n_per_level[lv] > 0 && (!xy[lv] || !score[lv] || !type[lv]))) return SVO_ERR_INVALID;
+        host_select_level(lv, n_per_level[lv], xy[lv], score[lv], type[lv], kps, info);
+    }
+    *n_out = (int)info.size();
+    const size_t n = std::min<size_t>(info.size(), (size_t)std::max(0, max_out));
+    for (size_t j = 0; j < n; j++) {
+        if (kps2d) { kps2d[2 * j] = kps[2 * j]; kps2d[2 * j + 1] = kps[2 * j + 1]; }
+        if (score_out) score_out[j] = info[j].score;
+        if (type_out) type_out[j] = info[j].type;
+        if (level_out) level_out[j] = info[j].level;
+    }
+    return SVO_OK;
+}
+int svo_host_find_bad_keypoints(int width, int height, int n, const float *kps2d, const uint8_t *flags, uint8_t *keep)
+{
+    if (n < 0 || (n > 0 && (!kps2d || !flags || !keep))) return SVO_ERR_INVALID;
+    for (int i = 0; i < n; i++)
+        keep[i] = host_is_bad(kps2d[2 * i], kps2d[2 * i + 1], width, height, flags[i] & SVO_FLAG_IGNORE_COMPLETELY, flags[i] & SVO_FLAG_IGNORE_REFINEMENT) ? 0 : 1;
+    return SVO_OK;
+}
+int svo_host_merge_keypoints(int width, int height, int grid_width, int grid_height, int n_old, const float *old_kps2d, int n_new,
+                             const float *new_kps2d, int max_out, int *appended, int *n_out)
+{
+    if (width < 1 || height < 1 || grid_width < 1 || grid_height < 1 || n_old < 0 || n_new < 0 || !n_out || (n_old > 0 && !old_kps2d) ||
+        (n_new > 0 && !new_kps2d))
+        return SVO_ERR_INVALID;
+    std::vector<int> app;
+    // calculate_depth hands (grid_width, grid_height) to parameters declared (grid_height, grid_width): cells are
+    // grid_height wide and grid_width tall (depth_calculator.cpp:88-90, :179-180)
+    host_merge(width, height, grid_height, grid_width, old_kps2d, (size_t)n_old, new_kps2d, (size_t)n_new, app);
+    *n_out = (int)app.size();
+    for (size_t i = 0; i < app.size() && (int)i < max_out; i++) appended[i] = app[i];
+    return SVO_OK;
+}
+int svo_host_keyframe_needed(int width, int height, int grid_width, int grid_height, int n, const float *kps2d, const uint8_t *flags, int *needed)
+{
+    if (grid_width < 1 || grid_height < 1 || n < 0 || !needed || (n > 0 && (!kps2d || !flags))) return SVO_ERR_INVALID;
+    std::vector<uint8_t> ic((size_t)n);
+    for (int i = 0; i < n; i++) ic[i] = (flags[i] & SVO_FLAG_IGNORE_COMPLETELY) ? 1 : 0;
+    *needed = host_keyframe_needed(width, height, grid_width, grid_height, kps2d, ic.data(), 1, (size_t)n) ? 1 : 0;
+    return SVO_OK;
+}
+struct svo_motion_filter { MotionFilter f; };
+int svo_motion_filter_create(svo_motion_filter **out)
+{
+    if (!out) return SVO_ERR_INVALID;
+    *out = new svo_motion_filter();
+    return SVO_OK;
+}
+int svo_motion_filter_destroy(svo_motion_filter *m) { if (!m) return SVO_ERR_INVALID; delete m; return SVO_OK; }
+int svo_motion_filter_update(svo_motion_filter *m, const svo_pose *pose, const float speed[6], const float pv[6], const float sv[6], double dt,
+                             svo_pose *filtered, float state_pre12[12])
+{
+    if (!m || !pose || !speed || !pv || !sv) return SVO_ERR_INVALID;
+    MotionFilter &kf = m->f;
+    // StereoSlam::update_pose (stereo_slam.cpp:296-359)
+    for (int i = 0; i < 6; i++) kf.A[i * 12 + (i + 6)] = (float)dt;
+    kf.predict();
+    for (int i = 0; i < 6; i++) { kf.R[i * 12 + i] = pv[i]; kf.R[(i + 6) * 12 + (i + 6)] = sv[i]; }
+    const float z[12] = {pose->x, pose->y, pose->z, pose->rx, pose->ry, pose->rz, speed[0], speed[1], speed[2], speed[3], speed[4], speed[5]};
+    kf.correct(z);
+    if (filtered) { filtered->x = kf.xpost[0]; filtered->y = kf.xpost[1]; filtered->z = kf.xpost[2]; filtered->rx = kf.xpost[3]; filtered->ry = kf.xpost[4]; filtered->rz = kf.xpost[5]; }
+    if (state_pre12) std::memcpy(state_pre12, kf.xpre, sizeof(kf.xpre));
+    return SVO_OK;
+}
+
 int svo_slam_last_counters(svo_slam *s, long long *out8)
 {
     if (!s || !out8) return SVO_ERR_INVALID;
     for (int k = 0; k < 8; k++) out8[k] = s->counters[k];
+    return SVO_OK;
+}
+int svo_slam_dropped_keypoints(svo_slam *s, long long *dropped)
+{
+    if (!s || !dropped) return SVO_ERR_INVALID;
+    *dropped = s->dropped_for_capacity;
     return SVO_OK;
 }
 int svo_slam_last_stats(svo_slam *s, float *gpu_ms, int *launches, int *keyframe_created)

@@ -30,8 +30,10 @@ class Frame:
         self.id, self.pose, self.time_stamp, self.kps = fid, pose, time_stamp, kps
 
     def image(self, kind="left", level=0):
+        """Pixels of THIS frame (the reference's getters return value copies): a keyframe is addressed by its absolute index;
+        the current frame's images are only on the device until the next new_image, after which this raises."""
         k = {"left": 0, "right": 1, "opt_flow": 2}[kind]
-        return self._slam._image(self._index, k, level)
+        return self._slam._image(self._index, k, level, self.id)
 
 
 class KeyFrame(Frame):
@@ -39,12 +41,12 @@ class KeyFrame(Frame):
 
 
 class StereoSlam:
-    def __init__(self, camera_settings, width, height, device=0):
+    def __init__(self, camera_settings, width, height, device=0, max_keypoints=0):
         if isinstance(camera_settings, dict):
             camera_settings = CameraSettings(**camera_settings)
         self.camera_settings, self.width, self.height = camera_settings, width, height
         out = C.c_void_p()
-        rc = capi.lib().svo_slam_create(C.byref(camera_settings), device, width, height, C.byref(out))
+        rc = capi.lib().svo_slam_create_with_capacity(C.byref(camera_settings), device, width, height, max_keypoints, C.byref(out))
         if rc:
             raise SvoError(rc, capi.lib().svo_slam_last_error(None).decode())
         self._h = out
@@ -107,11 +109,15 @@ class StereoSlam:
         self._ck(capi.lib().svo_slam_new_image_end(self._h))
         self._keep = None
 
-    def _image(self, index, kind, level):
+    def _image(self, index, kind, level, frame_id=None):
         ctx = capi.Context(self.camera_settings, self.width, self.height, _borrowed=capi.lib().svo_slam_ctx(self._h))
         w, h = ctx.level_size(kind, level)
         out = np.empty((h, w), np.uint8)
         if index is None:
+            fid = C.c_uint64()
+            self._ck(capi.lib().svo_slam_get_frame(self._h, C.byref(fid), None, None, None))
+            if frame_id is not None and fid.value != frame_id:
+                raise SvoError(capi.SVO_ERR_STATE, f"images of frame {frame_id} are gone: the sequence is at frame {fid.value}")
             self._ck(capi.lib().svo_slam_get_frame_image(self._h, kind, level, out.ctypes.data_as(C.c_void_p), C.c_size_t(w)))
         else:
             self._ck(capi.lib().svo_slam_get_keyframe_image(self._h, index, kind, level, out.ctypes.data_as(C.c_void_p), C.c_size_t(w)))
@@ -119,6 +125,10 @@ class StereoSlam:
 
     def _fetch(self, index):
         fid, pose, ts, n = C.c_uint64(), Pose(), C.c_double(), C.c_int()
+        if index is not None and index < 0:   # "latest keyframe": pin the absolute index, later keyframes must not change what this object shows
+            index = capi.lib().svo_slam_keyframe_count(self._h) - 1
+            if index < 0:
+                return None
         if index is None:
             rc = capi.lib().svo_slam_get_frame(self._h, C.byref(fid), C.byref(pose), C.byref(ts), C.byref(n))
         else:
@@ -173,6 +183,12 @@ class StereoSlam:
         ms, n, kf = C.c_float(), C.c_int(), C.c_int()
         self._ck(capi.lib().svo_slam_last_stats(self._h, C.byref(ms), C.byref(n), C.byref(kf)))
         return dict(gpu_ms=ms.value, launches=n.value, keyframe_created=bool(kf.value))
+
+    def dropped_keypoints(self):
+        """New keypoints keyframes could not take because the device keypoint block was full (0 unless max_keypoints is tiny)."""
+        out = C.c_longlong()
+        self._ck(capi.lib().svo_slam_dropped_keypoints(self._h, C.byref(out)))
+        return int(out.value)
 
     def last_counters(self):
         out = (C.c_longlong * 8)()

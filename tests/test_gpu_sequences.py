@@ -1,0 +1,424 @@
+"""GPU parity over whole sequences and across keyframes (run on the B200 box: pytest -m gpu), through the C-ABI.
+
+The checker is the CPU oracle, which tests/test_ref_pin.py pins bit for bit to the reference itself (oracle/_ref).
+What is compared, for the free-running facade (svo_slam_*) against the free-running oracle:
+  * every frame: pose (<= 1e-4 m relative / 1e-4 rad per frame is the bar for identical inputs; a free-running pair drifts
+    apart by rounding, so the sequence bound is stated per case and the measured maximum is written to the report);
+  * every keyframe, when it is created and again at the end (after the write-backs of stereo_slam.cpp:205-226) and the
+    final frame: the keypoint lists entry by entry — 2-D, 3-D, level, type, keyframe_id, keypoint_index, the three flags,
+    both vote counters, score, depth-filter state.  Identity fields (level, type, origin keyframe, index) and the positions
+    of NEW keypoints (integers out of the detector) must be exact; flags and counters may flip where a float lands on the
+    other side of a threshold: the flip rates are counted, bounded and reported, never hidden in a quantile.
+The numbers go to gpurun_out/parity_report.json (copied to profiles/ by hand).
+"""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from stereo_svo_slam_b200 import StereoSlam, capi, synth
+from tests.golden import make_ref_golden as mg
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REPORT = os.path.join(ROOT, "gpurun_out", "parity_report.json")
+
+POSE_TOL_T, POSE_TOL_R, DEPTH_RTOL = 1e-4, 1e-4, 1e-3
+
+
+def report(key, value):
+    os.makedirs(os.path.dirname(REPORT), exist_ok=True)
+    data = {}
+    if os.path.exists(REPORT):
+        try:
+            data = json.load(open(REPORT))
+        except Exception:
+            data = {}
+    data[key] = value
+    json.dump(data, open(REPORT, "w"), indent=1, sort_keys=True)
+
+
+def gpu_lists(f):
+    """Frame / KeyFrame of the facade -> the column names of oracle.OracleSlam.frame()."""
+    i = f.kps.info
+    flags = (i["ignore_during_refinement"].astype(np.int32) | (i["ignore_completely"].astype(np.int32) << 1) |
+             (i["ignore_temporary"].astype(np.int32) << 2))
+    return dict(kps2d=f.kps.kps2d, kps3d=f.kps.kps3d, level=i["level"].astype(np.int32), type=i["type"].astype(np.int32),
+                keyframe_id=i["keyframe_id"].astype(np.int32), keypoint_index=i["keypoint_index"].astype(np.int32), flags=flags,
+                inlier_count=i["inlier_count"].astype(np.int32), outlier_count=i["outlier_count"].astype(np.int32),
+                score=i["score"].astype(np.float32), kf_state=i["kf_inv_depth"].astype(np.float32), kf_cov=i["kf_variance"].astype(np.float32))
+
+
+def compare_lists(g, o, own_id=None):
+    """-> dict of mismatch counts / maxima; raises on a structural difference (length, identity fields, new positions)."""
+    n = len(o["flags"])
+    assert len(g["flags"]) == n, (len(g["flags"]), n)
+    for key in ("level", "type", "keyframe_id", "keypoint_index"):
+        assert (g[key] == o[key]).all(), (key, int((g[key] != o[key]).sum()), n)
+    assert (g["score"] == o["score"]).all()
+    if own_id is not None:       # the keypoints this keyframe introduced: integer positions straight from the detector
+        new = o["keyframe_id"] == own_id
+        assert (g["kps2d"][new] == o["kps2d"][new]).all()
+    sc = np.maximum(1.0, np.abs(o["kps3d"]).max(axis=1)) if n else np.ones(0)
+    st = np.maximum(1e-6, np.abs(o["kf_state"]))
+    return dict(n=n, flag_flips=int((g["flags"] != o["flags"]).sum()),
+                vote_diffs=int(((g["inlier_count"] != o["inlier_count"]) | (g["outlier_count"] != o["outlier_count"])).sum()),
+                max_2d=float(np.abs(g["kps2d"] - o["kps2d"]).max()) if n else 0.0,
+                max_3d_rel=float((np.abs(g["kps3d"] - o["kps3d"]).max(axis=1) / sc).max()) if n else 0.0,
+                max_state_rel=float((np.abs(g["kf_state"] - o["kf_state"]) / st).max()) if n else 0.0)
+
+
+def merge_stats(acc, s):
+    for k, v in s.items():
+        acc[k] = acc.get(k, 0) + v if k in ("n", "flag_flips", "vote_diffs") else max(acc.get(k, 0.0), v)
+
+
+SEQUENCES = [
+    # name, synth config, frames, settings overrides, sequence seed, pose bound as a multiple of the per-frame tolerance
+    ("SF_three_keyframes", "SF", 100, {}, None, 10),
+    ("C3_across_keyframe_2", "C3", 64, {}, None, 5),
+    ("C4_50_frames", "C4", 50, {}, None, 5),
+    ("EuRoC_yaml", "C3", 64, dict(grid_width=54, grid_height=48, search_x=60, search_y=6, max_pyramid_levels=6, min_pyramid_level_pose_estimation=2), 4, 5),
+    ("Blender_yaml", "C3", 64, dict(fx=470.0, fy=470.0, cx=376.0, cy=240.0, baseline=28.2, grid_width=75, grid_height=48, search_x=50, search_y=6,
+                                    max_pyramid_levels=5, min_pyramid_level_pose_estimation=2), 4, 5),
+]
+
+
+@pytest.mark.parametrize("name,cfg,frames,over,seed,bound", SEQUENCES, ids=[s[0] for s in SEQUENCES])
+def test_free_running_sequence_and_keyframe_lists(name, cfg, frames, over, seed, bound):
+    c = dict(synth.CONFIGS[cfg])
+    d = synth.settings_dict(cfg)
+    d.update(over)
+    c.update({k: v for k, v in over.items() if k in ("fx", "fy", "cx", "cy", "baseline")})
+    seq = synth.make_sequence(c, seed=seed)
+    o = orc.OracleSlam(orc.CameraSettings(**d), c["width"], c["height"], tracing=False)
+    g = StereoSlam(capi.CameraSettings(**d), c["width"], c["height"])
+    worst_t = worst_r = 0.0
+    at_creation, n_mismatch, kf_frames = {}, 0, []
+    for k in range(frames):
+        L, R = seq.render(k)
+        o.new_image(L, R, k / 20.0)
+        g.new_image(L, R, k / 20.0)
+        gp, op = g.pose(), o.pose()
+        worst_t = max(worst_t, np.abs(gp[:3] - op[:3]).max() / max(1.0, np.abs(op[:3]).max()))
+        worst_r = max(worst_r, np.abs(gp[3:] - op[3:]).max())
+        assert g.keyframe_count() == o.n_keyframes(), (k, g.keyframe_count(), o.n_keyframes())
+        f = g.get_frame()
+        assert f.id == k
+        n_mismatch += int(len(f.kps) != o.n_kps())
+        while len(kf_frames) < o.n_keyframes():   # a keyframe was created in this frame: compare it as created
+            kid = len(kf_frames)
+            kf_frames.append(k)
+            merge_stats(at_creation, compare_lists(gpu_lists(g.get_keyframes()[kid]), o.keyframe_full(kid), own_id=kid))
+    assert n_mismatch == 0, f"keypoint count differed from the oracle on {n_mismatch} of {frames} frames"
+    at_end = {}
+    for kid, kf in enumerate(g.get_keyframes()):
+        okf = o.keyframe_full(kid)
+        assert kf.id == okf["id"] == kid
+        assert np.abs(kf.pose - okf["pose"]).max() <= bound * POSE_TOL_T
+        merge_stats(at_end, compare_lists(gpu_lists(kf), okf, own_id=kid))
+    final = compare_lists(gpu_lists(g.get_frame()), o.frame())
+    traj, otraj = g.get_trajectory(), o.trajectory()
+    assert traj.shape == otraj.shape == (frames, 6)
+    rep = dict(frames=frames, keyframes_at=kf_frames, pose_max_rel_t=worst_t, pose_max_r=worst_r, keyframes_as_created=at_creation,
+               keyframes_at_end=at_end, final_frame=final, dropped_keypoints=g.dropped_keypoints())
+    report("free_running/" + name, rep)
+    assert worst_t <= bound * POSE_TOL_T and worst_r <= bound * POSE_TOL_R, rep
+    for s in (at_creation, at_end, final):
+        assert s["flag_flips"] <= max(1, s["n"] // 100) and s["vote_diffs"] <= max(2, s["n"] // 50), rep
+        assert s["max_3d_rel"] <= 5 * DEPTH_RTOL and s["max_2d"] <= 0.05, rep
+    if cfg == "SF":
+        assert len(kf_frames) >= 3 and set(np.unique(o.frame()["keyframe_id"])) == {0, 1, 2}
+    if name == "C3_across_keyframe_2":
+        assert len(kf_frames) == 2 and kf_frames[1] == 46
+    g.close()
+
+
+def test_update_pose_between_frames():
+    """StereoSlam::update_pose (stereo_slam.cpp:296-359) called between frames with dt > 0 (the IMU entry of the app,
+    src/app/slam_app.cpp:133) on the facade and on the oracle: same returned poses, same trajectory, same keyframes."""
+    name, cfg, frames, over, imu = next(c for c in mg.CASES if c[0] == "SF_imu")
+    c, d = synth.CONFIGS[cfg], synth.settings_dict(cfg)
+    seq = synth.make_sequence(cfg)
+    o = orc.OracleSlam(orc.CameraSettings(**d), c["width"], c["height"], tracing=False)
+    g = StereoSlam(capi.CameraSettings(**d), c["width"], c["height"])
+    worst = worst_imu = 0.0
+    for k in range(frames):
+        L, R = seq.render(k)
+        o.new_image(L, R, k / 20.0)
+        g.new_image(L, R, k / 20.0)
+        worst = max(worst, np.abs(g.pose() - o.pose()).max())
+        if k % 3 == 2:
+            a, b = g.update_pose(*mg.imu_call(k)), o.update_pose(*mg.imu_call(k))
+            worst_imu = max(worst_imu, np.abs(a - b).max())
+        assert g.keyframe_count() == o.n_keyframes() and len(g.get_frame().kps) == o.n_kps(), k
+    report("update_pose/SF_imu", dict(frames=frames, keyframes=o.n_keyframes(), pose_max=worst, imu_out_max=worst_imu))
+    assert o.n_keyframes() >= 4
+    assert worst <= 10 * POSE_TOL_T and worst_imu <= 10 * POSE_TOL_T
+    # the oracle itself reproduces the reference's vectors for this run bit for bit (tests/test_ref_pin.py)
+    assert np.abs(g.get_trajectory() - mg_vectors()["SF_imu/trajectory"]).max() <= 10 * POSE_TOL_T
+    g.close()
+
+
+def mg_vectors():
+    return np.load(os.path.join(ROOT, "tests", "golden", "ref_vectors.npz"))
+
+
+# ------------------------------------------------------------------------------------------------ teacher forced
+def _oracle_inputs(slam):
+    t = slam.trace
+    n = len(t("align_in_flags"))
+    kfid = t("align_in_kfid").astype(np.int32)
+    kpidx = t("align_in_kpidx").astype(np.int64)
+    ref2d = np.zeros((n, 2), np.float32)
+    for k in np.unique(kfid):
+        _, k2, _ = slam.keyframe(int(k))
+        m = kfid == k
+        ref2d[m] = k2[kpidx[m]]
+    return dict(prev_kps2d=t("align_in_kps2d").reshape(-1, 2), kps3d=t("align_in_kps3d").reshape(-1, 3), ref_kps2d=ref2d,
+                keyframe_id=kfid, flags=t("align_in_flags").astype(np.uint8), inlier=t("align_in_counts").reshape(-1, 2)[:, 0].astype(np.int32),
+                outlier=t("align_in_counts").reshape(-1, 2)[:, 1].astype(np.int32),
+                kf_state=np.stack([t("align_in_kfx"), t("align_in_kfP")], 1), pose_prior=t("align_pose_in"))
+
+
+@pytest.mark.parametrize("cfg,frames", [("SF", 100), ("C3", 64)])
+def test_teacher_forced_across_keyframes(cfg, frames):
+    """Every tracking frame of the oracle's run, INCLUDING the frames after keyframes #2 and #3 (keypoints from several origin
+    keyframes, template cache entries with first > 0): the oracle's inputs go through the fused CUDA frame and every stage
+    output is compared.  Identical inputs, so identical positions => exact integer results are required wherever the float
+    keypoint lands on the same pixel; the mismatch counts are totalled and reported."""
+    d = synth.settings_dict(cfg)
+    c = synth.CONFIGS[cfg]
+    seq = synth.make_sequence(cfg)
+    slam = orc.OracleSlam(orc.CameraSettings(**d), c["width"], c["height"], tracing=True)
+    ctx = capi.Context(capi.CameraSettings(**d), c["width"], c["height"])
+    prev_slot, n_kf = None, 0
+    tot = dict(frames=0, keypoints=0, path_flips=0, klt_status_diff=0, disparity_diff=0, flag_diff=0, vote_diff=0, multi_origin_frames=0)
+    mx = dict(pose_aligned_t=0.0, pose_aligned_r=0.0, pose_refined_t=0.0, pose_refined_r=0.0, flow_px=0.0, depth_rel=0.0, kps2d_px=0.0)
+    for k in range(frames):
+        L, R = seq.render(k)
+        slam.new_image(L, R, k / 20.0)
+        slot = ctx.upload(L, R)
+        if k > 0:
+            inp = _oracle_inputs(slam)
+            t = slam.trace
+            out = ctx.track_frame(prev_slot, slot, keypoint_index=t("align_in_kpidx").astype(np.int32), **inp)
+            n = len(inp["flags"])
+            tot["frames"] += 1
+            tot["keypoints"] += n
+            tot["multi_origin_frames"] += int(len(np.unique(inp["keyframe_id"])) > 1)
+            tot["path_flips"] += int(not (out["align_evals"] == t("align_evals").reshape(8, 2).astype(np.int32)).all())
+            for key, a, b in (("pose_aligned", out["pose_aligned"], t("align_pose_out")), ("pose_refined", out["pose_refined"], t("ref_pose_out"))):
+                mx[key + "_t"] = max(mx[key + "_t"], float(np.abs(a[:3] - b[:3]).max() / max(1.0, np.abs(b[:3]).max())))
+                mx[key + "_r"] = max(mx[key + "_r"], float(np.abs(a[3:] - b[3:]).max()))
+            st, ost = out["klt_status"], t("klt_status").astype(np.uint8)
+            tot["klt_status_diff"] += int((st != ost).sum())
+            ok = (st == 1) & (ost == 1)
+            if ok.any():
+                mx["flow_px"] = max(mx["flow_px"], float(np.abs(out["klt_pts"][ok] - t("klt_next").reshape(-1, 2)[ok]).max()))
+            dd, od = out["disparity"], t("df_disp")
+            fl, ofl = out["flags"], t("df_out_flags").astype(np.uint8)
+            cnt = np.stack([out["inlier"], out["outlier"]], 1)
+            ocnt = t("df_out_counts").reshape(-1, 2).astype(np.int32)
+            tot["disparity_diff"] += int((dd != od).sum())
+            tot["flag_diff"] += int((fl != ofl).sum())
+            tot["vote_diff"] += int((cnt != ocnt).any(axis=1).sum())
+            good = (fl == ofl) & (dd == od)
+            z, oz = out["kps3d"], t("df_out_kps3d").reshape(-1, 3)
+            if good.any():
+                rel = np.abs(z[good] - oz[good]).max(axis=1) / np.maximum(1.0, np.abs(oz[good]).max(axis=1))
+                mx["depth_rel"] = max(mx["depth_rel"], float(rel.max()))
+                mx["kps2d_px"] = max(mx["kps2d_px"], float(np.abs(out["kps2d"][good] - t("df_out_kps2d").reshape(-1, 2)[good]).max()))
+            # the depth filter on the ORACLE's own stage inputs: identical positions, so everything integer must be exact
+            cin = t("df_in_counts").reshape(-1, 2).astype(np.int32)
+            s = ctx.depth_filter_update(slot, t("df_in_kps2d").reshape(-1, 2), inp["ref_kps2d"], inp["keyframe_id"], t("df_in_kps3d").reshape(-1, 3),
+                                        t("df_in_flags").astype(np.uint8), cin[:, 0], cin[:, 1], np.stack([t("df_in_kfx"), t("df_in_kfP")], 1),
+                                        t("df_pose"))
+            assert (s["disparity"] == od).all() and (s["flags"] == ofl).all(), k
+            assert (np.stack([s["inlier"], s["outlier"]], 1) == ocnt).all(), k
+            rel = np.abs(s["kps3d"] - oz).max(axis=1) / np.maximum(1.0, np.abs(oz).max(axis=1))
+            assert rel.max() <= DEPTH_RTOL, (k, rel.max())
+        while n_kf < slam.n_keyframes():
+            kf = slam.keyframe_full(n_kf)
+            assert ctx.keyframe_commit(slot, kf["pose"]) == n_kf
+            own = kf["keyframe_id"] == n_kf          # like the facade: templates of the keypoints this keyframe introduced
+            first = int(np.argmax(own))
+            assert own[first:].all() and not own[:first].any()
+            ctx.keyframe_set_templates(n_kf, kf["kps2d"][first:], first)
+            n_kf += 1
+        if prev_slot is not None:
+            ctx.release(prev_slot)
+        prev_slot = slot
+    rep = dict(totals=tot, maxima=mx,
+               rates=dict(klt_status=tot["klt_status_diff"] / tot["keypoints"], disparity=tot["disparity_diff"] / tot["keypoints"],
+                          flags=tot["flag_diff"] / tot["keypoints"], votes=tot["vote_diff"] / tot["keypoints"], solver_path=tot["path_flips"] / tot["frames"]))
+    report("teacher_forced/" + cfg, rep)
+    assert n_kf >= 2 and tot["multi_origin_frames"] >= 10, rep
+    assert max(mx["pose_aligned_t"], mx["pose_refined_t"]) <= POSE_TOL_T and max(mx["pose_aligned_r"], mx["pose_refined_r"]) <= POSE_TOL_R, rep
+    assert mx["flow_px"] <= 0.01 and mx["depth_rel"] <= DEPTH_RTOL and mx["kps2d_px"] <= 0.05, rep
+    assert rep["rates"]["klt_status"] <= 0.005 and rep["rates"]["disparity"] <= 0.01 and rep["rates"]["flags"] <= 0.01 and rep["rates"]["votes"] <= 0.01, rep
+    ctx.close()
+
+
+# ------------------------------------------------------------------------------------------------ small parity holes
+def sha(a):
+    import hashlib
+    return np.frombuffer(hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest(), np.uint8)
+
+
+def test_scharr_levels_and_borders_bit_exact(fixture_images, cv2_vectors):
+    """cv::buildOpticalFlowPyramid(left, win, 2) (stereo_slam.cpp:139): the int16 Scharr planes of all three levels against
+    the oracle AND the hashes of cv2's own output, the BORDER_CONSTANT(0) frame around them and the BORDER_REFLECT_101
+    frame around the image levels."""
+    L, R = fixture_images["left"], fixture_images["right"]
+    h, w = L.shape
+    ctx = capi.Context(capi.CameraSettings(**synth.settings_dict("C3")), w, h)
+    slot = ctx.upload(L, R)
+    lv = L
+    for i in range(3):
+        der = ctx.download(slot, 3, i)
+        assert der.shape == (lv.shape[0], lv.shape[1], 2) and der.dtype == np.int16
+        assert (der == orc.scharr(lv)).all()
+        assert (sha(der) == cv2_vectors[f"lkpyr_der{i}_sha"]).all(), f"Scharr level {i} differs from cv2"
+        framed = ctx.download(slot, 5, i)
+        pad = (framed.shape[0] - lv.shape[0]) // 2
+        assert pad == 32 and (framed[pad:-pad, pad:-pad] == der).all()
+        border = framed.copy()
+        border[pad:-pad, pad:-pad] = 0
+        assert not border.any(), "derivative border must be BORDER_CONSTANT 0"
+        img = ctx.download(slot, 4, i)
+        assert (img == np.pad(lv, pad, mode="reflect")).all(), "image border must be BORDER_REFLECT_101"
+        assert (sha(img[pad:-pad, pad:-pad]) == cv2_vectors[f"lkpyr_img{i}_sha"]).all()
+        lv = orc.pyr_down(lv)
+    ctx.close()
+
+
+def _scene(cfg, k0, k1):
+    c = synth.CONFIGS[cfg]
+    seq = synth.make_sequence(cfg)
+    return c, seq, seq.render(k0), seq.render(k1)
+
+
+@pytest.mark.parametrize("which", ["none", "one", "two", "three", "collinear", "all_outside"])
+def test_rank_deficient_hessian(which):
+    """pose_estimator.cpp:405 / pose_refinement.cpp:398: `hessian.inv(DECOMP_SVD)` is a float pseudo-inverse; with fewer than
+    three usable keypoints (or collinear ones) H is rank deficient and the reference still takes the pseudo-inverse step, and a
+    zero step when cv::invert reports an exactly singular matrix.  A rank-deficient solve is defined by rounding noise in the
+    null space on both sides, so the comparable quantities are: (1) the exactly singular cases are identical (no step);
+    (2) the step reduces the cost like the oracle's; (3) with three keypoints in general position H has full rank and the
+    ordinary tolerance applies."""
+    cfg = "S"
+    d = synth.settings_dict(cfg)
+    gcs, ocs = capi.CameraSettings(**d), orc.CameraSettings(**d)
+    c, seq, (L0, R0), (L1, R1) = _scene(cfg, 0, 2)
+    o = orc.OracleSlam(ocs, c["width"], c["height"], tracing=False)
+    o.new_image(L0, R0, 0.0)
+    kf = o.keyframe_full(0)
+    k2, k3 = kf["kps2d"], kf["kps3d"]
+    inside = np.nonzero((k2[:, 0] > 60) & (k2[:, 0] < 260) & (k2[:, 1] > 60) & (k2[:, 1] < 180))[0]
+    if which == "none":
+        sel = inside[:0]
+    elif which == "one":
+        sel = inside[:1]
+    elif which == "two":
+        sel = inside[[0, -1]]
+    elif which == "three":
+        sel = inside[[0, len(inside) // 2, -1]]
+    elif which == "collinear":
+        row = k2[inside, 1]
+        r0 = np.bincount(row.astype(np.int64) // 24).argmax()       # keypoints of one grid row: nearly collinear in the image
+        sel = inside[(row.astype(np.int64) // 24) == r0][:6]
+    else:
+        sel = inside[[0, len(inside) // 2, -1]]
+    p2, p3 = k2[sel].copy(), k3[sel].copy()
+    if which == "all_outside":   # every 5x5 footprint leaves the image: all terms are zero, H == 0 exactly
+        p2[:] = [[0.5, 0.5], [1.0, 200.0], [318.5, 1.0]]
+    ctx = capi.Context(gcs, c["width"], c["height"])
+    s0, s1 = ctx.upload(L0, R0), ctx.upload(L1, R1)
+    guess = np.zeros(6, np.float32)
+    gp, gcost, gev = ctx.align(s0, s1, p2, p3, guess)
+    op, ocost, oev = orc.align(L0, L1, ocs, p2, p3, guess)
+    cost0 = orc.align_cost(L0, L1, ocs, p2, p3, guess, d["min_pyramid_level_pose_estimation"], want_grad=False)[0]
+    cost_gpu_pose = orc.align_cost(L0, L1, ocs, p2, p3, gp, d["min_pyramid_level_pose_estimation"], want_grad=False)[0]
+    rep = dict(n=len(sel), gpu_pose=gp.tolist(), oracle_pose=op.tolist(), cost_start=cost0, cost_gpu=gcost, cost_oracle=ocost,
+               cost_of_gpu_pose_by_oracle=cost_gpu_pose, gpu_evals=gev.tolist(), oracle_evals=oev.tolist())
+    report("rank_deficient/align_" + which, rep)
+    if which in ("none", "all_outside"):
+        assert (gp == guess).all() and (op == guess).all() and gcost == ocost == 0.0, rep
+    elif which == "three":
+        assert np.abs(gp - op).max() <= 20 * POSE_TOL_T, rep   # full rank but poorly conditioned: float SVD vs double LDL^T
+    else:
+        assert np.isfinite(gp).all() and np.isfinite(op).all(), rep
+        moved_o, moved_g = np.abs(op).max() > 0, np.abs(gp).max() > 0
+        assert moved_o == moved_g, rep                          # not a zero step where the reference steps
+        assert abs(gcost - cost_gpu_pose) <= 1e-3 * max(1.0, cost_gpu_pose), rep    # the kernel's cost is the cost of its pose
+        assert gcost <= cost0 + 1e-3 and ocost <= cost0 + 1e-3, rep
+    if len(sel) == 0:
+        ctx.close()
+        return
+    # the reprojection solver with the same keypoint subsets
+    flags = np.zeros(len(sel), np.uint8)
+    true = seq.pose(2).astype(np.float32)
+    obs = orc.project(ocs, true, p3) if len(sel) else np.zeros((0, 2), np.float32)
+    g2, gc2, ge2 = ctx.reproj_refine(obs, p3, flags, guess)
+    o2, oc2, oe2 = orc.refine(ocs, obs, p3, flags.astype(np.int32), guess)
+    report("rank_deficient/refine_" + which, dict(n=len(sel), gpu_pose=g2.tolist(), oracle_pose=o2.tolist(), cost_gpu=gc2, cost_oracle=oc2,
+                                                    gpu_evals=ge2.tolist(), oracle_evals=oe2.tolist()))
+    if which in ("three", "all_outside"):
+        assert np.abs(g2 - o2).max() <= 20 * POSE_TOL_T          # three points in general position: full rank
+    else:
+        c_start = float(np.abs(orc.project(ocs, guess, p3) - obs).sum())
+        assert np.isfinite(g2).all() and gc2 <= c_start + 1e-4 and oc2 <= c_start + 1e-4
+        assert (np.abs(g2).max() > 0) == (np.abs(o2).max() > 0)
+    ctx.close()
+
+
+# ------------------------------------------------------------------------------------------------ robustness
+def test_failed_new_image_leaves_the_sequence_intact():
+    """A new_image call that fails (row stride below the width) must not consume the current frame: the sequence goes on and
+    stays bit-identical to an undisturbed run."""
+    cfg = "S"
+    c, d = synth.CONFIGS[cfg], synth.settings_dict(cfg)
+    seq = synth.make_sequence(cfg)
+    runs = []
+    for disturb in (False, True):
+        g = StereoSlam(capi.CameraSettings(**d), c["width"], c["height"])
+        for k in range(8):
+            L, R = seq.render(k)
+            if disturb and k in (0, 3, 5):
+                rc = capi.lib().svo_slam_new_image(g._h, L.ctypes.data_as(C.c_void_p), C.c_size_t(c["width"] - 1),
+                                                   R.ctypes.data_as(C.c_void_p), C.c_size_t(c["width"]), C.c_float(k / 20.0))
+                assert rc == capi.SVO_ERR_INVALID
+                assert b"stride" in capi.lib().svo_slam_last_error(g._h)
+                if k == 0:
+                    assert g.get_frame() is None
+            g.new_image(L, R, k / 20.0)
+        runs.append((g.get_trajectory().copy(), gpu_lists(g.get_frame())))
+        g.close()
+    assert runs[0][0].tobytes() == runs[1][0].tobytes()
+    for key in runs[0][1]:
+        assert runs[0][1][key].tobytes() == runs[1][1][key].tobytes(), key
+
+
+def test_keypoint_capacity_overflow_is_not_fatal():
+    """The reference's keypoint lists are unbounded; the device block is not.  With a capacity far below one keypoint per
+    cell the keyframe keeps its best-scored new keypoints and tracking goes on (no SVO_ERR_CAPACITY on every later frame)."""
+    cfg = "S"
+    c, d = synth.CONFIGS[cfg], synth.settings_dict(cfg)
+    seq = synth.make_sequence(cfg)
+    g = StereoSlam(capi.CameraSettings(**d), c["width"], c["height"], max_keypoints=64)
+    full = StereoSlam(capi.CameraSettings(**d), c["width"], c["height"])
+    for k in range(6):
+        L, R = seq.render(k)
+        g.new_image(L, R, k / 20.0)
+        full.new_image(L, R, k / 20.0)
+    n, nf = len(g.get_frame().kps), len(full.get_frame().kps)
+    assert n == 64 and nf > 64 and g.dropped_keypoints() == nf - 64 and full.dropped_keypoints() == 0
+    kept = g.get_keyframes()[0].kps.info["score"]
+    assert kept.min() >= np.sort(full.get_keyframes()[0].kps.info["score"])[::-1][63]
+    assert np.abs(g.pose() - seq.pose(5)).max() < 0.02      # still tracks
+    g.close()
+    full.close()
