@@ -230,6 +230,18 @@ def lk(prev_img, next_img, prev_pts, init_pts, win=31):
     return nxt, status, err
 
 
+def lk_iters(prev_img, next_img, prev_pts, init_pts, win=31):
+    """lk() plus, per point, the largest iteration count of any level (30: that level did not converge)."""
+    prev_img, next_img = _u8(prev_img), _u8(next_img)
+    h, w = prev_img.shape
+    prev_pts = _f32(prev_pts).reshape(-1, 2)
+    nxt = _f32(init_pts).reshape(-1, 2).copy()
+    n = prev_pts.shape[0]
+    status, err, it = np.empty(n, np.uint8), np.empty(n, np.float32), np.zeros(n, np.int32)
+    lib().orc_lk_iters(_p(prev_img), _p(next_img), w, h, win, _p(prev_pts), _p(nxt), n, _p(status), _p(err), _p(it))
+    return nxt, status, err, it
+
+
 def ssd_disparity(left, right, cs, kps2d, mode):
     left, right = _u8(left), _u8(right)
     h, w = left.shape

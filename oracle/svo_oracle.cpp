@@ -729,14 +729,18 @@ struct OracleSlam {
         tr("klt_init", act.data(), act.size());
         tri("klt_kf", kfid);
         double t0 = now_ms();
+        std::vector<float> lk_max_iters(tracing ? n : 0);
         for (size_t i = 0; i < n; i++) {
             KeyFrame *k = keyframes[f.kps.info[i].keyframe_id].get();
+            int it[3];
             lk_track_point(k->img->opt_flow, f.img->opt_flow, cs.window_size_opt_flow, 2, 30, 0.01 * 0.01, 1e-4, &ref[2 * i], &act[2 * i],
-                           &status[i], &err[i]);
+                           &status[i], &err[i], tracing ? it : nullptr);
+            if (tracing) lk_max_iters[i] = (float)std::max(it[0], std::max(it[1], it[2]));
             if (status[i] == 0) err[i] = std::numeric_limits<float>::infinity();  // optical_flow.cpp:46-50
         }
         stage_ms[2] = now_ms() - t0;
         tr("klt_next", act.data(), act.size());
+        tr("klt_max_iters", lk_max_iters.data(), lk_max_iters.size());   // 30 on some level: that level's iteration did not converge
         tr("klt_err", err.data(), err.size());
         if (tracing) { std::vector<float> s(status.begin(), status.end()); trace["klt_status"] = s; }
         for (size_t i = n; i > 0; i--) {
@@ -1054,6 +1058,19 @@ void orc_lk(const uint8_t *prev, const uint8_t *next, int w, int h, int win, con
     build_lk_pyramid(next, w, h, w, 2, b);
     for (int i = 0; i < n; i++)
         lk_track_point(a, b, win, 2, 30, 0.01 * 0.01, 1e-4, prev_pts + 2 * i, next_pts + 2 * i, status + i, err + i);
+}
+// same as orc_lk, plus per point the largest iteration count any level used (30 = that level ran out of iterations)
+void orc_lk_iters(const uint8_t *prev, const uint8_t *next, int w, int h, int win, const float *prev_pts, float *next_pts, int n,
+                  uint8_t *status, float *err, int *max_iters)
+{
+    LKPyramid a, b;
+    build_lk_pyramid(prev, w, h, w, 2, a);
+    build_lk_pyramid(next, w, h, w, 2, b);
+    for (int i = 0; i < n; i++) {
+        int it[3];
+        lk_track_point(a, b, win, 2, 30, 0.01 * 0.01, 1e-4, prev_pts + 2 * i, next_pts + 2 * i, status + i, err + i, it);
+        max_iters[i] = std::max(it[0], std::max(it[1], it[2]));
+    }
 }
 void orc_ssd_disparity(const uint8_t *left, const uint8_t *right, int w, int h, const OrcCameraSettings *cs, const float *kps2d, int n,
                        int mode, float *out)

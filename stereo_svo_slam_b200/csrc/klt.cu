@@ -486,6 +486,21 @@ __global__ void __launch_bounds__(KLT_THREADS) klt31_kernel(KltArgs a)
 #define KLTW_REG_ROWS 48     // staged search region per warp: 32 window rows + 8 above + 8 below
 #define KLTW_REG_PITCH 17    // words per staged row: 64 bytes + 1 word (odd pitch: the 32 rows of a warp-wide load hit 32 banks)
 
+// two-way dot product of SIGNED 16-bit halves of a with UNSIGNED bytes of b (lower / upper pair), plus c — the CUDA intrinsics
+// __dp2a_lo/hi only come as all-signed or all-unsigned
+__device__ __forceinline__ int dp2a_lo_s16u8(uint32_t a, uint32_t b, int c)
+{
+    int d;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int dp2a_hi_s16u8(uint32_t a, uint32_t b, int c)
+{
+    int d;
+    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
 // exact warp-wide sum of a 32-bit signed value per lane (|v| < 2^31), returned as 64 bit to every lane
 __device__ __forceinline__ long long warp_sum_i32_exact(int v)
 {
@@ -750,7 +765,9 @@ __global__ void __launch_bounds__(32 * KLTW_WARPS, 4) klt31w_kernel(KltArgs a)
 #pragma unroll
             for (int k = 0; k < 8; k++) bot[k] = __shfl_down_sync(0xffffffffu, top[k], 1);
             bot[8] = 0;
-            const uint32_t Wt = (uint32_t)w00 | ((uint32_t)w01 << 16), Wb = (uint32_t)w10 | ((uint32_t)w11 << 16);
+            // Q14 weights as SIGNED 16-bit pairs: OpenCV takes iw11 as the remainder 2^14 - iw00 - iw01 - iw10, which is -1
+            // when the three rounded weights add up to 2^14 + 1 (fractions of a few 1e-5 of a pixel)
+            const uint32_t Wt = ((uint32_t)w00 & 0xffffu) | ((uint32_t)w01 << 16), Wb = ((uint32_t)w10 & 0xffffu) | ((uint32_t)w11 << 16);
             int acc1 = 0, acc2 = 0;
 #pragma unroll
             for (int k = 0; k < 8; k++) {
@@ -759,14 +776,14 @@ __global__ void __launch_bounds__(32 * KLTW_WARPS, 4) klt31w_kernel(KltArgs a)
                 for (int q = 0; q < 4; q++) {
                     const int x = 4 * k + q;
                     if (x < 31) {
-                        unsigned v;
+                        int v;
                         // rounding constant and template value ride in as the accumulator of the first dot product
-                        const unsigned c0 = (unsigned)Iw[x];
-                        if (q == 0) v = __dp2a_lo(Wt, top[k], __dp2a_lo(Wb, bot[k], c0));
-                        else if (q == 1) v = __dp2a_lo(Wt, ts, __dp2a_lo(Wb, bs, c0));
-                        else if (q == 2) v = __dp2a_hi(Wt, top[k], __dp2a_hi(Wb, bot[k], c0));
-                        else v = __dp2a_hi(Wt, ts, __dp2a_hi(Wb, bs, c0));
-                        const int diff = (int)v >> 9;
+                        const int c0 = Iw[x];
+                        if (q == 0) v = dp2a_lo_s16u8(Wt, top[k], dp2a_lo_s16u8(Wb, bot[k], c0));
+                        else if (q == 1) v = dp2a_lo_s16u8(Wt, ts, dp2a_lo_s16u8(Wb, bs, c0));
+                        else if (q == 2) v = dp2a_hi_s16u8(Wt, top[k], dp2a_hi_s16u8(Wb, bot[k], c0));
+                        else v = dp2a_hi_s16u8(Wt, ts, dp2a_hi_s16u8(Wb, bs, c0));
+                        const int diff = v >> 9;
                         if (want_err) acc1 += abs(diff);
                         else { acc1 += diff * Ix[x]; acc2 += diff * Iy[x]; }   // <= 31 * 8160 * 4080 < 2^31
                     }

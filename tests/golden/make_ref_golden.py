@@ -23,7 +23,7 @@ from stereo_svo_slam_b200 import synth  # noqa: E402
 CASES = [
     ("S", "S", 120, {}, False),
     ("SF", "SF", 100, {}, False),          # three keyframes: merge with old keypoints, several origin keyframes
-    ("SF_imu", "SF", 40, {}, True),        # StereoSlam::update_pose called between frames with dt > 0
+    ("SF_imu", "SF", 80, {}, True),        # StereoSlam::update_pose called between frames with dt > 0
     ("S_dist", "S", 30, dict(k1=-0.12, k2=0.05, p1=0.001, p2=-0.0015, k3=0.01), False),   # full projectPoints model
     ("S_blender_grid", "S", 30, dict(grid_width=25, grid_height=16, max_pyramid_levels=5), False),  # odd grid, 5 levels
     ("C3", "C3", 64, {}, False),           # BASELINE configs[2]; keyframe #2 at frame 46
@@ -31,12 +31,14 @@ CASES = [
 FIELDS = ("kps2d", "kps3d", "score", "kf_state", "kf_cov") + orc.INFO_COLS[:-1]   # colour is rand(): not compared
 
 
-def imu_call(k):
-    """A deterministic fake IMU sample for the frame gap after frame k (pose, speed, variances, dt)."""
+def imu_call(seq, k):
+    """A deterministic IMU-like sample for the gap after frame k: the pose half a frame ahead and the velocity of the synthetic
+    trajectory, both with noise, the app's kind of variances, dt = 0.025 s (pose, speed, variances, dt)."""
     rng = np.random.default_rng(9000 + k)
-    pose = (rng.standard_normal(6) * 0.01).astype(np.float32)
-    speed = (rng.standard_normal(6) * 0.1).astype(np.float32)
-    return pose, speed, np.full(6, 0.5, np.float32), np.full(6, 2.0, np.float32), 0.05
+    p0, p1 = seq.pose(k), seq.pose(k + 1)
+    pose = (0.5 * (p0 + p1) + rng.standard_normal(6) * 2e-3).astype(np.float32)
+    speed = ((p1 - p0) / 0.05 + rng.standard_normal(6) * 0.05).astype(np.float32)
+    return pose, speed, np.full(6, 0.5, np.float32), np.full(6, 2.0, np.float32), 0.025
 
 
 def run_case(slam_cls, cfg, frames, over, imu, on_frame=None):
@@ -52,7 +54,7 @@ def run_case(slam_cls, cfg, frames, over, imu, on_frame=None):
         if on_frame:
             on_frame(k, slam)
         if imu and k % 3 == 2:
-            imu_out.append(slam.update_pose(*imu_call(k)))
+            imu_out.append(slam.update_pose(*imu_call(seq, k)))
     return slam, np.array(imu_out, np.float32).reshape(-1, 6)
 
 
