@@ -1,22 +1,27 @@
 #!/usr/bin/env python
 """bench.py — tracked stereo frames/s of the tracking hot path (BASELINE.json metric) on N B200s.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--streams S] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--streams S] [--frames-per-step F] [--impl reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 Workload (config.workload): BASELINE.json configs[2] — EuRoC-shaped synthetic stereo, 752x480, 4-level pyramid,
-30x24 grid (~430-500 keypoints/frame) — as S independent sequences per GPU (configs[4] = 64 sequences is
-S=8 on 8 GPUs).  configs[0]/[1] (Blender videos) cannot run: the .mkv files are missing from the reference
-checkout (.MISSING_LARGE_BLOBS).  A *step* advances every sequence of every rank by one stereo frame
-(StereoSlam::new_image: pyramids -> sparse alignment -> KLT -> reprojection GN -> depth filter -> host
-bookkeeping, keyframe creation when the reference would create one).
+30x24 grid (~430-500 keypoints/frame) — as S independent sequences per GPU.  configs[0]/[1] (Blender videos) cannot run:
+the .mkv files are missing from the reference checkout (.MISSING_LARGE_BLOBS).  A *step* advances every sequence of
+every rank by F stereo frames (default 100: `--steps 20` times 64 000 frames per GPU, more than a second) through
+StereoSlam::new_image: pyramids -> sparse alignment -> KLT -> reprojection GN -> depth filter -> host bookkeeping,
+keyframe creation when the reference would create one (the 64 rendered frames of a sequence cross the second keyframe;
+`keyframes_in_timed_region` says how many fell into the timed steps).  One svo_slam_run_many call per step: the per-frame
+host work is native code on `--host-threads` threads, Python runs once per step.
 
-  value  : whole-job frames/s with the stereo frames already resident in HBM (svo_slam_new_image_device_begin)
+  value  : whole-job frames/s with the stereo frames already resident in HBM
   e2e    : the same through the reference-facing call with HOST (pinned) buffers; every frame crosses PCIe inside the timed
-           region (the ingest kernel reads the page-locked images over PCIe, results come back by DMA)
+           region (the ingest kernel reads the page-locked images over PCIe, the results come back to host memory)
+  aggregate : Mpatches/s (alignment) and Mwindows/s (KLT) of the whole job, from the library's work counters
+  configs4  : BASELINE configs[4] literally — 64 streams in total, partitioned over the N GPUs (64 / N per GPU)
   roofline / single_stream / kernels : one sequence, per-stage CUDA events on the launching stream
-  cpu_baseline : the CPU oracle ("port" of the reference's single-threaded path) on one host core, bounded sample
-  --impl reference : the same workload on the CPU oracle with all host threads (one sequence per thread)
+  cpu_baseline : the reference itself (oracle/_ref: its unmodified sources built against oracle/cvshim) on one host core
+  --impl reference : the same workload on the reference itself, one process per host core (the library is single-threaded
+           and keeps process-global state), every step a bounded sample (F/12 frames per sequence)
 """
 import argparse
 import ctypes as C
@@ -26,6 +31,7 @@ import subprocess
 import sys
 import threading
 import time
+import multiprocessing as mp
 
 import numpy as np
 
@@ -40,6 +46,7 @@ if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
 from stereo_svo_slam_b200 import synth  # noqa: E402
 
 CFG = "C3"
+PROFILE_FILE = "r02_kernel_profile.json"   # per-kernel ncu figures of this round (tools/ncu_profile_json.py)
 METRIC = "tracked_stereo_frames_per_s"
 UNIT = "frames/s"
 
@@ -172,84 +179,156 @@ def algorithmic_bytes(c, n_kps, evals_per_level, klt_levels=3):
 
 
 # --------------------------------------------------------------------------------------------- reference arm
-def run_oracle(frames, cfg, steps, warmup, threads, tri=lambda t: t):
+def _ref_kind():
+    from oracle import oracle as orc
+    return "reference" if orc.have_ref() else "port"
+
+
+def _ref_worker(args):
+    """One process = one host core: its share of the sequences on the reference itself (oracle/_ref), frame by frame."""
+    cfg, seeds, nframes, F, W, K, start_evt, ready_q, done_q = args
     from oracle import oracle as orc
     c = synth.CONFIGS[cfg]
-    S = frames.shape[0]
-    slams = [orc.OracleSlam(orc.CameraSettings(**synth.settings_dict(cfg)), c["width"], c["height"], tracing=False) for _ in range(S)]
+    frames = make_frames(cfg, seeds, nframes)
+    cs = orc.CameraSettings(**synth.settings_dict(cfg))
+    use_ref = orc.have_ref()
+    slams = [(orc.RefSlam(cs, c["width"], c["height"]) if use_ref else orc.OracleSlam(cs, c["width"], c["height"], tracing=False)) for _ in seeds]
 
-    def advance(s, k):
-        slams[s].new_image(frames[s, tri(k), 0], frames[s, tri(k), 1], k / 20.0)
+    def fresh(i):
+        if use_ref:
+            slams[i].close()
+            return orc.RefSlam(cs, c["width"], c["height"])
+        return orc.OracleSlam(cs, c["width"], c["height"], tracing=False)
 
-    def step(k):
-        if threads <= 1:
-            for s in range(S):
-                advance(s, k)
-        else:
-            ts = [threading.Thread(target=advance, args=(s, k)) for s in range(S)]
-            for t in ts:
-                t.start()
-            for t in ts:
-                t.join()
+    def step(k0):
+        for k in range(k0, k0 + F):
+            f = k % nframes
+            for i in range(len(slams)):
+                if f == 0 and k > 0:          # the stream starts its next sequence: a new StereoSlam, like the b200 arm's reset
+                    slams[i] = fresh(i)
+                slams[i].new_image(frames[i, f, 0], frames[i, f, 1], f / 20.0)
+    for w in range(W):
+        step(w * F)
+    ready_q.put(1)
+    start_evt.wait()
+    t0 = time.time()
+    for k in range(K):
+        step((W + k) * F)
+    done_q.put((t0, time.time(), len(seeds) * F * K))
 
-    for k in range(warmup):
-        step(k)
+
+def run_reference(cfg, seeds, nframes, F, W, K, procs):
+    """frames/s of the reference on `procs` host cores; returns (fps, seconds, kind)."""
+    ctx = mp.get_context("spawn")
+    groups = [seeds[p::procs] for p in range(procs) if seeds[p::procs]]
+    start_evt, ready_q, done_q = ctx.Event(), ctx.Queue(), ctx.Queue()
+    ps = [ctx.Process(target=_ref_worker, args=((cfg, g, nframes, F, W, K, start_evt, ready_q, done_q),)) for g in groups]
+    for p_ in ps:
+        p_.start()
+    for _ in ps:
+        ready_q.get()
+    start_evt.set()
+    res = [done_q.get() for _ in ps]
+    for p_ in ps:
+        p_.join()
+    seconds = max(r[1] for r in res) - min(r[0] for r in res)
+    return sum(r[2] for r in res) / seconds, seconds, _ref_kind()
+
+
+def run_reference_one_core(frames, cfg, n, warm):
+    """the reference on ONE host core over the first sequence: frames/s over n frames after `warm` warm-up frames"""
+    from oracle import oracle as orc
+    c = synth.CONFIGS[cfg]
+    cs = orc.CameraSettings(**synth.settings_dict(cfg))
+    sl = orc.RefSlam(cs, c["width"], c["height"]) if orc.have_ref() else orc.OracleSlam(cs, c["width"], c["height"], tracing=False)
+    for k in range(warm):
+        sl.new_image(frames[0, k, 0], frames[0, k, 1], k / 20.0)
     t0 = time.perf_counter()
-    for k in range(warmup, warmup + steps):
-        step(k)
+    for k in range(warm, warm + n):
+        sl.new_image(frames[0, k, 0], frames[0, k, 1], k / 20.0)
     dt = time.perf_counter() - t0
-    return S * steps / dt, dt, slams
+    return n / dt, dt, _ref_kind()
+
+
+def stream_seeds(rank, world, streams_per_gpu, total_streams=0):
+    """Which sequences (by seed) a rank owns.  Weak scaling: streams_per_gpu sequences per GPU, seeds 1000 + rank*S + s.
+    BASELINE configs[4] (total_streams > 0): that many sequences in total, stream s on GPU s mod N, seeds 1000 + s.
+    Sequences are independent: no rank ever needs another rank's data (replicas only)."""
+    if total_streams > 0:
+        return [1000 + s for s in range(total_streams) if s % world == rank]
+    return [1000 + rank * streams_per_gpu + s for s in range(streams_per_gpu)]
+
+
+def aggregate_ranks(seconds, counters, all_reduce=None):
+    """Whole-job figures from per-rank ones: the time is the MAX over ranks, the work counters are SUMMED.
+    all_reduce(list_of_floats, "max" | "sum") -> list; None for a single process."""
+    if all_reduce is None:
+        return seconds, list(counters)
+    return all_reduce([seconds], "max")[0], all_reduce(list(counters), "sum")
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--frames-per-step", type=int, default=100, help="frames every sequence advances per step")
     ap.add_argument("--frames", type=int, default=64, help="rendered frames per sequence (played forward/backward: continuous motion)")
-    ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--streams", type=int, default=32, help="independent sequences per GPU")
-    ap.add_argument("--host-threads", type=int, default=0, help="host threads driving the sequences of one GPU (0 = min(16, cores / ranks))")
+    ap.add_argument("--streams", type=int, default=32, help="independent sequences per GPU (weak scaling)")
+    ap.add_argument("--total-streams", type=int, default=0, help="BASELINE configs[4]: this many sequences in total, stream s on GPU s mod N (strong scaling)")
+    ap.add_argument("--host-threads", type=int, default=0, help="native host threads driving the sequences of one GPU (0 = min(16, cores / ranks))")
     ap.add_argument("--align-cluster", type=int, default=0, choices=[0, 1, 2, 4, 8, 16],
                     help="SMs per alignment solve in the multi-sequence runs (measured: 8 and 4 give the same aggregate throughput, 1 is 20 %% slower)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs4", action="store_true")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     W = max(a.warmup, 3)
-    K, S = a.steps, a.streams
+    K, F = a.steps, max(1, a.frames_per_step)
     if a.host_threads <= 0:
         a.host_threads = max(1, min(16, (os.cpu_count() or 1) // max(1, world)))
     c = synth.CONFIGS[CFG]
-    nframes = min(a.frames, W + K)   # rendered frames; step t shows frame tri(t) = forward/backward sweep (continuous motion)
+    nframes = max(2, a.frames)   # rendered frames; frame t of a sequence shows rendered frame tri(t): forward/backward sweep
 
     def tri(t):
-        if nframes <= 1:
-            return 0
         p = t % (2 * nframes - 2)
         return p if p < nframes else 2 * nframes - 2 - p
+
+    def seeds_for(rank_, world_, total):
+        return stream_seeds(rank_, world_, a.streams, total)
+    seeds = seeds_for(rank, world, a.total_streams)
+    S = len(seeds)
     config = {"workload": f"BASELINE configs[2] EuRoC-shaped synthetic 752x480 ({CFG}: 4-level pyramid, 30x24 grid), "
-                          f"{S} independent sequences per GPU (configs[4] = 8 GPUs x S); configs[0]/[1] blocked: .mkv missing",
-              "sequences_per_gpu": S, "host_threads_per_gpu": a.host_threads, "rendered_frames_per_sequence": nframes,
-              "playback": "forward/backward sweep over the rendered frames (continuous camera motion, strictly increasing timestamps)", "seeds": "1000 + rank*S + s",
-              "l2_hygiene": "every step touches new frames (0.72 MB/sequence) and all sequences' pyramids; single-stream working "
-                            "set (<3 MB) is L2 resident by nature of the path — kernels are latency/ALU bound (DESIGN.md)"}
+                          + (f"configs[4]: {a.total_streams} independent sequences in total, stream s on GPU s mod N" if a.total_streams else
+                             f"{a.streams} independent sequences per GPU") + "; configs[0]/[1] blocked: .mkv missing",
+              "sequences_per_gpu": S, "frames_per_step_per_sequence": F, "host_threads_per_gpu": a.host_threads,
+              "rendered_frames_per_sequence": nframes,
+              "playback": "a stream is a succession of finite sequences (BASELINE configs[4] streams are 200 frames long): the rendered frames "
+                          "played forward, then the stream restarts with a fresh tracker on the same device resources (svo_slam_reset) — every "
+                          "pass creates keyframe #1 at its frame 0 and keyframe #2 around frame 46, like the reference would",
+              "seeds": "1000 + s, s mod N == rank" if a.total_streams else "1000 + rank*S + s",
+              "l2_hygiene": "every step touches new frames (0.72 MB per frame and sequence: 2.3 GB per step and GPU, far beyond the 126 MB L2) "
+                            "and all sequences' pyramids; a single sequence's working set (<3 MB) is L2 resident by nature of the path — "
+                            "the kernels are latency/issue bound (DESIGN.md)"}
 
     if a.impl == "reference":
-        # the reference's own CPU implementation of the path = the oracle port (the reference library cannot be built
-        # here: no OpenCV C++ SDK), all host threads, rank 0 only.
+        # the reference's own CPU implementation of the path: oracle/_ref (its unmodified sources), one process per host core,
+        # rank 0 only.  A step is a bounded sample of the b200 arm's step: F/12 frames per sequence.
         if rank != 0:
             return
-        threads = min(S, os.cpu_count() or 1)
-        k_ref, w_ref = min(K, 60), min(W, 3)
-        frames = make_frames(CFG, [1000 + s for s in range(S)], nframes)
-        fps, dt, _ = run_oracle(frames, CFG, k_ref, w_ref, threads, tri)
-        print(json.dumps({"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": a.gpus, "steps": k_ref, "warmup": w_ref,
-                          "ms_per_step": 1e3 * dt / k_ref, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                          "dtype": "u8/f32", "data": "synthetic", "config": config,
-                          "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
-                                           "sample": f"{S} sequences x {k_ref} frames after {w_ref} warm-up frames, one sequence per host thread"},
+        procs = min(S, os.cpu_count() or 1)
+        f_ref = max(1, F // 12)
+        fps, seconds, kind = run_reference(CFG, seeds, nframes, f_ref, W, K, procs)
+        sample = (f"{S} sequences x {K} steps x {f_ref} frames (a step of the b200 arm is {F} frames per sequence) after {W} warm-up steps, "
+                  f"one process per host core ({procs}); " + ("oracle/_ref = the reference's unmodified sources built against oracle/cvshim"
+                                                             if kind == "reference" else "oracle port (oracle/_ref not built)"))
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": a.gpus, "steps": K, "warmup": W,
+                          "ms_per_step": 1e3 * seconds / K, "higher_is_better": True, "scaling": "strong" if a.total_streams else "weak",
+                          "vs_baseline": None, "dtype": "u8/f32", "data": "synthetic", "config": config,
+                          "cpu_baseline": {"value": fps, "unit": UNIT, "cores": procs, "kind": kind, "sample": sample},
                           "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
@@ -262,11 +341,8 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    seeds = [1000 + rank * S + s for s in range(S)]
-    frames_np = make_frames(CFG, seeds, nframes)                       # [S][F][2][H][W]
-    host = torch.from_numpy(frames_np).pin_memory()                    # pinned host inputs (e2e)
-    dev = host.to("cuda", non_blocking=False)                          # HBM-resident inputs (value)
     H_, W_ = c["height"], c["width"]
+    img = H_ * W_
     settings = capi.CameraSettings(**synth.settings_dict(CFG))
     lib = capi.lib()
 
@@ -276,140 +352,120 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def run(mode, clocks=None):
-        slams = [StereoSlam(settings, W_, H_, device=local_rank) for _ in range(S)]
+    def all_reduce(vals, op):
+        t = torch.tensor(vals, device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX if op == "max" else dist.ReduceOp.SUM)
+        return t.tolist()
+
+    def load_inputs(seed_list):
+        fr = make_frames(CFG, seed_list, nframes)                      # [S][F][2][H][W]
+        h = torch.from_numpy(fr).pin_memory()                          # pinned host inputs (e2e)
+        return fr, h, h.to("cuda", non_blocking=False)                 # HBM-resident inputs (value)
+
+    def run(mode, host, dev, n_seq, clocks=None):
+        """W warm-up steps, then K timed steps of F frames per sequence; returns whole-rank counters and the time (max over ranks)"""
+        slams = [StereoSlam(settings, W_, H_, device=local_rank) for _ in range(n_seq)]
         for sl in slams:   # many sequences share the GPU: SM time per frame matters, not the latency of one solve
             sl.set_align_cluster(a.align_cluster)
-        hptr = host.data_ptr()
-        dptr = dev.data_ptr()
-        img = H_ * W_
-        launches0 = [None] * S
+        base = dev.data_ptr() if mode == "device" else host.data_ptr()
+        handles = (C.c_void_p * n_seq)(*[sl._h for sl in slams])
+        bad = C.c_int(-1)
         step_times = []
+        # the frame tables of all steps (pointers into the resident frame tensor, timestamps) are laid out before the clock starts
+        seq_off = (np.arange(n_seq, dtype=np.int64) * nframes)[:, None]
+        tables = []
+        for k in range(W + K):
+            t = k * F + np.arange(F, dtype=np.int64)
+            fr = (t % nframes)[None, :]                       # a stream = the rendered sequence over and over, each pass a new sequence
+            left = (base + (seq_off + fr) * 2 * img).astype(np.uint64).reshape(-1)
+            right = left + np.uint64(img)
+            ts = np.tile(((t % nframes) / 20.0).astype(np.float32), n_seq)
+            rs = np.tile(((t % nframes == 0) & (t > 0)).astype(np.uint8), n_seq)
+            tables.append((np.ascontiguousarray(left), np.ascontiguousarray(right), np.ascontiguousarray(ts), np.ascontiguousarray(rs)))
 
-        T = max(1, min(a.host_threads, S))
-        groups = [list(range(t, S, T)) for t in range(T)]
+        def step(k):
+            lp, rp, ts, rs = tables[k]
+            t0 = time.perf_counter()
+            rc = lib.svo_slam_run_many_restart(handles, n_seq, F, lp.ctypes.data_as(C.c_void_p), rp.ctypes.data_as(C.c_void_p), C.c_size_t(W_),
+                                               C.c_size_t(W_), ts.ctypes.data_as(C.c_void_p), rs.ctypes.data_as(C.c_void_p),
+                                               1 if mode == "device" else 0, a.host_threads, C.byref(bad))
+            step_times.append(time.perf_counter() - t0)
+            if rc:
+                raise RuntimeError(f"sequence {bad.value}: " + lib.svo_slam_last_error(slams[max(bad.value, 0)]._h).decode())
 
-        def advance(group, k):
-            for s in group:
-                sl = slams[s]
-                off = ((s * nframes + tri(k)) * 2) * img
-                if mode == "device":
-                    rc = lib.svo_slam_new_image_device_begin(sl._h, C.c_void_p(dptr + off), C.c_size_t(W_), C.c_void_p(dptr + off + img),
-                                                             C.c_size_t(W_), C.c_float(k / 20.0))
-                else:
-                    rc = lib.svo_slam_new_image_begin(sl._h, C.c_void_p(hptr + off), C.c_size_t(W_), C.c_void_p(hptr + off + img),
-                                                      C.c_size_t(W_), C.c_float(k / 20.0))
-                if rc:
-                    raise RuntimeError(lib.svo_slam_last_error(sl._h).decode())
-            for s in group:
-                rc = lib.svo_slam_new_image_end(slams[s]._h)
-                if rc:
-                    raise RuntimeError(lib.svo_slam_last_error(slams[s]._h).decode())
-
-        def drive(k0, k1):
-            """every host thread advances its own sequences frame by frame (ctypes releases the GIL)"""
-            errs = []
-
-            def work(group):
-                try:
-                    torch.cuda.set_device(local_rank)
-                    for k in range(k0, k1):
-                        t_ = time.perf_counter()
-                        advance(group, k)
-                        step_times.append((time.perf_counter() - t_, k, group[0]))
-                except Exception as e:  # noqa: BLE001
-                    errs.append(e)
-            if T == 1:
-                work(groups[0])
-            else:
-                ts = [threading.Thread(target=work, args=(g,)) for g in groups]
-                for t in ts:
-                    t.start()
-                for t in ts:
-                    t.join()
-            if errs:
-                if os.environ.get("SVO_DEBUG_MARKS"):
-                    b64 = (C.c_int * 64)()
-                    for s_, sl_ in enumerate(slams):
-                        lib.svo_debug_marks(C.c_void_p(lib.svo_slam_ctx(sl_._h)), b64)
-                        if b64[16]:
-                            sys.stderr.write(f"[align timeout] mode {mode} seq {s_}: {list(b64)}\n")
-                raise errs[0]
-
-        wd_sec = float(os.environ.get("BENCH_WATCHDOG", "0"))
-        wd = {"stop": False}
-        if wd_sec > 0:   # developer aid: report where every sequence stands if the run stops making progress
-            def watchdog():
-                last, t_last = -1, time.perf_counter()
-                while not wd["stop"]:
-                    time.sleep(1.0)
-                    cur = len(step_times)
-                    if cur != last:
-                        last, t_last = cur, time.perf_counter()
-                    elif time.perf_counter() - t_last > wd_sec:
-                        buf16 = (C.c_int * 64)()
-                        for s_, sl_ in enumerate(slams):
-                            if getattr(sl_, "_h", None):
-                                lib.svo_debug_marks(C.c_void_p(lib.svo_slam_ctx(sl_._h)), buf16)
-                                sys.stderr.write(f"[watchdog] mode {mode} seq {s_}: marks {list(buf16)}\n")
-                        sys.stderr.write(f"[watchdog] steps done {cur}, per-thread last k: {sorted((g, k) for _, k, g in step_times[-64:])[-16:]}\n")
-                        sys.stderr.flush()
-                        os._exit(3)
-            threading.Thread(target=watchdog, daemon=True).start()
-        drive(0, W)
+        def totals():
+            tot = np.zeros(8, np.int64)
+            cnt = C.c_longlong()
+            nl = 0
+            for sl in slams:
+                tot += np.array(list(sl.total_counters().values()), np.int64)
+                lib.svo_launch_count(C.c_void_p(lib.svo_slam_ctx(sl._h)), C.byref(cnt))
+                nl += cnt.value
+            return tot, nl
+        for k in range(W):
+            step(k)
         step_times.clear()
-        cnt = C.c_longlong()
-        for s, sl in enumerate(slams):
-            lib.svo_launch_count(C.c_void_p(lib.svo_slam_ctx(sl._h)), C.byref(cnt))
-            launches0[s] = cnt.value
+        tot0, nl0 = totals()
         barrier()
         if clocks:
             clocks.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         t0 = time.perf_counter()
-        drive(W, W + K)
+        for k in range(W, W + K):
+            step(k)
         torch.cuda.synchronize()
         e1.record()
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
-        wd["stop"] = True
         dev_s = e0.elapsed_time(e1) / 1e3
         ck = clocks.stop() if clocks else None
-        nl = 0
-        for s, sl in enumerate(slams):
-            lib.svo_launch_count(C.c_void_p(lib.svo_slam_ctx(sl._h)), C.byref(cnt))
-            nl += cnt.value - launches0[s]
+        tot1, nl1 = totals()
+        d = tot1 - tot0
         kps = int(np.mean([len(sl.get_frame().kps) for sl in slams]))
-        nkf = int(np.sum([sl.keyframe_count() for sl in slams]))
-        poses = np.stack([sl.pose() for sl in slams])
         for sl in slams:
             sl.close()
-        t = torch.tensor([max(wall, dev_s)], device="cuda", dtype=torch.float64)
-        ln = torch.tensor([nl], device="cuda", dtype=torch.int64)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dist.all_reduce(ln, op=dist.ReduceOp.SUM)
-        nl = int(ln.item())
+        seconds, sums = aggregate_ranks(max(wall, dev_s), [float(x) for x in d] + [float(nl1 - nl0)], all_reduce if world > 1 else None)
         st_ = sorted(step_times)
-        trace = {"host_step_ms_p50": 1e3 * st_[len(st_) // 2][0], "host_step_ms_p99": 1e3 * st_[int(len(st_) * 0.99)][0],
-                 "host_step_ms_max": 1e3 * st_[-1][0], "slowest_steps": [(round(1e3 * d, 2), k, g) for d, k, g in st_[-4:]]} if st_ else {}
-        return dict(seconds=float(t.item()), launches=nl, kps=kps, keyframes=nkf, poses=poses, clocks=ck, trace=trace)
+        trace = {"host_step_ms_p50": 1e3 * st_[len(st_) // 2], "host_step_ms_max": 1e3 * st_[-1], "host_us_per_frame_p50": 1e6 * st_[len(st_) // 2] / (n_seq * F)} if st_ else {}
+        return dict(seconds=seconds, frames=sums[0], tracking_frames=sums[1], keyframes=sums[2], patches=sums[3], windows=sums[4], keypoints=sums[5],
+                    launches=int(sums[8]), kps=kps, clocks=ck, trace=trace)
 
+    def summarize(r):
+        fps = r["frames"] / r["seconds"]
+        return {"value": fps, "mpatches_per_s": r["patches"] / r["seconds"] / 1e6, "mwindows_per_s": r["windows"] / r["seconds"] / 1e6,
+                "keyframes_in_timed_region": int(r["keyframes"]), "frames_in_timed_region": int(r["frames"]), "seconds": r["seconds"]}
+
+    frames_np, host, dev = load_inputs(seeds)
     if os.environ.get("BENCH_ONLY") == "host":     # developer switch: end-to-end run only
-        r = run("host")
+        r = run("host", host, dev, S)
         if rank == 0:
-            print(json.dumps({"e2e": S * K * world / r["seconds"], "trace": r["trace"]}))
+            print(json.dumps({"e2e": summarize(r), "trace": r["trace"]}))
         return
-    r_dev = run("device", None if os.environ.get("BENCH_NO_NVML") else ClockSampler(local_rank))
+    r_dev = run("device", host, dev, S, None if os.environ.get("BENCH_NO_NVML") else ClockSampler(local_rank))
     if os.environ.get("BENCH_ONLY") == "device":   # developer switch: whole-job device-resident run only
         if rank == 0:
-            print(json.dumps({"value": S * K * world / r_dev["seconds"], "trace": r_dev["trace"]}))
+            print(json.dumps({"value": summarize(r_dev), "trace": r_dev["trace"]}))
         return
-    r_e2e = run("host")
-    total_frames = S * K * world
-    value = total_frames / r_dev["seconds"]
-    e2e = total_frames / r_e2e["seconds"]
+    r_e2e = run("host", host, dev, S)
+    value, e2e = r_dev["frames"] / r_dev["seconds"], r_e2e["frames"] / r_e2e["seconds"]
+    n_kps_multi = r_dev["keypoints"] / max(r_dev["tracking_frames"], 1.0)
+
+    # ---------------- BASELINE configs[4] as stated: 64 streams in total over the N GPUs (strong scaling), same step definition
+    c4s = None
+    if not a.no_configs4 and not a.total_streams:
+        seeds64 = seeds_for(rank, world, 64)
+        if len(seeds64) == S and seeds64 == seeds:
+            fr64, h64, d64 = frames_np, host, dev
+        else:
+            del dev
+            fr64, h64, d64 = load_inputs(seeds64)
+        r64d = run("device", h64, d64, len(seeds64))
+        r64h = run("host", h64, d64, len(seeds64))
+        c4s = {"workload": "BASELINE configs[4]: 64 independent 752x480 streams in total, stream s on GPU s mod N (seeds 1000..1063)",
+               "streams_per_gpu": len(seeds64), "scaling": "strong", "device_resident": summarize(r64d), "e2e": summarize(r64h)}
+        del d64, h64
+        dev = None
 
     out = None
     if rank == 0:
@@ -417,8 +473,9 @@ def main():
         # frames, CUDA-graph replay): wall time per call and device time per frame (events around ingest .. D2H)
         sl = StereoSlam(settings, W_, H_, device=local_rank)
         host_np = host.numpy()
+        n1 = W + 200
         walls_g, gpu_g = [], []
-        for k in range(W + min(K, 200)):
+        for k in range(n1):
             t0 = time.perf_counter()
             sl.new_image(host_np[0, tri(k), 0], host_np[0, tri(k), 1], k / 20.0)
             walls_g.append(time.perf_counter() - t0)
@@ -431,7 +488,6 @@ def main():
         sl = StereoSlam(settings, W_, H_, device=local_rank)
         ctxp = C.c_void_p(lib.svo_slam_ctx(sl._h))
         lib.svo_set_profiling(ctxp, 1)
-        n1 = W + min(K, 200)
         stage = np.zeros((n1, 8), np.float32)
         cnt = np.zeros((n1, 8), np.float64)
         walls = []
@@ -452,15 +508,14 @@ def main():
         patches = cm[1] * (cm[2] + cm[3])          # (keypoint, level, evaluation) 4x4 patches per frame
         windows = cm[6]                            # (keypoint, level, LK iteration) 31x31 windows per frame
         peak, peak_src = peaks()
-        # DRAM traffic per launch of each kernel, from the committed `ncu --set full` capture (profiles/r01_traffic.json)
-        traffic_tbl = {}
+        prof = {}
         try:
-            traffic_tbl = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            prof = json.load(open(os.path.join(ROOT, "profiles", PROFILE_FILE)))
         except Exception:  # noqa: BLE001
             pass
 
         def traffic_of(kernel):
-            for name, rec in traffic_tbl.items():
+            for name, rec in prof.get("kernels", {}).items():
                 if name.startswith(kernel):
                     return rec.get("dram_bytes_per_launch")
             return None
@@ -476,6 +531,21 @@ def main():
             b = {0: ab["pyramids"], 1: ab["align"], 2: ab["klt"], 3: ab["refine"], 4: ab["ssd"], 5: ab["filter"], 6: 0}[i]
             kernels.append({"stage": nm, "ms": float(st[i]), "share": float(st[i] / max(st[7], 1e-9)), "algorithmic_bytes": int(b),
                             "achieved_gbs": float(b / (st[i] * 1e-3) / 1e9) if st[i] > 0 else None})
+        klt_fused_bytes = 6965 * n_kps             # SURVEY §8d primary definition (derivative-fused layout)
+        kernels[2]["achieved_gbs_survey_fused_layout"] = float(klt_fused_bytes / (st[2] * 1e-3) / 1e9) if st[2] > 0 else None
+        kernels[2]["algorithmic_bytes_survey_fused_layout"] = int(klt_fused_bytes)
+        # ---------------- the bound that applies: instruction issue.  A frame's warp instructions (ncu smsp__inst_executed.sum of every
+        # kernel of a frame, profiles/) over the chip's issue rate (148 SMs x 4 schedulers x 1 instruction per clock) is the least
+        # time a frame can take on a saturated GPU however well latencies are hidden; achieved = what a frame takes at saturation.
+        sm_clock = (r_dev["clocks"] or {}).get("sm_mhz") or 1965.0
+        inst_per_frame = float(prof.get("warp_instructions_per_frame", 8.0e6))
+        floor_us = inst_per_frame / (148 * 4 * sm_clock * 1e6) * 1e6
+        per_gpu_fps = value / world
+        issue = {"bound": "issue", "kernel": "whole frame (8 kernels)", "achieved": per_gpu_fps, "peak": 1e6 / floor_us, "unit": "frames/s per GPU",
+                 "frac": per_gpu_fps * floor_us / 1e6, "us_per_frame_at_saturation": 1e6 / per_gpu_fps, "issue_floor_us_per_frame": floor_us,
+                 "warp_instructions_per_frame": inst_per_frame, "sm_mhz": sm_clock,
+                 "source": f"profiles/{PROFILE_FILE} (ncu smsp__inst_executed.sum per kernel of one C3 tracking frame)" if prof else
+                           "profiles/r01 figure (8.0 M warp instructions per frame)"}
         # PCIe context for e2e: what the link delivers to SM-driven (zero-copy) reads of page-locked memory, measured live
         pcie = {}
         try:
@@ -492,18 +562,27 @@ def main():
             pcie = {"bytes_per_frame": int(per_frame), "achieved_gbs": float(e2e / world * per_frame / 1e9), "link_peak_gbs": float(best),
                     "frac": float(e2e / world * per_frame / 1e9 / best) if best > 0 else None,
                     "note": "per GPU; link_peak = zero-copy read of a 64 MB page-locked buffer by 148 CTAs (one stream, sequential), "
-                            "the e2e traffic is 32 interleaved streams of 722 KB frames plus the keypoint blocks in both directions"}
+                            "the e2e traffic is the interleaved streams' 722 KB frames plus the keypoint blocks in both directions"}
         except Exception as e:  # noqa: BLE001
             pcie = {"error": str(e)}
+        sd, se = summarize(r_dev), summarize(r_e2e)
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-               "ms_per_step": 1e3 * r_dev["seconds"] / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "ms_per_step": 1e3 * r_dev["seconds"] / K, "higher_is_better": True, "scaling": "strong" if a.total_streams else "weak", "vs_baseline": None,
                "dtype": "u8/f32", "data": "synthetic", "config": config,
-               "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(S * 2 * H_ * W_ + S * n_kps * 45),
-                       "d2h_bytes_per_step": int(S * n_kps * 90), "ms_per_step": 1e3 * r_e2e["seconds"] / K, "pcie": pcie},
+               "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(S * F * (2 * H_ * W_ + n_kps_multi * 45)),
+                       "d2h_bytes_per_step": int(S * F * n_kps_multi * 90), "ms_per_step": 1e3 * r_e2e["seconds"] / K,
+                       "mpatches_per_s": se["mpatches_per_s"], "mwindows_per_s": se["mwindows_per_s"],
+                       "keyframes_in_timed_region": se["keyframes_in_timed_region"], "pcie": pcie},
+               "aggregate": {"frames_per_s": value, "mpatches_per_s": sd["mpatches_per_s"], "mwindows_per_s": sd["mwindows_per_s"],
+                             "n_gpus": world, "note": "whole job, device-resident run; patch = (keypoint, level, evaluation) 4x4 residual patch of the "
+                                                      "alignment, window = (keypoint, level, LK iteration) 31x31 window (SURVEY.md §8d)"},
+               "keyframes_in_timed_region": sd["keyframes_in_timed_region"], "frames_in_timed_region": sd["frames_in_timed_region"],
+               "timed_seconds": r_dev["seconds"],
                "gpu_launches": int(r_dev["launches"]),
                "host_step_trace": {"value": r_dev["trace"], "e2e": r_e2e["trace"]},
                "clocks": r_dev["clocks"],
-               "keypoints_per_frame": r_dev["kps"], "keyframes_created": r_dev["keyframes"],
+               "keypoints_per_frame": r_dev["kps"],
+               "configs4": c4s,
                "single_stream": {"frames_per_s": 1.0 / wall_graph, "ms_per_frame_wall": 1e3 * wall_graph, "ms_per_frame_gpu": gpu_graph,
                                  "ms_per_frame_gpu_staged_events": float(st[7]), "ms_per_frame_wall_staged_events": 1e3 * med_wall,
                                  "pose_iter_latency_us": float(1e3 * st[1] / max(cm[2] + cm[3], 1.0)),
@@ -512,13 +591,13 @@ def main():
                                  "mwindows_per_s": float(windows / (st[2] * 1e-3) / 1e6) if st[2] > 0 else None,
                                  "note": "one sequence, synchronous new_image calls with page-locked host frames (what the reference app does); "
                                          "*_staged_events: same with a CUDA event between the stages (kernel-by-kernel launches, source of the stage table)"},
-               "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                            "frac": achieved / peak,
-                            "traffic": traffic_of(stage_kernel.get(dom, "?")),
-                            "traffic_source": "profiles/r01_traffic.json (ncu --set full, dram__bytes_read+write per launch)",
-                            "algorithmic_bytes_per_launch": int(dom_bytes), "peak_source": peak_src,
-                            "limiter": "dependency latency / integer+fp32 ALU, not HBM: the per-frame working set (<3 MB) is L2-resident "
-                                       "(SURVEY.md §8d); see profiles/ for the ncu evidence"},
+               "roofline": dict(issue, hbm={"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                                            "frac": achieved / peak, "traffic": traffic_of(stage_kernel.get(dom, "?")),
+                                            "traffic_source": f"profiles/{PROFILE_FILE} (ncu --set full, dram__bytes_read+write per launch)",
+                                            "algorithmic_bytes_per_launch": int(dom_bytes), "peak_source": peak_src,
+                                            "note": "the dominant kernel of a lone sequence against the HBM roofline, for the record: the per-frame "
+                                                    "working set (<3 MB) is L2 resident, the kernel is bound by dependent-issue latency (SURVEY.md §8d)"},
+                                traffic=traffic_of(stage_kernel.get(dom, "?"))),
                "kernels": kernels}
         if world == 1 and not os.environ.get("BENCH_NO_C4"):
             # ---------------- BASELINE configs[3]: high-density stress (1280x720, 5 levels, ~3-4k keypoints), one sequence
@@ -544,13 +623,15 @@ def main():
                                 "mpatches_per_s": float(cn4[1] * (cn4[2] + cn4[3]) / (st4[1] * 1e-3) / 1e6) if st4[1] > 0 else None,
                                 "mwindows_per_s": float(cn4[6] / (st4[2] * 1e-3) / 1e6) if st4[2] > 0 else None,
                                 "align_gbs": float(120 * cn4[1] * (cn4[2] + cn4[3]) / (st4[1] * 1e-3) / 1e9) if st4[1] > 0 else None,
-                                "klt_gbs": float((3 * 6144 + 29) * cn4[0] / (st4[2] * 1e-3) / 1e9) if st4[2] > 0 else None}
+                                "klt_gbs_materialised_derivative_layout": float((3 * 6144 + 29) * cn4[0] / (st4[2] * 1e-3) / 1e9) if st4[2] > 0 else None,
+                                "klt_gbs_survey_fused_layout": float(6965 * cn4[0] / (st4[2] * 1e-3) / 1e9) if st4[2] > 0 else None}
         if not a.no_cpu_baseline and world == 1:
             kb, wb = 30, 3
-            fps, dt, _ = run_oracle(frames_np[:1], CFG, kb, wb, 1, tri)
-            out["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": 1, "kind": "port",
-                                   "sample": f"1 sequence, {kb} frames after {wb} warm-up (oracle = single-threaded "
-                                             "restatement of the reference; the reference library is single-threaded)"}
+            fps, dt, kind = run_reference_one_core(frames_np, CFG, kb, wb)
+            out["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": 1, "kind": kind,
+                                   "sample": f"1 sequence, {kb} frames after {wb} warm-up frames on one host core ("
+                                             + ("oracle/_ref = the reference's unmodified sources built against oracle/cvshim" if kind == "reference"
+                                                else "oracle port; oracle/_ref not built") + "; the reference library is single-threaded)"}
         print(json.dumps(out, default=lambda o: float(o) if isinstance(o, (np.floating,)) else (int(o) if isinstance(o, np.integer) else str(o))))
     if world > 1:
         dist.barrier()

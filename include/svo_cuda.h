@@ -58,6 +58,9 @@ typedef struct svo_ctx svo_ctx;
 int svo_ctx_create(const svo_camera_settings *settings, int device, int width, int height, int max_keypoints,
                    svo_ctx **out);
 int svo_ctx_destroy(svo_ctx *ctx);
+/* back to an empty sequence: all image sets and keyframes are given back, keyframe tables and template cache rewound; device
+ * memory, streams and captured frame graphs are kept (a new StereoSlam on the same camera without a single allocation) */
+int svo_ctx_reset(svo_ctx *ctx);
 const char *svo_last_error(svo_ctx *ctx); /* ctx may be NULL: last error of a failed svo_ctx_create */
 int svo_device_count(void);
 
@@ -270,6 +273,9 @@ int svo_slam_create(const svo_camera_settings *settings, int device, int width, 
 int svo_slam_create_with_capacity(const svo_camera_settings *settings, int device, int width, int height, int max_keypoints,
                                   svo_slam **out);
 int svo_slam_destroy(svo_slam *s);
+/* a fresh StereoSlam on the same camera settings (frame, keyframes, trajectory, motion filter, counters of the sequence all
+ * start over; keyframe ids restart at 0) that keeps every device resource of the old one: the next image is a first image */
+int svo_slam_reset(svo_slam *s);
 const char *svo_slam_last_error(svo_slam *s);
 /* StereoSlam::new_image (stereo_slam.cpp:123-271) */
 int svo_slam_new_image(svo_slam *s, const uint8_t *left, size_t left_stride, const uint8_t *right, size_t right_stride,
@@ -305,6 +311,25 @@ int svo_slam_last_stats(svo_slam *s, float *gpu_ms, int *launches, int *keyframe
  * evaluations, alignment gradient evaluations, refinement cost evaluations, refinement gradient evaluations,
  * LK iterations summed over keypoints and levels, keypoints tracked by LK (status 1)} */
 int svo_slam_last_counters(svo_slam *s, long long *out8);
+/* cumulative since creation: {frames, tracking frames, keyframes created, alignment patches (keypoint x evaluation),
+ * LK windows (keypoint x level x iteration), keypoints summed over tracking frames, alignment evaluations, refinement
+ * evaluations} — the numerators of frames/s, Mpatches/s and Mwindows/s */
+int svo_slam_total_counters(svo_slam *s, long long *out8);
+/* n independent sequences advanced by n_frames frames each in ONE call (StereoSlam::new_image for every (sequence, frame)):
+ * left[i * n_frames + f] / right[...] / time_stamps[...] are frame f of sequence i (host pointers, or device pointers with
+ * on_device != 0; one row stride for all).  `workers` host threads share the sequences (worker t owns sequences t, t + workers,
+ * ...) and each walks its sequences through their frames on its own — no barrier between frames, the per-frame work of the
+ * host (packing, launches, bookkeeping, keyframe creation) is native code on as many cores as the caller grants.  Frames of
+ * one sequence are processed in order; results are those of n_frames svo_slam_new_image calls per sequence.  On failure the
+ * first error code is returned, *failed_sequence (may be NULL) names the sequence, its message is in svo_slam_last_error. */
+int svo_slam_run_many(svo_slam *const *slams, int n, int n_frames, const uint8_t *const *left, const uint8_t *const *right,
+                      size_t left_stride, size_t right_stride, const float *time_stamps, int on_device, int workers,
+                      int *failed_sequence);
+/* same, for streams made of many finite sequences: restart[i * n_frames + f] != 0 (restart may be NULL) means frame f of
+ * stream i is the FIRST image of a new sequence — svo_slam_reset runs before it */
+int svo_slam_run_many_restart(svo_slam *const *slams, int n, int n_frames, const uint8_t *const *left, const uint8_t *const *right,
+                              size_t left_stride, size_t right_stride, const float *time_stamps, const uint8_t *restart,
+                              int on_device, int workers, int *failed_sequence);
 /* the device context behind the facade (for stage-level probes in tests) */
 svo_ctx *svo_slam_ctx(svo_slam *s);
 /* new keypoints that keyframes could not take because the device keypoint block (svo_keypoint_capacity) was full; the

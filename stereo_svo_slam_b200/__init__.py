@@ -8,4 +8,4 @@ Package layout (only what the path needs):
   build.py   in-tree nvcc build
 """
 from .capi import CameraSettings, SvoError  # noqa: F401
-from .slam import StereoSlam  # noqa: F401
+from .slam import StereoSlam, run_many  # noqa: F401

@@ -111,7 +111,7 @@ struct svo_ctx {
     KfTemplates *d_kf_tpl = nullptr;           // per keyframe: LK templates of the keypoints it introduced (svo_keyframe_set_templates)
     bool use_templates = true;
     std::vector<uint8_t *> tpl_chunks;         // bump-allocated, never freed before the context goes (keyframes live forever)
-    size_t tpl_chunk_bytes = 0, tpl_chunk_used = 0;
+    size_t tpl_chunk_bytes = 0, tpl_chunk_used = 0, tpl_first_bytes = 0;
     float *d_tpl_kps = nullptr;                // cell_cap * 2 floats: keyframe positions handed to klt_template_kernel
     int kf_cap = 0, kf_count = 0;
     std::vector<int> kf_slot;
@@ -374,7 +374,7 @@ extern "C" int svo_ctx_create(const svo_camera_settings *s, int device, int widt
         uint8_t *c = nullptr;
         CKC(cudaMalloc(&c, first));
         ctx->tpl_chunks.push_back(c);
-        ctx->tpl_chunk_bytes = first; ctx->tpl_chunk_used = 0;
+        ctx->tpl_chunk_bytes = first; ctx->tpl_chunk_used = 0; ctx->tpl_first_bytes = first;
     }
 #undef CKC
     *out = ctx;
@@ -417,6 +417,25 @@ extern "C" int svo_ctx_destroy(svo_ctx *ctx)
     for (int k = 0; k < 9; k++) if (ctx->sev[k]) cudaEventDestroy(ctx->sev[k]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
+    return SVO_OK;
+}
+
+// Start over with an empty sequence: every image set and keyframe is given back, the keyframe tables and the template cache
+// are rewound.  All device memory, the streams and the captured frame graphs stay (they refer to slots and tables by address).
+extern "C" int svo_ctx_reset(svo_ctx *ctx)
+{
+    if (!ctx) return SVO_ERR_INVALID;
+    ctx->err[0] = 0;
+    if (ctx->track_pending) { snprintf(ctx->err, sizeof(ctx->err), "svo_ctx_reset while a frame is in flight"); return SVO_ERR_STATE; }
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (auto &s : ctx->slots) { s.refcount = 0; s.derivs_valid = false; }
+    ctx->kf_count = 0;
+    ctx->kf_slot.clear();
+    if (ctx->d_kf_tpl) CK(cudaMemsetAsync(ctx->d_kf_tpl, 0, (size_t)ctx->kf_cap * sizeof(KfTemplates), ctx->stream));
+    while (ctx->tpl_chunks.size() > 1) { cudaFree(ctx->tpl_chunks.back()); ctx->tpl_chunks.pop_back(); }
+    ctx->tpl_chunk_used = 0;
+    if (!ctx->tpl_chunks.empty()) ctx->tpl_chunk_bytes = ctx->tpl_first_bytes;
     return SVO_OK;
 }
 

@@ -14,6 +14,8 @@
 #include <vector>
 #include <chrono>
 #include <cstdlib>
+#include <thread>
+#include <atomic>
 
 #include "../../include/svo_cuda.h"
 
@@ -223,6 +225,9 @@ struct svo_slam {
     std::vector<int> io_kfid, io_kpidx, io_inl, io_outl, io_kltit;
     std::vector<uint8_t> io_kltst;
     long long counters[8] = {0};
+    // since creation: frames, tracking frames, keyframes, alignment patches (keypoint x evaluation), LK windows (keypoint x level x
+    // iteration), keypoints summed over tracking frames, alignment evaluations, refinement evaluations
+    long long totals[8] = {0};
     std::vector<uint8_t> io_flags;
     bool pending = false;
     bool pending_first = false;
@@ -412,6 +417,8 @@ struct svo_slam {
         }
         svo_pose p = {frame->pose[0], frame->pose[1], frame->pose[2], frame->pose[3], frame->pose[4], frame->pose[5]};
         trajectory.push_back(p);
+        totals[0]++;
+        totals[2] += last_keyframe_created;
     }
 
     // Nothing of the instance's state changes unless the frame was enqueued: a failed call (bad stride, capacity, CUDA
@@ -513,6 +520,8 @@ struct svo_slam {
             for (int l = 0; l < 8; l++) { ce += io.align_evals[2 * l]; ge += io.align_evals[2 * l + 1]; }
             counters[0] = (long long)n; counters[1] = used; counters[2] = ce; counters[3] = ge;
             counters[4] = io.refine_evals[0]; counters[5] = io.refine_evals[1]; counters[6] = it; counters[7] = tr;
+            totals[1]++; totals[3] += used * (ce + ge); totals[4] += it; totals[5] += (long long)n; totals[6] += ce + ge;
+            totals[7] += io.refine_evals[0] + io.refine_evals[1];
         }
         frame->kps.info = previous->kps.info;
         frame->kps.kps3d = io_kps3d;
@@ -768,6 +777,81 @@ int svo_slam_last_counters(svo_slam *s, long long *out8)
     for (int k = 0; k < 8; k++) out8[k] = s->counters[k];
     return SVO_OK;
 }
+int svo_slam_total_counters(svo_slam *s, long long *out8)
+{
+    if (!s || !out8) return SVO_ERR_INVALID;
+    for (int k = 0; k < 8; k++) out8[k] = s->totals[k];
+    return SVO_OK;
+}
+
+// Many independent sequences, many frames each, one call: worker thread t owns sequences t, t + workers, ... and walks them
+// through their frames on its own (begin on all of its sequences, then end on all of them, frame after frame) — there is no
+// barrier between frames or between workers, so the GPU always has other sequences' work queued while one finishes.
+int svo_slam_reset(svo_slam *s)
+{
+    if (!s) return SVO_ERR_INVALID;
+    if (s->pending) { snprintf(s->err, sizeof(s->err), "svo_slam_reset while a frame is in flight"); return SVO_ERR_STATE; }
+    int rc = svo_ctx_reset(s->ctx);
+    if (rc) return s->fail(rc);
+    s->keyframes.clear();
+    s->frame.reset();
+    s->previous.reset();
+    s->trajectory.clear();
+    for (int i = 0; i < 6; i++) s->motion[i] = 0;
+    s->kf = MotionFilter();
+    s->last_keyframe_created = 0;
+    return SVO_OK;   // totals[] keep counting: they describe the work of the handle, not of one sequence
+}
+
+int svo_slam_run_many(svo_slam *const *slams, int n, int n_frames, const uint8_t *const *left, const uint8_t *const *right,
+                      size_t left_stride, size_t right_stride, const float *time_stamps, int on_device, int workers, int *failed_sequence)
+{
+    return svo_slam_run_many_restart(slams, n, n_frames, left, right, left_stride, right_stride, time_stamps, nullptr, on_device, workers,
+                                     failed_sequence);
+}
+
+int svo_slam_run_many_restart(svo_slam *const *slams, int n, int n_frames, const uint8_t *const *left, const uint8_t *const *right,
+                              size_t left_stride, size_t right_stride, const float *time_stamps, const uint8_t *restart, int on_device,
+                              int workers, int *failed_sequence)
+{
+    if (!slams || n < 1 || n_frames < 0 || !left || !right || !time_stamps) return SVO_ERR_INVALID;
+    for (int i = 0; i < n; i++) if (!slams[i]) return SVO_ERR_INVALID;
+    if (workers < 1) workers = 1;
+    if (workers > n) workers = n;
+    std::atomic<int> rc_first{SVO_OK}, bad{-1};
+    auto work = [&](int t) {
+        for (int f = 0; f < n_frames && rc_first.load(std::memory_order_relaxed) == SVO_OK; f++) {
+            int rc = SVO_OK, who = -1;
+            for (int i = t; i < n && rc == SVO_OK; i += workers) {
+                const size_t k = (size_t)i * n_frames + f;
+                if (restart && restart[k] && (rc = svo_slam_reset(slams[i]))) { who = i; break; }
+                rc = slams[i]->new_image_begin(left[k], left_stride, right[k], right_stride, time_stamps[k], on_device != 0);
+                if (rc) who = i;
+            }
+            // every sequence whose frame was enqueued must be finished, also after a failure of a later one
+            for (int i = t; i < n; i += workers) {
+                if (!slams[i]->pending) continue;
+                const int r2 = slams[i]->new_image_end();
+                if (r2 && rc == SVO_OK) { rc = r2; who = i; }
+            }
+            if (rc) {
+                int expect = SVO_OK;
+                if (rc_first.compare_exchange_strong(expect, rc)) bad.store(who);
+                return;
+            }
+        }
+    };
+    if (workers == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        th.reserve(workers);
+        for (int t = 0; t < workers; t++) th.emplace_back(work, t);
+        for (auto &x : th) x.join();
+    }
+    if (failed_sequence) *failed_sequence = bad.load();
+    return rc_first.load();
+}
+
 int svo_slam_dropped_keypoints(svo_slam *s, long long *dropped)
 {
     if (!s || !dropped) return SVO_ERR_INVALID;

@@ -57,6 +57,10 @@ class StereoSlam:
             capi.lib().svo_slam_destroy(self._h)
             self._h = None
 
+    def reset(self):
+        """A fresh StereoSlam on the same camera that keeps every device resource (svo_slam_reset): the next image is a first image."""
+        self._ck(capi.lib().svo_slam_reset(self._h))
+
     def __del__(self):
         try:
             self.close()
@@ -190,6 +194,12 @@ class StereoSlam:
         self._ck(capi.lib().svo_slam_dropped_keypoints(self._h, C.byref(out)))
         return int(out.value)
 
+    def total_counters(self):
+        out = (C.c_longlong * 8)()
+        self._ck(capi.lib().svo_slam_total_counters(self._h, out))
+        names = ("frames", "tracking_frames", "keyframes", "align_patches", "klt_windows", "keypoints", "align_evaluations", "refine_evaluations")
+        return dict(zip(names, [int(v) for v in out]))
+
     def last_counters(self):
         out = (C.c_longlong * 8)()
         self._ck(capi.lib().svo_slam_last_counters(self._h, out))
@@ -200,3 +210,47 @@ class StereoSlam:
     def context(self):
         """The device context behind the facade (stage-level probes)."""
         return capi.Context(self.camera_settings, self.width, self.height, _borrowed=capi.lib().svo_slam_ctx(self._h))
+
+
+def run_many(slams, left, right, time_stamps, workers=4, on_device=False, strides=None, restart=None):
+    """svo_slam_run_many: advance len(slams) independent sequences by F frames each in one native call.
+
+    left / right: per sequence a list of F frames — numpy uint8 arrays (H, W) with a common row stride, or, with
+    on_device=True, integer device addresses (row stride = strides or the image width); time_stamps: [n][F] floats.
+    `workers` native host threads share the sequences; no Python runs between the frames.  restart: optional [n][F] booleans —
+    True makes that frame the first image of a new sequence of the stream (svo_slam_reset before it)."""
+    n = len(slams)
+    if n == 0:
+        return
+    F = len(left[0])
+    lp, rp = (C.c_void_p * (n * F))(), (C.c_void_p * (n * F))()
+    ts = np.empty(n * F, np.float32)
+    keep = []
+    stride = strides
+    for i in range(n):
+        if len(left[i]) != F or len(right[i]) != F or len(time_stamps[i]) != F:
+            raise SvoError(capi.SVO_ERR_INVALID, "every sequence needs the same number of frames")
+        for f in range(F):
+            a, b = left[i][f], right[i][f]
+            if on_device:
+                lp[i * F + f], rp[i * F + f] = int(a), int(b)
+            else:
+                a, b = StereoSlam._img(a), StereoSlam._img(b)
+                if stride is None:
+                    stride = a.strides[0]
+                if a.strides[0] != stride or b.strides[0] != stride:
+                    raise SvoError(capi.SVO_ERR_INVALID, "all frames of one run_many call must share one row stride")
+                keep.append((a, b))
+                lp[i * F + f], rp[i * F + f] = a.ctypes.data, b.ctypes.data
+            ts[i * F + f] = time_stamps[i][f]
+    if stride is None:
+        stride = slams[0].width
+    handles = (C.c_void_p * n)(*[s._h for s in slams])
+    bad = C.c_int(-1)
+    rs = None if restart is None else np.ascontiguousarray(np.asarray(restart, dtype=np.uint8).reshape(n * F))
+    rc = capi.lib().svo_slam_run_many_restart(handles, n, F, lp, rp, C.c_size_t(stride), C.c_size_t(stride), ts.ctypes.data_as(C.c_void_p),
+                                              None if rs is None else rs.ctypes.data_as(C.c_void_p), 1 if on_device else 0, int(workers),
+                                              C.byref(bad))
+    if rc:
+        who = slams[bad.value] if 0 <= bad.value < n else slams[0]
+        raise SvoError(rc, f"sequence {bad.value}: " + capi.lib().svo_slam_last_error(who._h).decode())

@@ -483,3 +483,52 @@ def test_klt_random_starts_match_oracle():
     assert conv.sum() > n // 5, rep
     assert rep["flow_over_0p01_converged"] == 0, rep
     ctx.close()
+
+
+def test_run_many_equals_frame_by_frame_calls():
+    """svo_slam_run_many (n sequences x F frames in one native call on a pool of host threads) gives, bit for bit, what
+    new_image gives called frame by frame; a failing sequence is named and the others are left in a consistent state."""
+    from stereo_svo_slam_b200 import run_many
+    cfg = "S"
+    c, d = synth.CONFIGS[cfg], synth.settings_dict(cfg)
+    seqs = [synth.make_sequence(cfg, seed=200 + i) for i in range(5)]
+    F = 12
+    frames = [[s.render(k) for k in range(F)] for s in seqs]
+    ts = [[k / 20.0 for k in range(F)] for _ in seqs]
+    one = [StereoSlam(capi.CameraSettings(**d), c["width"], c["height"]) for _ in seqs]
+    for i, sl in enumerate(one):
+        for k in range(F):
+            sl.new_image(frames[i][k][0], frames[i][k][1], ts[i][k])
+    for workers in (1, 3, 8):
+        many = [StereoSlam(capi.CameraSettings(**d), c["width"], c["height"]) for _ in seqs]
+        run_many(many, [[f[0] for f in fr[:5]] for fr in frames], [[f[1] for f in fr[:5]] for fr in frames], [t[:5] for t in ts], workers=workers)
+        run_many(many, [[f[0] for f in fr[5:]] for fr in frames], [[f[1] for f in fr[5:]] for fr in frames], [t[5:] for t in ts], workers=workers)
+        for a, b in zip(one, many):
+            assert a.get_trajectory().tobytes() == b.get_trajectory().tobytes()
+            la, lb = gpu_lists(a.get_frame()), gpu_lists(b.get_frame())
+            assert all(la[k].tobytes() == lb[k].tobytes() for k in la)
+            tc = b.total_counters()
+            assert tc["frames"] == F and tc["tracking_frames"] == F - 1 and tc["keyframes"] == b.keyframe_count() and tc["align_patches"] > 0
+        # a bad frame in sequence 2 (wrong row stride is caught before anything is enqueued): error names the sequence
+        with pytest.raises(capi.SvoError) as e:
+            run_many(many, [[f[0] for f in fr[:2]] for fr in frames], [[f[1] for f in fr[:2]] for fr in frames], [[1.0, 1.05]] * len(seqs),
+                     workers=workers, strides=c["width"] - 1)
+        assert "stride" in str(e.value)
+        for sl in many:
+            assert len(sl.get_trajectory()) == F      # nothing was consumed
+            sl.close()
+    # streams of finite sequences: a restart flag makes a frame the first image of a fresh tracker on the same device resources
+    many = [StereoSlam(capi.CameraSettings(**d), c["width"], c["height"]) for _ in seqs]
+    twice = lambda fr, ch: [[f[ch] for f in x] + [f[ch] for f in x] for x in fr]
+    restart = [[k == F for k in range(2 * F)] for _ in seqs]
+    run_many(many, twice(frames, 0), twice(frames, 1), [t + t for t in ts], workers=3, restart=restart)
+    for a, b in zip(one, many):
+        assert a.get_trajectory().tobytes() == b.get_trajectory().tobytes()        # the second pass alone, identical to a fresh instance
+        la, lb = gpu_lists(a.get_frame()), gpu_lists(b.get_frame())
+        assert all(la[k].tobytes() == lb[k].tobytes() for k in la)
+        assert b.keyframe_count() == a.keyframe_count() and b.total_counters()["frames"] == 2 * F
+        b.reset()
+        assert b.get_frame() is None and b.keyframe_count() == 0 and len(b.get_trajectory()) == 0
+        b.close()
+    for sl in one:
+        sl.close()

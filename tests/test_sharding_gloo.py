@@ -1,49 +1,81 @@
-"""Multi-GPU is replicas only: ranks own disjoint sequences, no data-path collective; the only
-communication is the barrier and the max-over-ranks time. Covered here with a world-size-2 gloo group on CPU."""
+"""Multi-GPU is replicas only: ranks own disjoint sequences, there is no data-path collective;
+the only communication is the barrier and the reduction of (time, work counters) for the one JSON line.  Covered here with a
+world-size-2 gloo group on CPU, through bench.py's own partition and aggregation helpers (bench.stream_seeds,
+bench.aggregate_ranks) — the code the N-GPU bench runs."""
 import os
 import socket
+import sys
 
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-
-def seeds_for(rank, streams):
-    # bench.py: seeds = [1000 + rank * S + s for s in range(S)]
-    return [1000 + rank * streams + s for s in range(streams)]
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
 
 
-def _worker(rank, world, port, streams, out):
+def _worker(rank, world, port, streams, total, out):
+    import bench
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    mine = torch.tensor(seeds_for(rank, streams), dtype=torch.int64)
-    gathered = [torch.zeros_like(mine) for _ in range(world)]
-    dist.all_gather(gathered, mine)
-    t = torch.tensor([0.5 + rank], dtype=torch.float64)     # pretend per-rank elapsed seconds
+
+    def all_reduce(vals, op):
+        t = torch.tensor(vals, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX if op == "max" else dist.ReduceOp.SUM)
+        return t.tolist()
+    mine = bench.stream_seeds(rank, world, streams, total)
+    pad = torch.full((64,), -1, dtype=torch.int64)
+    pad[:len(mine)] = torch.tensor(mine, dtype=torch.int64)
+    gathered = [torch.zeros_like(pad) for _ in range(world)]
+    dist.all_gather(gathered, pad)
     dist.barrier()
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    # pretend this rank tracked 40 frames per owned sequence in (0.5 + rank) seconds, with 7 keyframes and 1000 patches per frame
+    frames = 40.0 * len(mine)
+    seconds, sums = bench.aggregate_ranks(0.5 + rank, [frames, 7.0, 1000.0 * frames], all_reduce)
     if rank == 0:
-        out.put((torch.cat(gathered).tolist(), float(t.item())))
+        out.put(([int(v) for g in gathered for v in g.tolist() if v >= 0], seconds, sums))
     dist.destroy_process_group()
 
 
-def test_rank_partition_and_max_time():
-    world, streams = 2, 4
+def _run(world, streams, total):
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, streams, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, streams, total, q)) for r in range(world)]
     for p in procs:
         p.start()
-    seeds, tmax = q.get(timeout=120)
+    res = q.get(timeout=180)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
+    return res
+
+
+def test_weak_scaling_partition_and_aggregation():
+    world, streams = 2, 4
+    seeds, seconds, sums = _run(world, streams, 0)
     assert sorted(seeds) == list(range(1000, 1000 + world * streams)) and len(set(seeds)) == world * streams
-    assert tmax == 1.5   # whole-job time = slowest rank
-    # whole-job value = all ranks' frames / max time
-    frames_per_rank = streams * 40
-    assert abs(world * frames_per_rank / tmax - 213.333) < 1e-2
+    assert seconds == 1.5                                    # whole-job time = slowest rank
+    assert sums == [320.0, 14.0, 320000.0]                   # work counters are summed over ranks
+    assert abs(sums[0] / seconds - 213.333) < 1e-2           # whole-job value = all ranks' frames / max time
+
+
+def test_configs4_partition_of_64_streams():
+    # BASELINE configs[4]: 64 streams in total, stream s on GPU s mod N
+    seeds, seconds, sums = _run(2, 32, 64)
+    assert sorted(seeds) == list(range(1000, 1064))
+    assert sums[0] == 64 * 40.0 and seconds == 1.5
+
+
+def test_partition_is_disjoint_and_complete_for_every_world_size():
+    import bench
+    for world in (1, 2, 4, 8):
+        got = [s for r in range(world) for s in bench.stream_seeds(r, world, 32, 64)]
+        assert sorted(got) == list(range(1000, 1064))
+        assert all(len(bench.stream_seeds(r, world, 32, 64)) == 64 // world for r in range(world))
+        got = [s for r in range(world) for s in bench.stream_seeds(r, world, 5, 0)]
+        assert sorted(got) == list(range(1000, 1000 + 5 * world))
+    assert bench.aggregate_ranks(2.0, [1.0, 2.0]) == (2.0, [1.0, 2.0])
