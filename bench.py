@@ -282,6 +282,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs4", action="store_true")
+    ap.add_argument("--playback", default="restart", choices=["restart", "sweep"], help="restart: streams of finite sequences (default); "
+                    "sweep: one endless sequence per stream, no keyframes in steady state (developer comparison with round 1)")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -376,11 +378,16 @@ def main():
         tables = []
         for k in range(W + K):
             t = k * F + np.arange(F, dtype=np.int64)
-            fr = (t % nframes)[None, :]                       # a stream = the rendered sequence over and over, each pass a new sequence
+            if a.playback == "sweep":                         # developer option: one endless sequence, forward/backward over the frames
+                fr = np.array([tri(int(x)) for x in t], np.int64)[None, :]
+                ts = np.tile((t / 20.0).astype(np.float32), n_seq)
+                rs = np.zeros(n_seq * F, np.uint8)
+            else:
+                fr = (t % nframes)[None, :]                   # a stream = the rendered sequence over and over, each pass a new sequence
+                ts = np.tile(((t % nframes) / 20.0).astype(np.float32), n_seq)
+                rs = np.tile(((t % nframes == 0) & (t > 0)).astype(np.uint8), n_seq)
             left = (base + (seq_off + fr) * 2 * img).astype(np.uint64).reshape(-1)
             right = left + np.uint64(img)
-            ts = np.tile(((t % nframes) / 20.0).astype(np.float32), n_seq)
-            rs = np.tile(((t % nframes == 0) & (t > 0)).astype(np.uint8), n_seq)
             tables.append((np.ascontiguousarray(left), np.ascontiguousarray(right), np.ascontiguousarray(ts), np.ascontiguousarray(rs)))
 
         def step(k):
@@ -423,11 +430,13 @@ def main():
         tot1, nl1 = totals()
         d = tot1 - tot0
         kps = int(np.mean([len(sl.get_frame().kps) for sl in slams]))
+        last_gpu_ms = float(np.mean([sl.last_stats()["gpu_ms"] for sl in slams]))   # device time of every sequence's last frame (latency under load)
         for sl in slams:
             sl.close()
         seconds, sums = aggregate_ranks(max(wall, dev_s), [float(x) for x in d] + [float(nl1 - nl0)], all_reduce if world > 1 else None)
         st_ = sorted(step_times)
-        trace = {"host_step_ms_p50": 1e3 * st_[len(st_) // 2], "host_step_ms_max": 1e3 * st_[-1], "host_us_per_frame_p50": 1e6 * st_[len(st_) // 2] / (n_seq * F)} if st_ else {}
+        trace = {"host_step_ms_p50": 1e3 * st_[len(st_) // 2], "host_step_ms_max": 1e3 * st_[-1], "host_us_per_frame_p50": 1e6 * st_[len(st_) // 2] / (n_seq * F),
+                 "frame_latency_ms_under_load": last_gpu_ms} if st_ else {}
         return dict(seconds=seconds, frames=sums[0], tracking_frames=sums[1], keyframes=sums[2], patches=sums[3], windows=sums[4], keypoints=sums[5],
                     launches=int(sums[8]), kps=kps, clocks=ck, trace=trace)
 

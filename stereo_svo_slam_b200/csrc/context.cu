@@ -7,6 +7,8 @@
 #include <cstring>
 #include <algorithm>
 #include <vector>
+#include <atomic>
+#include <chrono>
 
 #include "kernels.cuh"
 
@@ -86,6 +88,9 @@ struct IoLayout {
     size_t kps3d, flags, inlier, outlier, kf_state;                // in/out
     size_t pose_aligned, pose_refined, rd_aligned, rd_refined, costs, evals, klt_pts, klt_err, klt_status, klt_iters, disparity, kps2d_ref_in, kps2d_out;  // out
     size_t in_end, inout_begin, total;
+    size_t hdr_src, hdr_seq;   // inside the first 64-byte block, behind n: frame sources {left, right, pitch, pitch} (4 x u64), sequence number
+    size_t stamps;             // device only: %globaltimer at the start of the frame's first kernel
+    size_t done;               // host mirror: completion record {sequence number, -, t_start, t_end}
 };
 
 struct svo_ctx {
@@ -137,6 +142,7 @@ struct svo_ctx {
     // CUDA-graph cache of the whole per-frame sequence (upload + pyramids + tracking), keyed by the fixed resources
     struct FrameGraph {
         int prev_slot, cur_slot, bucket, src_kind, stage_idx;
+        bool slim;
         cudaGraphExec_t exec;
         cudaGraphNode_t left_copy, right_copy;
         unsigned long long last_use;
@@ -148,6 +154,12 @@ struct svo_ctx {
     bool use_fork = true;     // two-branch frame graph (SVO_NO_FORK=1: linear chain)
     bool import_rode = false; // the keypoint import of the frame being captured is part of lk_side_kernel (no launch of its own)
     bool use_ingest = true;   // SM-driven frame ingest instead of copy-engine DMA (SVO_NO_INGEST=1 turns it off)
+    // two driver calls per frame (ingest launch + graph launch) instead of nine: the frame's device time comes from %globaltimer
+    // stamps instead of two event records and a query, completion from a sequence number the last kernel stores behind the results
+    // in the host mirror instead of a stream synchronisation (SVO_NO_SLIM=1: off)
+    bool use_slim = true;
+    bool capturing_slim = false, slim_pending = false;
+    unsigned frame_seq = 0;
     unsigned long long graph_clock = 0;
     long long graph_launches = 0, graph_captures = 0, graph_updates = 0;
     float stage_ms[8] = {0};
@@ -212,10 +224,23 @@ static void make_layout(IoLayout &L, int M)
     L.disparity = take((size_t)M * 4);
     L.kps2d_ref_in = take((size_t)M * 8);
     L.kps2d_out = take((size_t)M * 8);
+    L.stamps = take(16);
+    L.done = take(32);
     L.total = o;
+    L.hdr_src = L.n + 16;
+    L.hdr_seq = L.n + 48;
 }
 
 #define CK(expr) SVO_CUDA_CHECK(ctx->err, expr)
+
+static inline void svo_cpu_relax()
+{
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#elif defined(__aarch64__)
+    asm volatile("yield");
+#endif
+}
 
 extern "C" int svo_device_count(void)
 {
@@ -259,6 +284,7 @@ extern "C" int svo_ctx_create(const svo_camera_settings *s, int device, int widt
     ctx->use_graphs = getenv("SVO_NO_GRAPHS") == nullptr;
     ctx->use_ingest = getenv("SVO_NO_INGEST") == nullptr;
     ctx->use_fork = getenv("SVO_NO_FORK") == nullptr;
+    ctx->use_slim = getenv("SVO_NO_SLIM") == nullptr;
     if (getenv("SVO_INGEST_MIX")) {   // developer experiment: every second context uploads by copy-engine DMA
         static int counter = 0;
         ctx->use_ingest = (counter++ & 1) == 0;
@@ -345,7 +371,7 @@ extern "C" int svo_ctx_create(const svo_camera_settings *s, int device, int widt
         out.src = ctx->d_io; out.dst = ctx->d_hio; out.n_ptr = reinterpret_cast<const int *>(ctx->d_io + L.n); out.max_n = ctx->max_kps;
         int k = 0;
         auto add = [&](IoCopyArgs &a, size_t off, unsigned elem, unsigned per_n) { a.arr[k].off = (unsigned)off; a.arr[k].elem = elem; a.arr[k].per_n = per_n; k++; };
-        add(in, L.n, 16, 0); add(in, L.pose_prior, 24, 0); add(in, L.prev_kps2d, 8, 1); add(in, L.ref_kps2d, 8, 1); add(in, L.kf_id, 4, 1); add(in, L.kp_index, 4, 1);
+        add(in, L.n, 64, 0); /* the 64-byte frame header: n, ..., sequence number */ add(in, L.pose_prior, 24, 0); add(in, L.prev_kps2d, 8, 1); add(in, L.ref_kps2d, 8, 1); add(in, L.kf_id, 4, 1); add(in, L.kp_index, 4, 1);
         add(in, L.kps3d, 12, 1); add(in, L.flags, 1, 1); add(in, L.inlier, 4, 1); add(in, L.outlier, 4, 1); add(in, L.kf_state, 8, 1);
         in.narr = k; k = 0;
         add(out, L.kps3d, 12, 1); add(out, L.flags, 1, 1); add(out, L.inlier, 4, 1); add(out, L.outlier, 4, 1); add(out, L.kf_state, 8, 1);
@@ -547,6 +573,7 @@ static int enqueue_upload(svo_ctx *ctx, Slot &s, const uint8_t *left, size_t ls,
     // preferred path: the SMs fetch the pair themselves (zero-copy from page-locked host memory, or device memory)
     if (ctx->use_ingest) {
         IngestArgs ia;
+        ia.t_start = nullptr;
         ia.dst[0] = dl; ia.dst[1] = dr; ia.w = ctx->W; ia.h = ctx->H; ia.spitch[0] = ls; ia.spitch[1] = rs;
         bool ok = true;
         if (src_kind == 2) { ia.src[0] = left; ia.src[1] = right; }
@@ -1135,7 +1162,7 @@ extern "C" int svo_depth_filter_update(svo_ctx *ctx, int slot, int n, const floa
     fa.kps2d = DP(float, kps2d_ref_in); fa.ref_kps2d = DP(float, ref_kps2d); fa.kps3d = DP(float, kps3d);
     fa.flags = DP(uint8_t, flags); fa.inlier = DP(int, inlier); fa.outlier = DP(int, outlier); fa.kf_state = DP(float, kf_state);
     fa.pose = DP(float, pose_refined); fa.kps2d_out = DP(float, kps2d_out); fa.n_ptr = DP(int, n); fa.max_kps = n; fa.cam = ctx->cam;
-    fa.do_export = 0; fa.rdn_in = nullptr;
+    fa.do_export = 0; fa.rdn_in = nullptr; fa.done_rec = nullptr; fa.seq_ptr = nullptr; fa.t_start = nullptr;
     launch_depth_filter(fa, ctx->stream);
     ctx->launch_total += 2;
     CK(cudaGetLastError());
@@ -1396,6 +1423,12 @@ static int enqueue_track(svo_ctx *ctx, int prev_slot, int cur_slot, int n, int g
         fa.pose = DP(float, pose_refined); fa.kps2d_out = DP(float, kps2d_out); fa.n_ptr = DP(int, n); fa.max_kps = grid_n; fa.cam = ctx->cam;
         fa.do_export = ctx->d_hio != nullptr; fa.exp = ctx->io_out;   // results go to the host mirror from the same kernel
         fa.rdn_in = DP(double, rd_refined);
+        fa.done_rec = nullptr; fa.seq_ptr = nullptr; fa.t_start = nullptr;
+        if (ctx->capturing_slim && ctx->d_hio && !getenv("SVO_SLIM_NOREC")) {
+            fa.done_rec = reinterpret_cast<unsigned long long *>(ctx->d_hio + L.done);
+            fa.seq_ptr = reinterpret_cast<const unsigned *>(ctx->d_io + L.hdr_seq);
+            fa.t_start = reinterpret_cast<const unsigned long long *>(ctx->d_io + L.stamps);
+        }
         mark(ctx, 8);
         launch_depth_filter(fa, ctx->stream); launches++;
         mark(ctx, 9);
@@ -1445,8 +1478,10 @@ static int capture_frame_graph(svo_ctx *ctx, svo_ctx::FrameGraph &g, int n, cuda
     CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
     int launches = 0;
     const bool forked = ctx->use_fork, branch_import = forked && ctx->d_hio != nullptr;
+    ctx->capturing_slim = g.slim;
     int rc = enqueue_pyramids(ctx, s, forked, branch_import);
     if (!rc) rc = enqueue_track(ctx, g.prev_slot, g.cur_slot, n, g.bucket, false, &launches, forked, branch_import);
+    ctx->capturing_slim = false;
     cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
     if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
     CK(e);
@@ -1513,10 +1548,29 @@ extern "C" int svo_frame_begin(svo_ctx *ctx, const uint8_t *left, size_t ls, con
         ctx->stage_idx ^= 1;
         left = stage; right = stage + img; ls = rs = (size_t)ctx->W;
     }
-    // the two image copies go on the stream directly (their source changes every frame); pyramids + tracking replay
+    // Slim form (one driver call per frame): the SMs can fetch the pair themselves and the keypoint block is host-mapped, so the
+    // ingest kernel is the first node of the replayed graph; it reads this frame's sources from the frame header.
+    const uint8_t *vs_left = src_kind == 2 ? left : ctx->zc_left, *vs_right = src_kind == 2 ? right : ctx->zc_right;
+    const bool slim = ctx->use_slim && ctx->use_ingest && ctx->d_hio && vs_left && vs_right && !(ctx->W & 15) &&
+                      !((reinterpret_cast<uintptr_t>(vs_left) | reinterpret_cast<uintptr_t>(vs_right) | ls | rs) & 15);
     const double tt1 = g_trace ? now_ms() : 0;
-    CK(cudaEventRecord(ctx->ev0, ctx->stream));   // the frame's device time starts with its ingest
-    if ((rc = enqueue_upload(ctx, ctx->slots[cur], left, ls, right, rs, src_kind, true))) return rc;
+    if (slim) {
+        *reinterpret_cast<unsigned *>(ctx->h_io + ctx->lay.hdr_seq) = ++ctx->frame_seq;
+        // the ingest stays a launch of its own: as a graph node it would have to fetch this frame's sources from the frame
+        // header first — one more dependent PCIe round trip in front of every frame (measured: +0.25 ms of latency under load)
+        IngestArgs ia;
+        ia.src[0] = vs_left; ia.src[1] = vs_right; ia.spitch[0] = ls; ia.spitch[1] = rs;
+        ia.dst[0] = ctx->d_rect_packed[0] ? ctx->d_raw[0] : ctx->slots[cur].dev.left[0].ptr;
+        ia.dst[1] = ctx->d_rect_packed[1] ? ctx->d_raw[1] : ctx->slots[cur].dev.right0.ptr;
+        ia.w = ctx->W; ia.h = ctx->H;
+        ia.t_start = reinterpret_cast<unsigned long long *>(ctx->d_io + ctx->lay.stamps);
+        launch_ingest(ia, ctx->arena->users < 4, ctx->stream);
+        ctx->launch_total += 1;
+    } else {
+        // the two image copies go on the stream directly (their source changes every frame); pyramids + tracking replay
+        CK(cudaEventRecord(ctx->ev0, ctx->stream));   // the frame's device time starts with its ingest
+        if ((rc = enqueue_upload(ctx, ctx->slots[cur], left, ls, right, rs, src_kind, true))) return rc;
+    }
     const double tt2 = g_trace ? now_ms() : 0;
     const int bucket = std::min(ctx->max_kps, (n + 127) / 128 * 128);
     // one executable graph per (previous, current) image-set pair; when the keypoint count moves to another grid-size
@@ -1524,7 +1578,7 @@ extern "C" int svo_frame_begin(svo_ctx *ctx, const uint8_t *left, size_t ls, con
     // topology, new grid sizes) — no instantiation, hence no device allocation, after the first two tracking frames
     svo_ctx::FrameGraph *g = nullptr;
     for (auto &c : ctx->graphs)
-        if (c.exec && c.prev_slot == prev_slot && c.cur_slot == cur) { g = &c; break; }
+        if (c.exec && c.prev_slot == prev_slot && c.cur_slot == cur && c.slim == slim) { g = &c; break; }
     if (g && g->bucket != bucket) {
         svo_ctx::FrameGraph ng = *g;
         ng.bucket = bucket; ng.exec = nullptr;
@@ -1553,7 +1607,7 @@ extern "C" int svo_frame_begin(svo_ctx *ctx, const uint8_t *left, size_t ls, con
             ctx->graphs.erase(ctx->graphs.begin() + v);
         }
         svo_ctx::FrameGraph ng;
-        ng.prev_slot = prev_slot; ng.cur_slot = cur; ng.bucket = bucket; ng.src_kind = src_kind; ng.stage_idx = stage_idx;
+        ng.prev_slot = prev_slot; ng.cur_slot = cur; ng.bucket = bucket; ng.src_kind = src_kind; ng.stage_idx = stage_idx; ng.slim = slim;
         ng.exec = nullptr; ng.left_copy = ng.right_copy = nullptr; ng.last_use = 0; ng.launches = 0;
         cudaGraph_t graph = nullptr;
         if ((rc = capture_frame_graph(ctx, ng, n, &graph))) return rc;
@@ -1568,7 +1622,8 @@ extern "C" int svo_frame_begin(svo_ctx *ctx, const uint8_t *left, size_t ls, con
     g->last_use = ++ctx->graph_clock;
     const double tt3 = g_trace ? now_ms() : 0;
     CK(cudaGraphLaunch(g->exec, ctx->stream));
-    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    if (!slim) CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->slim_pending = slim;
     if (g_trace && now_ms() - tt0 > 3.0)
         fprintf(stderr, "[slow frame_begin] pack+alloc %.2f upload %.2f graph lookup/capture %.2f launch %.2f ms\n", tt1 - tt0, tt2 - tt1, tt3 - tt2, now_ms() - tt3);
     ctx->graph_launches++;
@@ -1600,11 +1655,33 @@ extern "C" int svo_track_frame_end(svo_ctx *ctx, svo_track_io *io)
     if (!ctx || !io) return SVO_ERR_INVALID;
     if (!ctx->track_pending) { snprintf(ctx->err, sizeof(ctx->err), "svo_track_frame_end without _begin"); return SVO_ERR_STATE; }
     ctx->track_pending = false;
-    CK(cudaSetDevice(ctx->device));
     const double ts0 = g_trace ? now_ms() : 0;
-    CK(cudaStreamSynchronize(ctx->stream));
-    if (g_trace && now_ms() - ts0 > 20.0) fprintf(stderr, "[slow frame_end] stream sync %.2f ms\n", now_ms() - ts0);
-    CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+    bool polled = false;
+    static const bool slim_sync = getenv("SVO_SLIM_SYNC") != nullptr;   // developer switch: slim graph, but wait with cudaStreamSynchronize
+    if (ctx->slim_pending && slim_sync) ctx->slim_pending = false;
+    if (ctx->slim_pending) {
+        // the frame's last kernel stores the sequence number behind its results (system-scope fence): poll it, no driver call
+        ctx->slim_pending = false;
+        volatile unsigned *flag = reinterpret_cast<volatile unsigned *>(ctx->h_io + ctx->lay.done);
+        const unsigned want = ctx->frame_seq;
+        const auto t_poll = std::chrono::steady_clock::now();
+        for (unsigned spins = 0; !polled; spins++) {
+            if (*flag == want) { polled = true; break; }
+            svo_cpu_relax();
+            if ((spins & 0xfff) == 0xfff && std::chrono::steady_clock::now() - t_poll > std::chrono::seconds(2)) break;   // a fault never raises the flag
+        }
+        std::atomic_thread_fence(std::memory_order_acquire);
+        if (polled) {
+            const unsigned long long *rec = reinterpret_cast<const unsigned long long *>(ctx->h_io + ctx->lay.done);
+            ctx->last_ms = (float)((double)(rec[3] - rec[2]) * 1e-6);
+        }
+    }
+    if (!polled) {
+        CK(cudaSetDevice(ctx->device));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (g_trace && now_ms() - ts0 > 20.0) fprintf(stderr, "[slow frame_end] stream sync %.2f ms\n", now_ms() - ts0);
+        if (cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1) != cudaSuccess) { cudaGetLastError(); ctx->last_ms = 0.f; }
+    }
     if (ctx->profiling) {
         // sev: 0 upload start, 1 pyramids done, 2 inputs on device, 3 align, 4 klt, 5 refine, 6 ssd, 7 filter, 8 d2h
         float t;

@@ -79,6 +79,7 @@ struct IngestArgs {
     size_t spitch[2];
     uint8_t *dst[2];         // contiguous rows (pitch == w)
     int w, h;
+    unsigned long long *t_start;          // device: %globaltimer when the frame's first kernel starts, or null
 };
 bool ingest_supported(const IngestArgs &a);
 void launch_ingest(const IngestArgs &a, bool deep_queue, cudaStream_t st);
@@ -214,6 +215,11 @@ struct FilterArgs {
     const double *rdn_in;         // 9: Rodrigues(-r) of `pose` as the refinement kernel left it (or null: computed here)
     int do_export;                // run io_copy_block(exp) when the update is done (results straight to the host mirror)
     IoCopyArgs exp;
+    // completion record in the host mirror, written after the export: {frame sequence number, -, t_start, t_end (ns)} — the host
+    // polls the sequence number instead of synchronising the stream (null: no record)
+    unsigned long long *done_rec;        // 4 x u64 in mapped host memory
+    const unsigned *seq_ptr;             // device copy of the frame header's sequence number
+    const unsigned long long *t_start;   // device: stamp left by the ingest kernel
 };
 void launch_depth_filter(const FilterArgs &a, cudaStream_t st);
 

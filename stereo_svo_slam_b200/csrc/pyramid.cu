@@ -272,6 +272,11 @@ __global__ void __launch_bounds__(128) ingest_kernel(IngestArgs a, int depth)
     const uint8_t *__restrict__ src = z ? a.src[1] : a.src[0];
     uint8_t *__restrict__ dst = z ? a.dst[1] : a.dst[0];
     const size_t sp = z ? a.spitch[1] : a.spitch[0];
+    if (a.t_start && blockIdx.x == 0 && z == 0 && threadIdx.x == 0) {   // device-side time stamp of the frame's first kernel
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        *a.t_start = t;
+    }
     const int c16 = a.w >> 4;                        // 16-byte chunks per row
     const int total = c16 * a.h;
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(ingest_buf) + threadIdx.x * 16;

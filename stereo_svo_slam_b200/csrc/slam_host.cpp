@@ -21,6 +21,8 @@
 
 // developer trace (SVO_TRACE_KF=1): host time of the keyframe path, stage by stage
 static const bool g_trace_kf = getenv("SVO_TRACE_KF") != nullptr;
+// developer trace (SVO_HOST_PROFILE=1): host time per frame by phase, printed when a facade instance is destroyed
+static const bool g_host_prof = getenv("SVO_HOST_PROFILE") != nullptr;
 static inline double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 namespace {
@@ -233,6 +235,7 @@ struct svo_slam {
     bool pending_first = false;
     int last_keyframe_created = 0;
     long long dropped_for_capacity = 0;  // new keypoints a keyframe could not take (device keypoint block full)
+    double prof_ms[6] = {0, 0, 0, 0, 0, 0};   // SVO_HOST_PROFILE: pack, svo_frame_begin, wait+unpack (svo_track_frame_end), write-back, keyframe, motion filter
     float last_gpu_ms = 0;
     int last_launches = 0;
 
@@ -454,6 +457,7 @@ struct svo_slam {
             }
             frame->kps = std::move(u);
         }
+        const double tp0 = g_host_prof ? now_ms() : 0;
         const size_t n = frame->kps.size();
         io_prev2d = frame->kps.kps2d;
         io_kps3d = frame->kps.kps3d;
@@ -479,7 +483,9 @@ struct svo_slam {
         io.keypoint_index = io_kpidx.data();
         std::memcpy(io.pose_prior, nf->pose, sizeof(io.pose_prior));
         // pyramids (stereo_slam.cpp:135-139) + the whole tracking sequence, one CUDA graph launch in steady state
+        const double tp1 = g_host_prof ? now_ms() : 0;
         rc = svo_frame_begin(ctx, left, ls, right, rs, on_device ? 1 : 0, frame->slot, &io, &nf->slot);
+        if (g_host_prof) { prof_ms[0] += tp1 - tp0; prof_ms[1] += now_ms() - tp1; }
         if (rc) return fail(rc);
         previous = std::move(frame);
         frame = std::move(nf);
@@ -506,9 +512,11 @@ struct svo_slam {
             finish_frame();
             return SVO_OK;
         }
+        const double te0 = g_host_prof ? now_ms() : 0;
         rc = svo_track_frame_end(ctx, &io);
         if (rc) return fail(rc);
         svo_last_track_timing(ctx, &last_gpu_ms, &last_launches);
+        const double te1 = g_host_prof ? now_ms() : 0;
         const size_t n = (size_t)io.n;
         std::memcpy(frame->pose, io.pose_refined, sizeof(frame->pose));
         {
@@ -542,6 +550,8 @@ struct svo_slam {
             ki.inlier_count = in.inlier_count; ki.outlier_count = in.outlier_count;
             ki.kf_inv_depth = in.kf_inv_depth; ki.kf_variance = in.kf_variance;  // cv::KalmanFilter copies share state (Q13)
         }
+        const double te2 = g_host_prof ? now_ms() : 0;
+        if (g_host_prof) { prof_ms[2] += te1 - te0; prof_ms[3] += te2 - te1; }
         if (keyframe_needed(*frame)) {  // stereo_slam.cpp:231-246
             rc = create_keyframe(*frame);
             if (rc) return rc == SVO_ERR_STATE ? rc : fail(rc);
@@ -550,7 +560,9 @@ struct svo_slam {
             if (c < frame->kps.info.size() / 4)
                 for (auto &in : frame->kps.info) in.ignore_temporary = 0;
         }
+        const double te3 = g_host_prof ? now_ms() : 0;
         finish_frame();
+        if (g_host_prof) { prof_ms[4] += te3 - te2; prof_ms[5] += now_ms() - te3; }
         return SVO_OK;
     }
 };
@@ -583,6 +595,11 @@ int svo_slam_create(const svo_camera_settings *settings, int device, int width, 
 int svo_slam_destroy(svo_slam *s)
 {
     if (!s) return SVO_ERR_INVALID;
+    if (g_host_prof && s->totals[1] > 0) {
+        const double f = 1e3 / (double)s->totals[1];
+        fprintf(stderr, "[host profile] %lld tracking frames, us per frame: pack %.2f frame_begin %.2f wait+unpack %.2f write-back %.2f keyframe %.2f motion filter %.2f\n",
+                s->totals[1], s->prof_ms[0] * f, s->prof_ms[1] * f, s->prof_ms[2] * f, s->prof_ms[3] * f, s->prof_ms[4] * f, s->prof_ms[5] * f);
+    }
     if (s->ctx) svo_ctx_destroy(s->ctx);
     delete s;
     return SVO_OK;
@@ -819,26 +836,47 @@ int svo_slam_run_many_restart(svo_slam *const *slams, int n, int n_frames, const
     if (workers < 1) workers = 1;
     if (workers > n) workers = n;
     std::atomic<int> rc_first{SVO_OK}, bad{-1};
+    // A worker keeps every one of its sequences busy on the device: as soon as frame f of a sequence is finished (results
+    // unpacked, bookkeeping done) frame f + 1 of the SAME sequence is enqueued, then the worker turns to its next sequence —
+    // at any time all but one of a worker's sequences have a frame queued.
     auto work = [&](int t) {
-        for (int f = 0; f < n_frames && rc_first.load(std::memory_order_relaxed) == SVO_OK; f++) {
-            int rc = SVO_OK, who = -1;
+        int rc = SVO_OK, who = -1;
+        auto begin = [&](int i, int f) {
+            const size_t k = (size_t)i * n_frames + f;
+            if (restart && restart[k] && (rc = svo_slam_reset(slams[i]))) { who = i; return; }
+            rc = slams[i]->new_image_begin(left[k], left_stride, right[k], right_stride, time_stamps[k], on_device != 0);
+            if (rc) who = i;
+        };
+        static const bool phased = getenv("SVO_RUN_MANY_PHASED") != nullptr;   // developer switch: begin all, then end all, per frame
+        if (phased) {
+            for (int f = 0; f < n_frames && rc == SVO_OK; f++) {
+                for (int i = t; i < n && rc == SVO_OK; i += workers) begin(i, f);
+                for (int i = t; i < n; i += workers) {
+                    if (!slams[i]->pending) continue;
+                    const int r2 = slams[i]->new_image_end();
+                    if (r2 && rc == SVO_OK) { rc = r2; who = i; }
+                }
+            }
+        }
+        if (!phased && n_frames > 0)
+            for (int i = t; i < n && rc == SVO_OK; i += workers) begin(i, 0);
+        for (int f = 0; !phased && f < n_frames && rc == SVO_OK; f++) {
+            if (rc_first.load(std::memory_order_relaxed) != SVO_OK) break;
             for (int i = t; i < n && rc == SVO_OK; i += workers) {
-                const size_t k = (size_t)i * n_frames + f;
-                if (restart && restart[k] && (rc = svo_slam_reset(slams[i]))) { who = i; break; }
-                rc = slams[i]->new_image_begin(left[k], left_stride, right[k], right_stride, time_stamps[k], on_device != 0);
-                if (rc) who = i;
+                rc = slams[i]->new_image_end();
+                if (rc) { who = i; break; }
+                if (f + 1 < n_frames) begin(i, f + 1);
             }
-            // every sequence whose frame was enqueued must be finished, also after a failure of a later one
-            for (int i = t; i < n; i += workers) {
-                if (!slams[i]->pending) continue;
-                const int r2 = slams[i]->new_image_end();
-                if (r2 && rc == SVO_OK) { rc = r2; who = i; }
-            }
-            if (rc) {
-                int expect = SVO_OK;
-                if (rc_first.compare_exchange_strong(expect, rc)) bad.store(who);
-                return;
-            }
+        }
+        // every sequence whose frame was enqueued is finished, also after a failure (of this worker or of another one)
+        for (int i = t; i < n; i += workers) {
+            if (!slams[i]->pending) continue;
+            const int r2 = slams[i]->new_image_end();
+            if (r2 && rc == SVO_OK) { rc = r2; who = i; }
+        }
+        if (rc) {
+            int expect = SVO_OK;
+            if (rc_first.compare_exchange_strong(expect, rc)) bad.store(who);
         }
     };
     if (workers == 1) work(0);

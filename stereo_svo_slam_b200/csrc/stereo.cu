@@ -710,6 +710,19 @@ __global__ void __launch_bounds__(DF_THREADS) depth_filter_kernel(FilterArgs a)
     if (a.do_export) {
         __syncthreads();   // this CTA wrote the last results of the frame; everything earlier in the stream is complete
         io_copy_block(a.exp);
+        if (a.done_rec) {
+            // completion record: the CTA barrier orders every thread's result stores before thread 0's system-scope fence
+            // (fences are cumulative), the fence orders them before the sequence number the host polls for — ONE fence per frame
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                unsigned long long t;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                a.done_rec[2] = *a.t_start;
+                a.done_rec[3] = t;
+                __threadfence_system();
+                *reinterpret_cast<volatile unsigned *>(a.done_rec) = *a.seq_ptr;
+            }
+        }
     }
 }
 
