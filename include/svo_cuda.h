@@ -221,6 +221,14 @@ int svo_frame_begin(svo_ctx *ctx, const uint8_t *left, size_t left_stride, const
  * 8, or 16 for frames with more than 1024 keypoints.  Results agree within the pose tolerance (the cross-keypoint sums
  * are grouped differently), each setting is deterministic.  Env SVO_ALIGN_CLUSTER sets the default. */
 int svo_set_align_cluster(svo_ctx *ctx, int ctas);
+/* Width of the line searches of the two Gauss-Newton solvers.  Most trial steps of a running sequence are rejected and halved, and
+ * every trial pose x0 + 2^-j * step is known as soon as the step is: wide = 1 evaluates several of them per round on otherwise
+ * idle SMs (refinement: an 8-CTA cluster, CTA c takes trial j + c; alignment: two half-clusters take trials j and j + 1) and
+ * replays the reference's accept / halve / stop rule over the costs in order — the same evaluations, decisions and bits as the
+ * sequential search (wide = 0), fewer dependent rounds, more SMs held per frame.  -1 (default): wide while fewer than four
+ * sequences share the device (latency of one stream), sequential otherwise (throughput of many).  Env SVO_SOLVER_WIDTH sets
+ * the default. */
+int svo_set_solver_width(svo_ctx *ctx, int wide);
 /* CUDA-graph replay on/off (default on; env SVO_NO_GRAPHS=1 turns it off); counters for tests */
 int svo_set_graphs(svo_ctx *ctx, int on);
 int svo_graph_stats(svo_ctx *ctx, long long *graph_launches, long long *graph_captures);
@@ -244,6 +252,10 @@ int svo_sync(svo_ctx *ctx);
  * out16[15] = stamps enqueued by the host, [16..63] = record of a barrier wait of the alignment kernel that timed out;
  * all -1 when the aid is off */
 int svo_debug_marks(svo_ctx *ctx, int *out64);
+/* developer aid (env SVO_SOLVER_TRACE=1 at context creation): phase stamps of the last alignment (which = 0) or refinement
+ * (which = 1) solve: out[0] = entries n, out[1..n] = SM clock << 16 | extra << 8 | tag (0 start, 1 level start, 2 level images
+ * staged, 3 reference terms cached, 4 cost round done (extra = trial poses in it), 5 gradient round done, 6 end) */
+int svo_debug_solver_trace(svo_ctx *ctx, int which, unsigned long long *out, int cap);
 /* developer probe: bandwidth (GB/s) at which `ctas` CTAs of 256 threads read page-locked host memory over PCIe with the
  * access pattern of the frame-ingest kernel (16-byte loads) — the e2e roofline of zero-copy ingest */
 int svo_debug_zero_copy_bandwidth(svo_ctx *ctx, const void *pinned_host, size_t bytes, int ctas, int reps, float *gb_per_s);

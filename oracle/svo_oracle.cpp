@@ -397,10 +397,12 @@ static float gn_driver(CB &cb, const PoseM &guess, PoseM &out, float stop_thr, i
     float prev_cost = cb.do_calc(x0);
     int evals = 1, grads = 0;
     int i;
+    static const bool gn_trace = getenv("SVO_ORACLE_GN_TRACE") != nullptr;   // developer aid: the accept (a) / halve (r) / stop (s) pattern
     for (i = 0; i < maxIter; i++) {
         float gradient[6];
         cb.get_gradient(x0, gradient);
         grads++;
+        if (gn_trace) fputc('G', stderr);
         float k = 1.0;
         for (; i < maxIter; i++) {
             float x[6];
@@ -411,15 +413,19 @@ static float gn_driver(CB &cb, const PoseM &guess, PoseM &out, float stop_thr, i
             if (new_cost < prev_cost) {
                 x0 = _x;
                 prev_cost = new_cost;
+                if (gn_trace) fputc('a', stderr);
                 break;
             } else if (fabs(new_cost - prev_cost) < stop_thr) {
                 i = maxIter;
+                if (gn_trace) fputc('s', stderr);
                 break;
             } else {
                 k /= 2;
+                if (gn_trace) fputc('r', stderr);
             }
         }
     }
+    if (gn_trace) fprintf(stderr, " thr %g\n", (double)stop_thr);
     out = x0;
     if (n_evals) *n_evals = evals;
     if (n_grads) *n_grads = grads;

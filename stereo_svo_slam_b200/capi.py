@@ -157,6 +157,11 @@ class Context:
         """SMs sharing the alignment solve of a frame: 8 = lowest latency (default), 1-2 = lowest SM time per frame."""
         self._ck(lib().svo_set_align_cluster(self.h_ctx, ctas))
 
+    def set_solver_width(self, wide):
+        """Line searches of the two solvers: 1 = several trial poses per round on idle SMs (one sequence alone), 0 = sequential,
+        -1 = automatic (svo_set_solver_width); the same bits either way."""
+        self._ck(lib().svo_set_solver_width(self.h_ctx, wide))
+
     def release(self, slot):
         self._ck(lib().svo_slot_release(self.h_ctx, slot))
 

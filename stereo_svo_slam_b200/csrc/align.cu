@@ -26,12 +26,13 @@
 #define ALIGN_WARPS (ALIGN_THREADS / 32)
 #define NGRAD 27             // 21 (H upper triangle) + 6 (b)
 
+#define ALIGN_DEPTH 16       // halving steps whose rotation matrices are prepared right after a gradient (x0 + 2^-j grad, j < 16)
 struct AlignHdr {
     unsigned long long bar;                // TMA completion barrier (level images)
     unsigned long long xbar[3];            // DSMEM exchange barriers: cost (two, alternating) and gradient
-    double Rd[18][9];                      // Rodrigues(-r): two tables of 8 step sizes (k = 2^-j) + 2 spare slots, see rd_slot()
+    double Rd[2 * ALIGN_DEPTH + 2][9];     // Rodrigues(-r): two tables of ALIGN_DEPTH step sizes (k = 2^-j) + 2 spare slots
     double warp_cost[ALIGN_WARPS];         // this CTA's per-warp cost partials
-    double cl_cost[2][CLMAX];                 // per-CTA cost partials of the whole cluster (written through DSMEM), double buffered
+    double cl_cost[2][CLMAX];              // per-CTA cost partials of the whole cluster ([group][CTA of the group], written through DSMEM), double buffered
     float warp_grad[ALIGN_WARPS][NGRAD];   // this CTA's per-warp partials of H (21) and b (6)
     double cl_grad[CLMAX][NGRAD];             // per-CTA partials of the whole cluster (written through DSMEM)
     double red_out[NGRAD];
@@ -40,33 +41,6 @@ struct AlignHdr {
 };
 #define HDR_BYTES ((sizeof(AlignHdr) + 127) / 128 * 128)
 
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity)
-{
-    uint32_t ok = 0;
-    const uint32_t addr = smem_u32(bar);
-    while (!ok) {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(ok)
-            : "r"(addr), "r"(parity)
-            : "memory");
-    }
-}
 // developer aid: same wait, but after ~2 s of polling it records where it was stuck in dbg[] (mapped host memory) and traps
 __device__ __noinline__ void mbar_wait_dbg(unsigned long long *bar, uint32_t parity, int *dbg, int tag, int crank, int level, int mode, int evals, int grads)
 {
@@ -96,43 +70,6 @@ __device__ __noinline__ void mbar_wait_dbg(unsigned long long *bar, uint32_t par
             __trap();
         }
     }
-}
-
-__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, unsigned long long *bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
-__device__ __forceinline__ unsigned cluster_ctarank()
-{
-    unsigned r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all()
-{
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// store a double into the shared memory of CTA `rank` of this cluster (distributed shared memory)
-__device__ __forceinline__ void dsmem_store_f64(void *local_smem_ptr, unsigned rank, double v)
-{
-    uint32_t local = smem_u32(local_smem_ptr), remote;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(rank));
-    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(remote), "d"(v) : "memory");
-}
-
-// Push a double into CTA `rank`'s shared memory and signal that CTA's mbarrier with the 8 transferred bytes
-// (st.async + complete_tx): data and notification travel together, no cluster-scope fence or barrier is needed.
-__device__ __forceinline__ void dsmem_push_f64(void *local_slot, unsigned long long *local_bar, unsigned rank, double v)
-{
-    uint32_t slot = smem_u32(local_slot), bar = smem_u32(local_bar), rslot, rbar;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rslot) : "r"(slot), "r"(rank));
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(bar), "r"(rank));
-    asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(rslot), "l"(__double_as_longlong(v)), "r"(rbar)
-                 : "memory");
 }
 
 // exact u8 -> float without the slow I2F path: 0x4B000000 | v is the float 8388608 + v
@@ -267,63 +204,20 @@ __device__ __forceinline__ void intensity_diff_row(const uint8_t *im1, const uin
     }
 }
 
-// 6x6 SPD solve in double (LDL^T, one reciprocal per pivot); returns false when H is not numerically positive definite
-__device__ bool solve6(const double *Hu /*21 upper-tri row-major*/, const double *b, double *x)
-{
-    double A[6][6];
-    {
-        int k = 0;
-#pragma unroll
-        for (int i = 0; i < 6; i++)
-#pragma unroll
-            for (int j = i; j < 6; j++) { A[i][j] = Hu[k]; A[j][i] = Hu[k]; k++; }
-    }
-    double maxd = 0;
-#pragma unroll
-    for (int i = 0; i < 6; i++) maxd = fmax(maxd, A[i][i]);
-    if (!(maxd > 0)) return false;
-    double L[6][6], D[6], Dinv[6];
-    bool ok = true;
-#pragma unroll
-    for (int j = 0; j < 6; j++) {
-        double d = A[j][j];
-#pragma unroll
-        for (int q = 0; q < j; q++) d -= L[j][q] * L[j][q] * D[q];
-        if (!(d > 1e-13 * maxd)) { ok = false; d = 1.0; }
-        D[j] = d;
-        Dinv[j] = 1.0 / d;
-#pragma unroll
-        for (int i = j + 1; i < 6; i++) {
-            double t = A[i][j];
-#pragma unroll
-            for (int q = 0; q < j; q++) t -= L[i][q] * L[j][q] * D[q];
-            L[i][j] = t * Dinv[j];
-        }
-    }
-    if (!ok) return false;
-    double y[6];
-#pragma unroll
-    for (int i = 0; i < 6; i++) {
-        double t = b[i];
-#pragma unroll
-        for (int q = 0; q < i; q++) t -= L[i][q] * y[q];
-        y[i] = t;
-    }
-#pragma unroll
-    for (int i = 5; i >= 0; i--) {
-        double t = y[i] * Dinv[i];
-#pragma unroll
-        for (int q = i + 1; q < 6; q++) t -= L[q][i] * x[q];
-        x[i] = t;
-    }
-    return true;
-}
-
 // One thread-block CLUSTER (8 CTAs x 256 threads) = one frame.  Four lanes share a keypoint: lane r of the quad owns
 // row r of its 4x4 patch.  kSmem: level images staged in every CTA's shared memory (TMA), else read via L1/L2.
-template <bool kSmem, int CL>
+//
+// G > 1 (svo_set_solver_width): the cluster has G groups of CL CTAs.  Every group covers ALL keypoints exactly like a cluster of CL
+// CTAs would (same keypoint -> thread mapping, same reduction trees: the same bits); gradients are evaluated by every group for
+// itself, and in a cost round group g evaluates trial pose x0 + 2^-(j+g) grad.  A line search of a running sequence is a run of
+// rejected-and-halved steps ("G a G r r a G r r r r r r s": 22 cost evaluations for 7 gradients per C3 frame), every trial pose and
+// its matrix is known once the gradient is, and a rejected step decides nothing but "try the next one": the G costs of a round are
+// exchanged across the whole cluster and every thread replays the accept / halve / stop rule of estimate_pose_at_level over them
+// in order.  Same evaluations, decisions and counters as the sequential search; a run of rejections costs 1/G of the rounds.
+template <bool kSmem, int CL, int G>
 __global__ void __launch_bounds__(ALIGN_THREADS, 1) sparse_align_kernel(AlignArgs a)
 {
+    static_assert(CL * G <= CLMAX, "cluster too large");
     constexpr int KPS_PER_PASS = CL * ALIGN_WARPS * 8;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     AlignHdr *hdr = reinterpret_cast<AlignHdr *>(smem_raw);
@@ -331,17 +225,20 @@ __global__ void __launch_bounds__(ALIGN_THREADS, 1) sparse_align_kernel(AlignArg
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int quad = lane >> 2, row = lane & 3;
-    const unsigned crank = cluster_ctarank();
+    const unsigned prank = cluster_ctarank();                       // rank in the physical cluster of CL * G CTAs
+    const unsigned grp = G > 1 ? prank / CL : 0, crank = G > 1 ? prank % CL : prank;   // group (trial pose of a cost round), rank in the group
     const DevCam cam = a.cam;
     if (tid == 0) {
         if (kSmem) mbar_init(&hdr->bar, 1);
         for (int k = 0; k < 3; k++) mbar_init(&hdr->xbar[k], 1);
         hdr->n = min(*a.n_ptr, a.max_kps);
-        if (crank == 0) for (int k = 0; k < 16; k++) a.evals_out[k] = 0;
+        if (prank == 0) for (int k = 0; k < 16; k++) a.evals_out[k] = 0;
     }
     __syncthreads();
     cluster_sync_all();   // every CTA's shared memory is live before anyone writes into it remotely
     const int n = hdr->n;
+    SolverTrace trc(a.trace, tid == 0 && prank == 0);
+    trc.stamp(0);
     const int npass = (n + KPS_PER_PASS - 1) / KPS_PER_PASS;
     const bool nodist = dev_cam_nodist(cam);
     uint32_t phase = 0, xphase[3] = {0, 0, 0};
@@ -357,7 +254,7 @@ __global__ void __launch_bounds__(ALIGN_THREADS, 1) sparse_align_kernel(AlignArg
 #pragma unroll
     for (int k = 0; k < 6; k++) { x0[k] = a.pose_in[k]; xt[k] = x0[k]; grad[k] = 0.f; }
     float prev_cost = 0.f;
-    int x0slot = 16, sp = 1, tb = 0, xtslot = 0;
+    int x0slot = 2 * ALIGN_DEPTH, sp = 1, tb = 0, xtslot = 0;
 
     const int lv_hi = (a.probe_level >= 0) ? a.probe_level : cam.max_levels - 1;
     const int lv_lo = (a.probe_level >= 0) ? a.probe_level : cam.min_level;
@@ -380,6 +277,7 @@ __global__ void __launch_bounds__(ALIGN_THREADS, 1) sparse_align_kernel(AlignArg
             pimg = P.ptr; cimg = C.ptr;
         }
         const int pitch = w;  // halfSample levels are stored with pitch == width
+        trc.stamp(1, level);
 
         // setLevel (pose_estimator.cpp:541-562)
         const int divider = 1 << level;
@@ -390,14 +288,15 @@ __global__ void __launch_bounds__(ALIGN_THREADS, 1) sparse_align_kernel(AlignArg
         // x0 + 2^-j grad (table tb); cost evaluations then find theirs ready, and an accepted pose keeps its slot as
         // "the matrix of x0" while the next gradient fills the other table.  j >= 8 falls back to a spare slot.
         if (level == lv_hi) {
-            if (tid == 0) dev_rodrigues_d(-x0[3], -x0[4], -x0[5], hdr->Rd[16]);   // overlaps the TMA copy
-            x0slot = 16; sp = 1; tb = 0;
+            if (tid == 0) dev_rodrigues_d(-x0[3], -x0[4], -x0[5], hdr->Rd[2 * ALIGN_DEPTH]);   // overlaps the TMA copy
+            x0slot = 2 * ALIGN_DEPTH; sp = 1; tb = 0;
         }
         if (kSmem) {
-            if (a.dbg) mbar_wait_dbg(&hdr->bar, phase, a.dbg, 1, (int)crank, level, -1, 0, 0);
+            if (a.dbg) mbar_wait_dbg(&hdr->bar, phase, a.dbg, 1, (int)prank, level, -1, 0, 0);
             else mbar_wait(&hdr->bar, phase);
             phase ^= 1;
         }
+        trc.stamp(2, level);
 
         // ---- per-level cache of the pose-independent reference terms of this lane's patch row
         //      (calculate_hessian :346-395 image part, get_gradient :449-460 reference part)
@@ -440,36 +339,62 @@ __global__ void __launch_bounds__(ALIGN_THREADS, 1) sparse_align_kernel(AlignArg
         }
         // (each thread only ever reads back the scratch entries it wrote itself)
         __syncthreads();  // Rd of x0 visible
+        trc.stamp(3, level);
+
+        // pose-independent inputs of this lane's keypoint of the first pass (all of them for up to 64 x CL keypoints), kept in
+        // registers for the whole level: the ~30 evaluations of a level re-read and re-divide nothing
+        const int i_first = (warp * CL + (int)crank) * 8 + quad;
+        const bool act_first = (i_first < n) && !(a.flags && (a.flags[i_first] & SVO_F_IGN_TEMP));
+        float bx_first = 0.f, by_first = 0.f, P_first[3] = {0.f, 0.f, 0.f};
+        if (act_first) {
+            bx_first = a.kps2d[2 * i_first]; by_first = a.kps2d[2 * i_first + 1];
+            if (level != 0) { bx_first = bx_first / fdiv; by_first = by_first / fdiv; }   // setLevel :558-561
+            P_first[0] = a.kps3d[3 * i_first]; P_first[1] = a.kps3d[3 * i_first + 1]; P_first[2] = a.kps3d[3 * i_first + 2];
+        }
 
         // ---- Gauss-Newton driver (estimate_pose_at_level :166-222).
         //  mode 0: cost at x0 (initial)   mode 1: gradient at x0   mode 2: cost at xt   mode 3: level done
         int mode = 0, it = 0, n_evals = 0, n_grads = 0, jstep = 0;
         float kstep = 1.f;
         while (mode != 3) {
-            const float *x = (mode == 2) ? xt : x0;
-            const double *Rd = hdr->Rd[(mode == 2) ? xtslot : x0slot];
-            const float tx = x[0], ty = x[1], tz = x[2];
             if (mode != 1) {
                 // ---------------- do_calc: bilinear SAD (prev @ reference position, cur @ projection)
+                // trials of this round: group g takes halving step jstep + g as long as its matrix is in the table, the iteration
+                // budget allows it (it + g < 50) and the pose is a trial at all (mode 2, table slot); otherwise every group
+                // evaluates the same pose (the bits are the same) and group 0's result is used
+                int nvalid = 1;
+                if (G > 1 && mode == 2 && xtslot < 2 * ALIGN_DEPTH) { while (nvalid < G && jstep + nvalid < ALIGN_DEPTH && it + nvalid < 50) nvalid++; }
+                const int g_mine = (G > 1 && nvalid > 1) ? (int)grp : 0;
+                const bool mine = g_mine < nvalid;
+                float xg[6], kg = kstep;
+                for (int q = 0; q < g_mine; q++) kg = kg / 2;
+#pragma unroll
+                for (int k = 0; k < 6; k++) xg[k] = (mode == 2) ? (g_mine == 0 ? xt[k] : x0[k] + (kg * grad[k])) : x0[k];
+                const double *Rd = hdr->Rd[(mode == 2) ? (mine ? xtslot + g_mine : xtslot) : x0slot];
+                const float tx = xg[0], ty = xg[1], tz = xg[2];
                 double part = 0.0;
-                for (int pass = 0; pass < npass; pass++) {
+                for (int pass = 0; mine && pass < npass; pass++) {
                     const int i = ((pass * ALIGN_WARPS + warp) * CL + (int)crank) * 8 + quad;
-                    const bool active = (i < n) && !(a.flags && (a.flags[i] & SVO_F_IGN_TEMP));
+                    const bool active = pass == 0 ? act_first : ((i < n) && !(a.flags && (a.flags[i] & SVO_F_IGN_TEMP)));
                     float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
                     if (active) {
-                        float bx = a.kps2d[2 * i], by = a.kps2d[2 * i + 1];
-                        if (level != 0) { bx = bx / fdiv; by = by / fdiv; }
+                        float bx = bx_first, by = by_first, Px = P_first[0], Py = P_first[1], Pz = P_first[2];
+                        if (pass != 0) {
+                            bx = a.kps2d[2 * i]; by = a.kps2d[2 * i + 1];
+                            if (level != 0) { bx = bx / fdiv; by = by / fdiv; }
+                            Px = a.kps3d[3 * i]; Py = a.kps3d[3 * i + 1]; Pz = a.kps3d[3 * i + 2];
+                        }
                         float u, v;
-                        dev_project_nd(nodist, Rd, a.kps3d[3 * i], a.kps3d[3 * i + 1], a.kps3d[3 * i + 2], tx, ty, tz, lfx, lfy, lcx, lcy, cam, u, v);
+                        dev_project_nd(nodist, Rd, Px, Py, Pz, tx, ty, tz, lfx, lfy, lcx, lcy, cam, u, v);
                         intensity_diff_row(pimg, cimg, w, h, pitch, bx, by, u, v, cam.win_pose, row, d0, d1, d2, d3);
                     }
                     // the reference adds the 16 |dI| terms of a patch sequentially in raster order: chain the four rows
                     float run = 0.f;
 #pragma unroll
                     for (int rr = 0; rr < 4; rr++) {
-                        float mine = run;
-                        mine += d0; mine += d1; mine += d2; mine += d3;
-                        run = __shfl_sync(0xffffffffu, mine, (lane & ~3) | rr);
+                        float mine_sum = run;
+                        mine_sum += d0; mine_sum += d1; mine_sum += d2; mine_sum += d3;
+                        run = __shfl_sync(0xffffffffu, mine_sum, (lane & ~3) | rr);
                     }
                     if (row == 0) part += (double)run;   // one lane per keypoint carries the patch cost
                 }
@@ -477,56 +402,64 @@ __global__ void __launch_bounds__(ALIGN_THREADS, 1) sparse_align_kernel(AlignArg
                 for (int o = 16; o > 0; o >>= 1) part += __shfl_down_sync(0xffffffffu, part, o);
                 if (lane == 0) hdr->warp_cost[warp] = part;
                 __syncthreads();
-                if (tid < CL) {   // lane t pushes this CTA's partial into CTA t's table and signals CTA t's barrier
+                if (tid < CL * G) {   // lane t pushes this CTA's partial into CTA t's table and signals CTA t's barrier (every CTA pushes in
+                                      // every round, with or without a trial of its own: see the note on cbuf)
                     double cta = 0.0;
 #pragma unroll
                     for (int q = 0; q < ALIGN_WARPS; q++) cta += hdr->warp_cost[q];
-                    dsmem_push_f64(&hdr->cl_cost[cbuf][crank], &hdr->xbar[cbuf], (unsigned)tid, cta);
-                    if (tid == 0) mbar_expect_tx(&hdr->xbar[cbuf], CL * 8);
+                    dsmem_push_f64(&hdr->cl_cost[cbuf][grp * CL + crank], &hdr->xbar[cbuf], (unsigned)tid, cta);
+                    if (tid == 0) mbar_expect_tx(&hdr->xbar[cbuf], CL * G * 8);
                 }
-                if (a.dbg) mbar_wait_dbg(&hdr->xbar[cbuf], xphase[cbuf], a.dbg, 2 + cbuf, (int)crank, level, mode, n_evals, n_grads);
+                if (a.dbg) mbar_wait_dbg(&hdr->xbar[cbuf], xphase[cbuf], a.dbg, 2 + cbuf, (int)prank, level, mode, n_evals, n_grads);
                 else mbar_wait(&hdr->xbar[cbuf], xphase[cbuf]);
                 xphase[cbuf] ^= 1;
-                double tot = 0.0;
-#pragma unroll
-                for (int q = 0; q < CL; q++) tot += hdr->cl_cost[cbuf][q];
+                const double *table = hdr->cl_cost[cbuf];
                 cbuf ^= 1;
-                const float cost = (float)tot;
-                n_evals++;
-                if (mode == 0) {
-                    prev_cost = cost;
-                    mode = 1;   // it == 0 < 50
-                } else if (cost < prev_cost) {
+                trc.stamp(4, nvalid);
+                // replay of the sequential driver over the costs of this round, in order
+                for (int g = 0; g < nvalid && mode != 3 && mode != 1; g++) {
+                    double tot = 0.0;
 #pragma unroll
-                    for (int k = 0; k < 6; k++) x0[k] = xt[k];
-                    prev_cost = cost;
-                    it++;       // outer loop increment after `break`
-                    mode = (it < 50) ? 1 : 3;
-                    x0slot = xtslot;                 // the accepted pose keeps its matrix
-                    if (xtslot >= 16) sp ^= 1; else tb ^= 1;   // ... and the next gradient / fallback writes elsewhere
-                } else if (fabsf(cost - prev_cost) < 1.0f) {
-                    mode = 3;
-                } else {
-                    kstep = kstep / 2;
-                    jstep++;
-                    it++;       // inner loop increment
-                    if (it < 50) {
+                    for (int q = 0; q < CL; q++) tot += table[g * CL + q];
+                    const float cost = (float)tot;
+                    n_evals++;
+                    if (mode == 0) {
+                        prev_cost = cost;
+                        mode = 1;   // it == 0 < 50
+                    } else if (cost < prev_cost) {
 #pragma unroll
-                        for (int k = 0; k < 6; k++) xt[k] = x0[k] + (kstep * grad[k]);
-                        if (jstep < 8) {
-                            xtslot = tb * 8 + jstep;
-                        } else {   // rare: more than 7 halvings — compute on demand
-                            xtslot = 16 + sp;
-                            if (tid == 0) dev_rodrigues_d(-xt[3], -xt[4], -xt[5], hdr->Rd[xtslot]);
-                            __syncthreads();
-                        }
-                        mode = 2;
-                    } else {
+                        for (int k = 0; k < 6; k++) x0[k] = xt[k];
+                        prev_cost = cost;
+                        it++;       // outer loop increment after `break`
+                        mode = (it < 50) ? 1 : 3;
+                        x0slot = xtslot;                 // the accepted pose keeps its matrix
+                        if (xtslot >= 2 * ALIGN_DEPTH) sp ^= 1; else tb ^= 1;   // ... and the next gradient / fallback writes elsewhere
+                    } else if (fabsf(cost - prev_cost) < 1.0f) {
                         mode = 3;
+                    } else {
+                        kstep = kstep / 2;
+                        jstep++;
+                        it++;       // inner loop increment
+                        if (it < 50) {
+#pragma unroll
+                            for (int k = 0; k < 6; k++) xt[k] = x0[k] + (kstep * grad[k]);
+                            if (jstep < ALIGN_DEPTH) {
+                                xtslot = tb * ALIGN_DEPTH + jstep;
+                            } else {   // rare: ALIGN_DEPTH halvings and more — compute on demand (g is the last trial of its round here)
+                                xtslot = 2 * ALIGN_DEPTH + sp;
+                                if (tid == 0) dev_rodrigues_d(-xt[3], -xt[4], -xt[5], hdr->Rd[xtslot]);
+                                __syncthreads();
+                            }
+                            mode = 2;
+                        } else {
+                            mode = 3;
+                        }
                     }
                 }
             } else {
-                // ---------------- get_gradient at x0 (Hessian rebuilt on every call)
+                // ---------------- get_gradient at x0 (Hessian rebuilt on every call); every group for itself
+                const double *Rd = hdr->Rd[x0slot];
+                const float tx = x0[0], ty = x0[1], tz = x0[2];
                 float Rif[9];
 #pragma unroll
                 for (int k = 0; k < 9; k++) Rif[k] = (float)Rd[k];   // inv_rot_mat = float(Rodrigues(-r))
@@ -535,14 +468,14 @@ __global__ void __launch_bounds__(ALIGN_THREADS, 1) sparse_align_kernel(AlignArg
                 for (int k = 0; k < NGRAD; k++) acc[k] = 0.f;
                 for (int pass = 0; pass < npass; pass++) {
                     const int i = ((pass * ALIGN_WARPS + warp) * CL + (int)crank) * 8 + quad;
-                    if (i >= n) continue;
-                    if (a.flags && (a.flags[i] & SVO_F_IGN_TEMP)) continue;
+                    if (pass == 0 ? !act_first : ((i >= n) || (a.flags && (a.flags[i] & SVO_F_IGN_TEMP)))) continue;
                     const size_t slot = (size_t)4 * i + row;
                     const unsigned mask = __float_as_uint(scr[(size_t)12 * SN + slot]);
                     float g0v[4], g1v[4], spv[4];
 #pragma unroll
                     for (int c = 0; c < 4; c++) { g0v[c] = scr[(size_t)c * SN + slot]; g1v[c] = scr[(size_t)(4 + c) * SN + slot]; spv[c] = scr[(size_t)(8 + c) * SN + slot]; }
-                    const float Px = a.kps3d[3 * i], Py = a.kps3d[3 * i + 1], Pz = a.kps3d[3 * i + 2];
+                    const float Px = pass == 0 ? P_first[0] : a.kps3d[3 * i], Py = pass == 0 ? P_first[1] : a.kps3d[3 * i + 1],
+                                Pz = pass == 0 ? P_first[2] : a.kps3d[3 * i + 2];
                     float u, v;
                     dev_project_nd(nodist, Rd, Px, Py, Pz, tx, ty, tz, lfx, lfy, lcx, lcy, cam, u, v);
                     float X, Y, Z;
@@ -580,6 +513,7 @@ __global__ void __launch_bounds__(ALIGN_THREADS, 1) sparse_align_kernel(AlignArg
                     }
                 }
                 // warp reduce (float) -> CTA partial (double, 27 threads) -> every CTA's table through DSMEM
+                trc.stamp(7);
                 {
                     const float t = warp_sum_scatter<NGRAD>(acc, lane);   // lane k: warp sum of term k
                     if (lane < NGRAD) hdr->warp_grad[warp][lane] = t;
@@ -590,10 +524,10 @@ __global__ void __launch_bounds__(ALIGN_THREADS, 1) sparse_align_kernel(AlignArg
 #pragma unroll
                     for (int q = 0; q < ALIGN_WARPS; q++) t += (double)hdr->warp_grad[q][tid];
 #pragma unroll
-                    for (unsigned dst = 0; dst < CL; dst++) dsmem_push_f64(&hdr->cl_grad[crank][tid], &hdr->xbar[2], dst, t);
+                    for (unsigned dst = 0; dst < CL; dst++) dsmem_push_f64(&hdr->cl_grad[crank][tid], &hdr->xbar[2], grp * CL + dst, t);
                     if (tid == 0) mbar_expect_tx(&hdr->xbar[2], CL * NGRAD * 8);
                 }
-                if (a.dbg) mbar_wait_dbg(&hdr->xbar[2], xphase[2], a.dbg, 4, (int)crank, level, mode, n_evals, n_grads);
+                if (a.dbg) mbar_wait_dbg(&hdr->xbar[2], xphase[2], a.dbg, 4, (int)prank, level, mode, n_evals, n_grads);
                 else mbar_wait(&hdr->xbar[2], xphase[2]);
                 xphase[2] ^= 1;
                 if (tid < NGRAD) {
@@ -603,10 +537,15 @@ __global__ void __launch_bounds__(ALIGN_THREADS, 1) sparse_align_kernel(AlignArg
                     hdr->red_out[tid] = t;
                 }
                 __syncthreads();
-                if (tid == 0) {   // every CTA solves the same 6x6 system redundantly: no further cluster traffic
+                trc.stamp(8);
+                n_grads++;
+                // every CTA solves the same 6x6 system redundantly (no further cluster traffic), and so do 16 lanes of it (two in each
+                // warp) side by side, each going straight on to the matrix of "its" trial pose x0 + 2^-j grad, j = warp + 8 * lane:
+                // no block barrier between the solve and the Rodrigues formulas
+                if (lane < ALIGN_DEPTH / ALIGN_WARPS) {
                     double dx[6];
                     float delta[6], pg[6], Rf[9];
-                    if (solve6(hdr->red_out, hdr->red_out + 21, dx)) {
+                    if (dev_solve6(hdr->red_out, hdr->red_out + 21, dx)) {
 #pragma unroll
                         for (int k = 0; k < 6; k++) delta[k] = (float)dx[k];
                     } else {
@@ -621,39 +560,41 @@ __global__ void __launch_bounds__(ALIGN_THREADS, 1) sparse_align_kernel(AlignArg
                     float g[6];
                     dev_m33v(Rf, pg[0], pg[1], pg[2], g[0], g[1], g[2]);
                     dev_m33v(Rf, pg[3], pg[4], pg[5], g[3], g[4], g[5]);
+                    if (tid == 0) {
 #pragma unroll
-                    for (int k = 0; k < 6; k++) hdr->grad[k] = g[k];
+                        for (int k = 0; k < 6; k++) hdr->grad[k] = g[k];
+                    }
+                    const int j = warp + ALIGN_WARPS * lane;
+                    float kj = 1.f;
+                    for (int q = 0; q < j; q++) kj = kj / 2;   // the driver's own sequence of halvings
+                    dev_rodrigues_d(-(x0[3] + (kj * g[3])), -(x0[4] + (kj * g[4])), -(x0[5] + (kj * g[5])), hdr->Rd[tb * ALIGN_DEPTH + j]);
                 }
                 __syncthreads();
-                n_grads++;
 #pragma unroll
                 for (int k = 0; k < 6; k++) grad[k] = hdr->grad[k];
-                if (lane == 0) {   // warp j prepares the matrix of x0 + 2^-j grad (same float expressions as the driver)
-                    float kj = 1.f;
-                    for (int q = 0; q < warp; q++) kj = kj / 2;
-                    dev_rodrigues_d(-(x0[3] + (kj * grad[3])), -(x0[4] + (kj * grad[4])), -(x0[5] + (kj * grad[5])), hdr->Rd[tb * 8 + warp]);
-                }
-                __syncthreads();
                 kstep = 1.f;
                 jstep = 0;
 #pragma unroll
                 for (int k = 0; k < 6; k++) xt[k] = x0[k] + (kstep * grad[k]);
-                xtslot = tb * 8;
+                xtslot = tb * ALIGN_DEPTH;
                 mode = 2;
+                trc.stamp(5);
                 if (a.probe_level >= 0) {
-                    if (tid == 0 && crank == 0)
+                    if (tid == 0 && prank == 0)
                         for (int k = 0; k < 6; k++) a.probe_grad[k] = grad[k];
                     mode = 3;
                 }
             }
         }
-        if (tid == 0 && crank == 0 && level < 8) { a.evals_out[2 * level] = n_evals; a.evals_out[2 * level + 1] = n_grads; }
+        if (tid == 0 && prank == 0 && level < 8) { a.evals_out[2 * level] = n_evals; a.evals_out[2 * level + 1] = n_grads; }
     }
-    if (tid == 0 && crank == 0) {
+    if (tid == 0 && prank == 0) {
         for (int k = 0; k < 6; k++) a.pose_out[k] = x0[k];
         *a.cost_out = prev_cost;
     }
-    if (a.rd_out && crank == 0 && tid < 9) a.rd_out[tid] = hdr->Rd[x0slot][tid];   // the matrix of the final pose, for KLT / refinement
+    if (a.rd_out && prank == 0 && tid < 9) a.rd_out[tid] = hdr->Rd[x0slot][tid];   // the matrix of the final pose, for KLT / refinement
+    trc.stamp(6);
+    trc.finish();
     cluster_sync_all();   // no CTA exits while others may still write into its shared memory
 }
 
@@ -684,43 +625,49 @@ size_t align_scratch_floats(int max_kps) { return (size_t)13 * 4 * max_kps; }
 cudaError_t align_init_device()
 {
     cudaError_t e = cudaSuccess;
-#define ALIGN_OPT_IN(c) if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_kernel<true, c>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024))
-    ALIGN_OPT_IN(1); ALIGN_OPT_IN(2); ALIGN_OPT_IN(4); ALIGN_OPT_IN(8); ALIGN_OPT_IN(16);
+#define ALIGN_OPT_IN(c, g) \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_kernel<true, c, g>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)); \
+    if (e == cudaSuccess && (c) * (g) > 8) e = cudaFuncSetAttribute(sparse_align_kernel<true, c, g>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1); \
+    if (e == cudaSuccess && (c) * (g) > 8) e = cudaFuncSetAttribute(sparse_align_kernel<false, c, g>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1)
+    ALIGN_OPT_IN(1, 1); ALIGN_OPT_IN(2, 1); ALIGN_OPT_IN(4, 1); ALIGN_OPT_IN(8, 1); ALIGN_OPT_IN(16, 1);
+    ALIGN_OPT_IN(8, 2); ALIGN_OPT_IN(4, 2); ALIGN_OPT_IN(4, 4);
 #undef ALIGN_OPT_IN
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_kernel<true, 16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(sparse_align_kernel<false, 16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     return e;
 }
 
-template <int CL>
+template <int CL, int G>
 static cudaError_t launch_align_cl(const AlignArgs &a, bool fit, size_t need, cudaStream_t st)
 {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(CL, 1, 1);
+    cfg.gridDim = dim3(CL * G, 1, 1);
     cfg.blockDim = dim3(ALIGN_THREADS, 1, 1);
     cfg.dynamicSmemBytes = HDR_BYTES + (fit ? need : 0);
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[0].val.clusterDim.x = CL * G; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (fit) return cudaLaunchKernelEx(&cfg, sparse_align_kernel<true, CL>, a);
-    return cudaLaunchKernelEx(&cfg, sparse_align_kernel<false, CL>, a);
+    if (fit) return cudaLaunchKernelEx(&cfg, sparse_align_kernel<true, CL, G>, a);
+    return cudaLaunchKernelEx(&cfg, sparse_align_kernel<false, CL, G>, a);
 }
 
-// cluster = number of SMs that share one frame's solve: 8 minimises the latency of a single sequence (75 us), 1-2
+// cluster = number of SMs that share one evaluation of a frame's solve: 8 minimises the latency of a single sequence, 1-2
 // minimise the SM time per frame when many sequences are in flight (the solve is a chain of ~28 dependent evaluations,
-// so SMs x duration is what a frame costs the GPU)
+// so SMs x duration is what a frame costs the GPU).  groups > 1: that many such clusters side by side, one trial pose of the
+// line search each (svo_set_solver_width); the results do not depend on it.
 cudaError_t launch_align(const AlignArgs &a, cudaStream_t st)
 {
     size_t need;
     bool fit = align_levels_fit(a, need);
+    if (a.groups == 2 && a.cluster == 8) return launch_align_cl<8, 2>(a, fit, need, st);
+    if (a.groups == 2 && a.cluster == 4) return launch_align_cl<4, 2>(a, fit, need, st);
+    if (a.groups == 4 && a.cluster == 4) return launch_align_cl<4, 4>(a, fit, need, st);
     switch (a.cluster) {
-    case 1: return launch_align_cl<1>(a, fit, need, st);
-    case 2: return launch_align_cl<2>(a, fit, need, st);
-    case 4: return launch_align_cl<4>(a, fit, need, st);
-    case 16: return launch_align_cl<16>(a, fit, need, st);
-    default: return launch_align_cl<8>(a, fit, need, st);
+    case 1: return launch_align_cl<1, 1>(a, fit, need, st);
+    case 2: return launch_align_cl<2, 1>(a, fit, need, st);
+    case 4: return launch_align_cl<4, 1>(a, fit, need, st);
+    case 16: return launch_align_cl<16, 1>(a, fit, need, st);
+    default: return launch_align_cl<8, 1>(a, fit, need, st);
     }
 }

@@ -331,6 +331,149 @@ __device__ __forceinline__ void block_reduce_sum(double (&v)[NV], double *scratc
     }
     __syncthreads();
 }
+// ---- thread-block clusters: mbarrier, 1-D TMA bulk copies and distributed-shared-memory pushes (alignment and refinement solvers)
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity)
+{
+    uint32_t ok = 0;
+    const uint32_t addr = smem_u32(bar);
+    while (!ok) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ unsigned cluster_ctarank()
+{
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// store a double into the shared memory of CTA `rank` of this cluster (distributed shared memory)
+__device__ __forceinline__ void dsmem_store_f64(void *local_smem_ptr, unsigned rank, double v)
+{
+    uint32_t local = smem_u32(local_smem_ptr), remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(rank));
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(remote), "d"(v) : "memory");
+}
+
+// Push a double into CTA `rank`'s shared memory and signal that CTA's mbarrier with the 8 transferred bytes
+// (st.async + complete_tx): data and notification travel together, no cluster-scope fence or barrier is needed.
+__device__ __forceinline__ void dsmem_push_f64(void *local_slot, unsigned long long *local_bar, unsigned rank, double v)
+{
+    uint32_t slot = smem_u32(local_slot), bar = smem_u32(local_bar), rslot, rbar;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rslot) : "r"(slot), "r"(rank));
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(bar), "r"(rank));
+    asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(rslot), "l"(__double_as_longlong(v)), "r"(rbar)
+                 : "memory");
+}
+
+// 1 / d for the pivots of the 6x6 solve: hardware reciprocal approximation (MUFU.RCP64H) refined by two Newton steps in fused
+// arithmetic (relative error far below one ulp before the final rounding) — a third of the latency of the IEEE division, which
+// sits six times on the critical path of every gradient round of both solvers
+__device__ __forceinline__ double dev_rcp_fast(double d)
+{
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+    x = fma(x, fma(-d, x, 1.0), x);
+    x = fma(x, fma(-d, x, 1.0), x);
+    x = fma(x, fma(-d, x, 1.0), x);
+    return x;
+}
+
+// 6x6 SPD solve in double (LDL^T), the solvers' own arithmetic (the reference inverts in float: any accurate solve is within the
+// pose tolerance), so it is written for latency: explicitly fused multiply-adds (this file is compiled with -fmad=false for the
+// reference-exact float code) and one fast reciprocal per pivot.  Returns false when H is not numerically positive definite.
+__device__ __forceinline__ bool dev_solve6(const double *Hu /*21 upper-tri row-major*/, const double *b, double *x)
+{
+    double A[6][6];
+    {
+        int k = 0;
+#pragma unroll
+        for (int i = 0; i < 6; i++)
+#pragma unroll
+            for (int j = i; j < 6; j++) { A[i][j] = Hu[k]; A[j][i] = Hu[k]; k++; }
+    }
+    double maxd = 0;
+#pragma unroll
+    for (int i = 0; i < 6; i++) maxd = fmax(maxd, A[i][i]);
+    if (!(maxd > 0)) return false;
+    // W[i][j] = L[i][j] * D[j] (the un-normalised column), L[i][j] = W[i][j] / D[j]
+    double L[6][6], W[6][6], Dinv[6];
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+        double d = A[j][j];
+#pragma unroll
+        for (int q = 0; q < j; q++) d = fma(-W[j][q], L[j][q], d);
+        if (!(d > 1e-13 * maxd)) { ok = false; d = 1.0; }
+        Dinv[j] = dev_rcp_fast(d);
+#pragma unroll
+        for (int i = j + 1; i < 6; i++) {
+            double t = A[i][j];
+#pragma unroll
+            for (int q = 0; q < j; q++) t = fma(-W[i][q], L[j][q], t);
+            W[i][j] = t;
+            L[i][j] = t * Dinv[j];
+        }
+    }
+    if (!ok) return false;
+    double y[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        double t = b[i];
+#pragma unroll
+        for (int q = 0; q < i; q++) t = fma(-L[i][q], y[q], t);
+        y[i] = t;
+    }
+#pragma unroll
+    for (int i = 5; i >= 0; i--) {
+        double t = y[i] * Dinv[i];
+#pragma unroll
+        for (int q = i + 1; q < 6; q++) t = fma(-L[q][i], x[q], t);
+        x[i] = t;
+    }
+    return true;
+}
+
+// developer aid (SVO_SOLVER_TRACE): one thread stamps the phases of a solver kernel with the SM clock
+struct SolverTrace {
+    unsigned long long *buf; int n; bool on;
+    __device__ __forceinline__ SolverTrace(unsigned long long *b, bool writer) : buf(b), n(0), on(b != nullptr && writer) {}
+    __device__ __forceinline__ void stamp(int tag, int extra = 0)
+    {
+        if (on && n < 1000) { buf[1 + n] = ((unsigned long long)clock64() << 16) | ((unsigned long long)(extra & 255) << 8) | (unsigned)(tag & 255); n++; }
+    }
+    __device__ __forceinline__ void finish() { if (on) buf[0] = (unsigned long long)n; }
+};
 #endif  // __CUDACC__
 
 #define SVO_CUDA_CHECK(ctx_err, expr)                                                                   \

@@ -150,6 +150,8 @@ struct svo_ctx {
     };
     std::vector<FrameGraph> graphs;
     bool use_graphs = true;
+    int solver_width = -1;    // svo_set_solver_width: -1 auto (wide while fewer than four sequences share the device), 0 sequential, 1 wide
+    int align_groups4 = 4;    // wide line search with 4-CTA clusters: 4 or 2 trial poses per round (developer switch SVO_ALIGN_GROUPS)
     int align_cluster = 0;    // SMs per alignment solve (svo_set_align_cluster); 0 = by keypoint count: 8, or 16 above 1024 keypoints
     bool use_fork = true;     // two-branch frame graph (SVO_NO_FORK=1: linear chain)
     bool import_rode = false; // the keypoint import of the frame being captured is part of lk_side_kernel (no launch of its own)
@@ -168,6 +170,7 @@ struct svo_ctx {
     uint32_t *d_rect_packed[2] = {nullptr, nullptr};
     uint8_t *d_raw[2] = {nullptr, nullptr};   // raw (distorted) images of the frame being uploaded
     int *h_marks = nullptr, *d_marks = nullptr;   // SVO_DEBUG_MARKS
+    unsigned long long *h_trace = nullptr, *d_trace = nullptr;   // SVO_SOLVER_TRACE: 2 x 1024 words (alignment, refinement), mapped host memory
     int mark_seq = 0;
     char err[256];
 };
@@ -289,9 +292,20 @@ extern "C" int svo_ctx_create(const svo_camera_settings *s, int device, int widt
         static int counter = 0;
         ctx->use_ingest = (counter++ & 1) == 0;
     }
+    if (getenv("SVO_SOLVER_WIDTH")) {
+        const int w = atoi(getenv("SVO_SOLVER_WIDTH"));
+        if (w >= -1 && w <= 1) ctx->solver_width = w;
+    }
+    if (getenv("SVO_ALIGN_GROUPS") && atoi(getenv("SVO_ALIGN_GROUPS")) == 2) ctx->align_groups4 = 2;
     if (getenv("SVO_ALIGN_CLUSTER")) {
         const int c = atoi(getenv("SVO_ALIGN_CLUSTER"));
         if (c == 1 || c == 2 || c == 4 || c == 8 || c == 16) ctx->align_cluster = c;
+    }
+    if (getenv("SVO_SOLVER_TRACE")) {
+        if (cudaHostAlloc(&ctx->h_trace, 2048 * sizeof(unsigned long long), cudaHostAllocMapped) == cudaSuccess) {
+            memset(ctx->h_trace, 0, 2048 * sizeof(unsigned long long));
+            cudaHostGetDevicePointer((void **)&ctx->d_trace, ctx->h_trace, 0);
+        }
     }
     if (getenv("SVO_DEBUG_MARKS")) {
         if (cudaHostAlloc(&ctx->h_marks, 64 * sizeof(int), cudaHostAllocMapped) == cudaSuccess) {
@@ -420,6 +434,8 @@ extern "C" int svo_ctx_destroy(svo_ctx *ctx)
     for (int k = 0; k < 2; k++) if (ctx->h_stage[k]) cudaFreeHost(ctx->h_stage[k]);
     if (ctx->d_io) cudaFree(ctx->d_io);
     if (ctx->h_io) cudaFreeHost(ctx->h_io);
+    if (ctx->h_marks) cudaFreeHost(ctx->h_marks);
+    if (ctx->h_trace) cudaFreeHost(ctx->h_trace);
     if (ctx->d_align_scratch) cudaFree(ctx->d_align_scratch);
     if (ctx->d_detect_scratch) cudaFree(ctx->d_detect_scratch);
     if (ctx->d_cell_xy) cudaFree(ctx->d_cell_xy);
@@ -786,6 +802,16 @@ extern "C" int svo_debug_zero_copy_bandwidth(svo_ctx *ctx, const void *pinned_ho
     return SVO_OK;
 }
 
+extern "C" int svo_debug_solver_trace(svo_ctx *ctx, int which, unsigned long long *out, int cap)
+{
+    if (!ctx || !out || which < 0 || which > 1 || cap < 1) return SVO_ERR_INVALID;
+    if (!ctx->h_trace) { out[0] = 0; return SVO_OK; }
+    const volatile unsigned long long *src = ctx->h_trace + 1024 * which;
+    const unsigned long long n0 = src[0]; const int n = n0 < 1000 ? (int)n0 : 1000;
+    for (int k = 0; k <= n && k < cap; k++) out[k] = src[k];
+    return SVO_OK;
+}
+
 extern "C" int svo_debug_marks(svo_ctx *ctx, int *out64)
 {
     if (!ctx || !out64) return SVO_ERR_INVALID;
@@ -794,12 +820,27 @@ extern "C" int svo_debug_marks(svo_ctx *ctx, int *out64)
     return SVO_OK;
 }
 
+// wide line searches (svo_set_solver_width) for this launch / capture?
+static bool wide_solvers(const svo_ctx *ctx) { return ctx->solver_width < 0 ? ctx->arena->users < 4 : ctx->solver_width != 0; }
+
 extern "C" int svo_set_align_cluster(svo_ctx *ctx, int ctas)
 {
     if (!ctx || (ctas != 0 && ctas != 1 && ctas != 2 && ctas != 4 && ctas != 8 && ctas != 16)) return SVO_ERR_INVALID;
     if (ctx->track_pending) { snprintf(ctx->err, sizeof(ctx->err), "svo_set_align_cluster while a frame is in flight"); return SVO_ERR_STATE; }
     if (ctas != ctx->align_cluster) {
         ctx->align_cluster = ctas;
+        for (auto &g : ctx->graphs) destroy_graph(g);   // captured sequences hold the old launch shape
+        ctx->graphs.clear();
+    }
+    return SVO_OK;
+}
+
+extern "C" int svo_set_solver_width(svo_ctx *ctx, int wide)
+{
+    if (!ctx || wide < -1 || wide > 1) return SVO_ERR_INVALID;
+    if (ctx->track_pending) { snprintf(ctx->err, sizeof(ctx->err), "svo_set_solver_width while a frame is in flight"); return SVO_ERR_STATE; }
+    if (wide != ctx->solver_width) {
+        ctx->solver_width = wide;
         for (auto &g : ctx->graphs) destroy_graph(g);   // captured sequences hold the old launch shape
         ctx->graphs.clear();
     }
@@ -996,7 +1037,15 @@ static void fill_align_args(svo_ctx *ctx, int prev_slot, int cur_slot, AlignArgs
     a.scratch = ctx->d_align_scratch; a.max_kps = ctx->max_kps; a.cam = ctx->cam;
     a.probe_level = -1; a.probe_grad = nullptr;
     a.dbg = ctx->d_marks ? ctx->d_marks + 16 : nullptr;
+    a.trace = ctx->d_trace;
     a.cluster = ctx->align_cluster ? ctx->align_cluster : (n > 1024 ? 16 : 8);
+    // wide line search: two (cluster 8) or up to four (cluster 4) trial poses per round; a frame of more than 1024 keypoints keeps
+    // all 16 SMs of the largest cluster on one evaluation
+    a.groups = 1;
+    if (wide_solvers(ctx)) {
+        if (a.cluster == 8) a.groups = 2;
+        else if (a.cluster == 4) a.groups = ctx->align_groups4;
+    }
     a.rd_out = nullptr;
     (void)n;
 }
@@ -1119,8 +1168,8 @@ extern "C" int svo_reproj_refine(svo_ctx *ctx, const float *kps2d, const float *
     a.kps2d = DP(float, kps2d_ref_in); a.kps3d = DP(float, kps3d); a.flags = DP(uint8_t, flags); a.n_ptr = DP(int, n);
     a.pose_in = DP(float, pose_aligned); a.pose_out = DP(float, pose_refined);
     a.cost_out = DP(float, costs) + 1; a.evals_out = DP(int, evals) + 16; a.cam = ctx->cam;
-    a.rd_in = nullptr; a.rd_out = nullptr;
-    launch_refine(a, (n + 127) / 128 * 128, ctx->stream);
+    a.rd_in = nullptr; a.rd_out = nullptr; a.trace = ctx->d_trace ? ctx->d_trace + 1024 : nullptr;
+    launch_refine(a, (n + 127) / 128 * 128, wide_solvers(ctx), ctx->stream);
     ctx->launch_total += 1;
     CK(cudaGetLastError());
     if ((rc = down(ctx, pose_out, ctx->lay.pose_refined, 24))) return rc;
@@ -1401,10 +1450,10 @@ static int enqueue_track(svo_ctx *ctx, int prev_slot, int cur_slot, int n, int g
     ra.kps2d = DP(float, kps2d_ref_in); ra.kps3d = DP(float, kps3d); ra.flags = DP(uint8_t, flags); ra.n_ptr = DP(int, n);
     ra.pose_in = DP(float, pose_aligned); ra.pose_out = DP(float, pose_refined);
     ra.cost_out = DP(float, costs) + 1; ra.evals_out = DP(int, evals) + 16; ra.cam = ctx->cam;
-    ra.rd_in = DP(double, rd_aligned); ra.rd_out = DP(double, rd_refined);
+    ra.rd_in = DP(double, rd_aligned); ra.rd_out = DP(double, rd_refined); ra.trace = ctx->d_trace ? ctx->d_trace + 1024 : nullptr;
     const int ref_bucket = std::min(ctx->max_kps, (grid_n + 127) / 128 * 128);   // == the graph's bucket
-    launch_refine(ra, ref_bucket, ctx->stream); launches++;
-    for (int k = 0; k < diag_dup("refine"); k++) launch_refine(ra, ref_bucket, ctx->stream);
+    launch_refine(ra, ref_bucket, wide_solvers(ctx), ctx->stream); launches++;
+    for (int k = 0; k < diag_dup("refine"); k++) launch_refine(ra, ref_bucket, wide_solvers(ctx), ctx->stream);
     mark(ctx, 7);
     if (prof) CK(cudaEventRecord(ctx->sev[5], ctx->stream));
     if (n > 0) {

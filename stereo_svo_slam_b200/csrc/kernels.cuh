@@ -119,9 +119,11 @@ struct AlignArgs {
     // probe mode: single level, single evaluation
     int probe_level;       // -1 = normal
     float *probe_grad;     // 6
-    int cluster;           // CTAs (SMs) cooperating on the frame: 1, 2, 4 or 8
+    int cluster;           // CTAs (SMs) cooperating on one evaluation of the frame: 1, 2, 4, 8 or 16
+    int groups;            // such clusters side by side, one trial pose of the line search each: 1, or 2 / 4 with cluster 8 / 4
     double *rd_out;        // 9: Rodrigues(-r) of pose_out in double, for the kernels that project with the aligned pose next (or null)
     int *dbg;              // developer aid (SVO_DEBUG_MARKS): where a stuck barrier wait was, else null
+    unsigned long long *trace;   // developer aid (SVO_SOLVER_TRACE): [0] = entries, then (clock64 << 16 | extra << 8 | tag) per phase, else null
 };
 cudaError_t launch_align(const AlignArgs &a, cudaStream_t st);
 size_t align_scratch_floats(int max_kps);
@@ -181,8 +183,9 @@ struct RefineArgs {
     DevCam cam;
     const double *rd_in;   // 9: Rodrigues(-r) of pose_in as the alignment kernel left it (or null: computed here)
     double *rd_out;        // 9: Rodrigues(-r) of pose_out (or null)
+    unsigned long long *trace;   // developer aid (SVO_SOLVER_TRACE), as in AlignArgs
 };
-void launch_refine(const RefineArgs &a, int bucket, cudaStream_t st);
+void launch_refine(const RefineArgs &a, int bucket, bool wide, cudaStream_t st);
 void launch_project(const float *pose, const float *kps3d, const int *n_ptr, int max_kps, DevCam cam, float *kps2d, cudaStream_t st);
 
 // ---- stereo.cu

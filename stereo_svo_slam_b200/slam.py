@@ -92,6 +92,11 @@ class StereoSlam:
         1-2 when many sequences share the GPU."""
         self.context().set_align_cluster(ctas)
 
+    def set_solver_width(self, wide):
+        """1: wide line searches (several trial poses per round on idle SMs: lowest latency of one sequence), 0: sequential
+        (fewest SMs per frame), -1: automatic (svo_set_solver_width).  Same results bit for bit."""
+        self.context().set_solver_width(wide)
+
     # ---- StereoSlam::new_image (stereo_slam.cpp:123)
     def new_image(self, left, right, time_stamp):
         left, right = self._img(left), self._img(right)

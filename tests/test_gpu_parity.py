@@ -467,6 +467,55 @@ def test_scheduling_knobs_are_bit_identical(monkeypatch, knob, setting):
         assert a2.shape == b2.shape and (a2 == b2).all() and (a3 == b3).all()
 
 
+@pytest.mark.parametrize("cfg,frames,base_env,wide_env", [
+    ("C3", 20, {"SVO_SOLVER_WIDTH": "0"}, {"SVO_SOLVER_WIDTH": "1"}),                                   # 2 x 8 alignment CTAs, 8 refinement CTAs
+    ("C3", 12, {"SVO_SOLVER_WIDTH": "0", "SVO_ALIGN_CLUSTER": "4"}, {"SVO_SOLVER_WIDTH": "1", "SVO_ALIGN_CLUSTER": "4"}),   # 4 x 4
+    ("C3", 12, {"SVO_SOLVER_WIDTH": "0", "SVO_ALIGN_CLUSTER": "4"}, {"SVO_SOLVER_WIDTH": "1", "SVO_ALIGN_CLUSTER": "4", "SVO_ALIGN_GROUPS": "2"}),
+    ("S", 30, {"SVO_SOLVER_WIDTH": "0"}, {}),                                                            # the default of a lone sequence is wide
+    ("C4", 6, {"SVO_SOLVER_WIDTH": "0"}, {"SVO_SOLVER_WIDTH": "1"}),                                    # > 1024 keypoints: 512-thread refinement CTAs
+])
+def test_wide_line_search_is_bit_identical(monkeypatch, cfg, frames, base_env, wide_env):
+    """svo_set_solver_width: several trial poses of a line search per round (alignment: groups of CTAs of one cluster, refinement:
+    one CTA per trial) and the reference's accept / halve / stop rule replayed over the costs in order must give the sequential
+    search's poses, keypoints and evaluation COUNTS bit for bit (estimate_pose_at_level pose_estimator.cpp:166-222,
+    PoseRefiner::update_pose pose_refinement.cpp:236-290)."""
+    from stereo_svo_slam_b200 import StereoSlam
+    gcs, _ = mk(cfg)
+    c = synth.CONFIGS[cfg]
+    seq = synth.make_sequence(cfg)
+    runs = []
+    for env in (base_env, wide_env):
+        for k in ("SVO_SOLVER_WIDTH", "SVO_ALIGN_CLUSTER", "SVO_ALIGN_GROUPS"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        g = StereoSlam(gcs, c["width"], c["height"])
+        poses, kps, cnt = [], [], []
+        for k in range(frames):
+            L, R = seq.render(k)
+            g.new_image(L, R, k / 20.0)
+            poses.append(g.pose())
+            f = g.get_frame()
+            kps.append((f.kps.kps2d.copy(), f.kps.kps3d.copy()))
+            cnt.append(list(g.last_counters().values()))
+        runs.append((np.array(poses), kps, np.array(cnt), g.keyframe_count()))
+        g.close()
+    (p0, k0, c0, n0), (p1, k1, c1, n1) = runs
+    assert n1 == n0 and (p1 == p0).all()
+    assert (c1 == c0).all(), np.argwhere(c1 != c0)[:5]
+    assert c0[1:, 2].min() >= 4 and c0[1:, 4].min() >= 2      # the solvers did run (cost evaluations of alignment and refinement)
+    for (a2, a3), (b2, b3) in zip(k1, k0):
+        assert a2.shape == b2.shape and (a2 == b2).all() and (a3 == b3).all()
+
+
+def test_solver_width_knob(c3ctx):
+    ctx, _, _ = c3ctx
+    for w in (1, 0, -1):
+        ctx.set_solver_width(w)
+    with pytest.raises(capi.SvoError):
+        ctx.set_solver_width(2)
+
+
 def test_error_behaviour(c3ctx):
     ctx, gcs, _ = c3ctx
     with pytest.raises(capi.SvoError):
