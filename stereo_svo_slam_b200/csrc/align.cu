@@ -117,6 +117,65 @@ __device__ __forceinline__ float patch_sum(const uint8_t *img, int pitch, float 
     return v;
 }
 
+// six consecutive pixels at any byte address as exact floats (three aligned words; reads up to 11 bytes past p: inside the 16
+// bytes of slack every staged / stored level has)
+__device__ __forceinline__ void load6f(const uint8_t *p, float (&o)[6])
+{
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(p);
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(addr & ~(uintptr_t)3);
+    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+    const int sh = (int)(addr & 3) * 8;
+    const uint32_t t0 = __funnelshift_r(w0, w1, sh), t1 = __funnelshift_r(w1, w2, sh);
+    o[0] = __uint_as_float(__byte_perm(t0, 0x4B000000u, 0x7440)) - 8388608.0f;
+    o[1] = __uint_as_float(__byte_perm(t0, 0x4B000000u, 0x7441)) - 8388608.0f;
+    o[2] = __uint_as_float(__byte_perm(t0, 0x4B000000u, 0x7442)) - 8388608.0f;
+    o[3] = __uint_as_float(__byte_perm(t0, 0x4B000000u, 0x7443)) - 8388608.0f;
+    o[4] = __uint_as_float(__byte_perm(t1, 0x4B000000u, 0x7440)) - 8388608.0f;
+    o[5] = __uint_as_float(__byte_perm(t1, 0x4B000000u, 0x7441)) - 8388608.0f;
+}
+
+// get_patch_sum at the four pixels (cx, cy), (cx + 1, cy), ... of one patch row (the positions the residual loop of get_gradient
+// visits by repeated `+= 1.f`): their 3x3 footprints overlap, so the 3 x 6 pixels are fetched once (nine word loads instead of
+// thirty-six byte loads); every sum is then formed from its own weights in patch_sum's operation order — the same bits.  Returns
+// false (nothing computed) when the four footprints are not simply one pixel apart (a float increment that crossed a binade and
+// changed the integer part differently): the caller then takes the one-by-one route.
+__device__ __forceinline__ bool patch_sum_row4(const uint8_t *img, int pitch, float cx, float cy, float (&out)[4])
+{
+    float px[4] = {cx, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int c = 1; c < 4; c++) px[c] = px[c - 1] + 1.f;
+    const float sy = cy - 0.5f, fyf = floorf(sy);
+    const int ipy = (int)fyf;
+    const float y2 = sy - fyf, y1 = 1.0f - y2;
+    int ipx[4];
+    float x2[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        const float sx = px[c] - 0.5f, fxf = floorf(sx);
+        ipx[c] = (int)fxf;
+        x2[c] = sx - fxf;
+    }
+    if (ipx[1] != ipx[0] + 1 || ipx[2] != ipx[0] + 2 || ipx[3] != ipx[0] + 3) return false;
+    const uint8_t *s1 = img + ipy * pitch + ipx[0];
+    float r0[6], r1[6], r2[6];
+    load6f(s1, r0); load6f(s1 + pitch, r1); load6f(s1 + 2 * pitch, r2);
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        const float x1 = 1.0f - x2[c];
+        float v = x1 * y1 * r0[c];
+        v = v + y1 * r0[c + 1];
+        v = v + x2[c] * y1 * r0[c + 2];
+        v = v + x1 * r1[c];
+        v = v + r1[c + 1];
+        v = v + x2[c] * r1[c + 2];
+        v = v + x1 * y2 * r2[c];
+        v = v + y2 * r2[c + 1];
+        v = v + x2[c] * y2 * r2[c + 2];
+        out[c] = v;
+    }
+    return true;
+}
+
 // _get_intensity_diff (image_comparison.cpp:9-91); PATCH > 0: compile-time window (footprints cached in registers)
 template <int PATCH>
 __device__ __forceinline__ float intensity_diff(const uint8_t *im1, const uint8_t *im2, int w, int h, int pitch, float c1x, float c1y,
@@ -167,41 +226,66 @@ __device__ __forceinline__ float intensity_diff(const uint8_t *im1, const uint8_
     return intensity;
 }
 
-// One row (4 pixels) of _get_intensity_diff for the 4x4 window of the shipped configurations; other window sizes
-// use the generic whole-patch routine on lane 0 of the quad (d0 carries the whole patch sum, in the reference's order).
-__device__ __forceinline__ void intensity_diff_row(const uint8_t *im1, const uint8_t *im2, int w, int h, int pitch, float c1x, float c1y,
-                                                   float c2x, float c2y, int patch, int row, float &d0, float &d1, float &d2, float &d3)
+// One row (4 pixels) of _get_intensity_diff (image_comparison.cpp:9-91) for the 4x4 window of the shipped configurations, in two
+// halves: the reference-image half (bilinear samples i1 of the previous image at the keypoint: pose-independent, so a lane keeps
+// them in registers for a whole level) and the current-image half (samples at the projection, |i1 - i2|).  Same operations on the
+// same values as the one-piece routine: the same bits.  Other window sizes use the generic whole-patch routine on lane 0 of the
+// quad (d0 carries the whole patch sum, in the reference's order).
+__device__ __forceinline__ void ref_row4(const uint8_t *im1, int w, int h, int pitch, float c1x, float c1y, int row, float (&i1)[4], bool &ok)
+{
+    float half = ((float)4 - 1.0f) / 2.0f;
+    float s1x = c1x - half, s1y = c1y - half;
+    float f1x = floorf(s1x), f1y = floorf(s1y);
+    int ip1x = (int)f1x, ip1y = (int)f1y;
+    float x12 = s1x - f1x, y12 = s1y - f1y;
+    float x11 = 1.0f - x12, y11 = 1.0f - y12;
+    float m11 = x11 * y11, m12 = x12 * y11, m13 = x11 * y12, m14 = x12 * y12;
+    ok = ip1y >= 0 && ip1y + 4 < h && ip1x >= 0 && ip1x + 4 < w;
+#pragma unroll
+    for (int j = 0; j < 4; j++) i1[j] = 0.f;
+    if (ok) {
+        const uint8_t *p1 = im1 + (ip1y + row) * pitch + ip1x;
+        float a0[5], a1[5];
+        load5f(p1, a0); load5f(p1 + pitch, a1);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            float t = 0.f;
+            t += m11 * a0[j]; t += m12 * a0[j + 1]; t += m13 * a1[j]; t += m14 * a1[j + 1];
+            i1[j] = t;
+        }
+    }
+}
+__device__ __forceinline__ void cur_row4(const uint8_t *im2, int w, int h, int pitch, float c2x, float c2y, int row, const float (&i1)[4], bool ok1,
+                                         float &d0, float &d1, float &d2, float &d3)
 {
     d0 = d1 = d2 = d3 = 0.f;
-    if (patch != 4) {
-        if (row == 0) d0 = intensity_diff<0>(im1, im2, w, h, pitch, c1x, c1y, c2x, c2y, patch);
-        return;
-    }
     float half = ((float)4 - 1.0f) / 2.0f;
-    float s1x = c1x - half, s1y = c1y - half, s2x = c2x - half, s2y = c2y - half;
-    float f1x = floorf(s1x), f1y = floorf(s1y), f2x = floorf(s2x), f2y = floorf(s2y);
-    int ip1x = (int)f1x, ip1y = (int)f1y, ip2x = (int)f2x, ip2y = (int)f2y;
-    float x12 = s1x - f1x, y12 = s1y - f1y, x22 = s2x - f2x, y22 = s2y - f2y;
-    float x11 = 1.0f - x12, y11 = 1.0f - y12;
+    float s2x = c2x - half, s2y = c2y - half;
+    float f2x = floorf(s2x), f2y = floorf(s2y);
+    int ip2x = (int)f2x, ip2y = (int)f2y;
+    float x22 = s2x - f2x, y22 = s2y - f2y;
     float x21 = 1.0f - x22, y21 = 1.0f - y22;
-    float m11 = x11 * y11, m12 = x12 * y11, m13 = x11 * y12, m14 = x12 * y12;
     float m21 = x21 * y21, m22 = x22 * y21, m23 = x21 * y22, m24 = x22 * y22;
-    if (ip1y >= 0 && ip1y + 4 < h && ip2y >= 0 && ip2y + 4 < h && ip1x >= 0 && ip1x + 4 < w && ip2x >= 0 && ip2x + 4 < w) {
-        const uint8_t *p1 = im1 + (ip1y + row) * pitch + ip1x, *p2 = im2 + (ip2y + row) * pitch + ip2x;
-        float a0[5], a1[5], b0[5], b1[5];
-#pragma unroll
-        for (int j = 0; j < 5; j++) { a0[j] = 0.f; a1[j] = 0.f; b0[j] = 0.f; b1[j] = 0.f; }
-        load5f(p1, a0); load5f(p1 + pitch, a1); load5f(p2, b0); load5f(p2 + pitch, b1);
+    if (ok1 && ip2y >= 0 && ip2y + 4 < h && ip2x >= 0 && ip2x + 4 < w) {
+        const uint8_t *p2 = im2 + (ip2y + row) * pitch + ip2x;
+        float b0[5], b1[5];
+        load5f(p2, b0); load5f(p2 + pitch, b1);
         float d[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            float i1 = 0.f, i2 = 0.f;
-            i1 += m11 * a0[j]; i1 += m12 * a0[j + 1]; i1 += m13 * a1[j]; i1 += m14 * a1[j + 1];
+            float i2 = 0.f;
             i2 += m21 * b0[j]; i2 += m22 * b0[j + 1]; i2 += m23 * b1[j]; i2 += m24 * b1[j + 1];
-            d[j] = fabsf(i1 - i2);
+            d[j] = fabsf(i1[j] - i2);
         }
         d0 = d[0]; d1 = d[1]; d2 = d[2]; d3 = d[3];
     }
+}
+// window sizes other than 4: the generic whole-patch routine on lane 0 of the quad (the whole patch sum in the reference's order);
+// kept out of line — no shipped configuration takes it, and the solver loop has to stay small
+static __device__ __noinline__ float intensity_diff_generic(const uint8_t *im1, const uint8_t *im2, int w, int h, int pitch, float c1x, float c1y,
+                                                            float c2x, float c2y, int patch)
+{
+    return intensity_diff<0>(im1, im2, w, h, pitch, c1x, c1y, c2x, c2y, patch);
 }
 
 // One thread-block CLUSTER (8 CTAs x 256 threads) = one frame.  Four lanes share a keypoint: lane r of the quad owns
@@ -277,6 +361,10 @@ __global__ void __launch_bounds__(ALIGN_THREADS, 1) sparse_align_kernel(AlignArg
             pimg = P.ptr; cimg = C.ptr;
         }
         const int pitch = w;  // halfSample levels are stored with pitch == width
+        // the reference's footprint tests promote to double — ((double)x - 2.0) < 0, ((double)x + 3.0) >= w, ... — and a float plus
+        // or minus a small integer is exact in double, so they are exactly x < 2.f, x >= (float)(w - 3), ...: float compares, no
+        // conversions and no trip through the double-precision pipe (12 per keypoint row and gradient evaluation)
+        const float wm3 = (float)(w - 3), hm3 = (float)(h - 3), wm2 = (float)(w - 2), hm2 = (float)(h - 2);
         trc.stamp(1, level);
 
         // setLevel (pose_estimator.cpp:541-562)
@@ -315,10 +403,12 @@ __global__ void __launch_bounds__(ALIGN_THREADS, 1) sparse_align_kernel(AlignArg
             }
             unsigned mask = 0;
             const size_t slot = (size_t)4 * i + row;
-#pragma unroll
+            // (a loop, not four unrolled copies of five inlined patch sums: this code runs once per level, i.e. always from a cold
+            // instruction cache, and what it costs is the fetch of its own instructions)
+#pragma unroll 1
             for (int c = 0; c < 4; c++) {
                 float g0 = 0.f, g1 = 0.f;
-                if (!(((double)kx - 2.0) < 0 || ((double)ky - 2.0) < 0 || ((double)kx + 3.0) >= w || ((double)ky + 3.0) >= h)) {
+                if (!(kx < 2.f || ky < 2.f || kx >= wm3 || ky >= hm3)) {   // ((double)kx - 2.0) < 0 || ... || ((double)kx + 3.0) >= w: see wm3
                     float i1 = patch_sum(pimg, pitch, kx + 1.f, ky), i2 = patch_sum(pimg, pitch, kx - 1.f, ky);
                     float i3 = patch_sum(pimg, pitch, kx, ky + 1.f), i4 = patch_sum(pimg, pitch, kx, ky - 1.f);
                     g0 = i1 - i2; g1 = i3 - i4;
@@ -328,7 +418,7 @@ __global__ void __launch_bounds__(ALIGN_THREADS, 1) sparse_align_kernel(AlignArg
                 scr[(size_t)(4 + c) * SN + slot] = g1;
                 kx += 1.f;
                 float sp = 0.f;
-                if (!(((double)rx - 1.0) < 0 || ((double)ry - 1.0) < 0 || ((double)rx + 2.0) > w || ((double)ry + 2.0) > h)) {
+                if (!(rx < 1.f || ry < 1.f || rx > wm2 || ry > hm2)) {
                     sp = patch_sum(pimg, pitch, rx, ry);
                     mask |= 1u << (4 + c);
                 }
@@ -351,6 +441,11 @@ __global__ void __launch_bounds__(ALIGN_THREADS, 1) sparse_align_kernel(AlignArg
             if (level != 0) { bx_first = bx_first / fdiv; by_first = by_first / fdiv; }   // setLevel :558-561
             P_first[0] = a.kps3d[3 * i_first]; P_first[1] = a.kps3d[3 * i_first + 1]; P_first[2] = a.kps3d[3 * i_first + 2];
         }
+        // ... and so do the bilinear samples of this lane's row of the reference patch (4x4 window)
+        const bool win4 = cam.win_pose == 4;
+        float i1_first[4] = {0.f, 0.f, 0.f, 0.f};
+        bool ok1_first = false;
+        if (act_first && win4) ref_row4(pimg, w, h, pitch, bx_first, by_first, row, i1_first, ok1_first);
 
         // ---- Gauss-Newton driver (estimate_pose_at_level :166-222).
         //  mode 0: cost at x0 (initial)   mode 1: gradient at x0   mode 2: cost at xt   mode 3: level done
@@ -373,20 +468,25 @@ __global__ void __launch_bounds__(ALIGN_THREADS, 1) sparse_align_kernel(AlignArg
                 const double *Rd = hdr->Rd[(mode == 2) ? (mine ? xtslot + g_mine : xtslot) : x0slot];
                 const float tx = xg[0], ty = xg[1], tz = xg[2];
                 double part = 0.0;
+                // (one loop body for the register-held first pass and the later ones)
                 for (int pass = 0; mine && pass < npass; pass++) {
                     const int i = ((pass * ALIGN_WARPS + warp) * CL + (int)crank) * 8 + quad;
                     const bool active = pass == 0 ? act_first : ((i < n) && !(a.flags && (a.flags[i] & SVO_F_IGN_TEMP)));
                     float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
                     if (active) {
                         float bx = bx_first, by = by_first, Px = P_first[0], Py = P_first[1], Pz = P_first[2];
+                        float i1[4] = {i1_first[0], i1_first[1], i1_first[2], i1_first[3]};
+                        bool ok1 = ok1_first;
                         if (pass != 0) {
                             bx = a.kps2d[2 * i]; by = a.kps2d[2 * i + 1];
                             if (level != 0) { bx = bx / fdiv; by = by / fdiv; }
                             Px = a.kps3d[3 * i]; Py = a.kps3d[3 * i + 1]; Pz = a.kps3d[3 * i + 2];
+                            if (win4) ref_row4(pimg, w, h, pitch, bx, by, row, i1, ok1);
                         }
                         float u, v;
                         dev_project_nd(nodist, Rd, Px, Py, Pz, tx, ty, tz, lfx, lfy, lcx, lcy, cam, u, v);
-                        intensity_diff_row(pimg, cimg, w, h, pitch, bx, by, u, v, cam.win_pose, row, d0, d1, d2, d3);
+                        if (win4) cur_row4(cimg, w, h, pitch, u, v, row, i1, ok1, d0, d1, d2, d3);
+                        else if (row == 0) d0 = intensity_diff_generic(pimg, cimg, w, h, pitch, bx, by, u, v, cam.win_pose);
                     }
                     // the reference adds the 16 |dI| terms of a patch sequentially in raster order: chain the four rows
                     float run = 0.f;
@@ -481,27 +581,42 @@ __global__ void __launch_bounds__(ALIGN_THREADS, 1) sparse_align_kernel(AlignArg
                     float X, Y, Z;
                     dev_m33v(Rif, Px - tx, Py - ty, Pz - tz, X, Y, Z);
                     float J[12];
-                    J[0] = -lfx / Z; J[1] = 0.f; J[2] = lfx * X / (Z * Z); J[3] = lfx * X * Y / (Z * Z);
-                    J[4] = -lfx * (1 + (X * X) / (Z * Z)); J[5] = lfx * Y / Z;
-                    J[6] = 0.f; J[7] = -lfy / Z; J[8] = lfy * Y / (Z * Z); J[9] = lfy * (1 + (Y * Y) / (Z * Z));
-                    J[10] = -lfy * X * Y / (Z * Z); J[11] = -lfy * X / Z;
+                    dev_jacobian(lfx, lfy, X, Y, Z, J);
                     float qx = u - 2.f, qy = v - 2.f;       // residual loop, current-image coordinates
                     for (int r = 0; r < row; r++) { qx += 1.f; qx += 1.f; qx += 1.f; qx += 1.f; qy += 1.f; qx -= 4.f; }
+                    // residuals of the four pixels of this row: all four inside the image (the usual case) -> one shared fetch
+                    float diffv[4] = {0.f, 0.f, 0.f, 0.f};
+                    {
+                        float qxc[4] = {qx, 0.f, 0.f, 0.f};
+#pragma unroll
+                        for (int c = 1; c < 4; c++) qxc[c] = qxc[c - 1] + 1.f;
+                        bool all_in = ((mask >> 4) & 15u) == 15u && !(qy < 1.f || qy > hm2);
+#pragma unroll
+                        for (int c = 0; c < 4; c++) all_in = all_in && !(qxc[c] < 1.f || qxc[c] > wm2);
+                        float ps[4];
+                        if (all_in && patch_sum_row4(cimg, pitch, qx, qy, ps)) {
+#pragma unroll
+                            for (int c = 0; c < 4; c++) diffv[c] = ps[c] - spv[c];
+                        } else {   // a row that leaves the image: pixel by pixel (rare: a loop, not four more inlined patch sums)
+#pragma unroll 1
+                            for (int c = 0; c < 4; c++) {
+                                const float qc = c == 0 ? qxc[0] : c == 1 ? qxc[1] : c == 2 ? qxc[2] : qxc[3];
+                                const float sv = c == 0 ? spv[0] : c == 1 ? spv[1] : c == 2 ? spv[2] : spv[3];
+                                float dv = 0.f;
+                                if ((mask & (1u << (4 + c))) && !(qc < 1.f || qy < 1.f || qc > wm2 || qy > hm2)) dv = patch_sum(cimg, pitch, qc, qy) - sv;
+                                if (c == 0) diffv[0] = dv; else if (c == 1) diffv[1] = dv; else if (c == 2) diffv[2] = dv; else diffv[3] = dv;
+                            }
+                        }
+                    }
 #pragma unroll
                     for (int c = 0; c < 4; c++) {
                         float gj[6];
 #pragma unroll
                         for (int k = 0; k < 6; k++) {
-                            float t = 0.f;
-                            t += g0v[c] * J[k];
-                            t += g1v[c] * J[6 + k];
+                            const float t = __fmaf_rn(g1v[c], J[6 + k], g0v[c] * J[k]);   // enters H and b only (regrouped sums)
                             gj[k] = (mask & (1u << c)) ? t : 0.f;
                         }
-                        float diff = 0.f;
-                        if ((mask & (1u << (4 + c))) &&
-                            !(((double)qx - 1.0) < 0 || ((double)qy - 1.0) < 0 || ((double)qx + 2.0) > w || ((double)qy + 2.0) > h)) {
-                            diff = patch_sum(cimg, pitch, qx, qy) - spv[c];
-                        }
+                        const float diff = diffv[c];
                         int hk = 0;
 #pragma unroll
                         for (int p = 0; p < 6; p++)
@@ -509,7 +624,6 @@ __global__ void __launch_bounds__(ALIGN_THREADS, 1) sparse_align_kernel(AlignArg
                             for (int q = p; q < 6; q++) { acc[hk] = __fmaf_rn(gj[p], gj[q], acc[hk]); hk++; }   // sum order differs from the reference anyway
 #pragma unroll
                         for (int p = 0; p < 6; p++) acc[21 + p] = __fmaf_rn(-gj[p], diff, acc[21 + p]);
-                        qx += 1.f;
                     }
                 }
                 // warp reduce (float) -> CTA partial (double, 27 threads) -> every CTA's table through DSMEM
@@ -551,6 +665,7 @@ __global__ void __launch_bounds__(ALIGN_THREADS, 1) sparse_align_kernel(AlignArg
                     } else {
                         dev_pinv_step(hdr->red_out, hdr->red_out + 21, delta);   // rank-deficient H: the reference's pseudo-inverse step
                     }
+                    trc.stamp(9);
                     dev_expmap(delta, pg);
                     // rot_mat = float(Rodrigues(r)) == transpose of float(Rodrigues(-r)) bit for bit
 #pragma unroll
@@ -564,10 +679,12 @@ __global__ void __launch_bounds__(ALIGN_THREADS, 1) sparse_align_kernel(AlignArg
 #pragma unroll
                         for (int k = 0; k < 6; k++) hdr->grad[k] = g[k];
                     }
+                    trc.stamp(10);
                     const int j = warp + ALIGN_WARPS * lane;
                     float kj = 1.f;
                     for (int q = 0; q < j; q++) kj = kj / 2;   // the driver's own sequence of halvings
                     dev_rodrigues_d(-(x0[3] + (kj * g[3])), -(x0[4] + (kj * g[4])), -(x0[5] + (kj * g[5])), hdr->Rd[tb * ALIGN_DEPTH + j]);
+                    trc.stamp(11);
                 }
                 __syncthreads();
 #pragma unroll

@@ -38,7 +38,8 @@ static inline DevCam make_devcam(const svo_camera_settings &s)
 
 #ifdef __CUDACC__
 // cv::Rodrigues (vector -> matrix) in double — same expression order as OpenCV (pose_manager.cpp:15-16).
-__device__ __forceinline__ void dev_rodrigues_d(float r0, float r1, float r2, double R[9])
+// (not inlined: it is used at three places of each solver kernel; measured neutral in time, 4 KB less code per kernel)
+static __device__ __noinline__ void dev_rodrigues_d(float r0, float r1, float r2, double R[9])
 {
     double rx = r0, ry = r1, rz = r2;
     double theta = sqrt(rx * rx + ry * ry + rz * rz);
@@ -51,9 +52,14 @@ __device__ __forceinline__ void dev_rodrigues_d(float r0, float r1, float r2, do
     double c1 = 1. - c;
     double it = 1. / theta;
     rx *= it; ry *= it; rz *= it;
-    R[0] = c * 1 + c1 * (rx * rx) + s * 0;     R[1] = c * 0 + c1 * (rx * ry) + s * (-rz); R[2] = c * 0 + c1 * (rx * rz) + s * ry;
-    R[3] = c * 0 + c1 * (rx * ry) + s * rz;    R[4] = c * 1 + c1 * (ry * ry) + s * 0;     R[5] = c * 0 + c1 * (ry * rz) + s * (-rx);
-    R[6] = c * 0 + c1 * (rx * rz) + s * (-ry); R[7] = c * 0 + c1 * (ry * rz) + s * rx;    R[8] = c * 1 + c1 * (rz * rz) + s * 0;
+    // OpenCV writes R = c I + c1 r r^T + s [r]x out in full — R[1] = c * 0 + c1 * (rx * ry) + s * (-rz) and so on.  c * 1 is c, adding a
+    // product with 0 changes nothing and a + s * (-b) is a - s * b, all exactly, so the 24 operations below give the same bits as
+    // the 63 of the full expressions (up to the sign of a zero entry) — this runs on single lanes inside every gradient round
+    const double xx = c1 * (rx * rx), xy = c1 * (rx * ry), xz = c1 * (rx * rz), yy = c1 * (ry * ry), yz = c1 * (ry * rz), zz = c1 * (rz * rz);
+    const double sx = s * rx, sy = s * ry, sz = s * rz;
+    R[0] = c + xx;  R[1] = xy - sz; R[2] = xz + sy;
+    R[3] = xy + sz; R[4] = c + yy;  R[5] = yz - sx;
+    R[6] = xz - sy; R[7] = yz + sx; R[8] = c + zz;
 }
 __device__ __forceinline__ void dev_rodrigues_f(float r0, float r1, float r2, float R[9])
 {
@@ -100,11 +106,20 @@ __device__ __forceinline__ bool dev_cam_nodist(const DevCam &cam)
 {
     return cam.k1 == 0.f && cam.k2 == 0.f && cam.p1 == 0.f && cam.p2 == 0.f && cam.k3 == 0.f;
 }
+// (the full model out of line: no shipped camera takes it)
+static __device__ __noinline__ void dev_project_dist(const double *Rd, float px, float py, float pz, float tx, float ty, float tz,
+                                                     float fx, float fy, float cx, float cy, float k1, float k2, float p1, float p2,
+                                                     float k3, float *uv)
+{
+    dev_project(Rd, px, py, pz, tx, ty, tz, fx, fy, cx, cy, k1, k2, p1, p2, k3, uv[0], uv[1]);
+}
 __device__ __forceinline__ void dev_project_nd(bool nodist, const double *Rd, float px, float py, float pz, float tx, float ty, float tz,
                                                float fx, float fy, float cx, float cy, const DevCam &cam, float &u, float &v)
 {
     if (!nodist) {
-        dev_project(Rd, px, py, pz, tx, ty, tz, fx, fy, cx, cy, cam.k1, cam.k2, cam.p1, cam.p2, cam.k3, u, v);
+        float uv[2];
+        dev_project_dist(Rd, px, py, pz, tx, ty, tz, fx, fy, cx, cy, cam.k1, cam.k2, cam.p1, cam.p2, cam.k3, uv);
+        u = uv[0]; v = uv[1];
         return;
     }
     double X = (double)(px - tx), Y = (double)(py - ty), Z = (double)(pz - tz);
@@ -126,21 +141,15 @@ __device__ __forceinline__ void dev_expmap(const float tw[6], float out[6])
     const float C1 = 0x1.d6bbp-2f;   // 1.f - cosf(1.f)
     const float C2 = 0x1.44aaep-3f;  // 1.f - sinf(1.f)
     float w0 = tw[3], w1 = tw[4], w2 = tw[5];
-    float K[9] = {0.f, -w2, w1, w2, 0.f, -w0, -w1, w0, 0.f};
+    // M = I + C1 K + C2 K K with K = [w]x, formed by the reference as generic 3x3 float products (s = 0; s += K(i,k) * K(k,j)).  The
+    // zero entries of K contribute exact zeros, so each entry of K K is one product or a sum of two, written out here in the
+    // reference's order of additions: the same bits with a third of the operations.
+    const float k00 = (-(w2 * w2)) - (w1 * w1), k11 = (-(w2 * w2)) - (w0 * w0), k22 = (-(w1 * w1)) - (w0 * w0);
+    const float k01 = w1 * w0, k02 = w2 * w0, k12 = w2 * w1;
     float M[9];
-#pragma unroll
-    for (int i = 0; i < 3; i++)
-#pragma unroll
-        for (int j = 0; j < 3; j++) {
-            float s = 0.f;
-            s += K[i * 3 + 0] * K[0 * 3 + j];
-            s += K[i * 3 + 1] * K[1 * 3 + j];
-            s += K[i * 3 + 2] * K[2 * 3 + j];
-            float e = (i == j) ? 1.f : 0.f;
-            float a = K[i * 3 + j] * C1;
-            float b = s * C2;
-            M[i * 3 + j] = (e + a) + b;
-        }
+    M[0] = 1.f + k00 * C2;            M[1] = (-w2) * C1 + k01 * C2;      M[2] = w1 * C1 + k02 * C2;
+    M[3] = w2 * C1 + k01 * C2;        M[4] = 1.f + k11 * C2;             M[5] = (-w0) * C1 + k12 * C2;
+    M[6] = (-w1) * C1 + k02 * C2;     M[7] = w0 * C1 + k12 * C2;         M[8] = 1.f + k22 * C2;
     dev_m33v(M, tw[0], tw[1], tw[2], out[0], out[1], out[2]);
     out[3] = w0; out[4] = w1; out[5] = w2;
 }
@@ -396,16 +405,28 @@ __device__ __forceinline__ void dsmem_push_f64(void *local_slot, unsigned long l
                  : "memory");
 }
 
+// 2x6 Jacobian of the projection wrt the twist (pose_estimator.cpp:366-380, pose_refinement.cpp:354-366), the reference's own
+// expressions with their fourteen divisions.  Taking 1/Z once and multiplying through saves a third of the instructions of a
+// gradient round (measured: -0.25 us per round), but the entries then differ by an ulp, and with ONE usable keypoint the reference's
+// float SVD finds H = J^T J exactly singular and takes no step, which only the reference's own bits reproduce
+// (tests/test_gpu_sequences.py::test_rank_deficient_hessian[one]) — so the divisions stay.
+__device__ __forceinline__ void dev_jacobian(float fx, float fy, float X, float Y, float Z, float (&J)[12])
+{
+    J[0] = -fx / Z; J[1] = 0.f; J[2] = fx * X / (Z * Z); J[3] = fx * X * Y / (Z * Z);
+    J[4] = -fx * (1 + (X * X) / (Z * Z)); J[5] = fx * Y / Z;
+    J[6] = 0.f; J[7] = -fy / Z; J[8] = fy * Y / (Z * Z); J[9] = fy * (1 + (Y * Y) / (Z * Z));
+    J[10] = -fy * X * Y / (Z * Z); J[11] = -fy * X / Z;
+}
+
 // 1 / d for the pivots of the 6x6 solve: hardware reciprocal approximation (MUFU.RCP64H) refined by two Newton steps in fused
-// arithmetic (relative error far below one ulp before the final rounding) — a third of the latency of the IEEE division, which
-// sits six times on the critical path of every gradient round of both solvers
+// arithmetic — a third of the latency of the IEEE division, which sits six times on the critical path of every gradient round
+// of both solvers
 __device__ __forceinline__ double dev_rcp_fast(double d)
 {
     double x;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
     x = fma(x, fma(-d, x, 1.0), x);
-    x = fma(x, fma(-d, x, 1.0), x);
-    x = fma(x, fma(-d, x, 1.0), x);
+    x = fma(x, fma(-d, x, 1.0), x);   // >= 40 good bits even from a 10-bit seed: far below what the float step delta resolves
     return x;
 }
 

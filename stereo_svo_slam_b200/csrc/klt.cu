@@ -611,10 +611,14 @@ void launch_klt_templates(const KltTemplateArgs &a, cudaStream_t st)
     klt_template_kernel<<<(a.n + KLTW_WARPS - 1) / KLTW_WARPS, 32 * KLTW_WARPS, 0, st>>>(a);
 }
 
-__global__ void __launch_bounds__(32 * KLTW_WARPS, 4) klt31w_kernel(KltArgs a)
+// WARPS keypoints per CTA.  The warps of a CTA never talk to each other; what the CTA size decides is when a finished warp's registers
+// and shared memory go back to the SM: a CTA lives as long as its slowest warp (27 LK iterations per keypoint on average, up to 90),
+// so with many frames in flight one-warp CTAs return their slot as soon as their keypoint is done (WARPS = 1, 16 CTAs per SM).
+template <int WARPS>
+__global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) klt31w_kernel(KltArgs a)
 {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int i = blockIdx.x * KLTW_WARPS + wid;
+    const int i = blockIdx.x * WARPS + wid;
     const int n = min(*a.n_ptr, a.max_kps);
     if (i >= n) return;   // whole warp exits together
     constexpr int win = 31;
@@ -652,7 +656,7 @@ __global__ void __launch_bounds__(32 * KLTW_WARPS, 4) klt31w_kernel(KltArgs a)
     // window moves by a fraction of a pixel per iteration), re-staged if the window ever leaves it.  A lane reads ITS row
     // of the window, so a 4-byte global load of the warp touches 32 cache lines (32 L1 wavefronts); the same load from
     // shared memory with an odd word pitch is one conflict-free wavefront — 9 loads per iteration, ~27 iterations per keypoint.
-    __shared__ uint32_t s_win[KLTW_WARPS][KLTW_REG_ROWS * KLTW_REG_PITCH];
+    __shared__ uint32_t s_win[WARPS][KLTW_REG_ROWS * KLTW_REG_PITCH];
     uint32_t *swin = s_win[wid];
     int reg_x0 = 0, reg_y0 = 0;
     bool staged = false;
@@ -847,6 +851,7 @@ __global__ void __launch_bounds__(32 * KLTW_WARPS, 4) klt31w_kernel(KltArgs a)
 }
 
 static int g_klt_variant = -1;  // SVO_KLT_VARIANT=block selects the CTA-per-keypoint kernel (A/B measurements)
+static int g_klt_warps = -1;    // SVO_KLT_WARPS=1|4: keypoints per CTA of the warp-per-keypoint kernel
 
 void launch_klt(const KltArgs &a, cudaStream_t st)
 {
@@ -855,7 +860,12 @@ void launch_klt(const KltArgs &a, cudaStream_t st)
         const char *e = getenv("SVO_KLT_VARIANT");
         g_klt_variant = (e && e[0] == 'b') ? 1 : 0;
     }
-    if (a.cam.win_flow == 31 && g_klt_variant == 0) klt31w_kernel<<<(a.max_kps + KLTW_WARPS - 1) / KLTW_WARPS, 32 * KLTW_WARPS, 0, st>>>(a);
+    if (g_klt_warps < 0) {
+        const char *e = getenv("SVO_KLT_WARPS");
+        g_klt_warps = (e && atoi(e) == 4) ? 4 : 1;
+    }
+    if (a.cam.win_flow == 31 && g_klt_variant == 0 && g_klt_warps == 4) klt31w_kernel<4><<<(a.max_kps + 3) / 4, 128, 0, st>>>(a);
+    else if (a.cam.win_flow == 31 && g_klt_variant == 0) klt31w_kernel<1><<<a.max_kps, 32, 0, st>>>(a);
     else if (a.cam.win_flow == 31) klt31_kernel<<<a.max_kps, KLT_THREADS, 0, st>>>(a);
     else klt_pyr_lk_kernel<0><<<a.max_kps, KLT_THREADS, 0, st>>>(a);
 }

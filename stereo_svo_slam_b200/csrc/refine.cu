@@ -69,6 +69,21 @@ __global__ void __launch_bounds__(REF_THREADS, 1) reproj_refine_kernel(RefineArg
             c_kp[q][0] = a.kps2d[2 * i]; c_kp[q][1] = a.kps2d[2 * i + 1];
         }
     }
+    // keypoint q of this thread (global index i): from the registers above, or from memory beyond them; false = ignored keypoint
+    auto fetch_kp = [&](int q, int i, float &Px, float &Py, float &Pz, float &k0, float &k1) -> bool {
+        if (q < REF_CACHED) {
+            bool act = c_act[0];
+            Px = c_P[0][0]; Py = c_P[0][1]; Pz = c_P[0][2]; k0 = c_kp[0][0]; k1 = c_kp[0][1];
+#pragma unroll
+            for (int r = 1; r < REF_CACHED; r++)
+                if (q == r) { act = c_act[r]; Px = c_P[r][0]; Py = c_P[r][1]; Pz = c_P[r][2]; k0 = c_kp[r][0]; k1 = c_kp[r][1]; }
+            return act;
+        }
+        if (a.flags[i] & (SVO_F_IGN_REFINE | SVO_F_IGN_COMPLETE | SVO_F_IGN_TEMP)) return false;
+        Px = a.kps3d[3 * i]; Py = a.kps3d[3 * i + 1]; Pz = a.kps3d[3 * i + 2];
+        k0 = a.kps2d[2 * i]; k1 = a.kps2d[2 * i + 1];
+        return true;
+    };
     __syncthreads();
     trc.stamp(1);
     int mode = 0, it = 0, n_evals = 0, n_grads = 0, cbuf = 0, xb = 0, jstep = 0;
@@ -92,19 +107,13 @@ __global__ void __launch_bounds__(REF_THREADS, 1) reproj_refine_kernel(RefineArg
             const float tx = xg[0], ty = xg[1], tz = xg[2];
             if (mine) {
                 double part = 0.0;
-#pragma unroll
-                for (int q = 0; q < REF_CACHED; q++) {
-                    if (!c_act[q]) continue;
+                // (one loop body for cached and uncached keypoints)
+                for (int q = 0, i = tid; i < n; q++, i += nthr) {
+                    float Px, Py, Pz, k0, k1;
+                    if (!fetch_kp(q, i, Px, Py, Pz, k0, k1)) continue;
                     float u, v;
-                    dev_project_nd(nodist, Rd, c_P[q][0], c_P[q][1], c_P[q][2], tx, ty, tz, cam.fx, cam.fy, cam.cx, cam.cy, cam, u, v);
-                    float d0 = fabsf(u - c_kp[q][0]), d1 = fabsf(v - c_kp[q][1]);
-                    part += (double)(d0 + d1);
-                }
-                for (int i = tid + REF_CACHED * nthr; i < n; i += nthr) {
-                    if (a.flags[i] & (SVO_F_IGN_REFINE | SVO_F_IGN_COMPLETE | SVO_F_IGN_TEMP)) continue;
-                    float u, v;
-                    dev_project_nd(nodist, Rd, a.kps3d[3 * i], a.kps3d[3 * i + 1], a.kps3d[3 * i + 2], tx, ty, tz, cam.fx, cam.fy, cam.cx, cam.cy, cam, u, v);
-                    float d0 = fabsf(u - a.kps2d[2 * i]), d1 = fabsf(v - a.kps2d[2 * i + 1]);
+                    dev_project_nd(nodist, Rd, Px, Py, Pz, tx, ty, tz, cam.fx, cam.fy, cam.cx, cam.cy, cam, u, v);
+                    float d0 = fabsf(u - k0), d1 = fabsf(v - k1);
                     part += (double)(d0 + d1);
                 }
 #pragma unroll
@@ -191,12 +200,8 @@ __global__ void __launch_bounds__(REF_THREADS, 1) reproj_refine_kernel(RefineArg
                     if ((fabs((double)d0) > 3.0) || (fabs((double)d1) > 3.0)) return;
                     float X, Y, Z;
                     dev_m33v(Rif, Px - tx, Py - ty, Pz - tz, X, Y, Z);
-                    const float fx = cam.fx, fy = cam.fy;
                     float J[12];
-                    J[0] = -fx / Z; J[1] = 0.f; J[2] = fx * X / (Z * Z); J[3] = fx * X * Y / (Z * Z);
-                    J[4] = -fx * (1 + (X * X) / (Z * Z)); J[5] = fx * Y / Z;
-                    J[6] = 0.f; J[7] = -fy / Z; J[8] = fy * Y / (Z * Z); J[9] = fy * (1 + (Y * Y) / (Z * Z));
-                    J[10] = -fy * X * Y / (Z * Z); J[11] = -fy * X / Z;
+                    dev_jacobian(cam.fx, cam.fy, X, Y, Z, J);
                     int hk = 0;
 #pragma unroll
                     for (int p = 0; p < 6; p++)
@@ -216,12 +221,9 @@ __global__ void __launch_bounds__(REF_THREADS, 1) reproj_refine_kernel(RefineArg
                         acc[21 + p] += t;
                     }
                 };
-#pragma unroll
-                for (int q = 0; q < REF_CACHED; q++)
-                    if (c_act[q]) accumulate(c_P[q][0], c_P[q][1], c_P[q][2], c_kp[q][0], c_kp[q][1]);
-                for (int i = tid + REF_CACHED * nthr; i < n; i += nthr) {
-                    if (a.flags[i] & (SVO_F_IGN_REFINE | SVO_F_IGN_COMPLETE | SVO_F_IGN_TEMP)) continue;
-                    accumulate(a.kps3d[3 * i], a.kps3d[3 * i + 1], a.kps3d[3 * i + 2], a.kps2d[2 * i], a.kps2d[2 * i + 1]);
+                for (int q = 0, i = tid; i < n; q++, i += nthr) {
+                    float Px, Py, Pz, k0, k1;
+                    if (fetch_kp(q, i, Px, Py, Pz, k0, k1)) accumulate(Px, Py, Pz, k0, k1);
                 }
                 trc.stamp(7);
                 const float t = warp_sum_scatter<RNGRAD>(acc, lane);   // lane k: warp sum of term k
@@ -248,6 +250,7 @@ __global__ void __launch_bounds__(REF_THREADS, 1) reproj_refine_kernel(RefineArg
                 } else {
                     dev_pinv_step(hdr.red_out, hdr.red_out + 21, tw);   // rank-deficient H: the reference's pseudo-inverse step
                 }
+                trc.stamp(9);
                 dev_expmap(tw, g);  // used as is — not rotated to world (pose_refinement.cpp:401-411)
                 if (tid == 0) {
 #pragma unroll
@@ -257,6 +260,7 @@ __global__ void __launch_bounds__(REF_THREADS, 1) reproj_refine_kernel(RefineArg
                 float kj = 1.f;
                 for (int q = 0; q < j; q++) kj = kj / 2;   // the driver's own sequence of halvings
                 dev_rodrigues_d(-(x0[3] + (kj * g[3])), -(x0[4] + (kj * g[4])), -(x0[5] + (kj * g[5])), hdr.Rd[tb * REF_DEPTH + j]);
+                trc.stamp(11);
             }
             __syncthreads();
 #pragma unroll
@@ -301,7 +305,8 @@ static void launch_refine_cluster(const RefineArgs &a, cudaStream_t st)
 // round; same bits as the single CTA) — for a sequence that has the GPU to itself, where the SMs it occupies are idle anyway.
 void launch_refine(const RefineArgs &a, int bucket, bool wide, cudaStream_t st)
 {
-    if (bucket > 1024) {   // C4: 114 instead of 128 us with 512 threads; no gain for a few hundred keypoints
+    static const int big_from = getenv("SVO_REFINE_THREADS") && atoi(getenv("SVO_REFINE_THREADS")) == 512 ? 256 : 1024;   // developer A/B switch
+    if (bucket > big_from) {   // C4: 114 instead of 128 us with 512 threads; no gain for a few hundred keypoints
         if (wide) launch_refine_cluster<512>(a, st);
         else reproj_refine_kernel<512, 1><<<1, 512, 0, st>>>(a, 1 << 30);
     } else {

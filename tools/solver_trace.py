@@ -26,7 +26,7 @@ except Exception:  # noqa: BLE001
     mhz = 1965.0
 lib = capi.lib()
 ctx = C.c_void_p(lib.svo_slam_ctx(g._h))
-names = {0: "start", 1: "level", 2: "images staged", 3: "reference terms", 4: "cost round", 5: "gradient round", 6: "end", 7: "  grad: keypoints done", 8: "  grad: sums exchanged"}
+names = {0: "start", 1: "level", 2: "images staged", 3: "reference terms", 4: "cost round", 5: "gradient round", 6: "end", 7: "  grad: keypoints done", 8: "  grad: sums exchanged", 9: "  grad: 6x6 solved", 10: "  grad: expmap + rotation", 11: "  grad: Rodrigues of the trial pose"}
 for which, kname in ((0, "sparse_align_kernel"), (1, "reproj_refine_kernel")):
     buf = (C.c_ulonglong * 1024)()
     lib.svo_debug_solver_trace(ctx, which, buf, 1024)
