@@ -235,19 +235,55 @@ def run_reference(cfg, seeds, nframes, F, W, K, procs):
     return sum(r[2] for r in res) / seconds, seconds, _ref_kind()
 
 
-def run_reference_one_core(frames, cfg, n, warm):
-    """the reference on ONE host core over the first sequence: frames/s over n frames after `warm` warm-up frames"""
+def run_reference_one_core(frames, cfg, passes, warm):
+    """the reference on ONE host core over the first stream: `passes` passes over its rendered sequence (every pass a fresh
+    StereoSlam, keyframe creation included — the b200 arm's stream definition) after `warm` warm-up frames; frames/s"""
     from oracle import oracle as orc
     c = synth.CONFIGS[cfg]
     cs = orc.CameraSettings(**synth.settings_dict(cfg))
-    sl = orc.RefSlam(cs, c["width"], c["height"]) if orc.have_ref() else orc.OracleSlam(cs, c["width"], c["height"], tracing=False)
+
+    def fresh():
+        return orc.RefSlam(cs, c["width"], c["height"]) if orc.have_ref() else orc.OracleSlam(cs, c["width"], c["height"], tracing=False)
+    sl = fresh()
     for k in range(warm):
         sl.new_image(frames[0, k, 0], frames[0, k, 1], k / 20.0)
+    if orc.have_ref():
+        sl.close()
+    nf = frames.shape[1]
     t0 = time.perf_counter()
-    for k in range(warm, warm + n):
-        sl.new_image(frames[0, k, 0], frames[0, k, 1], k / 20.0)
+    for _ in range(passes):
+        sl = fresh()
+        for k in range(nf):
+            sl.new_image(frames[0, k, 0], frames[0, k, 1], k / 20.0)
+        if orc.have_ref():
+            sl.close()
     dt = time.perf_counter() - t0
-    return n / dt, dt, _ref_kind()
+    return passes * nf / dt, dt, _ref_kind()
+
+
+def prefer_host_memory_near_gpu(local_rank):
+    """Best effort: make this process allocate its (page-locked) frame buffers on the NUMA node its GPU hangs off
+    (set_mempolicy(MPOL_PREFERRED)).  With 8 ranks reading 0.78 MB per frame over PCIe, frames that sit on the other socket cross the
+    inter-socket link first.  Returns what was done, for the JSON line."""
+    import platform
+    info = {"numa_node": None, "policy": "default"}
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local_rank)
+        bus = "%04x:%02x:%02x.0" % (getattr(pr, "pci_domain_id", 0), pr.pci_bus_id, pr.pci_device_id)
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        info["numa_node"] = node
+        info["nodes_online"] = open("/sys/devices/system/node/online").read().strip()
+        if node >= 0:
+            nr = {"x86_64": 238, "aarch64": 237}.get(platform.machine())
+            if nr is not None:
+                libc = C.CDLL(None, use_errno=True)
+                mask = C.c_ulong(1 << node)
+                rc = libc.syscall(nr, 1, C.byref(mask), C.c_ulong(C.sizeof(mask) * 8))   # MPOL_PREFERRED = 1
+                info["policy"] = f"preferred node {node}" if rc == 0 else f"default (set_mempolicy errno {C.get_errno()})"
+    except Exception as e:  # noqa: BLE001
+        info["policy"] = "default (" + str(e)[:80] + ")"
+    return info
 
 
 def stream_seeds(rank, world, streams_per_gpu, total_streams=0):
@@ -343,6 +379,7 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    config["host_memory"] = prefer_host_memory_near_gpu(local_rank)
     H_, W_ = c["height"], c["width"]
     img = H_ * W_
     settings = capi.CameraSettings(**synth.settings_dict(CFG))
@@ -480,19 +517,24 @@ def main():
     if rank == 0:
         # ---------------- single sequence, the way an application runs it (one synchronous new_image per frame, page-locked
         # frames, CUDA-graph replay): wall time per call and device time per frame (events around ingest .. D2H)
-        sl = StereoSlam(settings, W_, H_, device=local_rank)
         host_np = host.numpy()
         n1 = W + 200
-        walls_g, gpu_g = [], []
-        for k in range(n1):
-            t0 = time.perf_counter()
-            sl.new_image(host_np[0, tri(k), 0], host_np[0, tri(k), 1], k / 20.0)
-            walls_g.append(time.perf_counter() - t0)
-            stt = sl.last_stats()
-            if not stt["keyframe_created"]:
-                gpu_g.append(stt["gpu_ms"])
-        sl.close()
-        wall_graph, gpu_graph = float(np.median(walls_g[W:])), float(np.median(gpu_g[W:]))
+
+        def lone(width):
+            sl_ = StereoSlam(settings, W_, H_, device=local_rank)
+            sl_.set_solver_width(width)
+            walls_, gpu_ = [], []
+            for k in range(n1):
+                t0 = time.perf_counter()
+                sl_.new_image(host_np[0, tri(k), 0], host_np[0, tri(k), 1], k / 20.0)
+                walls_.append(time.perf_counter() - t0)
+                stt = sl_.last_stats()
+                if not stt["keyframe_created"]:
+                    gpu_.append(stt["gpu_ms"])
+            sl_.close()
+            return float(np.median(walls_[W:])), float(np.median(gpu_[W:]))
+        wall_graph, gpu_graph = lone(-1)       # library default: a lone sequence gets the wide line searches (svo_set_solver_width)
+        wall_seq, gpu_seq = lone(0)            # sequential line searches (what the multi-sequence runs use)
         # ---------------- the same sequence with per-stage CUDA events (kernel-by-kernel launches): stage table, roofline
         sl = StereoSlam(settings, W_, H_, device=local_rank)
         ctxp = C.c_void_p(lib.svo_slam_ctx(sl._h))
@@ -593,12 +635,14 @@ def main():
                "keypoints_per_frame": r_dev["kps"],
                "configs4": c4s,
                "single_stream": {"frames_per_s": 1.0 / wall_graph, "ms_per_frame_wall": 1e3 * wall_graph, "ms_per_frame_gpu": gpu_graph,
+                                 "ms_per_frame_gpu_sequential_line_search": gpu_seq, "ms_per_frame_wall_sequential_line_search": 1e3 * wall_seq,
                                  "ms_per_frame_gpu_staged_events": float(st[7]), "ms_per_frame_wall_staged_events": 1e3 * med_wall,
                                  "pose_iter_latency_us": float(1e3 * st[1] / max(cm[2] + cm[3], 1.0)),
                                  "align_evaluations_per_frame": float(cm[2] + cm[3]),
                                  "mpatches_per_s": float(patches / (st[1] * 1e-3) / 1e6) if st[1] > 0 else None,
                                  "mwindows_per_s": float(windows / (st[2] * 1e-3) / 1e6) if st[2] > 0 else None,
-                                 "note": "one sequence, synchronous new_image calls with page-locked host frames (what the reference app does); "
+                                 "note": "one sequence, synchronous new_image calls with page-locked host frames (what the reference app does), wide line "
+                                         "searches (svo_set_solver_width default for a lone sequence; *_sequential_line_search: width 0, same bits); "
                                          "*_staged_events: same with a CUDA event between the stages (kernel-by-kernel launches, source of the stage table)"},
                "roofline": dict(issue, hbm={"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
                                             "frac": achieved / peak, "traffic": traffic_of(stage_kernel.get(dom, "?")),
@@ -635,10 +679,11 @@ def main():
                                 "klt_gbs_materialised_derivative_layout": float((3 * 6144 + 29) * cn4[0] / (st4[2] * 1e-3) / 1e9) if st4[2] > 0 else None,
                                 "klt_gbs_survey_fused_layout": float(6965 * cn4[0] / (st4[2] * 1e-3) / 1e9) if st4[2] > 0 else None}
         if not a.no_cpu_baseline and world == 1:
-            kb, wb = 30, 3
-            fps, dt, kind = run_reference_one_core(frames_np, CFG, kb, wb)
-            out["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": 1, "kind": kind,
-                                   "sample": f"1 sequence, {kb} frames after {wb} warm-up frames on one host core ("
+            pb, wb = int(os.environ.get("BENCH_CPU_PASSES", "6")), 3
+            fps, dt, kind = run_reference_one_core(frames_np, CFG, pb, wb)
+            out["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": 1, "kind": kind, "seconds": dt,
+                                   "sample": f"1 stream, {pb} passes over its {nframes}-frame sequence ({pb * nframes} frames, {dt:.1f} s; every pass a fresh "
+                                             f"tracker with its keyframes) after {wb} warm-up frames on one host core ("
                                              + ("oracle/_ref = the reference's unmodified sources built against oracle/cvshim" if kind == "reference"
                                                 else "oracle port; oracle/_ref not built") + "; the reference library is single-threaded)"}
         print(json.dumps(out, default=lambda o: float(o) if isinstance(o, (np.floating,)) else (int(o) if isinstance(o, np.integer) else str(o))))
