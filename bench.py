@@ -310,11 +310,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--frames-per-step", type=int, default=100, help="frames every sequence advances per step")
     ap.add_argument("--frames", type=int, default=64, help="rendered frames per sequence (played forward/backward: continuous motion)")
-    ap.add_argument("--streams", type=int, default=32, help="independent sequences per GPU (weak scaling)")
+    ap.add_argument("--streams", type=int, default=48, help="independent sequences per GPU (weak scaling)")
     ap.add_argument("--total-streams", type=int, default=0, help="BASELINE configs[4]: this many sequences in total, stream s on GPU s mod N (strong scaling)")
     ap.add_argument("--host-threads", type=int, default=0, help="native host threads driving the sequences of one GPU (0 = min(16, cores / ranks))")
-    ap.add_argument("--align-cluster", type=int, default=0, choices=[0, 1, 2, 4, 8, 16],
-                    help="SMs per alignment solve in the multi-sequence runs (measured: 8 and 4 give the same aggregate throughput, 1 is 20 %% slower)")
+    ap.add_argument("--align-cluster", type=int, default=-1, choices=[-1, 0, 1, 2, 4, 8, 16],
+                    help="SMs per alignment solve in the multi-sequence runs (svo_set_align_cluster; 0 = library default 8/16).  -1 (default): by the "
+                         "number of sequences on the GPU — 2 from 56 sequences, 4 from 24, else the library default.  Measured on one B200 "
+                         "(frames/s, device-resident; gpurun_out/s10_sweep.txt, s11_sweep.txt): 32 sequences 57.8k / 60.5k / 57.1k / 45.9k with 8 / 4 / 2 / 1 "
+                         "SMs, 48 sequences 57.8k / 61.6k / 62.9k, 64 sequences 61.1k (4) / 63.5k (2) / 61.7k (1): what a frame costs the GPU is the time its "
+                         "cluster holds its SMs, so smaller clusters win as soon as there are enough sequences to hide their longer solves")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs4", action="store_true")
@@ -344,6 +348,9 @@ def main():
                              f"{a.streams} independent sequences per GPU") + "; configs[0]/[1] blocked: .mkv missing",
               "sequences_per_gpu": S, "frames_per_step_per_sequence": F, "host_threads_per_gpu": a.host_threads,
               "rendered_frames_per_sequence": nframes,
+              "align_cluster": "SMs per alignment solve (svo_set_align_cluster): %s for the %d sequences per GPU of this run (0 = library default 8); "
+                               "a deployment knob, results within the pose tolerance for every setting" % (
+                                   a.align_cluster if a.align_cluster >= 0 else (2 if S >= 56 else (4 if S >= 24 else 0)), S),
               "playback": "a stream is a succession of finite sequences (BASELINE configs[4] streams are 200 frames long): the rendered frames "
                           "played forward, then the stream restarts with a fresh tracker on the same device resources (svo_slam_reset) — every "
                           "pass creates keyframe #1 at its frame 0 and keyframe #2 around frame 46, like the reference would",
@@ -401,11 +408,16 @@ def main():
         h = torch.from_numpy(fr).pin_memory()                          # pinned host inputs (e2e)
         return fr, h, h.to("cuda", non_blocking=False)                 # HBM-resident inputs (value)
 
+    def cluster_for(n_seq):
+        if a.align_cluster >= 0:
+            return a.align_cluster
+        return 2 if n_seq >= 56 else (4 if n_seq >= 24 else 0)
+
     def run(mode, host, dev, n_seq, clocks=None):
         """W warm-up steps, then K timed steps of F frames per sequence; returns whole-rank counters and the time (max over ranks)"""
         slams = [StereoSlam(settings, W_, H_, device=local_rank) for _ in range(n_seq)]
         for sl in slams:   # many sequences share the GPU: SM time per frame matters, not the latency of one solve
-            sl.set_align_cluster(a.align_cluster)
+            sl.set_align_cluster(cluster_for(n_seq))
         base = dev.data_ptr() if mode == "device" else host.data_ptr()
         handles = (C.c_void_p * n_seq)(*[sl._h for sl in slams])
         bad = C.c_int(-1)
