@@ -7,8 +7,9 @@
 // lk_pad_level0_kernel / lk_pyrdown_kernel : cv::buildOpticalFlowPyramid(left, win, 2) image levels:
 //   level 0 copy, levels 1..2 = cv::pyrDown ([1 4 6 4 1]^2, (sum+128)>>8, even samples,
 //   size (w+1)/2 x (h+1)/2).  Every level is stored with a SVO_LK_PAD-pixel BORDER_REFLECT_101 frame, which
-//   is both pyrDown's border rule and the padding calcOpticalFlowPyrLK expects around its windows; the
-//   Scharr derivative images OpenCV stores next to them are NOT materialised (fused into the KLT kernel).
+//   is both pyrDown's border rule and the padding calcOpticalFlowPyrLK expects around its windows.
+// lk_scharr_kernel : the interleaved int16 Scharr derivative levels OpenCV stores next to them (zero border), built only for
+//   image sets that become keyframes — the only ones optical flow ever uses as its reference (optical_flow.cpp:41-44).
 #include <cstdlib>
 #include "kernels.cuh"
 
