@@ -89,9 +89,22 @@ def _frame(opcode, payload):
     return head + payload
 
 
+MAX_REQUEST_BYTES = 64 * 1024   # the viewer's requests are a few bytes; anything larger is dropped with the connection
+SEND_TIMEOUT_S = 2.0            # a viewer that stops reading must not stall the tracking loop for longer
+
+
 class _Client:
     def __init__(self, sock):
         self.sock, self.buf, self.resource, self.open = sock, b"", None, True
+
+    def send(self, data):
+        """sendall that never raises into the tracking loop: a viewer that went away (or stalls) just loses its connection"""
+        try:
+            self.sock.sendall(data)
+            return True
+        except OSError:      # BrokenPipeError, ConnectionResetError, socket.timeout
+            self.open = False
+            return False
 
     def handshake(self):
         if b"\r\n\r\n" not in self.buf:
@@ -102,11 +115,11 @@ class _Client:
         hdr = {k.strip().lower(): v.strip() for k, v in (ln.split(":", 1) for ln in lines[1:] if ":" in ln)}
         key = hdr.get("sec-websocket-key")
         if not key:
-            self.sock.sendall(b"HTTP/1.1 400 Bad Request\r\n\r\n")
+            self.send(b"HTTP/1.1 400 Bad Request\r\n\r\n")
             self.open = False
             return
         acc = base64.b64encode(hashlib.sha1(key.encode() + _GUID).digest())
-        self.sock.sendall(b"HTTP/1.1 101 Switching Protocols\r\nUpgrade: websocket\r\nConnection: Upgrade\r\nSec-WebSocket-Accept: " + acc + b"\r\n\r\n")
+        self.send(b"HTTP/1.1 101 Switching Protocols\r\nUpgrade: websocket\r\nConnection: Upgrade\r\nSec-WebSocket-Accept: " + acc + b"\r\n\r\n")
 
     def frames(self):
         """complete frames in the buffer -> (opcode, payload); fragmented messages are not used by the viewer"""
@@ -122,6 +135,10 @@ class _Client:
                     return
                 n, off = struct.unpack(">Q", self.buf[2:10])[0], 10
             masked = b1 & 0x80
+            if n > MAX_REQUEST_BYTES:     # never buffer what a client merely announces
+                self.open = False
+                self.buf = b""
+                return
             if len(self.buf) < off + (4 if masked else 0) + n:
                 return
             mask = self.buf[off:off + 4] if masked else None
@@ -136,7 +153,9 @@ class _Client:
 class WebSocketServer:
     """WebSocketServer("svo", 8001, backend) of the reference (websocketserver.cpp:35-55), polled from the tracking thread."""
 
-    def __init__(self, slam, port=8001, host="0.0.0.0"):
+    def __init__(self, slam, port=8001, host="127.0.0.1"):
+        """host: loopback by default — the reference's server listens on every interface (QHostAddress::Any); pass "0.0.0.0" to do
+        the same (the keyframe dump is unauthenticated)"""
         self.slam = slam
         self.srv = socket.socket(socket.AF_INET, socket.SOCK_STREAM)
         self.srv.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
@@ -154,7 +173,7 @@ class WebSocketServer:
         for s in ready:
             if s is self.srv:
                 conn, _ = self.srv.accept()
-                conn.setblocking(True)
+                conn.settimeout(SEND_TIMEOUT_S)
                 self.clients.append(_Client(conn))
                 continue
             c = next(x for x in self.clients if x.sock is s)
@@ -166,6 +185,9 @@ class WebSocketServer:
                 c.open = False
                 continue
             c.buf += data
+            if len(c.buf) > 2 * MAX_REQUEST_BYTES:
+                c.open = False
+                continue
             if c.resource is None:
                 c.handshake()
                 if c.resource is None or not c.open:
@@ -173,17 +195,15 @@ class WebSocketServer:
             for op, payload in c.frames():
                 if op == 1:      # text
                     out = answer(self.slam, c.resource, payload.decode("utf8", "replace"))
-                    if out is not None:
-                        s.sendall(_frame(1, out.encode("utf8")))
+                    if out is not None and c.send(_frame(1, out.encode("utf8"))):
                         sent += 1
                 elif op == 9:    # ping
-                    s.sendall(_frame(10, payload))
+                    c.send(_frame(10, payload))
                 elif op == 8:    # close
-                    try:
-                        s.sendall(_frame(8, payload[:2]))
-                    except OSError:
-                        pass
+                    c.send(_frame(8, payload[:2]))
                     c.open = False
+                if not c.open:
+                    break
         for c in [x for x in self.clients if not x.open]:
             c.sock.close()
             self.clients.remove(c)

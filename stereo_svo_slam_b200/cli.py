@@ -184,7 +184,7 @@ def iter_synthetic(cfg, frames):
         yield left, right, k / 20.0
 
 
-def run(frames, settings, device=0, trajectory=None, verbose=False, rectification=None, websocket_port=None):
+def run(frames, settings, device=0, trajectory=None, verbose=False, rectification=None, websocket_port=None, websocket_host="127.0.0.1"):
     from .slam import StereoSlam
     slam, t_algo, stamps, server = None, 0.0, [], None
     for left, right, ts in frames:
@@ -198,7 +198,7 @@ def run(frames, settings, device=0, trajectory=None, verbose=False, rectificatio
                     slam.set_rectification(which, c["K"], c["D"], c["R"], c["P"])
             if websocket_port is not None:
                 from .backend import WebSocketServer     # the reference app's server (src/app/main.cpp:208), for qt-viewer
-                server = WebSocketServer(slam, websocket_port)
+                server = WebSocketServer(slam, websocket_port, websocket_host)
         t0 = time.perf_counter()
         slam.new_image(left, right, ts)
         t_algo += time.perf_counter() - t0           # the reference's TickMeter brackets exactly new_image (slam_app.cpp:187-190)
@@ -227,6 +227,7 @@ def main(argv=None):
     ap.add_argument("--trajectory", "-t", help="trajectory CSV to write")
     ap.add_argument("--device", type=int, default=0)
     ap.add_argument("--websocket", type=int, metavar="PORT", help="serve the reference's /keyframes, /pose, /trajectory JSON (qt-viewer uses 8001)")
+    ap.add_argument("--websocket-host", default="127.0.0.1", help="interface of the WebSocket server (the reference listens on all: 0.0.0.0)")
     ap.add_argument("--verbose", action="store_true")
     a = ap.parse_args(argv)
     if a.synthetic:
@@ -238,7 +239,7 @@ def main(argv=None):
         settings = read_settings(a.settings)
         frames = iter_video(a.video) if a.video else iter_euroc(a.euroc) if a.euroc else iter_pairs(a.pairs)
     rect = read_rectification(a.settings) if a.euroc else None
-    traj, stamps, _ = run(frames, settings, a.device, a.trajectory, a.verbose, rect, a.websocket)
+    traj, stamps, _ = run(frames, settings, a.device, a.trajectory, a.verbose, rect, a.websocket, a.websocket_host)
     if stamps:
         print(f"{len(stamps)} frames, {len(stamps) / stamps[-1]:.1f} frames/s (algorithm time, test/extract_fps.py definition)")
     return 0

@@ -110,6 +110,55 @@ def test_websocket_round_trip(resource, message, key):
     assert (isinstance(msg, list) and len(msg) == 2) if key is None else key in msg
 
 
+def _handshake(port, resource="/keyframes"):
+    c = socket.create_connection(("127.0.0.1", port), timeout=5)
+    key = base64.b64encode(os.urandom(16))
+    c.sendall(b"GET " + resource.encode() + b" HTTP/1.1\r\nHost: localhost\r\nUpgrade: websocket\r\nConnection: Upgrade\r\n"
+              b"Sec-WebSocket-Key: " + key + b"\r\nSec-WebSocket-Version: 13\r\n\r\n")
+    return c
+
+
+def test_websocket_server_survives_bad_clients():
+    """The server runs on the tracking thread: a viewer that disconnects in the middle of an answer, announces a huge frame
+    or never reads must cost its own connection, never an exception in (or a stall of) the frame loop."""
+    class BigSlam(FakeSlam):
+        pass
+    slam = BigSlam()
+    srv = backend.WebSocketServer(slam, port=0)           # loopback by default
+    assert srv.srv.getsockname()[0] == "127.0.0.1"
+    # 1. request, then vanish without reading the answer
+    c = _handshake(srv.port)
+    for _ in range(20):
+        srv.serve_pending(timeout=0.02)
+    mask = os.urandom(4)
+    c.sendall(bytes([0x81, 0x83]) + mask + bytes(b ^ mask[i % 4] for i, b in enumerate(b"get")))
+    c.setsockopt(socket.SOL_SOCKET, socket.SO_LINGER, struct.pack("ii", 1, 0))   # RST on close
+    c.close()
+    for _ in range(20):
+        srv.serve_pending(timeout=0.02)                   # must not raise BrokenPipeError / ConnectionResetError
+    assert srv.clients == []
+    # 2. a frame header that announces 1 GiB: dropped, nothing buffered
+    c = _handshake(srv.port)
+    for _ in range(20):
+        srv.serve_pending(timeout=0.02)
+    c.sendall(bytes([0x81, 0x80 | 127]) + struct.pack(">Q", 1 << 30) + os.urandom(4) + b"x" * 100)
+    for _ in range(20):
+        srv.serve_pending(timeout=0.02)
+    assert srv.clients == []
+    c.close()
+    # 3. the server still answers a well-behaved client afterwards
+    got = {}
+    t = threading.Thread(target=lambda: got.setdefault("text", _ws_client(srv.port, "/pose", "x")))
+    t.start()
+    for _ in range(200):
+        srv.serve_pending(timeout=0.05)
+        if not t.is_alive():
+            break
+    t.join(timeout=5)
+    srv.close()
+    assert "pose" in json.loads(got["text"])
+
+
 def test_slam_accelerator_views_follow_the_cython_wrapper():
     """slam_accelerator drop-in: attribute-style access of src/python/wrapper/slam_accelerator.pyx
     (draw_kps.py reads kps2d[i].x, info[i].color['r'], info[i].type == KeyPointType.KP_FAST, pose.x, id)."""
