@@ -525,6 +525,30 @@ def main():
         del d64, h64
         dev = None
 
+    # ---------------- what the box delivers from page-locked host memory when ALL ranks read at once (the ceiling of e2e at N GPUs:
+    # on the 8-GPU boxes of this pool a GPU gets 23-35 GB/s then, against 51 GB/s alone): every rank reads 64 MB x 8 between barriers
+    link_all = None
+    if world > 1:
+        try:
+            probe = torch.empty(64 << 20, dtype=torch.uint8).pin_memory()
+            pctx = capi.Context(settings, W_, H_, device=local_rank)
+            gbs = C.c_float()
+            mine = 0.0
+            for _ in range(3):
+                barrier()
+                if lib.svo_debug_zero_copy_bandwidth(pctx.h_ctx, C.c_void_p(probe.data_ptr()), C.c_size_t(64 << 20), 148, 8, C.byref(gbs)) == 0:
+                    mine = max(mine, gbs.value)
+            barrier()
+            pctx.close()
+            del probe
+            tmin = torch.tensor([mine], device="cuda", dtype=torch.float64)
+            tsum = tmin.clone()
+            dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+            dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+            link_all = {"slowest_gpu_gbs": float(tmin.item()), "sum_gbs": float(tsum.item())}
+        except Exception as e:  # noqa: BLE001
+            link_all = {"error": str(e)[:100]}
+
     out = None
     if rank == 0:
         # ---------------- single sequence, the way an application runs it (one synchronous new_image per frame, page-locked
@@ -623,6 +647,10 @@ def main():
             del probe
             per_frame = 2 * H_ * W_ + n_kps * 45 + n_kps * 90
             pcie = {"bytes_per_frame": int(per_frame), "achieved_gbs": float(e2e / world * per_frame / 1e9), "link_peak_gbs": float(best),
+                    "all_gpus_reading": None if link_all is None else dict(
+                        link_all, frames_per_s_ceiling=(world * link_all["slowest_gpu_gbs"] * 1e9 / per_frame) if "slowest_gpu_gbs" in link_all else None,
+                        note="zero-copy read bandwidth with every rank reading its own page-locked buffer at once; every rank has the same work and a "
+                             "step ends with the slowest rank, so N x the slowest GPU's share / bytes per frame bounds e2e at N GPUs"),
                     "frac": float(e2e / world * per_frame / 1e9 / best) if best > 0 else None,
                     "note": "per GPU; link_peak = zero-copy read of a 64 MB page-locked buffer by 148 CTAs (one stream, sequential), "
                             "the e2e traffic is the interleaved streams' 722 KB frames plus the keypoint blocks in both directions"}

@@ -1128,7 +1128,7 @@ static int klt_common(svo_ctx *ctx, const int *keyframe_ids, int prev_slot, int 
     a.next_pts = DP(float, klt_pts); a.status = DP(uint8_t, klt_status); a.err = DP(float, klt_err);
     a.flags = nullptr; a.kps2d_out = nullptr; a.iters = nullptr;
     a.max_kps = n; a.cam = ctx->cam;
-    launch_klt(a, ctx->stream);
+    launch_klt(a, wide_solvers(ctx), ctx->stream);
     ctx->launch_total += 1;
     CK(cudaGetLastError());
     if ((rc = down(ctx, next_pts, ctx->lay.klt_pts, (size_t)n * 8))) return rc;
@@ -1425,8 +1425,8 @@ static int enqueue_track(svo_ctx *ctx, int prev_slot, int cur_slot, int n, int g
         ka.n_ptr = DP(int, n); ka.next_pts = DP(float, klt_pts); ka.status = DP(uint8_t, klt_status); ka.err = DP(float, klt_err);
         ka.flags = DP(uint8_t, flags); ka.kps2d_out = DP(float, kps2d_ref_in); ka.max_kps = grid_n; ka.cam = ctx->cam;
         ka.iters = DP(int, klt_iters);
-        launch_klt(ka, ctx->stream); launches++;
-        for (int k = 0; k < diag_dup("klt"); k++) launch_klt(ka, ctx->stream);
+        launch_klt(ka, wide_solvers(ctx), ctx->stream); launches++;
+        for (int k = 0; k < diag_dup("klt"); k++) launch_klt(ka, wide_solvers(ctx), ctx->stream);
         mark(ctx, 6);
     }
     // the stereo SSD of the depth filter only needs the positions the KLT stage left: with `forked` it runs beside the

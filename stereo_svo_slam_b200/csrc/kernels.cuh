@@ -170,7 +170,7 @@ struct KltArgs {
     int max_kps;
     DevCam cam;
 };
-void launch_klt(const KltArgs &a, cudaStream_t st);
+void launch_klt(const KltArgs &a, bool wide, cudaStream_t st);   // wide: two warps per keypoint (a sequence alone on the device)
 
 // ---- refine.cu
 struct RefineArgs {

@@ -60,6 +60,21 @@ __device__ __forceinline__ void lk_weights(float a, float b, int &iw00, int &iw0
     iw11 = (1 << 14) - iw00 - iw01 - iw10;
 }
 
+// calcOpticalFlowPyrLK's two stop tests, evaluated by OpenCV in double on float operands: `dx*dx + dy*dy <= 0.01*0.01` and
+// `fabs(dx + prev_dx) < 0.01`.  The double-precision pipe answers in ~25 cycles per dependent operation and these tests close the
+// loop-carried chain of every LK iteration, so they are decided in float wherever float can decide them exactly:
+//  * |f| < 0.01 (double) for a float f  <=>  |f| <= 0x1.47ae14p-7f, the largest float below the double 0.01 — exact, always;
+//  * the squared step is compared in float first; only a value within 1e-4 (relative) of the threshold — float rounding is 1e-7 —
+//    goes through the reference's double expression.
+__device__ __forceinline__ bool lk_step_converged(float dx, float dy)
+{
+    const float sf = __fmaf_rn(dx, dx, dy * dy);
+    if (sf < 0.9999e-4f) return true;
+    if (sf > 1.0001e-4f) return false;
+    return (double)dx * (double)dx + (double)dy * (double)dy <= 0.01 * 0.01;
+}
+__device__ __forceinline__ bool lk_below_eps(float f) { return fabsf(f) <= 0x1.47ae14p-7f; }
+
 template <int WIN>
 __global__ void __launch_bounds__(KLT_THREADS) klt_pyr_lk_kernel(KltArgs a)
 {
@@ -191,8 +206,8 @@ __global__ void __launch_bounds__(KLT_THREADS) klt_pyr_lk_kernel(KltArgs a)
             float dy = (float)((A12 * fb1 - A11 * fb2) * D);
             qx += dx; qy += dy;
             nx = qx + half; ny = qy + half;
-            if ((double)dx * (double)dx + (double)dy * (double)dy <= 0.01 * 0.01) break;
-            if (j > 0 && fabs((double)(dx + pdx)) < 0.01 && fabs((double)(dy + pdy)) < 0.01) {
+            if (lk_step_converged(dx, dy)) break;
+            if (j > 0 && lk_below_eps(dx + pdx) && lk_below_eps(dy + pdy)) {
                 nx -= dx * 0.5f; ny -= dy * 0.5f;
                 break;
             }
@@ -420,8 +435,8 @@ __global__ void __launch_bounds__(KLT_THREADS) klt31_kernel(KltArgs a)
             float dy = (float)((A12 * fb1 - A11 * fb2) * D);
             qx += dx; qy += dy;
             nx = qx + half; ny = qy + half;
-            if ((double)dx * (double)dx + (double)dy * (double)dy <= 0.01 * 0.01) break;
-            if (j > 0 && fabs((double)(dx + pdx)) < 0.01 && fabs((double)(dy + pdy)) < 0.01) {
+            if (lk_step_converged(dx, dy)) break;
+            if (j > 0 && lk_below_eps(dx + pdx) && lk_below_eps(dy + pdy)) {
                 nx -= dx * 0.5f; ny -= dy * 0.5f;
                 break;
             }
@@ -812,8 +827,8 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) klt31w_kernel(KltArgs 
             float dy = (float)((A12 * fb1 - A11 * fb2) * D);
             qx += dx; qy += dy;
             nx = qx + half; ny = qy + half;
-            if ((double)dx * (double)dx + (double)dy * (double)dy <= 0.01 * 0.01) break;
-            if (j > 0 && fabs((double)(dx + pdx)) < 0.01 && fabs((double)(dy + pdy)) < 0.01) {
+            if (lk_step_converged(dx, dy)) break;
+            if (j > 0 && lk_below_eps(dx + pdx) && lk_below_eps(dy + pdy)) {
                 nx -= dx * 0.5f; ny -= dy * 0.5f;
                 break;
             }
@@ -850,10 +865,252 @@ __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS) klt31w_kernel(KltArgs 
     }
 }
 
+// Two warps per keypoint (a sequence that has the device to itself): what a lone frame waits for in the KLT stage is its SLOWEST
+// keypoint — up to 90 LK iterations against 10 on average — and an iteration of klt31w_kernel is ~350 instructions of ONE warp
+// with nothing else on its scheduler to hide their latency.  Here lane l of warp h owns columns 16h .. 16h + 15 of window row l:
+// half the template in registers, half the window pass per iteration; the two partial sums meet through shared memory (exact
+// integers, so the order of the additions is immaterial) behind one CTA barrier per iteration, and both warps then take the same
+// 2x2 update redundantly.  Same bits as klt31w_kernel; twice the warps, so it is not the shape for many sequences per device.
+__global__ void __launch_bounds__(64, 8) klt31h_kernel(KltArgs a)
+{
+    const int lane = threadIdx.x & 31, hw = threadIdx.x >> 5;
+    const int i = blockIdx.x;
+    const int n = min(*a.n_ptr, a.max_kps);
+    if (i >= n) return;   // whole CTA exits together
+    constexpr int win = 31;
+    const float half = 15.0f;
+    const bool have_row = lane < win;
+    const int x0h = 16 * hw;                // first window column of this warp
+
+    float init_x, init_y;
+    if (a.init_pts) { init_x = a.init_pts[2 * i]; init_y = a.init_pts[2 * i + 1]; }
+    else {
+        double Rd[9];
+        const float *p = a.pose;
+        if (a.pose_rd) { for (int k = 0; k < 9; k++) Rd[k] = a.pose_rd[k]; } else dev_rodrigues_d(-p[3], -p[4], -p[5], Rd);
+        dev_project(Rd, a.kps3d[3 * i], a.kps3d[3 * i + 1], a.kps3d[3 * i + 2], p[0], p[1], p[2], a.cam.fx, a.cam.fy, a.cam.cx, a.cam.cy,
+                    a.cam.k1, a.cam.k2, a.cam.p1, a.cam.p2, a.cam.k3, init_x, init_y);
+    }
+    const float ppx = a.prev_pts[2 * i], ppy = a.prev_pts[2 * i + 1];
+    const LevelDesc *prev_lv = a.keyframe_ids ? (a.kf_lk_table + (size_t)a.keyframe_ids[i] * 2 * SVO_LK_LEVELS) : a.prev_fixed;
+    const LevelDesc *prev_dv = a.keyframe_ids ? (prev_lv + SVO_LK_LEVELS) : a.prev_fixed_deriv;
+    const uint4 *tpl_data = nullptr;
+    const float4 *tpl_hdr = nullptr;
+    int tpl_slot = 0;
+    if (a.kf_tpl_table && a.kp_index && a.keyframe_ids) {
+        const KfTemplates t = a.kf_tpl_table[a.keyframe_ids[i]];
+        const int idx = a.kp_index[i] - t.first;
+        if (t.data && idx >= 0 && idx < t.count) { tpl_data = t.data; tpl_hdr = t.hdr; tpl_slot = idx; }
+    }
+
+    float nx = init_x, ny = init_y;
+    int status = 1;
+    float err = 0.f;
+    int total_iters = 0;
+
+    __shared__ uint32_t swin[KLTW_REG_ROWS * KLTW_REG_PITCH + KLTW_REG_PITCH];
+    __shared__ long long s_part[2][2][2];   // [buffer][warp][b1, b2]
+    int pbuf = 0;
+    int reg_x0 = 0, reg_y0 = 0;
+    bool staged = false;
+    auto stage = [&](const LevelDesc &J, int ox, int oy) {
+        const int x0 = min(max(((ox - 8) >> 4) << 4, -SVO_LK_PAD), J.pitch - SVO_LK_PAD - 64);
+        const int y0 = min(max(oy - 8, -SVO_LK_PAD), J.h + SVO_LK_PAD - KLTW_REG_ROWS);
+        __syncthreads();   // both warps are done with the previous region
+        uint4 v[KLTW_REG_ROWS * 4 / 64];
+#pragma unroll
+        for (int t = 0; t < KLTW_REG_ROWS * 4 / 64; t++) {
+            const int idx = (int)threadIdx.x + 64 * t, r = idx >> 2, c = idx & 3;
+            v[t] = *reinterpret_cast<const uint4 *>(J.ptr + (ptrdiff_t)(y0 + r) * J.pitch + x0 + 16 * c);
+        }
+#pragma unroll
+        for (int t = 0; t < KLTW_REG_ROWS * 4 / 64; t++) {
+            const int idx = (int)threadIdx.x + 64 * t, r = idx >> 2, c = idx & 3;
+            uint32_t *d = swin + r * KLTW_REG_PITCH + 4 * c;
+            d[0] = v[t].x; d[1] = v[t].y; d[2] = v[t].z; d[3] = v[t].w;
+        }
+        __syncthreads();
+        reg_x0 = x0; reg_y0 = y0; staged = true;
+    };
+    auto ensure_staged = [&](const LevelDesc &J, int ox, int oy) {   // CTA uniform: both warps carry the same positions
+        const int rx = ox - reg_x0, ry = oy - reg_y0;
+        if (!staged || rx < 0 || rx > 31 || ry < 0 || ry > KLTW_REG_ROWS - 32) stage(J, ox, oy);
+    };
+    // CTA-wide exact sum of one value pair per lane (both warps get both totals)
+    auto cta_sum2 = [&](int p1, int p2, long long &o1, long long &o2) {
+        const long long w1 = warp_sum_i32_exact(p1), w2 = warp_sum_i32_exact(p2);
+        if (lane == 0) { s_part[pbuf][hw][0] = w1; s_part[pbuf][hw][1] = w2; }
+        __syncthreads();
+        o1 = s_part[pbuf][0][0] + s_part[pbuf][1][0];
+        o2 = s_part[pbuf][0][1] + s_part[pbuf][1][1];
+        pbuf ^= 1;   // a buffer is written again two sums later, i.e. after the barrier that follows every reader of this one
+    };
+
+    for (int level = SVO_LK_LEVELS - 1; level >= 0; level--) {
+        const LevelDesc I = prev_lv[level];
+        const LevelDesc Dv = prev_dv[level];
+        const LevelDesc J = a.cur[level];
+        staged = false;
+        const float scale = (float)(1. / (1 << level));
+        float px = ppx * scale, py = ppy * scale;
+        float qx, qy;
+        if (level == SVO_LK_LEVELS - 1) { qx = nx * scale; qy = ny * scale; }
+        else { qx = nx * 2.f; qy = ny * 2.f; }
+        nx = qx; ny = qy;
+        px -= half; py -= half;
+        const int ipx = (int)floorf(px), ipy = (int)floorf(py);
+        if (ipx < -win || ipx >= I.w || ipy < -win || ipy >= I.h) {
+            if (level == 0) { status = 0; err = 0.f; }
+            continue;
+        }
+        int iw00, iw01, iw10, iw11;
+        lk_weights(px - (float)ipx, py - (float)ipy, iw00, iw01, iw10, iw11);
+
+        // ---- this lane's HALF row of the template: columns x0h .. x0h + 15 (column 31 does not exist: zero)
+        int Iw[16], Ix[16], Iy[16];
+        float A11, A12, A22;
+        if (tpl_data) {
+            const uint4 *src = tpl_data + ((size_t)(tpl_slot * SVO_LK_LEVELS + level) * KLT_TPL_CHUNKS) * 32 + lane;
+            const float4 h = tpl_hdr[tpl_slot * SVO_LK_LEVELS + level];
+            A11 = h.x; A12 = h.y; A22 = h.z;
+            if (level > 0) {
+                const char *nxt = reinterpret_cast<const char *>(tpl_data + ((size_t)(tpl_slot * SVO_LK_LEVELS + level - 1) * KLT_TPL_CHUNKS) * 32);
+                if (threadIdx.x < 48) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + 128 * threadIdx.x));
+            }
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                const uint4 wa = src[(size_t)(2 * hw + c) * 32], wb = src[(size_t)(4 + 2 * hw + c) * 32], wc = src[(size_t)(8 + 2 * hw + c) * 32];
+                const uint32_t ua[4] = {wa.x, wa.y, wa.z, wa.w}, ub[4] = {wb.x, wb.y, wb.z, wb.w}, uc[4] = {wc.x, wc.y, wc.z, wc.w};
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int xl = 8 * c + 2 * q;
+                    Iw[xl] = (int)(short)(ua[q] & 0xffffu); Ix[xl] = (int)(short)(ub[q] & 0xffffu); Iy[xl] = (int)(short)(uc[q] & 0xffffu);
+                    Iw[xl + 1] = (int)ua[q] >> 16; Ix[xl + 1] = (int)ub[q] >> 16; Iy[xl + 1] = (int)uc[q] >> 16;   // the pad of column 31 is stored as 0
+                }
+            }
+        } else {
+            // keyframe without cached templates (stage entry points): every warp builds whole rows and keeps its half
+            int fIw[31], fIx[31], fIy[31], acc11, acc12, acc22;
+            klt31_build_row(I, Dv, ipx, ipy, iw00, iw01, iw10, iw11, lane, have_row, fIw, fIx, fIy, acc11, acc12, acc22);
+            const long long s11 = warp_sum_i32_exact(acc11), s12 = warp_sum_i32_exact(acc12), s22 = warp_sum_i32_exact(acc22);
+            const float FLT_SCALE0 = 1.f / (1 << 20);
+            A11 = (float)s11 * FLT_SCALE0; A12 = (float)s12 * FLT_SCALE0; A22 = (float)s22 * FLT_SCALE0;
+#pragma unroll
+            for (int xl = 0; xl < 16; xl++) {
+                Iw[xl] = hw ? (xl < 15 ? fIw[16 + (xl < 15 ? xl : 0)] : 0) : fIw[xl];
+                Ix[xl] = hw ? (xl < 15 ? fIx[16 + (xl < 15 ? xl : 0)] : 0) : fIx[xl];
+                Iy[xl] = hw ? (xl < 15 ? fIy[16 + (xl < 15 ? xl : 0)] : 0) : fIy[xl];
+            }
+        }
+        const float FLT_SCALE = 1.f / (1 << 20);
+        float D = A11 * A22 - A12 * A12;
+        float minEig = (A22 + A11 - sqrtf((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) / (float)(2 * win * win);
+        if ((double)minEig < 1e-4 || D < 1.1920929e-07f) {
+            if (level == 0) status = 0;
+            continue;
+        }
+        D = 1.f / D;
+        qx -= half; qy -= half;
+        float pdx = 0.f, pdy = 0.f;
+#pragma unroll
+        for (int x = 0; x < 16; x++) Iw[x] = (1 << 8) - (Iw[x] << 9);
+        // this lane's half of one evaluation pass over the window at integer origin (ox, oy)
+        auto window_pass = [&](int ox, int oy, int w00, int w01, int w10, int w11, int &o1, int &o2, bool want_err) {
+            ensure_staged(J, ox, oy);
+            const int rx = ox - reg_x0 + x0h, ry = oy - reg_y0;
+            const uint32_t *base = swin + (ry + lane) * KLTW_REG_PITCH + (rx >> 2);
+            const int sh = (rx & 3) * 8;
+            uint32_t wv[6];
+#pragma unroll
+            for (int k = 0; k < 6; k++) wv[k] = base[k];
+            uint32_t top[5], bot[5];
+#pragma unroll
+            for (int k = 0; k < 5; k++) top[k] = __funnelshift_r(wv[k], wv[k + 1], sh);
+#pragma unroll
+            for (int k = 0; k < 5; k++) bot[k] = __shfl_down_sync(0xffffffffu, top[k], 1);
+            const uint32_t Wt = ((uint32_t)w00 & 0xffffu) | ((uint32_t)w01 << 16), Wb = ((uint32_t)w10 & 0xffffu) | ((uint32_t)w11 << 16);
+            int acc1 = 0, acc2 = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t ts = __funnelshift_r(top[k], top[k + 1], 8), bs = __funnelshift_r(bot[k], bot[k + 1], 8);
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int xl = 4 * k + q;
+                    int v;
+                    const int c0 = Iw[xl];
+                    if (q == 0) v = dp2a_lo_s16u8(Wt, top[k], dp2a_lo_s16u8(Wb, bot[k], c0));
+                    else if (q == 1) v = dp2a_lo_s16u8(Wt, ts, dp2a_lo_s16u8(Wb, bs, c0));
+                    else if (q == 2) v = dp2a_hi_s16u8(Wt, top[k], dp2a_hi_s16u8(Wb, bot[k], c0));
+                    else v = dp2a_hi_s16u8(Wt, ts, dp2a_hi_s16u8(Wb, bs, c0));
+                    int diff = v >> 9;
+                    if (xl == 15 && hw) diff = 0;          // column 31 is not part of the window
+                    if (want_err) acc1 += abs(diff);
+                    else { acc1 += diff * Ix[xl]; acc2 += diff * Iy[xl]; }
+                }
+            }
+            if (!have_row) { acc1 = 0; acc2 = 0; }
+            o1 = acc1; o2 = acc2;
+        };
+        for (int j = 0; j < 30; j++) {
+            const int iqx = (int)floorf(qx), iqy = (int)floorf(qy);
+            if (iqx < -win || iqx >= J.w || iqy < -win || iqy >= J.h) {
+                if (level == 0) status = 0;
+                break;
+            }
+            lk_weights(qx - (float)iqx, qy - (float)iqy, iw00, iw01, iw10, iw11);
+            total_iters++;
+            int p1, p2;
+            window_pass(iqx, iqy, iw00, iw01, iw10, iw11, p1, p2, false);
+            long long b1, b2;
+            cta_sum2(p1, p2, b1, b2);
+            float fb1 = (float)b1 * FLT_SCALE, fb2 = (float)b2 * FLT_SCALE;
+            float dx = (float)((A12 * fb2 - A22 * fb1) * D);
+            float dy = (float)((A12 * fb1 - A11 * fb2) * D);
+            qx += dx; qy += dy;
+            nx = qx + half; ny = qy + half;
+            if (lk_step_converged(dx, dy)) break;
+            if (j > 0 && lk_below_eps(dx + pdx) && lk_below_eps(dy + pdy)) {
+                nx -= dx * 0.5f; ny -= dy * 0.5f;
+                break;
+            }
+            pdx = dx; pdy = dy;
+        }
+        if (status && level == 0) {
+            float ex = nx - half, ey = ny - half;
+            const int iex = (int)floorf(ex), iey = (int)floorf(ey);
+            if (iex < -win || iex >= J.w || iey < -win || iey >= J.h) { status = 0; continue; }
+            lk_weights(ex - (float)iex, ey - (float)iey, iw00, iw01, iw10, iw11);
+            int e1, e2;
+            window_pass(iex, iey, iw00, iw01, iw10, iw11, e1, e2, true);
+            long long e, dummy;
+            cta_sum2(e1, 0, e, dummy);
+            err = (float)e * 1.f / (float)(32 * win * win);
+        }
+    }
+
+    if (threadIdx.x == 0) {
+        if (status == 0) err = __int_as_float(0x7f800000);  // optical_flow.cpp:46-50
+        a.next_pts[2 * i] = nx; a.next_pts[2 * i + 1] = ny;
+        a.status[i] = (uint8_t)status;
+        a.err[i] = err;
+        if (a.iters) a.iters[i] = total_iters;
+        if (a.flags) {  // pose_refinement.cpp:125-150
+            uint8_t f = a.flags[i];
+            float ox = init_x, oy = init_y;
+            float d = (init_x - nx) * (init_x - nx) + (init_y - ny) * (init_y - ny);
+            if (err > 20) f |= SVO_F_IGN_COMPLETE;
+            else if (d > 81) f |= SVO_F_IGN_REFINE;
+            else { f &= (uint8_t)~SVO_F_IGN_REFINE; ox = nx; oy = ny; }
+            a.flags[i] = f;
+            a.kps2d_out[2 * i] = ox; a.kps2d_out[2 * i + 1] = oy;
+        }
+    }
+}
+
 static int g_klt_variant = -1;  // SVO_KLT_VARIANT=block selects the CTA-per-keypoint kernel (A/B measurements)
 static int g_klt_warps = -1;    // SVO_KLT_WARPS=1|4: keypoints per CTA of the warp-per-keypoint kernel
 
-void launch_klt(const KltArgs &a, cudaStream_t st)
+void launch_klt(const KltArgs &a, bool wide, cudaStream_t st)
 {
     if (a.max_kps <= 0) return;
     if (g_klt_variant < 0) {
@@ -864,7 +1121,11 @@ void launch_klt(const KltArgs &a, cudaStream_t st)
         const char *e = getenv("SVO_KLT_WARPS");
         g_klt_warps = (e && atoi(e) == 4) ? 4 : 1;
     }
-    if (a.cam.win_flow == 31 && g_klt_variant == 0 && g_klt_warps == 4) klt31w_kernel<4><<<(a.max_kps + 3) / 4, 128, 0, st>>>(a);
+    static const bool no_split = getenv("SVO_KLT_NO_SPLIT") != nullptr;   // developer A/B switch
+    // two warps per keypoint: -8 % for a lone frame of a few hundred keypoints (the stage lasts as long as its slowest keypoint), a
+    // loss once the keypoints outnumber the warp slots (C4, 3 000 keypoints: 59 -> 65 us)
+    if (a.cam.win_flow == 31 && g_klt_variant == 0 && wide && !no_split && a.max_kps <= 1024) klt31h_kernel<<<a.max_kps, 64, 0, st>>>(a);
+    else if (a.cam.win_flow == 31 && g_klt_variant == 0 && g_klt_warps == 4) klt31w_kernel<4><<<(a.max_kps + 3) / 4, 128, 0, st>>>(a);
     else if (a.cam.win_flow == 31 && g_klt_variant == 0) klt31w_kernel<1><<<a.max_kps, 32, 0, st>>>(a);
     else if (a.cam.win_flow == 31) klt31_kernel<<<a.max_kps, KLT_THREADS, 0, st>>>(a);
     else klt_pyr_lk_kernel<0><<<a.max_kps, KLT_THREADS, 0, st>>>(a);
