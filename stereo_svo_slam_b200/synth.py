@@ -85,8 +85,11 @@ class SyntheticStereo:
         v0 = np.clip(v0, 0, 2 * self.h - 1.001)
         x0, y0 = np.floor(u0).astype(np.int64), np.floor(v0).astype(np.int64)
         a, b = (u0 - x0).astype(np.float32), (v0 - y0).astype(np.float32)
-        T = self.tex
-        val = (1 - a) * (1 - b) * T[y0, x0] + a * (1 - b) * T[y0, x0 + 1] + (1 - a) * b * T[y0 + 1, x0] + a * b * T[y0 + 1, x0 + 1]
+        T = self.tex.reshape(-1)              # one flat index per pixel instead of four 2-D fancy indexings (same values, half the time)
+        W2 = self.tex.shape[1]
+        idx = y0 * W2 + x0
+        a1, b1 = 1 - a, 1 - b
+        val = a1 * b1 * T[idx] + a * b1 * T[idx + 1] + a1 * b * T[idx + W2] + a * b * T[idx + W2 + 1]
         return np.clip(np.rint(val), 0, 255).astype(np.uint8)
 
     def render(self, k):
