@@ -407,6 +407,35 @@ def test_slam_free_running_matches_oracle(cfg, frames, cluster):
     g.close()
 
 
+@pytest.mark.parametrize("cfg", ["C3", "S", "C4"])
+def test_frame_pyramids_of_the_graph_path_are_bit_exact(cfg):
+    """The images a tracking frame leaves on the device — level 0 of both cameras and every half-sample level of the left one
+    (createImgPyramid, stereo_slam.cpp:93-121) — on the path new_image really takes: ingest kernel + CUDA-graph replay.  Pageable
+    frames (staged) and page-locked frames (read over PCIe by the kernel itself)."""
+    import torch
+    from stereo_svo_slam_b200 import StereoSlam
+    gcs, _ = mk(cfg)
+    c = synth.CONFIGS[cfg]
+    seq = synth.make_sequence(cfg)
+    g = StereoSlam(gcs, c["width"], c["height"])
+    pinned = torch.empty((2, c["height"], c["width"]), dtype=torch.uint8).pin_memory()
+    for k in range(5):
+        L, R = seq.render(k)
+        if k % 2:            # page-locked source: zero-copy ingest
+            pinned[0].copy_(torch.from_numpy(L)); pinned[1].copy_(torch.from_numpy(R))
+            g.new_image(pinned[0].numpy(), pinned[1].numpy(), k / 20.0)
+        else:
+            g.new_image(L, R, k / 20.0)
+        f = g.get_frame()
+        want = L
+        for level in range(c["max_pyramid_levels"]):
+            got = f.image("left", level)
+            assert got.shape == want.shape and (got == want).all(), (k, level)
+            want = orc.half_sample(want)
+        assert (f.image("right", 0) == R).all(), k
+    g.close()
+
+
 def test_cuda_graph_replay_is_bit_identical():
     """The per-frame sequence replayed as a CUDA graph (default) and launched kernel by kernel give the same bits."""
     import ctypes as C
