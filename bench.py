@@ -295,6 +295,15 @@ def stream_seeds(rank, world, streams_per_gpu, total_streams=0):
     return [1000 + rank * streams_per_gpu + s for s in range(streams_per_gpu)]
 
 
+def align_cluster_for(n_seq, override=-1):
+    """SMs per alignment solve (svo_set_align_cluster) for n_seq sequences on one GPU: what a frame costs the GPU is the time its
+    cluster holds its SMs, so smaller clusters win once there are enough sequences to hide their longer solves (measured, DESIGN.md
+    section 4).  override >= 0: the --align-cluster flag (0 = library default: 8, or 16 above 1024 keypoints)."""
+    if override >= 0:
+        return override
+    return 2 if n_seq >= 56 else (4 if n_seq >= 24 else 0)
+
+
 def aggregate_ranks(seconds, counters, all_reduce=None):
     """Whole-job figures from per-rank ones: the time is the MAX over ranks, the work counters are SUMMED.
     all_reduce(list_of_floats, "max" | "sum") -> list; None for a single process."""
@@ -350,7 +359,7 @@ def main():
               "rendered_frames_per_sequence": nframes,
               "align_cluster": "SMs per alignment solve (svo_set_align_cluster): %s for the %d sequences per GPU of this run (0 = library default 8); "
                                "a deployment knob, results within the pose tolerance for every setting" % (
-                                   a.align_cluster if a.align_cluster >= 0 else (2 if S >= 56 else (4 if S >= 24 else 0)), S),
+                                   align_cluster_for(S, a.align_cluster), S),
               "playback": "a stream is a succession of finite sequences (BASELINE configs[4] streams are 200 frames long): the rendered frames "
                           "played forward, then the stream restarts with a fresh tracker on the same device resources (svo_slam_reset) — every "
                           "pass creates keyframe #1 at its frame 0 and keyframe #2 around frame 46, like the reference would",
@@ -409,9 +418,7 @@ def main():
         return fr, h, h.to("cuda", non_blocking=False)                 # HBM-resident inputs (value)
 
     def cluster_for(n_seq):
-        if a.align_cluster >= 0:
-            return a.align_cluster
-        return 2 if n_seq >= 56 else (4 if n_seq >= 24 else 0)
+        return align_cluster_for(n_seq, a.align_cluster)
 
     def run(mode, host, dev, n_seq, clocks=None):
         """W warm-up steps, then K timed steps of F frames per sequence; returns whole-rank counters and the time (max over ranks)"""

@@ -79,3 +79,12 @@ def test_partition_is_disjoint_and_complete_for_every_world_size():
         got = [s for r in range(world) for s in bench.stream_seeds(r, world, 5, 0)]
         assert sorted(got) == list(range(1000, 1000 + 5 * world))
     assert bench.aggregate_ranks(2.0, [1.0, 2.0]) == (2.0, [1.0, 2.0])
+
+
+def test_alignment_cluster_policy_follows_the_streams_per_gpu():
+    """bench.align_cluster_for: configs[4] puts 64 / 32 / 16 / 8 streams on a GPU at N = 1 / 2 / 4 / 8 — 2, 4, library default, library
+    default SMs per alignment solve; the --align-cluster flag overrides."""
+    import bench
+    assert [bench.align_cluster_for(len(bench.stream_seeds(0, n, 48, 64))) for n in (1, 2, 4, 8)] == [2, 4, 0, 0]
+    assert bench.align_cluster_for(48) == 4 and bench.align_cluster_for(56) == 2 and bench.align_cluster_for(23) == 0
+    assert bench.align_cluster_for(48, 8) == 8 and bench.align_cluster_for(4, 0) == 0
