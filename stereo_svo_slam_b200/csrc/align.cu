@@ -498,15 +498,15 @@ __global__ void __launch_bounds__(ALIGN_THREADS, 1) sparse_align_kernel(AlignArg
                     }
                     if (row == 0) part += (double)run;   // one lane per keypoint carries the patch cost
                 }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) part += __shfl_down_sync(0xffffffffu, part, o);
+                // only the eight quad leaders of a warp (row == 0) carry a value: three butterfly steps instead of five
+                part += __shfl_xor_sync(0xffffffffu, part, 4);
+                part += __shfl_xor_sync(0xffffffffu, part, 8);
+                part += __shfl_xor_sync(0xffffffffu, part, 16);
                 if (lane == 0) hdr->warp_cost[warp] = part;
                 __syncthreads();
                 if (tid < CL * G) {   // lane t pushes this CTA's partial into CTA t's table and signals CTA t's barrier (every CTA pushes in
                                       // every round, with or without a trial of its own: see the note on cbuf)
-                    double cta = 0.0;
-#pragma unroll
-                    for (int q = 0; q < ALIGN_WARPS; q++) cta += hdr->warp_cost[q];
+                    const double cta = tree_sum<ALIGN_WARPS>(hdr->warp_cost);
                     dsmem_push_f64(&hdr->cl_cost[cbuf][grp * CL + crank], &hdr->xbar[cbuf], (unsigned)tid, cta);
                     if (tid == 0) mbar_expect_tx(&hdr->xbar[cbuf], CL * G * 8);
                 }
@@ -518,10 +518,7 @@ __global__ void __launch_bounds__(ALIGN_THREADS, 1) sparse_align_kernel(AlignArg
                 trc.stamp(4, nvalid);
                 // replay of the sequential driver over the costs of this round, in order
                 for (int g = 0; g < nvalid && mode != 3 && mode != 1; g++) {
-                    double tot = 0.0;
-#pragma unroll
-                    for (int q = 0; q < CL; q++) tot += table[g * CL + q];
-                    const float cost = (float)tot;
+                    const float cost = (float)tree_sum<CL>(table + g * CL);
                     n_evals++;
                     if (mode == 0) {
                         prev_cost = cost;
@@ -634,9 +631,7 @@ __global__ void __launch_bounds__(ALIGN_THREADS, 1) sparse_align_kernel(AlignArg
                 }
                 __syncthreads();
                 if (tid < NGRAD) {
-                    double t = 0.0;
-#pragma unroll
-                    for (int q = 0; q < ALIGN_WARPS; q++) t += (double)hdr->warp_grad[q][tid];
+                    const double t = tree_sum<ALIGN_WARPS>(&hdr->warp_grad[0][tid], NGRAD);
 #pragma unroll
                     for (unsigned dst = 0; dst < CL; dst++) dsmem_push_f64(&hdr->cl_grad[crank][tid], &hdr->xbar[2], grp * CL + dst, t);
                     if (tid == 0) mbar_expect_tx(&hdr->xbar[2], CL * NGRAD * 8);
@@ -645,10 +640,7 @@ __global__ void __launch_bounds__(ALIGN_THREADS, 1) sparse_align_kernel(AlignArg
                 else mbar_wait(&hdr->xbar[2], xphase[2]);
                 xphase[2] ^= 1;
                 if (tid < NGRAD) {
-                    double t = 0.0;
-#pragma unroll
-                    for (int q = 0; q < CL; q++) t += hdr->cl_grad[q][tid];
-                    hdr->red_out[tid] = t;
+                    hdr->red_out[tid] = tree_sum<CL>(&hdr->cl_grad[0][tid], NGRAD);
                 }
                 __syncthreads();
                 trc.stamp(8);

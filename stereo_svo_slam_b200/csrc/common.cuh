@@ -485,6 +485,18 @@ __device__ __forceinline__ bool dev_solve6(const double *Hu /*21 upper-tri row-m
     return true;
 }
 
+// Sum of N values spaced `stride` apart as a balanced binary tree, in double.  The solvers' cross-warp and cross-CTA sums are
+// chains of dependent double-precision additions on the critical path of every evaluation round (the FP64 pipe answers in ~25
+// cycles): a tree of depth log2(N) instead of a chain of length N.  The grouping is fixed (deterministic) and is the solvers' own —
+// the reference adds floats sequentially, and a double holds these sums of a few thousand floats exactly in all but pathological
+// cases, so the grouping does not even show in the bits.
+template <int N, typename T>
+__device__ __forceinline__ double tree_sum(const T *v, int stride = 1)
+{
+    if constexpr (N == 1) return (double)v[0];
+    else return tree_sum<N / 2, T>(v, stride) + tree_sum<N - N / 2, T>(v + (size_t)(N / 2) * stride, stride);
+}
+
 // developer aid (SVO_SOLVER_TRACE): one thread stamps the phases of a solver kernel with the SM clock
 struct SolverTrace {
     unsigned long long *buf; int n; bool on;

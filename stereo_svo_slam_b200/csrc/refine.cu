@@ -130,11 +130,7 @@ __global__ void __launch_bounds__(REF_THREADS, 1) reproj_refine_kernel(RefineArg
                 // this round push too (an unused slot): EVERY peer's push of exchange e + 1 then tells that the peer is done reading
                 // the table of exchange e, which is what makes the two alternating buffers safe
                 if (tid < NCL) {
-                    double tot = 0.0;
-                    if (mine) {
-#pragma unroll
-                        for (int q = 0; q < REF_WARPS; q++) tot += hdr.cost_part[cb][q];
-                    }
+                    const double tot = mine ? tree_sum<REF_WARPS>(hdr.cost_part[cb]) : 0.0;
                     dsmem_push_f64(&hdr.cl_cost[xb][crank], &hdr.xbar[xb], (unsigned)tid, tot);
                 }
                 if (tid == 0) mbar_expect_tx(&hdr.xbar[xb], NCL * 8);
@@ -143,8 +139,7 @@ __global__ void __launch_bounds__(REF_THREADS, 1) reproj_refine_kernel(RefineArg
                 costs = hdr.cl_cost[xb];
                 xb ^= 1;   // alternates over the whole solve: a buffer is free again exactly two exchanges later (see sparse_align_kernel)
             } else {
-#pragma unroll
-                for (int q = 0; q < REF_WARPS; q++) tot_local += hdr.cost_part[cb][q];
+                tot_local = tree_sum<REF_WARPS>(hdr.cost_part[cb]);
             }
             trc.stamp(4, nvalid);
             // replay of the sequential driver over the costs of this round
@@ -231,10 +226,7 @@ __global__ void __launch_bounds__(REF_THREADS, 1) reproj_refine_kernel(RefineArg
             }
             __syncthreads();
             if (tid < RNGRAD) {
-                double t = 0.0;
-#pragma unroll
-                for (int q = 0; q < REF_WARPS; q++) t += (double)hdr.grad_part[tid][q];
-                hdr.red_out[tid] = t;
+                hdr.red_out[tid] = tree_sum<REF_WARPS>(hdr.grad_part[tid]);
             }
             __syncthreads();
             trc.stamp(8);
