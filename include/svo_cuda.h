@@ -253,7 +253,8 @@ int svo_sync(svo_ctx *ctx);
  * all -1 when the aid is off */
 int svo_debug_marks(svo_ctx *ctx, int *out64);
 /* developer aid (env SVO_SOLVER_TRACE=1 at context creation): phase stamps of the last alignment (which = 0) or refinement
- * (which = 1) solve: out[0] = entries n, out[1..n] = SM clock << 16 | extra << 8 | tag (0 start, 1 level start, 2 level images
+ * (which = 1) solve, or of the last depth-filter / export kernel (which = 2; tags 1 matrices ready, 2 keypoint updated, 3 all
+ * keypoints done, 4 export table ready, 5 copies issued, 6 copies done in the CTA, 7 system fence passed): out[0] = entries n, out[1..n] = SM clock << 16 | extra << 8 | tag (0 start, 1 level start, 2 level images
  * staged, 3 reference terms cached, 4 cost round done (extra = trial poses in it), 5 gradient round done, 6 end) */
 int svo_debug_solver_trace(svo_ctx *ctx, int which, unsigned long long *out, int cap);
 /* developer probe: bandwidth (GB/s) at which `ctas` CTAs of 256 threads read page-locked host memory over PCIe with the

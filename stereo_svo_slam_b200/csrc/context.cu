@@ -804,9 +804,9 @@ extern "C" int svo_debug_zero_copy_bandwidth(svo_ctx *ctx, const void *pinned_ho
 
 extern "C" int svo_debug_solver_trace(svo_ctx *ctx, int which, unsigned long long *out, int cap)
 {
-    if (!ctx || !out || which < 0 || which > 1 || cap < 1) return SVO_ERR_INVALID;
+    if (!ctx || !out || which < 0 || which > 2 || cap < 1) return SVO_ERR_INVALID;
     if (!ctx->h_trace) { out[0] = 0; return SVO_OK; }
-    const volatile unsigned long long *src = ctx->h_trace + 1024 * which;
+    const volatile unsigned long long *src = ctx->h_trace + (which == 2 ? 512 : 1024 * which);
     const unsigned long long n0 = src[0]; const int n = n0 < 1000 ? (int)n0 : 1000;
     for (int k = 0; k <= n && k < cap; k++) out[k] = src[k];
     return SVO_OK;
@@ -1211,7 +1211,7 @@ extern "C" int svo_depth_filter_update(svo_ctx *ctx, int slot, int n, const floa
     fa.kps2d = DP(float, kps2d_ref_in); fa.ref_kps2d = DP(float, ref_kps2d); fa.kps3d = DP(float, kps3d);
     fa.flags = DP(uint8_t, flags); fa.inlier = DP(int, inlier); fa.outlier = DP(int, outlier); fa.kf_state = DP(float, kf_state);
     fa.pose = DP(float, pose_refined); fa.kps2d_out = DP(float, kps2d_out); fa.n_ptr = DP(int, n); fa.max_kps = n; fa.cam = ctx->cam;
-    fa.do_export = 0; fa.rdn_in = nullptr; fa.done_rec = nullptr; fa.seq_ptr = nullptr; fa.t_start = nullptr;
+    fa.do_export = 0; fa.rdn_in = nullptr; fa.done_rec = nullptr; fa.seq_ptr = nullptr; fa.t_start = nullptr; fa.trace = nullptr;
     launch_depth_filter(fa, ctx->stream);
     ctx->launch_total += 2;
     CK(cudaGetLastError());
@@ -1473,6 +1473,7 @@ static int enqueue_track(svo_ctx *ctx, int prev_slot, int cur_slot, int n, int g
         fa.do_export = ctx->d_hio != nullptr; fa.exp = ctx->io_out;   // results go to the host mirror from the same kernel
         fa.rdn_in = DP(double, rd_refined);
         fa.done_rec = nullptr; fa.seq_ptr = nullptr; fa.t_start = nullptr;
+        fa.trace = ctx->d_trace ? ctx->d_trace + 512 : nullptr;   // third trace region (the alignment kernel uses < 100 of its 1024 words)
         if (ctx->capturing_slim && ctx->d_hio && !getenv("SVO_SLIM_NOREC")) {
             fa.done_rec = reinterpret_cast<unsigned long long *>(ctx->d_hio + L.done);
             fa.seq_ptr = reinterpret_cast<const unsigned *>(ctx->d_io + L.hdr_seq);

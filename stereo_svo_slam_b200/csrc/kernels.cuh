@@ -223,6 +223,7 @@ struct FilterArgs {
     unsigned long long *done_rec;        // 4 x u64 in mapped host memory
     const unsigned *seq_ptr;             // device copy of the frame header's sequence number
     const unsigned long long *t_start;   // device: stamp left by the ingest kernel
+    unsigned long long *trace;           // developer aid (SVO_SOLVER_TRACE), as in AlignArgs, or null
 };
 void launch_depth_filter(const FilterArgs &a, cudaStream_t st);
 

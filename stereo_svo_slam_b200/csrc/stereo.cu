@@ -599,6 +599,8 @@ __global__ void __launch_bounds__(DF_THREADS) depth_filter_kernel(FilterArgs a)
 {
     __shared__ FrameMats fm;
     const int n = min(*a.n_ptr, a.max_kps);
+    SolverTrace trc(a.trace, threadIdx.x == 0);
+    trc.stamp(0);
     if (a.rdn_in) {
         // Rodrigues(-r) in double as the refinement kernel left it; float(Rodrigues(r)) is its transpose bit for bit
         if (threadIdx.x < 9) {
@@ -612,6 +614,7 @@ __global__ void __launch_bounds__(DF_THREADS) depth_filter_kernel(FilterArgs a)
         dev_rodrigues_d(-p[3], -p[4], -p[5], fm.Rdn);
     }
     __syncthreads();
+    trc.stamp(1);
     for (int i = threadIdx.x; i < n; i += DF_THREADS) {
         const DevCam cam = a.cam;
         const float fx = cam.fx, fy = cam.fy, cx = cam.cx, cy = cam.cy, baseline = cam.baseline;
@@ -707,23 +710,30 @@ __global__ void __launch_bounds__(DF_THREADS) depth_filter_kernel(FilterArgs a)
         dev_project(fm.Rdn, P0, P1, P2, c2[0], c2[1], c2[2], fx, fy, cx, cy, cam.k1, cam.k2, cam.p1, cam.p2, cam.k3, ou, ov);
         a.kps2d_out[2 * i] = ou; a.kps2d_out[2 * i + 1] = ov;
     }
+    trc.stamp(2);
     if (a.do_export) {
         __syncthreads();   // this CTA wrote the last results of the frame; everything earlier in the stream is complete
+        trc.stamp(3);
         io_copy_block(a.exp);
+        trc.stamp(5);
         if (a.done_rec) {
             // completion record: the CTA barrier orders every thread's result stores before thread 0's system-scope fence
             // (fences are cumulative), the fence orders them before the sequence number the host polls for — ONE fence per frame
             __syncthreads();
+            trc.stamp(6);
             if (threadIdx.x == 0) {
                 unsigned long long t;
                 asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
                 a.done_rec[2] = *a.t_start;
                 a.done_rec[3] = t;
                 __threadfence_system();
+                trc.stamp(7);
                 *reinterpret_cast<volatile unsigned *>(a.done_rec) = *a.seq_ptr;
             }
         }
     }
+    trc.stamp(8);
+    trc.finish();
 }
 
 void launch_depth_filter(const FilterArgs &a, cudaStream_t st)

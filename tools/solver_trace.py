@@ -27,7 +27,10 @@ except Exception:  # noqa: BLE001
 lib = capi.lib()
 ctx = C.c_void_p(lib.svo_slam_ctx(g._h))
 names = {0: "start", 1: "level", 2: "images staged", 3: "reference terms", 4: "cost round", 5: "gradient round", 6: "end", 7: "  grad: keypoints done", 8: "  grad: sums exchanged", 9: "  grad: 6x6 solved", 10: "  grad: expmap + rotation", 11: "  grad: Rodrigues of the trial pose"}
-for which, kname in ((0, "sparse_align_kernel"), (1, "reproj_refine_kernel")):
+for which, kname in ((0, "sparse_align_kernel"), (1, "reproj_refine_kernel"), (2, "depth_filter_kernel")):
+    if which == 2:
+        names = {0: "start", 1: "matrices ready", 2: "own keypoint updated", 3: "all keypoints done", 5: "export copies issued", 6: "export copies done in the CTA",
+                 7: "system fence passed", 8: "end"}
     buf = (C.c_ulonglong * 1024)()
     lib.svo_debug_solver_trace(ctx, which, buf, 1024)
     n = int(buf[0])
