@@ -27,6 +27,7 @@ CASES = [
     ("S_dist", "S", 30, dict(k1=-0.12, k2=0.05, p1=0.001, p2=-0.0015, k3=0.01), False),   # full projectPoints model
     ("S_blender_grid", "S", 30, dict(grid_width=25, grid_height=16, max_pyramid_levels=5), False),  # odd grid, 5 levels
     ("C3", "C3", 64, {}, False),           # BASELINE configs[2]; keyframe #2 at frame 46
+    ("C4", "C4", 12, {}, False),           # BASELINE configs[3]: 1280x720, 5 levels, 16x14 grid (3 000 keypoints per frame)
 ]
 FIELDS = ("kps2d", "kps3d", "score", "kf_state", "kf_cov") + orc.INFO_COLS[:-1]   # colour is rand(): not compared
 
