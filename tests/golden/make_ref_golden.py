@@ -28,6 +28,11 @@ CASES = [
     ("S_blender_grid", "S", 30, dict(grid_width=25, grid_height=16, max_pyramid_levels=5), False),  # odd grid, 5 levels
     ("C3", "C3", 64, {}, False),           # BASELINE configs[2]; keyframe #2 at frame 46
     ("C4", "C4", 12, {}, False),           # BASELINE configs[3]: 1280x720, 5 levels, 16x14 grid (3 000 keypoints per frame)
+    # the algorithm settings of the shipped src/app/EuRoC.yaml and Blender.yaml (BASELINE configs[0]/[1]; their videos are missing)
+    ("C3_euroc_yaml", "C3", 24, dict(grid_width=54, grid_height=48, search_x=60, search_y=6, max_pyramid_levels=6,
+                                     min_pyramid_level_pose_estimation=2), False),
+    ("C3_blender_yaml", "C3", 24, dict(grid_width=75, grid_height=48, search_x=50, search_y=6, max_pyramid_levels=5,
+                                       min_pyramid_level_pose_estimation=2), False),
 ]
 FIELDS = ("kps2d", "kps3d", "score", "kf_state", "kf_cov") + orc.INFO_COLS[:-1]   # colour is rand(): not compared
 

@@ -2,9 +2,9 @@
 
 oracle/_ref/libstereosvo_ref.so is built from the unmodified reference sources (/root/reference/src/lib/*.cpp) against
 oracle/cvshim (oracle/Makefile).  tests/golden/ref_vectors.npz holds its outputs (tests/golden/make_ref_golden.py):
-trajectories, final frames and every keyframe of seven runs — small, fast-motion (three keyframes), fast-motion with IMU
-updates, lens distortion, an odd grid with five pyramid levels, BASELINE configs[2] across keyframe #2 and BASELINE configs[3]
-(1280x720, five levels, 3 000 keypoints).
+trajectories, final frames and every keyframe of nine runs — small, fast-motion (three keyframes), fast-motion with IMU
+updates, lens distortion, an odd grid with five pyramid levels, BASELINE configs[2] across keyframe #2, BASELINE configs[3]
+(1280x720, five levels, 3 000 keypoints) and the algorithm settings of the shipped EuRoC.yaml and Blender.yaml.
 
  * everywhere: the oracle's restatement (oracle/svo_oracle.cpp) must reproduce those vectors BIT FOR BIT — positions,
    3-D points, levels, types, origin keyframe / index, flags, vote counters, scores, depth-filter states, IMU outputs;
