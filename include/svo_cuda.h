@@ -221,7 +221,8 @@ int svo_frame_begin(svo_ctx *ctx, const uint8_t *left, size_t left_stride, const
  * 8, or 16 for frames with more than 1024 keypoints.  Results agree within the pose tolerance (the cross-keypoint sums
  * are grouped differently), each setting is deterministic.  Env SVO_ALIGN_CLUSTER sets the default. */
 int svo_set_align_cluster(svo_ctx *ctx, int ctas);
-/* Width of the line searches of the two Gauss-Newton solvers.  Most trial steps of a running sequence are rejected and halved, and
+/* Latency mode of the tracking kernels.  Width of the line searches of the two Gauss-Newton solvers (and, with it, two warps per
+ * keypoint in the KLT kernel for frames of up to 1024 keypoints).  Most trial steps of a running sequence are rejected and halved, and
  * every trial pose x0 + 2^-j * step is known as soon as the step is: wide = 1 evaluates several of them per round on otherwise
  * idle SMs (refinement: an 8-CTA cluster, CTA c takes trial j + c; alignment: two half-clusters take trials j and j + 1) and
  * replays the reference's accept / halve / stop rule over the costs in order — the same evaluations, decisions and bits as the
